@@ -1,0 +1,34 @@
+"""Copies the small reference DATA fixtures this repo's tests need into tests/golden/ (the GPU box has no
+/root/reference) and records golden values derived from them.  Run once in the build container:
+
+    python tests/golden/make_golden.py
+
+Fixtures (data, not source) come from /root/reference/src/SAIGE/extdata/input:
+  plinkforGRM_1000samples_10kMarkers.{bed,bim,fam,frq}   -- pins decode / allele counts / MAF QC
+  nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.{bed,bim,fam} -- 22-chromosome LOCO set
+  pheno_1000samples.txt_withdosages_withBothTraitTypes.txt -- phenotypes/covariates of the bundled example
+"""
+import os
+import shutil
+import sys
+
+REF = "/root/reference/src/SAIGE/extdata/input"
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = [
+    ("plinkforGRM_1000samples_10kMarkers.bed", "grm10k.bed"),
+    ("plinkforGRM_1000samples_10kMarkers.bim", "grm10k.bim"),
+    ("plinkforGRM_1000samples_10kMarkers.fam", "grm10k.fam"),
+    ("plinkforGRM_1000samples_10kMarkers.frq", "grm10k.frq"),
+    ("nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.bed", "chr22_1000.bed"),
+    ("nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.bim", "chr22_1000.bim"),
+    ("nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.fam", "chr22_1000.fam"),
+    ("pheno_1000samples.txt_withdosages_withBothTraitTypes.txt", "pheno_1000samples.txt"),
+]
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit("reference tree not present; fixtures are already committed")
+    for src, dst in FILES:
+        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+        os.chmod(os.path.join(HERE, dst), 0o644)
+        print("copied", src, "->", dst)
