@@ -1,0 +1,173 @@
+/*
+ * saige_b200.h -- C ABI of libsaige_b200.so, the B200 (sm_100a) CUDA back end for SAIGE step 1.
+ *
+ * Every entry point below is what the reference's FFI layer would bind for the null-GLMM hot path:
+ * the bodies of the [[Rcpp::export]] functions in /root/reference/src/SAIGE/src/SAIGE_fitGLMM_fast.cpp
+ * ("FG.cpp") forward to these (see INTEGRATION.md and rcpp_shim/).  Each declaration cites the reference
+ * function it replaces.
+ *
+ * Conventions
+ *   - all entry points return 0 on success, non-zero on failure; sgb_last_error() gives the message.
+ *     Nothing in the library calls exit() (the reference does, FG.cpp:1947).
+ *   - all floating-point data at the boundary is fp64, column-major, in CALLER-OWNED HOST buffers
+ *     (R numeric vectors/matrices).  The library copies in and out; it never keeps caller pointers.
+ *   - one context == one GPU.  Multi-GPU runs are SPMD, one process (rank) per GPU, like the reference's
+ *     `mpirun -n G Rscript ...` (FG.cpp:1905-1913); markers are sharded over ranks and every GRM product
+ *     ends in one NCCL sum-allreduce (replaces MPI_Allreduce, FG.cpp:1619,1652).
+ *   - the library contains no RNG on the parity path: Rademacher probes and the variance-ratio marker
+ *     index set are drawn by the caller (R's RNG: FG.cpp:3052-3054, 866-868) and passed in.
+ *   - there is no CPU fallback: every compute entry fails if the CUDA device is unavailable.
+ */
+#ifndef SAIGE_B200_H
+#define SAIGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgb_ctx sgb_ctx;
+
+#define SGB_NCCL_ID_BYTES 128
+
+/* Which arithmetic engine computes GRM products.
+ *   SGB_ENGINE_TENSOR : 2-bit genotypes decoded in registers to u8, right-hand sides split into signed 7-bit
+ *                       limbs, exact int32 accumulation on the tensor cores, fp64 recombination (default).
+ *   SGB_ENGINE_F64    : plain fp64 FMA kernels (slow; the on-device cross-check of the tensor engine). */
+enum { SGB_ENGINE_TENSOR = 0, SGB_ENGINE_F64 = 1 };
+
+/* ---- life cycle -------------------------------------------------------------------------------- */
+/* Replaces the file-global `genoClass geno` (FG.cpp:1188) + gpuSymMatMult (gpuSymMatMult.hpp:13-36). */
+int sgb_create(int device, sgb_ctx **out);
+/* Multi-GPU: rank/world + a 128-byte NCCL unique id made by rank 0 with sgb_nccl_unique_id and
+ * distributed by the launcher (replaces MPI_Comm_rank/size, FG.cpp:1905-1906). */
+int sgb_nccl_unique_id(void *id128);
+int sgb_create_dist(int device, int rank, int world, const void *id128, sgb_ctx **out);
+void sgb_destroy(sgb_ctx *h);                       /* closeGenoFile_plink (FG.cpp:1191-1209) + ~gpuSymMatMult */
+const char *sgb_last_error(sgb_ctx *h);             /* h may be NULL: error of the last failed sgb_create* */
+int sgb_set_engine(sgb_ctx *h, int engine);
+int sgb_device_sync(sgb_ctx *h);
+
+/* ---- configuration set through exports before setgeno ------------------------------------------- */
+int sgb_set_min_maf_for_grm(sgb_ctx *h, float minMAF);             /* setminMAFforGRM (FG.cpp:4923) */
+int sgb_set_max_missing_rate_for_grm(sgb_ctx *h, float maxMiss);   /* setmaxMissingRateforGRM (FG.cpp:4928) */
+int sgb_set_min_mac_variance_ratio(sgb_ctx *h, float minMAC, float maxMAC, int isVarRatioGeno); /* FG.cpp:4970 */
+
+/* ---- genotype store ----------------------------------------------------------------------------- */
+/* setgeno -> genoClass::setGenoObj (FG.cpp:2267, 739-1024): reads <bed,bim,fam>, QC (MAF / missing rate in
+ * fp32 with the reference's expression order, FG.cpp:438-493), best-guess imputation (FG.cpp:447,556-558),
+ * variance-ratio hold-out (FG.cpp:496-548; vr_rand_idx = g_randMarkerIndforVR drawn by the caller), re-pack
+ * in phenotype-sample order (FG.cpp:551-576), then builds the device layout.
+ *   subSampleInGeno[n_sub] : 1-based .fam row of each phenotyped sample
+ *   indicator[n_fam]       : 1 if the .fam sample has a phenotype */
+int sgb_setgeno(sgb_ctx *h, const char *bedfile, const char *bimfile, const char *famfile,
+                const int32_t *subSampleInGeno, int64_t n_sub, const uint8_t *indicator, int64_t n_fam,
+                int isDiagofKinSetAsOne, const int32_t *vr_rand_idx, int64_t n_vr_idx);
+/* Same, from a host-resident .bed body (no magic bytes), n_fam samples x n_bim markers, SNP-major. */
+int sgb_setgeno_mem(sgb_ctx *h, const uint8_t *bed_body, int64_t n_fam, int64_t n_bim,
+                    const int32_t *subSampleInGeno, int64_t n_sub, const uint8_t *indicator,
+                    int isDiagofKinSetAsOne, const int32_t *vr_rand_idx, int64_t n_vr_idx);
+/* Bench/test workload generator: counter-based synthetic genotypes written straight into the
+ * device layout; t0/t1 are per-marker uint32 thresholds.  Bit-identical to oracle/saige_oracle.c:orc_synth_bed. */
+int sgb_setgeno_synth(sgb_ctx *h, int64_t n_samples, int64_t n_markers, uint64_t seed,
+                      const uint32_t *t0, const uint32_t *t1);
+
+int64_t sgb_get_total_marker(sgb_ctx *h);           /* gettotalMarker: .bim lines (FG.cpp:1213) */
+int64_t sgb_get_num_qc_markers(sgb_ctx *h);         /* getMsub_MAFge_minMAFtoConstructGRM (FG.cpp:1271) */
+int64_t sgb_get_num_local_markers(sgb_ctx *h);      /* this rank's shard (gpuDistributeSNPs n_cols, FG.cpp:1913) */
+int64_t sgb_get_nnomissing(sgb_ctx *h);             /* getNnomissingOut (FG.cpp:1266) */
+int64_t sgb_get_num_vr_markers(sgb_ctx *h);
+int sgb_get_allele_freq_vec(sgb_ctx *h, double *out);        /* getAlleleFreqVec, float values widened (FG.cpp:1219) */
+int sgb_get_mac_vec(sgb_ctx *h, int32_t *out);               /* getMACVec (FG.cpp:1224) */
+int sgb_get_allele_count_vec(sgb_ctx *h, int32_t *out);      /* integer A1 count after imputation (bit-exact gate) */
+int sgb_get_mac_vec_for_var_ratio(sgb_ctx *h, int32_t *out); /* getMACVec_forVarRatio (FG.cpp:1230) */
+int sgb_get_index_vec_for_var_ratio(sgb_ctx *h, int32_t *out);/* getIndexVec_forVarRatio (FG.cpp:1235) */
+int sgb_get_is_var_ratio_geno(sgb_ctx *h);                   /* getIsVarRatioGeno (FG.cpp:1240) */
+int sgb_get_qcd_marker_index(sgb_ctx *h, uint8_t *out);      /* getQCdMarkerIndex, n_bim flags (FG.cpp:1249) */
+int sgb_get_one_snp_geno(sgb_ctx *h, int64_t snp_idx, int32_t *out);             /* Get_OneSNP_Geno (FG.cpp:2281) */
+int sgb_get_one_snp_geno_for_var_ratio(sgb_ctx *h, int64_t snp_idx, int32_t *out); /* FG.cpp:2291 */
+int sgb_get_one_snp_stdgeno(sgb_ctx *h, int64_t snp_idx, double *out);           /* Get_OneSNP_StdGeno (FG.cpp:2302) */
+
+/* ---- LOCO bookkeeping --------------------------------------------------------------------------- */
+int sgb_set_start_end_index_vec(sgb_ctx *h, const int32_t *start, const int32_t *end, int n); /* FG.cpp:3084 */
+int sgb_set_start_end_index(sgb_ctx *h, int start, int end, int chromIndex);                  /* FG.cpp:3067 */
+int sgb_set_diag_of_stdgeno_loco(sgb_ctx *h);                                                 /* FG.cpp:4934 */
+
+/* ---- GRM products ------------------------------------------------------------------------------- */
+int sgb_get_diag_of_kin(sgb_ctx *h, double *out);                       /* get_DiagofKin (FG.cpp:4358) */
+/* getCrossprodMatAndKin[_LOCO] (FG.cpp:1953,1989): Y[N x k] = K.B, K = (1/M) sum_m z_m z_m^T; k >= 1 columns. */
+int sgb_get_crossprod_mat_and_kin(sgb_ctx *h, const double *B, int k, double *Y);
+int sgb_get_crossprod_mat_and_kin_loco(sgb_ctx *h, const double *B, int k, double *Y);
+int sgb_get_diag_of_sigma(sgb_ctx *h, const double *w, const double *tau, int loco, double *out); /* FG.cpp:2322,2368 */
+int sgb_get_crossprod(sgb_ctx *h, const double *B, int k, const double *w, const double *tau, int loco,
+                      double *Y);                                       /* getCrossprod[_LOCO] (FG.cpp:2397,2430) */
+
+/* ---- PCG ---------------------------------------------------------------------------------------- */
+/* getPCG1ofSigmaAndVector[_LOCO] (FG.cpp:2593,2943) for k right-hand sides at once.  Each column follows
+ * exactly the sequential recurrence and stops on its own ||r||^2 <= tolPCG (absolute, FG.cpp:2696);
+ * iters_out[k] (may be NULL) receives the per-column iteration counts the reference prints (FG.cpp:2798). */
+int sgb_get_pcg1_of_sigma_and_vector(sgb_ctx *h, const double *w, const double *tau, const double *B, int k,
+                                     int maxiterPCG, double tolPCG, int loco, double *X, int32_t *iters_out);
+
+/* ---- AI-REML ------------------------------------------------------------------------------------ */
+/* Probe source: fill out[N x count] (column-major) with the next `count` Rademacher vectors of the caller's
+ * RNG stream, i.e. 2*rbinom(N,1,0.5)-1 (FG.cpp:3134-3137).  Return 0 on success. */
+typedef int (*sgb_probe_fn)(void *user, int64_t n, int count, double *out);
+
+/* getCoefficients[_LOCO] (FG.cpp:3167,3203): Sigma_iY[N], Sigma_iX[N x p], cov[p x p], alpha[p], eta[N]. */
+int sgb_get_coefficients(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, const double *tau,
+                         int maxiterPCG, double tolPCG, int loco,
+                         double *Sigma_iY, double *Sigma_iX, double *cov, double *alpha, double *eta);
+/* getAIScore (FG.cpp:3279): out4 = {YPAPY, Trace, AI, nrun actually used}; PY[N]. */
+int sgb_get_ai_score(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, const double *tau,
+                     const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun,
+                     int maxiterPCG, double tolPCG, double traceCVcutoff, sgb_probe_fn probes, void *user,
+                     double *out4, double *PY);
+/* getAIScore_q (FG.cpp:3479): out8 = {YPAPY, YPA0PY, Trace0, Trace1, AI00, AI01, AI11, nrun used}. */
+int sgb_get_ai_score_q(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, const double *tau,
+                       const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun,
+                       int maxiterPCG, double tolPCG, double traceCVcutoff, sgb_probe_fn probes, void *user,
+                       double *out8, double *PY);
+/* fitglmmaiRPCG / fitglmmaiRPCG_q (FG.cpp:3302,3610): tau_inout[2] updated in place. */
+int sgb_fit_glmmai_rpcg(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, double *tau_inout,
+                        const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun,
+                        int maxiterPCG, double tolPCG, double tol, double traceCVcutoff,
+                        sgb_probe_fn probes, void *user);
+int sgb_fit_glmmai_rpcg_q(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, double *tau_inout,
+                          const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun,
+                          int maxiterPCG, double tolPCG, double tol, double traceCVcutoff,
+                          sgb_probe_fn probes, void *user);
+/* getSigma_X[_LOCO] / getSigma_G[_LOCO] (FG.cpp:3347-3405): k columns solved as one batch. */
+int sgb_get_sigma_x(sgb_ctx *h, const double *w, const double *tau, const double *X, int p,
+                    int maxiterPCG, double tolPCG, int loco, double *Sigma_iX);
+int sgb_get_sigma_g(sgb_ctx *h, const double *w, const double *tau, const double *Gmat, int k,
+                    int maxiterPCG, double tolPCG, int loco, double *Sigma_iG);
+double sgb_cal_cv(const double *x, int n);                                   /* calCV (FG.cpp:3104) */
+double sgb_inner_product(const double *x, const double *y, int64_t n);      /* innerProduct */
+
+/* ---- device-resident benchmark hooks (bench.py `value` leg: inputs already in HBM) ---------------- */
+/* Runs `reps` k-column GRM products on device-resident synthetic right-hand sides, timing with CUDA events
+ * on the library's stream; ms_out[reps] per-product times, and ms_kernel_out[2] the summed time of the two
+ * genotype sweeps of the LAST product.  Result left in an internal buffer (sgb_bench_fetch_result). */
+int sgb_bench_crossprod_device(sgb_ctx *h, int k, int reps, uint64_t seed, float *ms_out, float *ms_kernel_out);
+int sgb_bench_fetch_result(sgb_ctx *h, int k, double *Y, double *B);
+
+/* ---- counters (SURVEY.md section 5 "metrics") ----------------------------------------------------- */
+typedef struct {
+    int64_t n_crossprod_calls;      /* multi-vector GRM products */
+    int64_t n_crossprod_columns;    /* sum of k over them */
+    int64_t n_pcg_solves;           /* columns solved */
+    int64_t n_pcg_iterations;       /* sum over columns */
+    int64_t n_kernel_launches;      /* kernels of this library launched */
+    int64_t n_allreduce;            /* NCCL allreduces issued */
+    int64_t bytes_h2d, bytes_d2h;
+} sgb_counters;
+int sgb_get_counters(sgb_ctx *h, sgb_counters *out);
+int sgb_reset_counters(sgb_ctx *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAIGE_B200_H */

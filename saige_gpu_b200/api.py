@@ -1,0 +1,360 @@
+"""Host-side mirror of the reference's Rcpp export surface for the step-1 hot path.
+
+Same names, argument order and meaning as the `[[Rcpp::export]]` functions of
+/root/reference/src/SAIGE/src/SAIGE_fitGLMM_fast.cpp that src/SAIGE/R/SAIGE_fitGLMM_fast.R calls (the list is in
+SURVEY.md 8b), as methods of one object that owns the C-ABI context (the reference keeps a file-global `geno`).
+Every call goes through libsaige_b200.so; nothing here computes on the CPU.
+
+Differences from the reference, all forced by the boundary contract:
+  * errors raise SaigeB200Error instead of printing and continuing (FG.cpp:762-765) or exit() (FG.cpp:1947);
+  * random draws come from the caller: `vr_rand_idx` for setgeno (arma::randi, FG.cpp:866-868) and a `draw(n)`
+    callable for the trace estimator (R's rbinom, FG.cpp:3134-3137);
+  * vector arguments may also be N x k matrices where batching is possible (getCrossprodMatAndKin,
+    getPCG1ofSigmaAndVector, getSigma_G).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SaigeB200Error, PROBE_FN
+
+
+def _f64(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SaigeB200:
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None, engine="tensor"):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        if world > 1:
+            if nccl_id is None or len(nccl_id) != _lib.NCCL_ID_BYTES:
+                raise SaigeB200Error("world > 1 needs the %d-byte NCCL id made by nccl_unique_id()" % _lib.NCCL_ID_BYTES)
+            buf = (C.c_char * _lib.NCCL_ID_BYTES).from_buffer_copy(bytes(nccl_id))
+            rc = self._L.sgb_create_dist(device, rank, world, C.cast(buf, C.c_void_p), C.byref(h))
+        else:
+            rc = self._L.sgb_create(device, C.byref(h))
+        if rc:
+            raise SaigeB200Error(self._L.sgb_last_error(None).decode())
+        self._h = h
+        self.rank, self.world = rank, world
+        self._keep = []
+        if engine != "tensor":
+            self.set_engine(engine)
+
+    @staticmethod
+    def nccl_unique_id():
+        L = _lib.lib()
+        buf = (C.c_char * _lib.NCCL_ID_BYTES)()
+        if L.sgb_nccl_unique_id(C.cast(buf, C.c_void_p)):
+            raise SaigeB200Error(L.sgb_last_error(None).decode())
+        return bytes(buf)
+
+    def _ck(self, rc):
+        if rc:
+            raise SaigeB200Error(self._L.sgb_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sgb_destroy(self._h)
+            self._h = None
+
+    closeGenoFile_plink = close          # FG.cpp:1191
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_engine(self, engine):
+        self._ck(self._L.sgb_set_engine(self._h, {"tensor": 0, "f64": 1}[engine]))
+
+    def sync(self):
+        self._ck(self._L.sgb_device_sync(self._h))
+
+    # ---- configuration exports ----
+    def setminMAFforGRM(self, minMAFforGRM):
+        self._ck(self._L.sgb_set_min_maf_for_grm(self._h, float(minMAFforGRM)))
+
+    def setmaxMissingRateforGRM(self, maxMissingforGRM):
+        self._ck(self._L.sgb_set_max_missing_rate_for_grm(self._h, float(maxMissingforGRM)))
+
+    def setminMAC_VarianceRatio(self, t_minMACVarRatio, t_maxMACVarRatio, t_isVarianceRatioinGeno):
+        self._ck(self._L.sgb_set_min_mac_variance_ratio(self._h, float(t_minMACVarRatio), float(t_maxMACVarRatio),
+                                                        int(bool(t_isVarianceRatioinGeno))))
+
+    # ---- genotype store ----
+    def setgeno(self, bedfile, bimfile, famfile, subSampleInGeno, indicatorGenoSamplesWithPheno, memoryChunk=2.0,
+                isDiagofKinSetAsOne=False, vr_rand_idx=None):
+        sub = np.ascontiguousarray(subSampleInGeno, dtype=np.int32)
+        ind = np.ascontiguousarray(indicatorGenoSamplesWithPheno, dtype=np.uint8)
+        vr = np.ascontiguousarray([] if vr_rand_idx is None else vr_rand_idx, dtype=np.int32)
+        self._ck(self._L.sgb_setgeno(self._h, bedfile.encode(), bimfile.encode(), famfile.encode(), _p(sub), len(sub),
+                                     _p(ind), len(ind), int(bool(isDiagofKinSetAsOne)), _p(vr), len(vr)))
+        self._dims()
+
+    def setgeno_mem(self, bed_body, n_fam, n_bim, subSampleInGeno, indicatorGenoSamplesWithPheno,
+                    isDiagofKinSetAsOne=False, vr_rand_idx=None):
+        bed = np.ascontiguousarray(bed_body, dtype=np.uint8)
+        if bed.size < ((n_fam + 3) // 4) * n_bim:
+            raise SaigeB200Error("bed body shorter than n_bim * ceil(n_fam/4) bytes")
+        sub = np.ascontiguousarray(subSampleInGeno, dtype=np.int32)
+        ind = np.ascontiguousarray(indicatorGenoSamplesWithPheno, dtype=np.uint8)
+        if len(ind) != n_fam:
+            raise SaigeB200Error("indicator length != n_fam")
+        vr = np.ascontiguousarray([] if vr_rand_idx is None else vr_rand_idx, dtype=np.int32)
+        self._ck(self._L.sgb_setgeno_mem(self._h, _p(bed), n_fam, n_bim, _p(sub), len(sub), _p(ind),
+                                         int(bool(isDiagofKinSetAsOne)), _p(vr), len(vr)))
+        self._dims()
+
+    def setgeno_synth(self, n_samples, n_markers, seed, t0, t1):
+        t0 = np.ascontiguousarray(t0, dtype=np.uint32)
+        t1 = np.ascontiguousarray(t1, dtype=np.uint32)
+        assert len(t0) == n_markers and len(t1) == n_markers
+        self._ck(self._L.sgb_setgeno_synth(self._h, n_samples, n_markers, seed, _p(t0), _p(t1)))
+        self._dims()
+
+    def _dims(self):
+        L, h = self._L, self._h
+        self.N = L.sgb_get_nnomissing(h)
+        self.M = L.sgb_get_num_qc_markers(h)
+        self.M0 = L.sgb_get_total_marker(h)
+        self.Mloc = L.sgb_get_num_local_markers(h)
+        self.Mvr = L.sgb_get_num_vr_markers(h)
+
+    def gettotalMarker(self):
+        return self._L.sgb_get_total_marker(self._h)
+
+    def getNnomissingOut(self):
+        return self._L.sgb_get_nnomissing(self._h)
+
+    def getMsub_MAFge_minMAFtoConstructGRM(self):
+        return self._L.sgb_get_num_qc_markers(self._h)
+
+    def _ivec(self, fn, n, dtype=np.int32):
+        out = np.zeros(max(n, 1), dtype=dtype)
+        self._ck(fn(self._h, _p(out)))
+        return out[:n]
+
+    def getAlleleFreqVec(self):
+        return self._ivec(self._L.sgb_get_allele_freq_vec, self.M, np.float64)
+
+    def getMACVec(self):
+        return self._ivec(self._L.sgb_get_mac_vec, self.M)
+
+    def getAlleleCountVec(self):
+        return self._ivec(self._L.sgb_get_allele_count_vec, self.M)
+
+    def getMACVec_forVarRatio(self):
+        return self._ivec(self._L.sgb_get_mac_vec_for_var_ratio, self.Mvr)
+
+    def getIndexVec_forVarRatio(self):
+        return self._ivec(self._L.sgb_get_index_vec_for_var_ratio, self.Mvr)
+
+    def getIsVarRatioGeno(self):
+        return bool(self._L.sgb_get_is_var_ratio_geno(self._h))
+
+    def getQCdMarkerIndex(self):
+        return self._ivec(self._L.sgb_get_qcd_marker_index, self.M0, np.uint8).astype(bool)
+
+    def Get_OneSNP_Geno(self, SNPIdx):
+        out = np.zeros(self.N, dtype=np.int32)
+        self._ck(self._L.sgb_get_one_snp_geno(self._h, int(SNPIdx), _p(out)))
+        return out
+
+    def Get_OneSNP_Geno_forVarRatio(self, SNPIdx):
+        out = np.zeros(self.N, dtype=np.int32)
+        self._ck(self._L.sgb_get_one_snp_geno_for_var_ratio(self._h, int(SNPIdx), _p(out)))
+        return out
+
+    def Get_OneSNP_StdGeno(self, SNPIdx):
+        out = np.zeros(self.N, dtype=np.float64)
+        self._ck(self._L.sgb_get_one_snp_stdgeno(self._h, int(SNPIdx), _p(out)))
+        return out
+
+    # ---- LOCO ----
+    def setStartEndIndexVec(self, startIndex_vec, endIndex_vec):
+        s = np.ascontiguousarray(startIndex_vec, dtype=np.int32)
+        e = np.ascontiguousarray(endIndex_vec, dtype=np.int32)
+        self._ck(self._L.sgb_set_start_end_index_vec(self._h, _p(s), _p(e), len(s)))
+
+    def setStartEndIndex(self, startIndex, endIndex, chromIndex):
+        self._ck(self._L.sgb_set_start_end_index(self._h, int(startIndex), int(endIndex), int(chromIndex)))
+
+    def set_Diagof_StdGeno_LOCO(self):
+        self._ck(self._L.sgb_set_diag_of_stdgeno_loco(self._h))
+
+    # ---- GRM products ----
+    def get_DiagofKin(self):
+        out = np.zeros(self.N)
+        self._ck(self._L.sgb_get_diag_of_kin(self._h, _p(out)))
+        return out
+
+    def _mat(self, b):
+        b = np.asarray(b, dtype=np.float64)
+        one = b.ndim == 1
+        bm = _f64(b.reshape(self.N, -1))
+        return bm, one
+
+    def getCrossprodMatAndKin(self, bVec):
+        b, one = self._mat(bVec)
+        y = np.zeros_like(b, order="F")
+        self._ck(self._L.sgb_get_crossprod_mat_and_kin(self._h, _p(b), b.shape[1], _p(y)))
+        return y[:, 0].copy() if one else y
+
+    def getCrossprodMatAndKin_LOCO(self, bVec):
+        b, one = self._mat(bVec)
+        y = np.zeros_like(b, order="F")
+        self._ck(self._L.sgb_get_crossprod_mat_and_kin_loco(self._h, _p(b), b.shape[1], _p(y)))
+        return y[:, 0].copy() if one else y
+
+    def getDiagOfSigma(self, wVec, tauVec, loco=False):
+        w, tau = _f64(wVec), _f64(tauVec)
+        out = np.zeros(self.N)
+        self._ck(self._L.sgb_get_diag_of_sigma(self._h, _p(w), _p(tau), int(loco), _p(out)))
+        return out
+
+    def getDiagOfSigma_LOCO(self, wVec, tauVec):
+        return self.getDiagOfSigma(wVec, tauVec, True)
+
+    def getCrossprod(self, bVec, wVec, tauVec, loco=False):
+        b, one = self._mat(bVec)
+        w, tau = _f64(wVec), _f64(tauVec)
+        y = np.zeros_like(b, order="F")
+        self._ck(self._L.sgb_get_crossprod(self._h, _p(b), b.shape[1], _p(w), _p(tau), int(loco), _p(y)))
+        return y[:, 0].copy() if one else y
+
+    def getCrossprod_LOCO(self, bVec, wVec, tauVec):
+        return self.getCrossprod(bVec, wVec, tauVec, True)
+
+    # ---- PCG ----
+    def getPCG1ofSigmaAndVector(self, wVec, tauVec, bVec, maxiterPCG, tolPCG, loco=False, return_iter=False):
+        b, one = self._mat(bVec)
+        w, tau = _f64(wVec), _f64(tauVec)
+        x = np.zeros_like(b, order="F")
+        it = np.zeros(b.shape[1], dtype=np.int32)
+        self._ck(self._L.sgb_get_pcg1_of_sigma_and_vector(self._h, _p(w), _p(tau), _p(b), b.shape[1], int(maxiterPCG),
+                                                          float(tolPCG), int(loco), _p(x), _p(it)))
+        xo = x[:, 0].copy() if one else x
+        return (xo, (int(it[0]) if one else it)) if return_iter else xo
+
+    def getPCG1ofSigmaAndVector_LOCO(self, wVec, tauVec, bVec, maxiterPCG, tolPCG):
+        return self.getPCG1ofSigmaAndVector(wVec, tauVec, bVec, maxiterPCG, tolPCG, True)
+
+    # ---- AI-REML ----
+    def _probe_cb(self, draw):
+        N = self.N
+
+        def cb(user, n, count, out):
+            try:
+                U = np.asarray(draw(int(count)), dtype=np.float64).reshape(N, -1)
+                if U.shape[1] != count:
+                    return 1
+                dst = np.ctypeslib.as_array(out, shape=(int(n) * int(count),))
+                dst[:] = np.asfortranarray(U).ravel(order="F")
+                return 0
+            except Exception:      # never let an exception cross the C boundary
+                return 1
+        return PROBE_FN(cb)
+
+    def getCoefficients(self, Yvec, Xmat, wVec, tauVec, maxiterPCG, tolPCG, loco=False):
+        Y, X, w, tau = _f64(Yvec), _f64(np.asarray(Xmat).reshape(self.N, -1)), _f64(wVec), _f64(tauVec)
+        p = X.shape[1]
+        SiY, SiX = np.zeros(self.N), np.zeros((self.N, p), order="F")
+        cov, alpha, eta = np.zeros((p, p), order="F"), np.zeros(p), np.zeros(self.N)
+        self._ck(self._L.sgb_get_coefficients(self._h, _p(Y), _p(X), p, _p(w), _p(tau), int(maxiterPCG), float(tolPCG),
+                                              int(loco), _p(SiY), _p(SiX), _p(cov), _p(alpha), _p(eta)))
+        return dict(Sigma_iY=SiY, Sigma_iX=SiX, cov=cov, alpha=alpha, eta=eta)
+
+    def getCoefficients_LOCO(self, Yvec, Xmat, wVec, tauVec, maxiterPCG, tolPCG):
+        return self.getCoefficients(Yvec, Xmat, wVec, tauVec, maxiterPCG, tolPCG, True)
+
+    def _ai_args(self, Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov):
+        X = _f64(np.asarray(Xmat).reshape(self.N, -1))
+        p = X.shape[1]
+        return (_f64(Yvec), X, p, _f64(wVec), _f64(tauVec).copy(), _f64(Sigma_iY),
+                _f64(np.asarray(Sigma_iX).reshape(self.N, p)), _f64(np.asarray(cov).reshape(p, p)))
+
+    def getAIScore(self, Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff,
+                   draw):
+        Y, X, p, w, tau, SiY, SiX, cv = self._ai_args(Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov)
+        out4, PY = np.zeros(4), np.zeros(self.N)
+        cb = self._probe_cb(draw)
+        self._ck(self._L.sgb_get_ai_score(self._h, _p(Y), _p(X), p, _p(w), _p(tau), _p(SiY), _p(SiX), _p(cv), int(nrun),
+                                          int(maxiterPCG), float(tolPCG), float(traceCVcutoff), cb, None, _p(out4), _p(PY)))
+        return dict(YPAPY=out4[0], Trace=out4[1], PY=PY, AI=out4[2], nrun_used=int(out4[3]))
+
+    def getAIScore_q(self, Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff,
+                     draw):
+        Y, X, p, w, tau, SiY, SiX, cv = self._ai_args(Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov)
+        o, PY = np.zeros(8), np.zeros(self.N)
+        cb = self._probe_cb(draw)
+        self._ck(self._L.sgb_get_ai_score_q(self._h, _p(Y), _p(X), p, _p(w), _p(tau), _p(SiY), _p(SiX), _p(cv), int(nrun),
+                                            int(maxiterPCG), float(tolPCG), float(traceCVcutoff), cb, None, _p(o), _p(PY)))
+        return dict(YPAPY=o[0], YPA0PY=o[1], Trace=np.array([o[2], o[3]]), PY=PY,
+                    AI=np.array([[o[4], o[5]], [o[5], o[6]]]), nrun_used=int(o[7]))
+
+    def _fit(self, fn, Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, tol, traceCVcutoff,
+             draw):
+        Y, X, p, w, tau, SiY, SiX, cv = self._ai_args(Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov)
+        cb = self._probe_cb(draw)
+        self._ck(fn(self._h, _p(Y), _p(X), p, _p(w), _p(tau), _p(SiY), _p(SiX), _p(cv), int(nrun), int(maxiterPCG),
+                    float(tolPCG), float(tol), float(traceCVcutoff), cb, None))
+        return dict(tau=tau)
+
+    def fitglmmaiRPCG(self, *a, **kw):
+        return self._fit(self._L.sgb_fit_glmmai_rpcg, *a, **kw)
+
+    def fitglmmaiRPCG_q(self, *a, **kw):
+        return self._fit(self._L.sgb_fit_glmmai_rpcg_q, *a, **kw)
+
+    def getSigma_X(self, wVec, tauVec, Xmat, maxiterPCG, tolPCG, loco=False):
+        X = _f64(np.asarray(Xmat).reshape(self.N, -1))
+        w, tau = _f64(wVec), _f64(tauVec)
+        out = np.zeros_like(X, order="F")
+        self._ck(self._L.sgb_get_sigma_x(self._h, _p(w), _p(tau), _p(X), X.shape[1], int(maxiterPCG), float(tolPCG),
+                                         int(loco), _p(out)))
+        return out
+
+    def getSigma_G(self, wVec, tauVec, Gvec, maxiterPCG, tolPCG, loco=False):
+        G, one = self._mat(Gvec)
+        w, tau = _f64(wVec), _f64(tauVec)
+        out = np.zeros_like(G, order="F")
+        self._ck(self._L.sgb_get_sigma_g(self._h, _p(w), _p(tau), _p(G), G.shape[1], int(maxiterPCG), float(tolPCG),
+                                         int(loco), _p(out)))
+        return out[:, 0].copy() if one else out
+
+    def calCV(self, xVec):
+        x = _f64(xVec)
+        return self._L.sgb_cal_cv(_p(x), len(x))
+
+    def innerProduct(self, x, y):
+        x, y = _f64(x), _f64(y)
+        return self._L.sgb_inner_product(_p(x), _p(y), len(x))
+
+    # ---- bench hooks / counters ----
+    def bench_crossprod_device(self, k, reps, seed=1):
+        ms = np.zeros(reps, dtype=np.float32)
+        mk = np.zeros(2, dtype=np.float32)
+        self._ck(self._L.sgb_bench_crossprod_device(self._h, int(k), int(reps), int(seed), _p(ms), _p(mk)))
+        return ms, mk
+
+    def bench_fetch_result(self, k):
+        Y = np.zeros((self.N, k), order="F")
+        B = np.zeros((self.N, k), order="F")
+        self._ck(self._L.sgb_bench_fetch_result(self._h, int(k), _p(Y), _p(B)))
+        return Y, B
+
+    def counters(self):
+        c = _lib.Counters()
+        self._ck(self._L.sgb_get_counters(self._h, C.byref(c)))
+        return {n: getattr(c, n) for n, _ in c._fields_}
+
+    def reset_counters(self):
+        self._ck(self._L.sgb_reset_counters(self._h))

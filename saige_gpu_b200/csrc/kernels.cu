@@ -1,0 +1,987 @@
+// CUDA kernels of libsaige_b200.so (sm_100a).  See DESIGN.md for the data layout and the roofline of each.
+//
+// Hot kernel: pk2_gemm_kernel -- "packed 2-bit matrix x int8 limb matrix -> int32", used for BOTH genotype
+// sweeps of a GRM product (rows = markers over the marker-major copy, rows = samples over the sample-major
+// copy), for the GRM diagonal and for the LOCO per-chromosome diagonals.  Replaces, on the GPU, the work of
+// Get_OneSNP_StdGeno + dot + axpy (FG.cpp:582-662, 1478-1495) and of the reference's dense-fp32
+// cublasSgemv pair (gpuSymMatMult.cu:267,273).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "sgb_internal.h"
+
+#define LAUNCH_CHECK(h)                                                                               \
+    do {                                                                                              \
+        (h)->cnt.n_kernel_launches++;                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                                         \
+        if (e__ != cudaSuccess) return sgb_fail(h, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, \
+                                                cudaGetErrorString(e__));                             \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int k_grid_blocks(sgb_ctx *h, int64_t n)
+{
+    int64_t b = cdiv(n, 256 * 4);
+    if (b > SGB_PART_BLOCKS) b = SGB_PART_BLOCKS;
+    if (b < 1) b = 1;
+    (void)h;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over a 256-thread block; result valid in every thread.
+__device__ __forceinline__ double block_sum_256(double v, double *sm /* >= 8 doubles */)
+{
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += sm[i];
+    return t;
+}
+
+// fixed-order sum of nblk partials (every thread of the block computes the same value)
+__device__ __forceinline__ double sum_partials(const double *part, int nblk)
+{
+    double t = 0.0;
+    for (int i = 0; i < nblk; i++) t += part[i];
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ingest: allele / missing counts over raw PLINK rows (Get_OneSNP_Geno_atBeginning, FG.cpp:338-435)
+// ---------------------------------------------------------------------------------------------------
+__global__ void count_markers_kernel(const uint8_t *__restrict__ bed, int64_t B0, int64_t nmark,
+                                     const uint8_t *__restrict__ indmask, int32_t *__restrict__ ac,
+                                     int32_t *__restrict__ nmiss)
+{
+    int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= nmark) return;
+    int lane = threadIdx.x & 31;
+    const uint8_t *row = bed + m * B0;
+    int a = 0, ms = 0;
+    for (int64_t b = lane; b < B0; b += 32) {
+        uint32_t x = row[b], im = indmask[b];
+        uint32_t lo = x & 0x55u, hi = (x >> 1) & 0x55u;
+        uint32_t miss = lo & ~hi & im;              // code 01 : missing        (b=1,a=0 -> 3, FG.cpp:346)
+        uint32_t c2 = ~lo & ~hi & 0x55u & im;       // code 00 : 2 copies of A1 (FG.cpp:348)
+        uint32_t c1 = ~lo & hi & im;                // code 10 : 1 copy         (FG.cpp:350)
+        a += 2 * __popc(c2) + __popc(c1);
+        ms += __popc(miss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        ms += __shfl_xor_sync(0xffffffffu, ms, o);
+    }
+    if (lane == 0) { ac[m] = a; nmiss[m] = ms; }
+}
+
+int k_count_markers(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, int64_t nmark, const uint8_t *d_indmask,
+                    int32_t *d_ac, int32_t *d_nmiss)
+{
+    if (nmark <= 0) return 0;
+    count_markers_kernel<<<(unsigned)cdiv(nmark, 8), 256, 0, h->stream>>>(d_bed, B0, nmark, d_indmask, d_ac, d_nmiss);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// re-pack kept markers in phenotype-sample order with imputation, into the device coding (FG.cpp:551-576)
+__global__ void repack_kernel(const uint8_t *__restrict__ bed, int64_t B0, const int32_t *__restrict__ src_rows,
+                              const int32_t *__restrict__ fill, const int32_t *__restrict__ sub_idx, int identity,
+                              int64_t N, uint8_t *__restrict__ out, int64_t out_stride)
+{
+    int64_t r = blockIdx.y;
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t B = (N + 3) >> 2;
+    if (b >= B) return;
+    const uint8_t *row = bed + (int64_t)src_rows[r] * B0;
+    int fl = fill[r];
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int64_t k = 4 * b + j;
+        if (k < N) {
+            int64_t src = identity ? k : (int64_t)sub_idx[k] - 1;
+            int code = (row[src >> 2] >> ((src & 3) << 1)) & 3;
+            int g = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fl));
+            o |= (uint32_t)g << (2 * j);
+        }
+    }
+    out[r * out_stride + b] = (uint8_t)o;
+}
+
+int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_rows, const int32_t *d_fill,
+             int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_stride)
+{
+    if (nrows <= 0) return 0;
+    int64_t B = (N + 3) / 4;
+    for (int64_t r0 = 0; r0 < nrows; r0 += 65535) {
+        int64_t nr = nrows - r0 < 65535 ? nrows - r0 : 65535;
+        dim3 grid((unsigned)cdiv(B, 256), (unsigned)nr);
+        repack_kernel<<<grid, 256, 0, h->stream>>>(d_bed, B0, d_src_rows + r0, d_fill + r0, d_sub_idx, identity, N,
+                                                    d_out + r0 * out_stride, out_stride);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+// marker-major -> sample-major copy.  CTA tile: 128 markers x 256 samples.
+__global__ void __launch_bounds__(256) transpose_kernel(const uint8_t *__restrict__ G, int64_t sG, int64_t Mloc,
+                                                        uint8_t *__restrict__ Gt, int64_t sT, int64_t N)
+{
+    __shared__ uint8_t tile[128][64 + 4];
+    int64_t m0 = (int64_t)blockIdx.y * 128, b0 = (int64_t)blockIdx.x * 64;   // b0: byte offset in a marker row
+    for (int idx = threadIdx.x; idx < 128 * 16; idx += 256) {
+        int r = idx >> 4, q = idx & 15;
+        uint32_t v = 0;
+        if (m0 + r < Mloc && b0 + 4 * q < sG) v = *reinterpret_cast<const uint32_t *>(G + (m0 + r) * sG + b0 + 4 * q);
+        *reinterpret_cast<uint32_t *>(&tile[r][4 * q]) = v;
+    }
+    __syncthreads();
+    int64_t i = b0 * 4 + threadIdx.x;      // sample
+    if (i >= N) return;
+    int byte = threadIdx.x >> 2, sh = (threadIdx.x & 3) << 1;
+    uint32_t o[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc |= (uint32_t)((tile[w * 16 + j][byte] >> sh) & 3) << (2 * j);
+        o[w] = acc;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(Gt + i * sT + (m0 >> 2));
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+int k_transpose(sgb_ctx *h)
+{
+    if (h->Mloc <= 0) return 0;
+    dim3 grid((unsigned)cdiv(h->sG, 64), (unsigned)cdiv(h->Mloc, 128));
+    transpose_kernel<<<grid, 256, 0, h->stream>>>(h->dG, h->sG, h->Mloc, h->dGt, h->sT, h->N);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// synthetic genotypes (same integer hash as oracle/saige_oracle.c:mix32)
+__device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t m, uint64_t i, uint64_t salt)
+{
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (m + 1) + 0xBF58476D1CE4E5B9ull * (i + 1) + 0x94D049BB133111EBull * salt;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+// mode 0: count allele copies of raw marker (blockIdx.y + y0) into ac[];  mode 1: write local row r = blockIdx.y + y0
+// of the marker-major store for raw marker rows[r].
+__global__ void synth_kernel(int mode, int64_t y0, uint64_t seed, const uint32_t *__restrict__ t0,
+                             const uint32_t *__restrict__ t1, const int64_t *__restrict__ rows, int64_t N,
+                             int32_t *__restrict__ ac, uint8_t *__restrict__ G, int64_t sG)
+{
+    int64_t r = blockIdx.y + y0;
+    int64_t m = mode ? rows[r] : r;
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a0 = t0[m], a1 = t1[m];
+    uint32_t o = 0;
+    int cnt = 0;
+    if (b < ((N + 3) >> 2)) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t i = 4 * b + j;
+            if (i < N) {
+                uint32_t u = mix32(seed, (uint64_t)m, (uint64_t)i, 0);
+                int g = (u >= a0) + (u >= a1);
+                o |= (uint32_t)g << (2 * j);
+                cnt += g;
+            }
+        }
+        if (mode) G[r * sG + b] = (uint8_t)o;
+    }
+    if (!mode) {
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, of);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ac[m], cnt);
+    }
+}
+
+int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, int32_t *d_ac)
+{
+    // mode selected by d_ac: non-null => count pass over all M0 raw markers; null => fill local rows (h->ws holds rows)
+    int64_t B = (h->N + 3) / 4;
+    int64_t total = d_ac ? h->M0 : h->Mloc;
+    for (int64_t y0 = 0; y0 < total; y0 += 65535) {
+        int64_t ny = total - y0 < 65535 ? total - y0 : 65535;
+        dim3 grid((unsigned)cdiv(B, 256), (unsigned)ny);
+        synth_kernel<<<grid, 256, 0, h->stream>>>(d_ac ? 0 : 1, y0, seed, d_t0, d_t1, (const int64_t *)h->ws, h->N, d_ac,
+                                                   h->dG, h->sG);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tensor engine
+// ---------------------------------------------------------------------------------------------------
+// Decode one 32-bit word (16 genotypes, 2 bits each, value coding) into four registers of 4 x u8 via the byte
+// permute unit: the 2-bit codes, isolated on nibble boundaries, ARE the prmt selector nibbles into the byte
+// pool {0,1,2,.} (or {0,0,1,.} for the "genotype == 2" indicator plane).
+//   d[0] = genotypes {0,2,4,6}   d[1] = {8,10,12,14}   d[2] = {1,3,5,7}   d[3] = {9,11,13,15}
+__device__ __forceinline__ void decode16(uint32_t w, uint32_t pool, uint32_t (&d)[4])
+{
+    uint32_t e = w & 0x33333333u;
+    uint32_t o = (w >> 2) & 0x33333333u;
+    d[0] = __byte_perm(pool, 0u, e);
+    d[1] = __byte_perm(pool, 0u, e >> 16);
+    d[2] = __byte_perm(pool, 0u, o);
+    d[3] = __byte_perm(pool, 0u, o >> 16);
+}
+
+__device__ __forceinline__ void mma_u8s8(int32_t (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint8_t *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// out[r][c*8+l] += sum over this CTA's k-chunk of  P[r][.] * L[c][.][l]
+//   P      : packed rows, `stride` bytes each (multiple of 64), rows padded to a multiple of 128*MT
+//   L      : limb fragments, per column c: nblk blocks of 2048 bytes; block = 256 genotypes x 8 limbs laid out
+//            [lane(32)][mma j(8)][b0/b1(2)][byte(4)] so that a lane's 64 bytes are its B fragments of the 8 MMAs
+//   grid   : x = k-chunks, y = row tiles of 128*MT rows;  8 warps, each MT m16 tiles
+template <int MT, int NT>
+__global__ void __launch_bounds__(256, (MT * NT <= 4) ? 2 : 1)
+pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_total, int kblocks_per_chunk,
+                const int8_t *__restrict__ L, int64_t Lcol_stride, int c0, int ncol_total, int32_t *__restrict__ out,
+                uint32_t pool)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t row0 = ((int64_t)blockIdx.y * 8 + warp) * (16 * MT);
+    const int64_t kb0 = (int64_t)blockIdx.x * kblocks_per_chunk;
+    int64_t kb1 = kb0 + kblocks_per_chunk;
+    if (kb1 > kblocks_total) kb1 = kblocks_total;
+
+    int32_t acc[MT][NT][4];
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+        for (int b = 0; b < NT; b++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
+
+    const uint8_t *pa = P + (row0 + g) * stride + kb0 * SGB_KSTEP_BYTES + 16 * t;
+    const int8_t *pl = L + (int64_t)c0 * Lcol_stride + kb0 * 2048 + lane * 64;
+
+    uint4 raw[MT][2];
+#pragma unroll
+    for (int a = 0; a < MT; a++) {
+        raw[a][0] = ldg_stream(pa + (int64_t)(16 * a) * stride);
+        raw[a][1] = ldg_stream(pa + (int64_t)(16 * a + 8) * stride);
+    }
+
+    for (int64_t kb = kb0; kb < kb1; kb++) {
+        uint4 cur[MT][2];
+#pragma unroll
+        for (int a = 0; a < MT; a++) { cur[a][0] = raw[a][0]; cur[a][1] = raw[a][1]; }
+        if (kb + 1 < kb1) {
+            const uint8_t *pn = pa + (kb + 1 - kb0) * SGB_KSTEP_BYTES;
+#pragma unroll
+            for (int a = 0; a < MT; a++) {
+                raw[a][0] = ldg_stream(pn + (int64_t)(16 * a) * stride);
+                raw[a][1] = ldg_stream(pn + (int64_t)(16 * a + 8) * stride);
+            }
+        }
+        uint4 bf[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(pl + (int64_t)n * Lcol_stride + (kb - kb0) * 2048);
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[n][j] = __ldg(q + j);
+        }
+#pragma unroll
+        for (int a = 0; a < MT; a++) {
+            const uint32_t wl[4] = {cur[a][0].x, cur[a][0].y, cur[a][0].z, cur[a][0].w};
+            const uint32_t wh[4] = {cur[a][1].x, cur[a][1].y, cur[a][1].z, cur[a][1].w};
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                uint32_t dl[4], dh[4];
+                decode16(wl[wi], pool, dl);
+                decode16(wh[wi], pool, dh);
+#pragma unroll
+                for (int n = 0; n < NT; n++) {
+                    mma_u8s8(acc[a][n], dl[0], dh[0], dl[1], dh[1], bf[n][wi].x, bf[n][wi].y);
+                    mma_u8s8(acc[a][n], dl[2], dh[2], dl[3], dh[3], bf[n][wi].z, bf[n][wi].w);
+                }
+            }
+        }
+    }
+
+    // C fragment: c0 (row g, limb 2t) c1 (row g, limb 2t+1) c2 (row g+8, limb 2t) c3 (row g+8, limb 2t+1)
+    const int ncols8 = ncol_total * 8;
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+            int32_t *o = out + (row0 + 16 * a + g) * ncols8 + (c0 + n) * 8 + 2 * t;
+            if (acc[a][n][0]) atomicAdd(o, acc[a][n][0]);
+            if (acc[a][n][1]) atomicAdd(o + 1, acc[a][n][1]);
+            if (acc[a][n][2]) atomicAdd(o + 8 * ncols8, acc[a][n][2]);
+            if (acc[a][n][3]) atomicAdd(o + 8 * ncols8 + 1, acc[a][n][3]);
+        }
+}
+
+template <int MT, int NT>
+static int launch_pk2(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kblocks, const int8_t *L,
+                      int64_t Lcol_stride, int c0, int ncol_total, int32_t *out, uint32_t pool)
+{
+    const int64_t rows_per_cta = 128 * MT;
+    int64_t row_tiles = rows_pad / rows_per_cta;
+    // aim for >= ~16 CTAs per SM worth of tiles, each at least 8 k-steps long
+    int64_t want_tiles = (int64_t)h->sm_count * 16;
+    int64_t kchunks = cdiv(want_tiles, row_tiles);
+    if (kchunks < 1) kchunks = 1;
+    int64_t per = cdiv(kblocks, kchunks);
+    if (per < 8) per = 8;
+    if (per > kblocks) per = kblocks;
+    kchunks = cdiv(kblocks, per);
+    for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {
+        int64_t ny = row_tiles - y0 < 65535 ? row_tiles - y0 : 65535;
+        dim3 grid((unsigned)kchunks, (unsigned)ny);
+        pk2_gemm_kernel<MT, NT><<<grid, 256, 0, h->stream>>>(P + y0 * rows_per_cta * stride, stride, kblocks, (int)per, L,
+                                                              Lcol_stride, c0, ncol_total,
+                                                              out + y0 * rows_per_cta * ncol_total * 8, pool);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L,
+               int ncol, int32_t *out, uint32_t pool)
+{
+    if (rows_pad % SGB_ROW_ALIGN || kbytes % SGB_KSTEP_BYTES || stride % SGB_KSTEP_BYTES)
+        return sgb_fail(h, "k_pk2_gemm: unaligned operand (rows %lld, kbytes %lld, stride %lld)", (long long)rows_pad,
+                        (long long)kbytes, (long long)stride);
+    int64_t kblocks = kbytes / SGB_KSTEP_BYTES;
+    if (kblocks == 0 || rows_pad == 0 || ncol == 0) return 0;
+    int64_t Lcs = kblocks * 2048;
+    int c = 0;
+    while (c < ncol) {
+        int rem = ncol - c;
+        if (rem >= 4) { SGB_TRY((launch_pk2<2, 4>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 4; }
+        else if (rem >= 2) { SGB_TRY((launch_pk2<4, 2>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 2; }
+        else { SGB_TRY((launch_pk2<4, 1>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 1; }
+    }
+    return 0;
+}
+
+// column max of |V| as the bit pattern of a non-negative double (monotone as uint64)
+__global__ void colmax_kernel(const double *__restrict__ V, int64_t len, int64_t ld, unsigned long long *__restrict__ mx)
+{
+    int c = blockIdx.y;
+    const double *v = V + (int64_t)c * ld;
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[i]));
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o);
+        m = x > m ? x : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&mx[c], m);
+}
+
+// One thread per (genotype slot i of the padded k range, column c): 8 balanced base-128 digits of
+// round(v * 2^(54-E)), E = exponent of the column max, scattered into the fragment layout (see pk2_gemm_kernel).
+__global__ void split_limbs_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int64_t nblk,
+                                   const unsigned long long *__restrict__ mx, int8_t *__restrict__ L,
+                                   double *__restrict__ mult)
+{
+    int c = blockIdx.y;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblk * 256) return;
+    unsigned long long mb = mx[c];
+    int E = (int)((mb >> 52) & 0x7FF) - 1023;
+    if (E < -1000) E = -1000;
+    if (E > 1000) E = 1000;            // inf/nan columns produce garbage, like any fp arithmetic would
+    long long q = 0;
+    if (i < len && mb) q = __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 54 - E));
+    if (i == 0) mult[c] = mb ? scalbn(1.0, E - 54) : 0.0;
+    int r = (int)(i & 255);
+    int64_t blk = i >> 8;
+    int t = r >> 6, wi = (r >> 4) & 3, p = r & 15;
+    int odd = p & 1, half = (p >> 3) & 1, slot = (p & 7) >> 1;
+    int j = 2 * wi + odd;
+    int8_t *base = L + ((int64_t)c * nblk + blk) * 2048 + t * 64 + j * 8 + half * 4 + slot;
+#pragma unroll
+    for (int l = 0; l < SGB_LIMBS; l++) {
+        int d = (int)((q + 64) & 127) - 64;
+        q = (q - d) >> 7;
+        base[l * 256] = (int8_t)d;     // lane = l*4 + t  -> +l*4*64 bytes
+    }
+}
+
+int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult)
+{
+    unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);   // k <= 1024 slots
+    if (k > 1024) return sgb_fail(h, "too many columns (%d)", k);
+    CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
+    int gx = (int)cdiv(len, 256 * 8);
+    if (gx > 1024) gx = 1024;
+    if (gx < 1) gx = 1;
+    colmax_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
+    LAUNCH_CHECK(h);
+    split_limbs_kernel<<<dim3((unsigned)nblk, k), 256, 0, h->stream>>>(V, len, ld, nblk, mx, L, d_mult);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// raw[r + c*ld] = (sum_l acc[r][c*8+l] * 128^l) * mult[c];  acc is reset to 0 for the next product.
+__global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k, const double *__restrict__ mult,
+                                 double *__restrict__ raw, int64_t ld)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * k) return;
+    int64_t r = idx / k;
+    int c = (int)(idx - r * k);
+    int4 *p = reinterpret_cast<int4 *>(acc + (r * k + c) * 8);
+    int4 lo = p[0], hi = p[1];
+    p[0] = make_int4(0, 0, 0, 0);
+    p[1] = make_int4(0, 0, 0, 0);
+    long long l4 = (long long)lo.x + ((long long)lo.y << 7) + ((long long)lo.z << 14) + ((long long)lo.w << 21);
+    long long h4 = (long long)hi.x + ((long long)hi.y << 7) + ((long long)hi.z << 14) + ((long long)hi.w << 21);
+    double v = (double)h4 * 268435456.0 + (double)l4;    // 128^4 = 2^28; both halves exact (< 2^53)
+    raw[r + (int64_t)c * ld] = v * mult[c];
+}
+
+int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, double *raw, int64_t ld)
+{
+    if (rows * k == 0) return 0;
+    recombine_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, d_mult, raw, ld);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// f64 engine (slow on-device cross-check of the tensor engine; plain fp64 FMA, no tensor cores)
+// ---------------------------------------------------------------------------------------------------
+// out[m + c*ldo] = sum_i g_mi B[i + c*ldb]      one warp per marker
+__global__ void rowdot_f64_kernel(const uint8_t *__restrict__ G, int64_t sG, int64_t Mloc, int64_t N,
+                                  const double *__restrict__ B, int64_t ldb, int k, double *__restrict__ out, int64_t ldo)
+{
+    int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= Mloc) return;
+    int lane = threadIdx.x & 31;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(G + m * sG);
+    int64_t nw = (N + 15) >> 4;
+    for (int c = 0; c < k; c++) {
+        const double *b = B + (int64_t)c * ldb;
+        double s1 = 0.0, s2 = 0.0;
+        for (int64_t w = lane; w < nw; w += 32) {
+            uint32_t x = row[w];
+            int64_t i0 = w << 4;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                int64_t i = i0 + j;
+                uint32_t cd = (x >> (2 * j)) & 3u;
+                if (cd && i < N) {
+                    double bv = b[i];
+                    if (cd == 1) s1 += bv; else s2 += bv;
+                }
+            }
+        }
+        double s = warp_sum(s1 + 2.0 * s2);
+        if (lane == 0) out[m + (int64_t)c * ldo] = s;
+    }
+}
+
+int k_rowdot_f64(sgb_ctx *h, const double *B, int64_t ldb, int k, double *out, int64_t ldo)
+{
+    if (h->Mloc == 0) return 0;
+    rowdot_f64_kernel<<<(unsigned)cdiv(h->Mloc, 8), 256, 0, h->stream>>>(h->dG, h->sG, h->Mloc, h->N, B, ldb, k, out, ldo);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// out[i + c*ldo] = sum_m (g_mi==1 ? D1[m,c] : g_mi==2 ? D2[m,c] : 0)   thread per 16 samples, marker chunks + atomics
+__global__ void coldot_f64_kernel(const uint8_t *__restrict__ G, int64_t sG, int64_t Mloc, int64_t N,
+                                  const double *__restrict__ D1, const double *__restrict__ D2, int64_t ldd, int c,
+                                  int64_t mchunk, double *__restrict__ out, int64_t ldo)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nw = (N + 15) >> 4;
+    if (w >= nw) return;
+    int64_t m0 = (int64_t)blockIdx.y * mchunk, m1 = m0 + mchunk;
+    if (m1 > Mloc) m1 = Mloc;
+    double acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = 0.0;
+    const double *d1 = D1 + (int64_t)c * ldd, *d2 = D2 ? D2 + (int64_t)c * ldd : nullptr;
+    for (int64_t m = m0; m < m1; m++) {
+        uint32_t x = *reinterpret_cast<const uint32_t *>(G + m * sG + 4 * w);
+        if (!x) continue;
+        double a1 = d1[m], a2 = D2 ? d2[m] : 2.0 * a1;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            uint32_t cd = (x >> (2 * j)) & 3u;
+            acc[j] += cd == 1 ? a1 : (cd == 2 ? a2 : 0.0);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        int64_t i = (w << 4) + j;
+        if (i < N && acc[j] != 0.0) atomicAdd(out + i + (int64_t)c * ldo, acc[j]);
+    }
+}
+
+int k_coldot_f64(sgb_ctx *h, const double *D1, const double *D2, int64_t ldd, int k, double *out, int64_t ldo)
+{
+    for (int c = 0; c < k; c++) CUDA_OK(h, cudaMemsetAsync(out + (int64_t)c * ldo, 0, sizeof(double) * h->N, h->stream));
+    if (h->Mloc == 0) return 0;
+    int64_t nw = (h->N + 15) / 16;
+    int64_t gx = cdiv(nw, 128);
+    int64_t chunks = cdiv((int64_t)h->sm_count * 8, gx);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 4096) chunks = 4096;
+    int64_t mchunk = cdiv(h->Mloc, chunks);
+    chunks = cdiv(h->Mloc, mchunk);
+    for (int c = 0; c < k; c++) {
+        coldot_f64_kernel<<<dim3((unsigned)gx, (unsigned)chunks), 128, 0, h->stream>>>(h->dG, h->sG, h->Mloc, h->N, D1, D2,
+                                                                                       ldd, c, mchunk, out, ldo);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// algebra around the sweeps (standardisation folded in: z_m = (g_m - 2f_m) s_m)
+// ---------------------------------------------------------------------------------------------------
+__global__ void partial_colsum_kernel(const double *__restrict__ V, int64_t len, int64_t ld, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    int c = blockIdx.y;
+    const double *v = V + (int64_t)c * ld;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) s += v[i];
+    s = block_sum_256(s, sm);
+    if (threadIdx.x == 0) part[(int64_t)c * SGB_PART_BLOCKS + blockIdx.x] = s;
+}
+
+__global__ void finish_partials_kernel(const double *__restrict__ part, int nblk, double *__restrict__ out)
+{
+    int c = threadIdx.x;
+    out[c] = sum_partials(part + (int64_t)c * SGB_PART_BLOCKS, nblk);
+}
+
+int k_colsum(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, double *d_out)
+{
+    double *part = reinterpret_cast<double *>(h->ws);
+    int nb = k_grid_blocks(h, len);
+    partial_colsum_kernel<<<dim3(nb, k), 256, 0, h->stream>>>(V, len, ld, part);
+    LAUNCH_CHECK(h);
+    finish_partials_kernel<<<1, k, 0, h->stream>>>(part, nb, d_out);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// D[m,c] = s_m^2 (raw[m,c] - 2f_m sumb_c), zeroed inside [mask_lo, mask_hi) (the left-out chromosome);
+// part_t[c][blk] = partial of sum_m 2f_m D[m,c]
+__global__ void sweep1_post_kernel(const double *__restrict__ raw, int64_t ld, int64_t Mloc, const double *__restrict__ f2,
+                                   const double *__restrict__ s2, const double *__restrict__ colsum, int64_t mask_lo,
+                                   int64_t mask_hi, double *__restrict__ D, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    int c = blockIdx.y;
+    double sb = colsum[c];
+    double t = 0.0;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < Mloc; m += (int64_t)gridDim.x * blockDim.x) {
+        double d = s2[m] * (raw[m + (int64_t)c * ld] - f2[m] * sb);
+        if (m >= mask_lo && m < mask_hi) d = 0.0;
+        D[m + (int64_t)c * ld] = d;
+        t += f2[m] * d;
+    }
+    t = block_sum_256(t, sm);
+    if (threadIdx.x == 0) part[(int64_t)c * SGB_PART_BLOCKS + blockIdx.x] = t;
+}
+
+int k_sweep1_post(sgb_ctx *h, const double *raw, int64_t ld, int k, const double *d_colsum, int64_t mask_lo,
+                  int64_t mask_hi, double *D, double *d_t)
+{
+    double *part = reinterpret_cast<double *>(h->ws);
+    int nb = k_grid_blocks(h, h->Mloc);
+    sweep1_post_kernel<<<dim3(nb, k), 256, 0, h->stream>>>(raw, ld, h->Mloc, h->d_f2, h->d_s2, d_colsum, mask_lo, mask_hi, D, part);
+    LAUNCH_CHECK(h);
+    finish_partials_kernel<<<1, k, 0, h->stream>>>(part, nb, d_t);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+__global__ void sweep2_post_kernel(const double *__restrict__ raw, int64_t ldr, int64_t N, const double *__restrict__ t,
+                                   double inv_m, double *__restrict__ Y, int64_t ldy)
+{
+    int c = blockIdx.y;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) Y[i + (int64_t)c * ldy] = (raw[i + (int64_t)c * ldr] - t[c]) * inv_m;
+}
+
+int k_sweep2_post(sgb_ctx *h, const double *raw, int64_t ldr, int k, const double *d_t, double inv_m, double *Y, int64_t ldy)
+{
+    sweep2_post_kernel<<<dim3((unsigned)cdiv(h->N, 256), k), 256, 0, h->stream>>>(raw, ldr, h->N, d_t, inv_m, Y, ldy);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// diag_i = sum_m z_mi^2 = sum_m [g==1] s^2(1-4f) + [g==2] s^2(4-8f) + sum_m 4 f^2 s^2, per marker range (column)
+//   D1[m,c] = s^2(1-2*f2)   (weight of one copy; the "value" plane contributes g*D1)
+//   D2[m,c] = 2 s^2         (extra weight of the g==2 indicator plane: 4-8f = 2(1-4f) + 2)
+__global__ void diag_prep_kernel(int64_t Mloc, int64_t ld, const double *__restrict__ f2, const double *__restrict__ s2,
+                                 const int64_t *__restrict__ lo, const int64_t *__restrict__ hi, double *__restrict__ D1,
+                                 double *__restrict__ D2, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    int c = blockIdx.y;
+    int64_t l = lo[c], hh = hi[c];
+    double t = 0.0;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < Mloc; m += (int64_t)gridDim.x * blockDim.x) {
+        bool in = m >= l && m < hh;
+        double ss = s2[m], ff = f2[m];
+        D1[m + (int64_t)c * ld] = in ? ss * (1.0 - 2.0 * ff) : 0.0;
+        D2[m + (int64_t)c * ld] = in ? 2.0 * ss : 0.0;
+        if (in) t += ff * ff * ss;
+    }
+    t = block_sum_256(t, sm);
+    if (threadIdx.x == 0) part[(int64_t)c * SGB_PART_BLOCKS + blockIdx.x] = t;
+}
+
+int k_diag_prep(sgb_ctx *h, int nchr, const int64_t *d_lo, const int64_t *d_hi, double *D1, double *D2, double *d_const)
+{
+    double *part = reinterpret_cast<double *>(h->ws);
+    int nb = k_grid_blocks(h, h->Mloc);
+    diag_prep_kernel<<<dim3(nb, nchr), 256, 0, h->stream>>>(h->Mloc, h->rowsG, h->d_f2, h->d_s2, d_lo, d_hi, D1, D2, part);
+    LAUNCH_CHECK(h);
+    finish_partials_kernel<<<1, nchr, 0, h->stream>>>(part, nb, d_const);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+__global__ void diag_post_kernel(const double *__restrict__ r1, const double *__restrict__ r2, int64_t ld, int64_t N,
+                                 const double *__restrict__ cst, double *__restrict__ out, int64_t ldo)
+{
+    int c = blockIdx.y;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i + (int64_t)c * ldo] = r1[i + (int64_t)c * ld] + r2[i + (int64_t)c * ld] + cst[c];
+}
+
+int k_diag_post(sgb_ctx *h, const double *raw1, const double *raw2, int64_t ld, int ncol, const double *d_const,
+                double *out, int64_t ldo)
+{
+    diag_post_kernel<<<dim3((unsigned)cdiv(h->N, 256), ncol), 256, 0, h->stream>>>(raw1, raw2, ld, h->N, d_const, out, ldo);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sigma diag, PCG, small dense helpers
+// ---------------------------------------------------------------------------------------------------
+// getDiagOfSigma[_LOCO] (FG.cpp:2322-2393): tau1*diag*diag_scale + tau0/w, floored at 1e-4
+__global__ void sigma_diag_kernel(const double *__restrict__ diag, double diag_scale, int diag_one,
+                                  const double *__restrict__ w, double tau0, double tau1, int64_t N, double *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double d = (diag_one ? tau1 : tau1 * diag[i] * diag_scale) + tau0 / w[i];
+    if (d < 1e-4) d = 1e-4;
+    out[i] = d;
+}
+
+int k_sigma_diag(sgb_ctx *h, const double *diag, double diag_scale, int diag_one, const double *w, double tau0,
+                 double tau1, double *out)
+{
+    sigma_diag_kernel<<<(unsigned)cdiv(h->N, 256), 256, 0, h->stream>>>(diag, diag_scale, diag_one, w, tau0, tau1, h->N, out);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// x=0; r=b; z=r/diag; p=z; rz = r.z ; r2 = r.r      (FG.cpp:2599-2684).  `dsig` is diag(Sigma) (not inverted).
+__global__ void pcg_init_kernel(const double *__restrict__ B, const double *__restrict__ dsig, int64_t N,
+                                double *__restrict__ X, double *__restrict__ R, double *__restrict__ Z,
+                                double *__restrict__ P, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    int c = blockIdx.y;
+    double rz = 0.0, r2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = i + (int64_t)c * N;
+        double r = B[o], z = (1.0 / dsig[i]) * r;
+        X[o] = 0.0; R[o] = r; Z[o] = z; P[o] = z;
+        rz += r * z; r2 += r * r;
+    }
+    rz = block_sum_256(rz, sm);
+    r2 = block_sum_256(r2, sm);
+    if (threadIdx.x == 0) {
+        part[((int64_t)c * 2 + 0) * SGB_PART_BLOCKS + blockIdx.x] = rz;
+        part[((int64_t)c * 2 + 1) * SGB_PART_BLOCKS + blockIdx.x] = r2;
+    }
+}
+
+__global__ void pcg_init_finish_kernel(const double *__restrict__ part, int nblk, double *__restrict__ rz, double *__restrict__ r2)
+{
+    int c = threadIdx.x;
+    rz[c] = sum_partials(part + ((int64_t)c * 2 + 0) * SGB_PART_BLOCKS, nblk);
+    r2[c] = sum_partials(part + ((int64_t)c * 2 + 1) * SGB_PART_BLOCKS, nblk);
+}
+
+int k_pcg_init(sgb_ctx *h, const double *B, const double *dsig, int k, double *X, double *R, double *Z, double *P,
+               double *d_rz, double *d_r2)
+{
+    double *part = reinterpret_cast<double *>(h->ws);
+    int nb = k_grid_blocks(h, h->N);
+    pcg_init_kernel<<<dim3(nb, k), 256, 0, h->stream>>>(B, dsig, h->N, X, R, Z, P, part);
+    LAUNCH_CHECK(h);
+    pcg_init_finish_kernel<<<1, k, 0, h->stream>>>(part, nb, d_rz, d_r2);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+__global__ void gather_cols_kernel(const double *__restrict__ src, const int *__restrict__ cols, int64_t N, double *__restrict__ dst)
+{
+    int j = blockIdx.y;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[i + (int64_t)j * N] = src[i + (int64_t)cols[j] * N];
+}
+__global__ void scatter_cols_kernel(const double *__restrict__ src, const int *__restrict__ cols, int64_t N, double *__restrict__ dst)
+{
+    int j = blockIdx.y;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[i + (int64_t)cols[j] * N] = src[i + (int64_t)j * N];
+}
+int k_gather_cols(sgb_ctx *h, const double *src, const int *d_cols, int ncols, double *dst)
+{
+    gather_cols_kernel<<<dim3((unsigned)cdiv(h->N, 256), ncols), 256, 0, h->stream>>>(src, d_cols, h->N, dst);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+int k_scatter_cols(sgb_ctx *h, const double *src, const int *d_cols, int ncols, double *dst)
+{
+    scatter_cols_kernel<<<dim3((unsigned)cdiv(h->N, 256), ncols), 256, 0, h->stream>>>(src, d_cols, h->N, dst);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// Ap = tau0*p/w + tau1*Kp  (getCrossprod, FG.cpp:2397-2425), in place over the packed Kp; partial p.Ap
+__global__ void pcg_step1_kernel(const double *__restrict__ P, double *__restrict__ KP, const double *__restrict__ w,
+                                 double tau0, double tau1, const int *__restrict__ act, int64_t N, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    int j = blockIdx.y, c = act[j];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        double p = P[i + (int64_t)c * N];
+        double ap = tau0 * (p * (1.0 / w[i]));
+        if (tau1 != 0.0) ap += tau1 * KP[i + (int64_t)j * N];
+        KP[i + (int64_t)j * N] = ap;
+        s += p * ap;
+    }
+    s = block_sum_256(s, sm);
+    if (threadIdx.x == 0) part[(int64_t)j * SGB_PART_BLOCKS + blockIdx.x] = s;
+}
+
+int k_pcg_step1(sgb_ctx *h, const double *P, double *KP, const double *w, double tau0, double tau1, const int *d_act,
+                int nact, double *d_part)
+{
+    int nb = k_grid_blocks(h, h->N);
+    pcg_step1_kernel<<<dim3(nb, nact), 256, 0, h->stream>>>(P, KP, w, tau0, tau1, d_act, h->N, d_part);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// a = rz/pAp; x += a p; r -= a Ap; z = r/diag; partials of z.r and r.r     (FG.cpp:2710-2783)
+__global__ void pcg_step2_kernel(const double *__restrict__ P, const double *__restrict__ AP, const double *__restrict__ dsig,
+                                 const int *__restrict__ act, int64_t N, int nblk, double *__restrict__ X,
+                                 double *__restrict__ R, double *__restrict__ Z, const double *__restrict__ rz,
+                                 const double *__restrict__ part_in, double *__restrict__ part_out)
+{
+    __shared__ double sm[8];
+    int j = blockIdx.y, c = act[j];
+    double pap = sum_partials(part_in + (int64_t)j * SGB_PART_BLOCKS, nblk);
+    double a = rz[c] / pap;
+    double zr = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = i + (int64_t)c * N;
+        double p = P[o];
+        X[o] = X[o] + a * p;
+        double r = R[o] - a * AP[i + (int64_t)j * N];
+        double z = (1.0 / dsig[i]) * r;
+        R[o] = r; Z[o] = z;
+        zr += z * r; rr += r * r;
+    }
+    zr = block_sum_256(zr, sm);
+    rr = block_sum_256(rr, sm);
+    if (threadIdx.x == 0) {
+        part_out[((int64_t)j * 2 + 0) * SGB_PART_BLOCKS + blockIdx.x] = zr;
+        part_out[((int64_t)j * 2 + 1) * SGB_PART_BLOCKS + blockIdx.x] = rr;
+    }
+}
+
+int k_pcg_step2(sgb_ctx *h, const double *P, const double *AP, const double *dsig, const int *d_act, int nact,
+                double *X, double *R, double *Z, double *d_rz, const double *d_part_in, double *d_part_out)
+{
+    int nb = k_grid_blocks(h, h->N);
+    pcg_step2_kernel<<<dim3(nb, nact), 256, 0, h->stream>>>(P, AP, dsig, d_act, h->N, nb, X, R, Z, d_rz, d_part_in, d_part_out);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// bet = z1.r1 / z.r ; p = z1 + bet p ; publish new rz and r2 (rz_out != rz_in: other blocks still read rz_in)
+__global__ void pcg_step3_kernel(double *__restrict__ P, const double *__restrict__ Z, const int *__restrict__ act, int64_t N,
+                                 int nblk, const double *__restrict__ rz_in, double *__restrict__ rz_out,
+                                 double *__restrict__ r2, const double *__restrict__ part)
+{
+    int j = blockIdx.y, c = act[j];
+    double zr = sum_partials(part + ((int64_t)j * 2 + 0) * SGB_PART_BLOCKS, nblk);
+    double bet = zr / rz_in[c];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = i + (int64_t)c * N;
+        P[o] = Z[o] + bet * P[o];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rz_out[c] = zr;
+        r2[c] = sum_partials(part + ((int64_t)j * 2 + 1) * SGB_PART_BLOCKS, nblk);
+    }
+}
+
+int k_pcg_step3(sgb_ctx *h, double *P, const double *Z, const int *d_act, int nact, const double *rz_in, double *rz_out,
+                   double *d_r2, const double *d_part)
+{
+    int nb = k_grid_blocks(h, h->N);
+    pcg_step3_kernel<<<dim3(nb, nact), 256, 0, h->stream>>>(P, Z, d_act, h->N, nb, rz_in, rz_out, d_r2, d_part);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// out[q] = A[:,pairs[2q]] . B[:,pairs[2q+1]]
+__global__ void pair_dots_kernel(const double *__restrict__ A, int64_t lda, const double *__restrict__ B, int64_t ldb,
+                                 const int *__restrict__ pairs, int64_t N, double *__restrict__ part)
+{
+    __shared__ double sm[8];
+    int q = blockIdx.y;
+    const double *a = A + (int64_t)pairs[2 * q] * lda, *b = B + (int64_t)pairs[2 * q + 1] * ldb;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * b[i];
+    s = block_sum_256(s, sm);
+    if (threadIdx.x == 0) part[(int64_t)q * SGB_PART_BLOCKS + blockIdx.x] = s;
+}
+__global__ void finish_many_kernel(const double *__restrict__ part, int nblk, int n, double *__restrict__ out)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = sum_partials(part + (int64_t)q * SGB_PART_BLOCKS, nblk);
+}
+
+int k_pair_dots(sgb_ctx *h, const double *A, int64_t lda, const double *B, int64_t ldb, const int *d_pairs, int npairs,
+                double *d_out)
+{
+    if (npairs == 0) return 0;
+    if ((size_t)npairs * SGB_PART_BLOCKS * sizeof(double) > h->ws_bytes) return sgb_fail(h, "k_pair_dots: workspace too small");
+    double *part = reinterpret_cast<double *>(h->ws);
+    int nb = k_grid_blocks(h, h->N);
+    pair_dots_kernel<<<dim3(nb, npairs), 256, 0, h->stream>>>(A, lda, B, ldb, d_pairs, h->N, part);
+    LAUNCH_CHECK(h);
+    finish_many_kernel<<<(unsigned)cdiv(npairs, 128), 128, 0, h->stream>>>(part, nb, npairs, d_out);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// Out[:,j] = In[:,j] - SiX * C[:,j]      (P u = Sigma^-1 u - Sigma^-1 X (cov (Sigma^-1 X)^T u), FG.cpp:3139)
+__global__ void project_kernel(const double *__restrict__ In, const double *__restrict__ SiX, int p, const double *__restrict__ Cm,
+                               int64_t N, double *__restrict__ Out)
+{
+    int j = blockIdx.y;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double v = In[i + (int64_t)j * N];
+    for (int q = 0; q < p; q++) v -= SiX[i + (int64_t)q * N] * Cm[q + (int64_t)j * p];
+    Out[i + (int64_t)j * N] = v;
+}
+
+int k_project(sgb_ctx *h, const double *In, const double *SiX, int p, const double *d_C, int ncol, double *Out)
+{
+    if (ncol == 0) return 0;
+    project_kernel<<<dim3((unsigned)cdiv(h->N, 256), ncol), 256, 0, h->stream>>>(In, SiX, p, d_C, h->N, Out);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// eta = Y - tau0 (Sigma_iY - Sigma_iX alpha) / w        (FG.cpp:3194)
+__global__ void eta_kernel(const double *__restrict__ Y, const double *__restrict__ SiY, const double *__restrict__ SiX, int p,
+                           const double *__restrict__ alpha, const double *__restrict__ w, double tau0, int64_t N,
+                           double *__restrict__ eta)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double v = SiY[i];
+    for (int q = 0; q < p; q++) v -= SiX[i + (int64_t)q * N] * alpha[q];
+    eta[i] = Y[i] - tau0 * v / w[i];
+}
+
+int k_eta(sgb_ctx *h, const double *Y, const double *SiY, const double *SiX, int p, const double *d_alpha,
+          const double *w, double tau0, double *eta)
+{
+    eta_kernel<<<(unsigned)cdiv(h->N, 256), 256, 0, h->stream>>>(Y, SiY, SiX, p, d_alpha, w, tau0, h->N, eta);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+__global__ void rademacher_kernel(double *__restrict__ B, int64_t n, uint64_t seed)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) B[i] = (mix32(seed, 0x5151, (uint64_t)i, 7) & 1u) ? 1.0 : -1.0;
+}
+
+int k_rademacher_fill(sgb_ctx *h, double *B, int64_t n, uint64_t seed)
+{
+    rademacher_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(B, n, seed);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+__global__ void axpby_kernel(double a, const double *__restrict__ x, double b, const double *__restrict__ y, int64_t n,
+                             double *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + b * y[i];
+}
+
+int k_axpby(sgb_ctx *h, double a, const double *x, double b, const double *y, int64_t n, double *out)
+{
+    if (n == 0) return 0;
+    axpby_kernel<<<(unsigned)cdiv(n, 256), 256, 0, h->stream>>>(a, x, b, y, n, out);
+    LAUNCH_CHECK(h);
+    return 0;
+}

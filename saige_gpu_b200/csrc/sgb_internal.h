@@ -1,0 +1,159 @@
+// Internal declarations of libsaige_b200.so (not part of the ABI; the ABI is include/saige_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "saige_b200.h"
+
+#define SGB_LIMBS 8          // signed base-128 digits per fp64 value (56-bit fixed point)
+#define SGB_KSTEP_BYTES 64   // packed bytes (256 genotypes) consumed per k-step of the tensor kernel
+#define SGB_ROW_ALIGN 512    // row padding of both genotype copies (CTA tile of the tensor kernel)
+#define SGB_SHARD_BLOCK 1024 // markers per block of the block-cyclic marker->rank map
+
+struct sgb_dist;             // NCCL state (dist.cu)
+
+struct sgb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int engine = SGB_ENGINE_TENSOR;
+    int sm_count = 148;
+
+    // configuration (FG.cpp:35,99,57-59)
+    float minMAF = 0.f, maxMissing = 1.f;
+    bool isVarRatio = false;
+    float minMACvr = 20.f, maxMACvr = -1.f;
+    bool kinDiagOne = false;
+
+    // dimensions
+    int64_t N0 = 0, M0 = 0, N = 0, M = 0, Mloc = 0, Mvr = 0;
+    bool loaded = false;
+
+    // host-side marker statistics over ALL QC'd markers (every rank has them, like the reference's SPMD ranks)
+    std::vector<float> afreq, invstd, afreq_vr, invstd_vr;
+    std::vector<int32_t> mac, ac, mac_vr, ac_vr, index_vr;
+    std::vector<uint8_t> qc_mask;
+    std::vector<uint8_t> vr_packed;          // Mvr x ceil(N/4), device coding (value bits), host resident
+    std::vector<int64_t> loc2glob;           // local row -> global QC'd marker index (monotone)
+
+    // device genotype store, device coding: 2 bits per genotype = number of A1 copies (0,1,2), sample i of a
+    // marker at bits 2(i%4) of byte i/4; all padding is genotype 0.
+    uint8_t *dG = nullptr;   int64_t sG = 0, rowsG = 0;   // marker-major  [rowsG][sG],  rowsG>=Mloc
+    uint8_t *dGt = nullptr;  int64_t sT = 0, rowsT = 0;   // sample-major  [rowsT][sT],  rowsT>=N
+    double *d_f2 = nullptr;  // 2*f_m      per local marker
+    double *d_s = nullptr;   // 1/sqrt(2f(1-f)) per local marker
+    double *d_s2 = nullptr;  // s_m^2
+
+    // LOCO
+    std::vector<int32_t> startVec, endVec;
+    int loco_start = -1, loco_end = -1, loco_chrom = -1;
+    double *d_diag = nullptr;        // sum_m z_mi^2 over all markers (N), lazily computed (FG.cpp:665-704)
+    bool diag_ready = false;
+    double *d_diag_loco = nullptr;   // N x nchr: full - per-chromosome (FG.cpp:4934-4958)
+    std::vector<int64_t> msub_by_chr;
+    bool diag_loco_ready = false;
+
+    // scratch
+    void *ws = nullptr; size_t ws_bytes = 0;          // generic workspace
+    int32_t *d_acc1 = nullptr; size_t acc1_elems = 0; // int32 limb sums of sweep 1  [rowsG][8k]
+    int32_t *d_acc2 = nullptr; size_t acc2_elems = 0; // int32 limb sums of sweep 2  [rowsT][8k]
+    int8_t *d_limb = nullptr; size_t limb_bytes = 0;  // limb fragments
+    double *d_tmp = nullptr; size_t tmp_elems = 0;    // fp64 scratch (c/d vectors etc.)
+    double *d_scal = nullptr;                         // small scalar scratch (4096 doubles)
+    double *h_scal = nullptr;                         // pinned mirror
+    double *d_io = nullptr; size_t io_elems = 0;      // staging for host<->device vectors
+    double *d_bench = nullptr; size_t bench_elems = 0;
+    double *d_pcg = nullptr; size_t pcg_elems = 0;    // PCG state arena
+    double *d_ai = nullptr; size_t ai_elems = 0;      // per-call arena of the AI-REML entry points
+    int *d_idx = nullptr;                             // small int scratch (8192 ints)
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_sweep_ms[2] = {0.f, 0.f};
+    bool time_sweeps = false;
+
+    sgb_dist *dist = nullptr;
+    int rank = 0, world = 1;
+
+    sgb_counters cnt = {};
+};
+
+// ---- error helpers ----
+int sgb_fail(sgb_ctx *h, const char *fmt, ...);
+#define CUDA_OK(h, call)                                                                           \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return sgb_fail(h, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                                                cudaGetErrorString(e__));                          \
+    } while (0)
+#define SGB_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__) return rc__;         \
+    } while (0)
+
+int sgb_ensure(sgb_ctx *h, void **p, size_t *cur, size_t need_bytes);   // grow-only device buffer
+
+// ---- kernels.cu launchers (all on h->stream) ----
+int k_count_markers(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, int64_t nmark, const uint8_t *d_indmask,
+                    int32_t *d_ac, int32_t *d_nmiss);
+int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_rows, const int32_t *d_fill,
+             int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_stride);
+int k_transpose(sgb_ctx *h);   // dG -> dGt
+int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, int32_t *d_ac);
+
+// tensor engine: out[r][c*8+l] += sum_k P[r][k] * L[c][k][l]  (int32, exact)
+int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L,
+               int ncol, int32_t *out, uint32_t pool);
+// limb preparation: V[len x k] (ld) -> fragments [k][nblk][2048] + per-column multiplier (2^(E-54)) in d_mult[k]
+int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult);
+// raw[r + c*ld] = recombine(acc[r][c*8..]) * mult[c]; acc zeroed
+int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, double *raw, int64_t ld);
+
+// f64 engine
+int k_rowdot_f64(sgb_ctx *h, const double *B, int64_t ldb, int k, double *out, int64_t ldo);   // out[m,c]=sum_i g_mi B[i,c]
+int k_coldot_f64(sgb_ctx *h, const double *D1, const double *D2, int64_t ldd, int k, double *out, int64_t ldo);
+
+// algebra around the sweeps
+int k_colsum(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, double *d_out);   // deterministic
+int k_sweep1_post(sgb_ctx *h, const double *raw, int64_t ld, int k, const double *d_colsum, int64_t mask_lo,
+                  int64_t mask_hi, double *D, double *d_t);  // D = s^2 (raw - 2f*sumb) (masked), t = sum 2f D
+int k_sweep2_post(sgb_ctx *h, const double *raw, int64_t ldr, int k, const double *d_t, double inv_m, double *Y,
+                  int64_t ldy);
+int k_diag_prep(sgb_ctx *h, int nchr, const int64_t *h_lo, const int64_t *h_hi, double *D1, double *D2, double *d_const);
+int k_diag_post(sgb_ctx *h, const double *raw1, const double *raw2, int64_t ld, int ncol, const double *d_const,
+                double *out, int64_t ldo);
+
+// PCG / BLAS-1 (N x k column-major, ld = N)
+int k_sigma_diag(sgb_ctx *h, const double *diag, double diag_scale, int diag_one, const double *w, double tau0,
+                 double tau1, double *out);
+int k_pcg_init(sgb_ctx *h, const double *B, const double *minv, int k, double *X, double *R, double *Z, double *P,
+               double *d_rz, double *d_r2);
+int k_gather_cols(sgb_ctx *h, const double *src, const int *d_cols, int ncols, double *dst);
+int k_scatter_cols(sgb_ctx *h, const double *src, const int *d_cols, int ncols, double *dst);
+int k_pcg_step1(sgb_ctx *h, const double *P, double *KP, const double *w, double tau0, double tau1, const int *d_act,
+                int nact, double *d_part);   // KP := Ap (packed);   part[j][blk] = partial p.Ap
+int k_pcg_step2(sgb_ctx *h, const double *P, const double *AP, const double *minv, const int *d_act, int nact,
+                double *X, double *R, double *Z, double *d_rz, const double *d_part_in, double *d_part_out);
+int k_pcg_step3(sgb_ctx *h, double *P, const double *Z, const int *d_act, int nact, const double *rz_in, double *rz_out,
+                double *d_r2, const double *d_part);
+int k_pair_dots(sgb_ctx *h, const double *A, int64_t lda, const double *B, int64_t ldb, const int *d_pairs, int npairs,
+                double *d_out);   // d_out[q] = A[:,pairs[2q]] . B[:,pairs[2q+1]]   (deterministic)
+int k_project(sgb_ctx *h, const double *In, const double *SiX, int p, const double *d_C, int ncol, double *Out);
+int k_eta(sgb_ctx *h, const double *Y, const double *SiY, const double *SiX, int p, const double *d_alpha,
+          const double *w, double tau0, double *eta);
+int k_rademacher_fill(sgb_ctx *h, double *B, int64_t n, uint64_t seed);
+int k_axpby(sgb_ctx *h, double a, const double *x, double b, const double *y, int64_t n, double *out);
+int k_grid_blocks(sgb_ctx *h, int64_t n);
+#define SGB_PART_BLOCKS 256   // partial-sum slots per column of the deterministic reductions
+
+// crossprod.cu
+int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int loco);
+int sgb_diag_device(sgb_ctx *h);
+int sgb_diag_loco_device(sgb_ctx *h);
+int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const double *dB, int k, int maxiter, double tol,
+                   int loco, double *dX, int32_t *iters);
+int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n);
+int sgb_dist_init(sgb_ctx *h, int rank, int world, const void *id128);
+void sgb_dist_destroy(sgb_ctx *h);
+int sgb_dist_unique_id(void *id128, std::string &err);

@@ -1,0 +1,763 @@
+// GRM products, multi-right-hand-side PCG and the AI-REML entry points: the B200 replacement of
+// getCrossprodMatAndKin / getPCG1ofSigmaAndVector / getCoefficients / GetTrace / getAIScore / fitglmmaiRPCG
+// (FG.cpp:1953-2006, 2593-2809, 3113-3341, 3409-3662).  Everything stays device resident inside one entry point;
+// the host sees only scalars (dot products, tau) and the p x p covariance algebra.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "sgb_internal.h"
+
+#define NEED_LOADED(h) do { if (!(h)->loaded) return sgb_fail(h, "genotypes not loaded: call setgeno first"); } while (0)
+
+// d_scal layout (doubles)
+enum { SC_COLSUM = 0, SC_T = 1024, SC_MAX = 2048, SC_MULT1 = 3072, SC_MULT2 = 4096, SC_PCG = 5120 /* rzA,rzB,r2: 3x1024 */ };
+
+static int ensure_zeroed_i32(sgb_ctx *h, int32_t **p, size_t *cur_elems, size_t need_elems)
+{
+    if (*p && *cur_elems >= need_elems) return 0;
+    size_t bytes = *cur_elems * sizeof(int32_t);
+    SGB_TRY(sgb_ensure(h, (void **)p, &bytes, need_elems * sizeof(int32_t)));
+    *cur_elems = bytes / sizeof(int32_t);
+    CUDA_OK(h, cudaMemsetAsync(*p, 0, bytes, h->stream));
+    return 0;
+}
+
+static int ensure_f64(sgb_ctx *h, double **p, size_t *cur_elems, size_t need_elems)
+{
+    if (*p && *cur_elems >= need_elems) return 0;
+    size_t bytes = *cur_elems * sizeof(double);
+    SGB_TRY(sgb_ensure(h, (void **)p, &bytes, need_elems * sizeof(double)));
+    *cur_elems = bytes / sizeof(double);
+    return 0;
+}
+
+static void loco_local_range(sgb_ctx *h, int64_t gs, int64_t ge, int64_t *lo, int64_t *hi)
+{
+    *lo = std::lower_bound(h->loc2glob.begin(), h->loc2glob.end(), gs) - h->loc2glob.begin();
+    *hi = std::upper_bound(h->loc2glob.begin(), h->loc2glob.end(), ge) - h->loc2glob.begin();
+}
+
+// Y[N x k] (ld N) = K.B  or the LOCO product; dB, dY device pointers (ld N).  May be called with dY == dB.
+int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int loco)
+{
+    NEED_LOADED(h);
+    if (k < 1 || k > 1024) return sgb_fail(h, "crossprod: k=%d out of range", k);
+    const int64_t N = h->N, rowsG = h->rowsG, rowsT = h->rowsT;
+    int64_t lo = 0, hi = 0;
+    double mdiv = (double)h->M;
+    if (loco) {
+        if (h->loco_start < 0) return sgb_fail(h, "LOCO product requested before setStartEndIndex");
+        loco_local_range(h, h->loco_start, h->loco_end, &lo, &hi);
+        mdiv = (double)(h->M - (h->loco_end - h->loco_start + 1));       // FG.cpp:1848
+    }
+    const int64_t nblkN = h->sG / SGB_KSTEP_BYTES, nblkM = h->sT / SGB_KSTEP_BYTES;
+    // fp64 scratch: raw1 [rowsG*k] | D [rowsG*k] | raw2 [rowsT*k + k]
+    SGB_TRY(ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + rowsT + 1) * k));
+    double *raw1 = h->d_tmp, *D = raw1 + rowsG * k, *raw2 = D + rowsG * k;
+    double *sc = h->d_scal;
+    const bool tensor = h->engine == SGB_ENGINE_TENSOR;
+    if (tensor) {
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)k * std::max(nblkN, nblkM) * 2048));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc1, &h->acc1_elems, (size_t)rowsG * 8 * k));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * k));
+    }
+    h->cnt.n_crossprod_calls++; h->cnt.n_crossprod_columns += k;
+
+    SGB_TRY(k_colsum(h, dB, N, N, k, sc + SC_COLSUM));
+    // ---- sweep 1: raw1[m,c] = g_m . b_c over the marker-major copy ----
+    if (tensor) {
+        SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
+        SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, 0x00020100u));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
+        SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, sc + SC_MULT1, raw1, rowsG));
+    } else {
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
+        SGB_TRY(k_rowdot_f64(h, dB, N, k, raw1, rowsG));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
+    }
+    // ---- D = s^2 (raw1 - 2f sum b), left-out chromosome zeroed; t = sum_m 2f D ----
+    SGB_TRY(k_sweep1_post(h, raw1, rowsG, k, sc + SC_COLSUM, lo, hi, D, sc + SC_T));
+    // ---- sweep 2: raw2[i,c] = sum_m g_mi D[m,c] over the sample-major copy ----
+    if (tensor) {
+        SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
+        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, 0x00020100u));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, sc + SC_MULT2, raw2, rowsT));
+    } else {
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
+        SGB_TRY(k_coldot_f64(h, D, nullptr, rowsG, k, raw2, rowsT));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
+    }
+    const double *tvec = sc + SC_T;
+    if (h->world > 1) {
+        // one sum-allreduce per (multi-)product: the N x k partial and the k centring scalars travel together
+        CUDA_OK(h, cudaMemcpyAsync(raw2 + rowsT * k, sc + SC_T, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
+        SGB_TRY(sgb_allreduce_sum(h, raw2, rowsT * k + k));
+        tvec = raw2 + rowsT * k;
+    }
+    SGB_TRY(k_sweep2_post(h, raw2, rowsT, k, tvec, 1.0 / mdiv, dY, N));
+    if (h->time_sweeps) {
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        cudaEventElapsedTime(&h->last_sweep_ms[0], h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&h->last_sweep_ms[1], h->ev[2], h->ev[3]);
+    }
+    return 0;
+}
+
+// sum_m z_mi^2 for `nc` local-row ranges at once -> out[N x nc] (ld N); summed over ranks
+static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const std::vector<int64_t> &hi, double *out)
+{
+    const int64_t N = h->N, rowsG = h->rowsG, rowsT = h->rowsT;
+    const int64_t nblkM = h->sT / SGB_KSTEP_BYTES;
+    // D1 | D2 [rowsG*nc each] | r1 | r2 [rowsT*nc each] | const[nc]
+    SGB_TRY(ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + 2 * rowsT + 1) * nc));
+    double *D1 = h->d_tmp, *D2 = D1 + rowsG * nc, *r1 = D2 + rowsG * nc, *r2 = r1 + rowsT * nc, *cst = r2 + rowsT * nc;
+    int64_t *d_rng = reinterpret_cast<int64_t *>(h->d_idx);
+    if ((size_t)nc * 2 * sizeof(int64_t) > 8192 * sizeof(int)) return sgb_fail(h, "too many chromosome ranges");
+    std::vector<int64_t> both(lo);
+    both.insert(both.end(), hi.begin(), hi.end());
+    CUDA_OK(h, cudaMemcpyAsync(d_rng, both.data(), sizeof(int64_t) * 2 * nc, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    SGB_TRY(k_diag_prep(h, nc, d_rng, d_rng + nc, D1, D2, cst));
+    if (h->engine == SGB_ENGINE_TENSOR) {
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)nc * nblkM * 2048));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * nc));
+        SGB_TRY(k_split_limbs(h, D1, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT1));
+        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, 0x00020100u));   // value plane
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT1, r1, rowsT));
+        SGB_TRY(k_split_limbs(h, D2, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT2));
+        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, 0x00010000u));   // [g==2] plane
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT2, r2, rowsT));
+    } else {
+        // weight of g==2 is 2*D1 + D2; fold it into one pass and leave r2 = 0
+        SGB_TRY(k_axpby(h, 2.0, D1, 1.0, D2, rowsG * nc, D2));
+        SGB_TRY(k_coldot_f64(h, D1, D2, rowsG, nc, r1, rowsT));
+        CUDA_OK(h, cudaMemsetAsync(r2, 0, sizeof(double) * rowsT * nc, h->stream));
+    }
+    if (h->world > 1) SGB_TRY(sgb_allreduce_sum(h, r1, 2 * rowsT * nc + nc));
+    SGB_TRY(k_diag_post(h, r1, r2, rowsT, nc, cst, out, N));
+    return 0;
+}
+
+// Get_Diagof_StdGeno (FG.cpp:665-704): cached sum over all markers
+int sgb_diag_device(sgb_ctx *h)
+{
+    NEED_LOADED(h);
+    if (h->diag_ready) return 0;
+    std::vector<int64_t> lo(1, 0), hi(1, h->Mloc);
+    SGB_TRY(diag_ranges(h, 1, lo, hi, h->d_diag));
+    h->diag_ready = true;
+    return 0;
+}
+
+// set_Diagof_StdGeno_LOCO (FG.cpp:4934-4958): column c = full diag - diag over chromosome c
+int sgb_diag_loco_device(sgb_ctx *h)
+{
+    NEED_LOADED(h);
+    int nc = (int)h->startVec.size();
+    if (nc == 0) return sgb_fail(h, "set_Diagof_StdGeno_LOCO: call setStartEndIndexVec first");
+    SGB_TRY(sgb_diag_device(h));
+    std::vector<int64_t> lo(nc, 0), hi(nc, 0);
+    h->msub_by_chr.assign(nc, 0);
+    for (int c = 0; c < nc; c++)
+        if (h->startVec[c] != -1 && h->endVec[c] != -1) {
+            loco_local_range(h, h->startVec[c], h->endVec[c], &lo[c], &hi[c]);
+            h->msub_by_chr[c] = h->endVec[c] - h->startVec[c] + 1;
+        }
+    if (h->d_diag_loco) { cudaFree(h->d_diag_loco); h->d_diag_loco = nullptr; }
+    CUDA_OK(h, cudaMalloc((void **)&h->d_diag_loco, sizeof(double) * h->N * nc));
+    SGB_TRY(diag_ranges(h, nc, lo, hi, h->d_diag_loco));
+    for (int c = 0; c < nc; c++)
+        SGB_TRY(k_axpby(h, 1.0, h->d_diag, -1.0, h->d_diag_loco + (int64_t)c * h->N, h->N, h->d_diag_loco + (int64_t)c * h->N));
+    h->diag_loco_ready = true;
+    return 0;
+}
+
+// diag(Sigma) on device (not inverted), FG.cpp:2322-2393
+static int sigma_diag_device(sgb_ctx *h, const double *d_w, const double *tau, int loco, double *d_out)
+{
+    if (loco) {
+        if (!h->diag_loco_ready) return sgb_fail(h, "LOCO solve requested before set_Diagof_StdGeno_LOCO");
+        if (h->loco_chrom < 0 || h->loco_chrom >= (int)h->msub_by_chr.size()) return sgb_fail(h, "bad chromIndex %d", h->loco_chrom);
+        double scale = 1.0 / (double)(h->M - h->msub_by_chr[h->loco_chrom]);
+        return k_sigma_diag(h, h->d_diag_loco + (int64_t)h->loco_chrom * h->N, scale, 0, d_w, tau[0], tau[1], d_out);
+    }
+    if (!h->kinDiagOne) SGB_TRY(sgb_diag_device(h));
+    return k_sigma_diag(h, h->d_diag, 1.0 / (double)h->M, h->kinDiagOne ? 1 : 0, d_w, tau[0], tau[1], d_out);
+}
+
+// Multi-RHS Jacobi-PCG.  dB, dX device [N x k]; every column reproduces the sequential recurrence of
+// getPCG1ofSigmaAndVector (FG.cpp:2593-2809) and freezes once its own ||r||^2 <= tol.
+int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const double *dB, int k, int maxiter, double tol,
+                   int loco, double *dX, int32_t *iters)
+{
+    NEED_LOADED(h);
+    if (k < 1 || k > 1024) return sgb_fail(h, "pcg: k=%d out of range", k);
+    const int64_t N = h->N;
+    // arena: R,Z,P [N*k] | Pp,KP [N*k] | dsig [N] | partA [k*PB] | partB [2*k*PB]
+    size_t need = (size_t)N * k * 5 + N + (size_t)3 * k * SGB_PART_BLOCKS;
+    SGB_TRY(ensure_f64(h, &h->d_pcg, &h->pcg_elems, need));
+    double *R = h->d_pcg, *Z = R + N * k, *P = Z + N * k, *Pp = P + N * k, *KP = Pp + N * k, *dsig = KP + N * k;
+    double *partA = dsig + N, *partB = partA + (size_t)k * SGB_PART_BLOCKS;
+    double *rz[2] = {h->d_scal + SC_PCG, h->d_scal + SC_PCG + 1024}, *r2 = h->d_scal + SC_PCG + 2048;
+    SGB_TRY(sigma_diag_device(h, d_w, tau, loco, dsig));
+    SGB_TRY(k_pcg_init(h, dB, dsig, k, dX, R, Z, P, rz[0], r2));
+    CUDA_OK(h, cudaMemcpyAsync(h->h_scal, r2, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    std::vector<int> act, it(k, 0);
+    for (int c = 0; c < k; c++) if (h->h_scal[c] > tol) act.push_back(c);
+    int cur = 0, iter = 0;
+    while (!act.empty() && iter < maxiter) {
+        iter++;
+        int na = (int)act.size();
+        CUDA_OK(h, cudaMemcpyAsync(h->d_idx, act.data(), sizeof(int) * na, cudaMemcpyHostToDevice, h->stream));
+        if (tau[1] != 0.0) {                                   // FG.cpp:2401-2404 short-circuit
+            SGB_TRY(k_gather_cols(h, P, h->d_idx, na, Pp));
+            SGB_TRY(sgb_crossprod_device(h, Pp, na, KP, loco));
+        }
+        SGB_TRY(k_pcg_step1(h, P, KP, d_w, tau[0], tau[1], h->d_idx, na, partA));
+        SGB_TRY(k_pcg_step2(h, P, KP, dsig, h->d_idx, na, dX, R, Z, rz[cur], partA, partB));
+        SGB_TRY(k_pcg_step3(h, P, Z, h->d_idx, na, rz[cur], rz[cur ^ 1], r2, partB));
+        // columns that were inactive keep their rz in both buffers: copy forward the active ones only is implicit
+        // (step3 writes rz_out for active columns); inactive columns are never read again.
+        cur ^= 1;
+        CUDA_OK(h, cudaMemcpyAsync(h->h_scal, r2, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        std::vector<int> next;
+        for (int c : act) {
+            it[c] = iter;
+            if (h->h_scal[c] > tol) next.push_back(c);
+        }
+        act.swap(next);
+    }
+    for (int c = 0; c < k; c++) { h->cnt.n_pcg_solves++; h->cnt.n_pcg_iterations += it[c]; if (iters) iters[c] = it[c]; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small host linear algebra (p x p, p = number of fixed-effect columns)
+// ---------------------------------------------------------------------------------------------------
+// arma::inv_sympd(arma::symmatu(A)) with pinv fallback (FG.cpp:3185-3190).  A column-major p x p.
+static void inv_sympd_or_pinv(std::vector<double> &A, int p)
+{
+    for (int i = 0; i < p; i++) for (int j = 0; j < i; j++) A[i + j * p] = A[j + i * p];     // symmatu
+    std::vector<double> L(A);
+    bool ok = true;
+    for (int j = 0; j < p && ok; j++) {
+        double d = L[j + j * p];
+        for (int q = 0; q < j; q++) d -= L[j + q * p] * L[j + q * p];
+        if (!(d > 0)) { ok = false; break; }
+        d = sqrt(d);
+        L[j + j * p] = d;
+        for (int i = j + 1; i < p; i++) {
+            double v = L[i + j * p];
+            for (int q = 0; q < j; q++) v -= L[i + q * p] * L[j + q * p];
+            L[i + j * p] = v / d;
+        }
+    }
+    if (ok) {
+        // inverse via forward/back substitution on the identity
+        std::vector<double> inv(p * p, 0.0);
+        for (int c = 0; c < p; c++) {
+            std::vector<double> y(p, 0.0);
+            for (int i = 0; i < p; i++) {
+                double v = (i == c) ? 1.0 : 0.0;
+                for (int q = 0; q < i; q++) v -= L[i + q * p] * y[q];
+                y[i] = v / L[i + i * p];
+            }
+            for (int i = p - 1; i >= 0; i--) {
+                double v = y[i];
+                for (int q = i + 1; q < p; q++) v -= L[q + i * p] * inv[q + c * p];
+                inv[i + c * p] = v / L[i + i * p];
+            }
+        }
+        A = inv;
+        return;
+    }
+    // pinv through cyclic Jacobi eigen-decomposition of the symmetric matrix
+    std::vector<double> S(A), V(p * p, 0.0);
+    for (int i = 0; i < p; i++) V[i + i * p] = 1.0;
+    for (int sweep = 0; sweep < 100; sweep++) {
+        double off = 0.0;
+        for (int i = 0; i < p; i++) for (int j = 0; j < p; j++) if (i != j) off += S[i + j * p] * S[i + j * p];
+        if (off < 1e-300) break;
+        for (int a = 0; a < p; a++)
+            for (int b = a + 1; b < p; b++) {
+                double apq = S[a + b * p];
+                if (fabs(apq) < 1e-300) continue;
+                double th = (S[b + b * p] - S[a + a * p]) / (2.0 * apq);
+                double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int q = 0; q < p; q++) {
+                    double x = S[q + a * p], y = S[q + b * p];
+                    S[q + a * p] = c * x - s * y; S[q + b * p] = s * x + c * y;
+                }
+                for (int q = 0; q < p; q++) {
+                    double x = S[a + q * p], y = S[b + q * p];
+                    S[a + q * p] = c * x - s * y; S[b + q * p] = s * x + c * y;
+                }
+                for (int q = 0; q < p; q++) {
+                    double x = V[q + a * p], y = V[q + b * p];
+                    V[q + a * p] = c * x - s * y; V[q + b * p] = s * x + c * y;
+                }
+            }
+    }
+    double smax = 0.0;
+    for (int i = 0; i < p; i++) smax = std::max(smax, fabs(S[i + i * p]));
+    double tolv = p * smax * 2.220446049250313e-16;          // arma::pinv default tolerance
+    std::vector<double> inv(p * p, 0.0);
+    for (int q = 0; q < p; q++) {
+        double ev = S[q + q * p];
+        if (fabs(ev) <= tolv) continue;
+        for (int i = 0; i < p; i++) for (int j = 0; j < p; j++) inv[i + j * p] += V[i + q * p] * V[j + q * p] / ev;
+    }
+    A = inv;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-call device arena + staging helpers
+// ---------------------------------------------------------------------------------------------------
+struct arena {
+    sgb_ctx *h; double *base; size_t off;
+    double *take(size_t n) { double *p = base + off; off += n; return p; }
+};
+
+static int arena_begin(sgb_ctx *h, size_t elems, arena *a)
+{
+    SGB_TRY(ensure_f64(h, &h->d_ai, &h->ai_elems, elems));
+    a->h = h; a->base = h->d_ai; a->off = 0;
+    return 0;
+}
+
+static int up(sgb_ctx *h, double *dst, const double *src, size_t n)
+{
+    CUDA_OK(h, cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    h->cnt.bytes_h2d += sizeof(double) * n;
+    return 0;
+}
+static int down(sgb_ctx *h, double *dst, const double *src, size_t n)
+{
+    CUDA_OK(h, cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    h->cnt.bytes_d2h += sizeof(double) * n;
+    return 0;
+}
+
+// out[q] = A[:,ia[q]] . B[:,ib[q]] for npairs pairs; result copied to host
+static int dots_to_host(sgb_ctx *h, const double *A, const double *B, const std::vector<int> &pairs, double *out)
+{
+    int np = (int)pairs.size() / 2;
+    if (np == 0) return 0;
+    if (np > 2048) return sgb_fail(h, "too many dot products in one batch (%d)", np);
+    SGB_TRY(sgb_ensure(h, &h->ws, &h->ws_bytes, (size_t)np * SGB_PART_BLOCKS * sizeof(double)));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_idx, pairs.data(), sizeof(int) * pairs.size(), cudaMemcpyHostToDevice, h->stream));
+    SGB_TRY(k_pair_dots(h, A, h->N, B, h->N, h->d_idx, np, h->d_scal + SC_COLSUM));
+    CUDA_OK(h, cudaMemcpyAsync(h->h_scal, h->d_scal + SC_COLSUM, sizeof(double) * np, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_scal, sizeof(double) * np);
+    return 0;
+}
+
+// C = cov * V   (p x p times p x n, column-major)
+static std::vector<double> matmul_pp(const std::vector<double> &cov, int p, const double *V, int n)
+{
+    std::vector<double> C((size_t)p * n, 0.0);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < p; i++) {
+            double s = 0.0;
+            for (int q = 0; q < p; q++) s += cov[i + q * p] * V[q + (size_t)j * p];
+            C[i + (size_t)j * p] = s;
+        }
+    return C;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI: products, PCG
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sgb_get_diag_of_kin(sgb_ctx *h, double *out)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (h->kinDiagOne) { for (int64_t i = 0; i < h->N; i++) out[i] = 1.0; return 0; }      // FG.cpp:4372
+    SGB_TRY(sgb_diag_device(h));
+    SGB_TRY(down(h, out, h->d_diag, h->N));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < h->N; i++) out[i] /= (double)h->M;
+    return 0;
+}
+
+extern "C" int sgb_set_diag_of_stdgeno_loco(sgb_ctx *h)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    SGB_TRY(sgb_diag_loco_device(h));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int crossprod_host(sgb_ctx *h, const double *B, int k, double *Y, int loco)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (k < 1) return sgb_fail(h, "crossprod: k must be >= 1");
+    SGB_TRY(ensure_f64(h, &h->d_io, &h->io_elems, (size_t)h->N * k));
+    SGB_TRY(up(h, h->d_io, B, (size_t)h->N * k));
+    SGB_TRY(sgb_crossprod_device(h, h->d_io, k, h->d_io, loco));
+    SGB_TRY(down(h, Y, h->d_io, (size_t)h->N * k));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int sgb_get_crossprod_mat_and_kin(sgb_ctx *h, const double *B, int k, double *Y) { return crossprod_host(h, B, k, Y, 0); }
+extern "C" int sgb_get_crossprod_mat_and_kin_loco(sgb_ctx *h, const double *B, int k, double *Y) { return crossprod_host(h, B, k, Y, 1); }
+
+extern "C" int sgb_get_diag_of_sigma(sgb_ctx *h, const double *w, const double *tau, int loco, double *out)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    arena a;
+    SGB_TRY(arena_begin(h, (size_t)2 * h->N, &a));
+    double *dw = a.take(h->N), *dd = a.take(h->N);
+    SGB_TRY(up(h, dw, w, h->N));
+    SGB_TRY(sigma_diag_device(h, dw, tau, loco, dd));
+    SGB_TRY(down(h, out, dd, h->N));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int sgb_get_crossprod(sgb_ctx *h, const double *B, int k, const double *w, const double *tau, int loco, double *Y)
+{
+    NEED_LOADED(h);
+    // getCrossprod (FG.cpp:2397-2425): tau0 * b/w + tau1 * K b, short-circuit when tau1 == 0
+    if (tau[1] != 0.0) SGB_TRY(crossprod_host(h, B, k, Y, loco));
+    for (int c = 0; c < k; c++)
+        for (int64_t i = 0; i < h->N; i++) {
+            size_t o = (size_t)c * h->N + i;
+            double v = tau[0] * (B[o] * (1.0 / w[i]));
+            Y[o] = tau[1] != 0.0 ? v + tau[1] * Y[o] : v;
+        }
+    return 0;
+}
+
+extern "C" int sgb_get_pcg1_of_sigma_and_vector(sgb_ctx *h, const double *w, const double *tau, const double *B, int k,
+                                                int maxiterPCG, double tolPCG, int loco, double *X, int32_t *iters_out)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (k < 1) return sgb_fail(h, "pcg: k must be >= 1");
+    arena a;
+    SGB_TRY(arena_begin(h, (size_t)h->N * (2 * k + 1), &a));
+    double *dw = a.take(h->N), *dB = a.take((size_t)h->N * k), *dX = a.take((size_t)h->N * k);
+    SGB_TRY(up(h, dw, w, h->N));
+    SGB_TRY(up(h, dB, B, (size_t)h->N * k));
+    SGB_TRY(sgb_pcg_device(h, dw, tau, dB, k, maxiterPCG, tolPCG, loco, dX, iters_out));
+    SGB_TRY(down(h, X, dX, (size_t)h->N * k));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int sgb_get_sigma_x(sgb_ctx *h, const double *w, const double *tau, const double *X, int p, int maxiterPCG,
+                               double tolPCG, int loco, double *Sigma_iX)
+{
+    return sgb_get_pcg1_of_sigma_and_vector(h, w, tau, X, p, maxiterPCG, tolPCG, loco, Sigma_iX, nullptr);
+}
+extern "C" int sgb_get_sigma_g(sgb_ctx *h, const double *w, const double *tau, const double *Gm, int k, int maxiterPCG,
+                               double tolPCG, int loco, double *Sigma_iG)
+{
+    return sgb_get_pcg1_of_sigma_and_vector(h, w, tau, Gm, k, maxiterPCG, tolPCG, loco, Sigma_iG, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI: AI-REML
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sgb_get_coefficients(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, const double *tau,
+                                    int maxiterPCG, double tolPCG, int loco, double *Sigma_iY, double *Sigma_iX,
+                                    double *cov, double *alpha, double *eta)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (p < 1 || p > 30) return sgb_fail(h, "getCoefficients: p=%d out of range [1,30]", p);
+    const int64_t N = h->N;
+    arena a;
+    SGB_TRY(arena_begin(h, (size_t)N * (2 * (1 + p) + 2) + 64, &a));
+    double *dw = a.take(N), *dYX = a.take((size_t)N * (1 + p)), *dS = a.take((size_t)N * (1 + p)), *deta = a.take(N), *dal = a.take(64);
+    SGB_TRY(up(h, dw, w, N));
+    SGB_TRY(up(h, dYX, Y, N));
+    SGB_TRY(up(h, dYX + N, X, (size_t)N * p));
+    // Sigma^-1 [Y | X] as ONE (1+p)-column solve (the reference runs 1+p sequential solves, FG.cpp:3171-3178)
+    SGB_TRY(sgb_pcg_device(h, dw, tau, dYX, 1 + p, maxiterPCG, tolPCG, loco, dS, nullptr));
+    // X^T Sigma_iX (p x p) and Sigma_iX^T Y (p)
+    std::vector<int> pairs;
+    for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) { pairs.push_back(1 + i); pairs.push_back(1 + j); }   // X_i . SiX_j
+    for (int i = 0; i < p; i++) { pairs.push_back(0); pairs.push_back(1 + i); }                                   // Y . SiX_i
+    std::vector<double> d(pairs.size() / 2);
+    SGB_TRY(dots_to_host(h, dYX, dS, pairs, d.data()));
+    std::vector<double> covm(d.begin(), d.begin() + p * p);
+    inv_sympd_or_pinv(covm, p);
+    std::vector<double> al = matmul_pp(covm, p, d.data() + p * p, 1);
+    SGB_TRY(up(h, dal, al.data(), p));
+    SGB_TRY(k_eta(h, dYX, dS, dS + N, p, dal, dw, tau[0], deta));
+    SGB_TRY(down(h, Sigma_iY, dS, N));
+    SGB_TRY(down(h, Sigma_iX, dS + N, (size_t)N * p));
+    SGB_TRY(down(h, eta, deta, N));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    memcpy(cov, covm.data(), sizeof(double) * p * p);
+    memcpy(alpha, al.data(), sizeof(double) * p);
+    return 0;
+}
+
+// Shared body of getAIScore / getAIScore_q.  out: YPAPY, YPA0PY, Trace0, Trace1, AI00, AI01, AI11, nrun used.
+static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *X, int p, const double *w, const double *tau,
+                         const double *Sigma_iY, const double *Sigma_iX, const double *cov_in, int nrun, int maxiterPCG,
+                         double tolPCG, double traceCVcutoff, sgb_probe_fn probes, void *user, double *out8, double *PY_out)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (p < 1 || p > 30) return sgb_fail(h, "getAIScore: p=%d out of range [1,30]", p);
+    if (nrun < 2 || nrun > 500) return sgb_fail(h, "getAIScore: nrun=%d out of range [2,500]", nrun);
+    if (!probes) return sgb_fail(h, "getAIScore: probe callback is NULL (probes are drawn by the caller's RNG)");
+    const int64_t N = h->N;
+    const int kb = std::max(nrun, 10) + 2;         // widest batch: [U | APY | PY]
+    arena a;
+    SGB_TRY(arena_begin(h, (size_t)N * (2 + 2 * p + 4 * kb) + 4096, &a));
+    double *dw = a.take(N), *dY = a.take(N), *dX = a.take((size_t)N * p), *dSiX = a.take((size_t)N * p);
+    double *dB = a.take((size_t)N * kb);           // right-hand sides   [PY | U...] then [U... | APY | PY]
+    double *dK = a.take((size_t)N * kb);           // K.[PY | U...]
+    double *dS = a.take((size_t)N * kb);           // Sigma^-1 [...]
+    double *dPr = a.take((size_t)N * kb);          // projected
+    double *dC = a.take(4096);
+    SGB_TRY(up(h, dw, w, N));
+    SGB_TRY(up(h, dY, Y, N));
+    SGB_TRY(up(h, dX, X, (size_t)N * p));
+    SGB_TRY(up(h, dSiX, Sigma_iX, (size_t)N * p));
+    SGB_TRY(up(h, dB, Sigma_iY, N));               // dB[:,0] = Sigma_iY for now
+    std::vector<double> covm(cov_in, cov_in + p * p);
+    std::vector<int> pairs;
+    std::vector<double> d;
+    if (quant) {                                   // getAIScore_q recomputes cov from X^T Sigma_iX (FG.cpp:3488-3494)
+        pairs.clear();
+        for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) { pairs.push_back(i); pairs.push_back(j); }
+        d.resize(p * p);
+        SGB_TRY(dots_to_host(h, dX, dSiX, pairs, d.data()));
+        covm.assign(d.begin(), d.end());
+        inv_sympd_or_pinv(covm, p);
+    }
+    // PY = Sigma_iY - Sigma_iX (cov (Sigma_iX^T Y))                                  FG.cpp:3284
+    pairs.clear();
+    for (int i = 0; i < p; i++) { pairs.push_back(i); pairs.push_back(0); }
+    d.resize(p);
+    SGB_TRY(dots_to_host(h, dSiX, dY, pairs, d.data()));
+    std::vector<double> C = matmul_pp(covm, p, d.data(), 1);
+    SGB_TRY(up(h, dC, C.data(), p));
+    SGB_TRY(k_project(h, dB, dSiX, p, dC, 1, dB));            // dB[:,0] = PY
+    SGB_TRY(down(h, PY_out, dB, N));
+
+    std::vector<double> t1, t0;
+    double YPAPY = 0, YPA0PY = 0, AI00 = 0, AI01 = 0, AI11 = 0;
+    int nstart = 0, nend = nrun;
+    std::vector<double> hostU;
+    bool first = true;
+    while (true) {
+        const int nu = nend - nstart;
+        hostU.resize((size_t)N * nu);
+        if (probes(user, N, nu, hostU.data())) return sgb_fail(h, "getAIScore: probe callback failed");
+        if (first) {
+            // ---- one (1+nu)-column product K.[PY | U] ----                        FG.cpp:3285, 3140
+            SGB_TRY(up(h, dB + N, hostU.data(), (size_t)N * nu));
+            SGB_TRY(sgb_crossprod_device(h, dB, 1 + nu, dK, 0));
+            pairs.assign({0, 0});
+            if (quant) { pairs.push_back(0); pairs.push_back(0); }
+            double dd[2];
+            SGB_TRY(dots_to_host(h, dB, dK, pairs, dd));      // PY . APY
+            YPAPY = dd[0];
+            if (quant) {
+                pairs.assign({0, 0});
+                SGB_TRY(dots_to_host(h, dB, dB, pairs, dd));  // PY . PY (A0 = I)             FG.cpp:3499-3500
+                YPA0PY = dd[0];
+            }
+            // ---- right-hand sides of the batched solve: [U | APY | (PY)] ----
+            // dB currently [PY | U]; build dS-input in dPr: [U | APY | PY]
+            CUDA_OK(h, cudaMemcpyAsync(dPr, dB + N, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
+            CUDA_OK(h, cudaMemcpyAsync(dPr + (size_t)N * nu, dK, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
+            int ks = nu + 1;
+            if (quant) { CUDA_OK(h, cudaMemcpyAsync(dPr + (size_t)N * (nu + 1), dB, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream)); ks++; }
+            SGB_TRY(sgb_pcg_device(h, dw, tau, dPr, ks, maxiterPCG, tolPCG, 0, dS, nullptr));     // FG.cpp:3138, 3290
+            // coefficients of the projections
+            //   probes : Sigma_iX^T u            (FG.cpp:3139)
+            //   APY/PY : Sigma_iX^T (Sigma^-1 v) (FG.cpp:3291 -- the reference projects the SOLVED vector here)
+            pairs.clear();
+            for (int j = 0; j < nu; j++) for (int i = 0; i < p; i++) { pairs.push_back(i); pairs.push_back(j); }
+            d.resize((size_t)p * ks);
+            SGB_TRY(dots_to_host(h, dSiX, dPr, pairs, d.data()));
+            pairs.clear();
+            for (int j = nu; j < ks; j++) for (int i = 0; i < p; i++) { pairs.push_back(i); pairs.push_back(j); }
+            SGB_TRY(dots_to_host(h, dSiX, dS, pairs, d.data() + (size_t)p * nu));
+            C = matmul_pp(covm, p, d.data(), ks);
+            if ((size_t)p * ks > 4096) return sgb_fail(h, "getAIScore: p*nrun too large");
+            SGB_TRY(up(h, dC, C.data(), (size_t)p * ks));
+            SGB_TRY(k_project(h, dS, dSiX, p, dC, ks, dS));   // dS = [Pu... | PAPY | PA0PY]
+            // traces: Au.Pu (and u.Pu);  AI entries
+            pairs.clear();
+            for (int j = 0; j < nu; j++) { pairs.push_back(1 + j); pairs.push_back(j); }        // dK[:,1+j] . dS[:,j]
+            d.resize(nu);
+            SGB_TRY(dots_to_host(h, dK, dS, pairs, d.data()));
+            t1.insert(t1.end(), d.begin(), d.end());
+            if (quant) {
+                pairs.clear();
+                for (int j = 0; j < nu; j++) { pairs.push_back(j); pairs.push_back(j); }        // u . Pu
+                SGB_TRY(dots_to_host(h, dPr, dS, pairs, d.data()));
+                t0.insert(t0.end(), d.begin(), d.end());
+            }
+            pairs.assign({0, nu});                                                                // APY . PAPY
+            double ai[3];
+            SGB_TRY(dots_to_host(h, dK, dS, pairs, ai));
+            AI11 = ai[0];
+            if (quant) {
+                pairs.assign({0, nu, 0, nu + 1});                                                 // A0PY.PAPY , A0PY.PA0PY
+                SGB_TRY(dots_to_host(h, dB, dS, pairs, ai));
+                AI01 = ai[0]; AI00 = ai[1];
+            }
+            first = false;
+        } else {
+            // ---- 10 more probes (FG.cpp:3148-3153) ----
+            SGB_TRY(up(h, dPr, hostU.data(), (size_t)N * nu));
+            SGB_TRY(sgb_crossprod_device(h, dPr, nu, dK, 0));
+            SGB_TRY(sgb_pcg_device(h, dw, tau, dPr, nu, maxiterPCG, tolPCG, 0, dS, nullptr));
+            pairs.clear();
+            for (int j = 0; j < nu; j++) for (int i = 0; i < p; i++) { pairs.push_back(i); pairs.push_back(j); }
+            d.resize((size_t)p * nu);
+            SGB_TRY(dots_to_host(h, dSiX, dPr, pairs, d.data()));
+            C = matmul_pp(covm, p, d.data(), nu);
+            SGB_TRY(up(h, dC, C.data(), (size_t)p * nu));
+            SGB_TRY(k_project(h, dS, dSiX, p, dC, nu, dS));
+            pairs.clear();
+            for (int j = 0; j < nu; j++) { pairs.push_back(j); pairs.push_back(j); }
+            d.resize(nu);
+            SGB_TRY(dots_to_host(h, dK, dS, pairs, d.data()));
+            t1.insert(t1.end(), d.begin(), d.end());
+            if (quant) {
+                SGB_TRY(dots_to_host(h, dPr, dS, pairs, d.data()));
+                t0.insert(t0.end(), d.begin(), d.end());
+            }
+        }
+        double cv1 = sgb_cal_cv(t1.data(), (int)t1.size());
+        double cv0 = quant ? sgb_cal_cv(t0.data(), (int)t0.size()) : 0.0;
+        if (cv1 > traceCVcutoff || cv0 > traceCVcutoff) {
+            nstart = nend; nend += 10;
+            if (nend - nstart > kb) return sgb_fail(h, "internal: probe batch larger than arena");
+            if (nend > 2000) return sgb_fail(h, "getAIScore: trace estimator did not reach CV cutoff within 2000 probes");
+        } else break;
+    }
+    double m1 = 0, m0 = 0;
+    for (double v : t1) m1 += v;
+    m1 /= (double)t1.size();
+    if (quant) { for (double v : t0) m0 += v; m0 /= (double)t0.size(); }
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    out8[0] = YPAPY; out8[1] = YPA0PY; out8[2] = m0; out8[3] = m1; out8[4] = AI00; out8[5] = AI01; out8[6] = AI11;
+    out8[7] = (double)nend;
+    return 0;
+}
+
+extern "C" int sgb_get_ai_score(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, const double *tau,
+                                const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun, int maxiterPCG,
+                                double tolPCG, double traceCVcutoff, sgb_probe_fn probes, void *user, double *out4, double *PY)
+{
+    double o[8];
+    SGB_TRY(ai_score_impl(h, false, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, o, PY));
+    out4[0] = o[0]; out4[1] = o[3]; out4[2] = o[6]; out4[3] = o[7];
+    return 0;
+}
+
+extern "C" int sgb_get_ai_score_q(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, const double *tau,
+                                  const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun, int maxiterPCG,
+                                  double tolPCG, double traceCVcutoff, sgb_probe_fn probes, void *user, double *out8, double *PY)
+{
+    return ai_score_impl(h, true, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, out8, PY);
+}
+
+// fitglmmaiRPCG (FG.cpp:3302-3341)
+extern "C" int sgb_fit_glmmai_rpcg(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, double *tau,
+                                   const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun, int maxiterPCG,
+                                   double tolPCG, double tol, double traceCVcutoff, sgb_probe_fn probes, void *user)
+{
+    std::vector<double> PY(h->N > 0 ? h->N : 1);
+    double o[8];
+    SGB_TRY(ai_score_impl(h, false, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, o, PY.data()));
+    double score1 = o[0] - o[3], AI1 = o[6];
+    double Dtau = score1 / AI1;
+    double tau0[2] = {tau[0], tau[1]};
+    tau[1] = tau0[1] + Dtau;
+    for (int i = 0; i < 2; i++) if (tau[i] < tol) tau[i] = 0;
+    double step = 1.0;
+    while (tau[1] < 0.0) { step *= 0.5; tau[1] = tau0[1] + step * Dtau; }
+    for (int i = 0; i < 2; i++) if (tau[i] < tol) tau[i] = 0;
+    return 0;
+}
+
+// fitglmmaiRPCG_q (FG.cpp:3610-3662)
+extern "C" int sgb_fit_glmmai_rpcg_q(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, double *tau,
+                                     const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun, int maxiterPCG,
+                                     double tolPCG, double tol, double traceCVcutoff, sgb_probe_fn probes, void *user)
+{
+    std::vector<double> PY(h->N > 0 ? h->N : 1);
+    double o[8];
+    bool zero[2] = {tau[0] < tol, tau[1] < tol};
+    SGB_TRY(ai_score_impl(h, true, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, o, PY.data()));
+    double s0 = o[1] - o[2], s1 = o[0] - o[3];
+    double a00 = o[4], a01 = o[5], a11 = o[6];
+    double det = a00 * a11 - a01 * a01;
+    if (det == 0.0 || !std::isfinite(det)) return sgb_fail(h, "fitglmmaiRPCG_q: singular AI matrix");
+    double D0 = (a11 * s0 - a01 * s1) / det, D1 = (-a01 * s0 + a00 * s1) / det;     // solve(AI, score)
+    double tau0[2] = {tau[0], tau[1]};
+    tau[0] = tau0[0] + D0; tau[1] = tau0[1] + D1;
+    for (int i = 0; i < 2; i++) if (zero[i] && tau[i] < tol) tau[i] = 0;
+    double step = 1.0;
+    while (tau[0] < 0.0 || tau[1] < 0.0) {
+        step *= 0.5;
+        tau[0] = tau0[0] + step * D0; tau[1] = tau0[1] + step * D1;
+        for (int i = 0; i < 2; i++) if (zero[i] && tau[i] < tol) tau[i] = 0;
+    }
+    for (int i = 0; i < 2; i++) if (tau[i] < tol) tau[i] = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device-resident benchmark hook
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sgb_bench_crossprod_device(sgb_ctx *h, int k, int reps, uint64_t seed, float *ms_out, float *ms_kernel_out)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    const int64_t N = h->N;
+    SGB_TRY(ensure_f64(h, &h->d_bench, &h->bench_elems, (size_t)2 * N * k));
+    double *dB = h->d_bench, *dY = dB + (size_t)N * k;
+    SGB_TRY(k_rademacher_fill(h, dB, N * k, seed));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int r = 0; r < reps; r++) {
+        h->time_sweeps = (r == reps - 1);
+        CUDA_OK(h, cudaEventRecord(e0, h->stream));
+        int rc = sgb_crossprod_device(h, dB, k, dY, 0);
+        if (rc) { h->time_sweeps = false; cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        CUDA_OK(h, cudaEventRecord(e1, h->stream));
+        CUDA_OK(h, cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&ms_out[r], e0, e1);
+    }
+    h->time_sweeps = false;
+    if (ms_kernel_out) { ms_kernel_out[0] = h->last_sweep_ms[0]; ms_kernel_out[1] = h->last_sweep_ms[1]; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+extern "C" int sgb_bench_fetch_result(sgb_ctx *h, int k, double *Y, double *B)
+{
+    NEED_LOADED(h);
+    const int64_t N = h->N;
+    if (!h->d_bench || h->bench_elems < (size_t)2 * N * k) return sgb_fail(h, "no benchmark result of that width");
+    if (B) SGB_TRY(down(h, B, h->d_bench, (size_t)N * k));
+    if (Y) SGB_TRY(down(h, Y, h->d_bench + (size_t)N * k, (size_t)N * k));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}

@@ -1,0 +1,523 @@
+// Context life cycle and the packed-genotype store: the B200 replacement of genoClass (FG.cpp:37-1183).
+//
+// Ingest pipeline (setgeno, FG.cpp:739-1024): raw PLINK rows are streamed to the GPU in chunks; a count kernel
+// produces per-marker allele/missing counts over the phenotyped samples; the QC decision is then taken on the host
+// in fp32 with the reference's exact expression order (FG.cpp:438-493) so boundary markers cannot flip; kept
+// markers owned by this rank are re-packed on the GPU (sample gather + best-guess imputation) straight into the
+// marker-major device store; the sample-major copy used by the second sweep is produced by a transpose kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <fstream>
+#include <string>
+#include <vector>
+#include "sgb_internal.h"
+
+static std::string g_create_error;
+
+int sgb_fail(sgb_ctx *h, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+extern "C" const char *sgb_last_error(sgb_ctx *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int sgb_ensure(sgb_ctx *h, void **p, size_t *cur, size_t need)
+{
+    if (*cur >= need && *p) return 0;
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    if (*p) CUDA_OK(h, cudaFree(*p));
+    *p = nullptr; *cur = 0;
+    size_t want = need + need / 8 + 256;
+    CUDA_OK(h, cudaMalloc(p, want));
+    *cur = want;
+    return 0;
+}
+
+static int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+static int create_common(int device, sgb_ctx **out)
+{
+    if (!out) return sgb_fail(nullptr, "sgb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return sgb_fail(nullptr, "sgb_create: no CUDA device available (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return sgb_fail(nullptr, "sgb_create: device %d out of range (0..%d)", device, ndev - 1);
+    sgb_ctx *h = new sgb_ctx();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return sgb_fail(nullptr, "cudaSetDevice(%d) failed", device); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 8) { delete h; return sgb_fail(nullptr, "device %d (sm_%d%d) is not supported; built for sm_100a", device, prop.major, prop.minor); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return sgb_fail(nullptr, "cudaStreamCreate failed"); }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    if (cudaMalloc((void **)&h->d_scal, sizeof(double) * 8192) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_idx, sizeof(int) * 8192) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_scal, sizeof(double) * 8192) != cudaSuccess) {
+        delete h;
+        return sgb_fail(nullptr, "scalar scratch allocation failed");
+    }
+    h->ws_bytes = 0;
+    if (sgb_ensure(h, &h->ws, &h->ws_bytes, (size_t)8 << 20)) { std::string m = h->err; delete h; return sgb_fail(nullptr, "%s", m.c_str()); }
+    *out = h;
+    return 0;
+}
+
+extern "C" int sgb_create(int device, sgb_ctx **out) { return create_common(device, out); }
+
+extern "C" int sgb_create_dist(int device, int rank, int world, const void *id128, sgb_ctx **out)
+{
+    SGB_TRY(create_common(device, out));
+    (*out)->rank = 0; (*out)->world = 1;
+    if (world > 1) {
+        int rc = sgb_dist_init(*out, rank, world, id128);
+        if (rc) { g_create_error = (*out)->err; sgb_destroy(*out); *out = nullptr; return rc; }
+    }
+    return 0;
+}
+
+extern "C" int sgb_nccl_unique_id(void *id128)
+{
+    std::string err;
+    int rc = sgb_dist_unique_id(id128, err);
+    if (rc) g_create_error = err;
+    return rc;
+}
+
+static void free_store(sgb_ctx *h)
+{
+    cudaSetDevice(h->device);
+    void **ptrs[] = {(void **)&h->dG, (void **)&h->dGt, (void **)&h->d_f2, (void **)&h->d_s, (void **)&h->d_s2,
+                     (void **)&h->d_diag, (void **)&h->d_diag_loco};
+    for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    h->loaded = false; h->diag_ready = false; h->diag_loco_ready = false;
+    h->Mloc = h->M = h->Mvr = 0;
+}
+
+extern "C" void sgb_destroy(sgb_ctx *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    sgb_dist_destroy(h);
+    free_store(h);
+    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx};
+    for (auto p : ptrs) if (p) cudaFree(p);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int sgb_set_engine(sgb_ctx *h, int engine)
+{
+    if (engine != SGB_ENGINE_TENSOR && engine != SGB_ENGINE_F64) return sgb_fail(h, "unknown engine %d", engine);
+    h->engine = engine;
+    h->diag_ready = false; h->diag_loco_ready = false;
+    return 0;
+}
+extern "C" int sgb_device_sync(sgb_ctx *h) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaStreamSynchronize(h->stream)); return 0; }
+extern "C" int sgb_set_min_maf_for_grm(sgb_ctx *h, float v) { h->minMAF = v; return 0; }
+extern "C" int sgb_set_max_missing_rate_for_grm(sgb_ctx *h, float v) { h->maxMissing = v; return 0; }
+extern "C" int sgb_set_min_mac_variance_ratio(sgb_ctx *h, float mn, float mx, int is)
+{
+    h->minMACvr = mn; h->maxMACvr = mx; h->isVarRatio = is != 0;
+    return 0;
+}
+
+// ---- QC decision for one marker, fp32, reference expression order (FG.cpp:438-548) ----------------
+struct qc_out { int ac; int mac; int fill; float afreq, invstd; bool passQC, passVR; };
+
+static qc_out qc_marker(const sgb_ctx *h, int64_t N, int alleleCount, int numMissing, bool in_vr_set)
+{
+    qc_out o;
+    float altFreq = alleleCount / float((N - numMissing) * 2);
+    float missingRate = numMissing / float(N);
+    o.fill = int(roundf(2 * altFreq));
+    if (numMissing > 0) alleleCount = alleleCount + o.fill * numMissing;
+    altFreq = alleleCount / float(N * 2);
+    float maf = std::min(altFreq, 1 - altFreq);
+    o.mac = std::min(alleleCount, int(N) * 2 - alleleCount);
+    o.passQC = (maf >= h->minMAF && missingRate <= h->maxMissing);
+    o.passVR = false;
+    if (h->isVarRatio) {
+        if (h->maxMACvr != -1) {
+            if (o.mac >= h->minMACvr && o.mac < h->maxMACvr) o.passVR = true;
+            else if (o.mac >= h->maxMACvr) o.passVR = in_vr_set;
+        } else if (o.mac >= h->minMACvr) o.passVR = in_vr_set;
+        if (o.passVR) o.passQC = false;
+    }
+    float Std = sqrtf(2 * altFreq * (1 - altFreq));
+    o.invstd = (Std == 0) ? 0.f : 1 / Std;
+    o.afreq = altFreq; o.ac = alleleCount;
+    return o;
+}
+
+static bool owns(const sgb_ctx *h, int64_t gidx) { return (gidx / SGB_SHARD_BLOCK) % h->world == h->rank; }
+
+// allocate the device store for Mloc local markers and upload the per-marker fp64 constants
+static int alloc_store(sgb_ctx *h)
+{
+    h->sG = round_up((h->N + 3) / 4, SGB_KSTEP_BYTES);
+    h->rowsG = round_up(std::max<int64_t>(h->Mloc, 1), SGB_ROW_ALIGN);
+    h->sT = round_up((h->rowsG + 3) / 4, SGB_KSTEP_BYTES);
+    h->rowsT = round_up(h->N, SGB_ROW_ALIGN);
+    CUDA_OK(h, cudaMalloc((void **)&h->dG, (size_t)h->rowsG * h->sG));
+    CUDA_OK(h, cudaMalloc((void **)&h->dGt, (size_t)h->rowsT * h->sT));
+    CUDA_OK(h, cudaMemsetAsync(h->dG, 0, (size_t)h->rowsG * h->sG, h->stream));
+    CUDA_OK(h, cudaMemsetAsync(h->dGt, 0, (size_t)h->rowsT * h->sT, h->stream));
+    CUDA_OK(h, cudaMalloc((void **)&h->d_f2, sizeof(double) * h->rowsG));
+    CUDA_OK(h, cudaMalloc((void **)&h->d_s, sizeof(double) * h->rowsG));
+    CUDA_OK(h, cudaMalloc((void **)&h->d_s2, sizeof(double) * h->rowsG));
+    CUDA_OK(h, cudaMalloc((void **)&h->d_diag, sizeof(double) * h->N));
+    std::vector<double> f2(h->rowsG, 0.0), s(h->rowsG, 0.0), s2(h->rowsG, 0.0);
+    for (int64_t r = 0; r < h->Mloc; r++) {
+        // fp64 definitions the GPU path is graded on (DESIGN.md "parity definition"): exact integer allele count
+        double f = (double)h->ac[h->loc2glob[r]] / (double)(2 * h->N);
+        double v = 2.0 * f * (1.0 - f);
+        f2[r] = 2.0 * f;
+        s[r] = v > 0 ? 1.0 / sqrt(v) : 0.0;
+        s2[r] = s[r] * s[r];
+    }
+    CUDA_OK(h, cudaMemcpyAsync(h->d_f2, f2.data(), sizeof(double) * h->rowsG, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_s, s.data(), sizeof(double) * h->rowsG, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_s2, s2.data(), sizeof(double) * h->rowsG, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->cnt.bytes_h2d += 3 * sizeof(double) * h->rowsG;
+    return 0;
+}
+
+struct chunk_reader {     // yields raw marker rows [m0, m1) either from memory or from a .bed file
+    const uint8_t *mem = nullptr;
+    FILE *fp = nullptr;
+    int64_t B0 = 0;
+    std::vector<uint8_t> buf;
+    const uint8_t *get(int64_t m0, int64_t m1)
+    {
+        if (mem) return mem + m0 * B0;
+        buf.resize((size_t)(m1 - m0) * B0);
+        if (fseeko(fp, 3 + (off_t)m0 * B0, SEEK_SET)) return nullptr;                     // FG.cpp:902
+        if (fread(buf.data(), 1, buf.size(), fp) != buf.size()) return nullptr;
+        return buf.data();
+    }
+};
+
+static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, const int32_t *sub, int64_t N,
+                        const uint8_t *indicator, int diagOne, const int32_t *vr_idx, int64_t n_vr)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    free_store(h);
+    if (N <= 0 || N0 <= 0 || M0 < 0) return sgb_fail(h, "setgeno: bad dimensions N0=%lld M0=%lld N=%lld", (long long)N0, (long long)M0, (long long)N);
+    h->kinDiagOne = diagOne != 0;
+    h->N0 = N0; h->M0 = M0; h->N = N;
+    const int64_t B0 = (N0 + 3) / 4, B = (N + 3) / 4;
+    bool identity = (N == N0);
+    for (int64_t k = 0; k < N; k++) {
+        if (sub[k] < 1 || sub[k] > N0) return sgb_fail(h, "setgeno: subSampleInGeno[%lld]=%d out of range", (long long)k, sub[k]);
+        if (sub[k] != k + 1) identity = false;
+    }
+    std::vector<uint8_t> indmask(B0, 0), in_vr(M0 + 1, 0);
+    for (int64_t i = 0; i < N0; i++) if (indicator[i]) indmask[i >> 2] |= (uint8_t)(1u << ((i & 3) << 1));
+    for (int64_t j = 0; j < n_vr; j++) if (vr_idx[j] >= 0 && vr_idx[j] < M0) in_vr[vr_idx[j]] = 1;
+
+    uint8_t *d_indmask = nullptr; int32_t *d_sub = nullptr;
+    CUDA_OK(h, cudaMalloc((void **)&d_indmask, B0));
+    CUDA_OK(h, cudaMalloc((void **)&d_sub, sizeof(int32_t) * N));
+    CUDA_OK(h, cudaMemcpy(d_indmask, indmask.data(), B0, cudaMemcpyHostToDevice));
+    CUDA_OK(h, cudaMemcpy(d_sub, sub, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+
+    // ---- pass 1: counts for every raw marker ----
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(M0, ((int64_t)256 << 20) / B0));
+    uint8_t *d_raw = nullptr; int32_t *d_ac = nullptr, *d_nm = nullptr;
+    CUDA_OK(h, cudaMalloc((void **)&d_raw, (size_t)chunk * B0));
+    CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * chunk));
+    CUDA_OK(h, cudaMalloc((void **)&d_nm, sizeof(int32_t) * chunk));
+    std::vector<int32_t> ac_raw(M0), nm_raw(M0);
+    for (int64_t m0 = 0; m0 < M0; m0 += chunk) {
+        int64_t m1 = std::min(M0, m0 + chunk);
+        const uint8_t *src = rd.get(m0, m1);
+        if (!src) return sgb_fail(h, "setgeno: short read of .bed at marker %lld", (long long)m0);
+        CUDA_OK(h, cudaMemcpyAsync(d_raw, src, (size_t)(m1 - m0) * B0, cudaMemcpyHostToDevice, h->stream));
+        h->cnt.bytes_h2d += (m1 - m0) * B0;
+        SGB_TRY(k_count_markers(h, d_raw, B0, m1 - m0, d_indmask, d_ac, d_nm));
+        CUDA_OK(h, cudaMemcpyAsync(ac_raw.data() + m0, d_ac, sizeof(int32_t) * (m1 - m0), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaMemcpyAsync(nm_raw.data() + m0, d_nm, sizeof(int32_t) * (m1 - m0), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
+
+    // ---- host QC (fp32, reference order) ----
+    h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
+    h->afreq_vr.clear(); h->invstd_vr.clear(); h->mac_vr.clear(); h->ac_vr.clear(); h->index_vr.clear();
+    h->qc_mask.assign(M0, 0); h->loc2glob.clear();
+    std::vector<int32_t> fill_raw(M0, 0);
+    std::vector<int8_t> kind(M0, 0);      // 1 = GRM store, 2 = VR store
+    for (int64_t m = 0; m < M0; m++) {
+        qc_out q = qc_marker(h, N, ac_raw[m], nm_raw[m], in_vr[m] != 0);
+        fill_raw[m] = q.fill;
+        if (q.passQC) {
+            int64_t gidx = (int64_t)h->afreq.size();
+            h->afreq.push_back(q.afreq); h->invstd.push_back(q.invstd); h->mac.push_back(q.mac); h->ac.push_back(q.ac);
+            h->qc_mask[m] = 1; kind[m] = 1;
+            if (owns(h, gidx)) h->loc2glob.push_back(gidx);
+        }
+        if (h->isVarRatio && q.passVR) {
+            h->afreq_vr.push_back(q.afreq); h->invstd_vr.push_back(q.invstd); h->mac_vr.push_back(q.mac); h->ac_vr.push_back(q.ac);
+            h->index_vr.push_back((int32_t)m); kind[m] = 2;
+        }
+    }
+    h->M = (int64_t)h->afreq.size();
+    h->Mvr = (int64_t)h->index_vr.size();
+    h->Mloc = (int64_t)h->loc2glob.size();
+    SGB_TRY(alloc_store(h));
+    h->vr_packed.assign((size_t)h->Mvr * B, 0);
+
+    // ---- pass 2: re-pack kept rows ----
+    uint8_t *d_vr = nullptr; int32_t *d_rows = nullptr, *d_fill = nullptr;
+    CUDA_OK(h, cudaMalloc((void **)&d_rows, sizeof(int32_t) * chunk));
+    CUDA_OK(h, cudaMalloc((void **)&d_fill, sizeof(int32_t) * chunk));
+    int64_t gidx = 0, lrow = 0, vrow = 0;
+    std::vector<int32_t> rows, fills, vrows, vfills;
+    for (int64_t m0 = 0; m0 < M0; m0 += chunk) {
+        int64_t m1 = std::min(M0, m0 + chunk);
+        rows.clear(); fills.clear(); vrows.clear(); vfills.clear();
+        for (int64_t m = m0; m < m1; m++) {
+            if (kind[m] == 1) { if (owns(h, gidx)) { rows.push_back((int32_t)(m - m0)); fills.push_back(fill_raw[m]); } gidx++; }
+            else if (kind[m] == 2) { vrows.push_back((int32_t)(m - m0)); vfills.push_back(fill_raw[m]); }
+        }
+        if (rows.empty() && vrows.empty()) continue;
+        if (M0 > chunk || m0 > 0 || true) {          // (re)upload this chunk
+            const uint8_t *src = rd.get(m0, m1);
+            if (!src) return sgb_fail(h, "setgeno: short read of .bed at marker %lld", (long long)m0);
+            CUDA_OK(h, cudaMemcpyAsync(d_raw, src, (size_t)(m1 - m0) * B0, cudaMemcpyHostToDevice, h->stream));
+            h->cnt.bytes_h2d += (m1 - m0) * B0;
+        }
+        if (!rows.empty()) {
+            CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+            CUDA_OK(h, cudaMemcpyAsync(d_fill, fills.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+            SGB_TRY(k_repack(h, d_raw, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG + lrow * h->sG, h->sG));
+            CUDA_OK(h, cudaStreamSynchronize(h->stream));
+            lrow += (int64_t)rows.size();
+        }
+        if (!vrows.empty()) {
+            if (!d_vr) CUDA_OK(h, cudaMalloc((void **)&d_vr, (size_t)std::min<int64_t>(chunk, M0) * B));
+            CUDA_OK(h, cudaMemcpyAsync(d_rows, vrows.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
+            CUDA_OK(h, cudaMemcpyAsync(d_fill, vfills.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
+            SGB_TRY(k_repack(h, d_raw, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, B));
+            CUDA_OK(h, cudaMemcpyAsync(h->vr_packed.data() + (size_t)vrow * B, d_vr, (size_t)vrows.size() * B, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_OK(h, cudaStreamSynchronize(h->stream));
+            vrow += (int64_t)vrows.size();
+        }
+    }
+    SGB_TRY(k_transpose(h));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_raw); cudaFree(d_ac); cudaFree(d_nm); cudaFree(d_rows); cudaFree(d_fill); cudaFree(d_indmask); cudaFree(d_sub);
+    if (d_vr) cudaFree(d_vr);
+    h->loaded = true;
+    return 0;
+}
+
+static int64_t count_lines(const char *path)
+{
+    std::ifstream f(path);
+    if (!f.is_open()) return -1;
+    int64_t n = 0;
+    std::string junk;
+    while (std::getline(f, junk)) n++;          // FG.cpp:767-771, 782-786
+    return n;
+}
+
+extern "C" int sgb_setgeno(sgb_ctx *h, const char *bed, const char *bim, const char *fam, const int32_t *sub, int64_t n_sub,
+                           const uint8_t *indicator, int64_t n_fam, int diagOne, const int32_t *vr_idx, int64_t n_vr)
+{
+    int64_t N0 = count_lines(fam);
+    if (N0 < 0) return sgb_fail(h, "Error! fam file not open! (%s)", fam);         // FG.cpp:762-765 (but as an error)
+    int64_t M0 = count_lines(bim);
+    if (M0 < 0) return sgb_fail(h, "Error! bim file not open! (%s)", bim);
+    if (n_fam != N0) return sgb_fail(h, "setgeno: indicator length %lld != %lld samples in %s", (long long)n_fam, (long long)N0, fam);
+    chunk_reader rd;
+    rd.fp = fopen(bed, "rb");
+    if (!rd.fp) return sgb_fail(h, "Error! bed file not open! (%s)", bed);
+    unsigned char magic[3] = {0, 0, 0};
+    if (fread(magic, 1, 3, rd.fp) != 3 || magic[0] != 0x6C || magic[1] != 0x1B || magic[2] != 0x01) {
+        fclose(rd.fp);
+        return sgb_fail(h, "%s is not a SNP-major PLINK .bed (bad magic bytes)", bed);
+    }
+    rd.B0 = (N0 + 3) / 4;
+    int rc = setgeno_impl(h, rd, N0, M0, sub, n_sub, indicator, diagOne, vr_idx, n_vr);
+    fclose(rd.fp);
+    return rc;
+}
+
+extern "C" int sgb_setgeno_mem(sgb_ctx *h, const uint8_t *bed_body, int64_t n_fam, int64_t n_bim, const int32_t *sub,
+                               int64_t n_sub, const uint8_t *indicator, int diagOne, const int32_t *vr_idx, int64_t n_vr)
+{
+    chunk_reader rd;
+    rd.mem = bed_body; rd.B0 = (n_fam + 3) / 4;
+    return setgeno_impl(h, rd, n_fam, n_bim, sub, n_sub, indicator, diagOne, vr_idx, n_vr);
+}
+
+extern "C" int sgb_setgeno_synth(sgb_ctx *h, int64_t N, int64_t M0, uint64_t seed, const uint32_t *t0, const uint32_t *t1)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    free_store(h);
+    if (N <= 0 || M0 <= 0) return sgb_fail(h, "setgeno_synth: bad dimensions");
+    h->kinDiagOne = false;
+    h->N0 = N; h->M0 = M0; h->N = N;
+    uint32_t *d_t0 = nullptr, *d_t1 = nullptr; int32_t *d_ac = nullptr;
+    CUDA_OK(h, cudaMalloc((void **)&d_t0, sizeof(uint32_t) * M0));
+    CUDA_OK(h, cudaMalloc((void **)&d_t1, sizeof(uint32_t) * M0));
+    CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * M0));
+    CUDA_OK(h, cudaMemcpy(d_t0, t0, sizeof(uint32_t) * M0, cudaMemcpyHostToDevice));
+    CUDA_OK(h, cudaMemcpy(d_t1, t1, sizeof(uint32_t) * M0, cudaMemcpyHostToDevice));
+    CUDA_OK(h, cudaMemsetAsync(d_ac, 0, sizeof(int32_t) * M0, h->stream));
+    SGB_TRY(k_synth(h, seed, d_t0, d_t1, d_ac));
+    std::vector<int32_t> ac_raw(M0);
+    CUDA_OK(h, cudaMemcpyAsync(ac_raw.data(), d_ac, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
+    h->afreq_vr.clear(); h->invstd_vr.clear(); h->mac_vr.clear(); h->ac_vr.clear(); h->index_vr.clear();
+    h->qc_mask.assign(M0, 0); h->loc2glob.clear(); h->vr_packed.clear();
+    bool save_vr = h->isVarRatio; h->isVarRatio = false;
+    std::vector<int64_t> rows;
+    for (int64_t m = 0; m < M0; m++) {
+        qc_out q = qc_marker(h, N, ac_raw[m], 0, false);
+        if (!q.passQC) continue;
+        int64_t gidx = (int64_t)h->afreq.size();
+        h->afreq.push_back(q.afreq); h->invstd.push_back(q.invstd); h->mac.push_back(q.mac); h->ac.push_back(q.ac);
+        h->qc_mask[m] = 1;
+        if (owns(h, gidx)) { h->loc2glob.push_back(gidx); rows.push_back(m); }
+    }
+    h->isVarRatio = save_vr;
+    h->M = (int64_t)h->afreq.size(); h->Mvr = 0; h->Mloc = (int64_t)h->loc2glob.size();
+    SGB_TRY(alloc_store(h));
+    SGB_TRY(sgb_ensure(h, &h->ws, &h->ws_bytes, sizeof(int64_t) * (rows.size() + 1)));
+    CUDA_OK(h, cudaMemcpyAsync(h->ws, rows.data(), sizeof(int64_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+    SGB_TRY(k_synth(h, seed, d_t0, d_t1, nullptr));
+    SGB_TRY(k_transpose(h));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_t0); cudaFree(d_t1); cudaFree(d_ac);
+    h->loaded = true;
+    return 0;
+}
+
+// ---- getters -----------------------------------------------------------------------------------------
+#define NEED_LOADED(h) do { if (!(h)->loaded) return sgb_fail(h, "genotypes not loaded: call setgeno first"); } while (0)
+
+extern "C" int64_t sgb_get_total_marker(sgb_ctx *h) { return h->M0; }
+extern "C" int64_t sgb_get_num_qc_markers(sgb_ctx *h) { return h->M; }
+extern "C" int64_t sgb_get_num_local_markers(sgb_ctx *h) { return h->Mloc; }
+extern "C" int64_t sgb_get_nnomissing(sgb_ctx *h) { return h->N; }
+extern "C" int64_t sgb_get_num_vr_markers(sgb_ctx *h) { return h->Mvr; }
+extern "C" int sgb_get_is_var_ratio_geno(sgb_ctx *h) { return h->isVarRatio ? 1 : 0; }
+extern "C" int sgb_get_allele_freq_vec(sgb_ctx *h, double *out) { NEED_LOADED(h); for (int64_t i = 0; i < h->M; i++) out[i] = h->afreq[i]; return 0; }
+extern "C" int sgb_get_mac_vec(sgb_ctx *h, int32_t *out) { NEED_LOADED(h); std::copy(h->mac.begin(), h->mac.end(), out); return 0; }
+extern "C" int sgb_get_allele_count_vec(sgb_ctx *h, int32_t *out) { NEED_LOADED(h); std::copy(h->ac.begin(), h->ac.end(), out); return 0; }
+extern "C" int sgb_get_mac_vec_for_var_ratio(sgb_ctx *h, int32_t *out) { NEED_LOADED(h); std::copy(h->mac_vr.begin(), h->mac_vr.end(), out); return 0; }
+extern "C" int sgb_get_index_vec_for_var_ratio(sgb_ctx *h, int32_t *out) { NEED_LOADED(h); std::copy(h->index_vr.begin(), h->index_vr.end(), out); return 0; }
+extern "C" int sgb_get_qcd_marker_index(sgb_ctx *h, uint8_t *out) { NEED_LOADED(h); std::copy(h->qc_mask.begin(), h->qc_mask.end(), out); return 0; }
+
+static void decode_row(const uint8_t *row, int64_t N, int32_t *out)
+{
+    for (int64_t i = 0; i < N; i++) out[i] = (row[i >> 2] >> ((i & 3) << 1)) & 3;
+}
+
+// Get_OneSNP_Geno (FG.cpp:223-272).  In a multi-rank run the row lives on one rank; the owner broadcasts it.
+extern "C" int sgb_get_one_snp_geno(sgb_ctx *h, int64_t idx, int32_t *out)
+{
+    NEED_LOADED(h);
+    if (idx < 0 || idx >= h->M) return sgb_fail(h, "Get_OneSNP_Geno: index %lld out of range [0,%lld)", (long long)idx, (long long)h->M);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    const int64_t B = (h->N + 3) / 4;
+    std::vector<uint8_t> row(B, 0);
+    bool mine = owns(h, idx);
+    if (mine) {
+        int64_t r = std::lower_bound(h->loc2glob.begin(), h->loc2glob.end(), idx) - h->loc2glob.begin();
+        CUDA_OK(h, cudaMemcpyAsync(row.data(), h->dG + r * h->sG, B, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        h->cnt.bytes_d2h += B;
+    }
+    if (h->world > 1) {
+        // sum-allreduce of the decoded row (non-owners contribute zeros)
+        std::vector<double> tmp(h->N, 0.0);
+        if (mine) for (int64_t i = 0; i < h->N; i++) tmp[i] = (row[i >> 2] >> ((i & 3) << 1)) & 3;
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_io, &h->io_elems, sizeof(double) * h->N));
+        CUDA_OK(h, cudaMemcpyAsync(h->d_io, tmp.data(), sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
+        SGB_TRY(sgb_allreduce_sum(h, h->d_io, h->N));
+        CUDA_OK(h, cudaMemcpyAsync(tmp.data(), h->d_io, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < h->N; i++) out[i] = (int32_t)tmp[i];
+        return 0;
+    }
+    decode_row(row.data(), h->N, out);
+    return 0;
+}
+
+extern "C" int sgb_get_one_snp_geno_for_var_ratio(sgb_ctx *h, int64_t idx, int32_t *out)
+{
+    NEED_LOADED(h);
+    if (idx < 0 || idx >= h->Mvr) return sgb_fail(h, "Get_OneSNP_Geno_forVarRatio: index %lld out of range [0,%lld)", (long long)idx, (long long)h->Mvr);
+    decode_row(h->vr_packed.data() + (size_t)idx * ((h->N + 3) / 4), h->N, out);
+    return 0;
+}
+
+extern "C" int sgb_get_one_snp_stdgeno(sgb_ctx *h, int64_t idx, double *out)
+{
+    std::vector<int32_t> g(h->N > 0 ? h->N : 1);
+    SGB_TRY(sgb_get_one_snp_geno(h, idx, g.data()));
+    double f = (double)h->ac[idx] / (double)(2 * h->N), v = 2.0 * f * (1.0 - f);
+    double s = v > 0 ? 1.0 / sqrt(v) : 0.0;
+    for (int64_t i = 0; i < h->N; i++) out[i] = ((double)g[i] - 2.0 * f) * s;
+    return 0;
+}
+
+// ---- LOCO bookkeeping (FG.cpp:3067-3091) -------------------------------------------------------------
+extern "C" int sgb_set_start_end_index_vec(sgb_ctx *h, const int32_t *start, const int32_t *end, int n)
+{
+    h->startVec.assign(start, start + n);
+    h->endVec.assign(end, end + n);
+    h->diag_loco_ready = false;
+    return 0;
+}
+
+extern "C" int sgb_set_start_end_index(sgb_ctx *h, int start, int end, int chromIndex)
+{
+    NEED_LOADED(h);
+    if (start < 0 || end < start || end >= h->M) return sgb_fail(h, "setStartEndIndex: bad range [%d,%d] for %lld markers", start, end, (long long)h->M);
+    h->loco_start = start; h->loco_end = end; h->loco_chrom = chromIndex;
+    return 0;
+}
+
+extern "C" int sgb_get_counters(sgb_ctx *h, sgb_counters *out) { *out = h->cnt; return 0; }
+extern "C" int sgb_reset_counters(sgb_ctx *h) { h->cnt = sgb_counters(); return 0; }
+
+extern "C" double sgb_cal_cv(const double *x, int n)
+{
+    // calCV (FG.cpp:3104-3110): (sd/mean)/n with the n-1 standard deviation
+    double mean = 0.0;
+    for (int i = 0; i < n; i++) mean += x[i];
+    mean /= n;
+    double ss = 0.0;
+    for (int i = 0; i < n; i++) ss += (x[i] - mean) * (x[i] - mean);
+    double sd = n > 1 ? sqrt(ss / (n - 1)) : 0.0;
+    return (sd / mean) / n;
+}
+
+extern "C" double sgb_inner_product(const double *x, const double *y, int64_t n)
+{
+    double s = 0.0;
+    for (int64_t i = 0; i < n; i++) s += x[i] * y[i];
+    return s;
+}

@@ -1,0 +1,296 @@
+"""Step-1 driver: the part of src/SAIGE/R/SAIGE_fitGLMM_fast.R ("FG.R") that sits between `fitNULLGLMM` and the
+native exports, restated in Python so that the whole null-GLMM fit can be run and timed without R.
+
+In a real deployment this layer is the UNCHANGED R code; it is mirrored here, function by
+function and with the same names, because R is not available in the build/bench environment.  It only calls
+the export mirror in api.py (i.e. the C ABI); no numerical work on genotypes happens here.
+
+  Get_Coef / Get_Coef_LOCO              FG.R:2-35, 42-73
+  glmmkin_ai_PCG_Rcpp_Binary            FG.R:79-304
+  glmmkin_ai_PCG_Rcpp_Quantitative      FG.R:309-549
+  ScoreTest_NULL_Model                  FG.R:579-591
+  Covariate_Transform[_Back]            FG.R:1612-1659
+  extractVarianceRatio                  FG.R:2152-2423 (single ratio, full-GRM path)
+  updateChrStartEndIndexVec             R/Util.R:29-65
+"""
+import time
+
+import numpy as np
+
+
+class Binomial:
+    name = "binomial"
+
+    @staticmethod
+    def linkinv(eta):
+        return 1.0 / (1.0 + np.exp(-eta))
+
+    @staticmethod
+    def mu_eta(eta):
+        e = np.exp(-np.abs(eta))
+        return np.maximum(e / (1.0 + e) ** 2, np.finfo(float).eps)
+
+    @staticmethod
+    def variance(mu):
+        return mu * (1.0 - mu)
+
+
+class Gaussian:
+    name = "gaussian"
+    linkinv = staticmethod(lambda eta: eta)
+    mu_eta = staticmethod(lambda eta: np.ones_like(eta))
+    variance = staticmethod(lambda mu: np.ones_like(mu))
+
+
+def glm_fit(y, X, family, offset=None, maxit=25, epsilon=1e-8):
+    """R's glm.fit IRLS; provides fit0 (FG.R:1119)."""
+    n = len(y)
+    offset = np.zeros(n) if offset is None else offset
+    if family.name == "binomial":
+        mu = (y + 0.5) / 2.0
+        eta = np.log(mu / (1 - mu))
+    else:
+        mu = y.astype(np.float64).copy()
+        eta = mu.copy()
+    devold = np.inf
+    coef = np.zeros(X.shape[1])
+    for _ in range(maxit):
+        me = family.mu_eta(eta)
+        z = (eta - offset) + (y - mu) / me
+        sw = np.sqrt(me ** 2 / family.variance(mu))
+        coef, *_ = np.linalg.lstsq(X * sw[:, None], z * sw, rcond=None)
+        eta = X @ coef + offset
+        mu = family.linkinv(eta)
+        if family.name == "binomial":
+            with np.errstate(divide="ignore", invalid="ignore"):
+                d = 2 * (np.where(y > 0, y * np.log(y / mu), 0) + np.where(y < 1, (1 - y) * np.log((1 - y) / (1 - mu)), 0))
+            dev = d.sum()
+        else:
+            dev = ((y - mu) ** 2).sum()
+        if abs(dev - devold) / (abs(dev) + 0.1) < epsilon:
+            break
+        devold = dev
+    return dict(coef=coef, eta=eta, mu=mu, y=y, offset=offset, family=family, X=X)
+
+
+def Covariate_Transform(X1):
+    Q, R = np.linalg.qr(X1)
+    return Q * np.sqrt(X1.shape[0]), dict(qrr=R, N=X1.shape[0])
+
+
+def Covariate_Transform_Back(coef, param):
+    return np.linalg.solve(param["qrr"], coef * np.sqrt(param["N"]))
+
+
+def ScoreTest_NULL_Model(mu, mu2, y, X):
+    V = np.asarray(mu2, dtype=np.float64)
+    res = y - mu
+    XV = (X * V[:, None]).T
+    XVX = X.T @ XV.T
+    XVX_inv = np.linalg.inv(XVX)
+    XXVX_inv = X @ XVX_inv
+    return dict(XV=XV, XVX=XVX, XXVX_inv=XXVX_inv, XVX_inv=XVX_inv, S_a=(X * res[:, None]).sum(0),
+                XVX_inv_XV=XXVX_inv * V[:, None], V=V)
+
+
+def updateChrStartEndIndexVec(geno, chrVec):
+    chrVec = np.asarray(chrVec)
+    start, end = [], []
+    for c in range(1, 23):
+        idx = np.nonzero(chrVec == c)[0]
+        if len(idx):
+            if start and start[-1] != -1 and (idx.min() <= start[-1] or idx.max() <= end[-1]):
+                raise ValueError("ERROR! chromosomes need to be ordered from 1 to 22 in the bim file.")
+            start.append(int(idx.min())); end.append(int(idx.max()))
+        else:
+            start.append(-1); end.append(-1)
+    LOCO = sum(s != -1 for s in start) > 1
+    geno.setStartEndIndexVec(start, end)
+    return LOCO, start, end
+
+
+class ProbeStream:
+    """Stand-in for R's RNG on the trace estimator: GetTrace re-seeds to 200 on every call (FG.cpp:3114) and then
+    draws 2*rbinom(N,1,0.5)-1 per run, so every call sees the same probe sequence.  Here the sequence is a fixed
+    N x nmax Rademacher matrix; `fresh()` returns a draw(n) callable that starts again at column 0."""
+
+    def __init__(self, N, nmax=130, seed=200):
+        rng = np.random.default_rng(seed)
+        self.U = np.asfortranarray(rng.integers(0, 2, size=(N, nmax)).astype(np.float64) * 2.0 - 1.0)
+
+    def fresh(self):
+        pos = [0]
+
+        def draw(n):
+            out = self.U[:, pos[0]:pos[0] + n]
+            if out.shape[1] != n:
+                raise RuntimeError("probe matrix exhausted")
+            pos[0] += n
+            return out
+        return draw
+
+
+def Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, loco=False):
+    tol_coef = 0.1
+    mu = family.linkinv(eta0)
+    me = family.mu_eta(eta0)
+    Y = eta0 - offset + (y - mu) / me
+    sqrtW = me / np.sqrt(family.variance(mu))
+    W = sqrtW ** 2
+    for _ in range(maxiter):
+        rc = geno.getCoefficients(Y, X, W, tau, maxiterPCG, tolPCG, loco)
+        alpha = rc["alpha"]
+        eta = rc["eta"] + offset
+        mu = family.linkinv(eta)
+        me = family.mu_eta(eta)
+        Y = eta - offset + (y - mu) / me
+        sqrtW = me / np.sqrt(family.variance(mu))
+        W = sqrtW ** 2
+        if np.max(np.abs(alpha - alpha0) / (np.abs(alpha) + np.abs(alpha0) + tol_coef)) < tol_coef:
+            break
+        alpha0 = alpha
+    return dict(Y=Y, alpha=alpha, eta=eta, W=W, cov=rc["cov"], sqrtW=sqrtW, Sigma_iY=rc["Sigma_iY"],
+                Sigma_iX=rc["Sigma_iX"], mu=mu)
+
+
+def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxiter=20, tol=0.02, nrun=30,
+                   tolPCG=1e-5, maxiterPCG=500, traceCVcutoff=0.0025, LOCO=False, verbose=False, timings=None):
+    """glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549)."""
+    y, X, offset, family = fit0["y"], fit0["X"], fit0["offset"], fit0["family"]
+    n = len(y)
+    quant = trait == "quantitative"
+    eta = fit0["eta"]
+    alpha0, eta0 = fit0["coef"], eta
+    tau = np.array([0.0, 0.0])
+    tauInit = np.asarray(tauInit, dtype=np.float64)
+    if not quant:
+        tau[0] = 1.0
+        tau[1] = 0.1 if tauInit[1] == 0 else tauInit[1]
+    elif tauInit.sum() == 0:
+        tau[:] = (1.0, 0.0)
+    else:
+        tau[:] = tauInit
+    tau0 = tau.copy()
+    t0 = time.time()
+    rc = Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter)
+    if not quant:
+        re = geno.getAIScore(rc["Y"], X, rc["W"], tau, rc["Sigma_iY"], rc["Sigma_iX"], rc["cov"], nrun, maxiterPCG, tolPCG,
+                             traceCVcutoff, probes.fresh())
+        tau[1] = max(0.0, tau0[1] + tau0[1] ** 2 * (re["YPAPY"] - re["Trace"]) / n)
+    else:
+        re = geno.getAIScore_q(rc["Y"], X, rc["W"], tau, rc["Sigma_iY"], rc["Sigma_iX"], rc["cov"], nrun, maxiterPCG,
+                               tolPCG, traceCVcutoff, probes.fresh())
+        tau[1] = max(0.0, tau0[1] + tau0[1] ** 2 * (re["YPAPY"] - re["Trace"][1]) / n)
+        tau[0] = max(0.0, tau0[0] + tau0[0] ** 2 * (re["YPA0PY"] - re["Trace"][0]) / n)
+    if verbose:
+        print("Variance component estimates:", tau)
+    tau_path = [tau.copy()]
+    alpha = fit0["coef"] if quant else rc["alpha"]
+    i = 0
+    for i in range(1, maxiter + 1):
+        alpha0 = alpha if quant else rc["alpha"]
+        tau0 = tau.copy()
+        eta0 = eta
+        rc = Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter)
+        fit = (geno.fitglmmaiRPCG_q if quant else geno.fitglmmaiRPCG)(
+            rc["Y"], X, rc["W"], tau, rc["Sigma_iY"], rc["Sigma_iX"], rc["cov"], nrun, maxiterPCG, tolPCG, tol,
+            traceCVcutoff, probes.fresh())
+        tau = np.asarray(fit["tau"], dtype=np.float64)
+        alpha, eta = rc["alpha"], rc["eta"]
+        tau_path.append(tau.copy())
+        if verbose:
+            print("Iteration", i, "tau:", tau)
+        if quant and tau[0] <= 0:
+            raise RuntimeError("ERROR! The first variance component parameter estimate is 0")
+        if (not quant and tau[1] == 0) or (quant and tau[1] <= 0):
+            break
+        if np.max(np.abs(tau - tau0) / (np.abs(tau) + np.abs(tau0) + tol)) < tol:
+            break
+        if np.max(tau) > tol ** (-2):
+            i = maxiter
+            break
+    rc = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter)
+    alpha, eta, mu = rc["alpha"], rc["eta"], rc["mu"]
+    mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau[0])
+    out = dict(theta=tau, coefficients=alpha, linear_predictors=eta, fitted_values=mu, Y=rc["Y"], residuals=y - mu,
+               cov=rc["cov"], converged=i < maxiter, obj_noK=ScoreTest_NULL_Model(mu, mu2, y, X), y=y, X=X,
+               traitType=trait, LOCO=LOCO, tau_path=tau_path, offset=offset)
+    if timings is not None:
+        timings["fit_s"] = time.time() - t0
+    if LOCO:
+        t1 = time.time()
+        geno.set_Diagof_StdGeno_LOCO()
+        out["LOCOResult"] = []
+        for j, (s, e) in enumerate(zip(geno_start_vec(geno), geno_end_vec(geno))):
+            if s == -1 or e == -1:
+                out["LOCOResult"].append(dict(isLOCO=False))
+                continue
+            geno.setStartEndIndex(s, e, j)
+            rl = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, loco=True)
+            alpha, eta, mu = rl["alpha"], rl["eta"], rl["mu"]
+            mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau[0])
+            out["LOCOResult"].append(dict(isLOCO=True, coefficients=alpha, linear_predictors=eta, fitted_values=mu,
+                                          Y=rl["Y"], residuals=y - mu, cov=rl["cov"],
+                                          obj_noK=ScoreTest_NULL_Model(mu, mu2, y, X)))
+        if timings is not None:
+            timings["loco_s"] = time.time() - t1
+    return out
+
+
+def geno_start_vec(geno):
+    return geno._loco_start
+
+
+def geno_end_vec(geno):
+    return geno._loco_end
+
+
+def set_loco_ranges(geno, chr_of_qc_marker):
+    """FG.R:116-125: chromosome ranges over QC-passing markers -> setStartEndIndexVec."""
+    LOCO, start, end = updateChrStartEndIndexVec(geno, chr_of_qc_marker)
+    geno._loco_start, geno._loco_end = start, end
+    return LOCO
+
+
+def extractVarianceRatio(geno, model, family, marker_order, numMarkers=30, maxiterPCG=500, tolPCG=1e-5,
+                         ratioCVcutoff=0.001, batch=True):
+    """FG.R:2152-2423 (one ratio).  `marker_order` = the caller's `sample(MACindex)` permutation (FG.R:2242).
+    With batch=True the getSigma_G solves of a round (numMarkers, then +10 per CV retry) run as one multi-column
+    PCG; results are identical to the sequential loop because each column follows its own recurrence."""
+    mu, eta, y, X = model["fitted_values"], model["linear_predictors"], model["y"], model["X"]
+    tau, noK = model["theta"], model["obj_noK"]
+    me = family.mu_eta(eta)
+    W = (me / np.sqrt(family.variance(mu))) ** 2
+    Sigma_iX = geno.getSigma_X(W, tau, X, maxiterPCG, tolPCG)
+    use_vr = geno.getIsVarRatioGeno() and geno.Mvr > 0
+    N = geno.N
+    ratios, pos, target = [], 0, numMarkers
+    XtSiX = X.T @ Sigma_iX
+    while True:
+        take = marker_order[pos:pos + (target - len(ratios))]
+        pos += len(take)
+        if len(take):
+            Gs, ACs = [], []
+            for i in take:
+                G0 = (geno.Get_OneSNP_Geno_forVarRatio(i) if use_vr else geno.Get_OneSNP_Geno(i)).astype(np.float64)
+                if G0.sum() / (2 * N) > 0.5:
+                    G0 = 2 - G0
+                ACs.append(G0.sum())
+                Gs.append(G0 - noK["XXVX_inv"] @ (noK["XV"] @ G0))
+            Gm = np.column_stack(Gs)
+            if batch:
+                SiG = geno.getSigma_G(W, tau, Gm, maxiterPCG, tolPCG)
+            else:
+                SiG = np.column_stack([geno.getSigma_G(W, tau, Gm[:, j], maxiterPCG, tolPCG) for j in range(Gm.shape[1])])
+            for j in range(Gm.shape[1]):
+                Gt, AC, Sg = Gm[:, j], ACs[j], SiG[:, j]
+                gn = Gt / np.sqrt(AC)
+                var1 = (Gt @ Sg - Gt @ Sigma_iX @ np.linalg.solve(XtSiX, X.T @ Sg)) / AC
+                var2 = float((mu * (1 - mu)) @ (gn * gn)) if model["traitType"] == "binary" else float(gn @ gn)
+                ratios.append(var1 / var2)
+        cv = geno.calCV(np.array(ratios))
+        if cv > ratioCVcutoff and pos < len(marker_order):
+            target += 10
+        else:
+            break
+    return float(np.mean(ratios)), ratios
