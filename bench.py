@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- GRM matvecs/s of the step-1 null-GLMM hot path on synthetic genotypes (BASELINE.json metric).
+
+A "step" is one k=1 GRM.vector product y = K b over the whole marker set (the unit of work of one PCG iteration,
+getCrossprodMatAndKin, FG.cpp:1953).  Workload at every GPU count: BASELINE.json configs[2], synthetic
+200,000 samples x 500,000 markers (the configuration the metric is quoted on; 2 x 25 GB packed copies fit one
+180 GB B200), markers sharded block-cyclically over the ranks => "strong" scaling, one NCCL allreduce per product.
+
+  value   : whole-job matvecs/s with genotypes and vectors resident in HBM, CUDA-event timed on the library's stream
+  e2e     : the same through the public C-ABI call with HOST (pinned) vectors, H2D + D2H inside the timed region
+  roofline: the dominant kernel (pk2_gemm_kernel, 2 launches per product) against the measured HBM peak
+  cpu_baseline / --impl reference : the reference's CPU matvec (fp32, marker loop of parallelCrossProdOpenMP,
+            FG.cpp:1576-1598, restated in oracle/saige_oracle.c) on all host cores, on a bounded marker sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N samples, M markers)
+    "c3_200kx500k": (200_000, 500_000),
+    "c2_50kx500k": (50_000, 500_000),
+    "small_20kx50k": (20_000, 50_000),
+}
+SEED = 20260117
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(N, M, threads_note=True, target_s=12.0):
+    """Reference CPU matvec (fp32, reference operation order) on a bounded marker sample of the same workload."""
+    from oracle import oracle as O
+    cores = O.lib().orc_num_threads()
+    msample = 2048
+    bed = O.synth_bed(N, msample, SEED)
+    g = O.OracleGeno(mode=O.REF32)
+    g.minMAF, g.maxMissing = 0.01, 0.15
+    g.setgeno(bed, N, msample, np.arange(1, N + 1), np.ones(N, np.uint8))
+    b = np.random.default_rng(1).integers(0, 2, N) * 2.0 - 1.0
+    g.getCrossprodMatAndKin(b)                      # warm-up
+    reps, t0 = 0, time.time()
+    while True:
+        g.getCrossprodMatAndKin(b)
+        reps += 1
+        if time.time() - t0 > target_s or reps >= 50:
+            break
+    per_sample = (time.time() - t0) / reps
+    per_matvec = per_sample * (M / g.M)
+    return {"value": 1.0 / per_matvec, "unit": "matvecs/s", "cores": int(cores), "kind": "port",
+            "sample": "%d of %d markers x %d samples, fp32 reference-order matvec (oracle ref32 mode, OpenMP), "
+                      "%d reps, scaled linearly in M" % (g.M, M, N, reps),
+            "s_per_sample_matvec": per_sample}
+
+
+def run_reference(args, N, M, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_baseline(N, M, target_s=max(2.0, 1.5 * args.steps))
+    line = {"impl": "reference", "metric": "grm_matvecs_per_s", "value": cb["value"], "unit": "matvecs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n_samples": N, "n_markers": M, "k": 1},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_200kx500k", choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="tensor", choices=["tensor", "f64"])
+    ap.add_argument("--k-batch", type=int, default=31, help="width of the extra batched-product measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-step1", action="store_true", help="skip the step-1 wall-time extra")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    N, M = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return run_reference(args, N, M, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from saige_gpu_b200 import SaigeB200, synth, step1
+
+    if world > 1:
+        # control plane only (barrier, max over ranks, NCCL id exchange); the data path uses the library's own NCCL
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        ids = [SaigeB200.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g = SaigeB200(device=local_rank, rank=rank, world=world, nccl_id=ids[0], engine=args.engine)
+    else:
+        g = SaigeB200(device=local_rank, engine=args.engine)
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        g.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- workload: synthetic genotypes generated straight into the device store ----
+    t_load0 = time.time()
+    _, t0, t1 = synth.thresholds(M, SEED)
+    g.setminMAFforGRM(0.01)
+    g.setmaxMissingRateforGRM(0.15)
+    g.setgeno_synth(N, M, SEED, t0, t1)
+    t_load = time.time() - t_load0
+    Bbytes = (N + 3) // 4
+    Mloc = g.Mloc
+
+    # ---- device-resident leg ("value") ----
+    W, K = args.warmup, args.steps
+    barrier()
+    g.bench_crossprod_device(1, W)                         # warm-up (also sizes every scratch buffer)
+    g.reset_counters()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, mk = g.bench_crossprod_device(1, K)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = g.counters()["n_kernel_launches"]
+    total_ms = max_over_ranks(float(ms.sum()))
+    value = K / (total_ms * 1e-3)
+    sweep_ms = float(mk.sum()) / (2 * K)                   # average duration of one pk2_gemm launch
+    bytes_launch = Mloc * Bbytes                           # algorithmic bytes of one sweep: the packed shard, once
+    peak, peak_src = measured_hbm_peak()
+    achieved = bytes_launch / (sweep_ms * 1e-3) / 1e9
+    bytes_alg_product = 2 * Mloc * Bbytes + 16 * N + 16 * Mloc * 2
+
+    # ---- batched products (the Hutchinson probes + phenotype ride in ONE multi-vector product) ----
+    kb = args.k_batch
+    g.bench_crossprod_device(kb, 1)
+    barrier()
+    msb, _ = g.bench_crossprod_device(kb, max(2, K // 5))
+    barrier()
+    batch_ms = max_over_ranks(float(msb.mean()))
+
+    # ---- end-to-end leg: the public C-ABI call on pinned host vectors ----
+    hb = torch.empty(N, dtype=torch.float64).pin_memory()
+    hy = torch.empty(N, dtype=torch.float64).pin_memory()
+    hb.copy_(torch.from_numpy(np.random.default_rng(3).integers(0, 2, N) * 2.0 - 1.0))
+    import ctypes as C
+    L, h = g._L, g._h
+    pb, py = C.c_void_p(hb.data_ptr()), C.c_void_p(hy.data_ptr())
+    for _ in range(W):
+        g._ck(L.sgb_get_crossprod_mat_and_kin(h, pb, 1, py))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e2e0 = time.perf_counter()
+    for _ in range(K):
+        g._ck(L.sgb_get_crossprod_mat_and_kin(h, pb, 1, py))      # returns after the D2H of y completed
+    g.sync()
+    t_e2e = max_over_ranks(time.perf_counter() - t_e2e0)
+    barrier()
+    e2e_value = K / t_e2e
+    checksum = float(hy.sum())
+
+    # ---- extras on rank 0: CPU baseline beside it, step-1 wall time ----
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(N, M)
+    step1_info = None
+    if not args.no_step1:
+        # polygenic liability (h2 ~ 0.3) from 200 causal markers read back through Get_OneSNP_StdGeno
+        rngc = np.random.default_rng(SEED + 5)
+        causal = np.sort(rngc.choice(g.M, size=200, replace=False))
+        gterm = np.zeros(N)
+        for m_idx in causal:
+            gterm += rngc.normal() * g.Get_OneSNP_StdGeno(int(m_idx))
+        gterm *= np.sqrt(0.3 / 0.7) * 1.8 / max(gterm.std(), 1e-12)
+        y, _, X = synth.phenotype(N, SEED, gterm=gterm)
+        probes = step1.ProbeStream(N, nmax=70, seed=200)
+        fit0 = step1.glm_fit(y, X, step1.Binomial)
+        g.reset_counters()
+        barrier()
+        ts = time.time()
+        tim = {}
+        model = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim)
+        g.sync()
+        wall = max_over_ranks(time.time() - ts)
+        c = g.counters()
+        step1_info = {"wall_s": wall, "load_synth_s": t_load, "tau": [float(v) for v in model["theta"]],
+                      "converged": bool(model["converged"]), "outer_iterations": len(model["tau_path"]) - 1,
+                      "pcg_solves": c["n_pcg_solves"], "pcg_iterations": c["n_pcg_iterations"],
+                      "product_columns": c["n_crossprod_columns"], "products": c["n_crossprod_calls"], "LOCO": False,
+                      "note": "binary trait, 3 fixed-effect columns, nrun=30 probes, tolPCG=1e-5, full GRM, no LOCO refits"}
+
+    if rank == 0:
+        line = {
+            "metric": "grm_matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int8 tensor-core limbs, exact int32 accumulate, fp64 recombine" if args.engine == "tensor" else "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "n_samples": N, "n_markers": M, "markers_per_gpu": int(Mloc), "k": 1,
+                       "engine": args.engine, "l2_policy": "inputs (%.1f GB packed genotypes per sweep) >> 126 MB L2" % (bytes_launch / 1e9),
+                       "sharding": "block-cyclic markers, 1 NCCL allreduce of N fp64 per product" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
+                    "api": "sgb_get_crossprod_mat_and_kin (host pinned vectors)", "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "pk2_gemm_kernel", "peak_source": peak_src,
+                         "bytes_per_launch": int(bytes_launch), "avg_launch_ms": sweep_ms,
+                         "sweep1_ms": float(mk[:, 0].mean()), "sweep2_ms": float(mk[:, 1].mean()),
+                         "whole_product_frac": bytes_alg_product / (total_ms / K * 1e-3) / 1e9 / peak},
+            "batched": {"k": kb, "ms_per_product": batch_ms, "columns_per_s": kb / (batch_ms * 1e-3)},
+            "cpu_baseline": cb,
+            "step1": step1_info,
+        }
+        print(json.dumps(line))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

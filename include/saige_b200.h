@@ -149,8 +149,8 @@ double sgb_inner_product(const double *x, const double *y, int64_t n);      /* i
 
 /* ---- device-resident benchmark hooks (bench.py `value` leg: inputs already in HBM) ---------------- */
 /* Runs `reps` k-column GRM products on device-resident synthetic right-hand sides, timing with CUDA events
- * on the library's stream; ms_out[reps] per-product times, and ms_kernel_out[2] the summed time of the two
- * genotype sweeps of the LAST product.  Result left in an internal buffer (sgb_bench_fetch_result). */
+ * on the library's stream; ms_out[reps] per-product times, and ms_kernel_out[2*reps] (may be NULL) the device time of
+ * the two genotype sweeps {sweep 1, sweep 2} of each product.  Result left in an internal buffer (sgb_bench_fetch_result). */
 int sgb_bench_crossprod_device(sgb_ctx *h, int k, int reps, uint64_t seed, float *ms_out, float *ms_kernel_out);
 int sgb_bench_fetch_result(sgb_ctx *h, int k, double *Y, double *B);
 

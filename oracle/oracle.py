@@ -30,20 +30,25 @@ def lib():
         if not os.path.exists(so):
             subprocess.check_call(["make", "-C", _HERE, "libsaige_oracle.so"])
         L = C.CDLL(so)
+        L.orc_new.restype = C.c_void_p
+        L.orc_free.argtypes = [C.c_void_p]
         L.orc_setgeno.restype = C.c_int
-        L.orc_setgeno.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+        L.orc_setgeno.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int64]
         for n in ("orc_get_M", "orc_get_M0", "orc_get_N", "orc_get_Mvr", "orc_get_B"):
             getattr(L, n).restype = C.c_int64
+            getattr(L, n).argtypes = [C.c_void_p]
         for n in ("orc_afreq", "orc_invstd", "orc_mac", "orc_ac", "orc_packed"):
             getattr(L, n).restype = C.c_void_p
-            getattr(L, n).argtypes = [C.c_int]
+            getattr(L, n).argtypes = [C.c_void_p, C.c_int]
         L.orc_index_vr.restype = C.c_void_p
+        L.orc_index_vr.argtypes = [C.c_void_p]
         L.orc_qc_mask.restype = C.c_void_p
-        L.orc_one_snp_geno.argtypes = [C.c_int64, C.c_int, C.c_void_p]
-        L.orc_one_snp_stdgeno.argtypes = [C.c_int64, C.c_int, C.c_void_p]
-        L.orc_crossprod_range.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-        L.orc_diag_range.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.orc_qc_mask.argtypes = [C.c_void_p]
+        L.orc_one_snp_geno.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.orc_one_snp_stdgeno.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.orc_crossprod_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_diag_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.orc_synth_bed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_num_threads.restype = C.c_int
         _LIB = L
@@ -104,6 +109,7 @@ class OracleGeno:
 
     def __init__(self, mode=FP64):
         self.mode = mode
+        self._g = C.c_void_p(lib().orc_new())
         self.minMAF = 0.0            # minMAFtoConstructGRM (FG.cpp:35, setminMAFforGRM FG.cpp:4923)
         self.maxMissing = 1.0        # geno.maxMissingRate (setmaxMissingRateforGRM FG.cpp:4928)
         self.isVarRatio = False      # setminMAC_VarianceRatio (FG.cpp:4970)
@@ -114,6 +120,12 @@ class OracleGeno:
         self.startIndexVec = self.endIndexVec = None
         self.startIndex = self.endIndex = self.chromIndex = None
 
+    def __del__(self):
+        try:
+            lib().orc_free(self._g)
+        except Exception:
+            pass
+
     def setgeno(self, bed, N0, M0, subSampleInGeno, indicator, isDiagofKinSetAsOne=False, vr_rand_idx=None):
         """setgeno -> genoClass::setGenoObj (FG.cpp:2267, 739-1024)."""
         L = lib()
@@ -122,35 +134,35 @@ class OracleGeno:
         ind = np.ascontiguousarray(indicator, dtype=np.uint8)
         vr = np.ascontiguousarray(vr_rand_idx if vr_rand_idx is not None else [], dtype=np.int32)
         bed = np.ascontiguousarray(bed, dtype=np.uint8)
-        rc = L.orc_setgeno(_ptr(bed), N0, M0, _ptr(sub), len(sub), _ptr(ind), self.minMAF, self.maxMissing,
+        rc = L.orc_setgeno(self._g, _ptr(bed), N0, M0, _ptr(sub), len(sub), _ptr(ind), self.minMAF, self.maxMissing,
                            int(self.isVarRatio), self.minMACvr, self.maxMACvr, _ptr(vr), len(vr))
         assert rc == 0
-        self.N, self.M, self.M0, self.Mvr, self.B = (L.orc_get_N(), L.orc_get_M(), L.orc_get_M0(),
-                                                     L.orc_get_Mvr(), L.orc_get_B())
-        self.alleleFreqVec = _view(L.orc_afreq(0), self.M, np.float32)
-        self.invstdvVec = _view(L.orc_invstd(0), self.M, np.float32)
-        self.MACVec = _view(L.orc_mac(0), self.M, np.int32)
-        self.ACVec = _view(L.orc_ac(0), self.M, np.int32)
-        self.qc_mask = _view(L.orc_qc_mask(), self.M0, np.uint8).astype(bool)
-        self.MACVec_forVarRatio = _view(L.orc_mac(1), self.Mvr, np.int32)
-        self.markerIndexVec_forVarRatio = _view(L.orc_index_vr(), self.Mvr, np.int32)
-        self.alleleFreqVec_forVarRatio = _view(L.orc_afreq(1), self.Mvr, np.float32)
+        self.N, self.M, self.M0, self.Mvr, self.B = (L.orc_get_N(self._g), L.orc_get_M(self._g), L.orc_get_M0(self._g),
+                                                     L.orc_get_Mvr(self._g), L.orc_get_B(self._g))
+        self.alleleFreqVec = _view(L.orc_afreq(self._g, 0), self.M, np.float32)
+        self.invstdvVec = _view(L.orc_invstd(self._g, 0), self.M, np.float32)
+        self.MACVec = _view(L.orc_mac(self._g, 0), self.M, np.int32)
+        self.ACVec = _view(L.orc_ac(self._g, 0), self.M, np.int32)
+        self.qc_mask = _view(L.orc_qc_mask(self._g), self.M0, np.uint8).astype(bool)
+        self.MACVec_forVarRatio = _view(L.orc_mac(self._g, 1), self.Mvr, np.int32)
+        self.markerIndexVec_forVarRatio = _view(L.orc_index_vr(self._g), self.Mvr, np.int32)
+        self.alleleFreqVec_forVarRatio = _view(L.orc_afreq(self._g, 1), self.Mvr, np.float32)
         self._diag = None
         self._diag_loco = None
 
     def packed(self, vr=False):
         L = lib()
         n = (self.Mvr if vr else self.M) * self.B
-        return _view(L.orc_packed(int(vr)), n, np.uint8).reshape(-1, self.B)
+        return _view(L.orc_packed(self._g, int(vr)), n, np.uint8).reshape(-1, self.B)
 
     def Get_OneSNP_Geno(self, idx, vr=False):
         out = np.zeros(self.N, dtype=np.int32)
-        lib().orc_one_snp_geno(idx, int(vr), _ptr(out))
+        lib().orc_one_snp_geno(self._g, idx, int(vr), _ptr(out))
         return out
 
     def Get_OneSNP_StdGeno(self, idx):
         out = np.zeros(self.N, dtype=np.float64)
-        lib().orc_one_snp_stdgeno(idx, self.mode, _ptr(out))
+        lib().orc_one_snp_stdgeno(self._g, idx, self.mode, _ptr(out))
         return out
 
     # -- GRM.vector (FG.cpp:1576-1598, 1669-1708, 1746-1851, 1953-2006) --
@@ -159,7 +171,7 @@ class OracleGeno:
         k = 1 if b.ndim == 1 else b.shape[1]
         bf = np.asfortranarray(b.reshape(self.N, k))
         out = np.zeros((self.N, k), dtype=np.float64, order="F")
-        lib().orc_crossprod_range(m0, m1, _ptr(bf), k, self.mode, _ptr(out))
+        lib().orc_crossprod_range(self._g, m0, m1, _ptr(bf), k, self.mode, _ptr(out))
         return out[:, 0].copy() if b.ndim == 1 else out
 
     def getCrossprodMatAndKin(self, b):
@@ -176,7 +188,7 @@ class OracleGeno:
     def Get_Diagof_StdGeno(self):
         if self._diag is None:
             out = np.zeros(self.N, dtype=np.float64)
-            lib().orc_diag_range(0, self.M, self.mode, _ptr(out))
+            lib().orc_diag_range(self._g, 0, self.M, self.mode, _ptr(out))
             self._diag = out
         return self._diag
 
@@ -201,7 +213,7 @@ class OracleGeno:
             s, e = self.startIndexVec[k], self.endIndexVec[k]
             if s != -1 and e != -1:
                 out = np.zeros(self.N)
-                lib().orc_diag_range(int(s), int(e) + 1, self.mode, _ptr(out))
+                lib().orc_diag_range(self._g, int(s), int(e) + 1, self.mode, _ptr(out))
                 self._diag_loco[:, k] = full - out
                 self.Msub_byChr[k] = e - s + 1
 

@@ -341,9 +341,9 @@ class SaigeB200:
     # ---- bench hooks / counters ----
     def bench_crossprod_device(self, k, reps, seed=1):
         ms = np.zeros(reps, dtype=np.float32)
-        mk = np.zeros(2, dtype=np.float32)
+        mk = np.zeros(2 * reps, dtype=np.float32)
         self._ck(self._L.sgb_bench_crossprod_device(self._h, int(k), int(reps), int(seed), _p(ms), _p(mk)))
-        return ms, mk
+        return ms, mk.reshape(reps, 2)
 
     def bench_fetch_result(self, k):
         Y = np.zeros((self.N, k), order="F")

@@ -20,6 +20,19 @@
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Device coding of the genotype store ("pair-ternary"): one nibble holds TWO genotypes A (even sample) and
+// B (odd sample) as n = A + 3*B in 0..8; a byte = nibble(samples 4b, 4b+1) | nibble(samples 4b+2, 4b+3) << 4.
+// Still 2 bits per genotype, but the UNMASKED nibble is directly a prmt selector (see decode16).
+__host__ __device__ __forceinline__ uint32_t sgb_pack4(int g0, int g1, int g2, int g3)
+{
+    return (uint32_t)(g0 + 3 * g1) | ((uint32_t)(g2 + 3 * g3) << 4);
+}
+__host__ __device__ __forceinline__ void sgb_unpack_nibble(uint32_t n, int &a, int &b)
+{
+    b = (int)((n * 11u) >> 5);      // n / 3 for n in 0..8
+    a = (int)n - 3 * b;
+}
+
 int k_grid_blocks(sgb_ctx *h, int64_t n)
 {
     int64_t b = cdiv(n, 256 * 4);
@@ -110,18 +123,17 @@ __global__ void repack_kernel(const uint8_t *__restrict__ bed, int64_t B0, const
     if (b >= B) return;
     const uint8_t *row = bed + (int64_t)src_rows[r] * B0;
     int fl = fill[r];
-    uint32_t o = 0;
+    int gq[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         int64_t k = 4 * b + j;
         if (k < N) {
             int64_t src = identity ? k : (int64_t)sub_idx[k] - 1;
             int code = (row[src >> 2] >> ((src & 3) << 1)) & 3;
-            int g = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fl));
-            o |= (uint32_t)g << (2 * j);
+            gq[j] = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fl));
         }
     }
-    out[r * out_stride + b] = (uint8_t)o;
+    out[r * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
 }
 
 int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_rows, const int32_t *d_fill,
@@ -154,13 +166,18 @@ __global__ void __launch_bounds__(256) transpose_kernel(const uint8_t *__restric
     __syncthreads();
     int64_t i = b0 * 4 + threadIdx.x;      // sample
     if (i >= N) return;
-    int byte = threadIdx.x >> 2, sh = (threadIdx.x & 3) << 1;
+    const int byte = threadIdx.x >> 2, nsh = (threadIdx.x & 2) << 1, odd = threadIdx.x & 1;
     uint32_t o[8];
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         uint32_t acc = 0;
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc |= (uint32_t)((tile[w * 16 + j][byte] >> sh) & 3) << (2 * j);
+        for (int j = 0; j < 16; j += 2) {
+            int a0, b0, a1, b1;
+            sgb_unpack_nibble((tile[w * 16 + j][byte] >> nsh) & 15u, a0, b0);
+            sgb_unpack_nibble((tile[w * 16 + j + 1][byte] >> nsh) & 15u, a1, b1);
+            acc |= (uint32_t)((odd ? b0 : a0) + 3 * (odd ? b1 : a1)) << (2 * j);
+        }
         o[w] = acc;
     }
     uint4 *dst = reinterpret_cast<uint4 *>(Gt + i * sT + (m0 >> 2));
@@ -197,20 +214,19 @@ __global__ void synth_kernel(int mode, int64_t y0, uint64_t seed, const uint32_t
     int64_t m = mode ? rows[r] : r;
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t a0 = t0[m], a1 = t1[m];
-    uint32_t o = 0;
     int cnt = 0;
     if (b < ((N + 3) >> 2)) {
+        int gq[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int64_t i = 4 * b + j;
             if (i < N) {
                 uint32_t u = mix32(seed, (uint64_t)m, (uint64_t)i, 0);
-                int g = (u >= a0) + (u >= a1);
-                o |= (uint32_t)g << (2 * j);
-                cnt += g;
+                gq[j] = (u >= a0) + (u >= a1);
+                cnt += gq[j];
             }
         }
-        if (mode) G[r * sG + b] = (uint8_t)o;
+        if (mode) G[r * sG + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
     }
     if (!mode) {
 #pragma unroll
@@ -237,18 +253,32 @@ int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t
 // ---------------------------------------------------------------------------------------------------
 // tensor engine
 // ---------------------------------------------------------------------------------------------------
-// Decode one 32-bit word (16 genotypes, 2 bits each, value coding) into four registers of 4 x u8 via the byte
-// permute unit: the 2-bit codes, isolated on nibble boundaries, ARE the prmt selector nibbles into the byte
-// pool {0,1,2,.} (or {0,0,1,.} for the "genotype == 2" indicator plane).
-//   d[0] = genotypes {0,2,4,6}   d[1] = {8,10,12,14}   d[2] = {1,3,5,7}   d[3] = {9,11,13,15}
-__device__ __forceinline__ void decode16(uint32_t w, uint32_t pool, uint32_t (&d)[4])
+// Decode one 32-bit word (16 genotypes in pair-ternary nibbles) into four registers of 4 x u8 with the byte
+// permute unit.  A nibble n = A + 3B (0..8) is used UNMASKED as the prmt selector: selector values 0..7 pick a
+// byte of the 8-byte pool, selector 8 (A = B = 2) means "replicate the sign of pool byte 0" = 0x00.  With
+//   pool_A[idx] = c0 - plane(idx % 3)      pool_B[idx] = c0 - plane(idx / 3)
+// (plane(g) = g with c0 = 2, or plane(g) = [g == 2] with c0 = 1) both the in-pool cases and the sign case give
+// exactly c0 - plane(genotype), so no mask / shift of the 2-bit fields is needed at all:
+//   d[0] = samples {0,2,4,6}   d[1] = {8,10,12,14}   d[2] = {1,3,5,7}   d[3] = {9,11,13,15}
+// The products come out as sum (c0 - plane) * limb; recombine_kernel turns them back with the column limb sums.
+struct pk2_pools { uint32_t ax, ay, bx, by; };
+
+// raw PTX prmt (generic mode): selector bit 3 of a nibble = replicate the sign of the selected byte.  The CUDA
+// intrinsic __byte_perm masks that bit away, so it cannot be used here.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
-    uint32_t e = w & 0x33333333u;
-    uint32_t o = (w >> 2) & 0x33333333u;
-    d[0] = __byte_perm(pool, 0u, e);
-    d[1] = __byte_perm(pool, 0u, e >> 16);
-    d[2] = __byte_perm(pool, 0u, o);
-    d[3] = __byte_perm(pool, 0u, o >> 16);
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__device__ __forceinline__ void decode16(uint32_t w, const pk2_pools &pl, uint32_t (&d)[4])
+{
+    uint32_t hi = w >> 16;
+    d[0] = prmt(pl.ax, pl.ay, w);
+    d[1] = prmt(pl.ax, pl.ay, hi);
+    d[2] = prmt(pl.bx, pl.by, w);
+    d[3] = prmt(pl.bx, pl.by, hi);
 }
 
 __device__ __forceinline__ void mma_u8s8(int32_t (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -278,7 +308,7 @@ template <int MT, int NT>
 __global__ void __launch_bounds__(256, (MT * NT <= 4) ? 2 : 1)
 pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_total, int kblocks_per_chunk,
                 const int8_t *__restrict__ L, int64_t Lcol_stride, int c0, int ncol_total, int32_t *__restrict__ out,
-                uint32_t pool)
+                pk2_pools pool)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -358,7 +388,7 @@ pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_t
 
 template <int MT, int NT>
 static int launch_pk2(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kblocks, const int8_t *L,
-                      int64_t Lcol_stride, int c0, int ncol_total, int32_t *out, uint32_t pool)
+                      int64_t Lcol_stride, int c0, int ncol_total, int32_t *out, pk2_pools pool)
 {
     const int64_t rows_per_cta = 128 * MT;
     int64_t row_tiles = rows_pad / rows_per_cta;
@@ -382,8 +412,12 @@ static int launch_pk2(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows
 }
 
 int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L,
-               int ncol, int32_t *out, uint32_t pool)
+               int ncol, int32_t *out, int plane)
 {
+    // pool bytes idx 0..7: A-position value f(idx % 3), B-position value f(idx / 3); f(g) = 2-g or 1-[g==2]
+    pk2_pools pool;
+    if (plane == SGB_PLANE_VALUE) { pool.ax = 0x02000102u; pool.ay = 0x01020001u; pool.bx = 0x01020202u; pool.by = 0x00000101u; }
+    else                          { pool.ax = 0x01000101u; pool.ay = 0x01010001u; pool.bx = 0x01010101u; pool.by = 0x00000101u; }
     if (rows_pad % SGB_ROW_ALIGN || kbytes % SGB_KSTEP_BYTES || stride % SGB_KSTEP_BYTES)
         return sgb_fail(h, "k_pk2_gemm: unaligned operand (rows %lld, kbytes %lld, stride %lld)", (long long)rows_pad,
                         (long long)kbytes, (long long)stride);
@@ -419,21 +453,22 @@ __global__ void colmax_kernel(const double *__restrict__ V, int64_t len, int64_t
 }
 
 // One thread per (genotype slot i of the padded k range, column c): 8 balanced base-128 digits of
-// round(v * 2^(54-E)), E = exponent of the column max, scattered into the fragment layout (see pk2_gemm_kernel).
+// round(v * 2^(53-E)), E = exponent of the column max, scattered into the fragment layout (see pk2_gemm_kernel).
 __global__ void split_limbs_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int64_t nblk,
                                    const unsigned long long *__restrict__ mx, int8_t *__restrict__ L,
-                                   double *__restrict__ mult)
+                                   double *__restrict__ mult, int32_t *__restrict__ limbsum)
 {
     int c = blockIdx.y;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nblk * 256) return;
     unsigned long long mb = mx[c];
     int E = (int)((mb >> 52) & 0x7FF) - 1023;
     if (E < -1000) E = -1000;
     if (E > 1000) E = 1000;            // inf/nan columns produce garbage, like any fp arithmetic would
     long long q = 0;
-    if (i < len && mb) q = __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 54 - E));
-    if (i == 0) mult[c] = mb ? scalbn(1.0, E - 54) : 0.0;
+    // |v| < 2^(E+1)  =>  |q| <= 2^54, inside the range of 8 balanced base-128 digits (|.| <= 63*(128^8-1)/127 ~ 2^54.99)
+    if (i < len && mb) q = __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E));
+    if (i == 0) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
+    const bool inb = i < nblk * 256;
     int r = (int)(i & 255);
     int64_t blk = i >> 8;
     int t = r >> 6, wi = (r >> 4) & 3, p = r & 15;
@@ -444,11 +479,17 @@ __global__ void split_limbs_kernel(const double *__restrict__ V, int64_t len, in
     for (int l = 0; l < SGB_LIMBS; l++) {
         int d = (int)((q + 64) & 127) - 64;
         q = (q - d) >> 7;
-        base[l * 256] = (int8_t)d;     // lane = l*4 + t  -> +l*4*64 bytes
+        if (inb) base[l * 256] = (int8_t)d;     // lane = l*4 + t  -> +l*4*64 bytes
+        // column sum of this limb (exact integers): undoes the c0 - plane offset of the decode in recombine_kernel
+        int sres = d;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
+        if ((threadIdx.x & 31) == 0 && sres) atomicAdd(&limbsum[c * SGB_LIMBS + l], sres);
     }
 }
 
-int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult)
+int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult,
+                  int32_t *d_limbsum)
 {
     unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);   // k <= 1024 slots
     if (k > 1024) return sgb_fail(h, "too many columns (%d)", k);
@@ -458,14 +499,15 @@ int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, i
     if (gx < 1) gx = 1;
     colmax_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
     LAUNCH_CHECK(h);
-    split_limbs_kernel<<<dim3((unsigned)nblk, k), 256, 0, h->stream>>>(V, len, ld, nblk, mx, L, d_mult);
+    CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * SGB_LIMBS * k, h->stream));
+    split_limbs_kernel<<<dim3((unsigned)nblk, k), 256, 0, h->stream>>>(V, len, ld, nblk, mx, L, d_mult, d_limbsum);
     LAUNCH_CHECK(h);
     return 0;
 }
 
 // raw[r + c*ld] = (sum_l acc[r][c*8+l] * 128^l) * mult[c];  acc is reset to 0 for the next product.
 __global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k, const double *__restrict__ mult,
-                                 double *__restrict__ raw, int64_t ld)
+                                 const int32_t *__restrict__ limbsum, int c0, double *__restrict__ raw, int64_t ld)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * k) return;
@@ -475,16 +517,23 @@ __global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k,
     int4 lo = p[0], hi = p[1];
     p[0] = make_int4(0, 0, 0, 0);
     p[1] = make_int4(0, 0, 0, 0);
+    // acc = sum (c0 - plane) * limb  ->  sum plane * limb = c0 * (column limb sum) - acc
+    const int4 *ls = reinterpret_cast<const int4 *>(limbsum + c * 8);
+    int4 s0 = ls[0], s1 = ls[1];
+    lo.x = c0 * s0.x - lo.x; lo.y = c0 * s0.y - lo.y; lo.z = c0 * s0.z - lo.z; lo.w = c0 * s0.w - lo.w;
+    hi.x = c0 * s1.x - hi.x; hi.y = c0 * s1.y - hi.y; hi.z = c0 * s1.z - hi.z; hi.w = c0 * s1.w - hi.w;
     long long l4 = (long long)lo.x + ((long long)lo.y << 7) + ((long long)lo.z << 14) + ((long long)lo.w << 21);
     long long h4 = (long long)hi.x + ((long long)hi.y << 7) + ((long long)hi.z << 14) + ((long long)hi.w << 21);
     double v = (double)h4 * 268435456.0 + (double)l4;    // 128^4 = 2^28; both halves exact (< 2^53)
     raw[r + (int64_t)c * ld] = v * mult[c];
 }
 
-int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, double *raw, int64_t ld)
+int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
+                double *raw, int64_t ld)
 {
     if (rows * k == 0) return 0;
-    recombine_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, d_mult, raw, ld);
+    recombine_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, d_mult, d_limbsum,
+                                                                           plane == SGB_PLANE_VALUE ? 2 : 1, raw, ld);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -508,13 +557,12 @@ __global__ void rowdot_f64_kernel(const uint8_t *__restrict__ G, int64_t sG, int
             uint32_t x = row[w];
             int64_t i0 = w << 4;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                int64_t i = i0 + j;
-                uint32_t cd = (x >> (2 * j)) & 3u;
-                if (cd && i < N) {
-                    double bv = b[i];
-                    if (cd == 1) s1 += bv; else s2 += bv;
-                }
+            for (int j = 0; j < 8; j++) {
+                int ga, gb;
+                sgb_unpack_nibble((x >> (4 * j)) & 15u, ga, gb);
+                int64_t i = i0 + 2 * j;
+                if (ga && i < N) { double bv = b[i]; if (ga == 1) s1 += bv; else s2 += bv; }
+                if (gb && i + 1 < N) { double bv = b[i + 1]; if (gb == 1) s1 += bv; else s2 += bv; }
             }
         }
         double s = warp_sum(s1 + 2.0 * s2);
@@ -549,9 +597,11 @@ __global__ void coldot_f64_kernel(const uint8_t *__restrict__ G, int64_t sG, int
         if (!x) continue;
         double a1 = d1[m], a2 = D2 ? d2[m] : 2.0 * a1;
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            uint32_t cd = (x >> (2 * j)) & 3u;
-            acc[j] += cd == 1 ? a1 : (cd == 2 ? a2 : 0.0);
+        for (int j = 0; j < 8; j++) {
+            int ga, gb;
+            sgb_unpack_nibble((x >> (4 * j)) & 15u, ga, gb);
+            acc[2 * j] += ga == 1 ? a1 : (ga == 2 ? a2 : 0.0);
+            acc[2 * j + 1] += gb == 1 ? a1 : (gb == 2 ? a2 : 0.0);
         }
     }
 #pragma unroll

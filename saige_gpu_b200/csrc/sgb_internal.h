@@ -6,7 +6,7 @@
 #include <vector>
 #include "saige_b200.h"
 
-#define SGB_LIMBS 8          // signed base-128 digits per fp64 value (56-bit fixed point)
+#define SGB_LIMBS 8          // signed base-128 digits per fp64 value (55-bit fixed point: round(v * 2^(53-E)))
 #define SGB_KSTEP_BYTES 64   // packed bytes (256 genotypes) consumed per k-step of the tensor kernel
 #define SGB_ROW_ALIGN 512    // row padding of both genotype copies (CTA tile of the tensor kernel)
 #define SGB_SHARD_BLOCK 1024 // markers per block of the block-cyclic marker->rank map
@@ -38,7 +38,7 @@ struct sgb_ctx {
     std::vector<int64_t> loc2glob;           // local row -> global QC'd marker index (monotone)
 
     // device genotype store, device coding: 2 bits per genotype = number of A1 copies (0,1,2), sample i of a
-    // marker at bits 2(i%4) of byte i/4; all padding is genotype 0.
+    // marker in the pair-ternary nibble coding of kernels.cu (sgb_pack4); all padding is genotype 0.
     uint8_t *dG = nullptr;   int64_t sG = 0, rowsG = 0;   // marker-major  [rowsG][sG],  rowsG>=Mloc
     uint8_t *dGt = nullptr;  int64_t sT = 0, rowsT = 0;   // sample-major  [rowsT][sT],  rowsT>=N
     double *d_f2 = nullptr;  // 2*f_m      per local marker
@@ -67,6 +67,7 @@ struct sgb_ctx {
     double *d_pcg = nullptr; size_t pcg_elems = 0;    // PCG state arena
     double *d_ai = nullptr; size_t ai_elems = 0;      // per-call arena of the AI-REML entry points
     int *d_idx = nullptr;                             // small int scratch (8192 ints)
+    int32_t *d_limbsum = nullptr;                     // [2][1024][8] column limb sums of the current split
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_sweep_ms[2] = {0.f, 0.f};
@@ -103,12 +104,15 @@ int k_transpose(sgb_ctx *h);   // dG -> dGt
 int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, int32_t *d_ac);
 
 // tensor engine: out[r][c*8+l] += sum_k P[r][k] * L[c][k][l]  (int32, exact)
+enum { SGB_PLANE_VALUE = 0, SGB_PLANE_IS2 = 1 };   // which function of the genotype the decode feeds the MMA
 int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L,
-               int ncol, int32_t *out, uint32_t pool);
-// limb preparation: V[len x k] (ld) -> fragments [k][nblk][2048] + per-column multiplier (2^(E-54)) in d_mult[k]
-int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult);
+               int ncol, int32_t *out, int plane);
+// limb preparation: V[len x k] (ld) -> fragments [k][nblk][2048] + per-column multiplier (2^(E-53)) in d_mult[k]
+int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult,
+                  int32_t *d_limbsum);
 // raw[r + c*ld] = recombine(acc[r][c*8..]) * mult[c]; acc zeroed
-int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, double *raw, int64_t ld);
+int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
+                double *raw, int64_t ld);
 
 // f64 engine
 int k_rowdot_f64(sgb_ctx *h, const double *B, int64_t ldb, int k, double *out, int64_t ldo);   // out[m,c]=sum_i g_mi B[i,c]

@@ -68,11 +68,11 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     SGB_TRY(k_colsum(h, dB, N, N, k, sc + SC_COLSUM));
     // ---- sweep 1: raw1[m,c] = g_m . b_c over the marker-major copy ----
     if (tensor) {
-        SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1));
+        SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1, h->d_limbsum));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
-        SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, 0x00020100u));
+        SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
-        SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, sc + SC_MULT1, raw1, rowsG));
+        SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
     } else {
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
         SGB_TRY(k_rowdot_f64(h, dB, N, k, raw1, rowsG));
@@ -82,11 +82,11 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     SGB_TRY(k_sweep1_post(h, raw1, rowsG, k, sc + SC_COLSUM, lo, hi, D, sc + SC_T));
     // ---- sweep 2: raw2[i,c] = sum_m g_mi D[m,c] over the sample-major copy ----
     if (tensor) {
-        SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2));
+        SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2, h->d_limbsum + 8192));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
-        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, 0x00020100u));
+        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, sc + SC_MULT2, raw2, rowsT));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
     } else {
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
         SGB_TRY(k_coldot_f64(h, D, nullptr, rowsG, k, raw2, rowsT));
@@ -126,12 +126,12 @@ static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const
     if (h->engine == SGB_ENGINE_TENSOR) {
         SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)nc * nblkM * 2048));
         SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * nc));
-        SGB_TRY(k_split_limbs(h, D1, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT1));
-        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, 0x00020100u));   // value plane
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT1, r1, rowsT));
-        SGB_TRY(k_split_limbs(h, D2, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT2));
-        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, 0x00010000u));   // [g==2] plane
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT2, r2, rowsT));
+        SGB_TRY(k_split_limbs(h, D1, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT1, h->d_limbsum));
+        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_VALUE));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, r1, rowsT));
+        SGB_TRY(k_split_limbs(h, D2, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT2, h->d_limbsum + 8192));
+        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_IS2));   // [g==2] plane
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_IS2, r2, rowsT));
     } else {
         // weight of g==2 is 2*D1 + D2; fold it into one pass and leave r2 = 0
         SGB_TRY(k_axpby(h, 2.0, D1, 1.0, D2, rowsG * nc, D2));
@@ -737,16 +737,16 @@ extern "C" int sgb_bench_crossprod_device(sgb_ctx *h, int k, int reps, uint64_t 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int r = 0; r < reps; r++) {
-        h->time_sweeps = (r == reps - 1);
+        h->time_sweeps = true;
         CUDA_OK(h, cudaEventRecord(e0, h->stream));
         int rc = sgb_crossprod_device(h, dB, k, dY, 0);
         if (rc) { h->time_sweeps = false; cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
         CUDA_OK(h, cudaEventRecord(e1, h->stream));
         CUDA_OK(h, cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ms_out[r], e0, e1);
+        if (ms_kernel_out) { ms_kernel_out[2 * r] = h->last_sweep_ms[0]; ms_kernel_out[2 * r + 1] = h->last_sweep_ms[1]; }
     }
     h->time_sweeps = false;
-    if (ms_kernel_out) { ms_kernel_out[0] = h->last_sweep_ms[0]; ms_kernel_out[1] = h->last_sweep_ms[1]; }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }

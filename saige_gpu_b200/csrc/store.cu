@@ -66,6 +66,7 @@ static int create_common(int device, sgb_ctx **out)
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
     if (cudaMalloc((void **)&h->d_scal, sizeof(double) * 8192) != cudaSuccess ||
         cudaMalloc((void **)&h->d_idx, sizeof(int) * 8192) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_limbsum, sizeof(int32_t) * 16384) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_scal, sizeof(double) * 8192) != cudaSuccess) {
         delete h;
         return sgb_fail(nullptr, "scalar scratch allocation failed");
@@ -114,7 +115,7 @@ extern "C" void sgb_destroy(sgb_ctx *h)
     cudaStreamSynchronize(h->stream);
     sgb_dist_destroy(h);
     free_store(h);
-    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx};
+    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx, h->d_limbsum};
     for (auto p : ptrs) if (p) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -429,9 +430,16 @@ extern "C" int sgb_get_mac_vec_for_var_ratio(sgb_ctx *h, int32_t *out) { NEED_LO
 extern "C" int sgb_get_index_vec_for_var_ratio(sgb_ctx *h, int32_t *out) { NEED_LOADED(h); std::copy(h->index_vr.begin(), h->index_vr.end(), out); return 0; }
 extern "C" int sgb_get_qcd_marker_index(sgb_ctx *h, uint8_t *out) { NEED_LOADED(h); std::copy(h->qc_mask.begin(), h->qc_mask.end(), out); return 0; }
 
+// pair-ternary nibble coding of the device store (kernels.cu: sgb_pack4): nibble = A + 3B
+static inline int decode_sample(const uint8_t *row, int64_t i)
+{
+    unsigned n = (row[i >> 2] >> ((i & 2) << 1)) & 15u;
+    unsigned b = (n * 11u) >> 5;
+    return (i & 1) ? (int)b : (int)(n - 3 * b);
+}
 static void decode_row(const uint8_t *row, int64_t N, int32_t *out)
 {
-    for (int64_t i = 0; i < N; i++) out[i] = (row[i >> 2] >> ((i & 3) << 1)) & 3;
+    for (int64_t i = 0; i < N; i++) out[i] = decode_sample(row, i);
 }
 
 // Get_OneSNP_Geno (FG.cpp:223-272).  In a multi-rank run the row lives on one rank; the owner broadcasts it.
@@ -452,7 +460,7 @@ extern "C" int sgb_get_one_snp_geno(sgb_ctx *h, int64_t idx, int32_t *out)
     if (h->world > 1) {
         // sum-allreduce of the decoded row (non-owners contribute zeros)
         std::vector<double> tmp(h->N, 0.0);
-        if (mine) for (int64_t i = 0; i < h->N; i++) tmp[i] = (row[i >> 2] >> ((i & 3) << 1)) & 3;
+        if (mine) for (int64_t i = 0; i < h->N; i++) tmp[i] = decode_sample(row.data(), i);
         SGB_TRY(sgb_ensure(h, (void **)&h->d_io, &h->io_elems, sizeof(double) * h->N));
         CUDA_OK(h, cudaMemcpyAsync(h->d_io, tmp.data(), sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
         SGB_TRY(sgb_allreduce_sum(h, h->d_io, h->N));

@@ -30,12 +30,14 @@ def chromosomes(M):
     return chrs
 
 
-def phenotype(N, seed, prevalence=0.1):
-    """x1 ~ N(0,1), x2 ~ Bernoulli(0.5), binary y with the given prevalence and a random-effect-like noise term."""
+def phenotype(N, seed, prevalence=0.1, gterm=None):
+    """x1 ~ N(0,1), x2 ~ Bernoulli(0.5), binary y with the given prevalence; `gterm` is the polygenic part of the
+    liability (a combination of standardised genotypes), unstructured noise when not given."""
     rng = np.random.default_rng(seed + 1)
     x1 = rng.normal(size=N)
     x2 = rng.integers(0, 2, size=N).astype(np.float64)
-    gterm = rng.normal(scale=0.6, size=N)
+    if gterm is None:
+        gterm = rng.normal(scale=0.6, size=N)
     eta = np.log(prevalence / (1 - prevalence)) + 0.5 * x1 + 0.3 * x2 + gterm
     y = (rng.uniform(size=N) < 1 / (1 + np.exp(-eta))).astype(np.float64)
     yq = 0.5 * x1 + 0.3 * x2 + gterm + rng.normal(size=N)

@@ -1,0 +1,79 @@
+"""The C-ABI library loads and exports every symbol include/saige_b200.h declares; without a GPU the compute path
+refuses to run (no CPU fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "saige_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(sgb_[a-z0-9_]+)\s*\(", src))
+    names -= {"sgb_probe_fn"}
+    return sorted(names)
+
+
+def test_header_declares_the_hot_path():
+    names = declared_symbols()
+    for must in ("sgb_setgeno", "sgb_get_crossprod_mat_and_kin", "sgb_get_crossprod_mat_and_kin_loco",
+                 "sgb_get_diag_of_kin", "sgb_get_pcg1_of_sigma_and_vector", "sgb_get_coefficients", "sgb_get_ai_score",
+                 "sgb_get_ai_score_q", "sgb_fit_glmmai_rpcg", "sgb_fit_glmmai_rpcg_q", "sgb_get_sigma_x", "sgb_get_sigma_g",
+                 "sgb_set_diag_of_stdgeno_loco", "sgb_create_dist"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from saige_gpu_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build it first: python -c 'import __graft_entry__ as g; g.build()'"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(L, name), "libsaige_b200.so does not export %s" % name
+
+
+def test_binding_covers_every_declared_symbol():
+    from saige_gpu_b200 import _lib
+    assert set(_lib.EXPORTED_SYMBOLS) == set(declared_symbols())
+    _lib.lib()
+
+
+def test_library_has_no_torch_or_oracle_dependency():
+    import subprocess
+    from saige_gpu_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "libcudart" in out
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "saige_gpu_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "saige_oracle" not in txt.replace(
+                    "oracle/saige_oracle.c", ""), f
+
+
+def test_no_cpu_fallback_without_gpu():
+    from saige_gpu_b200 import SaigeB200, SaigeB200Error
+    cudart = ctypes.CDLL("libcudart.so.12")
+    n = ctypes.c_int(0)
+    if cudart.cudaGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(SaigeB200Error, match="no CPU fallback"):
+        SaigeB200(device=0)
+
+
+def test_host_helpers_without_device():
+    """calCV / innerProduct are pure host functions of the ABI (FG.cpp:3104-3110)."""
+    import numpy as np
+    from saige_gpu_b200 import _lib
+    L = _lib.lib()
+    x = np.array([1.0, 2.0, 4.0, 8.0])
+    cv = L.sgb_cal_cv(x.ctypes.data, 4)
+    assert abs(cv - (np.std(x, ddof=1) / np.mean(x)) / 4) < 1e-15
+    y = np.array([1.0, -1.0, 0.5, 2.0])
+    assert L.sgb_inner_product(x.ctypes.data, y.ctypes.data, 4) == float(x @ y)

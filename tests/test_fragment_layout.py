@@ -7,7 +7,7 @@ LIMBS = 8
 
 
 def split_limbs(v, E):
-    q = np.rint(np.ldexp(v, 54 - E)).astype(np.int64)
+    q = np.rint(np.ldexp(v, 53 - E)).astype(np.int64)
     out = np.zeros((len(v), LIMBS), dtype=np.int64)
     for l in range(LIMBS):
         d = ((q + 64) & 127) - 64
@@ -25,14 +25,37 @@ def frag_offset(r, l):
     return (l * 4 + t) * 64 + j * 8 + half * 4 + slot
 
 
-def decode16(w, pool=(0, 1, 2, 3)):
-    """mirrors decode16(): returns 4 registers, each a list of 4 byte values"""
-    e = w & 0x33333333
-    o = (w >> 2) & 0x33333333
+POOLS = {  # (ax, ay, bx, by) exactly as in k_pk2_gemm
+    "value": (0x02000102, 0x01020001, 0x01020202, 0x00000101),
+    "is2": (0x01000101, 0x01010001, 0x01010101, 0x00000101),
+}
 
-    def prmt(sel):
-        return [pool[(sel >> (4 * s)) & 7] for s in range(4)]
-    return [prmt(e & 0xFFFF), prmt(e >> 16), prmt(o & 0xFFFF), prmt(o >> 16)]
+
+def prmt(a, b, sel):
+    """PTX prmt.b32 generic mode: nibble bits 0-2 pick a byte of {a,b}; bit 3 replicates that byte's sign."""
+    pool = [(a >> (8 * i)) & 255 for i in range(4)] + [(b >> (8 * i)) & 255 for i in range(4)]
+    out = []
+    for s in range(4):
+        n = (sel >> (4 * s)) & 15
+        v = pool[n & 7]
+        out.append((255 if v & 128 else 0) if n & 8 else v)
+    return out
+
+
+def decode16(w, plane="value"):
+    """mirrors decode16(): returns 4 registers, each a list of 4 byte values"""
+    ax, ay, bx, by = POOLS[plane]
+    hi = w >> 16
+    return [prmt(ax, ay, w), prmt(ax, ay, hi), prmt(bx, by, w), prmt(bx, by, hi)]
+
+
+def pack_row(geno):
+    """pair-ternary nibble coding (sgb_pack4): nibble = A + 3B"""
+    n = len(geno)
+    out = np.zeros((n + 3) // 4, dtype=np.uint8)
+    g = np.concatenate([geno, np.zeros((-n) % 4, dtype=geno.dtype)])
+    out[:] = (g[0::4] + 3 * g[1::4]) | ((g[2::4] + 3 * g[3::4]) << 4)
+    return out
 
 
 def test_recombination_is_exact_enough():
@@ -42,8 +65,18 @@ def test_recombination_is_exact_enough():
     E = int(np.floor(np.log2(mx)))
     limbs = split_limbs(v, E)
     assert limbs.min() >= -64 and limbs.max() <= 63
-    rec = sum(limbs[:, l].astype(np.float64) * 128.0 ** l for l in range(LIMBS)) * 2.0 ** (E - 54)
-    assert np.max(np.abs(rec - v)) <= 2.0 ** (E - 54)          # half an ulp of the fixed-point grid, doubled for slack
+    rec = sum(limbs[:, l].astype(np.float64) * 128.0 ** l for l in range(LIMBS)) * 2.0 ** (E - 53)
+    assert np.max(np.abs(rec - v)) <= 2.0 ** (E - 53)          # half an ulp of the fixed-point grid, doubled for slack
+
+
+def test_limb_range_covers_the_largest_mantissa():
+    """The column maximum may sit just below 2^(E+1); its fixed-point image must still fit 8 balanced digits."""
+    for top in (1.0, 1.5, 1.984375, 1.9999999999999998):
+        v = np.array([top, -top, top * 0.37, 1e-30, 0.0]) * 2.0 ** 7
+        E = int(np.floor(np.log2(np.abs(v).max())))
+        limbs = split_limbs(v, E)                      # asserts that no carry is left after 8 digits
+        rec = sum(limbs[:, l].astype(np.float64) * 128.0 ** l for l in range(LIMBS)) * 2.0 ** (E - 53)
+        assert np.max(np.abs(rec - v)) <= 2.0 ** (E - 53)
 
 
 def test_fragment_offsets_are_a_bijection():
@@ -58,9 +91,7 @@ def test_warp_tile_product_matches_dense():
     """One warp, one k-step (64 bytes = 256 genotypes per row), 16 rows, one limb column group."""
     rng = np.random.default_rng(7)
     geno = rng.integers(0, 3, size=(16, 256))
-    packed = np.zeros((16, 64), dtype=np.uint8)
-    for i in range(256):
-        packed[:, i >> 2] |= (geno[:, i] << (2 * (i & 3))).astype(np.uint8)
+    packed = np.stack([pack_row(geno[r]) for r in range(16)])
     b = rng.normal(size=256)
     E = int(np.floor(np.log2(np.abs(b).max())))
     limbs = split_limbs(b, E)                     # 256 x 8
@@ -88,14 +119,20 @@ def test_warp_tile_product_matches_dense():
                 Bm[4 * t + s, g] = b0[s]; Bm[16 + 4 * t + s, g] = b1[s]
         C += A @ Bm
     expect = geno @ limbs
+    # the decode feeds (2 - g); recombine_kernel undoes it with the column limb sums
+    C = 2 * limbs.sum(0)[None, :] - C
     assert np.array_equal(C, expect)
-    rec = sum(C[:, l].astype(np.float64) * 128.0 ** l for l in range(LIMBS)) * 2.0 ** (E - 54)
+    rec = sum(C[:, l].astype(np.float64) * 128.0 ** l for l in range(LIMBS)) * 2.0 ** (E - 53)
     assert np.allclose(rec, geno @ b, rtol=1e-12, atol=1e-12)
 
 
-def test_indicator_plane_pool():
-    w = 0b10_01_00_10_10_00_01_10_00_00_10_01_10_10_01_00
-    val = decode16(w, pool=(0, 1, 2, 3))
-    ind = decode16(w, pool=(0, 0, 1, 0))
-    for a, b in zip(val, ind):
-        assert [int(x == 2) for x in a] == b
+def test_decode_planes_cover_all_nine_nibbles():
+    rng = np.random.default_rng(3)
+    geno = np.concatenate([np.array([2, 2, 0, 0, 1, 2, 2, 1, 0, 1, 1, 0, 2, 0, 1, 1]), rng.integers(0, 3, 48)])
+    words = pack_row(geno).view(np.uint32)
+    order = [0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15]       # d[0], d[1], d[2], d[3]
+    for wi, w in enumerate(words):
+        val = sum(decode16(int(w), "value"), [])
+        ind = sum(decode16(int(w), "is2"), [])
+        g = geno[16 * wi + np.array([0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15])]
+        assert val == list(2 - g) and ind == list(1 - (g == 2).astype(int)), order

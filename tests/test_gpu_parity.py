@@ -29,6 +29,15 @@ def gpu():
     g.close()
 
 
+@pytest.fixture()
+def gpu2():
+    """A second, throw-away context for tests that load other genotype sets."""
+    from saige_gpu_b200 import SaigeB200
+    g = SaigeB200(device=0)
+    yield g
+    g.close()
+
+
 @pytest.fixture(scope="module")
 def pair10k(gpu, grm10k):
     """GPU context and oracle both loaded with the bundled 10k-marker set, MAF >= 0.01, missing <= 0.15."""
@@ -91,6 +100,13 @@ def test_crossprod_special_vectors(pair10k):
     assert np.all(z == 0)
     e = np.zeros(o.N); e[3] = 1.0
     assert rel(g.getCrossprodMatAndKin(e), o.getCrossprodMatAndKin(e)) < TOL_MATVEC
+    # column maxima just below a power of two exercise the top of the fixed-point limb range
+    rng = np.random.default_rng(11)
+    for top in (1.984375, 1.9999999999999998, 1.0, 3.999):
+        v = rng.uniform(-1, 1, size=o.N)
+        v[rng.integers(0, o.N, 5)] = top
+        v[rng.integers(0, o.N, 5)] = -top
+        assert rel(g.getCrossprodMatAndKin(v), o.getCrossprodMatAndKin(v)) < TOL_MATVEC, top
 
 
 def test_crossprod_is_linear_and_symmetric(pair10k):
@@ -122,7 +138,8 @@ def test_diag_of_kin(pair10k, engine):
     g.set_engine("tensor")
 
 
-def test_loco_products_and_diag(gpu, chr22):
+def test_loco_products_and_diag(gpu2, chr22):
+    gpu = gpu2
     from oracle import oracle as O
     from saige_gpu_b200 import step1
     N0, M0 = chr22["N0"], chr22["M0"]
@@ -148,7 +165,8 @@ def test_loco_products_and_diag(gpu, chr22):
         assert it == ito and rel(x, xo) < TOL_FIT
 
 
-def test_ingest_missing_subset_and_vr_holdout(gpu):
+def test_ingest_missing_subset_and_vr_holdout(gpu2):
+    gpu = gpu2
     """Synthetic .bed with 2% missing calls, a phenotyped subset in shuffled order and a VR hold-out index set."""
     from oracle import oracle as O
     N0, M0 = 1237, 3000

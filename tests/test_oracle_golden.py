@@ -1,0 +1,150 @@
+"""Pins the CPU oracle against the reference's own fixtures and checks its internal consistency (no GPU).
+
+Golden vectors available for this path:
+  * extdata/input/plinkforGRM_1000samples_10kMarkers.frq  <-> .bed : A1 frequency of all 10,000 markers
+    (pins 2-bit decode, allele counting convention, MAF filter) -- committed as tests/golden/grm10k.*
+  * extdata/output/example_binary.rda / .varianceRatio.txt: theta=(1, 0.33267712593078613),
+    varianceRatio 0.94022084164312 -- scale-of-answer sanity only (their .bed is missing from the reference mount,
+    and they depend on R's RNG); same cohort / phenotype file as used here.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+@pytest.fixture(scope="module")
+def o10k(grm10k):
+    o = O.OracleGeno()
+    o.minMAF, o.maxMissing = 0.01, 0.15
+    o.setgeno(grm10k["bed"], grm10k["N0"], grm10k["M0"], np.arange(1, grm10k["N0"] + 1), np.ones(grm10k["N0"], np.uint8))
+    return o
+
+
+def test_frq_golden_exact(grm10k, golden_dir):
+    o = O.OracleGeno()            # no QC: all 10,000 markers
+    o.setgeno(grm10k["bed"], grm10k["N0"], grm10k["M0"], np.arange(1, 1001), np.ones(1000, np.uint8))
+    lines = open(os.path.join(golden_dir, "grm10k.frq")).readlines()[1:]
+    frq = np.array([float(l.split()[4]) for l in lines])
+    nchr = np.array([int(l.split()[5]) for l in lines])
+    assert o.M == 10000 and np.all(nchr == 2000)
+    mine = o.ACVec / 2000.0
+    assert np.max(np.abs(mine - frq)) == 0.0 or all(float("%.4g" % a) == b for a, b in zip(mine, frq))
+    # float32 values the reference stores (FG.cpp:484) are the rounded exact ratios
+    assert np.array_equal(o.alleleFreqVec, (o.ACVec / np.float32(2000)).astype(np.float32))
+
+
+def test_qc_counts_match_survey(o10k):
+    assert o10k.M == 9650                      # markers with MAF >= 0.01
+    assert int((o10k.MACVec >= 20).sum()) == 9650
+    assert o10k.qc_mask.sum() == 9650 and len(o10k.qc_mask) == 10000
+
+
+def test_diag_reference_points(o10k):
+    d = o10k.get_DiagofKin()
+    assert np.allclose(d[:4], [1.00114237, 1.08651917, 1.03021335, 1.05902383], atol=2e-8)
+    assert abs(d.mean() - 0.99846759) < 1e-7
+
+
+def test_ref32_mode_close_to_fp64(grm10k, o10k):
+    o32 = O.OracleGeno(mode=O.REF32)
+    o32.minMAF, o32.maxMissing = 0.01, 0.15
+    o32.setgeno(grm10k["bed"], 1000, 10000, np.arange(1, 1001), np.ones(1000, np.uint8))
+    b = np.random.default_rng(0).integers(0, 2, 1000) * 2.0 - 1
+    y64, y32 = o10k.getCrossprodMatAndKin(b), o32.getCrossprodMatAndKin(b)
+    gap = np.linalg.norm(y32 - y64) / np.linalg.norm(y64)
+    assert 1e-9 < gap < 1e-5                   # fp32 reference arithmetic vs fp64 restatement (SURVEY: ~1e-6)
+
+
+def test_crossprod_equals_explicit_standardised_matrix(o10k):
+    Z = np.column_stack([o10k.Get_OneSNP_StdGeno(m) for m in range(0, 400)])
+    b = np.random.default_rng(2).normal(size=1000)
+    want = Z @ (Z.T @ b)
+    got = o10k._crossprod_range(0, 400, b)
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-12
+    diag = np.zeros(1000)
+    O.lib().orc_diag_range(o10k._g, 0, 400, 0, diag.ctypes.data)
+    assert np.allclose(diag, (Z * Z).sum(1), rtol=1e-12)
+
+
+def test_decode_and_packing_conventions(o10k):
+    g = o10k.Get_OneSNP_Geno(5)
+    assert set(np.unique(g)) <= {0, 1, 2}
+    assert g.sum() == o10k.ACVec[5]
+    z = o10k.Get_OneSNP_StdGeno(5)
+    assert abs(z.sum()) < 1e-9 and abs((z * z).sum() / 1000 - 1.0) < 0.2
+    packed = o10k.packed()
+    assert packed.shape == (9650, 250)
+    # PLINK codes after re-packing: 00 -> 2 copies, 10 -> 1, 11 -> 0, never 01 (FG.cpp:41-44,559-565)
+    codes = (packed[5][:, None] >> np.array([0, 2, 4, 6])) & 3
+    assert not np.any(codes == 1)
+
+
+def test_imputation_and_subset(golden_dir):
+    N0, M0 = 403, 500
+    bed = O.synth_bed(N0, M0, seed=5, miss_rate=0.05)
+    rng = np.random.default_rng(0)
+    keep = np.sort(rng.choice(N0, 300, replace=False))
+    sub = rng.permutation(keep) + 1
+    ind = np.zeros(N0, np.uint8); ind[keep] = 1
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.0, 1.0
+    o.setgeno(bed, N0, M0, sub, ind)
+    B0 = (N0 + 3) // 4
+    for m in (0, 7, 499):
+        raw = (bed[m * B0:(m + 1) * B0][:, None] >> np.array([0, 2, 4, 6])) & 3
+        raw = raw.reshape(-1)[:N0]
+        gmap = np.array([2, 3, 1, 0])[raw]                 # bed code -> copies of A1, 3 = missing
+        sel = gmap[sub - 1]
+        nmiss = int((sel == 3).sum())
+        ac = int(sel[sel != 3].sum())
+        fill = int(np.round(2 * np.float32(ac) / np.float32(2 * (300 - nmiss)) + 1e-12))
+        expect = np.where(sel == 3, fill, sel)
+        assert np.array_equal(o.Get_OneSNP_Geno(m), expect)
+        assert o.ACVec[m] == expect.sum()
+
+
+def test_pcg_solves_sigma_system(o10k):
+    rng = np.random.default_rng(1)
+    w = rng.uniform(0.05, 0.25, 1000)
+    tau = np.array([1.0, 0.5])
+    b = rng.normal(size=1000)
+    x, it = o10k.getPCG1ofSigmaAndVector(w, tau, b, 500, 1e-5, return_iter=True)
+    r = b - o10k.getCrossprod(x, w, tau)
+    assert r @ r <= 1e-5 and 1 <= it < 100
+
+
+def test_loco_consistency(chr22):
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.01, 0.15
+    o.setgeno(chr22["bed"], chr22["N0"], chr22["M0"], np.arange(1, 1001), np.ones(1000, np.uint8))
+    chrq = chr22["chrs"][o.qc_mask]
+    LOCO, s, e = O.updateChrStartEndIndexVec(chrq)
+    assert LOCO and np.all(s >= 0) and o.M == 864
+    o.setStartEndIndexVec(s, e)
+    o.set_Diagof_StdGeno_LOCO()
+    assert o.Msub_byChr.sum() == o.M
+    b = np.random.default_rng(0).normal(size=1000)
+    tot = np.zeros(1000)
+    for j in range(22):
+        o.setStartEndIndex(s[j], e[j], j)
+        yl = o.getCrossprodMatAndKin_LOCO(b)
+        tot += (o._crossprod_range(0, o.M, b) - yl * (o.M - o.Msub_byChr[j]))    # = chromosome-j part
+    assert np.allclose(tot, o._crossprod_range(0, o.M, b), rtol=1e-10, atol=1e-9)
+
+
+def test_step1_scale_of_answer(o10k, golden_dir):
+    """Same cohort and phenotype as the reference's bundled example; different marker set and RNG, so only the
+    scale of the answer is comparable: example_binary.rda has theta = (1, 0.3327), varianceRatio.txt 0.9402."""
+    rows = [l.split() for l in open(os.path.join(golden_dir, "pheno_1000samples.txt"))]
+    col = {h: i for i, h in enumerate(rows[0])}
+    y = np.array([float(r[col["y_binary"]]) for r in rows[1:]])
+    X = np.column_stack([np.ones(1000), [float(r[col["x1"]]) for r in rows[1:]], [float(r[col["x2"]]) for r in rows[1:]]])
+    assert int(y.sum()) == 98                                # 98 cases / 902 controls
+    U = np.random.default_rng(200).integers(0, 2, size=(1000, 130)) * 2.0 - 1.0
+    fit0 = O.glm_fit(y, X, O.Binomial)
+    m = O.glmmkin_ai_PCG(o10k, fit0, (0, 0), U, trait="binary")
+    assert m["converged"] and m["theta"][0] == 1.0
+    assert 0.2 < m["theta"][1] < 0.5                         # reference: 0.3327 / 0.3350 on its 128k-marker set
+    vr, _ = O.extractVarianceRatio(o10k, m, O.Binomial, np.random.default_rng(1).permutation(o10k.M)[:200])
+    assert 0.85 < vr < 1.05                                  # reference: 0.9402
