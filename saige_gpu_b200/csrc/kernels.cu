@@ -302,10 +302,11 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t *p)
 // out[r][c*8+l] += sum over this CTA's k-chunk of  P[r][.] * L[c][.][l]
 //   P      : packed rows, `stride` bytes each (multiple of 64), rows padded to a multiple of 128*MT
 //   L      : limb fragments, per column c: nblk blocks of 2048 bytes; block = 256 genotypes x 8 limbs laid out
-//            [lane(32)][mma j(8)][b0/b1(2)][byte(4)] so that a lane's 64 bytes are its B fragments of the 8 MMAs
+//            [mma pair(4)][lane(32)][mma of the pair(2)][b0/b1(2)][byte(4)]: one coalesced 16-byte load per lane and
+//            MMA pair brings the B fragments {b0,b1} of MMAs 2q and 2q+1
 //   grid   : x = k-chunks, y = row tiles of 128*MT rows;  8 warps, each MT m16 tiles
 template <int MT, int NT>
-__global__ void __launch_bounds__(256, (MT * NT <= 4) ? 2 : 1)
+__global__ void __launch_bounds__(256, (MT * NT <= 8) ? 2 : 1)   // <=128 regs for the k=1 path, 255 for wide tiles
 pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_total, int kblocks_per_chunk,
                 const int8_t *__restrict__ L, int64_t Lcol_stride, int c0, int ncol_total, int32_t *__restrict__ out,
                 pk2_pools pool)
@@ -326,7 +327,7 @@ pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_t
             for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
 
     const uint8_t *pa = P + (row0 + g) * stride + kb0 * SGB_KSTEP_BYTES + 16 * t;
-    const int8_t *pl = L + (int64_t)c0 * Lcol_stride + kb0 * 2048 + lane * 64;
+    const int8_t *pl = L + (int64_t)c0 * Lcol_stride + kb0 * 2048 + lane * 16;
 
     uint4 raw[MT][2];
 #pragma unroll
@@ -335,29 +336,26 @@ pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_t
         raw[a][1] = ldg_stream(pa + (int64_t)(16 * a + 8) * stride);
     }
 
+#pragma unroll 1
     for (int64_t kb = kb0; kb < kb1; kb++) {
-        uint4 cur[MT][2];
-#pragma unroll
-        for (int a = 0; a < MT; a++) { cur[a][0] = raw[a][0]; cur[a][1] = raw[a][1]; }
-        if (kb + 1 < kb1) {
-            const uint8_t *pn = pa + (kb + 1 - kb0) * SGB_KSTEP_BYTES;
-#pragma unroll
-            for (int a = 0; a < MT; a++) {
-                raw[a][0] = ldg_stream(pn + (int64_t)(16 * a) * stride);
-                raw[a][1] = ldg_stream(pn + (int64_t)(16 * a + 8) * stride);
-            }
-        }
         uint4 bf[NT][4];
 #pragma unroll
         for (int n = 0; n < NT; n++) {
             const uint4 *q = reinterpret_cast<const uint4 *>(pl + (int64_t)n * Lcol_stride + (kb - kb0) * 2048);
 #pragma unroll
-            for (int j = 0; j < 4; j++) bf[n][j] = __ldg(q + j);
+            for (int j = 0; j < 4; j++) bf[n][j] = __ldg(q + 32 * j);       // [mma pair j][lane] : 512 B per warp load
         }
+        const bool more = kb + 1 < kb1;
+        const uint8_t *pn = pa + (kb + 1 - kb0) * SGB_KSTEP_BYTES;
 #pragma unroll
         for (int a = 0; a < MT; a++) {
-            const uint32_t wl[4] = {cur[a][0].x, cur[a][0].y, cur[a][0].z, cur[a][0].w};
-            const uint32_t wh[4] = {cur[a][1].x, cur[a][1].y, cur[a][1].z, cur[a][1].w};
+            // consume this m-tile's 2 x 16 bytes, then immediately refill the same registers for the next k-step
+            const uint32_t wl[4] = {raw[a][0].x, raw[a][0].y, raw[a][0].z, raw[a][0].w};
+            const uint32_t wh[4] = {raw[a][1].x, raw[a][1].y, raw[a][1].z, raw[a][1].w};
+            if (more) {
+                raw[a][0] = ldg_stream(pn + (int64_t)(16 * a) * stride);
+                raw[a][1] = ldg_stream(pn + (int64_t)(16 * a + 8) * stride);
+            }
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 uint32_t dl[4], dh[4];
@@ -427,7 +425,7 @@ int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
     int c = 0;
     while (c < ncol) {
         int rem = ncol - c;
-        if (rem >= 4) { SGB_TRY((launch_pk2<2, 4>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 4; }
+        if (rem >= 4) { SGB_TRY((launch_pk2<4, 4>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 4; }
         else if (rem >= 2) { SGB_TRY((launch_pk2<4, 2>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 2; }
         else { SGB_TRY((launch_pk2<4, 1>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 1; }
     }
@@ -452,39 +450,48 @@ __global__ void colmax_kernel(const double *__restrict__ V, int64_t len, int64_t
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&mx[c], m);
 }
 
-// One thread per (genotype slot i of the padded k range, column c): 8 balanced base-128 digits of
-// round(v * 2^(53-E)), E = exponent of the column max, scattered into the fragment layout (see pk2_gemm_kernel).
+// Limb split.  One thread per group of 4 genotype slots that end up in the same 32-bit B-fragment register
+// (slots r, r+2, r+4, r+6 of a 256-slot block): 8 balanced base-128 digits of round(v * 2^(53-E)), E = exponent of the
+// column max, written as 8 words into the fragment layout of pk2_gemm_kernel; plus the exact column sums of every limb.
 __global__ void split_limbs_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int64_t nblk,
                                    const unsigned long long *__restrict__ mx, int8_t *__restrict__ L,
                                    double *__restrict__ mult, int32_t *__restrict__ limbsum)
 {
     int c = blockIdx.y;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long mb = mx[c];
     int E = (int)((mb >> 52) & 0x7FF) - 1023;
     if (E < -1000) E = -1000;
     if (E > 1000) E = 1000;            // inf/nan columns produce garbage, like any fp arithmetic would
-    long long q = 0;
-    // |v| < 2^(E+1)  =>  |q| <= 2^54, inside the range of 8 balanced base-128 digits (|.| <= 63*(128^8-1)/127 ~ 2^54.99)
-    if (i < len && mb) q = __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E));
-    if (i == 0) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
-    const bool inb = i < nblk * 256;
-    int r = (int)(i & 255);
-    int64_t blk = i >> 8;
-    int t = r >> 6, wi = (r >> 4) & 3, p = r & 15;
-    int odd = p & 1, half = (p >> 3) & 1, slot = (p & 7) >> 1;
-    int j = 2 * wi + odd;
-    int8_t *base = L + ((int64_t)c * nblk + blk) * 2048 + t * 64 + j * 8 + half * 4 + slot;
+    if (u == 0) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
+    const int64_t blk = u >> 6;
+    const int v = (int)(u & 63), t = v >> 4, wi = (v >> 2) & 3, half = (v >> 1) & 1, odd = v & 1;
+    const bool inb = blk < nblk;
+    const int64_t i0 = blk * 256 + t * 64 + wi * 16 + half * 8 + odd;
+    long long q[4];
+#pragma unroll
+    for (int sl = 0; sl < 4; sl++) {
+        int64_t i = i0 + 2 * sl;
+        // |v| < 2^(E+1)  =>  |q| <= 2^54, inside the range of 8 balanced base-128 digits (|.| <= 63*(128^8-1)/127 ~ 2^54.99)
+        q[sl] = (inb && i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E)) : 0;
+    }
+    uint32_t *base = reinterpret_cast<uint32_t *>(L + ((int64_t)c * nblk + blk) * 2048 + (wi * 32 + t) * 16 + odd * 8 + half * 4);
 #pragma unroll
     for (int l = 0; l < SGB_LIMBS; l++) {
-        int d = (int)((q + 64) & 127) - 64;
-        q = (q - d) >> 7;
-        if (inb) base[l * 256] = (int8_t)d;     // lane = l*4 + t  -> +l*4*64 bytes
-        // column sum of this limb (exact integers): undoes the c0 - plane offset of the decode in recombine_kernel
-        int sres = d;
+        uint32_t word = 0;
+        int ssum = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
-        if ((threadIdx.x & 31) == 0 && sres) atomicAdd(&limbsum[c * SGB_LIMBS + l], sres);
+        for (int sl = 0; sl < 4; sl++) {
+            int d = (int)((q[sl] + 64) & 127) - 64;
+            q[sl] = (q[sl] - d) >> 7;
+            word |= (uint32_t)(d & 255) << (8 * sl);
+            ssum += d;
+        }
+        if (inb) base[l * 16] = word;             // lane = l*4 + t  ->  +l*4 lanes * 16 bytes
+        // column sum of this limb (exact integers): undoes the c0 - plane offset of the decode in recombine_kernel
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        if ((threadIdx.x & 31) == 0 && ssum) atomicAdd(&limbsum[c * SGB_LIMBS + l], ssum);
     }
 }
 
@@ -500,7 +507,7 @@ int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, i
     colmax_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
     LAUNCH_CHECK(h);
     CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * SGB_LIMBS * k, h->stream));
-    split_limbs_kernel<<<dim3((unsigned)nblk, k), 256, 0, h->stream>>>(V, len, ld, nblk, mx, L, d_mult, d_limbsum);
+    split_limbs_kernel<<<dim3((unsigned)cdiv(nblk, 4), k), 256, 0, h->stream>>>(V, len, ld, nblk, mx, L, d_mult, d_limbsum);
     LAUNCH_CHECK(h);
     return 0;
 }

@@ -93,7 +93,8 @@ int sgb_fail(sgb_ctx *h, const char *fmt, ...);
         if (rc__) return rc__;         \
     } while (0)
 
-int sgb_ensure(sgb_ctx *h, void **p, size_t *cur, size_t need_bytes);   // grow-only device buffer
+int sgb_ensure(sgb_ctx *h, void **p, size_t *cur, size_t need_bytes);   // grow-only device buffer (sizes in BYTES)
+int sgb_ensure_f64(sgb_ctx *h, double **p, size_t *cur_elems, size_t need_elems);   // same, sizes in doubles
 
 // ---- kernels.cu launchers (all on h->stream) ----
 int k_count_markers(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, int64_t nmark, const uint8_t *d_indmask,

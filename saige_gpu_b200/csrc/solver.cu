@@ -24,7 +24,7 @@ static int ensure_zeroed_i32(sgb_ctx *h, int32_t **p, size_t *cur_elems, size_t 
     return 0;
 }
 
-static int ensure_f64(sgb_ctx *h, double **p, size_t *cur_elems, size_t need_elems)
+int sgb_ensure_f64(sgb_ctx *h, double **p, size_t *cur_elems, size_t need_elems)
 {
     if (*p && *cur_elems >= need_elems) return 0;
     size_t bytes = *cur_elems * sizeof(double);
@@ -54,7 +54,7 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     }
     const int64_t nblkN = h->sG / SGB_KSTEP_BYTES, nblkM = h->sT / SGB_KSTEP_BYTES;
     // fp64 scratch: raw1 [rowsG*k] | D [rowsG*k] | raw2 [rowsT*k + k]
-    SGB_TRY(ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + rowsT + 1) * k));
+    SGB_TRY(sgb_ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + rowsT + 1) * k));
     double *raw1 = h->d_tmp, *D = raw1 + rowsG * k, *raw2 = D + rowsG * k;
     double *sc = h->d_scal;
     const bool tensor = h->engine == SGB_ENGINE_TENSOR;
@@ -114,7 +114,7 @@ static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const
     const int64_t N = h->N, rowsG = h->rowsG, rowsT = h->rowsT;
     const int64_t nblkM = h->sT / SGB_KSTEP_BYTES;
     // D1 | D2 [rowsG*nc each] | r1 | r2 [rowsT*nc each] | const[nc]
-    SGB_TRY(ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + 2 * rowsT + 1) * nc));
+    SGB_TRY(sgb_ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + 2 * rowsT + 1) * nc));
     double *D1 = h->d_tmp, *D2 = D1 + rowsG * nc, *r1 = D2 + rowsG * nc, *r2 = r1 + rowsT * nc, *cst = r2 + rowsT * nc;
     int64_t *d_rng = reinterpret_cast<int64_t *>(h->d_idx);
     if ((size_t)nc * 2 * sizeof(int64_t) > 8192 * sizeof(int)) return sgb_fail(h, "too many chromosome ranges");
@@ -200,7 +200,7 @@ int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const doubl
     const int64_t N = h->N;
     // arena: R,Z,P [N*k] | Pp,KP [N*k] | dsig [N] | partA [k*PB] | partB [2*k*PB]
     size_t need = (size_t)N * k * 5 + N + (size_t)3 * k * SGB_PART_BLOCKS;
-    SGB_TRY(ensure_f64(h, &h->d_pcg, &h->pcg_elems, need));
+    SGB_TRY(sgb_ensure_f64(h, &h->d_pcg, &h->pcg_elems, need));
     double *R = h->d_pcg, *Z = R + N * k, *P = Z + N * k, *Pp = P + N * k, *KP = Pp + N * k, *dsig = KP + N * k;
     double *partA = dsig + N, *partB = partA + (size_t)k * SGB_PART_BLOCKS;
     double *rz[2] = {h->d_scal + SC_PCG, h->d_scal + SC_PCG + 1024}, *r2 = h->d_scal + SC_PCG + 2048;
@@ -328,7 +328,7 @@ struct arena {
 
 static int arena_begin(sgb_ctx *h, size_t elems, arena *a)
 {
-    SGB_TRY(ensure_f64(h, &h->d_ai, &h->ai_elems, elems));
+    SGB_TRY(sgb_ensure_f64(h, &h->d_ai, &h->ai_elems, elems));
     a->h = h; a->base = h->d_ai; a->off = 0;
     return 0;
 }
@@ -402,7 +402,7 @@ static int crossprod_host(sgb_ctx *h, const double *B, int k, double *Y, int loc
     NEED_LOADED(h);
     CUDA_OK(h, cudaSetDevice(h->device));
     if (k < 1) return sgb_fail(h, "crossprod: k must be >= 1");
-    SGB_TRY(ensure_f64(h, &h->d_io, &h->io_elems, (size_t)h->N * k));
+    SGB_TRY(sgb_ensure_f64(h, &h->d_io, &h->io_elems, (size_t)h->N * k));
     SGB_TRY(up(h, h->d_io, B, (size_t)h->N * k));
     SGB_TRY(sgb_crossprod_device(h, h->d_io, k, h->d_io, loco));
     SGB_TRY(down(h, Y, h->d_io, (size_t)h->N * k));
@@ -731,7 +731,7 @@ extern "C" int sgb_bench_crossprod_device(sgb_ctx *h, int k, int reps, uint64_t 
     NEED_LOADED(h);
     CUDA_OK(h, cudaSetDevice(h->device));
     const int64_t N = h->N;
-    SGB_TRY(ensure_f64(h, &h->d_bench, &h->bench_elems, (size_t)2 * N * k));
+    SGB_TRY(sgb_ensure_f64(h, &h->d_bench, &h->bench_elems, (size_t)2 * N * k));
     double *dB = h->d_bench, *dY = dB + (size_t)N * k;
     SGB_TRY(k_rademacher_fill(h, dB, N * k, seed));
     cudaEvent_t e0, e1;

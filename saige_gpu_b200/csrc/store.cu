@@ -461,7 +461,7 @@ extern "C" int sgb_get_one_snp_geno(sgb_ctx *h, int64_t idx, int32_t *out)
         // sum-allreduce of the decoded row (non-owners contribute zeros)
         std::vector<double> tmp(h->N, 0.0);
         if (mine) for (int64_t i = 0; i < h->N; i++) tmp[i] = decode_sample(row.data(), i);
-        SGB_TRY(sgb_ensure(h, (void **)&h->d_io, &h->io_elems, sizeof(double) * h->N));
+        SGB_TRY(sgb_ensure_f64(h, &h->d_io, &h->io_elems, (size_t)h->N));
         CUDA_OK(h, cudaMemcpyAsync(h->d_io, tmp.data(), sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
         SGB_TRY(sgb_allreduce_sum(h, h->d_io, h->N));
         CUDA_OK(h, cudaMemcpyAsync(tmp.data(), h->d_io, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));

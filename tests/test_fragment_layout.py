@@ -21,8 +21,7 @@ def frag_offset(r, l):
     """byte offset inside a 2048-byte block of limb l of genotype slot r (0..255) -- mirrors split_limbs_kernel"""
     t, wi, p = r >> 6, (r >> 4) & 3, r & 15
     odd, half, slot = p & 1, (p >> 3) & 1, (p & 7) >> 1
-    j = 2 * wi + odd
-    return (l * 4 + t) * 64 + j * 8 + half * 4 + slot
+    return (wi * 32 + l * 4 + t) * 16 + odd * 8 + half * 4 + slot
 
 
 POOLS = {  # (ax, ay, bx, by) exactly as in k_pk2_gemm
@@ -111,8 +110,9 @@ def test_warp_tile_product_matches_dense():
             dh = decode16(int(words[g + 8, 4 * t + wi]))
             q0 = 0 if j % 2 == 0 else 2
             a0, a1, a2, a3 = dl[q0], dh[q0], dl[q0 + 1], dh[q0 + 1]
-            b0 = [L[lane * 64 + j * 8 + s] for s in range(4)]
-            b1 = [L[lane * 64 + j * 8 + 4 + s] for s in range(4)]
+            off = ((j // 2) * 32 + lane) * 16 + (j % 2) * 8      # uint4 index (pair, lane); .x,.y / .z,.w
+            b0 = [L[off + s] for s in range(4)]
+            b1 = [L[off + 4 + s] for s in range(4)]
             for s in range(4):                              # PTX m16n8k32 fragment ownership
                 A[g, 4 * t + s] = a0[s]; A[g + 8, 4 * t + s] = a1[s]
                 A[g, 16 + 4 * t + s] = a2[s]; A[g + 8, 16 + 4 * t + s] = a3[s]
