@@ -1,0 +1,85 @@
+"""Size-independent properties of the CUDA path at a BASELINE.json-scale shape (config 2: 50,000 samples x 500,000
+markers would take the oracle hours, so correctness at that size is established through properties the domain
+offers): linearity, symmetry, positive semi-definiteness, K.1 = 0, tensor engine == fp64 engine on a marker
+sub-range, diag(K) == e_i^T K e_i, and PCG actually solving Sigma x = b (residual through an independent product)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N, M, SEED = 50_000, 500_000, 20260117
+
+
+@pytest.fixture(scope="module")
+def big():
+    from saige_gpu_b200 import SaigeB200, synth
+    g = SaigeB200(device=0)
+    _, t0, t1 = synth.thresholds(M, SEED)
+    g.setminMAFforGRM(0.01)
+    g.setmaxMissingRateforGRM(0.15)
+    g.setgeno_synth(N, M, SEED, t0, t1)
+    yield g
+    g.close()
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_shape_and_allele_counts(big):
+    from saige_gpu_b200 import synth
+    f, _, _ = synth.thresholds(M, SEED)
+    assert (big.N, big.M, big.M0) == (N, M, M)
+    ac = big.getAlleleCountVec()
+    assert np.max(np.abs(ac / (2.0 * N) - f)) < 0.01               # binomial sampling noise at N = 50k
+    g0 = big.Get_OneSNP_Geno(123_456)
+    assert g0.sum() == ac[123_456] and set(np.unique(g0)) <= {0, 1, 2}
+
+
+def test_linearity_symmetry_psd(big):
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(N, 3))
+    A[:, 2] = 2.0 * A[:, 0] - 3.0 * A[:, 1]
+    K = big.getCrossprodMatAndKin(A)
+    assert rel(K[:, 2], 2.0 * K[:, 0] - 3.0 * K[:, 1]) < 1e-10
+    s01, s10 = A[:, 0] @ K[:, 1], A[:, 1] @ K[:, 0]
+    assert abs(s01 - s10) / max(abs(s01), 1e-300) < 1e-9
+    assert A[:, 0] @ K[:, 0] > 0 and A[:, 1] @ K[:, 1] > 0
+    ones = big.getCrossprodMatAndKin(np.ones(N))
+    assert np.max(np.abs(ones)) < 1e-8                             # every marker column is centred exactly
+
+
+def test_diag_matches_unit_vector_products(big):
+    d = big.get_DiagofKin()
+    assert abs(d.mean() - 1.0) < 0.01
+    E = np.zeros((N, 3))
+    idx = [0, 31_415, N - 1]
+    for c, i in enumerate(idx):
+        E[i, c] = 1.0
+    K = big.getCrossprodMatAndKin(E)
+    for c, i in enumerate(idx):
+        assert abs(K[i, c] - d[i]) / d[i] < 1e-10
+
+
+def test_engines_agree_at_scale(big):
+    rng = np.random.default_rng(1)
+    b = rng.normal(size=N)
+    yt = big.getCrossprodMatAndKin(b)
+    big.set_engine("f64")
+    yf = big.getCrossprodMatAndKin(b)
+    big.set_engine("tensor")
+    assert rel(yt, yf) < 1e-10
+
+
+def test_pcg_residual_at_scale(big):
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0.05, 0.25, size=N)
+    tau = np.array([1.0, 0.5])
+    B = np.column_stack([rng.normal(size=N), rng.integers(0, 2, size=N) * 2.0 - 1.0])
+    X, it = big.getPCG1ofSigmaAndVector(w, tau, B, 500, 1e-5, return_iter=True)
+    R = B - big.getCrossprod(X, w, tau)
+    for c in range(2):
+        assert R[:, c] @ R[:, c] <= 1.05e-5 and 1 <= it[c] < 100
+    # batched == sequential, bit for bit
+    x0 = big.getPCG1ofSigmaAndVector(w, tau, B[:, 0], 500, 1e-5)
+    assert np.array_equal(x0, X[:, 0])
