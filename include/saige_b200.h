@@ -33,10 +33,13 @@ typedef struct sgb_ctx sgb_ctx;
 #define SGB_NCCL_ID_BYTES 128
 
 /* Which arithmetic engine computes GRM products.
- *   SGB_ENGINE_TENSOR : 2-bit genotypes decoded in registers to u8, right-hand sides split into signed 7-bit
- *                       limbs, exact int32 accumulation on the tensor cores, fp64 recombination (default).
- *   SGB_ENGINE_F64    : plain fp64 FMA kernels (slow; the on-device cross-check of the tensor engine). */
-enum { SGB_ENGINE_TENSOR = 0, SGB_ENGINE_F64 = 1 };
+ *   SGB_ENGINE_TENSOR : 2-bit genotypes decoded in registers to u8, right-hand sides split into signed 7-bit limbs,
+ *                       exact int32 accumulation on the tensor cores, fp64 recombination (default).  Batches of
+ *                       k >= 3 columns run on the tcgen05 kernel (A operand decoded straight into tensor memory,
+ *                       accumulator in TMEM); k <= 2 on the HBM-bound mma.sync kernel.  Both give identical bits.
+ *   SGB_ENGINE_F64    : plain fp64 FMA kernels (slow; the on-device cross-check of the tensor engine).
+ *   SGB_ENGINE_UMMA   : force the tcgen05 kernel for every k >= 2;  SGB_ENGINE_IMMA : force the mma.sync kernel. */
+enum { SGB_ENGINE_TENSOR = 0, SGB_ENGINE_F64 = 1, SGB_ENGINE_UMMA = 2, SGB_ENGINE_IMMA = 3 };
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
 /* Replaces the file-global `genoClass geno` (FG.cpp:1188) + gpuSymMatMult (gpuSymMatMult.hpp:13-36). */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsaige_b200.so")
 
 NCCL_ID_BYTES = 128
-ENGINE_TENSOR, ENGINE_F64 = 0, 1
+ENGINE_TENSOR, ENGINE_F64, ENGINE_UMMA = 0, 1, 2
 
 PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double))
 

@@ -73,7 +73,7 @@ class SaigeB200:
             pass
 
     def set_engine(self, engine):
-        self._ck(self._L.sgb_set_engine(self._h, {"tensor": 0, "f64": 1}[engine]))
+        self._ck(self._L.sgb_set_engine(self._h, {"tensor": 0, "f64": 1, "umma": 2, "imma": 3}[engine]))
 
     def sync(self):
         self._ck(self._L.sgb_device_sync(self._h))

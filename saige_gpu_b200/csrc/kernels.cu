@@ -513,14 +513,14 @@ int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, i
 }
 
 // raw[r + c*ld] = (sum_l acc[r][c*8+l] * 128^l) * mult[c];  acc is reset to 0 for the next product.
-__global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k, const double *__restrict__ mult,
+__global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k, int kpad, const double *__restrict__ mult,
                                  const int32_t *__restrict__ limbsum, int c0, double *__restrict__ raw, int64_t ld)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * k) return;
     int64_t r = idx / k;
     int c = (int)(idx - r * k);
-    int4 *p = reinterpret_cast<int4 *>(acc + (r * k + c) * 8);
+    int4 *p = reinterpret_cast<int4 *>(acc + (r * kpad + c) * 8);
     int4 lo = p[0], hi = p[1];
     p[0] = make_int4(0, 0, 0, 0);
     p[1] = make_int4(0, 0, 0, 0);
@@ -535,11 +535,11 @@ __global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k,
     raw[r + (int64_t)c * ld] = v * mult[c];
 }
 
-int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
-                double *raw, int64_t ld)
+int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, int kpad, const double *d_mult, const int32_t *d_limbsum,
+                int plane, double *raw, int64_t ld)
 {
     if (rows * k == 0) return 0;
-    recombine_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, d_mult, d_limbsum,
+    recombine_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, kpad, d_mult, d_limbsum,
                                                                            plane == SGB_PLANE_VALUE ? 2 : 1, raw, ld);
     LAUNCH_CHECK(h);
     return 0;

@@ -1,0 +1,424 @@
+// tcgen05 ("UMMA") version of the packed-genotype x limb product for WIDE right-hand-side batches (k >= 2 columns).
+//
+//   out[r][n] (+)= sum_k (c0 - plane(P[r][k])) * L[k][n]        n = column*8 + limb,  N = 16..128 per launch
+//
+// Blackwell-native data path, no shared-memory round trip for the genotypes:
+//   * each of the 128 threads of a CTA owns ONE ROW of a 128-row tile: it streams its row's packed bytes with 128-bit
+//     loads, decodes them in registers with prmt (same pair-ternary trick as pk2_gemm_kernel) and writes the u8 A
+//     operand straight into TENSOR MEMORY with tcgen05.st (TMEM lane = row, 4 k-values per 32-bit column);
+//   * the int8 limb operand B is staged in shared memory in the canonical K-major no-swizzle UMMA layout
+//     (the limb splitter already writes the global copy as an image of that layout, so staging is a flat cp.async copy);
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32) with A from TMEM, B from the smem
+//     descriptor and the int32 accumulator in TMEM; tcgen05.commit -> mbarrier releases the A/B stage two steps later;
+//   * the epilogue reads the accumulator with tcgen05.ld and adds it to the global int32 limb sums.
+// The legacy mma.sync kernel stays the k = 1 path (it is HBM-bound there) and the numerical cross-check of this one.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "sgb_internal.h"
+
+#define UMMA_ROWS 128            // rows per CTA tile = TMEM lanes = MMA M
+#define UMMA_KSTEP 256           // genotypes per pipeline step  (64 packed bytes per row, 8 MMAs of K=32)
+#define UMMA_KBLK 128            // genotypes per block of the limb image (one bulk copy)
+#define UMMA_A_COLS 64           // TMEM columns of one A stage   (256 k-values / 4 per column)
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity));
+}
+
+__device__ __forceinline__ uint32_t prmt_u(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u(const uint8_t *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// one 256-bit load = one full 32-byte sector per thread (sm_100 LDG.256): a row-per-thread access pattern would
+// otherwise request every sector twice with 128-bit loads
+struct u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ u32x8 ldg_stream_256(const uint8_t *p)
+{
+    u32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+struct umma_pools { uint32_t ax, ay, bx, by; };
+
+// 32 registers (one per TMEM column) -> this thread's lane of the A stage
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, int32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]     M=128, N from idesc, K=32, int8 -> int32
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+
+#define UMMA_STAGES 2            // A (TMEM) pipeline depth: one stage per producer group
+#define UMMA_MAX_BSTAGES 16      // B (smem) ring depth is chosen at launch: as many 128 x N byte stages as fit ~96 KB
+#define UMMA_PF 3                // packed-row prefetch distance of the producer threads, in steps
+#define UMMA_PGROUPS 2           // producer groups of 4 warps; group g owns the k-steps s = g (mod UMMA_PGROUPS)
+#define UMMA_PWARPS (4 * UMMA_PGROUPS)
+#define UMMA_THREADS (32 * (UMMA_PWARPS + 2))   // producers (+ epilogue), then one MMA-issuer warp and one bulk-copy warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// grid: x = k-chunks, y = 128-row tiles.  block: 192 threads.  dynamic smem: UMMA_STAGES * 128 * N bytes of B stages.
+//   P        packed rows (pair-ternary), `stride` bytes each (multiple of 64); rows padded to a multiple of 128
+//   L        limb operand as an image of the smem stage: [k-block of 128][N/8][k/16 (8)][n%8 (8)][k%16 (16)] int8
+//   out      int32 [rows][ldo]; this launch covers columns [n0, n0 + N)
+// Warp-specialised pipeline, UMMA_STAGES deep:
+//   producers : load 32 B of their row (prefetched UMMA_PF steps ahead) -> prmt decode -> tcgen05.st into A stage -> arrive full_a
+//   bulk warp : cp.async.bulk (TMA engine) of the next B stage image -> full_b (expect_tx)
+//   MMA warp  : wait full_a & full_b -> 4 x tcgen05.mma.kind::i8 (K = 32 each) -> tcgen05.commit -> empty (frees both stages)
+__global__ void __launch_bounds__(UMMA_THREADS, 2)
+pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_total, int ksteps_per_chunk,
+                const int8_t *__restrict__ L, int N, int64_t Lblk_stride, int32_t *__restrict__ out, int ldo, int n0,
+                int use_atomic, umma_pools pool, int tmem_cols, int nb, int dbg)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full_a[UMMA_STAGES], empty[UMMA_STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t ks0 = (int64_t)blockIdx.x * ksteps_per_chunk;
+    int64_t ks1 = ks0 + ksteps_per_chunk;
+    if (ks1 > ksteps_total) ks1 = ksteps_total;
+    const int nsteps = (int)(ks1 - ks0);
+    const uint32_t stage_bytes = (uint32_t)UMMA_KSTEP * (uint32_t)N;      // two 128-genotype limb blocks
+    const uint32_t half_bytes = stage_bytes / 2;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < UMMA_STAGES; i++) { mbar_init(&full_a[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < nb; i++) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_d = tmem_base + UMMA_STAGES * UMMA_A_COLS;
+
+    if (warp < UMMA_PWARPS) {
+        // ================= producers: one row per thread, k-steps interleaved over the producer groups =================
+        const int grp = warp >> 2, q4 = warp & 3;
+        const int64_t row = (int64_t)blockIdx.y * UMMA_ROWS + q4 * 32 + (tid & 31);
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;         // this warp's TMEM lane quarter
+        const uint8_t *prow = P + row * stride + ks0 * 64;
+        u32x8 pf[UMMA_PF][2];
+#pragma unroll
+        for (int i = 0; i < UMMA_PF; i++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { pf[i][0].v[j] = 0; pf[i][1].v[j] = 0; }
+            const int sp = grp + i * UMMA_PGROUPS;
+            if (sp < nsteps) { pf[i][0] = ldg_stream_256(prow + (int64_t)sp * 64); pf[i][1] = ldg_stream_256(prow + (int64_t)sp * 64 + 32); }
+        }
+        // the prefetch ring is indexed statically (loop unrolled by UMMA_PF): shifting a register queue would make every
+        // step wait for ALL loads in flight
+        for (int sbase = grp; sbase < nsteps; sbase += UMMA_PGROUPS * UMMA_PF) {
+#pragma unroll
+            for (int j = 0; j < UMMA_PF; j++) {
+                const int s = sbase + j * UMMA_PGROUPS;
+                if (s < nsteps) {
+                    const int st = s % UMMA_STAGES, u = s / UMMA_STAGES;
+                    if (u > 0) mbar_wait(&empty[st], (uint32_t)((u - 1) & 1));      // MMAs that read this A stage have completed
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        uint32_t a[32];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t wv = pf[j][hf].v[i], hi = wv >> 16;
+                            a[4 * i + 0] = prmt_u(pool.ax, pool.ay, wv);
+                            a[4 * i + 1] = prmt_u(pool.ax, pool.ay, hi);
+                            a[4 * i + 2] = prmt_u(pool.bx, pool.by, wv);
+                            a[4 * i + 3] = prmt_u(pool.bx, pool.by, hi);
+                        }
+                        tmem_st_x32(tmem_base + lane_base + st * UMMA_A_COLS + hf * 32, a);
+                    }
+                    if (s + UMMA_PF * UMMA_PGROUPS < nsteps) {
+                        pf[j][0] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * 64);
+                        pf[j][1] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * 64 + 32);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;");
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    mbar_arrive(&full_a[st]);
+                }
+            }
+        }
+        // ---- epilogue: all MMAs committed -> TMEM -> registers -> global int32 sums (columns split over the groups) ----
+        if (nsteps > 0) {
+            mbar_wait(&done_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            int32_t *o = out + row * ldo + n0;
+            for (int c = grp * 16; c < N; c += 16 * UMMA_PGROUPS) {
+                int32_t v[16];
+                tmem_ld_x16(tmem_d + lane_base + c, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                if (use_atomic) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (v[i]) atomicAdd(o + c + i, v[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<int4 *>(o + c + i) = make_int4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+        }
+    } else if (warp == UMMA_PWARPS) {
+        // ================= MMA issuer (one thread) =================
+        if (tid == 32 * UMMA_PWARPS) {
+            // instruction descriptor: D=s32, A=u8 (K-major, TMEM), B=s8 (K-major), N, M=128
+            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_ROWS >> 4) << 24);
+            for (int s = 0; s < nsteps; s++) {
+                const int st = s % UMMA_STAGES, u = s / UMMA_STAGES;
+                const int sbi = s % nb, ub = s / nb;
+                mbar_wait(&full_b[sbi], (uint32_t)(ub & 1));
+                mbar_wait(&full_a[st], (uint32_t)(u & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t sb = smem_u32(smem + sbi * stage_bytes);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    // K-major, no swizzle: core matrix = 8 n-rows x 16 k-bytes (128 B); LBO (next 16 k) = 128 B; SBO (next 8 n) = 1024 B
+                    const uint64_t desc = (uint64_t)(((sb + (j >> 2) * half_bytes + (j & 3) * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
+                                          ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+                    if (!(dbg & 1)) umma_i8_ts(tmem_d, tmem_base + st * UMMA_A_COLS + j * 8, desc, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_b[sbi])) : "memory");
+            }
+            if (nsteps > 0)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
+        }
+    } else {
+        // ================= B stage loader: one bulk copy (TMA engine) per step =================
+        if (tid == 32 * (UMMA_PWARPS + 1)) {
+            for (int s = 0; s < nsteps; s++) {
+                const int sbi = s % nb, ub = s / nb;
+                if (ub > 0) mbar_wait(&empty_b[sbi], (uint32_t)((ub - 1) & 1));
+                mbar_expect_tx(&full_b[sbi], stage_bytes);
+                if (!(dbg & 4)) {
+                    bulk_g2s(smem + sbi * stage_bytes, L + (2 * (ks0 + s)) * Lblk_stride, half_bytes, &full_b[sbi]);
+                    bulk_g2s(smem + sbi * stage_bytes + half_bytes, L + (2 * (ks0 + s) + 1) * Lblk_stride, half_bytes, &full_b[sbi]);
+                } else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full_b[sbi])), "r"(stage_bytes) : "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+}
+
+// Limb split for the UMMA engine: V[len x k] -> stage images + per-column multiplier + exact limb column sums.
+// One thread per (128-genotype block, TMEM column 0..31): the 4 genotype slots whose k-values share that column.
+__global__ void split_limbs_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int k, int ncolpad, int64_t nblk,
+                                        const unsigned long long *__restrict__ mx, int8_t *__restrict__ L,
+                                        double *__restrict__ mult, int32_t *__restrict__ limbsum)
+{
+    const int c = blockIdx.y;                         // column (0..ncolpad-1); columns >= k are zero padding
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t blk = u >> 5;
+    const int col = (int)(u & 31), w = col >> 2, q = col & 3;
+    const bool inb = blk < nblk;
+    const bool real = c < k;
+    unsigned long long mb = real ? mx[c] : 0ull;
+    int E = (int)((mb >> 52) & 0x7FF) - 1023;
+    if (E < -1000) E = -1000;
+    if (E > 1000) E = 1000;
+    if (u == 0 && real) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
+    // slot s of this column is genotype 16 w + {0,8,1,9}[q] + 2 s of the block (the order decode produces)
+    const int64_t i0 = blk * UMMA_KBLK + 16 * w + ((q & 1) ? 8 : 0) + ((q & 2) ? 1 : 0);
+    long long qv[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        int64_t i = i0 + 2 * s;
+        qv[s] = (inb && real && i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E)) : 0;
+    }
+    uint32_t *base = reinterpret_cast<uint32_t *>(L + (blk * (int64_t)ncolpad + c) * 1024 + w * 128 + 4 * q);
+#pragma unroll
+    for (int l = 0; l < SGB_LIMBS; l++) {
+        uint32_t word = 0;
+        int ssum = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            int d = (int)((qv[s] + 64) & 127) - 64;
+            qv[s] = (qv[s] - d) >> 7;
+            word |= (uint32_t)(d & 255) << (8 * s);
+            ssum += d;
+        }
+        if (inb) base[l * 4] = word;                   // +16 bytes per limb row
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        if ((threadIdx.x & 31) == 0 && ssum && real) atomicAdd(&limbsum[c * SGB_LIMBS + l], ssum);
+    }
+}
+
+__global__ void colmax_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, unsigned long long *__restrict__ mx)
+{
+    int c = blockIdx.y;
+    const double *v = V + (int64_t)c * ld;
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[i]));
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o);
+        m = x > m ? x : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&mx[c], m);
+}
+
+#define UMMA_LAUNCH_CHECK(h)                                                                            \
+    do {                                                                                                \
+        (h)->cnt.n_kernel_launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                           \
+        if (e__ != cudaSuccess) return sgb_fail(h, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, \
+                                                cudaGetErrorString(e__));                               \
+    } while (0)
+
+// bytes of the UMMA limb operand for k columns over `kbytes` packed bytes per row
+size_t k_umma_limb_bytes(int k, int64_t kbytes)
+{
+    int ncolpad = (k + 1) & ~1;
+    return (size_t)(kbytes / 32) * ncolpad * 1024;        // kbytes is a multiple of 64 => an even number of 128-genotype blocks
+}
+
+int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t kbytes, double *d_mult,
+                       int32_t *d_limbsum)
+{
+    unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);
+    if (k > 1024) return sgb_fail(h, "too many columns (%d)", k);
+    const int ncolpad = (k + 1) & ~1;
+    const int64_t nblk = kbytes / 32;
+    CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
+    CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * SGB_LIMBS * k, h->stream));
+    int gx = (int)cdiv64(len, 256 * 8);
+    if (gx > 1024) gx = 1024;
+    if (gx < 1) gx = 1;
+    colmax_umma_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
+    UMMA_LAUNCH_CHECK(h);
+    split_limbs_umma_kernel<<<dim3((unsigned)cdiv64(nblk * 32, 256), ncolpad), 256, 0, h->stream>>>(V, len, ld, k, ncolpad, nblk, mx, L,
+                                                                                                   d_mult, d_limbsum);
+    UMMA_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// out[r][c*8+l] += ...   for all k columns, in passes of <= 16 columns (N <= 128)
+int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
+               int32_t *out, int plane)
+{
+    if (rows_pad % UMMA_ROWS || kbytes % 64 || stride % 64)
+        return sgb_fail(h, "k_pk2_umma: unaligned operand (rows %lld, kbytes %lld, stride %lld)", (long long)rows_pad,
+                        (long long)kbytes, (long long)stride);
+    umma_pools pool;
+    if (plane == SGB_PLANE_VALUE) { pool.ax = 0x02000102u; pool.ay = 0x01020001u; pool.bx = 0x01020202u; pool.by = 0x00000101u; }
+    else                          { pool.ax = 0x01000101u; pool.ay = 0x01010001u; pool.bx = 0x01010101u; pool.by = 0x00000101u; }
+    const int ncolpad = (k + 1) & ~1;
+    const int64_t ksteps = kbytes / 64;
+    if (ksteps == 0 || rows_pad == 0 || k == 0) return 0;
+    const int64_t row_tiles = rows_pad / UMMA_ROWS;
+    // split K only when there are too few row tiles to fill the machine
+    int64_t kchunks = cdiv64((int64_t)h->sm_count * 4, row_tiles);
+    if (kchunks < 1) kchunks = 1;
+    int64_t per = cdiv64(ksteps, kchunks);
+    if (per < 8) per = 8;
+    if (per > ksteps) per = ksteps;
+    kchunks = cdiv64(ksteps, per);
+    const int use_atomic = 1;       // out is an accumulation buffer shared with other passes / chunks
+    const int dbg = getenv("SGB_UMMA_DBG") ? atoi(getenv("SGB_UMMA_DBG")) : 0;   // tuning experiments only (results invalid when != 0)
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    for (int c0 = 0; c0 < ncolpad; c0 += 16) {
+        int nc = ncolpad - c0 < 16 ? ncolpad - c0 : 16;      // columns this pass (even)
+        int N = nc * 8;
+        int tmem_cols = UMMA_STAGES * UMMA_A_COLS + N <= 256 ? 256 : 512;
+        int nb = (96 * 1024) / (UMMA_KSTEP * N);                // B ring depth (stages of 256 x N bytes)
+        if (nb > UMMA_MAX_BSTAGES) nb = UMMA_MAX_BSTAGES;
+        if (nb < 2) nb = 2;
+        // the limb image interleaves all ncolpad columns per k-block: this pass starts at column c0
+        const int8_t *Lp = L + (int64_t)c0 * 1024;
+        for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {
+            int64_t ny = row_tiles - y0 < 65535 ? row_tiles - y0 : 65535;
+            dim3 grid((unsigned)kchunks, (unsigned)ny);
+            pk2_umma_kernel<<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
+                                                                           (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
+                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
+            UMMA_LAUNCH_CHECK(h);
+        }
+    }
+    return 0;
+}

@@ -112,8 +112,14 @@ int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
 int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult,
                   int32_t *d_limbsum);
 // raw[r + c*ld] = recombine(acc[r][c*8..]) * mult[c]; acc zeroed
-int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
-                double *raw, int64_t ld);
+int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, int kpad, const double *d_mult, const int32_t *d_limbsum,
+                int plane, double *raw, int64_t ld);
+// tcgen05 path (pk2_umma.cu)
+size_t k_umma_limb_bytes(int k, int64_t kbytes);
+int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t kbytes, double *d_mult,
+                       int32_t *d_limbsum);
+int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
+               int32_t *out, int plane);
 
 // f64 engine
 int k_rowdot_f64(sgb_ctx *h, const double *B, int64_t ldb, int k, double *out, int64_t ldo);   // out[m,c]=sum_i g_mi B[i,c]

@@ -57,22 +57,27 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     SGB_TRY(sgb_ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(2 * rowsG + rowsT + 1) * k));
     double *raw1 = h->d_tmp, *D = raw1 + rowsG * k, *raw2 = D + rowsG * k;
     double *sc = h->d_scal;
-    const bool tensor = h->engine == SGB_ENGINE_TENSOR;
+    const bool tensor = h->engine != SGB_ENGINE_F64;
+    const bool umma = (h->engine == SGB_ENGINE_UMMA && k >= 2) || (h->engine == SGB_ENGINE_TENSOR && k >= 3);   // wide batches: tcgen05
+    const int kpad = umma ? ((k + 1) & ~1) : k;                     // accumulator columns (UMMA N is a multiple of 16)
     if (tensor) {
-        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)k * std::max(nblkN, nblkM) * 2048));
-        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc1, &h->acc1_elems, (size_t)rowsG * 8 * k));
-        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * k));
+        size_t lb = umma ? std::max(k_umma_limb_bytes(k, h->sG), k_umma_limb_bytes(k, h->sT)) : (size_t)k * std::max(nblkN, nblkM) * 2048;
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, lb));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc1, &h->acc1_elems, (size_t)rowsG * 8 * kpad));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * kpad));
     }
     h->cnt.n_crossprod_calls++; h->cnt.n_crossprod_columns += k;
 
     SGB_TRY(k_colsum(h, dB, N, N, k, sc + SC_COLSUM));
     // ---- sweep 1: raw1[m,c] = g_m . b_c over the marker-major copy ----
     if (tensor) {
-        SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1, h->d_limbsum));
+        if (umma) SGB_TRY(k_split_limbs_umma(h, dB, N, N, k, h->d_limb, h->sG, sc + SC_MULT1, h->d_limbsum));
+        else SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1, h->d_limbsum));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
-        SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
+        if (umma) SGB_TRY(k_pk2_umma(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
+        else SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
-        SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
+        SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, kpad, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
     } else {
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
         SGB_TRY(k_rowdot_f64(h, dB, N, k, raw1, rowsG));
@@ -82,11 +87,13 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     SGB_TRY(k_sweep1_post(h, raw1, rowsG, k, sc + SC_COLSUM, lo, hi, D, sc + SC_T));
     // ---- sweep 2: raw2[i,c] = sum_m g_mi D[m,c] over the sample-major copy ----
     if (tensor) {
-        SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2, h->d_limbsum + 8192));
+        if (umma) SGB_TRY(k_split_limbs_umma(h, D, h->Mloc, rowsG, k, h->d_limb, h->sT, sc + SC_MULT2, h->d_limbsum + 8192));
+        else SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2, h->d_limbsum + 8192));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
-        SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
+        if (umma) SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
+        else SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, kpad, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
     } else {
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
         SGB_TRY(k_coldot_f64(h, D, nullptr, rowsG, k, raw2, rowsT));
@@ -123,15 +130,15 @@ static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const
     CUDA_OK(h, cudaMemcpyAsync(d_rng, both.data(), sizeof(int64_t) * 2 * nc, cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     SGB_TRY(k_diag_prep(h, nc, d_rng, d_rng + nc, D1, D2, cst));
-    if (h->engine == SGB_ENGINE_TENSOR) {
+    if (h->engine != SGB_ENGINE_F64) {
         SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)nc * nblkM * 2048));
         SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * nc));
         SGB_TRY(k_split_limbs(h, D1, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT1, h->d_limbsum));
         SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_VALUE));
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, r1, rowsT));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, nc, h->d_scal + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, r1, rowsT));
         SGB_TRY(k_split_limbs(h, D2, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT2, h->d_limbsum + 8192));
         SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_IS2));   // [g==2] plane
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_IS2, r2, rowsT));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, nc, h->d_scal + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_IS2, r2, rowsT));
     } else {
         // weight of g==2 is 2*D1 + D2; fold it into one pass and leave r2 = 0
         SGB_TRY(k_axpby(h, 2.0, D1, 1.0, D2, rowsG * nc, D2));

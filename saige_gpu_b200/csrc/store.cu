@@ -125,7 +125,7 @@ extern "C" void sgb_destroy(sgb_ctx *h)
 
 extern "C" int sgb_set_engine(sgb_ctx *h, int engine)
 {
-    if (engine != SGB_ENGINE_TENSOR && engine != SGB_ENGINE_F64) return sgb_fail(h, "unknown engine %d", engine);
+    if (engine < SGB_ENGINE_TENSOR || engine > SGB_ENGINE_IMMA) return sgb_fail(h, "unknown engine %d", engine);
     h->engine = engine;
     h->diag_ready = false; h->diag_loco_ready = false;
     return 0;

@@ -63,12 +63,15 @@ def test_diag_matches_unit_vector_products(big):
 
 def test_engines_agree_at_scale(big):
     rng = np.random.default_rng(1)
-    b = rng.normal(size=N)
-    yt = big.getCrossprodMatAndKin(b)
+    B = rng.normal(size=(N, 4))
+    yt = big.getCrossprodMatAndKin(B)            # tcgen05 kernel (k = 4)
+    big.set_engine("imma")
+    yi = big.getCrossprodMatAndKin(B)            # mma.sync kernel
     big.set_engine("f64")
-    yf = big.getCrossprodMatAndKin(b)
+    yf = big.getCrossprodMatAndKin(B[:, 0])      # fp64 FMA kernels
     big.set_engine("tensor")
-    assert rel(yt, yf) < 1e-10
+    assert np.array_equal(yt, yi)
+    assert rel(yt[:, 0], yf) < 1e-10
 
 
 def test_pcg_residual_at_scale(big):

@@ -75,8 +75,8 @@ def test_frq_golden_through_gpu(pair10k, golden_dir):
     assert all(float("%.4g" % a) == b for a, b in zip(mine, frq[mask]))
 
 
-@pytest.mark.parametrize("engine", ["tensor", "f64"])
-@pytest.mark.parametrize("k", [1, 2, 3, 7, 31])
+@pytest.mark.parametrize("engine", ["tensor", "f64", "imma", "umma"])
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 16, 31])
 def test_crossprod_matches_oracle(pair10k, engine, k):
     g, o = pair10k
     g.set_engine(engine)
@@ -120,12 +120,19 @@ def test_crossprod_is_linear_and_symmetric(pair10k):
 
 
 def test_batched_equals_sequential(pair10k):
+    """Exact integer accumulation: a column's result is bit-identical whatever the batch width and whichever tensor
+    kernel (mma.sync or tcgen05) computed it."""
     g, _ = pair10k
     rng = np.random.default_rng(6)
     B = rng.normal(size=(g.N, 5))
-    Y = g.getCrossprodMatAndKin(B)
+    Y = g.getCrossprodMatAndKin(B)                                   # k = 5 -> tcgen05 kernel
     for c in range(5):
         assert np.array_equal(Y[:, c], g.getCrossprodMatAndKin(B[:, c])), "column result must not depend on the batch"
+    g.set_engine("imma")
+    assert np.array_equal(Y, g.getCrossprodMatAndKin(B))
+    g.set_engine("umma")
+    assert np.array_equal(Y[:, :2], g.getCrossprodMatAndKin(B[:, :2]))
+    g.set_engine("tensor")
 
 
 @pytest.mark.parametrize("engine", ["tensor", "f64"])

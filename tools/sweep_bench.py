@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 from saige_gpu_b200 import SaigeB200, synth
 N, M = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (200_000, 500_000)
 ks = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 4, 8, 31]
-g = SaigeB200()
+g = SaigeB200(engine=os.environ.get('SGB_ENGINE', 'tensor'))
 _, t0, t1 = synth.thresholds(M, 1)
 g.setminMAFforGRM(0.01); g.setgeno_synth(N, M, 1, t0, t1)
 bytes_sweep = g.Mloc * ((N + 3) // 4)
