@@ -199,6 +199,13 @@ def main():
     sweep_ms = float(mk.sum()) / (2 * K)                   # average duration of one pk2_gemm launch
     bytes_launch = Mloc * Bbytes                           # algorithmic bytes of one sweep: the packed shard, once
     peak, peak_src = measured_hbm_peak()
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+        if tj and tj["n_gpus"] == world and args.engine == "tensor":
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     achieved = bytes_launch / (sweep_ms * 1e-3) / 1e9
     bytes_alg_product = 2 * Mloc * Bbytes + 16 * N + 16 * Mloc * 2
 
@@ -235,6 +242,21 @@ def main():
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(N, M)
+    ingest_info = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # setgeno from a host-resident PLINK .bed body (QC + imputation + re-pack + transpose on the GPU), bounded sample
+        from oracle import oracle as O
+        n_i, m_i = N, 32768
+        bed_i = O.synth_bed(n_i, m_i, SEED, miss_rate=0.01)
+        gi = SaigeB200(device=local_rank)
+        gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
+        gi.setgeno_mem(bed_i, n_i, m_i, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))        # warm-up
+        ti = time.time()
+        gi.setgeno_mem(bed_i, n_i, m_i, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))
+        ti = time.time() - ti
+        ingest_info = {"bed_gbytes": bed_i.nbytes / 1e9, "seconds": ti, "gb_per_s": bed_i.nbytes / 1e9 / ti,
+                       "sample": "%d samples x %d markers, 1%% missing calls, host-resident .bed body" % (n_i, m_i)}
+        gi.close()
     step1_info = None
     if not args.no_step1:
         # polygenic liability (h2 ~ 0.3) from 200 causal markers read back through Get_OneSNP_StdGeno
@@ -278,12 +300,13 @@ def main():
                     "api": "sgb_get_crossprod_mat_and_kin (host pinned vectors)", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "pk2_gemm_kernel", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "pk2_gemm_kernel", "peak_source": peak_src,
                          "bytes_per_launch": int(bytes_launch), "avg_launch_ms": sweep_ms,
                          "sweep1_ms": float(mk[:, 0].mean()), "sweep2_ms": float(mk[:, 1].mean()),
                          "whole_product_frac": bytes_alg_product / (total_ms / K * 1e-3) / 1e9 / peak},
             "batched": {"k": kb, "ms_per_product": batch_ms, "columns_per_s": kb / (batch_ms * 1e-3)},
             "cpu_baseline": cb,
+            "ingest": ingest_info,
             "step1": step1_info,
         }
         print(json.dumps(line))

@@ -136,11 +136,49 @@ __global__ void repack_kernel(const uint8_t *__restrict__ bed, int64_t B0, const
     out[r * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
 }
 
+// gather variant: the raw row is staged in shared memory once, then every output byte gathers its 4 samples from it
+__global__ void __launch_bounds__(256) repack_gather_kernel(const uint8_t *__restrict__ bed, int64_t B0,
+                                                            const int32_t *__restrict__ src_rows, const int32_t *__restrict__ fill,
+                                                            const int32_t *__restrict__ sub_idx, int64_t N,
+                                                            uint8_t *__restrict__ out, int64_t out_stride)
+{
+    extern __shared__ uint8_t srow[];
+    const int64_t r = blockIdx.x;
+    const uint8_t *row = bed + (int64_t)src_rows[r] * B0;
+    for (int64_t b = threadIdx.x; b < B0; b += blockDim.x) srow[b] = row[b];
+    __syncthreads();
+    const int fl = fill[r];
+    const int64_t B = (N + 3) >> 2;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+        int gq[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t k = 4 * b + j;
+            if (k < N) {
+                int64_t src = (int64_t)sub_idx[k] - 1;
+                int code = (srow[src >> 2] >> ((src & 3) << 1)) & 3;
+                gq[j] = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fl));
+            }
+        }
+        out[r * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
+    }
+}
+
 int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_rows, const int32_t *d_fill,
              int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_stride)
 {
     if (nrows <= 0) return 0;
     int64_t B = (N + 3) / 4;
+    if (!identity && B0 <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_OK(h, cudaFuncSetAttribute(repack_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        repack_gather_kernel<<<(unsigned)nrows, 256, (size_t)B0, h->stream>>>(d_bed, B0, d_src_rows, d_fill, d_sub_idx, N, d_out, out_stride);
+        LAUNCH_CHECK(h);
+        return 0;
+    }
     for (int64_t r0 = 0; r0 < nrows; r0 += 65535) {
         int64_t nr = nrows - r0 < 65535 ? nrows - r0 : 65535;
         dim3 grid((unsigned)cdiv(B, 256), (unsigned)nr);

@@ -10,9 +10,11 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 #include <algorithm>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 #include "sgb_internal.h"
 
@@ -216,6 +218,80 @@ struct chunk_reader {     // yields raw marker rows [m0, m1) either from memory 
     }
 };
 
+// Host -> device streaming of raw .bed rows through two pinned staging buffers: the host fill of piece i+1 (fread, or
+// a 4-thread memcpy from the caller's buffer) overlaps the asynchronous H2D copy of piece i.
+struct stager {
+    sgb_ctx *h = nullptr;
+    uint8_t *pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t cap = 0;
+    int cur = 0;
+    int init(sgb_ctx *hh, size_t bytes)
+    {
+        h = hh; cap = bytes;
+        for (int i = 0; i < 2; i++) {
+            CUDA_OK(h, cudaMallocHost((void **)&pin[i], cap));
+            CUDA_OK(h, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    void destroy()
+    {
+        for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); pin[i] = nullptr; ev[i] = nullptr; }
+    }
+    static void par_copy(uint8_t *dst, const uint8_t *src, size_t n)
+    {
+        const int nt = n > ((size_t)8 << 20) ? 4 : 1;
+        if (nt == 1) { memcpy(dst, src, n); return; }
+        std::vector<std::thread> th;
+        size_t per = (n + nt - 1) / nt;
+        for (int t = 0; t < nt; t++) {
+            size_t o = t * per, len = o < n ? std::min(per, n - o) : 0;
+            if (len) th.emplace_back([=] { memcpy(dst + o, src + o, len); });
+        }
+        for (auto &x : th) x.join();
+    }
+    // rows [m0, m1) of the .bed body -> d_dst (device), asynchronously on h->stream
+    int push(chunk_reader &rd, int64_t m0, int64_t m1, uint8_t *d_dst)
+    {
+        const int64_t B0 = rd.B0;
+        const size_t total = (size_t)(m1 - m0) * B0;
+        for (size_t off = 0; off < total; off += cap) {
+            const size_t n = std::min(cap, total - off);
+            CUDA_OK(h, cudaEventSynchronize(ev[cur]));            // the previous H2D out of this buffer has finished
+            if (rd.mem) par_copy(pin[cur], rd.mem + (size_t)m0 * B0 + off, n);
+            else {
+                // marker i starts at byte 3 + B0*i of the file (FG.cpp:902); 4 threads pread disjoint slices
+                const off_t fo = 3 + (off_t)m0 * B0 + (off_t)off;
+                const int fd = fileno(rd.fp), nt = n > ((size_t)8 << 20) ? 4 : 1;
+                std::vector<std::thread> th;
+                std::vector<int> okv(nt, 1);
+                const size_t per = (n + nt - 1) / nt;
+                uint8_t *dstp = pin[cur];
+                for (int t = 0; t < nt; t++) {
+                    const size_t o = t * per, len = o < n ? std::min(per, n - o) : 0;
+                    if (!len) continue;
+                    th.emplace_back([=, &okv] {
+                        size_t done = 0;
+                        while (done < len) {
+                            ssize_t got = pread(fd, dstp + o + done, len - done, fo + (off_t)(o + done));
+                            if (got <= 0) { okv[t] = 0; return; }
+                            done += (size_t)got;
+                        }
+                    });
+                }
+                for (auto &x : th) x.join();
+                for (int v : okv) if (!v) return sgb_fail(h, "setgeno: short read of .bed at marker %lld", (long long)m0);
+            }
+            CUDA_OK(h, cudaMemcpyAsync(d_dst + off, pin[cur], n, cudaMemcpyHostToDevice, h->stream));
+            CUDA_OK(h, cudaEventRecord(ev[cur], h->stream));
+            h->cnt.bytes_h2d += n;
+            cur ^= 1;
+        }
+        return 0;
+    }
+};
+
 static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, const int32_t *sub, int64_t N,
                         const uint8_t *indicator, int diagOne, const int32_t *vr_idx, int64_t n_vr)
 {
@@ -241,23 +317,30 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     CUDA_OK(h, cudaMemcpy(d_sub, sub, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
 
     // ---- pass 1: counts for every raw marker ----
+    // When the raw .bed fits beside the two packed copies it is uploaded ONCE and kept on the device for the re-pack.
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(M0, ((int64_t)256 << 20) / B0));
+    size_t free_b = 0, total_b = 0;
+    CUDA_OK(h, cudaMemGetInfo(&free_b, &total_b));
+    const size_t raw_total = (size_t)M0 * B0;
+    const bool keep_raw = raw_total * 3 + ((size_t)4 << 30) < free_b;      // raw + marker-major + sample-major copies + slack
     uint8_t *d_raw = nullptr; int32_t *d_ac = nullptr, *d_nm = nullptr;
-    CUDA_OK(h, cudaMalloc((void **)&d_raw, (size_t)chunk * B0));
-    CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * chunk));
-    CUDA_OK(h, cudaMalloc((void **)&d_nm, sizeof(int32_t) * chunk));
+    CUDA_OK(h, cudaMalloc((void **)&d_raw, keep_raw ? raw_total : (size_t)chunk * B0));
+    CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * M0));
+    CUDA_OK(h, cudaMalloc((void **)&d_nm, sizeof(int32_t) * M0));
+    stager st;
+    SGB_TRY(st.init(h, (size_t)64 << 20));
     std::vector<int32_t> ac_raw(M0), nm_raw(M0);
     for (int64_t m0 = 0; m0 < M0; m0 += chunk) {
         int64_t m1 = std::min(M0, m0 + chunk);
-        const uint8_t *src = rd.get(m0, m1);
-        if (!src) return sgb_fail(h, "setgeno: short read of .bed at marker %lld", (long long)m0);
-        CUDA_OK(h, cudaMemcpyAsync(d_raw, src, (size_t)(m1 - m0) * B0, cudaMemcpyHostToDevice, h->stream));
-        h->cnt.bytes_h2d += (m1 - m0) * B0;
-        SGB_TRY(k_count_markers(h, d_raw, B0, m1 - m0, d_indmask, d_ac, d_nm));
-        CUDA_OK(h, cudaMemcpyAsync(ac_raw.data() + m0, d_ac, sizeof(int32_t) * (m1 - m0), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_OK(h, cudaMemcpyAsync(nm_raw.data() + m0, d_nm, sizeof(int32_t) * (m1 - m0), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        uint8_t *dst = keep_raw ? d_raw + (size_t)m0 * B0 : d_raw;
+        int rc = st.push(rd, m0, m1, dst);
+        if (rc) { st.destroy(); return rc; }
+        SGB_TRY(k_count_markers(h, dst, B0, m1 - m0, d_indmask, d_ac + m0, d_nm + m0));
+        if (!keep_raw) CUDA_OK(h, cudaStreamSynchronize(h->stream));      // the chunk buffer is reused
     }
+    CUDA_OK(h, cudaMemcpyAsync(ac_raw.data(), d_ac, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(nm_raw.data(), d_nm, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
 
     // ---- host QC (fp32, reference order) ----
     h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
@@ -299,16 +382,15 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
             else if (kind[m] == 2) { vrows.push_back((int32_t)(m - m0)); vfills.push_back(fill_raw[m]); }
         }
         if (rows.empty() && vrows.empty()) continue;
-        if (M0 > chunk || m0 > 0 || true) {          // (re)upload this chunk
-            const uint8_t *src = rd.get(m0, m1);
-            if (!src) return sgb_fail(h, "setgeno: short read of .bed at marker %lld", (long long)m0);
-            CUDA_OK(h, cudaMemcpyAsync(d_raw, src, (size_t)(m1 - m0) * B0, cudaMemcpyHostToDevice, h->stream));
-            h->cnt.bytes_h2d += (m1 - m0) * B0;
+        const uint8_t *d_chunk = keep_raw ? d_raw + (size_t)m0 * B0 : d_raw;
+        if (!keep_raw) {                              // second upload of this chunk (raw .bed too large to keep)
+            int rc = st.push(rd, m0, m1, d_raw);
+            if (rc) { st.destroy(); return rc; }
         }
         if (!rows.empty()) {
             CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
             CUDA_OK(h, cudaMemcpyAsync(d_fill, fills.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
-            SGB_TRY(k_repack(h, d_raw, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG + lrow * h->sG, h->sG));
+            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG + lrow * h->sG, h->sG));
             CUDA_OK(h, cudaStreamSynchronize(h->stream));
             lrow += (int64_t)rows.size();
         }
@@ -316,15 +398,18 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
             if (!d_vr) CUDA_OK(h, cudaMalloc((void **)&d_vr, (size_t)std::min<int64_t>(chunk, M0) * B));
             CUDA_OK(h, cudaMemcpyAsync(d_rows, vrows.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
             CUDA_OK(h, cudaMemcpyAsync(d_fill, vfills.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
-            SGB_TRY(k_repack(h, d_raw, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, B));
+            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, B));
             CUDA_OK(h, cudaMemcpyAsync(h->vr_packed.data() + (size_t)vrow * B, d_vr, (size_t)vrows.size() * B, cudaMemcpyDeviceToHost, h->stream));
             CUDA_OK(h, cudaStreamSynchronize(h->stream));
             vrow += (int64_t)vrows.size();
         }
     }
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    st.destroy();
+    cudaFree(d_raw); d_raw = nullptr;               // release the raw copy before the transpose needs its scratch
     SGB_TRY(k_transpose(h));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_raw); cudaFree(d_ac); cudaFree(d_nm); cudaFree(d_rows); cudaFree(d_fill); cudaFree(d_indmask); cudaFree(d_sub);
+    cudaFree(d_ac); cudaFree(d_nm); cudaFree(d_rows); cudaFree(d_fill); cudaFree(d_indmask); cudaFree(d_sub);
     if (d_vr) cudaFree(d_vr);
     h->loaded = true;
     return 0;
