@@ -306,3 +306,81 @@ def test_full_step1_matches_oracle(pair10k, golden_dir, trait):
         # scale-of-answer sanity against the reference's bundled example_binary.rda (other marker set, R's RNG):
         # theta = (1, 0.3327), intercept-only alpha = -2.52; same cohort and phenotype here.
         assert mg["theta"][0] == 1.0 and 0.05 < mg["theta"][1] < 1.5
+
+
+@pytest.mark.parametrize("shape", [(5, 9), (37, 50), (255, 257), (256, 1024), (1025, 777), (3001, 130)])
+def test_ragged_and_tiny_shapes(gpu2, shape):
+    """Sizes that are not multiples of the packing / tile units (4 samples per byte, 256-genotype k-steps, 128/512-row
+    tiles), down to a handful of samples: every engine against the oracle."""
+    from oracle import oracle as O
+    N0, M0 = shape
+    bed = O.synth_bed(N0, M0, seed=1000 + N0, miss_rate=0.03)
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.0, 1.0
+    o.setgeno(bed, N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+    g = gpu2
+    g.setminMAFforGRM(0.0); g.setmaxMissingRateforGRM(1.0); g.setminMAC_VarianceRatio(20, -1, False)
+    g.setgeno_mem(bed, N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+    assert (g.N, g.M) == (o.N, o.M) and np.array_equal(g.getAlleleCountVec(), o.ACVec)
+    for idx in (0, o.M // 2, o.M - 1):
+        assert np.array_equal(g.Get_OneSNP_Geno(idx), o.Get_OneSNP_Geno(idx))
+    rng = np.random.default_rng(N0)
+    B = rng.normal(size=(N0, 5))
+    want = o.getCrossprodMatAndKin(B)
+    for eng in ("tensor", "imma", "umma", "f64"):
+        g.set_engine(eng)
+        assert rel(g.getCrossprodMatAndKin(B), want) < TOL_MATVEC, eng
+        assert rel(g.getCrossprodMatAndKin(B[:, 0]), want[:, 0]) < TOL_MATVEC, eng
+        assert rel(g.get_DiagofKin(), o.get_DiagofKin()) < TOL_MATVEC, eng
+    g.set_engine("tensor")
+
+
+def test_pcg_limits_and_flags(pair10k):
+    g, o = pair10k
+    rng = np.random.default_rng(21)
+    w = rng.uniform(0.02, 0.25, size=o.N); tau = np.array([1.0, 2.5]); b = rng.normal(size=o.N)
+    # maxiterPCG reached before convergence (FG.cpp:2794-2796 prints "pcg did not converge"): same truncated iterate
+    x, it = g.getPCG1ofSigmaAndVector(w, tau, b, 2, 1e-12, return_iter=True)
+    xo, ito = o.getPCG1ofSigmaAndVector(w, tau, b, 2, 1e-12, return_iter=True)
+    assert it == ito == 2 and rel(x, xo) < TOL_FIT
+    # diag(Sigma) floor at 1e-4 (FG.cpp:2355-2357)
+    wbig = np.full(o.N, 1e9)
+    d = g.getDiagOfSigma(wbig, np.array([1.0, 0.0]))
+    assert np.all(d == 1e-4) and np.array_equal(d, o.getDiagOfSigma(wbig, np.array([1.0, 0.0])))
+
+
+def test_kin_diag_set_as_one(gpu2, grm10k):
+    """isDiagofKinSetAsOne (FG.cpp:2334-2340, 4372): diag(K) := 1 in the preconditioner and in get_DiagofKin."""
+    from oracle import oracle as O
+    N0, M0 = grm10k["N0"], grm10k["M0"]
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.01, 0.15
+    o.setgeno(grm10k["bed"], N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8), isDiagofKinSetAsOne=True)
+    g = gpu2
+    g.setminMAFforGRM(0.01); g.setmaxMissingRateforGRM(0.15)
+    g.setgeno_mem(grm10k["bed"], N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8), isDiagofKinSetAsOne=True)
+    assert np.all(g.get_DiagofKin() == 1.0)
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0.05, 0.25, size=N0); tau = np.array([1.0, 0.4]); b = rng.normal(size=N0)
+    assert rel(g.getDiagOfSigma(w, tau), o.getDiagOfSigma(w, tau)) < 1e-14
+    x, it = g.getPCG1ofSigmaAndVector(w, tau, b, 500, 1e-5, return_iter=True)
+    xo, ito = o.getPCG1ofSigmaAndVector(w, tau, b, 500, 1e-5, return_iter=True)
+    assert it == ito and rel(x, xo) < TOL_FIT
+
+
+def test_error_paths(gpu2, golden_dir):
+    from saige_gpu_b200 import SaigeB200Error
+    g = gpu2
+    with pytest.raises(SaigeB200Error, match="not loaded"):
+        g.N = 10; g.getCrossprodMatAndKin(np.zeros(10))
+    with pytest.raises(SaigeB200Error, match="bed file not open|fam file not open|bim file not open"):
+        g.setgeno("/nonexistent.bed", "/nonexistent.bim", "/nonexistent.fam", [1], [1])
+    p = os.path.join(golden_dir, "grm10k")
+    with pytest.raises(SaigeB200Error, match="out of range"):
+        g.setgeno(p + ".bed", p + ".bim", p + ".fam", [0, 5], np.ones(1000, np.uint8))
+    with pytest.raises(SaigeB200Error, match="indicator length"):
+        g.setgeno(p + ".bed", p + ".bim", p + ".fam", [1, 2], np.ones(10, np.uint8))
+    g.setminMAFforGRM(0.01)
+    g.setgeno(p + ".bed", p + ".bim", p + ".fam", np.arange(1, 1001), np.ones(1000, np.uint8))
+    with pytest.raises(SaigeB200Error, match="out of range"):
+        g.Get_OneSNP_Geno(g.M)
+    with pytest.raises(SaigeB200Error, match="setStartEndIndex"):
+        g.getCrossprodMatAndKin_LOCO(np.zeros(g.N))
