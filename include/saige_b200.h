@@ -150,6 +150,23 @@ int sgb_get_sigma_g(sgb_ctx *h, const double *w, const double *tau, const double
 double sgb_cal_cv(const double *x, int n);                                   /* calCV (FG.cpp:3104) */
 double sgb_inner_product(const double *x, const double *y, int64_t n);      /* innerProduct */
 
+/* ---- step 2: single-variant score test + SPA, batched over variants ------------------- */
+/* Null-model state of SAIGEClass (setSAIGEobjInCPP, SAIGE_test.cpp:30-120; fields chosen by ReadModel,
+ * R/readInGLMM.R:39-170): N model samples, p covariate columns; X, XXVX_inv, XVX_inv_XV are N x p column-major,
+ * XVX p x p; pos_in_fam[i] = 0-based .fam row of model sample i (PlinkClass::m_posSampleInPlink). */
+int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *mu, const double *res, const double *mu2,
+                        const double *y, const double *X, const double *XVX, const double *XXVX_inv,
+                        const double *XVX_inv_XV, const double *S_a, const double *tau, double varRatio, double SPAcutoff,
+                        const int32_t *pos_in_fam);
+/* mainMarkerInCPP loop body (Main.cpp:229-520) for n_markers raw PLINK rows (ceil(n_fam/4) bytes each, A1 = ALT):
+ * getOneMarker -> filter -> imputeGenoAndFlip (best_guess) -> scoreTestFast -> SPA / SPA_fast (SAIGE_test.cpp:212-292,
+ * 345-640).  out[n_markers x 20] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
+ * p.value, p.value.NA, Is.SPA, AF_case, AF_ctrl, N_case, N_ctrl, N_case_hom, N_case_het, N_ctrl_hom, N_ctrl_het, var2.
+ * se_two_sided = 1: SE of SPA-adjusted variants = |BETA| / |qnorm(p/2)| (matches the reference's bundled golden tables);
+ * 0: |BETA| / qnorm(p, upper) as this fork's source has it (SAIGE_test.cpp:523-526). */
+int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
+                           double min_mac, double max_missing, int se_two_sided, double *out);
+
 /* ---- device-resident benchmark hooks (bench.py `value` leg: inputs already in HBM) ---------------- */
 /* Runs `reps` k-column GRM products on device-resident synthetic right-hand sides, timing with CUDA events
  * on the library's stream; ms_out[reps] per-product times, and ms_kernel_out[2*reps] (may be NULL) the device time of

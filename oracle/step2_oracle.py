@@ -1,0 +1,212 @@
+"""CPU oracle for the NEXT row of SURVEY.md 8(f): step-2 single-variant score test with saddle-point approximation
+(binary and quantitative traits, PLINK input, full-GRM variance ratio).  TEST INFRASTRUCTURE ONLY.
+
+Restates, in numpy fp64:
+  PlinkClass::getOneMarker          /root/reference/src/SAIGE/src/PLINK.cpp:164-300   (alt-first: A1 of the .bim is ALT)
+  mainMarkerInCPP (marker loop)     src/Main.cpp:149-560
+  imputeGenoAndFlip                 src/UTIL.cpp:58-135
+  SAIGEClass::scoreTestFast         src/SAIGE_test.cpp:212-292
+  SAIGEClass::getMarkerPval         src/SAIGE_test.cpp:345-640   (SPA / SPA_fast dispatch, SE from the SPA p-value)
+  SPA, SPA_fast                     src/SPA.cpp:20-185
+  Korg/K1/K2/getroot/Get_Saddle_Prob (+ _fast) for the binomial CGF   src/SPA_binary.cpp:21-330
+  ReadModel                         src/SAIGE/R/readInGLMM.R:39-170 (which fields of the .rda step 2 consumes, LOCO swap)
+
+Pinned by the reference's own golden table extdata/output/genotype_100markers_marker_plink.txt (32 variants, produced
+from extdata/output/example_binary.rda + extdata/input/genotype_100markers.{bed,bim,fam}) -- tests/test_step2_golden.py.
+Not implemented (not exercised by that fixture): efficient-resampling exact test for MAC <= 4 (ER_binary_func.cpp),
+Firth correction, conditional analysis, sparse-GRM variance, categorical variance ratios.
+"""
+import numpy as np
+from scipy import stats
+
+EPS25 = np.finfo(np.float64).eps ** 0.25          # tol = eps^0.25 (SAIGE_test.cpp:515-516)
+
+
+def read_model(modglmm, chrom=None, LOCO=True):
+    """ReadModel (readInGLMM.R:39-170): returns the dict of arrays step 2 uses."""
+    m = dict(modglmm)
+    mu = np.asarray(m["fitted.values"], dtype=np.float64).ravel()
+    res = np.asarray(m["residuals"], dtype=np.float64).ravel()
+    noK = m["obj.noK"]
+    if LOCO and chrom is not None and bool(np.asarray(m["LOCO"]).ravel()[0]):
+        lr = m["LOCOResult"][int(chrom) - 1]
+        if lr is not None and isinstance(lr, dict) and "fitted.values" in lr:
+            mu = np.asarray(lr["fitted.values"], dtype=np.float64).ravel()
+            res = np.asarray(lr["residuals"], dtype=np.float64).ravel()
+            noK = lr["obj.noK"]
+    trait = m["traitType"][0] if isinstance(m["traitType"], list) else str(m["traitType"])
+    tau = np.asarray(m["theta"], dtype=np.float64).ravel()
+    mu2 = mu * (1 - mu) if trait == "binary" else np.full(len(mu), 1.0 / tau[0])
+    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, y=np.asarray(m["y"], dtype=np.float64).ravel(),
+                X=np.asarray(m["X"], dtype=np.float64), XV=np.asarray(noK["XV"]), XVX=np.asarray(noK["XVX"]),
+                XXVX_inv=np.asarray(noK["XXVX_inv"]), XVX_inv_XV=np.asarray(noK["XVX_inv_XV"]),
+                S_a=np.asarray(noK["S_a"]).ravel(), sampleID=list(m["sampleID"]))
+
+
+def plink_marker(bed_body, n_fam, marker, pos_in_plink):
+    """getOneMarker, alt-first: genotype = copies of A1; -1 = missing (PLINK.hpp:48-56)."""
+    B0 = (n_fam + 3) // 4
+    row = bed_body[marker * B0:(marker + 1) * B0]
+    codes = ((row[:, None] >> np.array([0, 2, 4, 6])) & 3).reshape(-1)[:n_fam]
+    g = np.array([2, -1, 1, 0])[codes]             # 0b00 HOM_ALT=2, 0b01 missing, 0b10 HET=1, 0b11 HOM_REF=0
+    return g[pos_in_plink].astype(np.float64)
+
+
+# ---- binomial cumulant generating function and its saddle point (SPA_binary.cpp) ----
+def _K0(t, mu, g):
+    return np.sum(np.log(1 - mu + mu * np.exp(g * t)))
+
+
+def _K1(t, mu, g, q):
+    return np.sum(mu * g / ((1 - mu) * np.exp(-g * t) + mu)) - q
+
+
+def _K2(t, mu, g):
+    e = np.exp(-g * t)
+    return np.sum((1 - mu) * mu * g * g * e / ((1 - mu) * e + mu) ** 2)
+
+
+def _getroot(K1f, K2f, q, gpos, gneg, tol, maxiter=1000, fast=False):
+    """getroot_K1_Binom / getroot_K1_fast_Binom (SPA_binary.cpp:70-140, 214-270): safeguarded Newton."""
+    if q >= gpos or q <= gneg:
+        return np.inf, 0, True
+    t, K1e, prev = 0.0, K1f(0.0), np.inf
+    rep, conv = 1, True
+    while rep <= maxiter:
+        K2e = K2f(t)
+        tnew = t - K1e / K2e
+        if np.isnan(tnew):
+            conv = False
+            break
+        if abs(tnew - t) < tol:
+            conv = True
+            break
+        if rep == maxiter:
+            conv = False
+            break
+        newK1 = K1f(tnew)
+        changed = (K1e * newK1 < 0) if fast else (np.sign(K1e) != np.sign(newK1))
+        if changed:
+            if abs(tnew - t) > prev - tol:
+                tnew = t + np.sign(newK1 - K1e) * prev / 2
+                newK1 = K1f(tnew)
+                prev = prev / 2
+            else:
+                prev = abs(tnew - t)
+        rep += 1
+        t, K1e = tnew, newK1
+    return t, rep, conv
+
+
+def _saddle_prob(zeta, K0f, K2f, q):
+    """Get_Saddle_Prob[_fast]_Binom (SPA_binary.cpp:146-214, 276-330), logp = False: Lugannani-Rice."""
+    k1, k2 = K0f(zeta), K2f(zeta)
+    temp1 = zeta * q - k1
+    if np.isfinite(k1) and np.isfinite(k2) and temp1 >= 0 and k2 >= 0:
+        w = np.sign(zeta) * np.sqrt(2 * temp1)
+        v = zeta * np.sqrt(k2)
+        if w != 0:
+            Z = w + np.log(v / w) / w
+            return (stats.norm.sf(Z) if Z > 0 else -stats.norm.cdf(Z)), True
+    return 0.0, False
+
+
+def spa_pvalue(mu, gt, q, qinv, pval_noadj, idx_nz, fast, var2=None):
+    """SPA / SPA_fast (SPA.cpp:20-185)."""
+    gpos, gneg = gt[gt > 0].sum(), gt[gt < 0].sum()
+    if fast:
+        gNB, muNB = gt[idx_nz], mu[idx_nz]
+        m1 = mu @ gt
+        NAmu = m1 - gNB @ muNB
+        NAsigma = var2 - np.sum(muNB * (1 - muNB) * gNB ** 2)
+        K0f = lambda t: _K0(t, muNB, gNB) + NAmu * t + 0.5 * NAsigma * t * t
+        K1f = lambda qq: (lambda t: _K1(t, muNB, gNB, qq) + NAmu + NAsigma * t)
+        K2f = lambda t: _K2(t, muNB, gNB) + NAsigma
+    else:
+        K0f = lambda t: _K0(t, mu, gt)
+        K1f = lambda qq: (lambda t: _K1(t, mu, gt, qq))
+        K2f = lambda t: _K2(t, mu, gt)
+    r1, _, c1 = _getroot(K1f(q), K2f, q, gpos, gneg, EPS25, fast=fast)
+    r2, _, c2 = _getroot(K1f(qinv), K2f, qinv, gpos, gneg, EPS25, fast=fast)
+    if not (c1 and c2):
+        return pval_noadj, False
+    conv = True
+    p1, s1 = _saddle_prob(r1, K0f, K2f, q)
+    p2, s2 = _saddle_prob(r2, K0f, K2f, qinv)
+    if not s1:
+        conv, p1 = False, pval_noadj / 2
+    if not s2:
+        conv, p2 = False, pval_noadj / 2
+    return abs(p1) + abs(p2), conv
+
+
+def score_test_fast(M, G, idx):
+    """scoreTestFast (SAIGE_test.cpp:212-292)."""
+    g1, X1, A1, res1 = G[idx], M["X"][idx], M["XVX_inv_XV"][idx], M["res"][idx]
+    Z = A1.T @ g1
+    Bv = X1 @ Z
+    gt1 = g1 - Bv
+    if M["trait"] == "binary":
+        mu21 = M["mu2"][idx]
+        var2 = float(Z @ M["XVX"] @ Z) - float(Bv ** 2 @ mu21) + float(gt1 ** 2 @ mu21)
+    else:
+        var2 = float(Z @ M["XVX"] @ Z) * M["tau"][0] + float(g1 @ g1) - 2 * float(g1 @ Bv)
+    var1 = var2 * M["varRatio"]
+    S = (float(res1 @ gt1) - float((M["S_a"] - res1 @ X1) @ Z)) / M["tau"][0]
+    stat = S * S / var1
+    pval = 1.0 if var1 <= np.finfo(float).tiny or not np.isfinite(stat) else float(stats.chi2.sf(stat, 1))
+    beta = S / var1
+    return dict(Beta=beta, seBeta=abs(beta) / np.sqrt(abs(stat)), pval=pval, Tstat=S, var1=var1, var2=var2)
+
+
+def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=2.0, se_two_sided=True):
+    """One pass of the mainMarkerInCPP loop body (Main.cpp:229-520).  Returns None when the marker is filtered."""
+    test_marker.__test__ = False
+    n = len(Graw)
+    miss = Graw < 0
+    cnt = n - int(miss.sum())
+    alt_counts = float(Graw[~miss].sum())
+    alt_freq = alt_counts / cnt / 2 if cnt > 0 else 0.0
+    missing_rate = miss.sum() / n
+    maf = min(alt_freq, 1 - alt_freq)
+    mac = maf * n * (1 - missing_rate) * 2
+    if missing_rate > max_missing or maf < min_maf or mac < min_mac:
+        return None
+    # imputeGenoAndFlip (UTIL.cpp:58-135), best_guess
+    G = Graw.copy()
+    flip = alt_freq > 0.5
+    if flip:
+        G = 2 - G
+        alt_freq = 1 - alt_freq
+    if miss.any():
+        G[miss] = np.round(2 * alt_freq)
+    alt_count = G.sum()
+    alt_freq = alt_count / (2 * n)
+    if flip:
+        alt_freq, alt_count = 1 - alt_freq, 2 * n - alt_count
+    idx = np.nonzero(G != 0)[0]
+    st = score_test_fast(M, G, idx)
+    std_stat = abs(st["Tstat"]) / np.sqrt(st["var1"])
+    pval, se, is_spa = st["pval"], st["seBeta"], False
+    if np.isfinite(std_stat) and std_stat > spa_cutoff and M["trait"] == "binary":
+        gt = G - M["XXVX_inv"] @ (M["XV"] @ G)                      # getadjGFast
+        m1 = float(M["mu"] @ gt)
+        q = st["Tstat"] / np.sqrt(st["var1"] / st["var2"]) + m1
+        qinv = -abs(q - m1) + m1 if q - m1 > 0 else (m1 if q == m1 else abs(q - m1) + m1)
+        fast = (n - len(idx)) / n >= 0.5
+        pspa, conv = spa_pvalue(M["mu"], gt, q, qinv, st["pval"], idx, fast, st["var2"])
+        if conv and pspa != 0:
+            is_spa = True
+            pval = pspa
+            # SE from the SPA p-value: the reference's bundled golden table corresponds to |qnorm(p/2)| (upstream SAIGE);
+            # this fork's source has qnorm(p, upper tail) (SAIGE_test.cpp:523-526) -> se_two_sided=False
+            se = abs(st["Beta"]) / abs(stats.norm.isf(pspa / 2 if se_two_sided else pspa))
+    sgn = -1.0 if flip else 1.0
+    y = M["y"]
+    case, ctrl = y == 1, y == 0
+    afc, aft = G[case].mean() / 2, G[ctrl].mean() / 2
+    if flip:
+        afc, aft = 1 - afc, 1 - aft
+    return dict(AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * st["Beta"], SE=se,
+                Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa,
+                AF_case=afc, AF_ctrl=aft, N_case=int(case.sum()), N_ctrl=int(ctrl.sum()))

@@ -338,6 +338,33 @@ class SaigeB200:
         x, y = _f64(x), _f64(y)
         return self._L.sgb_inner_product(_p(x), _p(y), len(x))
 
+    # ---- step 2: setSAIGEobjInCPP + mainMarkerInCPP ----
+    STEP2_COLUMNS = ("tested", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA",
+                     "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het",
+                     "var2")
+
+    def setSAIGEobjInCPP(self, model, varRatio, SPAcutoff, pos_in_fam):
+        """model: dict with mu, res, mu2, y, X, XVX, XXVX_inv, XVX_inv_XV, S_a, tau, trait (readInGLMM.R:39-170)."""
+        X = _f64(model["X"])
+        N, p = X.shape
+        arrs = [_f64(np.asarray(model[k], dtype=np.float64).reshape(-1) if k in ("mu", "res", "mu2", "y", "S_a", "tau") else model[k])
+                for k in ("mu", "res", "mu2", "y", "X", "XVX", "XXVX_inv", "XVX_inv_XV", "S_a", "tau")]
+        pos = np.ascontiguousarray(pos_in_fam, dtype=np.int32)
+        if len(pos) != N:
+            raise SaigeB200Error("pos_in_fam must have one entry per model sample")
+        self._ck(self._L.sgb_step2_set_model(self._h, N, p, int(model["trait"] == "binary"), *[_p(a) for a in arrs],
+                                             float(varRatio), float(SPAcutoff), _p(pos)))
+        self._step2_N = N
+
+    def mainMarkerInCPP(self, bed_rows, n_fam, n_markers, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, se_two_sided=True):
+        bed = np.ascontiguousarray(bed_rows, dtype=np.uint8)
+        if bed.size < ((n_fam + 3) // 4) * n_markers:
+            raise SaigeB200Error("bed_rows shorter than n_markers * ceil(n_fam/4) bytes")
+        out = np.zeros((n_markers, len(self.STEP2_COLUMNS)))
+        self._ck(self._L.sgb_step2_test_markers(self._h, _p(bed), int(n_fam), int(n_markers), float(min_MAF), float(min_MAC),
+                                                float(max_missing), int(bool(se_two_sided)), _p(out)))
+        return out
+
     # ---- bench hooks / counters ----
     def bench_crossprod_device(self, k, reps, seed=1):
         ms = np.zeros(reps, dtype=np.float32)

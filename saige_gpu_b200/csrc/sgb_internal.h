@@ -12,6 +12,7 @@
 #define SGB_SHARD_BLOCK 1024 // markers per block of the block-cyclic marker->rank map
 
 struct sgb_dist;             // NCCL state (dist.cu)
+struct sgb_step2;            // step-2 model state (step2.cu)
 
 struct sgb_ctx {
     int device = 0;
@@ -75,6 +76,7 @@ struct sgb_ctx {
 
     sgb_dist *dist = nullptr;
     int rank = 0, world = 1;
+    sgb_step2 *step2 = nullptr;
 
     sgb_counters cnt = {};
 };
@@ -168,3 +170,4 @@ int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n);
 int sgb_dist_init(sgb_ctx *h, int rank, int world, const void *id128);
 void sgb_dist_destroy(sgb_ctx *h);
 int sgb_dist_unique_id(void *id128, std::string &err);
+void sgb_step2_free(sgb_ctx *h);

@@ -1,0 +1,363 @@
+// Step-2 single-variant score test + saddle-point approximation, batched over variants.
+//
+// Replaces, per marker, the body of mainMarkerInCPP (Main.cpp:229-520): PlinkClass::getOneMarker (PLINK.cpp:164-300,
+// alt-first), the MAF/MAC/missing-rate filter, imputeGenoAndFlip (UTIL.cpp:58-135, best_guess), scoreTestFast
+// (SAIGE_test.cpp:212-292) and, when |T|/sqrt(var1) > SPAcutoff on a binary trait, getMarkerPval's SPA / SPA_fast
+// branch (SAIGE_test.cpp:345-640, SPA.cpp:20-185, SPA_binary.cpp:21-330).  All arithmetic fp64, like the reference.
+//
+// One CTA per variant.  The raw PLINK row (2 bits per .fam sample) is staged in shared memory; the per-sample model
+// vectors (mu, mu2, res, X, XVX_inv_XV, XXVX_inv: N x (3p + 3) doubles) are read through L2 by every CTA.
+// scoreTestFast's sums over the non-zero genotypes are folded into one pass:
+//     Z = A^T g,  W = (mu2*X)^T g,  T1 = sum mu2 g^2,  R0 = sum res g
+//     var2 = Z^T XVX Z + T1 - 2 Z.W            S = (R0 - S_a.Z) / tau0          (algebraically identical)
+// HBM-bound on the genotype bytes (N/4 per variant) once N is large; no tensor cores (integer decode + fp64 sums).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <algorithm>
+#include "sgb_internal.h"
+
+#define S2_MAXP 16
+#define S2_THREADS 256
+#define S2_NOUT 20      // doubles per variant in the result table (see include/saige_b200.h)
+
+struct s2_model {
+    int64_t N; int p; int binary;
+    const double *mu, *mu2, *res, *y, *X, *A /*XVX_inv_XV*/, *XXVXi /*XXVX_inv*/;
+    double XVX[S2_MAXP * S2_MAXP], S_a[S2_MAXP];
+    double tau0, varRatio, spa_cutoff;
+    const int32_t *pos;      // model sample -> row in the .fam
+};
+
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < S2_THREADS / 32; i++) t += sm[i];
+    return t;
+}
+
+// genotype of model sample i after flip / imputation: copies of the (possibly flipped) ALT allele
+__device__ __forceinline__ int s2_geno(const uint8_t *srow, int32_t src, int flip, int imputeG)
+{
+    int code = (srow[src >> 2] >> ((src & 3) << 1)) & 3;
+    int g = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : -1));      // PLINK.hpp:48-56, alt-first
+    if (g < 0) return imputeG;
+    return flip ? 2 - g : g;
+}
+
+struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + normal approximation of the zeros
+    double NAmu, NAsigma;
+    int fast;
+};
+
+__global__ void __launch_bounds__(S2_THREADS)
+step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
+             double max_missing, int se_two_sided, double *__restrict__ out)
+{
+    extern __shared__ uint8_t srow[];
+    __shared__ double red[S2_THREADS / 32];
+    __shared__ double Zs[S2_MAXP], Ws[S2_MAXP];
+    const int64_t m = blockIdx.x;
+    if (m >= nm) return;
+    const int tid = threadIdx.x, p = M.p;
+    const int64_t N = M.N;
+    double *o = out + m * S2_NOUT;
+    for (int64_t b = tid; b < B0; b += S2_THREADS) srow[b] = bed[m * B0 + b];
+    __syncthreads();
+
+    // ---- getOneMarker: counts over the model's samples ----
+    double c_alt = 0, c_miss = 0;
+    for (int64_t i = tid; i < N; i += S2_THREADS) {
+        int32_t src = M.pos[i];
+        int code = (srow[src >> 2] >> ((src & 3) << 1)) & 3;
+        c_alt += code == 0 ? 2.0 : (code == 2 ? 1.0 : 0.0);
+        c_miss += code == 1 ? 1.0 : 0.0;
+    }
+    const double altCounts0 = block_sum(c_alt, red), nMiss = block_sum(c_miss, red);
+    const double cnt = (double)N - nMiss;
+    double altFreq = cnt > 0 ? altCounts0 / cnt / 2.0 : 0.0;
+    const double missingRate = nMiss / (double)N;
+    const double MAF = fmin(altFreq, 1.0 - altFreq);
+    const double MAC0 = MAF * (double)N * (1.0 - missingRate) * 2.0;
+    if (missingRate > max_missing || MAF < min_maf || MAC0 < min_mac) {       // Main.cpp:296
+        if (tid == 0) { for (int c = 0; c < S2_NOUT; c++) o[c] = nan(""); o[0] = 0.0; o[2] = altFreq; o[3] = missingRate; }
+        return;
+    }
+    // ---- imputeGenoAndFlip (best_guess) ----
+    const int flip = altFreq > 0.5;
+    if (flip) altFreq = 1.0 - altFreq;
+    const int imputeG = nMiss > 0 ? (int)round(2.0 * altFreq) : 0;
+
+    // ---- one pass over the samples: every sum scoreTestFast needs + case/control tallies ----
+    double zs[S2_MAXP], ws[S2_MAXP];
+#pragma unroll
+    for (int j = 0; j < S2_MAXP; j++) { zs[j] = 0; ws[j] = 0; }
+    double t1 = 0, r0 = 0, gsum = 0, nz = 0, gcase = 0, ncase = 0, gctrl = 0, nctrl = 0, case_hom = 0, case_het = 0, ctrl_hom = 0, ctrl_het = 0;
+    for (int64_t i = tid; i < N; i += S2_THREADS) {
+        const int g = s2_geno(srow, M.pos[i], flip, imputeG);
+        const double yi = M.y[i];
+        if (yi == 1.0) { ncase += 1; gcase += g; case_hom += g == 2; case_het += g == 1; }
+        else { nctrl += 1; gctrl += g; ctrl_hom += g == 2; ctrl_het += g == 1; }
+        if (g) {
+            const double gd = (double)g, m2 = M.mu2[i];
+            gsum += gd; nz += 1;
+            t1 += m2 * gd * gd;
+            r0 += M.res[i] * gd;
+            for (int j = 0; j < p; j++) {
+                zs[j] += M.A[i + (int64_t)j * N] * gd;
+                ws[j] += m2 * M.X[i + (int64_t)j * N] * gd;
+            }
+        }
+    }
+    t1 = block_sum(t1, red); r0 = block_sum(r0, red); gsum = block_sum(gsum, red); nz = block_sum(nz, red);
+    gcase = block_sum(gcase, red); ncase = block_sum(ncase, red); gctrl = block_sum(gctrl, red); nctrl = block_sum(nctrl, red);
+    case_hom = block_sum(case_hom, red); case_het = block_sum(case_het, red);
+    ctrl_hom = block_sum(ctrl_hom, red); ctrl_het = block_sum(ctrl_het, red);
+    for (int j = 0; j < p; j++) {
+        double z = block_sum(zs[j], red), w = block_sum(ws[j], red);
+        if (tid == 0) { Zs[j] = z; Ws[j] = w; }
+    }
+    __syncthreads();
+    // altFreq / altCounts after imputation (UTIL.cpp:112-118)
+    double altCount = gsum;
+    altFreq = altCount / (2.0 * (double)N);
+    if (flip) { altFreq = 1.0 - altFreq; altCount = 2.0 * (double)N - altCount; }
+
+    // ---- scoreTestFast ----
+    double zxz = 0, zw = 0, saz = 0;
+    for (int a = 0; a < p; a++) {
+        double acc = 0;
+        for (int b = 0; b < p; b++) acc += M.XVX[a + b * p] * Zs[b];
+        zxz += Zs[a] * acc;
+        zw += Zs[a] * Ws[a];
+        saz += M.S_a[a] * Zs[a];
+    }
+    double var2;
+    if (M.binary) var2 = zxz + t1 - 2.0 * zw;
+    else {
+        // quantitative (SAIGE_test.cpp:246-248): ZtXVXZ*tau0 + g.g - 2 g.B ; mu2 = 1/tau0 constant => g.g = t1*tau0, g.B = zw*tau0
+        var2 = zxz * M.tau0 + t1 * M.tau0 - 2.0 * zw * M.tau0;
+    }
+    const double var1 = var2 * M.varRatio;
+    const double S = (r0 - saz) / M.tau0;
+    double stat = S * S / var1;
+    double pval_noadj;
+    if (var1 <= 2.2250738585072014e-308) pval_noadj = 1.0;
+    else if (isfinite(stat)) pval_noadj = erfc(sqrt(stat * 0.5));            // chi-square(1) upper tail
+    else { pval_noadj = 1.0; stat = 0.0; }
+    const double Beta = S / var1;
+    double seBeta = fabs(Beta) / sqrt(fabs(stat));
+    double pval = pval_noadj, isSPA = 0.0;
+
+    // ---- saddle-point approximation (binary traits) ----
+    const double StdStat = fabs(S) / sqrt(var1);
+    if (M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff) {
+        // gtilde_i = g_i - XXVX_inv[i,:] . (XV g),  XV g = W  (getadjGFast, SAIGE_test.cpp:306-315)
+        double m1p = 0, gpos = 0, gneg = 0, gmuNB = 0, sigNB = 0;
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            const int g = s2_geno(srow, M.pos[i], flip, imputeG);
+            double gt = (double)g;
+            for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
+            const double mu = M.mu[i];
+            m1p += mu * gt;
+            if (gt > 0) gpos += gt; else if (gt < 0) gneg += gt;
+            if (g) { gmuNB += gt * mu; sigNB += mu * (1.0 - mu) * gt * gt; }
+        }
+        const double m1 = block_sum(m1p, red);
+        gpos = block_sum(gpos, red); gneg = block_sum(gneg, red); gmuNB = block_sum(gmuNB, red); sigNB = block_sum(sigNB, red);
+        const int fast = ((double)N - nz) / (double)N >= 0.5;
+        const double NAmu = m1 - gmuNB, NAsigma = var2 - sigNB;
+        const double q = S / sqrt(var1 / var2) + m1;
+        double qinv;
+        if (q - m1 > 0) qinv = -fabs(q - m1) + m1; else if (q - m1 == 0) qinv = m1; else qinv = fabs(q - m1) + m1;
+        const double tol = 1.220703125e-4;          // eps^0.25 (SAIGE_test.cpp:515-516)
+
+        // CGF sums at t over the samples that enter exactly: all samples (SPA) or the non-zero genotypes (SPA_fast)
+        auto cgf = [&](double t, double &k0, double &k1, double &k2) {
+            double a0 = 0, a1 = 0, a2 = 0;
+            for (int64_t i = tid; i < N; i += S2_THREADS) {
+                const int g = s2_geno(srow, M.pos[i], flip, imputeG);
+                if (fast && !g) continue;
+                double gt = (double)g;
+                for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
+                const double mu = M.mu[i];
+                const double e = exp(-gt * t);
+                const double den = (1.0 - mu) * e + mu;
+                a0 += log(1.0 - mu + mu * exp(gt * t));
+                a1 += mu * gt / den;
+                a2 += (1.0 - mu) * mu * gt * gt * e / (den * den);
+            }
+            k0 = block_sum(a0, red); k1 = block_sum(a1, red); k2 = block_sum(a2, red);
+            if (fast) { k0 += NAmu * t + 0.5 * NAsigma * t * t; k1 += NAmu + NAsigma * t; k2 += NAsigma; }
+        };
+        double pside[2]; bool conv_all = true, saddle_all = true;
+        for (int side = 0; side < 2; side++) {
+            const double qq = side == 0 ? q : qinv;
+            double root; bool conv = true;
+            if (qq >= gpos || qq <= gneg) root = INFINITY;
+            else {
+                // getroot_K1[_fast]_Binom (SPA_binary.cpp:70-140, 214-270), init 0, maxiter 1000
+                double t = 0.0, k0, k1, k2, prevJump = INFINITY;
+                cgf(t, k0, k1, k2);
+                double K1e = k1 - qq;
+                int rep = 1;
+                while (true) {
+                    double tnew = t - K1e / k2;
+                    if (isnan(tnew)) { conv = false; break; }
+                    if (fabs(tnew - t) < tol) { conv = true; break; }
+                    if (rep == 1000) { conv = false; break; }
+                    double n0, n1, n2;
+                    cgf(tnew, n0, n1, n2);
+                    double newK1 = n1 - qq;
+                    const bool changed = fast ? (K1e * newK1 < 0) : ((K1e > 0) - (K1e < 0)) != ((newK1 > 0) - (newK1 < 0));
+                    if (changed) {
+                        if (fabs(tnew - t) > prevJump - tol) {
+                            const double d = newK1 - K1e;
+                            tnew = t + ((d > 0) - (d < 0)) * prevJump / 2;
+                            cgf(tnew, n0, n1, n2);
+                            newK1 = n1 - qq;
+                            prevJump = prevJump / 2;
+                        } else prevJump = fabs(tnew - t);
+                    }
+                    rep++; t = tnew; K1e = newK1; k2 = n2;
+                }
+                root = t;
+            }
+            if (!conv) { conv_all = false; break; }
+            // Get_Saddle_Prob[_fast]_Binom (SPA_binary.cpp:146-214, 276-330): Lugannani-Rice
+            double k0, k1, k2;
+            double ps = 0.0; bool isSaddle = false;
+            if (isfinite(root)) {
+                cgf(root, k0, k1, k2);
+                const double temp1 = root * qq - k0;
+                if (isfinite(k0) && isfinite(k2) && temp1 >= 0 && k2 >= 0) {
+                    const double w = ((root > 0) - (root < 0)) * sqrt(2.0 * temp1), v = root * sqrt(k2);
+                    if (w != 0) {
+                        const double Zt = w + log(v / w) / w;
+                        ps = Zt > 0 ? 0.5 * erfc(Zt * 0.7071067811865476) : -0.5 * erfc(-Zt * 0.7071067811865476);
+                        isSaddle = true;
+                    }
+                }
+            }
+            if (!isSaddle) { saddle_all = false; ps = pval_noadj / 2; }
+            pside[side] = ps;
+        }
+        if (conv_all) {
+            const double pspa = fabs(pside[0]) + fabs(pside[1]);
+            if (saddle_all && pspa != 0) {
+                isSPA = 1.0; pval = pspa;
+                // SE from the SPA p-value.  se_two_sided: |qnorm(p/2)| (what produced the reference's bundled golden tables);
+                // otherwise qnorm(p, upper tail) as written in this fork's source (SAIGE_test.cpp:523-526).
+                const double qv = fabs(normcdfinv(se_two_sided ? pspa * 0.5 : pspa));
+                seBeta = fabs(Beta) / qv;
+            }
+        }
+    }
+    if (tid == 0) {
+        const double sgn = flip ? -1.0 : 1.0;
+        double afc = ncase > 0 ? gcase / ncase / 2.0 : nan(""), aft = nctrl > 0 ? gctrl / nctrl / 2.0 : nan("");
+        if (flip) { afc = 1.0 - afc; aft = 1.0 - aft; case_hom = ncase - case_het - case_hom; ctrl_hom = nctrl - ctrl_het - ctrl_hom; }
+        o[0] = 1.0;            // tested
+        o[1] = altCount; o[2] = altFreq; o[3] = missingRate;
+        o[4] = sgn * Beta; o[5] = seBeta; o[6] = sgn * S; o[7] = var1; o[8] = pval; o[9] = pval_noadj; o[10] = isSPA;
+        o[11] = afc; o[12] = aft; o[13] = ncase; o[14] = nctrl; o[15] = case_hom; o[16] = case_het; o[17] = ctrl_hom; o[18] = ctrl_het;
+        o[19] = var2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct sgb_step2 {
+    s2_model M;
+    double *d_vec = nullptr;      // mu | mu2 | res | y | X | A | XXVXi
+    int32_t *d_pos = nullptr;
+    uint8_t *d_bed = nullptr; size_t bed_bytes = 0;
+    double *d_out = nullptr; size_t out_elems = 0;
+};
+
+extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *mu, const double *res,
+                                   const double *mu2, const double *y, const double *X, const double *XVX,
+                                   const double *XXVX_inv, const double *XVX_inv_XV, const double *S_a, const double *tau,
+                                   double varRatio, double SPAcutoff, const int32_t *pos_in_fam)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (p < 1 || p > S2_MAXP) return sgb_fail(h, "step2: p=%d out of range [1,%d]", p, S2_MAXP);
+    if (N < 1) return sgb_fail(h, "step2: empty model");
+    if (!h->step2) h->step2 = new sgb_step2();
+    sgb_step2 *s = h->step2;
+    if (s->d_vec) { cudaFree(s->d_vec); s->d_vec = nullptr; }
+    if (s->d_pos) { cudaFree(s->d_pos); s->d_pos = nullptr; }
+    const size_t nvec = (size_t)N * (4 + 3 * p);
+    CUDA_OK(h, cudaMalloc((void **)&s->d_vec, sizeof(double) * nvec));
+    CUDA_OK(h, cudaMalloc((void **)&s->d_pos, sizeof(int32_t) * N));
+    double *d = s->d_vec;
+    const double *src[7] = {mu, mu2, res, y, X, XVX_inv_XV, XXVX_inv};
+    const size_t len[7] = {(size_t)N, (size_t)N, (size_t)N, (size_t)N, (size_t)N * p, (size_t)N * p, (size_t)N * p};
+    const double *dev[7];
+    for (int i = 0; i < 7; i++) {
+        CUDA_OK(h, cudaMemcpyAsync(d, src[i], sizeof(double) * len[i], cudaMemcpyHostToDevice, h->stream));
+        dev[i] = d; d += len[i];
+    }
+    CUDA_OK(h, cudaMemcpyAsync(s->d_pos, pos_in_fam, sizeof(int32_t) * N, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    s2_model &M = s->M;
+    M.N = N; M.p = p; M.binary = binary;
+    M.mu = dev[0]; M.mu2 = dev[1]; M.res = dev[2]; M.y = dev[3]; M.X = dev[4]; M.A = dev[5]; M.XXVXi = dev[6];
+    for (int i = 0; i < p * p; i++) M.XVX[i] = XVX[i];
+    for (int i = 0; i < p; i++) M.S_a[i] = S_a[i];
+    M.tau0 = tau[0]; M.varRatio = varRatio; M.spa_cutoff = SPAcutoff; M.pos = s->d_pos;
+    return 0;
+}
+
+extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
+                                      double min_mac, double max_missing, int se_two_sided, double *out)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    sgb_step2 *s = h->step2;
+    if (!s || !s->d_vec) return sgb_fail(h, "step2: call sgb_step2_set_model first");
+    if (n_markers <= 0) return 0;
+    const int64_t B0 = (n_fam + 3) / 4;
+    if (B0 > 200 * 1024) return sgb_fail(h, "step2: more than 819,200 samples in the .fam are not supported yet");
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)512 << 20) / B0));
+    SGB_TRY(sgb_ensure(h, (void **)&s->d_bed, &s->bed_bytes, (size_t)chunk * B0));
+    size_t ob = s->out_elems * sizeof(double);
+    SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, sizeof(double) * (size_t)chunk * S2_NOUT));
+    s->out_elems = ob / sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    for (int64_t m0 = 0; m0 < n_markers; m0 += chunk) {
+        const int64_t nm = std::min(chunk, n_markers - m0);
+        CUDA_OK(h, cudaMemcpyAsync(s->d_bed, bed_rows + (size_t)m0 * B0, (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
+        h->cnt.bytes_h2d += nm * B0;
+        step2_kernel<<<(unsigned)nm, S2_THREADS, (size_t)B0, h->stream>>>(s->M, s->d_bed, B0, nm, min_maf, min_mac, max_missing,
+                                                                           se_two_sided, s->d_out);
+        h->cnt.n_kernel_launches++;
+        CUDA_OK(h, cudaGetLastError());
+        CUDA_OK(h, cudaMemcpyAsync(out + (size_t)m0 * S2_NOUT, s->d_out, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
+        h->cnt.bytes_d2h += sizeof(double) * nm * S2_NOUT;
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+void sgb_step2_free(sgb_ctx *h)
+{
+    sgb_step2 *s = h->step2;
+    if (!s) return;
+    if (s->d_vec) cudaFree(s->d_vec);
+    if (s->d_pos) cudaFree(s->d_pos);
+    if (s->d_bed) cudaFree(s->d_bed);
+    if (s->d_out) cudaFree(s->d_out);
+    delete s;
+    h->step2 = nullptr;
+}

@@ -116,6 +116,7 @@ extern "C" void sgb_destroy(sgb_ctx *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     sgb_dist_destroy(h);
+    sgb_step2_free(h);
     free_store(h);
     void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx, h->d_limbsum};
     for (auto p : ptrs) if (p) cudaFree(p);

@@ -1,0 +1,194 @@
+"""Minimal reader for R's `save()` files (.rda / .RData, serialization format 2/3, XDR, gzip/bzip2/xz or plain).
+
+Host-side stand-in for `load()` in `ReadModel` (/root/reference/src/SAIGE/R/readInGLMM.R:39-45): step 2 consumes the
+null model that step 1 wrote with `save(modglmm, file = ...)` (FG.R:1297-1301).  Only the SEXP types that occur in
+SAIGE model files are supported: NULL, symbols, pairlists, lists, character / logical / integer / real vectors,
+attributes (names, dim, dimnames, class), reference objects and the ALTREP compact sequences / wrappers.
+
+Returns plain Python objects: named lists -> dict (insertion ordered), unnamed lists -> list, atomic vectors ->
+numpy arrays (matrices reshaped column-major via `dim`), length-1 atomics stay arrays; NA_integer_ -> masked as -2^31.
+"""
+import bz2
+import gzip
+import lzma
+import struct
+
+import numpy as np
+
+NILVALUE_SXP, GLOBALENV_SXP, EMPTYENV_SXP, BASEENV_SXP = 254, 253, 242, 241
+REFSXP, PERSISTSXP, PACKAGESXP, NAMESPACESXP, BASENAMESPACE_SXP, MISSINGARG_SXP, UNBOUNDVALUE_SXP = 255, 247, 250, 249, 247, 251, 252
+ALTREP_SXP, ATTRLISTSXP, ATTRLANGSXP = 238, 239, 240
+NILSXP, SYMSXP, LISTSXP, CLOSXP, ENVSXP, PROMSXP, LANGSXP, CHARSXP, LGLSXP, INTSXP, REALSXP, CPLXSXP, STRSXP, VECSXP, EXPRSXP, RAWSXP, S4SXP = (
+    0, 1, 2, 3, 4, 5, 6, 9, 10, 13, 14, 15, 16, 19, 20, 24, 25)
+
+
+class RObject:
+    """Anything we do not convert (closures, environments, language objects): kept opaque."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __repr__(self):
+        return "<R %s>" % self.kind
+
+
+class _Reader:
+    def __init__(self, data):
+        self.b, self.p, self.refs = data, 0, []
+
+    def int(self):
+        v = struct.unpack_from(">i", self.b, self.p)[0]
+        self.p += 4
+        return v
+
+    def length(self):
+        n = self.int()
+        if n == -1:
+            hi, lo = struct.unpack_from(">II", self.b, self.p)
+            self.p += 8
+            n = (hi << 32) | lo
+        return n
+
+    def bytes(self, n):
+        v = self.b[self.p:self.p + n]
+        self.p += n
+        return v
+
+    def item(self):
+        flags = self.int()
+        typ = flags & 0xFF
+        has_attr, has_tag = bool(flags & 0x200), bool(flags & 0x400)
+        if typ in (NILVALUE_SXP, NILSXP):
+            return None
+        if typ in (GLOBALENV_SXP, EMPTYENV_SXP, BASEENV_SXP, MISSINGARG_SXP, UNBOUNDVALUE_SXP, 247):
+            return RObject("env/special %d" % typ)
+        if typ == REFSXP:
+            idx = flags >> 8
+            if idx == 0:
+                idx = self.int()
+            return self.refs[idx - 1]
+        if typ == SYMSXP:
+            name = self.item()
+            self.refs.append(name)
+            return name
+        if typ in (PACKAGESXP, NAMESPACESXP, PERSISTSXP):
+            self.int()          # 0
+            n = self.int()
+            obj = RObject("namespace " + " ".join(str(self.item()) for _ in range(n)))
+            self.refs.append(obj)
+            return obj
+        if typ == ENVSXP:
+            obj = RObject("environment")
+            self.refs.append(obj)
+            self.int()          # locked
+            for _ in range(4):  # enclos, frame, hashtab, attrib
+                self.item()
+            return obj
+        if typ in (LISTSXP, LANGSXP, CLOSXP, PROMSXP, ATTRLISTSXP, ATTRLANGSXP):
+            # pairlist chain: iterate instead of recursing on the tail
+            out, first = [], True
+            while True:
+                if not first:
+                    flags = self.int()
+                    typ = flags & 0xFF
+                    has_attr, has_tag = bool(flags & 0x200), bool(flags & 0x400)
+                    if typ in (NILVALUE_SXP, NILSXP):
+                        break
+                    if typ not in (LISTSXP, LANGSXP, CLOSXP, PROMSXP, ATTRLISTSXP, ATTRLANGSXP):
+                        self.p -= 4
+                        out.append((None, self.item()))
+                        break
+                first = False
+                if has_attr:
+                    self.item()
+                tag = self.item() if has_tag else None
+                out.append((tag, self.item()))
+            return out
+        if typ == CHARSXP:
+            n = self.int()
+            return None if n == -1 else self.bytes(n).decode("utf-8", "replace")
+        attr = None
+        if typ == ALTREP_SXP:
+            info, state, attr_ = self.item(), self.item(), self.item()
+            cls = info[0][1] if isinstance(info, list) else str(info)
+            val = self._altrep(str(cls), state)
+            return self._with_attr(val, attr_)
+        if typ == LGLSXP or typ == INTSXP:
+            n = self.length()
+            val = np.frombuffer(self.bytes(4 * n), dtype=">i4").astype(np.int32)
+            if typ == LGLSXP:
+                val = np.where(val == -2147483648, -1, val).astype(np.int8)
+        elif typ == REALSXP:
+            n = self.length()
+            val = np.frombuffer(self.bytes(8 * n), dtype=">f8").astype(np.float64)
+        elif typ == CPLXSXP:
+            n = self.length()
+            val = np.frombuffer(self.bytes(16 * n), dtype=">c16").astype(np.complex128)
+        elif typ == STRSXP:
+            n = self.length()
+            val = [self.item() for _ in range(n)]
+        elif typ in (VECSXP, EXPRSXP):
+            n = self.length()
+            val = [self.item() for _ in range(n)]
+        elif typ == RAWSXP:
+            n = self.length()
+            val = np.frombuffer(self.bytes(n), dtype=np.uint8).copy()
+        elif typ == S4SXP:
+            val = RObject("S4")
+        elif typ in (7, 8):      # SPECIALSXP / BUILTINSXP
+            n = self.int()
+            val = RObject("builtin " + self.bytes(n).decode())
+        else:
+            raise ValueError("unsupported SEXP type %d at byte %d" % (typ, self.p))
+        if has_attr:
+            attr = self.item()
+        return self._with_attr(val, attr)
+
+    def _altrep(self, cls, state):
+        if cls in ("compact_intseq", "compact_realseq"):
+            n, start, step = (float(x) for x in state[:3])
+            arr = start + step * np.arange(int(n))
+            return arr.astype(np.int32 if cls == "compact_intseq" else np.float64)
+        if cls.startswith("wrap_"):
+            return state[0][1] if isinstance(state, list) and state and isinstance(state[0], tuple) else state
+        if cls == "deferred_string":
+            src = state[0][1] if isinstance(state[0], tuple) else state[0]
+            return [("%d" % v if float(v).is_integer() else repr(float(v))) for v in np.asarray(src)]
+        raise ValueError("unsupported ALTREP class " + cls)
+
+    @staticmethod
+    def _with_attr(val, attr):
+        if not attr:
+            return val
+        a = {str(k): v for k, v in attr}
+        if isinstance(val, np.ndarray) and "dim" in a:
+            val = val.reshape(tuple(int(d) for d in a["dim"]), order="F")
+        if isinstance(val, list) and "names" in a and a["names"] is not None:
+            names = list(a["names"])
+            if len(names) == len(val) and all(n not in (None, "") for n in names):
+                return dict(zip(names, val))
+        return val
+
+
+def load_rda(path):
+    """Returns {object name: value} for every object saved in the file."""
+    raw = open(path, "rb").read()
+    if raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
+    elif raw[:3] == b"BZh":
+        raw = bz2.decompress(raw)
+    elif raw[:6] == b"\xfd7zXZ\x00":
+        raw = lzma.decompress(raw)
+    if raw[:5] not in (b"RDX2\n", b"RDX3\n"):
+        raise ValueError("%s: not an R save() file (magic %r)" % (path, raw[:5]))
+    r = _Reader(raw)
+    r.p = 5
+    if r.bytes(2) != b"X\n":
+        raise ValueError("only XDR serialization is supported")
+    version = r.int()
+    r.int(); r.int()             # writer version, min reader version
+    if version == 3:
+        n = r.int()
+        r.bytes(n)               # native encoding
+    top = r.item()
+    return {str(k): v for k, v in top}

@@ -1,0 +1,102 @@
+"""Step-2 driver: single-variant association tests from a step-1 null model, PLINK input.
+
+Python mirror of the R side of `SPAGMMATtest` for single-variant tests (/root/reference/src/SAIGE/R/
+SAIGE_Test_main.R:61-420, R/readInGLMM.R:39-170 `ReadModel`, R/SAIGE_SPATest_Marker.R `SAIGE.Marker`): read the
+null model (.rda written by step 1), the variance ratio, the PLINK files; match model samples to .fam rows; stream
+marker rows to the C ABI (`sgb_step2_test_markers` = the body of mainMarkerInCPP, Main.cpp:149-560); write the result
+table with the reference's column names.  No numerical work happens here."""
+import numpy as np
+
+from .rdata import load_rda
+
+OUT_COLUMNS = ["CHR", "POS", "MarkerID", "Allele1", "Allele2", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE",
+               "Tstat", "var", "p.value", "p.value.NA", "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom",
+               "N_case_het", "N_ctrl_hom", "N_ctrl_het"]
+
+
+def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
+    """readInGLMM.R:39-170: the fields step 2 consumes; with LOCO the chromosome's refit replaces mu/res/obj.noK."""
+    m = load_rda(GMMATmodelFile)["modglmm"]
+    mu = np.asarray(m["fitted.values"], dtype=np.float64).ravel()
+    res = np.asarray(m["residuals"], dtype=np.float64).ravel()
+    noK = m["obj.noK"]
+    has_loco = bool(np.asarray(m.get("LOCO", [0])).ravel()[0])
+    if LOCO:
+        if not has_loco:
+            raise ValueError("LOCO is TRUE but the null model file .rda does not contain LOCO results")
+        if chrom == "":
+            raise ValueError("chrom needs to be specified in order to apply Leave-one-chromosome-out")
+        c = int(str(chrom).replace("chr", ""))
+        if 1 <= c <= 22:
+            lr = m["LOCOResult"][c - 1]
+            if isinstance(lr, dict) and "fitted.values" in lr:
+                mu = np.asarray(lr["fitted.values"], dtype=np.float64).ravel()
+                res = np.asarray(lr["residuals"], dtype=np.float64).ravel()
+                noK = lr["obj.noK"]
+    trait = m["traitType"][0] if isinstance(m["traitType"], list) else str(m["traitType"])
+    tau = np.asarray(m["theta"], dtype=np.float64).ravel()
+    mu2 = mu * (1 - mu) if trait == "binary" else np.full(len(mu), 1.0 / tau[0])
+    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, y=np.asarray(m["y"], dtype=np.float64).ravel(),
+                X=np.asarray(m["X"], dtype=np.float64), XVX=np.asarray(noK["XVX"], dtype=np.float64),
+                XXVX_inv=np.asarray(noK["XXVX_inv"], dtype=np.float64),
+                XVX_inv_XV=np.asarray(noK["XVX_inv_XV"], dtype=np.float64), S_a=np.asarray(noK["S_a"], dtype=np.float64).ravel(),
+                sampleID=[str(s) for s in m["sampleID"]])
+
+
+def Get_Variance_Ratio(varianceRatioFile):
+    """readInGLMM.R:358-: first 'null' row of the step-1 variance-ratio file."""
+    rows = [l.split() for l in open(varianceRatioFile) if l.strip()]
+    for r in rows:
+        if len(r) < 2 or r[1] == "null":
+            return float(r[0])
+    return float(rows[0][0])
+
+
+def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioFile, SAIGEOutputFile=None, chrom="",
+                 LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
+                 is_output_moreDetails=True, se_two_sided=True):
+    """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given."""
+    model = ReadModel(GMMATmodelFile, chrom, LOCO)
+    ratio = Get_Variance_Ratio(varianceRatioFile)
+    fam = [l.split()[1] for l in open(famFile)]
+    bim = [l.split() for l in open(bimFile)]
+    where = {s: i for i, s in enumerate(fam)}
+    missing = [s for s in model["sampleID"] if s not in where]
+    if missing:
+        raise ValueError("%d samples of the null model are not in %s" % (len(missing), famFile))
+    pos = np.array([where[s] for s in model["sampleID"]], dtype=np.int32)
+    geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
+    raw = np.fromfile(bedFile, dtype=np.uint8)
+    if raw[0] != 0x6C or raw[1] != 0x1B or raw[2] != 0x01:
+        raise ValueError("%s is not a SNP-major PLINK .bed" % bedFile)
+    n_fam, B0 = len(fam), (len(fam) + 3) // 4
+    body = raw[3:]
+    rows = []
+    for m0 in range(0, len(bim), markers_per_chunk):
+        m1 = min(len(bim), m0 + markers_per_chunk)
+        res = geno.mainMarkerInCPP(body[m0 * B0:m1 * B0], n_fam, m1 - m0, min_MAF, min_MAC, max_missing, se_two_sided)
+        for j in range(m1 - m0):
+            r = res[j]
+            if r[0] != 1.0:
+                continue                                   # filtered: not written (Main.cpp:296 `continue`)
+            b = bim[m0 + j]
+            row = {"CHR": b[0], "POS": b[3], "MarkerID": b[1], "Allele1": b[5], "Allele2": b[4]}     # alt-first: A1 = ALT = Allele2
+            for name, v in zip(geno.STEP2_COLUMNS[1:19], r[1:19]):
+                row[name] = v
+            row["Is.SPA"] = bool(r[10])
+            rows.append(row)
+    if SAIGEOutputFile:
+        cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
+        with open(SAIGEOutputFile, "w") as f:
+            f.write("\t".join(cols) + "\n")
+            for row in rows:
+                f.write("\t".join(_fmt(row[c]) for c in cols) + "\n")
+    return rows
+
+
+def _fmt(v):
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, float):
+        return "%.6g" % v
+    return str(v)

@@ -7,6 +7,8 @@ Fixtures (data, not source) come from /root/reference/src/SAIGE/extdata/input:
   plinkforGRM_1000samples_10kMarkers.{bed,bim,fam,frq}   -- pins decode / allele counts / MAF QC
   nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.{bed,bim,fam} -- 22-chromosome LOCO set
   pheno_1000samples.txt_withdosages_withBothTraitTypes.txt -- phenotypes/covariates of the bundled example
+  genotype_100markers.{bed,bim,fam} + ../output/example_binary.{rda,varianceRatio.txt} + ../output/
+  genotype_100markers_marker_plink.txt -- step-2 inputs and the reference's golden result table (32 variants)
 """
 import os
 import shutil
@@ -23,6 +25,13 @@ FILES = [
     ("nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.bim", "chr22_1000.bim"),
     ("nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.fam", "chr22_1000.fam"),
     ("pheno_1000samples.txt_withdosages_withBothTraitTypes.txt", "pheno_1000samples.txt"),
+    # step 2: inputs + the reference's own golden result table
+    ("genotype_100markers.bed", "step2_100markers.bed"),
+    ("genotype_100markers.bim", "step2_100markers.bim"),
+    ("genotype_100markers.fam", "step2_100markers.fam"),
+    ("../output/example_binary.rda", "example_binary.rda"),
+    ("../output/example_binary.varianceRatio.txt", "example_binary.varianceRatio.txt"),
+    ("../output/genotype_100markers_marker_plink.txt", "step2_100markers_golden.txt"),
 ]
 
 if __name__ == "__main__":
