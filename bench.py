@@ -111,6 +111,35 @@ def cpu_baseline(N, M, threads_note=True, target_s=12.0):
             "s_per_sample_matvec": per_sample}
 
 
+def step1_c1_beside(device):
+    """BASELINE config 1 (bundled 1000 samples x 10k markers, binary trait): the full step-1 null-GLMM fit on the CPU
+    oracle (fp64 numpy + C matvec, all cores) and on the GPU, same probes; wall seconds and the relative tau gap."""
+    from oracle import oracle as O
+    from saige_gpu_b200 import SaigeB200, step1
+    pre = os.path.join(ROOT, "tests", "golden", "grm10k")
+    bed, N0, M0, _ = O.read_bed(pre)
+    rows = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "pheno_1000samples.txt"))]
+    col = {h: i for i, h in enumerate(rows[0])}
+    y = np.array([float(r[col["y_binary"]]) for r in rows[1:]])
+    X = np.column_stack([np.ones(N0), [float(r[col["x1"]]) for r in rows[1:]], [float(r[col["x2"]]) for r in rows[1:]]])
+    probes = step1.ProbeStream(N0, 130, 200)
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.01, 0.15
+    t = time.time()
+    o.setgeno(bed, N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+    mo = O.glmmkin_ai_PCG(o, O.glm_fit(y, X, O.Binomial), (0, 0), probes.U, trait="binary")
+    t_cpu = time.time() - t
+    gg = SaigeB200(device=device)
+    gg.setminMAFforGRM(0.01); gg.setmaxMissingRateforGRM(0.15)
+    t = time.time()
+    gg.setgeno(pre + ".bed", pre + ".bim", pre + ".fam", np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+    mg = step1.glmmkin_ai_PCG(gg, step1.glm_fit(y, X, step1.Binomial), probes, trait="binary")
+    t_gpu = time.time() - t
+    gg.close()
+    return {"workload": "c1_bundled_1000x10k (9650 markers pass QC), binary trait, incl. genotype load", "cpu_oracle_wall_s": t_cpu,
+            "gpu_wall_s": t_gpu, "tau_cpu": float(mo["theta"][1]), "tau_gpu": float(mg["theta"][1]),
+            "tau_rel_gap": abs(float(mg["theta"][1]) - float(mo["theta"][1])) / abs(float(mo["theta"][1]))}
+
+
 def run_reference(args, N, M, rank, world):
     if rank != 0:
         return
@@ -210,12 +239,15 @@ def main():
     bytes_alg_product = 2 * Mloc * Bbytes + 16 * N + 16 * Mloc * 2
 
     # ---- batched products (the Hutchinson probes + phenotype ride in ONE multi-vector product) ----
-    kb = args.k_batch
-    g.bench_crossprod_device(kb, 1)
-    barrier()
-    msb, _ = g.bench_crossprod_device(kb, max(3, K // 2))
-    barrier()
-    batch_ms = max_over_ranks(float(msb.mean()))
+    batched = []
+    for kb in sorted(set([4, 8, args.k_batch])):
+        g.bench_crossprod_device(kb, 1)
+        barrier()
+        msb, _ = g.bench_crossprod_device(kb, max(3, K // 2))
+        barrier()
+        bms = max_over_ranks(float(msb.mean()))
+        batched.append({"k": kb, "ms_per_product": bms, "columns_per_s": kb / (bms * 1e-3),
+                        "kernel": "pk2_umma_kernel (tcgen05, tensor-bound)" if args.engine == "tensor" else args.engine})
 
     # ---- end-to-end leg: the public C-ABI call on pinned host vectors ----
     hb = torch.empty(N, dtype=torch.float64).pin_memory()
@@ -242,6 +274,7 @@ def main():
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(N, M)
+        cb["step1_c1"] = step1_c1_beside(local_rank)
     ingest_info = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # setgeno from a host-resident PLINK .bed body (QC + imputation + re-pack + transpose on the GPU), bounded sample
@@ -304,7 +337,7 @@ def main():
                          "bytes_per_launch": int(bytes_launch), "avg_launch_ms": sweep_ms,
                          "sweep1_ms": float(mk[:, 0].mean()), "sweep2_ms": float(mk[:, 1].mean()),
                          "whole_product_frac": bytes_alg_product / (total_ms / K * 1e-3) / 1e9 / peak},
-            "batched": {"k": kb, "ms_per_product": batch_ms, "columns_per_s": kb / (batch_ms * 1e-3)},
+            "batched": batched,
             "cpu_baseline": cb,
             "ingest": ingest_info,
             "step1": step1_info,
