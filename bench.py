@@ -283,7 +283,7 @@ def main():
         bed_i = O.synth_bed(n_i, m_i, SEED, miss_rate=0.01)
         gi = SaigeB200(device=local_rank)
         gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
-        gi.setgeno_mem(bed_i, n_i, m_i, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))        # warm-up
+        gi.setgeno_mem(bed_i, n_i, 512, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))        # warm-up on the first 512 markers
         ti = time.time()
         gi.setgeno_mem(bed_i, n_i, m_i, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))
         ti = time.time() - ti
