@@ -111,6 +111,43 @@ def cpu_baseline(N, M, threads_note=True, target_s=12.0):
             "s_per_sample_matvec": per_sample}
 
 
+def reference_gpu_kernel(N, M, msample=4096):
+    """The reference's OWN GPU matvec (gpuSymMatMult::sym_sgemv: dense fp32 standardised A on the device, two
+    cublasSgemv, H2D/D2H of the vectors per call -- gpuSymMatMult.cu:246-287), compiled unmodified into oracle/_ref,
+    timed on this B200 on a marker sample and scaled linearly in M (both sgemv are bandwidth-bound in the columns)."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libgpusymmatmult_ref.so")
+    if not os.path.exists(so):
+        return None
+    from oracle import oracle as O
+    ref = C.CDLL(so)
+    ref.ref_set_matrix.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p]
+    ref.ref_sym_sgemv.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
+    bed = O.synth_bed(N, msample, SEED)
+    o = O.OracleGeno(mode=O.REF32)
+    o.minMAF, o.maxMissing = 0.01, 0.15
+    o.setgeno(bed, N, msample, np.arange(1, N + 1), np.ones(N, np.uint8))
+    A = np.empty((N, o.M), dtype=np.float32, order="F")
+    for m in range(o.M):
+        A[:, m] = o.Get_OneSNP_StdGeno(m)
+    if ref.ref_set_matrix(N, o.M, A.ctypes.data) != 0:
+        return None
+    x = (np.random.default_rng(1).integers(0, 2, N) * 2.0 - 1.0).astype(np.float32)
+    z = np.zeros(N, dtype=np.float32)
+    for _ in range(3):
+        ref.ref_sym_sgemv(N, x.ctypes.data, z.ctypes.data)
+    reps, t0 = 20, time.time()
+    for _ in range(reps):
+        ref.ref_sym_sgemv(N, x.ctypes.data, z.ctypes.data)
+    per = (time.time() - t0) / reps
+    ref.ref_free()
+    per_full = per * (M / o.M)
+    return {"value": 1.0 / per_full, "unit": "matvecs/s", "kind": "reference GPU kernel (gpuSymMatMult.cu, unmodified) on this B200",
+            "sample": "%d of %d markers x %d samples dense fp32 (%.1f GB), scaled linearly in M; the full matrix would need %.0f GB"
+                      % (o.M, M, N, A.nbytes / 1e9, 4.0 * N * M / 1e9),
+            "s_per_sample_matvec": per, "dense_bytes_per_matvec_full": 8.0 * N * M}
+
+
 def step1_c1_beside(device):
     """BASELINE config 1 (bundled 1000 samples x 10k markers, binary trait): the full step-1 null-GLMM fit on the CPU
     oracle (fp64 numpy + C matvec, all cores) and on the GPU, same probes; wall seconds and the relative tau gap."""
@@ -275,6 +312,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(N, M)
         cb["step1_c1"] = step1_c1_beside(local_rank)
+        try:
+            cb["reference_gpu_kernel"] = reference_gpu_kernel(N, M)
+        except Exception as e:                      # the reference class prints and returns codes; never fail the bench on it
+            cb["reference_gpu_kernel"] = {"error": str(e)}
     ingest_info = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # setgeno from a host-resident PLINK .bed body (QC + imputation + re-pack + transpose on the GPU), bounded sample

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include <algorithm>
 #include "sgb_internal.h"
 
@@ -280,6 +281,9 @@ struct sgb_step2 {
     int32_t *d_pos = nullptr;
     uint8_t *d_bed = nullptr; size_t bed_bytes = 0;
     double *d_out = nullptr; size_t out_elems = 0;
+    uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
+    double *pout[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
 extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *mu, const double *res,
@@ -325,28 +329,54 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     if (n_markers <= 0) return 0;
     const int64_t B0 = (n_fam + 3) / 4;
     if (B0 > 200 * 1024) return sgb_fail(h, "step2: more than 819,200 samples in the .fam are not supported yet");
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)512 << 20) / B0));
-    SGB_TRY(sgb_ensure(h, (void **)&s->d_bed, &s->bed_bytes, (size_t)chunk * B0));
+    // chunks of <= 256 MB of raw rows (several waves of CTAs each), double-buffered through pinned memory: the host copy of chunk c+1 and the
+    // D2H of chunk c-1's results overlap the kernel of chunk c
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)256 << 20) / B0));
+    const size_t cbytes = (size_t)chunk * B0, obytes = sizeof(double) * (size_t)chunk * S2_NOUT;
+    if (!s->pin[0] || s->pin_bytes < cbytes) {
+        for (int i = 0; i < 2; i++) {
+            if (s->pin[i]) cudaFreeHost(s->pin[i]);
+            if (s->pout[i]) cudaFreeHost(s->pout[i]);
+            s->pin[i] = nullptr; s->pout[i] = nullptr;
+        }
+        for (int i = 0; i < 2; i++) {
+            CUDA_OK(h, cudaMallocHost((void **)&s->pin[i], cbytes));
+            CUDA_OK(h, cudaMallocHost((void **)&s->pout[i], obytes));
+        }
+        s->pin_bytes = cbytes;
+    }
+    for (int i = 0; i < 2; i++) if (!s->ev[i]) CUDA_OK(h, cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+    SGB_TRY(sgb_ensure(h, (void **)&s->d_bed, &s->bed_bytes, 2 * cbytes));
     size_t ob = s->out_elems * sizeof(double);
-    SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, sizeof(double) * (size_t)chunk * S2_NOUT));
+    SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, 2 * obytes));
     s->out_elems = ob / sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    for (int64_t m0 = 0; m0 < n_markers; m0 += chunk) {
+    int cur = 0;
+    int64_t held_m0[2] = {-1, -1}, held_nm[2] = {0, 0};
+    for (int64_t m0 = 0; m0 < n_markers; m0 += chunk, cur ^= 1) {
         const int64_t nm = std::min(chunk, n_markers - m0);
-        CUDA_OK(h, cudaMemcpyAsync(s->d_bed, bed_rows + (size_t)m0 * B0, (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(h, cudaEventSynchronize(s->ev[cur]));                      // buffers `cur` are free again (chunk c-2 done)
+        if (held_m0[cur] >= 0) memcpy(out + (size_t)held_m0[cur] * S2_NOUT, s->pout[cur], sizeof(double) * held_nm[cur] * S2_NOUT);
+        memcpy(s->pin[cur], bed_rows + (size_t)m0 * B0, (size_t)nm * B0);
+        uint8_t *db = s->d_bed + cur * cbytes;
+        double *dout = s->d_out + cur * (size_t)chunk * S2_NOUT;
+        CUDA_OK(h, cudaMemcpyAsync(db, s->pin[cur], (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
         h->cnt.bytes_h2d += nm * B0;
-        step2_kernel<<<(unsigned)nm, S2_THREADS, (size_t)B0, h->stream>>>(s->M, s->d_bed, B0, nm, min_maf, min_mac, max_missing,
-                                                                           se_two_sided, s->d_out);
+        step2_kernel<<<(unsigned)nm, S2_THREADS, (size_t)B0, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout);
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
-        CUDA_OK(h, cudaMemcpyAsync(out + (size_t)m0 * S2_NOUT, s->d_out, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaMemcpyAsync(s->pout[cur], dout, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
         h->cnt.bytes_d2h += sizeof(double) * nm * S2_NOUT;
-        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        CUDA_OK(h, cudaEventRecord(s->ev[cur], h->stream));
+        held_m0[cur] = m0; held_nm[cur] = nm;
     }
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 2; i++)
+        if (held_m0[i] >= 0) memcpy(out + (size_t)held_m0[i] * S2_NOUT, s->pout[i], sizeof(double) * held_nm[i] * S2_NOUT);
     return 0;
 }
 
@@ -358,6 +388,7 @@ void sgb_step2_free(sgb_ctx *h)
     if (s->d_pos) cudaFree(s->d_pos);
     if (s->d_bed) cudaFree(s->d_bed);
     if (s->d_out) cudaFree(s->d_out);
+    for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }
     delete s;
     h->step2 = nullptr;
 }

@@ -54,8 +54,10 @@ def Get_Variance_Ratio(varianceRatioFile):
 
 def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioFile, SAIGEOutputFile=None, chrom="",
                  LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
-                 is_output_moreDetails=True, se_two_sided=True):
-    """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given."""
+                 is_output_moreDetails=True, se_two_sided=True, rank=0, world=1):
+    """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given.
+    Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the .bim
+    and writes its own part; there is no collective, the parts are concatenated in rank order."""
     model = ReadModel(GMMATmodelFile, chrom, LOCO)
     ratio = Get_Variance_Ratio(varianceRatioFile)
     fam = [l.split()[1] for l in open(famFile)]
@@ -72,8 +74,10 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
     n_fam, B0 = len(fam), (len(fam) + 3) // 4
     body = raw[3:]
     rows = []
-    for m0 in range(0, len(bim), markers_per_chunk):
-        m1 = min(len(bim), m0 + markers_per_chunk)
+    per_rank = (len(bim) + world - 1) // world
+    lo, hi = min(len(bim), rank * per_rank), min(len(bim), (rank + 1) * per_rank)
+    for m0 in range(lo, hi, markers_per_chunk):
+        m1 = min(hi, m0 + markers_per_chunk)
         res = geno.mainMarkerInCPP(body[m0 * B0:m1 * B0], n_fam, m1 - m0, min_MAF, min_MAC, max_missing, se_two_sided)
         for j in range(m1 - m0):
             r = res[j]

@@ -17,6 +17,7 @@ M = dict(mu=mu, res=res, mu2=mu2, tau=np.array([1.0, 0.3]), trait="binary", y=y,
 g = SaigeB200()
 g.setSAIGEobjInCPP(M, 0.95, 2.0, np.arange(N, dtype=np.int32))
 g.mainMarkerInCPP(bed[: ((N + 3) // 4) * 256], N, 256)
+g.mainMarkerInCPP(bed, N, nm)          # sizes the pinned staging buffers
 t = time.time(); out = g.mainMarkerInCPP(bed, N, nm); dt = time.time() - t
 print("N=%d variants=%d : %.3f s -> %.0f variants/s (%.1f GB/s of genotype bytes), SPA-adjusted %d, tested %d"
       % (N, nm, dt, nm / dt, bed.nbytes / dt / 1e9, int(out[:, 10].sum()), int(out[:, 0].sum())))
