@@ -167,12 +167,33 @@ int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
 
+/* ---- dense N x N GRM (BASELINE config 4) ---------------------------------------------------- */
+/* The reference fork ships no code for this step (docs/overview.md:19-21 describe a "full GRM" option of SAIGE-GPU; the
+ * GCTA-style files extdata/output/nfam_*_GRM.grm.bin give the output format).  K_ij = (1/M) sum_m z_mi z_mj with the same
+ * standardisation as getCrossprodMatAndKin (FG.cpp:1445-1502), built on the tcgen05 int8 tensor cores from the 2-bit
+ * store: weights s_m^2 as `weight_limbs` (2..8) base-128 digits, exact int32 accumulation, fp64 storage of the lower
+ * block-trapezoid sharded by 128-sample block-rows across ranks (collective call when created with sgb_create_dist).
+ * weight_limbs = 7 keeps the stored matrix within ~1e-13 of fp64 arithmetic; the build costs weight_limbs passes. */
+int sgb_dense_grm_build(sgb_ctx *h, int weight_limbs);
+int sgb_dense_grm_free(sgb_ctx *h);
+/* out[ni x nj] column-major = K[i0 .. i0+ni) [j0 .. j0+nj)  (collective when distributed) */
+int sgb_dense_grm_get_block(sgb_ctx *h, int64_t i0, int64_t ni, int64_t j0, int64_t nj, double *out);
+/* out6 = {weight_limbs, fixed-point exponent S, block-rows, stored bytes on this rank, build ms, int8 ops issued} */
+int sgb_dense_grm_info(sgb_ctx *h, double *out6);
+/* Which GRM getCrossprodMatAndKin / PCG / AI-REML use: the packed genotypes (default) or the stored dense matrix
+ * ("PCG on stored GRM"; no LOCO in that mode). */
+enum { SGB_GRM_PACKED = 0, SGB_GRM_DENSE = 1 };
+int sgb_set_grm_mode(sgb_ctx *h, int mode);
+
 /* ---- device-resident benchmark hooks (bench.py `value` leg: inputs already in HBM) ---------------- */
 /* Runs `reps` k-column GRM products on device-resident synthetic right-hand sides, timing with CUDA events
  * on the library's stream; ms_out[reps] per-product times, and ms_kernel_out[2*reps] (may be NULL) the device time of
  * the two genotype sweeps {sweep 1, sweep 2} of each product.  Result left in an internal buffer (sgb_bench_fetch_result). */
 int sgb_bench_crossprod_device(sgb_ctx *h, int k, int reps, uint64_t seed, float *ms_out, float *ms_kernel_out);
 int sgb_bench_fetch_result(sgb_ctx *h, int k, double *Y, double *B);
+/* Builds only block-rows [first_block_row, first_block_row + n_block_rows) of the dense GRM (a bounded sample of the
+ * build for bench.py; sgb_dense_grm_info reports time and operations). */
+int sgb_bench_dense_build(sgb_ctx *h, int weight_limbs, int64_t first_block_row, int64_t n_block_rows);
 
 /* ---- counters (SURVEY.md section 5 "metrics") ----------------------------------------------------- */
 typedef struct {

@@ -86,6 +86,12 @@ _SIGS = {
     "sgb_step2_test_markers": (C.c_int, [P, P, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, DP]),
     "sgb_bench_crossprod_device": (C.c_int, [P, C.c_int, C.c_int, C.c_uint64, P, P]),
     "sgb_bench_fetch_result": (C.c_int, [P, C.c_int, DP, DP]),
+    "sgb_dense_grm_build": (C.c_int, [P, C.c_int]),
+    "sgb_dense_grm_free": (C.c_int, [P]),
+    "sgb_dense_grm_get_block": (C.c_int, [P, I64, I64, I64, I64, DP]),
+    "sgb_dense_grm_info": (C.c_int, [P, DP]),
+    "sgb_set_grm_mode": (C.c_int, [P, C.c_int]),
+    "sgb_bench_dense_build": (C.c_int, [P, C.c_int, I64, I64]),
     "sgb_get_counters": (C.c_int, [P, C.POINTER(Counters)]),
     "sgb_reset_counters": (C.c_int, [P]),
 }

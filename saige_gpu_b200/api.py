@@ -365,6 +365,52 @@ class SaigeB200:
                                                 float(max_missing), int(bool(se_two_sided)), _p(out)))
         return out
 
+    # ---- dense N x N GRM (BASELINE config 4): tcgen05 build, stored-GRM products ----
+    def buildDenseGRM(self, weight_limbs=7):
+        """K = Z Z^T / M on the tensor cores from the loaded 2-bit store (collective when distributed)."""
+        self._ck(self._L.sgb_dense_grm_build(self._h, int(weight_limbs)))
+        return self.denseGRMInfo()
+
+    def freeDenseGRM(self):
+        self._ck(self._L.sgb_dense_grm_free(self._h))
+
+    def denseGRMInfo(self):
+        o = np.zeros(6)
+        self._ck(self._L.sgb_dense_grm_info(self._h, _p(o)))
+        return {"weight_limbs": int(o[0]), "fixed_point_exponent": int(o[1]), "block_rows": int(o[2]),
+                "stored_bytes": float(o[3]), "build_ms": float(o[4]), "int8_ops": float(o[5])}
+
+    def getDenseGRMBlock(self, i0, ni, j0, nj):
+        out = np.zeros((ni, nj), order="F")
+        self._ck(self._L.sgb_dense_grm_get_block(self._h, int(i0), int(ni), int(j0), int(nj), _p(out)))
+        return out
+
+    def setGRMMode(self, mode):
+        """'packed' (default: products from the 2-bit genotypes) or 'dense' (products / PCG from the stored matrix)."""
+        self._ck(self._L.sgb_set_grm_mode(self._h, {"packed": 0, "dense": 1}[mode]))
+
+    def writeDenseGRM(self, prefix, sample_ids=None, rows_per_read=2048):
+        """GCTA-style <prefix>.grm.bin / .grm.N.bin / .grm.id (fp32 lower triangle incl. diagonal, row by row), the
+        format of the reference's extdata/output/nfam_*_GRM.grm.bin."""
+        N = self.N
+        M = self.M
+        with open(prefix + ".grm.bin", "wb") as fb, open(prefix + ".grm.N.bin", "wb") as fn:
+            for i0 in range(0, N, rows_per_read):
+                ni = min(rows_per_read, N - i0)
+                blk = self.getDenseGRMBlock(i0, ni, 0, i0 + ni)
+                for a in range(ni):
+                    row = blk[a, :i0 + a + 1].astype(np.float32)
+                    fb.write(row.tobytes())
+                    fn.write(np.full(row.size, M, dtype=np.float32).tobytes())
+        with open(prefix + ".grm.id", "w") as f:
+            for i in range(N):
+                sid = sample_ids[i] if sample_ids is not None else str(i + 1)
+                f.write("%s\t%s\n" % (sid, sid))
+
+    def bench_dense_build(self, weight_limbs, first_block_row, n_block_rows):
+        self._ck(self._L.sgb_bench_dense_build(self._h, int(weight_limbs), int(first_block_row), int(n_block_rows)))
+        return self.denseGRMInfo()
+
     # ---- bench hooks / counters ----
     def bench_crossprod_device(self, k, reps, seed=1):
         ms = np.zeros(reps, dtype=np.float32)

@@ -15,6 +15,7 @@ struct nccl_api {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -35,8 +36,9 @@ static int load_nccl(std::string &err)
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(lib, "ncclBroadcast");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.GetErrorString) {
         err = "libnccl.so.2 lacks a required symbol";
         return 1;
     }
@@ -85,5 +87,15 @@ int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n)
     ncclResult_t r = g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, h->dist->comm, h->stream);
     if (r != ncclSuccess) return sgb_fail(h, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
     h->cnt.n_allreduce++;
+    return 0;
+}
+
+// in-place broadcast of a device buffer from `root` (dense-GRM build: every rank needs every marker shard)
+int sgb_broadcast_bytes(sgb_ctx *h, void *d, size_t bytes, int root)
+{
+    if (h->world <= 1) return 0;
+    if (!h->dist || !h->dist->comm) return sgb_fail(h, "broadcast requested but NCCL communicator is not initialised");
+    ncclResult_t r = g_nccl.Broadcast(d, d, bytes, ncclUint8, root, h->dist->comm, h->stream);
+    if (r != ncclSuccess) return sgb_fail(h, "ncclBroadcast: %s", g_nccl.GetErrorString(r));
     return 0;
 }

@@ -13,6 +13,7 @@
 
 struct sgb_dist;             // NCCL state (dist.cu)
 struct sgb_step2;            // step-2 model state (step2.cu)
+struct sgb_dense;            // stored dense GRM (dense_grm.cu)
 
 struct sgb_ctx {
     int device = 0;
@@ -77,6 +78,8 @@ struct sgb_ctx {
     sgb_dist *dist = nullptr;
     int rank = 0, world = 1;
     sgb_step2 *step2 = nullptr;
+    sgb_dense *dense = nullptr;
+    int grm_mode = SGB_GRM_PACKED;                    // which GRM the products / PCG use
 
     sgb_counters cnt = {};
 };
@@ -171,3 +174,6 @@ int sgb_dist_init(sgb_ctx *h, int rank, int world, const void *id128);
 void sgb_dist_destroy(sgb_ctx *h);
 int sgb_dist_unique_id(void *id128, std::string &err);
 void sgb_step2_free(sgb_ctx *h);
+void sgb_dense_free(sgb_ctx *h);
+int sgb_dense_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY);
+int sgb_broadcast_bytes(sgb_ctx *h, void *d, size_t bytes, int root);

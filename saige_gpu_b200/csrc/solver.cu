@@ -44,6 +44,10 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
 {
     NEED_LOADED(h);
     if (k < 1 || k > 1024) return sgb_fail(h, "crossprod: k=%d out of range", k);
+    if (h->grm_mode == SGB_GRM_DENSE) {
+        if (loco) return sgb_fail(h, "LOCO products are not available from the stored dense GRM (use the packed-genotype mode)");
+        return sgb_dense_crossprod_device(h, dB, k, dY);
+    }
     const int64_t N = h->N, rowsG = h->rowsG, rowsT = h->rowsT;
     int64_t lo = 0, hi = 0;
     double mdiv = (double)h->M;

@@ -103,6 +103,7 @@ extern "C" int sgb_nccl_unique_id(void *id128)
 static void free_store(sgb_ctx *h)
 {
     cudaSetDevice(h->device);
+    sgb_dense_free(h);          // a stored GRM belongs to the genotypes it was built from
     void **ptrs[] = {(void **)&h->dG, (void **)&h->dGt, (void **)&h->d_f2, (void **)&h->d_s, (void **)&h->d_s2,
                      (void **)&h->d_diag, (void **)&h->d_diag_loco};
     for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
