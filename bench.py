@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--workload", default="c3_200kx500k", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default="tensor", choices=["tensor", "f64"])
     ap.add_argument("--k-batch", type=int, default=31, help="width of the extra batched-product measurement")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-GRM build sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step1", action="store_true", help="skip the step-1 wall-time extra")
     args = ap.parse_args()
@@ -360,6 +361,30 @@ def main():
                       "note": "binary trait, 3 fixed-effect columns, nrun=30 probes, tolPCG=1e-5, full GRM, "
                               "22 leave-one-chromosome-out refits included; genotypes already resident (load_synth_s apart)"}
 
+    dense_info = None
+    if not args.no_dense and N < (1 << 18):
+        # BASELINE config 4 row: a bounded sample of the dense-GRM build (the last 8 block-rows per rank, i.e. full-height
+        # panels) on the tcgen05 int8 path, against 2 x the measured dense bf16 rate (int8 runs at twice bf16)
+        nbr = (N + 127) // 128
+        nsample = min(nbr, 8 * world)
+        barrier()
+        info = g.bench_dense_build(7, nbr - nsample, nsample)
+        dms = max_over_ranks(float(info["build_ms"]))
+        dops = float(info["int8_ops"]) * world
+        g.freeDenseGRM()
+        tpeak, tsrc = 2 * 2250.0, "nominal (2 x 2.25 PFLOP/s bf16)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = 2 * float(mp["bf16_tflops"]), "2 x measured dense bf16 burst (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+        dense_info = {"kernel": "pk2_umma_kernel (tcgen05 kind::i8, M=128 N=128 K=32)", "weight_limbs": 7,
+                      "sample": "last %d of %d block-rows (128 samples each) x %d markers" % (nsample, nbr, M),
+                      "ms": dms, "int8_tops": dops / (dms * 1e-3) / 1e12,
+                      "roofline": {"bound": "tensor", "achieved": dops / (dms * 1e-3) / 1e12, "peak": tpeak, "unit": "TOP/s",
+                                   "frac": dops / (dms * 1e-3) / 1e12 / tpeak, "peak_source": tsrc},
+                      "full_build_estimate_s": 7 * 2.0 * M * 128 * 128 * nbr * (nbr + 1) / 2 / (dops / (dms * 1e-3))}
+
     if rank == 0:
         line = {
             "metric": "grm_matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -382,6 +407,7 @@ def main():
             "cpu_baseline": cb,
             "ingest": ingest_info,
             "step1": step1_info,
+            "dense_grm": dense_info,
         }
         print(json.dumps(line))
     g.close()

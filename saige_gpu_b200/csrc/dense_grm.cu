@@ -38,7 +38,7 @@ struct sgb_dense {
     std::vector<int64_t> off;              // element offset of block-row R in `pool`, -1 if another rank owns it
     double *pool = nullptr; size_t pool_elems = 0;
     double *dU = nullptr;                  // U'_i as DG_UPIECES exact integer pieces [piece][N]
-    dg_item *d_items = nullptr; int64_t n_items = 0;
+    dg_item *d_items = nullptr; int64_t n_items = 0, n_items_b = 0;   // n_items_b mirrored chunks first, then the diagonal blocks
     double build_ms = 0.0;
     bool partial = false;                  // bench sample: not all block-rows were built
     double tensor_ops = 0.0;               // int8 multiply-adds x 2 issued by the build
@@ -170,8 +170,9 @@ __global__ void syrk_u_kernel(const double *__restrict__ raw, int64_t N, const d
 // y += K b from the stored trapezoid.  One CTA per (block-row, 512-row chunk of its panel):
 //   part A   y[128R + n] += sum_i panel[i][n] b[i]                    (rows of the block-row)
 //   part B   y[i]        += sum_n panel[i][n] b[128R + n]   (i < 128R) (the mirrored upper triangle)
-// A warp streams 8 panel rows at a time (lane = 4 consecutive n, one 32-byte load per row), keeps the part-A sums in
-// registers and reduces the part-B partials with a shuffle butterfly (9 shuffles per 8 rows).
+// A warp streams 4 panel rows at a time (lane = 4 consecutive n, one 32-byte load per row, the next group prefetched
+// into a second register buffer), keeps the part-A sums of KC columns in registers and reduces the part-B partials with
+// a shuffle butterfly (6 shuffles per 4 rows and column).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double4 ldg_f64x4(const double *p)
 {
@@ -180,81 +181,125 @@ __device__ __forceinline__ double4 ldg_f64x4(const double *p)
     return r;
 }
 
-template <int KC>
-__global__ void __launch_bounds__(256) dense_symv_kernel(const double *__restrict__ pool, const dg_item *__restrict__ items,
-                                                         const double *__restrict__ B, int64_t N, int c0, double *__restrict__ Y)
+// one group = 4 panel rows: part-A accumulation and the part-B sums of KC columns.  ib = the 4 row indices clamped to
+// N - 1 (rows beyond N hold zeros, so the value read there is irrelevant).
+template <int KC, bool PARTB>
+__device__ __forceinline__ void symv_group(const double4 (&kv)[4], const double *__restrict__ B, int64_t N, int64_t ib0, int64_t ib1,
+                                           int64_t ib2, int64_t ib3, const double (*sbn)[DG_BLOCK], int lane, double (&accA)[KC][4],
+                                           double (*sB)[DG_CHUNK], int lrow)
 {
-    __shared__ double red[8][KC][DG_BLOCK];
-    const dg_item it = items[blockIdx.x];
+#pragma unroll
+    for (int c = 0; c < KC; c++) {
+        const double *Bc = B + (int64_t)c * N;
+        const double b0 = __ldg(Bc + ib0), b1 = __ldg(Bc + ib1), b2 = __ldg(Bc + ib2), b3 = __ldg(Bc + ib3);
+        accA[c][0] += kv[0].x * b0; accA[c][1] += kv[0].y * b0; accA[c][2] += kv[0].z * b0; accA[c][3] += kv[0].w * b0;
+        accA[c][0] += kv[1].x * b1; accA[c][1] += kv[1].y * b1; accA[c][2] += kv[1].z * b1; accA[c][3] += kv[1].w * b1;
+        accA[c][0] += kv[2].x * b2; accA[c][1] += kv[2].y * b2; accA[c][2] += kv[2].z * b2; accA[c][3] += kv[2].w * b2;
+        accA[c][0] += kv[3].x * b3; accA[c][1] += kv[3].y * b3; accA[c][2] += kv[3].z * b3; accA[c][3] += kv[3].w * b3;
+        if (PARTB) {
+            const double4 bn = *reinterpret_cast<const double4 *>(&sbn[c][4 * lane]);
+            double pr[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) pr[r] = kv[r].x * bn.x + kv[r].y * bn.y + kv[r].z * bn.z + kv[r].w * bn.w;
+            // butterfly: 4 row partials over 32 lanes -> the lanes with (lane & 7) == 0 end with the full sum of row (lane >> 3)
+            const bool up16 = lane & 16, up8 = lane & 8;
+            const double s0 = up16 ? pr[0] : pr[2], k0 = up16 ? pr[2] : pr[0];
+            const double s1 = up16 ? pr[1] : pr[3], k1 = up16 ? pr[3] : pr[1];
+            const double q0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+            const double q1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            const double s2 = up8 ? q0 : q1, k2 = up8 ? q1 : q0;
+            double q = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
+            q += __shfl_xor_sync(0xffffffffu, q, 4);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            if ((lane & 7) == 0) sB[c][lrow + (lane >> 3)] = q;          // every chunk row belongs to exactly one warp and group
+        }
+    }
+}
+
+template <int KC, bool PARTB>
+__global__ void __launch_bounds__(256, (KC <= 2 ? 2 : 1))
+dense_symv_kernel(const double *__restrict__ pool, const dg_item *__restrict__ items, int64_t item0, const double *__restrict__ B, int64_t N,
+                  double *__restrict__ Y)
+{
+    __shared__ __align__(32) double sbn[KC][DG_BLOCK];     // b over the block-row's own samples; later the part-A sums
+    __shared__ double sB[PARTB ? KC : 1][DG_CHUNK];        // part-B sums of the chunk rows (flushed with coalesced atomics)
+    const dg_item it = items[item0 + blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double *panel = pool + it.off;
-    const int64_t jrow = (int64_t)it.R * DG_BLOCK + 4 * lane;
-    double bn[KC][4], accA[KC][4];
+    for (int e = threadIdx.x; e < KC * DG_BLOCK; e += 256) {
+        const int c = e / DG_BLOCK, n = e % DG_BLOCK;
+        const int64_t j = (int64_t)it.R * DG_BLOCK + n;
+        sbn[c][n] = j < N ? B[(int64_t)c * N + j] : 0.0;
+    }
+    __syncthreads();
+    double accA[KC][4];
 #pragma unroll
     for (int c = 0; c < KC; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            bn[c][j] = (jrow + j < N) ? B[(int64_t)(c0 + c) * N + jrow + j] : 0.0;
-            accA[c][j] = 0.0;
-        }
-    const int rows_per_warp = DG_CHUNK / 8;
-    const int r_begin = warp * rows_per_warp;
-    for (int g = r_begin; g < r_begin + rows_per_warp && g < it.rows; g += 8) {
-        double4 kv[8];
+        for (int j = 0; j < 4; j++) accA[c][j] = 0.0;
+    // it.rows is a multiple of 128 and a warp owns 64 consecutive chunk rows: all or nothing
+    const int g0 = warp * (DG_CHUNK / 8);
+    if (g0 < it.rows) {
+        const double *src = panel + ((int64_t)it.i0 + g0) * DG_BLOCK + 4 * lane;
+        const int64_t ibase = (int64_t)it.i0 + g0, last = N - 1;
+        double4 bufA[4], bufB[4];
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int64_t i = (int64_t)it.i0 + g + r;
-            kv[r] = (g + r < it.rows) ? ldg_f64x4(panel + i * DG_BLOCK + 4 * lane) : make_double4(0, 0, 0, 0);
-        }
+        for (int r = 0; r < 4; r++) bufA[r] = ldg_f64x4(src + (int64_t)r * DG_BLOCK);
+        // groups of 4 rows, double buffered in registers: the next group's loads are in flight while this one is consumed
+#pragma unroll 1
+        for (int g = 0; g < DG_CHUNK / 8; g += 8) {
 #pragma unroll
-        for (int c = 0; c < KC; c++) {
-            double pr[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int64_t i = (int64_t)it.i0 + g + r;
-                const double bi = (g + r < it.rows && i < N) ? __ldg(B + (int64_t)(c0 + c) * N + i) : 0.0;
-                accA[c][0] += kv[r].x * bi; accA[c][1] += kv[r].y * bi; accA[c][2] += kv[r].z * bi; accA[c][3] += kv[r].w * bi;
-                pr[r] = kv[r].x * bn[c][0] + kv[r].y * bn[c][1] + kv[r].z * bn[c][2] + kv[r].w * bn[c][3];
+            for (int r = 0; r < 4; r++) bufB[r] = ldg_f64x4(src + (int64_t)(g + 4 + r) * DG_BLOCK);
+            {
+                const int64_t i = ibase + g;
+                symv_group<KC, PARTB>(bufA, B, N, min(i, last), min(i + 1, last), min(i + 2, last), min(i + 3, last), sbn, lane, accA, sB, g0 + g);
             }
-            if (it.partB) {
-                // butterfly: 8 row partials over 32 lanes -> lane holds the full sum of row ((lane >> 2) & 7) after 3 halvings
-                const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
-                double q4[4], q2[2], q1;
+            if (g + 8 < DG_CHUNK / 8) {
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    double send = up16 ? pr[r] : pr[r + 4], keep = up16 ? pr[r + 4] : pr[r];
-                    q4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    double send = up8 ? q4[r] : q4[r + 2], keep = up8 ? q4[r + 2] : q4[r];
-                    q2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-                {
-                    double send = up4 ? q2[0] : q2[1], keep = up4 ? q2[1] : q2[0];
-                    q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-                q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-                q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-                const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                const int64_t i = (int64_t)it.i0 + g + rsel;
-                if ((lane & 3) == 0 && g + rsel < it.rows && i < N) atomicAdd(Y + (int64_t)(c0 + c) * N + i, q1);
+                for (int r = 0; r < 4; r++) bufA[r] = ldg_f64x4(src + (int64_t)(g + 8 + r) * DG_BLOCK);
+            }
+            {
+                const int64_t i = ibase + g + 4;
+                symv_group<KC, PARTB>(bufB, B, N, min(i, last), min(i + 1, last), min(i + 2, last), min(i + 3, last), sbn, lane, accA, sB, g0 + g + 4);
             }
         }
     }
+    // part-A sums of the 8 warps meet in shared memory (sbn is free now)
+    double (*red)[DG_BLOCK] = sbn;
+    __syncthreads();
+    for (int e = threadIdx.x; e < KC * DG_BLOCK; e += 256) red[e / DG_BLOCK][e % DG_BLOCK] = 0.0;
+    __syncthreads();
+    if (g0 < it.rows) {
 #pragma unroll
-    for (int c = 0; c < KC; c++)
+        for (int c = 0; c < KC; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) red[warp][c][4 * lane + j] = accA[c][j];
+            for (int j = 0; j < 4; j++) atomicAdd(&red[c][4 * lane + j], accA[c][j]);
+    }
     __syncthreads();
     for (int e = threadIdx.x; e < KC * DG_BLOCK; e += 256) {
         const int c = e / DG_BLOCK, n = e % DG_BLOCK;
-        double s = 0.0;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; w8++) s += red[w8][c][n];
         const int64_t j = (int64_t)it.R * DG_BLOCK + n;
-        if (j < N && s != 0.0) atomicAdd(Y + (int64_t)(c0 + c) * N + j, s);
+        const double v = red[c][n];
+        if (j < N && v != 0.0) atomicAdd(Y + (int64_t)c * N + j, v);
     }
+    if (PARTB)
+        for (int e = threadIdx.x; e < KC * DG_CHUNK; e += 256) {
+            const int c = e / DG_CHUNK, r = e % DG_CHUNK;
+            const int64_t i = (int64_t)it.i0 + r;
+            if (r < it.rows && i < N) atomicAdd(Y + (int64_t)c * N + i, sB[c][r]);
+        }
+}
+
+template <int KC>
+static void symv_launch(sgb_ctx *h, const sgb_dense *d, const double *B, int64_t N, double *Y)
+{
+    // items are ordered [mirrored chunks (part A + B) ..., diagonal blocks (part A only)]
+    if (d->n_items_b)
+        dense_symv_kernel<KC, true><<<(unsigned)d->n_items_b, 256, 0, h->stream>>>(d->pool, d->d_items, 0, B, N, Y);
+    if (d->n_items > d->n_items_b)
+        dense_symv_kernel<KC, false><<<(unsigned)(d->n_items - d->n_items_b), 256, 0, h->stream>>>(d->pool, d->d_items, d->n_items_b, B, N, Y);
+    h->cnt.n_kernel_launches += 2;
 }
 
 // out[a + b*ni] = K[i0+a][j0+b] if this rank stores it, else 0
@@ -379,7 +424,7 @@ static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n
     // ---- storage of the block-rows this rank owns ----
     d->off.assign((size_t)d->nbr, -1);
     size_t elems = 0;
-    std::vector<dg_item> items;
+    std::vector<dg_item> items, diag_items;
     for (int64_t R = br0; R < nbr_build; R++) {
         if (R % h->world != h->rank) continue;
         d->off[(size_t)R] = (int64_t)elems;
@@ -392,9 +437,11 @@ static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n
         }
         dg_item dgi;
         dgi.off = (int64_t)elems; dgi.R = (int32_t)R; dgi.i0 = (int32_t)(DG_BLOCK * R); dgi.rows = DG_BLOCK; dgi.partB = 0;
-        items.push_back(dgi);
+        diag_items.push_back(dgi);
         elems += (size_t)rows * DG_BLOCK;
     }
+    d->n_items_b = (int64_t)items.size();
+    items.insert(items.end(), diag_items.begin(), diag_items.end());
     d->pool_elems = elems;
     if (elems) {
         cudaError_t e = cudaMalloc((void **)&d->pool, sizeof(double) * elems);
@@ -478,10 +525,14 @@ int sgb_dense_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY)
         int c = 0;
         while (c < k) {
             const int left = k - c;
-            if (left >= 4) { dense_symv_kernel<4><<<(unsigned)d->n_items, 256, 0, h->stream>>>(d->pool, d->d_items, dB, N, c, acc); c += 4; }
-            else if (left >= 2) { dense_symv_kernel<2><<<(unsigned)d->n_items, 256, 0, h->stream>>>(d->pool, d->d_items, dB, N, c, acc); c += 2; }
-            else { dense_symv_kernel<1><<<(unsigned)d->n_items, 256, 0, h->stream>>>(d->pool, d->d_items, dB, N, c, acc); c += 1; }
-            DG_LAUNCH_CHECK(h);
+            const double *Bc = dB + (int64_t)c * N;
+            double *Yc = acc + (int64_t)c * N;
+            if (left >= 8) { symv_launch<8>(h, d, Bc, N, Yc); c += 8; }
+            else if (left >= 4) { symv_launch<4>(h, d, Bc, N, Yc); c += 4; }
+            else if (left >= 2) { symv_launch<2>(h, d, Bc, N, Yc); c += 2; }
+            else { symv_launch<1>(h, d, Bc, N, Yc); c += 1; }
+            cudaError_t e__ = cudaGetLastError();
+            if (e__ != cudaSuccess) return sgb_fail(h, "stored-GRM product launch failed: %s", cudaGetErrorString(e__));
         }
     }
     if (h->world > 1) SGB_TRY(sgb_allreduce_sum(h, acc, N * k));

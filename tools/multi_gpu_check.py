@@ -51,8 +51,23 @@ probes = step1.ProbeStream(N0, 130, 200)
 mo = O.glmmkin_ai_PCG(o, O.glm_fit(y, Xc, O.Binomial), (0, 0), probes.U, trait="binary")
 mg = step1.glmmkin_ai_PCG(g, step1.glm_fit(y, Xc, step1.Binomial), probes, trait="binary")
 res["tau"] = rel(mg["theta"], mo["theta"]); res["alpha"] = rel(mg["coefficients"], mo["coefficients"])
-worst_mv = max(v for k, v in res.items() if k not in ("pcg", "tau", "alpha"))
-ok = worst_mv < 1e-10 and res["pcg"] < 1e-6 and res["tau"] < 1e-6 and res["alpha"] < 1e-6
+# dense GRM: block-rows dealt over the ranks, every rank contracts over all marker shards (ncclBroadcast), products
+# from the stored matrix end in the same allreduce
+Z = np.stack([o.Get_OneSNP_StdGeno(m) for m in range(o.M)], axis=1)
+Kor = Z @ Z.T / o.M
+info = g.buildDenseGRM()
+res["denseK"] = rel(g.getDenseGRMBlock(0, N0, 0, N0), Kor)
+res["denseK_window"] = rel(g.getDenseGRMBlock(100, 300, 250, 500), Kor[100:400, 250:750])
+g.setGRMMode("dense")
+res["dense_product"] = rel(g.getCrossprodMatAndKin(B), Kor @ B)
+Xd, itd = g.getPCG1ofSigmaAndVector(w, tau, B, 500, 1e-5, return_iter=True)
+g.setGRMMode("packed")
+assert list(itd) == list(ito)
+res["dense_pcg"] = rel(Xd, Xo)
+assert info["stored_bytes"] < 8 * 128 * 128 * 8 * 9 / 2 / world * 1.6, info
+pcg_keys = ("pcg", "tau", "alpha", "dense_pcg")
+worst_mv = max(v for k, v in res.items() if k not in pcg_keys)
+ok = worst_mv < 1e-10 and res["dense_pcg"] < 1e-6 and res["pcg"] < 1e-6 and res["tau"] < 1e-6 and res["alpha"] < 1e-6
 print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e tau %.2e alpha %.2e allreduces %d -> %s"
       % (rank, world, g.Mloc, worst_mv, res["pcg"], res["tau"], res["alpha"], g.counters()["n_allreduce"], "OK" if ok else "FAIL"), flush=True)
 g.close(); dist.destroy_process_group()
