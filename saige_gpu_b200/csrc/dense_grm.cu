@@ -482,7 +482,9 @@ static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n
                 const int64_t nblk = s.sT / 32;
                 syrk_image_kernel<<<(unsigned)cdiv64(nblk * 1024, 256), 256, 0, h->stream>>>(s.gt, s.sT, DG_BLOCK * R, s.dig + (size_t)l * s.sT * 4, nblk, img);
                 h->cnt.n_kernel_launches++;
+                h->umma_accumulate = q > 0;            // shards after the first add to the int32 sums
                 rc = k_pk2_umma(h, s.gt, s.sT, rows, s.sT, img, 16, acc, SGB_PLANE_VALUE);
+                h->umma_accumulate = false;
                 d->tensor_ops += 2.0 * (double)rows * DG_BLOCK * (double)(s.sT * 4);
             }
             int64_t n = rows * DG_BLOCK;

@@ -13,6 +13,7 @@
 //     descriptor and the int32 accumulator in TMEM; tcgen05.commit -> mbarriers release the A stage and the B stage;
 //   * the epilogue reads the accumulator with tcgen05.ld and adds it to the global int32 limb sums.
 // Integer arithmetic is exact, so results are bit-identical to the mma.sync kernel (the k <= 2 path and cross-check).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -41,6 +42,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity));
+}
+
+// non-blocking test of an mbarrier phase (forward declared use below)
+__device__ __forceinline__ int mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return (int)ok;
+}
+
+__device__ __forceinline__ void mbar_wait2(uint64_t *bar, uint32_t parity, int spin)
+{
+    if (spin) { while (!mbar_test(bar, parity)) { } }
+    else mbar_wait(bar, parity);
 }
 
 __device__ __forceinline__ uint32_t prmt_u(uint32_t a, uint32_t b, uint32_t sel)
@@ -107,7 +128,7 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         : "memory");
 }
 
-#define UMMA_STAGES 2            // A (TMEM) pipeline depth: one stage per producer group
+#define UMMA_MAX_STAGES 3        // A (TMEM) pipeline depth: 2 stages of 64 columns, or 3 when the accumulator needs <= 64 columns
 #define UMMA_MAX_BSTAGES 16      // B (smem) ring depth is chosen at launch: as many 128 x N byte stages as fit ~96 KB
 #define UMMA_PF 3                // packed-row prefetch distance of the producer threads, in steps
 #define UMMA_PGROUPS 2           // producer groups of 4 warps; group g owns the k-steps s = g (mod UMMA_PGROUPS)
@@ -129,6 +150,55 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+
+// MMA issue loop, run by a WHOLE warp: every value in it is warp-uniform, so the compiler keeps descriptors, addresses
+// and barrier state on the uniform datapath, and one lane issues.  (A single thread running this loop needed ~12
+// dependent instructions per tcgen05.mma, the 63-cycle "floor" per MMA measured at small N, plus two integer divisions
+// per step for the ring indices.)  Ring indices and phases are counters, the 8 B descriptors of a step are the stage-0
+// descriptors plus one add.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
+    return leader != 0;
+}
+
+template <int STAGES>
+__device__ __forceinline__ void umma_issue_loop(int nsteps, int nb, int N, uint32_t smem_b0, uint32_t stage_bytes, uint32_t tmem_base,
+                                                uint32_t tmem_d, uint64_t *full_a, uint64_t *empty, uint64_t *full_b, uint64_t *empty_b,
+                                                uint64_t *done_bar, int lane, int skip_mma)
+{
+    // instruction descriptor: D=s32, A=u8 (K-major, TMEM), B=s8 (K-major), N, M=128
+    const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_ROWS >> 4) << 24);
+    const uint32_t half_bytes = stage_bytes >> 1, st16 = stage_bytes >> 4;
+    // K-major, no swizzle: core matrix = 8 n-rows x 16 k-bytes (128 B); LBO (next 16 k) = 128 B; SBO (next 8 n) = 1024 B; version bit 46
+    const uint32_t dhi = (uint32_t)(1024 >> 4) | (1u << 14);
+    uint32_t dlo[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) dlo[j] = (((smem_b0 + (j >> 2) * half_bytes + (j & 3) * 256) >> 4) & 0x3FFF) | ((uint32_t)(128 >> 4) << 16);
+    int st = 0, sbi = 0;
+    uint32_t pa = 0, pb = 0, boff = 0, ta = tmem_base;
+    for (int s = 0; s < nsteps; s++) {
+        mbar_wait(&full_b[sbi], pb);
+        mbar_wait(&full_a[st], pa);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (elect_one()) {
+            if (!skip_mma) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    umma_i8_ts(tmem_d, ta + j * 8, ((uint64_t)dhi << 32) | (uint64_t)(dlo[j] + boff), idesc, (s > 0 || j > 0) ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_b[sbi])) : "memory");
+        }
+        __syncwarp();
+        if (++st == STAGES) { st = 0; pa ^= 1; ta = tmem_base; } else ta += UMMA_A_COLS;
+        if (++sbi == nb) { sbi = 0; pb ^= 1; boff = 0; } else boff += st16;
+    }
+    if (lane == 0 && nsteps > 0)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done_bar)) : "memory");
+}
+
 // grid: x = k-chunks, y = 128-row tiles.  block: 192 threads.  dynamic smem: UMMA_STAGES * 128 * N bytes of B stages.
 //   P        packed rows (pair-ternary), `stride` bytes each (multiple of 64); rows padded to a multiple of 128
 //   L        limb operand as an image of the smem stage: [k-block of 128][N/8][k/16 (8)][n%8 (8)][k%16 (16)] int8
@@ -137,13 +207,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 //   producers : load 32 B of their row (prefetched UMMA_PF steps ahead) -> prmt decode -> tcgen05.st into A stage -> arrive full_a
 //   bulk warp : cp.async.bulk (TMA engine) of the next B stage image -> full_b (expect_tx)
 //   MMA warp  : wait full_a & full_b -> 4 x tcgen05.mma.kind::i8 (K = 32 each) -> tcgen05.commit -> empty (frees both stages)
+template <int UMMA_STAGES>
 __global__ void __launch_bounds__(UMMA_THREADS, 2)
 pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_total, int ksteps_per_chunk,
                 const int8_t *__restrict__ L, int N, int64_t Lblk_stride, int32_t *__restrict__ out, int ldo, int n0,
-                int use_atomic, umma_pools pool, int tmem_cols, int nb)
+                int use_atomic, umma_pools pool, int tmem_cols, int nb, int dbg)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t full_a[UMMA_STAGES], empty[UMMA_STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
+    __shared__ uint64_t full_a[UMMA_MAX_STAGES], empty[UMMA_MAX_STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -159,7 +230,7 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 32) {
-        for (int i = 0; i < UMMA_STAGES; i++) { mbar_init(&full_a[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < UMMA_STAGES; i++) { mbar_init(&full_a[i], 4); mbar_init(&empty[i], 1); }     // one arrive per producer warp
         for (int i = 0; i < nb; i++) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -176,6 +247,7 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
         const int64_t row = (int64_t)blockIdx.y * UMMA_ROWS + q4 * 32 + (tid & 31);
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;         // this warp's TMEM lane quarter
         const uint8_t *prow = P + row * stride + ks0 * 64;
+        const int l2_ahead = (dbg >> 8) ? (dbg >> 8) : 12;        // in k-steps of 64 bytes (even: whole lines)
         u32x8 pf[UMMA_PF][2];
 #pragma unroll
         for (int i = 0; i < UMMA_PF; i++) {
@@ -196,6 +268,7 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
                     asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) {
+                        if (dbg & 2) break;
                         uint32_t a[32];
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
@@ -207,13 +280,19 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
                         }
                         tmem_st_x32(tmem_base + lane_base + st * UMMA_A_COLS + hf * 32, a);
                     }
-                    if (s + UMMA_PF * UMMA_PGROUPS < nsteps) {
+                    if (s + UMMA_PF * UMMA_PGROUPS < nsteps && !(dbg & 4)) {
                         pf[j][0] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * 64);
                         pf[j][1] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * 64 + 32);
                     }
+                    // the register prefetch holds ~100 KB per SM in flight, not enough to cover DRAM latency at full rate:
+                    // group 0 also pulls the row's 128-byte line `l2_ahead` steps further on into L2 (one instruction)
+                    if (grp == 0 && s + l2_ahead < nsteps)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(s + l2_ahead) * 64));
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
-                    mbar_arrive(&full_a[st]);
+                    // 128 per-thread arrives on one mbarrier serialise (~470 cycles per step measured): one per warp instead
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&full_a[st]);
                 }
             }
         }
@@ -236,40 +315,196 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
             }
         }
     } else if (warp == UMMA_PWARPS) {
-        // ================= MMA issuer (one thread) =================
-        if (tid == 32 * UMMA_PWARPS) {
-            // instruction descriptor: D=s32, A=u8 (K-major, TMEM), B=s8 (K-major), N, M=128
-            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UMMA_ROWS >> 4) << 24);
-            for (int s = 0; s < nsteps; s++) {
-                const int st = s % UMMA_STAGES, u = s / UMMA_STAGES;
-                const int sbi = s % nb, ub = s / nb;
-                mbar_wait(&full_b[sbi], (uint32_t)(ub & 1));
-                mbar_wait(&full_a[st], (uint32_t)(u & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t sb = smem_u32(smem + sbi * stage_bytes);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    // K-major, no swizzle: core matrix = 8 n-rows x 16 k-bytes (128 B); LBO (next 16 k) = 128 B; SBO (next 8 n) = 1024 B
-                    const uint64_t desc = (uint64_t)(((sb + (j >> 2) * half_bytes + (j & 3) * 256) >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
-                                          ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
-                    umma_i8_ts(tmem_d, tmem_base + st * UMMA_A_COLS + j * 8, desc, idesc, (s > 0 || j > 0) ? 1u : 0u);
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_b[sbi])) : "memory");
-            }
-            if (nsteps > 0)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
-        }
+        // ================= MMA issuer warp =================
+        umma_issue_loop<UMMA_STAGES>(nsteps, nb, N, smem_u32(smem), stage_bytes, tmem_base, tmem_d, full_a, empty, full_b, empty_b, &done_bar,
+                                     tid & 31, dbg & 1);
     } else {
         // ================= B stage loader: one bulk copy (TMA engine) per step =================
         if (tid == 32 * (UMMA_PWARPS + 1)) {
+            int sbi = 0;
+            uint32_t pb = 1;                               // parity of the previous use of the stage
+            bool wrapped = false;
+            const int8_t *src = L + (2 * ks0) * Lblk_stride;
             for (int s = 0; s < nsteps; s++) {
-                const int sbi = s % nb, ub = s / nb;
-                if (ub > 0) mbar_wait(&empty_b[sbi], (uint32_t)((ub - 1) & 1));
-                mbar_expect_tx(&full_b[sbi], stage_bytes);
-                bulk_g2s(smem + sbi * stage_bytes, L + (2 * (ks0 + s)) * Lblk_stride, half_bytes, &full_b[sbi]);
-                bulk_g2s(smem + sbi * stage_bytes + half_bytes, L + (2 * (ks0 + s) + 1) * Lblk_stride, half_bytes, &full_b[sbi]);
+                if (wrapped) mbar_wait(&empty_b[sbi], pb);
+                if (dbg & 8) { mbar_arrive(&full_b[sbi]); }
+                else {
+                    mbar_expect_tx(&full_b[sbi], stage_bytes);
+                    bulk_g2s(smem + sbi * stage_bytes, src, half_bytes, &full_b[sbi]);
+                    bulk_g2s(smem + sbi * stage_bytes + half_bytes, src + Lblk_stride, half_bytes, &full_b[sbi]);
+                }
+                src += 2 * Lblk_stride;
+                if (++sbi == nb) { sbi = 0; pb ^= 1; wrapped = true; }
             }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Narrow batches (N <= 64, i.e. k <= 8 columns): the MMAs are short, so the kernel lives or dies by how many genotype
+// bytes are in flight.  Row-per-thread register prefetch tops out near 100 KB per SM (~4 TB/s measured); here the packed
+// rows are instead streamed by the TMA engine: ONE cp.async.bulk.tensor.2d per chunk moves a [128 rows x 128 bytes] box
+// into a 128B-swizzled shared-memory ring (conflict-free 128-bit reads with thread = row), tracked by one mbarrier per
+// chunk, which keeps up to 6 x 16 KB per CTA in flight without holding a single register.  (Per-row 1-D bulk copies of
+// 128 B were tried first: the TMA unit retires roughly one bulk operation per 38 cycles, 0.9 TB/s.)  Everything after
+// the shared-memory read is the pipeline of pk2_umma_kernel: prmt decode -> tcgen05.st -> tcgen05.mma -> tcgen05.ld.
+// ---------------------------------------------------------------------------------------------------
+#define UMMA_CH_BYTES 128                           // packed bytes per row and chunk = 2 k-steps
+#define UMMA_CH_SMEM (UMMA_ROWS * UMMA_CH_BYTES)    // 16384 B per chunk (128B swizzle: 16-byte unit j of row r sits at j ^ (r & 7))
+#define UMMA_MAX_CHUNKS 6
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(UMMA_THREADS, 2)
+pk2_umma_staged_kernel(const __grid_constant__ CUtensorMap tmap, int64_t ksteps_total, int ksteps_per_chunk,
+                       const int8_t *__restrict__ L, int N, int64_t Lblk_stride, int32_t *__restrict__ out, int ldo, int n0,
+                       int use_atomic, umma_pools pool, int tmem_cols, int nb, int nch)
+{
+    constexpr int STAGES = 3;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full_a[STAGES], empty[STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
+    __shared__ uint64_t full_c[UMMA_MAX_CHUNKS], empty_c[UMMA_MAX_CHUNKS];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ks0 = (int64_t)blockIdx.x * ksteps_per_chunk;
+    int64_t ks1 = ks0 + ksteps_per_chunk;
+    if (ks1 > ksteps_total) ks1 = ksteps_total;
+    const int nsteps = (int)(ks1 - ks0);
+    const uint32_t stage_bytes = (uint32_t)UMMA_KSTEP * (uint32_t)N;
+    const uint32_t half_bytes = stage_bytes / 2;
+    uint8_t *smem_b = smem;                                        // B ring: nb stages
+    uint8_t *smem_c = smem + (size_t)nb * stage_bytes;            // genotype chunk ring: nch chunks
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full_a[i], 4); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < nb; i++) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < nch; i++) { mbar_init(&full_c[i], 1); mbar_init(&empty_c[i], 4 * UMMA_PGROUPS); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_d = tmem_base + STAGES * UMMA_A_COLS;
+
+    if (warp < UMMA_PWARPS) {
+        // ================= producers: thread = row; group g owns the k-steps s = g (mod 2) =================
+        const int grp = warp >> 2, q4 = warp & 3;
+        const int r128 = q4 * 32 + lane;
+        const int64_t row = (int64_t)blockIdx.y * UMMA_ROWS + r128;
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        const uint32_t my_c = smem_u32(smem_c) + (uint32_t)r128 * UMMA_CH_BYTES;
+        const uint32_t sw = (uint32_t)(r128 & 7);                    // 128B swizzle phase of this row
+        for (int s = grp; s < nsteps; s += UMMA_PGROUPS) {
+            const int c = s >> 1, cs = c % nch, uc = c / nch;
+            const int st = s % STAGES, u = s / STAGES;
+            mbar_wait(&full_c[cs], (uint32_t)(uc & 1));
+            const uint32_t src = my_c + (uint32_t)cs * UMMA_CH_SMEM;
+            uint4 w4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) w4[i] = lds_u4(src + ((((uint32_t)grp * 4 + i) ^ sw) << 4));     // step parity = group
+            if (u > 0) mbar_wait(&empty[st], (uint32_t)((u - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t a[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint4 q = w4[2 * hf + (i >> 2)];
+                    const uint32_t wv = (i & 3) == 0 ? q.x : (i & 3) == 1 ? q.y : (i & 3) == 2 ? q.z : q.w, hi = wv >> 16;
+                    a[4 * i + 0] = prmt_u(pool.ax, pool.ay, wv);
+                    a[4 * i + 1] = prmt_u(pool.ax, pool.ay, hi);
+                    a[4 * i + 2] = prmt_u(pool.bx, pool.by, wv);
+                    a[4 * i + 3] = prmt_u(pool.bx, pool.by, hi);
+                }
+                tmem_st_x32(tmem_base + lane_base + st * UMMA_A_COLS + hf * 32, a);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_c[cs]);  // this warp's bytes of the chunk are in registers / TMEM
+            asm volatile("tcgen05.wait::st.sync.aligned;");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[st]);
+        }
+        if (nsteps > 0) {
+            mbar_wait(&done_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            int32_t *o = out + row * ldo + n0;
+            for (int c = grp * 16; c < N; c += 16 * UMMA_PGROUPS) {
+                int32_t v[16];
+                tmem_ld_x16(tmem_d + lane_base + c, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                if (use_atomic) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (v[i]) atomicAdd(o + c + i, v[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<int4 *>(o + c + i) = make_int4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+        }
+    } else if (warp == UMMA_PWARPS) {
+        // ================= MMA issuer warp =================
+        umma_issue_loop<STAGES>(nsteps, nb, N, smem_u32(smem_b), stage_bytes, tmem_base, tmem_d, full_a, empty, full_b, empty_b, &done_bar, lane, 0);
+    } else {
+        // ================= TMA warp: genotype chunks (all lanes, 4 rows each) and the B stages (lane 0) =================
+        // Both rings are refilled as soon as a slot frees up (non-blocking mbarrier tests), so a busy B ring never holds
+        // back the genotype stream.
+        const int nchunks = (nsteps + 1) >> 1;
+        int cA = 0, sB = 0;
+        while (cA < nchunks || sB < nsteps) {
+            int progressed = 0;
+            if (cA < nchunks) {
+                const int cs = cA % nch, uc = cA / nch;
+                int ok = 1;
+                if (lane == 0) {
+                    if (uc > 0) ok = mbar_test(&empty_c[cs], (uint32_t)((uc - 1) & 1));
+                    if (ok) {
+                        // a full chunk is released by both producer groups; a trailing half chunk only by group 0: it is never reused
+                        mbar_expect_tx(&full_c[cs], UMMA_CH_SMEM);
+                        tma_load_2d(smem_c + (size_t)cs * UMMA_CH_SMEM, &tmap, (int)((ks0 * 64 + (int64_t)cA * UMMA_CH_BYTES)),
+                                    (int)(blockIdx.y * UMMA_ROWS), &full_c[cs]);
+                    }
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) { cA++; progressed = 1; }
+            }
+            if (sB < nsteps) {
+                const int sbi = sB % nb, ub = sB / nb;
+                int ok = 1;
+                if (lane == 0) {
+                    if (ub > 0) ok = mbar_test(&empty_b[sbi], (uint32_t)((ub - 1) & 1));
+                    if (ok) {
+                        mbar_expect_tx(&full_b[sbi], stage_bytes);
+                        bulk_g2s(smem_b + sbi * stage_bytes, L + (2 * (ks0 + sB)) * Lblk_stride, half_bytes, &full_b[sbi]);
+                        bulk_g2s(smem_b + sbi * stage_bytes + half_bytes, L + (2 * (ks0 + sB) + 1) * Lblk_stride, half_bytes, &full_b[sbi]);
+                    }
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) { sB++; progressed = 1; }
+            }
+            if (!progressed) __nanosleep(128);        // both rings full: do not steal issue slots from the producers
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -373,6 +608,31 @@ int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int
     return 0;
 }
 
+// 2-D tensor map over packed rows [rows][stride bytes], box = 128 bytes x 128 rows, 128B swizzle (driver entry point
+// resolved through the runtime, so the library does not link libcuda)
+static int make_row_tensor_map(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows, CUtensorMap *out)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return sgb_fail(h, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)stride, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)stride};
+    const cuuint32_t box[2] = {UMMA_CH_BYTES, UMMA_ROWS};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)P, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sgb_fail(h, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
 // out[r][c*8+l] += ...   for all k columns, in passes of <= 16 columns (N <= 128)
 int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
                int32_t *out, int plane)
@@ -394,16 +654,30 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
     if (per < 8) per = 8;
     if (per > ksteps) per = ksteps;
     kchunks = cdiv64(ksteps, per);
-    const int use_atomic = 1;       // out is an accumulation buffer shared with other passes / chunks
+    // k-chunks of one row tile meet in `out` with atomics; a single chunk writes every element once (out was zeroed by
+    // the previous recombine), unless the caller accumulates several launches (dense-GRM build over marker shards)
+    const int use_atomic = (kchunks > 1 || h->umma_accumulate) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
+    }
+    static const int force_stages = getenv("SGB_UMMA_STAGES") ? atoi(getenv("SGB_UMMA_STAGES")) : 0;
+    static const int staged_env = getenv("SGB_UMMA_STAGED") ? atoi(getenv("SGB_UMMA_STAGED")) : -1;
+    static const int dbg = getenv("SGB_UMMA_DBG") ? atoi(getenv("SGB_UMMA_DBG")) : 0;      // timing experiments only (results wrong)
+    static bool attr2_set = false;
+    if (!attr2_set) {
+        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr2_set = true;
     }
     for (int c0 = 0; c0 < ncolpad; c0 += 16) {
         int nc = ncolpad - c0 < 16 ? ncolpad - c0 : 16;      // columns this pass (even)
         int N = nc * 8;
-        int tmem_cols = UMMA_STAGES * UMMA_A_COLS + N <= 256 ? 256 : 512;
+        // three A stages let the producers run a full step ahead of the MMAs; they fit 256 TMEM columns (2 CTAs per SM) for N <= 64
+        int stages = (N <= 64) ? 3 : 2;
+        if (force_stages == 2 || force_stages == 3) stages = force_stages;
+        int tmem_cols = stages * UMMA_A_COLS + N <= 256 ? 256 : 512;
         int nb = (96 * 1024) / (UMMA_KSTEP * N);                // B ring depth (stages of 256 x N bytes)
         if (nb > UMMA_MAX_BSTAGES) nb = UMMA_MAX_BSTAGES;
         if (nb < 2) nb = 2;
@@ -412,9 +686,25 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
         for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {
             int64_t ny = row_tiles - y0 < 65535 ? row_tiles - y0 : 65535;
             dim3 grid((unsigned)kchunks, (unsigned)ny);
-            pk2_umma_kernel<<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
+            const bool staged = staged_env > 0 && N <= 64;      // experimental TMA-staged producers: measured slower
+            if (staged) {
+                // shared memory: 2 B stages + as many 18 KB genotype chunks as fit 110 KB (2 CTAs per SM)
+                const int nb2 = 2;
+                int nch = (int)((110 * 1024 - (size_t)nb2 * UMMA_KSTEP * N) / UMMA_CH_SMEM);
+                if (nch > UMMA_MAX_CHUNKS) nch = UMMA_MAX_CHUNKS;
+                CUtensorMap tmap;
+                SGB_TRY(make_row_tensor_map(h, P + y0 * UMMA_ROWS * stride, stride, ny * UMMA_ROWS, &tmap));
+                pk2_umma_staged_kernel<<<grid, UMMA_THREADS, (size_t)nb2 * UMMA_KSTEP * N + (size_t)nch * UMMA_CH_SMEM, h->stream>>>(
+                    tmap, ksteps, (int)per, Lp, N, (int64_t)ncolpad * 1024,
+                    out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8), ncolpad * 8, c0 * 8, use_atomic, pool, 256, nb2, nch);
+            } else if (stages == 3)
+                pk2_umma_kernel<3><<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
                                                                            (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
-                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb);
+                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
+            else
+                pk2_umma_kernel<2><<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
+                                                                           (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
+                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
             UMMA_LAUNCH_CHECK(h);
         }
     }

@@ -79,6 +79,7 @@ struct sgb_ctx {
     int rank = 0, world = 1;
     sgb_step2 *step2 = nullptr;
     sgb_dense *dense = nullptr;
+    bool umma_accumulate = false;                     // k_pk2_umma adds to `out` instead of overwriting it
     int grm_mode = SGB_GRM_PACKED;                    // which GRM the products / PCG use
 
     sgb_counters cnt = {};
