@@ -204,6 +204,7 @@ typedef struct {
     int64_t n_kernel_launches;      /* kernels of this library launched */
     int64_t n_allreduce;            /* NCCL allreduces issued */
     int64_t bytes_h2d, bytes_d2h;
+    int64_t n_probe_product_reuse;  /* getAIScore calls that reused the cached K.U of the Hutchinson probes */
 } sgb_counters;
 int sgb_get_counters(sgb_ctx *h, sgb_counters *out);
 int sgb_reset_counters(sgb_ctx *h);

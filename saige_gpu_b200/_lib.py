@@ -18,7 +18,7 @@ PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_do
 class Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_crossprod_calls", "n_crossprod_columns", "n_pcg_solves",
                                          "n_pcg_iterations", "n_kernel_launches", "n_allreduce",
-                                         "bytes_h2d", "bytes_d2h")]
+                                         "bytes_h2d", "bytes_d2h", "n_probe_product_reuse")]
 
 
 class SaigeB200Error(RuntimeError):

@@ -561,6 +561,7 @@ extern "C" int sgb_set_grm_mode(sgb_ctx *h, int mode)
     if (mode != SGB_GRM_PACKED && mode != SGB_GRM_DENSE) return sgb_fail(h, "unknown GRM mode %d", mode);
     if (mode == SGB_GRM_DENSE && (!h->dense || h->dense->partial)) return sgb_fail(h, "stored-GRM mode requested before sgb_dense_grm_build");
     h->grm_mode = mode;
+    h->ku_cols = 0;            // cached probe products belong to the other GRM representation
     return 0;
 }
 

@@ -1081,3 +1081,23 @@ int k_axpby(sgb_ctx *h, double a, const double *x, double b, const double *y, in
     LAUNCH_CHECK(h);
     return 0;
 }
+
+// d_count[0] += number of positions where a and b differ bitwise (probe-product cache check)
+__global__ void count_diff_kernel(const unsigned long long *__restrict__ a, const unsigned long long *__restrict__ b, int64_t n, int *__restrict__ d_count)
+{
+    int local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) local += a[i] != b[i];
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(d_count, local);
+}
+
+int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d_count)
+{
+    CUDA_OK(h, cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
+    int64_t gb = cdiv(n, 256 * 8);
+    if (gb > (int64_t)h->sm_count * 16) gb = (int64_t)h->sm_count * 16;
+    if (gb < 1) gb = 1;
+    count_diff_kernel<<<(unsigned)gb, 256, 0, h->stream>>>(reinterpret_cast<const unsigned long long *>(a), reinterpret_cast<const unsigned long long *>(b), n, d_count);
+    LAUNCH_CHECK(h);
+    return 0;
+}

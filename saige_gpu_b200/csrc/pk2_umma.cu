@@ -671,8 +671,12 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
         CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         attr2_set = true;
     }
-    for (int c0 = 0; c0 < ncolpad; c0 += 16) {
-        int nc = ncolpad - c0 < 16 ? ncolpad - c0 : 16;      // columns this pass (even)
+    // passes of <= 16 columns, balanced: 20 columns run as 10 + 10 (two HBM-bound passes) rather than 16 + 4 (one
+    // tensor-bound and one HBM-bound pass)
+    const int npass = (ncolpad + 15) / 16;
+    const int per_pass = (((ncolpad + npass - 1) / npass) + 1) & ~1;
+    for (int c0 = 0; c0 < ncolpad; c0 += per_pass) {
+        int nc = ncolpad - c0 < per_pass ? ncolpad - c0 : per_pass;      // columns this pass (even)
         int N = nc * 8;
         // three A stages let the producers run a full step ahead of the MMAs; they fit 256 TMEM columns (2 CTAs per SM) for N <= 64
         int stages = (N <= 64) ? 3 : 2;

@@ -69,6 +69,10 @@ struct sgb_ctx {
     double *d_pcg = nullptr; size_t pcg_elems = 0;    // PCG state arena
     double *d_ai = nullptr; size_t ai_elems = 0;      // per-call arena of the AI-REML entry points
     int *d_idx = nullptr;                             // small int scratch (8192 ints)
+    // K.U of the Hutchinson probes: U is the same stream in every outer AI-REML iteration (set_seed(200) before each
+    // GetTrace, FG.cpp:3114), so the nrun-column product is computed once per (genotypes, GRM mode) and checked bitwise
+    double *d_ku = nullptr; size_t ku_elems = 0;      // [U | K.U]
+    int64_t ku_cols = 0;                              // 0 = nothing cached
     int32_t *d_limbsum = nullptr;                     // [2][1024][8] column limb sums of the current split
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -161,6 +165,7 @@ int k_eta(sgb_ctx *h, const double *Y, const double *SiY, const double *SiX, int
           const double *w, double tau0, double *eta);
 int k_rademacher_fill(sgb_ctx *h, double *B, int64_t n, uint64_t seed);
 int k_axpby(sgb_ctx *h, double a, const double *x, double b, const double *y, int64_t n, double *out);
+int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d_count);
 int k_grid_blocks(sgb_ctx *h, int64_t n);
 #define SGB_PART_BLOCKS 256   // partial-sum slots per column of the deterministic reductions
 

@@ -577,7 +577,27 @@ static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *
         if (first) {
             // ---- one (1+nu)-column product K.[PY | U] ----                        FG.cpp:3285, 3140
             SGB_TRY(up(h, dB + N, hostU.data(), (size_t)N * nu));
-            SGB_TRY(sgb_crossprod_device(h, dB, 1 + nu, dK, 0));
+            // K.U does not change between outer iterations (same probe stream): reuse it when U is bitwise the same
+            bool reuse = false;
+            if (h->ku_cols == nu && h->d_ku) {
+                int *d_cnt = h->d_idx + 8000, ndiff = 1;
+                SGB_TRY(k_count_diff(h, dB + N, h->d_ku, N * nu, d_cnt));
+                CUDA_OK(h, cudaMemcpyAsync(&ndiff, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_OK(h, cudaStreamSynchronize(h->stream));
+                reuse = ndiff == 0;
+            }
+            if (reuse) {
+                SGB_TRY(sgb_crossprod_device(h, dB, 1, dK, 0));
+                CUDA_OK(h, cudaMemcpyAsync(dK + N, h->d_ku + (size_t)N * nu, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
+                h->cnt.n_probe_product_reuse++;
+            } else {
+                SGB_TRY(sgb_crossprod_device(h, dB, 1 + nu, dK, 0));
+                h->ku_cols = 0;
+                SGB_TRY(sgb_ensure_f64(h, &h->d_ku, &h->ku_elems, (size_t)N * nu * 2));
+                CUDA_OK(h, cudaMemcpyAsync(h->d_ku, dB + N, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
+                CUDA_OK(h, cudaMemcpyAsync(h->d_ku + (size_t)N * nu, dK + N, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
+                h->ku_cols = nu;
+            }
             pairs.assign({0, 0});
             if (quant) { pairs.push_back(0); pairs.push_back(0); }
             double dd[2];

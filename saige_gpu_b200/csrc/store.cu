@@ -107,7 +107,7 @@ static void free_store(sgb_ctx *h)
     void **ptrs[] = {(void **)&h->dG, (void **)&h->dGt, (void **)&h->d_f2, (void **)&h->d_s, (void **)&h->d_s2,
                      (void **)&h->d_diag, (void **)&h->d_diag_loco};
     for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
-    h->loaded = false; h->diag_ready = false; h->diag_loco_ready = false;
+    h->loaded = false; h->diag_ready = false; h->diag_loco_ready = false; h->ku_cols = 0;
     h->Mloc = h->M = h->Mvr = 0;
 }
 
@@ -119,7 +119,7 @@ extern "C" void sgb_destroy(sgb_ctx *h)
     sgb_dist_destroy(h);
     sgb_step2_free(h);
     free_store(h);
-    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx, h->d_limbsum};
+    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx, h->d_limbsum, h->d_ku};
     for (auto p : ptrs) if (p) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -131,7 +131,7 @@ extern "C" int sgb_set_engine(sgb_ctx *h, int engine)
 {
     if (engine < SGB_ENGINE_TENSOR || engine > SGB_ENGINE_IMMA) return sgb_fail(h, "unknown engine %d", engine);
     h->engine = engine;
-    h->diag_ready = false; h->diag_loco_ready = false;
+    h->diag_ready = false; h->diag_loco_ready = false; h->ku_cols = 0;
     return 0;
 }
 extern "C" int sgb_device_sync(sgb_ctx *h) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaStreamSynchronize(h->stream)); return 0; }
