@@ -381,8 +381,8 @@ def main():
         dense_info = {"kernel": "pk2_umma_kernel (tcgen05 kind::i8, M=128 N=128 K=32)", "weight_limbs": 7,
                       "sample": "last %d of %d block-rows (128 samples each) x %d markers" % (nsample, nbr, M),
                       "ms": dms, "int8_tops": dops / (dms * 1e-3) / 1e12,
-                      "roofline": {"bound": "tensor", "achieved": dops / (dms * 1e-3) / 1e12, "peak": tpeak, "unit": "TOP/s",
-                                   "frac": dops / (dms * 1e-3) / 1e12 / tpeak, "peak_source": tsrc},
+                      "roofline": {"bound": "tensor", "achieved": dops / (dms * 1e-3) / 1e12 / world, "peak": tpeak, "unit": "TOP/s per GPU",
+                                   "frac": dops / (dms * 1e-3) / 1e12 / world / tpeak, "peak_source": tsrc},
                       "full_build_estimate_s": 7 * 2.0 * M * 128 * 128 * nbr * (nbr + 1) / 2 / (dops / (dms * 1e-3))}
 
     if rank == 0:

@@ -85,11 +85,11 @@ def Covariate_Transform_Back(coef, param):
 def ScoreTest_NULL_Model(mu, mu2, y, X):
     V = np.asarray(mu2, dtype=np.float64)
     res = y - mu
-    XV = (X * V[:, None]).T
-    XVX = X.T @ XV.T
+    XVt = X * V[:, None]                      # N x p once; XV is its transpose (a view)
+    XVX = X.T @ XVt
     XVX_inv = np.linalg.inv(XVX)
     XXVX_inv = X @ XVX_inv
-    return dict(XV=XV, XVX=XVX, XXVX_inv=XXVX_inv, XVX_inv=XVX_inv, S_a=(X * res[:, None]).sum(0),
+    return dict(XV=XVt.T, XVX=XVX, XXVX_inv=XXVX_inv, XVX_inv=XVX_inv, S_a=res @ X,
                 XVX_inv_XV=XXVX_inv * V[:, None], V=V)
 
 
