@@ -10,7 +10,7 @@
 // image  digit_l(m) * h_jm  (|.| <= 128) of a 128-sample panel, the A operand is the 2-bit sample-major store decoded
 // into TMEM by pk2_umma_kernel, accumulation is int32.  The centring terms are integers too: N phi_m = 2N - AC_m, so
 //   N^2 2^S M K_ij = N^2 Q_ij - N (U'_i + U'_j) + C',   U'_i = sum_m W_m (2N - AC_m) h_im,   C' = sum_m W_m (2N - AC_m)^2
-// is evaluated in 128-bit integer arithmetic (U' from four/five exact fp64 sweeps over 12-bit pieces of W) and rounded
+// is evaluated in 128-bit integer arithmetic (U' from one exact 5-column tensor sweep over 12-bit pieces of W) and rounded
 // to fp64 ONCE, after the cancellation.  Only the weight rounding (2^-(7 limbs - 2) relative to the largest weight)
 // separates the stored matrix from exact arithmetic.
 //
@@ -152,18 +152,18 @@ __global__ void syrk_finalize_kernel(double *__restrict__ panel, const double *_
         __int128 Us = 0;
 #pragma unroll
         for (int p = 0; p < DG_UPIECES; p++)
-            Us += (__int128)((long long)U[(int64_t)p * N + i] + (long long)U[(int64_t)p * N + j]) << (12 * p);
+            Us += (__int128)(__double2ll_rn(U[(int64_t)p * N + i]) + __double2ll_rn(U[(int64_t)p * N + j])) << (12 * p);
         const __int128 T = (__int128)N * ((__int128)N * Q - Us) + C;
         panel[e] = i128_to_double(T) * mul;
     }
 }
 
-// U'_p,i = 2 sum_m v_p,m - (G^T v_p)_i   (raw = G^T v from the f64 column-dot kernel; exact: all sums are integers < 2^53)
-__global__ void syrk_u_kernel(const double *__restrict__ raw, int64_t N, const double *__restrict__ sums, double *__restrict__ U)
+// U'_p,i = 2 sum_m v_p,m - (G^T v_p)_i   (raw = G^T v; exact: all sums are integers < 2^53)
+__global__ void syrk_u_kernel(const double *__restrict__ raw, int64_t ldr, int64_t N, const double *__restrict__ sums, double *__restrict__ U)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int p = blockIdx.y;
-    if (i < N) U[(int64_t)p * N + i] = 2.0 * sums[p] - raw[(int64_t)p * N + i];
+    if (i < N) U[(int64_t)p * N + i] = 2.0 * sums[p] - raw[(int64_t)p * ldr + i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -407,18 +407,26 @@ static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n
     for (int q = 0; q < h->world && h->world > 1; q++)
         SGB_TRY(sgb_broadcast_bytes(h, (void *)sh[(size_t)q].gt, (size_t)h->rowsT * sh[(size_t)q].sT, q));
 
-    // ---- U'_i over all markers: DG_UPIECES exact fp64 sweeps ----
+    // ---- U'_i over all markers: one DG_UPIECES-column sweep of the tensor engine (exact: 12-bit pieces, sums < 2^53) ----
     CUDA_OK(h, cudaMalloc((void **)&d->dU, sizeof(double) * N * DG_UPIECES));
     {
-        SGB_TRY(sgb_ensure_f64(h, &h->d_tmp, &h->tmp_elems, (size_t)(h->rowsG + N + 1) * DG_UPIECES));
-        double *dv = h->d_tmp, *raw = dv + h->rowsG * DG_UPIECES;
+        const int64_t rowsT = h->rowsT;
+        double *dv = nullptr, *raw = nullptr;
+        CUDA_OK(h, cudaMalloc((void **)&dv, sizeof(double) * (size_t)(h->rowsG + rowsT + 1) * DG_UPIECES));
+        raw = dv + h->rowsG * DG_UPIECES;
         CUDA_OK(h, cudaMemcpyAsync(dv, vloc.data(), sizeof(double) * h->rowsG * DG_UPIECES, cudaMemcpyHostToDevice, h->stream));
-        SGB_TRY(k_coldot_f64(h, dv, nullptr, h->rowsG, DG_UPIECES, raw, N));
-        CUDA_OK(h, cudaMemcpyAsync(raw + N * DG_UPIECES, sumv, sizeof(double) * DG_UPIECES, cudaMemcpyHostToDevice, h->stream));
-        if (h->world > 1) SGB_TRY(sgb_allreduce_sum(h, raw, (N + 1) * DG_UPIECES));
-        syrk_u_kernel<<<dim3((unsigned)cdiv64(N, 256), DG_UPIECES), 256, 0, h->stream>>>(raw, N, raw + N * DG_UPIECES, d->dU);
-        DG_LAUNCH_CHECK(h);
-        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        int rcu = sgb_gt_times_cols(h, dv, DG_UPIECES, raw);
+        if (!rcu) {
+            cudaMemcpyAsync(raw + rowsT * DG_UPIECES, sumv, sizeof(double) * DG_UPIECES, cudaMemcpyHostToDevice, h->stream);
+            if (h->world > 1) rcu = sgb_allreduce_sum(h, raw, (rowsT + 1) * DG_UPIECES);
+        }
+        if (!rcu) {
+            syrk_u_kernel<<<dim3((unsigned)cdiv64(N, 256), DG_UPIECES), 256, 0, h->stream>>>(raw, rowsT, N, raw + rowsT * DG_UPIECES, d->dU);
+            h->cnt.n_kernel_launches++;
+        }
+        cudaStreamSynchronize(h->stream);
+        cudaFree(dv);
+        if (rcu) return rcu;
     }
 
     // ---- storage of the block-rows this rank owns ----

@@ -171,6 +171,7 @@ int k_grid_blocks(sgb_ctx *h, int64_t n);
 
 // crossprod.cu
 int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int loco);
+int sgb_gt_times_cols(sgb_ctx *h, const double *D, int k, double *raw);   // raw (ld rowsT) = G^T D (ld rowsG), tensor engine
 int sgb_diag_device(sgb_ctx *h);
 int sgb_diag_loco_device(sgb_ctx *h);
 int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const double *dB, int k, int maxiter, double tol,

@@ -119,6 +119,23 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     return 0;
 }
 
+
+// raw[i + c*rowsT] = sum_m g_mi D[m + c*rowsG]  over the local markers, on the tensor engine (the second sweep of a
+// product on its own).  Exact whenever the entries of D are integers below 2^53 and the sums stay below 2^53.
+int sgb_gt_times_cols(sgb_ctx *h, const double *D, int k, double *raw)
+{
+    NEED_LOADED(h);
+    const int64_t rowsG = h->rowsG, rowsT = h->rowsT;
+    const int kpad = (k + 1) & ~1;
+    SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, k_umma_limb_bytes(k, h->sT)));
+    SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * kpad));
+    double *sc = h->d_scal;
+    SGB_TRY(k_split_limbs_umma(h, D, h->Mloc, rowsG, k, h->d_limb, h->sT, sc + SC_MULT2, h->d_limbsum + 8192));
+    SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
+    SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, kpad, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw, rowsT));
+    return 0;
+}
+
 // sum_m z_mi^2 for `nc` local-row ranges at once -> out[N x nc] (ld N); summed over ranks
 static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const std::vector<int64_t> &hi, double *out)
 {
