@@ -16,6 +16,8 @@
 #include <stdint.h>
 #include <string.h>
 #include <algorithm>
+#include <thread>
+#include <vector>
 #include "sgb_internal.h"
 
 #define S2_MAXP 16
@@ -28,6 +30,9 @@ struct s2_model {
     double XVX[S2_MAXP * S2_MAXP], S_a[S2_MAXP];
     double tau0, varRatio, spa_cutoff;
     const int32_t *pos;      // model sample -> row in the .fam
+    int identity;            // pos[i] == i: the model's samples are the first N rows of the .fam, in order
+    const uint32_t *ycase;   // identity only: bit 2j of word w set when sample 16w + j is a case (y == 1)
+    double ncase_tot;        // number of cases in the model
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sm)
@@ -57,6 +62,10 @@ struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + no
     int fast;
 };
 
+// IDENT: the model's samples are the first N rows of the .fam in order (the usual case).  Then genotype classes are
+// counted 16 samples at a time with popcounts on the raw PLINK words (allele / missing counts and every case-control
+// tally), warps skip 32-sample groups that hold no minor allele, and no per-sample index or phenotype is read.
+template <bool IDENT>
 __global__ void __launch_bounds__(S2_THREADS)
 step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
              double max_missing, int se_two_sided, double *__restrict__ out)
@@ -69,18 +78,39 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     const int tid = threadIdx.x, p = M.p;
     const int64_t N = M.N;
     double *o = out + m * S2_NOUT;
-    for (int64_t b = tid; b < B0; b += S2_THREADS) srow[b] = bed[m * B0 + b];
+    for (int64_t b = tid; b < B0 + 8; b += S2_THREADS) srow[b] = b < B0 ? bed[m * B0 + b] : (uint8_t)0;      // 8 pad bytes: word-wise reads
     __syncthreads();
 
     // ---- getOneMarker: counts over the model's samples ----
-    double c_alt = 0, c_miss = 0;
-    for (int64_t i = tid; i < N; i += S2_THREADS) {
-        int32_t src = M.pos[i];
-        int code = (srow[src >> 2] >> ((src & 3) << 1)) & 3;
-        c_alt += code == 0 ? 2.0 : (code == 2 ? 1.0 : 0.0);
-        c_miss += code == 1 ? 1.0 : 0.0;
+    double altCounts0, nMiss;
+    double k2c = 0, k1c = 0, kmc = 0, k2a = 0, k1a = 0;          // IDENT: hom-alt / het / missing among cases, hom-alt / het among all
+    if (IDENT) {
+        const int64_t nw = (N + 15) >> 4;
+        const uint32_t *wrow = reinterpret_cast<const uint32_t *>(srow);
+        int c2 = 0, c1 = 0, cm = 0, d2 = 0, d1 = 0, dm = 0;
+        for (int64_t w = tid; w < nw; w += S2_THREADS) {
+            const uint32_t x = wrow[w];
+            uint32_t valid = 0x55555555u;
+            if (w == nw - 1 && (N & 15)) valid &= (1u << (2 * (N & 15))) - 1u;
+            const uint32_t L = x & 0x55555555u, H = (x >> 1) & 0x55555555u;
+            const uint32_t homalt = ~L & ~H & valid, het = H & ~L & valid, miss = L & ~H & valid;      // PLINK.hpp:48-56, alt-first
+            const uint32_t yc = M.ycase[w];
+            c2 += __popc(homalt); c1 += __popc(het); cm += __popc(miss);
+            d2 += __popc(homalt & yc); d1 += __popc(het & yc); dm += __popc(miss & yc);
+        }
+        k2a = block_sum((double)c2, red); k1a = block_sum((double)c1, red); nMiss = block_sum((double)cm, red);
+        k2c = block_sum((double)d2, red); k1c = block_sum((double)d1, red); kmc = block_sum((double)dm, red);
+        altCounts0 = 2.0 * k2a + k1a;
+    } else {
+        double c_alt = 0, c_miss = 0;
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            int32_t src = M.pos[i];
+            int code = (srow[src >> 2] >> ((src & 3) << 1)) & 3;
+            c_alt += code == 0 ? 2.0 : (code == 2 ? 1.0 : 0.0);
+            c_miss += code == 1 ? 1.0 : 0.0;
+        }
+        altCounts0 = block_sum(c_alt, red); nMiss = block_sum(c_miss, red);
     }
-    const double altCounts0 = block_sum(c_alt, red), nMiss = block_sum(c_miss, red);
     const double cnt = (double)N - nMiss;
     double altFreq = cnt > 0 ? altCounts0 / cnt / 2.0 : 0.0;
     const double missingRate = nMiss / (double)N;
@@ -100,26 +130,61 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
 #pragma unroll
     for (int j = 0; j < S2_MAXP; j++) { zs[j] = 0; ws[j] = 0; }
     double t1 = 0, r0 = 0, gsum = 0, nz = 0, gcase = 0, ncase = 0, gctrl = 0, nctrl = 0, case_hom = 0, case_het = 0, ctrl_hom = 0, ctrl_het = 0;
-    for (int64_t i = tid; i < N; i += S2_THREADS) {
-        const int g = s2_geno(srow, M.pos[i], flip, imputeG);
-        const double yi = M.y[i];
-        if (yi == 1.0) { ncase += 1; gcase += g; case_hom += g == 2; case_het += g == 1; }
-        else { nctrl += 1; gctrl += g; ctrl_hom += g == 2; ctrl_het += g == 1; }
-        if (g) {
-            const double gd = (double)g, m2 = M.mu2[i];
-            gsum += gd; nz += 1;
-            t1 += m2 * gd * gd;
-            r0 += M.res[i] * gd;
-            for (int j = 0; j < p; j++) {
-                zs[j] += M.A[i + (int64_t)j * N] * gd;
-                ws[j] += m2 * M.X[i + (int64_t)j * N] * gd;
+    if (IDENT) {
+        // one warp per 32 consecutive samples (two PLINK words); groups without a minor allele are skipped
+        const int lane = tid & 31, warp = tid >> 5;
+        const uint32_t *wrow = reinterpret_cast<const uint32_t *>(srow);
+        const int64_t ng = (N + 31) >> 5, nw = (N + 15) >> 4;
+        const uint32_t allzero = flip ? 0u : 0xFFFFFFFFu;          // 16 x "no copy of the tested allele"
+        for (int64_t gI = warp; gI < ng; gI += S2_THREADS / 32) {
+            const uint32_t x0 = wrow[2 * gI], x1 = (2 * gI + 1 < nw) ? wrow[2 * gI + 1] : allzero;
+            if (x0 == allzero && x1 == allzero) continue;
+            const int64_t i = (gI << 5) + lane;
+            const uint32_t x = lane < 16 ? x0 : x1;
+            const int code = (int)((x >> ((lane & 15) << 1)) & 3u);
+            int g = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : -1));
+            g = g < 0 ? imputeG : (flip ? 2 - g : g);
+            if (i < N && g) {
+                const double gd = (double)g, m2 = M.mu2[i];
+                t1 += m2 * gd * gd;
+                r0 += M.res[i] * gd;
+                for (int j = 0; j < p; j++) {
+                    zs[j] += M.A[i + (int64_t)j * N] * gd;
+                    ws[j] += m2 * M.X[i + (int64_t)j * N] * gd;
+                }
             }
         }
+        t1 = block_sum(t1, red); r0 = block_sum(r0, red);
+        // every tally follows from the class counts of the first pass (in the flipped / imputed coding)
+        ncase = M.ncase_tot; nctrl = (double)N - ncase;
+        const double k2t = k2a - k2c, k1t = k1a - k1c, kmt = nMiss - kmc;            // controls
+        const double h2c = flip ? ncase - k2c - k1c - kmc : k2c, h2t = flip ? nctrl - k2t - k1t - kmt : k2t;   // two copies after the flip
+        case_hom = h2c + (imputeG == 2 ? kmc : 0.0); case_het = k1c + (imputeG == 1 ? kmc : 0.0);
+        ctrl_hom = h2t + (imputeG == 2 ? kmt : 0.0); ctrl_het = k1t + (imputeG == 1 ? kmt : 0.0);
+        gcase = 2.0 * case_hom + case_het; gctrl = 2.0 * ctrl_hom + ctrl_het;
+        gsum = gcase + gctrl; nz = case_hom + case_het + ctrl_hom + ctrl_het;
+    } else {
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            const int g = s2_geno(srow, M.pos[i], flip, imputeG);
+            const double yi = M.y[i];
+            if (yi == 1.0) { ncase += 1; gcase += g; case_hom += g == 2; case_het += g == 1; }
+            else { nctrl += 1; gctrl += g; ctrl_hom += g == 2; ctrl_het += g == 1; }
+            if (g) {
+                const double gd = (double)g, m2 = M.mu2[i];
+                gsum += gd; nz += 1;
+                t1 += m2 * gd * gd;
+                r0 += M.res[i] * gd;
+                for (int j = 0; j < p; j++) {
+                    zs[j] += M.A[i + (int64_t)j * N] * gd;
+                    ws[j] += m2 * M.X[i + (int64_t)j * N] * gd;
+                }
+            }
+        }
+        t1 = block_sum(t1, red); r0 = block_sum(r0, red); gsum = block_sum(gsum, red); nz = block_sum(nz, red);
+        gcase = block_sum(gcase, red); ncase = block_sum(ncase, red); gctrl = block_sum(gctrl, red); nctrl = block_sum(nctrl, red);
+        case_hom = block_sum(case_hom, red); case_het = block_sum(case_het, red);
+        ctrl_hom = block_sum(ctrl_hom, red); ctrl_het = block_sum(ctrl_het, red);
     }
-    t1 = block_sum(t1, red); r0 = block_sum(r0, red); gsum = block_sum(gsum, red); nz = block_sum(nz, red);
-    gcase = block_sum(gcase, red); ncase = block_sum(ncase, red); gctrl = block_sum(gctrl, red); nctrl = block_sum(nctrl, red);
-    case_hom = block_sum(case_hom, red); case_het = block_sum(case_het, red);
-    ctrl_hom = block_sum(ctrl_hom, red); ctrl_het = block_sum(ctrl_het, red);
     for (int j = 0; j < p; j++) {
         double z = block_sum(zs[j], red), w = block_sum(ws[j], red);
         if (tid == 0) { Zs[j] = z; Ws[j] = w; }
@@ -162,7 +227,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         // gtilde_i = g_i - XXVX_inv[i,:] . (XV g),  XV g = W  (getadjGFast, SAIGE_test.cpp:306-315)
         double m1p = 0, gpos = 0, gneg = 0, gmuNB = 0, sigNB = 0;
         for (int64_t i = tid; i < N; i += S2_THREADS) {
-            const int g = s2_geno(srow, M.pos[i], flip, imputeG);
+            const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
             double gt = (double)g;
             for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
             const double mu = M.mu[i];
@@ -183,14 +248,14 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         auto cgf = [&](double t, double &k0, double &k1, double &k2) {
             double a0 = 0, a1 = 0, a2 = 0;
             for (int64_t i = tid; i < N; i += S2_THREADS) {
-                const int g = s2_geno(srow, M.pos[i], flip, imputeG);
+                const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
                 if (fast && !g) continue;
                 double gt = (double)g;
                 for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
                 const double mu = M.mu[i];
                 const double e = exp(-gt * t);
                 const double den = (1.0 - mu) * e + mu;
-                a0 += log(1.0 - mu + mu * exp(gt * t));
+                a0 += log(1.0 - mu + mu / e);               // exp(gt t) = 1 / e: one exponential per sample
                 a1 += mu * gt / den;
                 a2 += (1.0 - mu) * mu * gt * gt * e / (den * den);
             }
@@ -279,6 +344,7 @@ struct sgb_step2 {
     s2_model M;
     double *d_vec = nullptr;      // mu | mu2 | res | y | X | A | XXVXi
     int32_t *d_pos = nullptr;
+    uint32_t *d_ycase = nullptr;
     uint8_t *d_bed = nullptr; size_t bed_bytes = 0;
     double *d_out = nullptr; size_t out_elems = 0;
     uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
@@ -317,7 +383,31 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     for (int i = 0; i < p * p; i++) M.XVX[i] = XVX[i];
     for (int i = 0; i < p; i++) M.S_a[i] = S_a[i];
     M.tau0 = tau[0]; M.varRatio = varRatio; M.spa_cutoff = SPAcutoff; M.pos = s->d_pos;
+    // identity fast path: pos[i] == i; the case mask lives in the bit positions of the PLINK low bits
+    M.identity = 1;
+    for (int64_t i = 0; i < N; i++) if (pos_in_fam[i] != (int32_t)i) { M.identity = 0; break; }
+    std::vector<uint32_t> yc((size_t)((N + 15) / 16) + 2, 0u);
+    double ncase = 0;
+    for (int64_t i = 0; i < N; i++) if (y[i] == 1.0) { yc[(size_t)(i >> 4)] |= 1u << (2 * (i & 15)); ncase += 1; }
+    if (s->d_ycase) { cudaFree(s->d_ycase); s->d_ycase = nullptr; }
+    CUDA_OK(h, cudaMalloc((void **)&s->d_ycase, sizeof(uint32_t) * yc.size()));
+    CUDA_OK(h, cudaMemcpy(s->d_ycase, yc.data(), sizeof(uint32_t) * yc.size(), cudaMemcpyHostToDevice));
+    M.ycase = s->d_ycase; M.ncase_tot = ncase;
     return 0;
+}
+
+// pageable -> pinned staging copy on 4 host threads (one thread tops out near 10 GB/s, below what the kernel consumes)
+static void s2_par_copy(uint8_t *dst, const uint8_t *src, size_t n)
+{
+    const int nt = n > ((size_t)8 << 20) ? 4 : 1;
+    if (nt == 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        const size_t o = t * per, len = o < n ? std::min(per, n - o) : 0;
+        if (len) th.emplace_back([=] { memcpy(dst + o, src + o, len); });
+    }
+    for (auto &x : th) x.join();
 }
 
 extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
@@ -352,7 +442,8 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     s->out_elems = ob / sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
         attr_set = true;
     }
     int cur = 0;
@@ -361,12 +452,16 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
         const int64_t nm = std::min(chunk, n_markers - m0);
         CUDA_OK(h, cudaEventSynchronize(s->ev[cur]));                      // buffers `cur` are free again (chunk c-2 done)
         if (held_m0[cur] >= 0) memcpy(out + (size_t)held_m0[cur] * S2_NOUT, s->pout[cur], sizeof(double) * held_nm[cur] * S2_NOUT);
-        memcpy(s->pin[cur], bed_rows + (size_t)m0 * B0, (size_t)nm * B0);
+        s2_par_copy(s->pin[cur], bed_rows + (size_t)m0 * B0, (size_t)nm * B0);
         uint8_t *db = s->d_bed + cur * cbytes;
         double *dout = s->d_out + cur * (size_t)chunk * S2_NOUT;
         CUDA_OK(h, cudaMemcpyAsync(db, s->pin[cur], (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
         h->cnt.bytes_h2d += nm * B0;
-        step2_kernel<<<(unsigned)nm, S2_THREADS, (size_t)B0, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout);
+        // dynamic smem: the raw row, padded so that the word-wise reads of the last (partial) word pair stay inside
+        if (s->M.identity)
+            step2_kernel<true><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout);
+        else
+            step2_kernel<false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout);
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
         CUDA_OK(h, cudaMemcpyAsync(s->pout[cur], dout, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
@@ -386,6 +481,7 @@ void sgb_step2_free(sgb_ctx *h)
     if (!s) return;
     if (s->d_vec) cudaFree(s->d_vec);
     if (s->d_pos) cudaFree(s->d_pos);
+    if (s->d_ycase) cudaFree(s->d_ycase);
     if (s->d_bed) cudaFree(s->d_bed);
     if (s->d_out) cudaFree(s->d_out);
     for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }
