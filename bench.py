@@ -332,6 +332,28 @@ def main():
         ingest_info = {"bed_gbytes": bed_i.nbytes / 1e9, "seconds": ti, "gb_per_s": bed_i.nbytes / 1e9 / ti,
                        "sample": "%d samples x %d markers, 1%% missing calls, host-resident .bed body" % (n_i, m_i)}
         gi.close()
+    step2_info = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # BASELINE config 5 row: single-variant score test + SPA through the C ABI from pageable host rows, bounded sample
+        from oracle import oracle as O
+        n2, m2 = N, 8192
+        rng2 = np.random.default_rng(SEED + 9)
+        bed2 = O.synth_bed(n2, m2, SEED + 9, miss_rate=0.005)
+        X2 = np.column_stack([np.ones(n2), rng2.normal(size=(n2, 2))])
+        mu_ = 1 / (1 + np.exp(-(X2 @ np.array([-2.2, 0.4, -0.3]) + rng2.normal(scale=0.3, size=n2))))
+        y2 = (rng2.uniform(size=n2) < mu_).astype(np.float64)
+        v2 = mu_ * (1 - mu_)
+        XVXi = np.linalg.inv(X2.T @ (X2 * v2[:, None]))
+        mdl = dict(mu=mu_, res=y2 - mu_, mu2=v2, tau=np.array([1.0, 0.3]), trait="binary", y=y2, X=X2, XVX=X2.T @ (X2 * v2[:, None]),
+                   XXVX_inv=X2 @ XVXi, XVX_inv_XV=(X2 @ XVXi) * v2[:, None], S_a=(y2 - mu_) @ X2)
+        g2 = SaigeB200(device=local_rank)
+        g2.setSAIGEobjInCPP(mdl, 0.95, 2.0, np.arange(n2, dtype=np.int32))
+        g2.mainMarkerInCPP(bed2, n2, m2)                       # sizes the pinned staging buffers
+        t2 = time.time(); o2 = g2.mainMarkerInCPP(bed2, n2, m2); t2 = time.time() - t2
+        step2_info = {"variants_per_s": m2 / t2, "gb_per_s_raw_rows": bed2.nbytes / t2 / 1e9, "spa_adjusted": int(o2[:, 10].sum()),
+                      "sample": "%d samples x %d variants (AF ~ U(0.05, 0.5), 0.5%% missing), binary trait, 3 covariate columns, "
+                                "SPA cutoff 2, host-resident PLINK rows" % (n2, m2)}
+        g2.close()
     step1_info = None
     if not args.no_step1:
         # polygenic liability (h2 ~ 0.3) from 200 causal markers read back through Get_OneSNP_StdGeno
@@ -408,6 +430,7 @@ def main():
             "ingest": ingest_info,
             "step1": step1_info,
             "dense_grm": dense_info,
+            "step2": step2_info,
         }
         print(json.dumps(line))
     g.close()
