@@ -13,7 +13,6 @@
 //     descriptor and the int32 accumulator in TMEM; tcgen05.commit -> mbarriers release the A stage and the B stage;
 //   * the epilogue reads the accumulator with tcgen05.ld and adds it to the global int32 limb sums.
 // Integer arithmetic is exact, so results are bit-identical to the mma.sync kernel (the k <= 2 path and cross-check).
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -42,26 +41,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity));
-}
-
-// non-blocking test of an mbarrier phase (forward declared use below)
-__device__ __forceinline__ int mbar_test(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return (int)ok;
-}
-
-__device__ __forceinline__ void mbar_wait2(uint64_t *bar, uint32_t parity, int spin)
-{
-    if (spin) { while (!mbar_test(bar, parity)) { } }
-    else mbar_wait(bar, parity);
 }
 
 __device__ __forceinline__ uint32_t prmt_u(uint32_t a, uint32_t b, uint32_t sel)
@@ -131,6 +110,7 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 #define UMMA_MAX_STAGES 3        // A (TMEM) pipeline depth: 2 stages of 64 columns, or 3 when the accumulator needs <= 64 columns
 #define UMMA_MAX_BSTAGES 16      // B (smem) ring depth is chosen at launch: as many 128 x N byte stages as fit ~96 KB
 #define UMMA_PF 3                // packed-row prefetch distance of the producer threads, in steps
+#define UMMA_L2_AHEAD 12         // L2 prefetch distance of the producers, in k-steps of 64 bytes (8..16 measured equal)
 #define UMMA_PGROUPS 2           // producer groups of 4 warps; group g owns the k-steps s = g (mod UMMA_PGROUPS)
 #define UMMA_PWARPS (4 * UMMA_PGROUPS)
 #define UMMA_THREADS (32 * (UMMA_PWARPS + 2))   // producers (+ epilogue), then one MMA-issuer warp and one bulk-copy warp
@@ -211,8 +191,18 @@ template <int UMMA_STAGES>
 __global__ void __launch_bounds__(UMMA_THREADS, 2)
 pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_total, int ksteps_per_chunk,
                 const int8_t *__restrict__ L, int N, int64_t Lblk_stride, int32_t *__restrict__ out, int ldo, int n0,
-                int use_atomic, umma_pools pool, int tmem_cols, int nb, int dbg)
+                int use_atomic, umma_pools pool, int tmem_cols, int nb, int dbg_arg)
 {
+    // Ablation switches (drop the loads / decode + tcgen05.st / MMAs / B copies; results are then wrong): only in builds
+    // with -DSGB_ABLATION (make ABLATION=1), where SGB_UMMA_DBG selects them at run time.  DESIGN.md 3.1b has the findings.
+#ifdef SGB_ABLATION
+    const int dbg = dbg_arg & 255;
+    const int l2_ahead = (dbg_arg >> 8) ? (dbg_arg >> 8) : UMMA_L2_AHEAD;
+#else
+    constexpr int dbg = 0;
+    constexpr int l2_ahead = UMMA_L2_AHEAD;
+    (void)dbg_arg;
+#endif
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_a[UMMA_MAX_STAGES], empty[UMMA_MAX_STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -247,7 +237,6 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
         const int64_t row = (int64_t)blockIdx.y * UMMA_ROWS + q4 * 32 + (tid & 31);
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;         // this warp's TMEM lane quarter
         const uint8_t *prow = P + row * stride + ks0 * 64;
-        const int l2_ahead = (dbg >> 8) ? (dbg >> 8) : 12;        // in k-steps of 64 bytes (even: whole lines)
         u32x8 pf[UMMA_PF][2];
 #pragma unroll
         for (int i = 0; i < UMMA_PF; i++) {
@@ -336,175 +325,6 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
                 src += 2 * Lblk_stride;
                 if (++sbi == nb) { sbi = 0; pb ^= 1; wrapped = true; }
             }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Narrow batches (N <= 64, i.e. k <= 8 columns): the MMAs are short, so the kernel lives or dies by how many genotype
-// bytes are in flight.  Row-per-thread register prefetch tops out near 100 KB per SM (~4 TB/s measured); here the packed
-// rows are instead streamed by the TMA engine: ONE cp.async.bulk.tensor.2d per chunk moves a [128 rows x 128 bytes] box
-// into a 128B-swizzled shared-memory ring (conflict-free 128-bit reads with thread = row), tracked by one mbarrier per
-// chunk, which keeps up to 6 x 16 KB per CTA in flight without holding a single register.  (Per-row 1-D bulk copies of
-// 128 B were tried first: the TMA unit retires roughly one bulk operation per 38 cycles, 0.9 TB/s.)  Everything after
-// the shared-memory read is the pipeline of pk2_umma_kernel: prmt decode -> tcgen05.st -> tcgen05.mma -> tcgen05.ld.
-// ---------------------------------------------------------------------------------------------------
-#define UMMA_CH_BYTES 128                           // packed bytes per row and chunk = 2 k-steps
-#define UMMA_CH_SMEM (UMMA_ROWS * UMMA_CH_BYTES)    // 16384 B per chunk (128B swizzle: 16-byte unit j of row r sits at j ^ (r & 7))
-#define UMMA_MAX_CHUNKS 6
-
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
-{
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__global__ void __launch_bounds__(UMMA_THREADS, 2)
-pk2_umma_staged_kernel(const __grid_constant__ CUtensorMap tmap, int64_t ksteps_total, int ksteps_per_chunk,
-                       const int8_t *__restrict__ L, int N, int64_t Lblk_stride, int32_t *__restrict__ out, int ldo, int n0,
-                       int use_atomic, umma_pools pool, int tmem_cols, int nb, int nch)
-{
-    constexpr int STAGES = 3;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t full_a[STAGES], empty[STAGES], full_b[UMMA_MAX_BSTAGES], empty_b[UMMA_MAX_BSTAGES], done_bar;
-    __shared__ uint64_t full_c[UMMA_MAX_CHUNKS], empty_c[UMMA_MAX_CHUNKS];
-    __shared__ uint32_t tmem_base_slot;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t ks0 = (int64_t)blockIdx.x * ksteps_per_chunk;
-    int64_t ks1 = ks0 + ksteps_per_chunk;
-    if (ks1 > ksteps_total) ks1 = ksteps_total;
-    const int nsteps = (int)(ks1 - ks0);
-    const uint32_t stage_bytes = (uint32_t)UMMA_KSTEP * (uint32_t)N;
-    const uint32_t half_bytes = stage_bytes / 2;
-    uint8_t *smem_b = smem;                                        // B ring: nb stages
-    uint8_t *smem_c = smem + (size_t)nb * stage_bytes;            // genotype chunk ring: nch chunks
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 32) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(&full_a[i], 4); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < nb; i++) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-        for (int i = 0; i < nch; i++) { mbar_init(&full_c[i], 1); mbar_init(&empty_c[i], 4 * UMMA_PGROUPS); }
-        mbar_init(&done_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tmem_base = tmem_base_slot;
-    const uint32_t tmem_d = tmem_base + STAGES * UMMA_A_COLS;
-
-    if (warp < UMMA_PWARPS) {
-        // ================= producers: thread = row; group g owns the k-steps s = g (mod 2) =================
-        const int grp = warp >> 2, q4 = warp & 3;
-        const int r128 = q4 * 32 + lane;
-        const int64_t row = (int64_t)blockIdx.y * UMMA_ROWS + r128;
-        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
-        const uint32_t my_c = smem_u32(smem_c) + (uint32_t)r128 * UMMA_CH_BYTES;
-        const uint32_t sw = (uint32_t)(r128 & 7);                    // 128B swizzle phase of this row
-        for (int s = grp; s < nsteps; s += UMMA_PGROUPS) {
-            const int c = s >> 1, cs = c % nch, uc = c / nch;
-            const int st = s % STAGES, u = s / STAGES;
-            mbar_wait(&full_c[cs], (uint32_t)(uc & 1));
-            const uint32_t src = my_c + (uint32_t)cs * UMMA_CH_SMEM;
-            uint4 w4[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) w4[i] = lds_u4(src + ((((uint32_t)grp * 4 + i) ^ sw) << 4));     // step parity = group
-            if (u > 0) mbar_wait(&empty[st], (uint32_t)((u - 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-                uint32_t a[32];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint4 q = w4[2 * hf + (i >> 2)];
-                    const uint32_t wv = (i & 3) == 0 ? q.x : (i & 3) == 1 ? q.y : (i & 3) == 2 ? q.z : q.w, hi = wv >> 16;
-                    a[4 * i + 0] = prmt_u(pool.ax, pool.ay, wv);
-                    a[4 * i + 1] = prmt_u(pool.ax, pool.ay, hi);
-                    a[4 * i + 2] = prmt_u(pool.bx, pool.by, wv);
-                    a[4 * i + 3] = prmt_u(pool.bx, pool.by, hi);
-                }
-                tmem_st_x32(tmem_base + lane_base + st * UMMA_A_COLS + hf * 32, a);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_c[cs]);  // this warp's bytes of the chunk are in registers / TMEM
-            asm volatile("tcgen05.wait::st.sync.aligned;");
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_a[st]);
-        }
-        if (nsteps > 0) {
-            mbar_wait(&done_bar, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            int32_t *o = out + row * ldo + n0;
-            for (int c = grp * 16; c < N; c += 16 * UMMA_PGROUPS) {
-                int32_t v[16];
-                tmem_ld_x16(tmem_d + lane_base + c, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-                if (use_atomic) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) if (v[i]) atomicAdd(o + c + i, v[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<int4 *>(o + c + i) = make_int4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                }
-            }
-        }
-    } else if (warp == UMMA_PWARPS) {
-        // ================= MMA issuer warp =================
-        umma_issue_loop<STAGES>(nsteps, nb, N, smem_u32(smem_b), stage_bytes, tmem_base, tmem_d, full_a, empty, full_b, empty_b, &done_bar, lane, 0);
-    } else {
-        // ================= TMA warp: genotype chunks (all lanes, 4 rows each) and the B stages (lane 0) =================
-        // Both rings are refilled as soon as a slot frees up (non-blocking mbarrier tests), so a busy B ring never holds
-        // back the genotype stream.
-        const int nchunks = (nsteps + 1) >> 1;
-        int cA = 0, sB = 0;
-        while (cA < nchunks || sB < nsteps) {
-            int progressed = 0;
-            if (cA < nchunks) {
-                const int cs = cA % nch, uc = cA / nch;
-                int ok = 1;
-                if (lane == 0) {
-                    if (uc > 0) ok = mbar_test(&empty_c[cs], (uint32_t)((uc - 1) & 1));
-                    if (ok) {
-                        // a full chunk is released by both producer groups; a trailing half chunk only by group 0: it is never reused
-                        mbar_expect_tx(&full_c[cs], UMMA_CH_SMEM);
-                        tma_load_2d(smem_c + (size_t)cs * UMMA_CH_SMEM, &tmap, (int)((ks0 * 64 + (int64_t)cA * UMMA_CH_BYTES)),
-                                    (int)(blockIdx.y * UMMA_ROWS), &full_c[cs]);
-                    }
-                }
-                ok = __shfl_sync(0xffffffffu, ok, 0);
-                if (ok) { cA++; progressed = 1; }
-            }
-            if (sB < nsteps) {
-                const int sbi = sB % nb, ub = sB / nb;
-                int ok = 1;
-                if (lane == 0) {
-                    if (ub > 0) ok = mbar_test(&empty_b[sbi], (uint32_t)((ub - 1) & 1));
-                    if (ok) {
-                        mbar_expect_tx(&full_b[sbi], stage_bytes);
-                        bulk_g2s(smem_b + sbi * stage_bytes, L + (2 * (ks0 + sB)) * Lblk_stride, half_bytes, &full_b[sbi]);
-                        bulk_g2s(smem_b + sbi * stage_bytes + half_bytes, L + (2 * (ks0 + sB) + 1) * Lblk_stride, half_bytes, &full_b[sbi]);
-                    }
-                }
-                ok = __shfl_sync(0xffffffffu, ok, 0);
-                if (ok) { sB++; progressed = 1; }
-            }
-            if (!progressed) __nanosleep(128);        // both rings full: do not steal issue slots from the producers
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -608,31 +428,6 @@ int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int
     return 0;
 }
 
-// 2-D tensor map over packed rows [rows][stride bytes], box = 128 bytes x 128 rows, 128B swizzle (driver entry point
-// resolved through the runtime, so the library does not link libcuda)
-static int make_row_tensor_map(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows, CUtensorMap *out)
-{
-    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return sgb_fail(h, "cuTensorMapEncodeTiled is not available from this driver");
-        encode = (encode_fn)fn;
-    }
-    const cuuint64_t gdim[2] = {(cuuint64_t)stride, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)stride};
-    const cuuint32_t box[2] = {UMMA_CH_BYTES, UMMA_ROWS};
-    const cuuint32_t estride[2] = {1, 1};
-    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)P, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return sgb_fail(h, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return 0;
-}
-
 // out[r][c*8+l] += ...   for all k columns, in passes of <= 16 columns (N <= 128)
 int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
                int32_t *out, int plane)
@@ -664,13 +459,11 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
         attr_set = true;
     }
     static const int force_stages = getenv("SGB_UMMA_STAGES") ? atoi(getenv("SGB_UMMA_STAGES")) : 0;
-    static const int staged_env = getenv("SGB_UMMA_STAGED") ? atoi(getenv("SGB_UMMA_STAGED")) : -1;
-    static const int dbg = getenv("SGB_UMMA_DBG") ? atoi(getenv("SGB_UMMA_DBG")) : 0;      // timing experiments only (results wrong)
-    static bool attr2_set = false;
-    if (!attr2_set) {
-        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr2_set = true;
-    }
+#ifdef SGB_ABLATION
+    static const int dbg = getenv("SGB_UMMA_DBG") ? atoi(getenv("SGB_UMMA_DBG")) : 0;
+#else
+    const int dbg = 0;
+#endif
     // passes of <= 16 columns, balanced: 20 columns run as 10 + 10 (two HBM-bound passes) rather than 16 + 4 (one
     // tensor-bound and one HBM-bound pass)
     const int npass = (ncolpad + 15) / 16;
@@ -690,18 +483,7 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
         for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {
             int64_t ny = row_tiles - y0 < 65535 ? row_tiles - y0 : 65535;
             dim3 grid((unsigned)kchunks, (unsigned)ny);
-            const bool staged = staged_env > 0 && N <= 64;      // experimental TMA-staged producers: measured slower
-            if (staged) {
-                // shared memory: 2 B stages + as many 18 KB genotype chunks as fit 110 KB (2 CTAs per SM)
-                const int nb2 = 2;
-                int nch = (int)((110 * 1024 - (size_t)nb2 * UMMA_KSTEP * N) / UMMA_CH_SMEM);
-                if (nch > UMMA_MAX_CHUNKS) nch = UMMA_MAX_CHUNKS;
-                CUtensorMap tmap;
-                SGB_TRY(make_row_tensor_map(h, P + y0 * UMMA_ROWS * stride, stride, ny * UMMA_ROWS, &tmap));
-                pk2_umma_staged_kernel<<<grid, UMMA_THREADS, (size_t)nb2 * UMMA_KSTEP * N + (size_t)nch * UMMA_CH_SMEM, h->stream>>>(
-                    tmap, ksteps, (int)per, Lp, N, (int64_t)ncolpad * 1024,
-                    out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8), ncolpad * 8, c0 * 8, use_atomic, pool, 256, nb2, nch);
-            } else if (stages == 3)
+            if (stages == 3)
                 pk2_umma_kernel<3><<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
                                                                            (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
                                                                            ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
