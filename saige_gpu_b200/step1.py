@@ -15,6 +15,8 @@ the export mirror in api.py (i.e. the C ABI); no numerical work on genotypes hap
 """
 import time
 
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 
@@ -221,17 +223,25 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
         t1 = time.time()
         geno.set_Diagof_StdGeno_LOCO()
         out["LOCOResult"] = []
-        for j, (s, e) in enumerate(zip(geno_start_vec(geno), geno_end_vec(geno))):
-            if s == -1 or e == -1:
-                out["LOCOResult"].append(dict(isLOCO=False))
-                continue
-            geno.setStartEndIndex(s, e, j)
-            rl = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, loco=True)
-            alpha, eta, mu = rl["alpha"], rl["eta"], rl["mu"]
-            mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau[0])
-            out["LOCOResult"].append(dict(isLOCO=True, coefficients=alpha, linear_predictors=eta, fitted_values=mu,
-                                          Y=rl["Y"], residuals=y - mu, cov=rl["cov"],
-                                          obj_noK=ScoreTest_NULL_Model(mu, mu2, y, X)))
+        # The refits are sequential (chromosome j starts from chromosome j-1's alpha / eta, FG.R:1253-1275), but the
+        # score-test matrices of chromosome j are output only: they are computed on a host thread while the GPU already
+        # solves chromosome j+1 (numpy and the ctypes call both release the GIL).
+        pending = []
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            for j, (s, e) in enumerate(zip(geno_start_vec(geno), geno_end_vec(geno))):
+                if s == -1 or e == -1:
+                    out["LOCOResult"].append(dict(isLOCO=False))
+                    continue
+                geno.setStartEndIndex(s, e, j)
+                rl = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, loco=True)
+                alpha, eta, mu = rl["alpha"], rl["eta"], rl["mu"]
+                mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau[0])
+                entry = dict(isLOCO=True, coefficients=alpha, linear_predictors=eta, fitted_values=mu,
+                             Y=rl["Y"], residuals=y - mu, cov=rl["cov"])
+                pending.append((entry, pool.submit(ScoreTest_NULL_Model, mu, mu2, y, X)))
+                out["LOCOResult"].append(entry)
+            for entry, fut in pending:
+                entry["obj_noK"] = fut.result()
         if timings is not None:
             timings["loco_s"] = time.time() - t1
     return out
