@@ -151,7 +151,18 @@ static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const
     CUDA_OK(h, cudaMemcpyAsync(d_rng, both.data(), sizeof(int64_t) * 2 * nc, cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     SGB_TRY(k_diag_prep(h, nc, d_rng, d_rng + nc, D1, D2, cst));
-    if (h->engine != SGB_ENGINE_F64) {
+    const bool umma = (h->engine == SGB_ENGINE_UMMA && nc >= 2) || (h->engine == SGB_ENGINE_TENSOR && nc >= 3);   // all chromosomes at once: tcgen05
+    if (umma) {
+        const int kpad = (nc + 1) & ~1;
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, k_umma_limb_bytes(nc, h->sT)));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * kpad));
+        SGB_TRY(k_split_limbs_umma(h, D1, h->Mloc, rowsG, nc, h->d_limb, h->sT, h->d_scal + SC_MULT1, h->d_limbsum));
+        SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_VALUE));
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, kpad, h->d_scal + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, r1, rowsT));
+        SGB_TRY(k_split_limbs_umma(h, D2, h->Mloc, rowsG, nc, h->d_limb, h->sT, h->d_scal + SC_MULT2, h->d_limbsum + 8192));
+        SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_IS2));   // [g==2] plane
+        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, kpad, h->d_scal + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_IS2, r2, rowsT));
+    } else if (h->engine != SGB_ENGINE_F64) {
         SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)nc * nblkM * 2048));
         SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * nc));
         SGB_TRY(k_split_limbs(h, D1, h->Mloc, rowsG, nc, h->d_limb, nblkM, h->d_scal + SC_MULT1, h->d_limbsum));
