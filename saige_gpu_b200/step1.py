@@ -159,6 +159,7 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
                    tolPCG=1e-5, maxiterPCG=500, traceCVcutoff=0.0025, LOCO=False, verbose=False, timings=None):
     """glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549)."""
     y, X, offset, family = fit0["y"], fit0["X"], fit0["offset"], fit0["family"]
+    X = np.asfortranarray(X, dtype=np.float64)      # column-major once: every ABI call takes it without another copy
     n = len(y)
     quant = trait == "quantitative"
     eta = fit0["eta"]
