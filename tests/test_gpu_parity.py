@@ -258,6 +258,35 @@ def test_ai_reml_pieces(pair10k, golden_dir):
     assert ag["nrun_used"] == ao["nrun_used"] and rel(ag["Trace"], ao["Trace"]) < TOL_FIT
 
 
+def test_probe_product_cache_is_transparent(pair10k, golden_dir):
+    """K.U of the Hutchinson probes is reused while U stays bitwise the same (GetTrace re-seeds before every call,
+    FG.cpp:3114); the reuse must not change a single bit, and any other U, engine or genotype set must miss."""
+    from oracle import oracle as O
+    g, o = pair10k
+    yb, _, X = _pheno(golden_dir)
+    fit0 = O.glm_fit(yb, X, O.Binomial)
+    mu = fit0["mu"]; W = mu * (1 - mu); Y = fit0["eta"] + (yb - mu) / W
+    tau = np.array([1.0, 0.2])
+    rc = g.getCoefficients(Y, X, W, tau, 500, 1e-5)
+    U = np.random.default_rng(7).integers(0, 2, size=(o.N, 40)) * 2.0 - 1.0
+    draws = O.make_draw(U)
+    args = (Y, X, W, tau, rc["Sigma_iY"], rc["Sigma_iX"], rc["cov"], 30, 500, 1e-5, 0.0025)
+    g.set_engine("tensor")                       # also drops whatever an earlier test cached
+    g.reset_counters()
+    a1 = g.getAIScore(*args, draws())
+    assert g.counters()["n_probe_product_reuse"] == 0
+    a2 = g.getAIScore(*args, draws())
+    assert g.counters()["n_probe_product_reuse"] == 1
+    for key in ("YPAPY", "Trace", "AI", "PY"):
+        assert np.array_equal(np.asarray(a1[key]), np.asarray(a2[key])), key
+    U2 = U.copy(); U2[17, 3] = -U2[17, 3]        # one flipped sign: a different probe set
+    a3 = g.getAIScore(*args, O.make_draw(U2)())
+    assert g.counters()["n_probe_product_reuse"] == 1
+    assert a3["Trace"] != a1["Trace"]
+    ao = O.getAIScore(o, *args, O.make_draw(U2)())
+    assert rel(a3["Trace"], ao["Trace"]) < TOL_FIT
+
+
 def test_ai_reml_quantitative_pieces(pair10k, golden_dir):
     from oracle import oracle as O
     g, o = pair10k
