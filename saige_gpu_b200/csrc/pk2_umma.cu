@@ -179,14 +179,16 @@ __device__ __forceinline__ void umma_issue_loop(int nsteps, int nb, int N, uint3
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done_bar)) : "memory");
 }
 
-// grid: x = k-chunks, y = 128-row tiles.  block: 192 threads.  dynamic smem: UMMA_STAGES * 128 * N bytes of B stages.
+// grid: x = k-chunks, y = 128-row tiles.  block: 320 threads (8 producer warps, MMA warp, bulk-copy warp).
+// dynamic smem: nb B stages of 256 x N bytes.
 //   P        packed rows (pair-ternary), `stride` bytes each (multiple of 64); rows padded to a multiple of 128
 //   L        limb operand as an image of the smem stage: [k-block of 128][N/8][k/16 (8)][n%8 (8)][k%16 (16)] int8
 //   out      int32 [rows][ldo]; this launch covers columns [n0, n0 + N)
 // Warp-specialised pipeline, UMMA_STAGES deep:
-//   producers : load 32 B of their row (prefetched UMMA_PF steps ahead) -> prmt decode -> tcgen05.st into A stage -> arrive full_a
+//   producers : load 64 B of their row (register ring UMMA_PF steps ahead, L2 prefetch UMMA_L2_AHEAD steps ahead) -> prmt decode
+//               -> tcgen05.st into the A stage -> one arrive per warp on full_a
 //   bulk warp : cp.async.bulk (TMA engine) of the next B stage image -> full_b (expect_tx)
-//   MMA warp  : wait full_a & full_b -> 4 x tcgen05.mma.kind::i8 (K = 32 each) -> tcgen05.commit -> empty (frees both stages)
+//   MMA warp  : wait full_a & full_b -> 8 x tcgen05.mma.kind::i8 (K = 32 each) -> tcgen05.commit -> empty (frees both stages)
 template <int UMMA_STAGES>
 __global__ void __launch_bounds__(UMMA_THREADS, 2)
 pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_total, int ksteps_per_chunk,

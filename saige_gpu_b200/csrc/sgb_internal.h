@@ -169,7 +169,7 @@ int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d
 int k_grid_blocks(sgb_ctx *h, int64_t n);
 #define SGB_PART_BLOCKS 256   // partial-sum slots per column of the deterministic reductions
 
-// crossprod.cu
+// solver.cu / dist.cu / step2.cu / dense_grm.cu
 int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int loco);
 int sgb_gt_times_cols(sgb_ctx *h, const double *D, int k, double *raw);   // raw (ld rowsT) = G^T D (ld rowsG), tensor engine
 int sgb_diag_device(sgb_ctx *h);
