@@ -320,9 +320,8 @@ def main():
     ingest_info = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # setgeno from a host-resident PLINK .bed body (QC + imputation + re-pack + transpose on the GPU), bounded sample
-        from oracle import oracle as O
         n_i, m_i = N, 32768
-        bed_i = O.synth_bed(n_i, m_i, SEED, miss_rate=0.01)
+        bed_i = synth.raw_bed(n_i, m_i, SEED, miss_rate=0.01)
         gi = SaigeB200(device=local_rank)
         gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
         gi.setgeno_mem(bed_i, n_i, 512, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))        # warm-up on the first 512 markers
@@ -335,10 +334,9 @@ def main():
     step2_info = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # BASELINE config 5 row: single-variant score test + SPA through the C ABI from pageable host rows, bounded sample
-        from oracle import oracle as O
         n2, m2 = N, 8192
         rng2 = np.random.default_rng(SEED + 9)
-        bed2 = O.synth_bed(n2, m2, SEED + 9, miss_rate=0.005)
+        bed2 = synth.raw_bed(n2, m2, SEED + 9, miss_rate=0.005)
         X2 = np.column_stack([np.ones(n2), rng2.normal(size=(n2, 2))])
         mu_ = 1 / (1 + np.exp(-(X2 @ np.array([-2.2, 0.4, -0.3]) + rng2.normal(scale=0.3, size=n2))))
         y2 = (rng2.uniform(size=n2) < mu_).astype(np.float64)

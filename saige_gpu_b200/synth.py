@@ -43,3 +43,30 @@ def phenotype(N, seed, prevalence=0.1, gterm=None):
     yq = 0.5 * x1 + 0.3 * x2 + gterm + rng.normal(size=N)
     X = np.column_stack([np.ones(N), x1, x2])
     return y, yq, X
+
+
+def raw_bed(n_samples, n_markers, seed, miss_rate=0.0, n_classes=32, pool_bytes=1 << 20):
+    """Body of a PLINK .bed (SNP-major, ceil(n/4) bytes per marker, no magic bytes) for throughput measurements of the
+    ingest and step-2 paths: markers fall into `n_classes` A1-frequency classes on [0.05, 0.5]; each class owns a pool
+    of bytes whose four 2-bit codes are i.i.d. Hardy-Weinberg draws (00 = hom A1, 10 = het, 11 = hom A2, 01 = missing
+    at `miss_rate`), and a marker row is a slice of its class pool at a random offset.  Fast (a memcpy per marker) and
+    statistically plain; parity tests use the oracle's generator instead."""
+    rng = np.random.default_rng(seed)
+    B0 = (n_samples + 3) // 4
+    pool_bytes = max(pool_bytes, 2 * B0)
+    fs = np.linspace(0.05, 0.5, n_classes)
+    codes = np.arange(256)
+    pools = []
+    for f in fs:
+        p = np.array([f * f, 0.0, 2 * f * (1 - f), (1 - f) ** 2]) * (1.0 - miss_rate)      # code 0, 1, 2, 3
+        p[1] = miss_rate
+        pb = np.ones(256)
+        for j in range(4):
+            pb *= p[(codes >> (2 * j)) & 3]
+        pools.append(rng.choice(256, size=pool_bytes, p=pb / pb.sum()).astype(np.uint8))
+    bed = np.empty(B0 * n_markers, dtype=np.uint8)
+    cls = rng.integers(0, n_classes, size=n_markers)
+    off = rng.integers(0, pool_bytes - B0, size=n_markers)
+    for m in range(n_markers):
+        bed[m * B0:(m + 1) * B0] = pools[cls[m]][off[m]:off[m] + B0]
+    return bed
