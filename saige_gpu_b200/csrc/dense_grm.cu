@@ -181,17 +181,17 @@ __device__ __forceinline__ double4 ldg_f64x4(const double *p)
     return r;
 }
 
-// one group = 4 panel rows: part-A accumulation and the part-B sums of KC columns.  ib = the 4 row indices clamped to
-// N - 1 (rows beyond N hold zeros, so the value read there is irrelevant).
+// one group = 4 panel rows: part-A accumulation and the part-B sums of KC columns.  sbi holds b over the chunk's rows
+// (staged once per CTA: the per-row values are warp-uniform, and 4 x KC uniform global loads per group kept the LSU
+// pipe at 60 %).
 template <int KC, bool PARTB>
-__device__ __forceinline__ void symv_group(const double4 (&kv)[4], const double *__restrict__ B, int64_t N, int64_t ib0, int64_t ib1,
-                                           int64_t ib2, int64_t ib3, const double (*sbn)[DG_BLOCK], int lane, double (&accA)[KC][4],
-                                           double (*sB)[DG_CHUNK], int lrow)
+__device__ __forceinline__ void symv_group(const double4 (&kv)[4], const double (*sbi)[DG_CHUNK], const double (*sbn)[DG_BLOCK], int lane,
+                                           double (&accA)[KC][4], double (*sB)[DG_CHUNK], int lrow)
 {
 #pragma unroll
     for (int c = 0; c < KC; c++) {
-        const double *Bc = B + (int64_t)c * N;
-        const double b0 = __ldg(Bc + ib0), b1 = __ldg(Bc + ib1), b2 = __ldg(Bc + ib2), b3 = __ldg(Bc + ib3);
+        const double2 b01 = *reinterpret_cast<const double2 *>(&sbi[c][lrow]), b23 = *reinterpret_cast<const double2 *>(&sbi[c][lrow + 2]);
+        const double b0 = b01.x, b1 = b01.y, b2 = b23.x, b3 = b23.y;
         accA[c][0] += kv[0].x * b0; accA[c][1] += kv[0].y * b0; accA[c][2] += kv[0].z * b0; accA[c][3] += kv[0].w * b0;
         accA[c][0] += kv[1].x * b1; accA[c][1] += kv[1].y * b1; accA[c][2] += kv[1].z * b1; accA[c][3] += kv[1].w * b1;
         accA[c][0] += kv[2].x * b2; accA[c][1] += kv[2].y * b2; accA[c][2] += kv[2].z * b2; accA[c][3] += kv[2].w * b2;
@@ -222,8 +222,12 @@ __global__ void __launch_bounds__(256, (KC <= 2 ? 2 : 1))
 dense_symv_kernel(const double *__restrict__ pool, const dg_item *__restrict__ items, int64_t item0, const double *__restrict__ B, int64_t N,
                   double *__restrict__ Y)
 {
-    __shared__ __align__(32) double sbn[KC][DG_BLOCK];     // b over the block-row's own samples; later the part-A sums
-    __shared__ double sB[PARTB ? KC : 1][DG_CHUNK];        // part-B sums of the chunk rows (flushed with coalesced atomics)
+    // dynamic shared memory: sbn [KC][128] (b over the block-row's own samples; later the part-A sums) | sbi [KC][512] (b over
+    // the chunk's rows) | sB [KC][512] (part-B sums of the chunk rows, flushed with coalesced atomics; PARTB only)
+    extern __shared__ __align__(32) double symv_smem[];
+    double (*sbn)[DG_BLOCK] = reinterpret_cast<double (*)[DG_BLOCK]>(symv_smem);
+    double (*sbi)[DG_CHUNK] = reinterpret_cast<double (*)[DG_CHUNK]>(symv_smem + KC * DG_BLOCK);
+    double (*sB)[DG_CHUNK] = reinterpret_cast<double (*)[DG_CHUNK]>(symv_smem + KC * DG_BLOCK + KC * DG_CHUNK);
     const dg_item it = items[item0 + blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double *panel = pool + it.off;
@@ -231,6 +235,11 @@ dense_symv_kernel(const double *__restrict__ pool, const dg_item *__restrict__ i
         const int c = e / DG_BLOCK, n = e % DG_BLOCK;
         const int64_t j = (int64_t)it.R * DG_BLOCK + n;
         sbn[c][n] = j < N ? B[(int64_t)c * N + j] : 0.0;
+    }
+    for (int e = threadIdx.x; e < KC * DG_CHUNK; e += 256) {
+        const int c = e / DG_CHUNK, r = e % DG_CHUNK;
+        const int64_t i = (int64_t)it.i0 + r;
+        sbi[c][r] = (r < it.rows && i < N) ? B[(int64_t)c * N + i] : 0.0;
     }
     __syncthreads();
     double accA[KC][4];
@@ -242,7 +251,6 @@ dense_symv_kernel(const double *__restrict__ pool, const dg_item *__restrict__ i
     const int g0 = warp * (DG_CHUNK / 8);
     if (g0 < it.rows) {
         const double *src = panel + ((int64_t)it.i0 + g0) * DG_BLOCK + 4 * lane;
-        const int64_t ibase = (int64_t)it.i0 + g0, last = N - 1;
         double4 bufA[4], bufB[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) bufA[r] = ldg_f64x4(src + (int64_t)r * DG_BLOCK);
@@ -251,18 +259,12 @@ dense_symv_kernel(const double *__restrict__ pool, const dg_item *__restrict__ i
         for (int g = 0; g < DG_CHUNK / 8; g += 8) {
 #pragma unroll
             for (int r = 0; r < 4; r++) bufB[r] = ldg_f64x4(src + (int64_t)(g + 4 + r) * DG_BLOCK);
-            {
-                const int64_t i = ibase + g;
-                symv_group<KC, PARTB>(bufA, B, N, min(i, last), min(i + 1, last), min(i + 2, last), min(i + 3, last), sbn, lane, accA, sB, g0 + g);
-            }
+            symv_group<KC, PARTB>(bufA, sbi, sbn, lane, accA, sB, g0 + g);
             if (g + 8 < DG_CHUNK / 8) {
 #pragma unroll
                 for (int r = 0; r < 4; r++) bufA[r] = ldg_f64x4(src + (int64_t)(g + 8 + r) * DG_BLOCK);
             }
-            {
-                const int64_t i = ibase + g + 4;
-                symv_group<KC, PARTB>(bufB, B, N, min(i, last), min(i + 1, last), min(i + 2, last), min(i + 3, last), sbn, lane, accA, sB, g0 + g + 4);
-            }
+            symv_group<KC, PARTB>(bufB, sbi, sbn, lane, accA, sB, g0 + g + 4);
         }
     }
     // part-A sums of the 8 warps meet in shared memory (sbn is free now)
@@ -295,10 +297,17 @@ template <int KC>
 static void symv_launch(sgb_ctx *h, const sgb_dense *d, const double *B, int64_t N, double *Y)
 {
     // items are ordered [mirrored chunks (part A + B) ..., diagonal blocks (part A only)]
+    const size_t smem_b = sizeof(double) * (size_t)KC * (DG_BLOCK + 2 * DG_CHUNK), smem_a = sizeof(double) * (size_t)KC * (DG_BLOCK + DG_CHUNK);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dense_symv_kernel<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        cudaFuncSetAttribute(dense_symv_kernel<KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        attr_set = true;
+    }
     if (d->n_items_b)
-        dense_symv_kernel<KC, true><<<(unsigned)d->n_items_b, 256, 0, h->stream>>>(d->pool, d->d_items, 0, B, N, Y);
+        dense_symv_kernel<KC, true><<<(unsigned)d->n_items_b, 256, smem_b, h->stream>>>(d->pool, d->d_items, 0, B, N, Y);
     if (d->n_items > d->n_items_b)
-        dense_symv_kernel<KC, false><<<(unsigned)(d->n_items - d->n_items_b), 256, 0, h->stream>>>(d->pool, d->d_items, d->n_items_b, B, N, Y);
+        dense_symv_kernel<KC, false><<<(unsigned)(d->n_items - d->n_items_b), 256, smem_a, h->stream>>>(d->pool, d->d_items, d->n_items_b, B, N, Y);
     h->cnt.n_kernel_launches += 2;
 }
 
