@@ -245,7 +245,9 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         const double tol = 1.220703125e-4;          // eps^0.25 (SAIGE_test.cpp:515-516)
 
         // CGF sums at t over the samples that enter exactly: all samples (SPA) or the non-zero genotypes (SPA_fast)
-        auto cgf = [&](double t, double &k0, double &k1, double &k2) {
+        // K0 is only needed at the root (Lugannani-Rice), the Newton iterations use K1 and K2: one exponential and one
+        // reciprocal per sample there (fp64 exp / log / divide are long software sequences)
+        auto cgf = [&](double t, double &k0, double &k1, double &k2, bool want0) {
             double a0 = 0, a1 = 0, a2 = 0;
             for (int64_t i = tid; i < N; i += S2_THREADS) {
                 const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
@@ -253,13 +255,15 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
                 double gt = (double)g;
                 for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
                 const double mu = M.mu[i];
-                const double e = exp(-gt * t);
+                const double x = gt * t;
+                const double e = exp(-x);
                 const double den = (1.0 - mu) * e + mu;
-                a0 += log(1.0 - mu + mu / e);               // exp(gt t) = 1 / e: one exponential per sample
-                a1 += mu * gt / den;
-                a2 += (1.0 - mu) * mu * gt * gt * e / (den * den);
+                const double r = 1.0 / den;
+                if (want0) a0 += x > 0 ? x + log(den) : log(1.0 - mu + mu / e);      // log(1 - mu + mu exp(x)), overflow-safe
+                a1 += mu * gt * r;
+                a2 += (1.0 - mu) * mu * gt * gt * e * (r * r);
             }
-            k0 = block_sum(a0, red); k1 = block_sum(a1, red); k2 = block_sum(a2, red);
+            k0 = want0 ? block_sum(a0, red) : 0.0; k1 = block_sum(a1, red); k2 = block_sum(a2, red);
             if (fast) { k0 += NAmu * t + 0.5 * NAsigma * t * t; k1 += NAmu + NAsigma * t; k2 += NAsigma; }
         };
         double pside[2]; bool conv_all = true, saddle_all = true;
@@ -270,7 +274,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             else {
                 // getroot_K1[_fast]_Binom (SPA_binary.cpp:70-140, 214-270), init 0, maxiter 1000
                 double t = 0.0, k0, k1, k2, prevJump = INFINITY;
-                cgf(t, k0, k1, k2);
+                cgf(t, k0, k1, k2, false);
                 double K1e = k1 - qq;
                 int rep = 1;
                 while (true) {
@@ -279,14 +283,14 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
                     if (fabs(tnew - t) < tol) { conv = true; break; }
                     if (rep == 1000) { conv = false; break; }
                     double n0, n1, n2;
-                    cgf(tnew, n0, n1, n2);
+                    cgf(tnew, n0, n1, n2, false);
                     double newK1 = n1 - qq;
                     const bool changed = fast ? (K1e * newK1 < 0) : ((K1e > 0) - (K1e < 0)) != ((newK1 > 0) - (newK1 < 0));
                     if (changed) {
                         if (fabs(tnew - t) > prevJump - tol) {
                             const double d = newK1 - K1e;
                             tnew = t + ((d > 0) - (d < 0)) * prevJump / 2;
-                            cgf(tnew, n0, n1, n2);
+                            cgf(tnew, n0, n1, n2, false);
                             newK1 = n1 - qq;
                             prevJump = prevJump / 2;
                         } else prevJump = fabs(tnew - t);
@@ -300,7 +304,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             double k0, k1, k2;
             double ps = 0.0; bool isSaddle = false;
             if (isfinite(root)) {
-                cgf(root, k0, k1, k2);
+                cgf(root, k0, k1, k2, true);
                 const double temp1 = root * qq - k0;
                 if (isfinite(k0) && isfinite(k2) && temp1 >= 0 && k2 >= 0) {
                     const double w = ((root > 0) - (root < 0)) * sqrt(2.0 * temp1), v = root * sqrt(k2);
