@@ -77,3 +77,21 @@ def test_host_helpers_without_device():
     assert abs(cv - (np.std(x, ddof=1) / np.mean(x)) / 4) < 1e-15
     y = np.array([1.0, -1.0, 0.5, 2.0])
     assert L.sgb_inner_product(x.ctypes.data, y.ctypes.data, 4) == float(x @ y)
+
+
+def test_raw_bed_generator_is_plink_shaped():
+    """bench.py feeds the ingest and step-2 samples from saige_gpu_b200.synth.raw_bed (no oracle outside the CPU-baseline
+    legs): right size, Hardy-Weinberg-like code frequencies, the requested missing rate, deterministic per seed."""
+    import numpy as np
+    from saige_gpu_b200 import synth
+    n, m = 4001, 64
+    bed = synth.raw_bed(n, m, seed=5, miss_rate=0.02)
+    B0 = (n + 3) // 4
+    assert bed.dtype == np.uint8 and bed.size == B0 * m
+    assert np.array_equal(bed, synth.raw_bed(n, m, seed=5, miss_rate=0.02))
+    rows = bed.reshape(m, B0)
+    codes = np.stack([(rows >> (2 * j)) & 3 for j in range(4)], axis=2).reshape(m, -1)[:, :n]
+    miss = (codes == 1).mean()
+    assert 0.012 < miss < 0.028
+    f = ((codes == 0) * 2 + (codes == 2)).sum(1) / (2.0 * (codes != 1).sum(1))      # A1 frequency per marker
+    assert f.min() > 0.02 and f.max() < 0.56 and f.std() > 0.05
