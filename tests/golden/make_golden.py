@@ -8,7 +8,8 @@ Fixtures (data, not source) come from /root/reference/src/SAIGE/extdata/input:
   nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr_random1000.{bed,bim,fam} -- 22-chromosome LOCO set
   pheno_1000samples.txt_withdosages_withBothTraitTypes.txt -- phenotypes/covariates of the bundled example
   genotype_100markers.{bed,bim,fam} + ../output/example_binary.{rda,varianceRatio.txt} + ../output/
-  genotype_100markers_marker_plink.txt -- step-2 inputs and the reference's golden result table (32 variants)
+  genotype_100markers_marker_plink.txt -- step-2 inputs and the reference's golden result table (32 variants);
+  genotype_100markers_marker_vcf.txt (LOCO off) and genotype_100markers_marker_bgen.txt (alleles swapped) -- two more
 """
 import os
 import shutil
@@ -32,6 +33,11 @@ FILES = [
     ("../output/example_binary.rda", "example_binary.rda"),
     ("../output/example_binary.varianceRatio.txt", "example_binary.varianceRatio.txt"),
     ("../output/genotype_100markers_marker_plink.txt", "step2_100markers_golden.txt"),
+    # two more golden tables of the same 100 markers and model: the run without LOCO (produced from the VCF copy of the
+    # genotypes) and the run with the alleles the other way round (produced from the BGEN copy: Allele2 is the major
+    # allele there, AF_Allele2 up to 0.99, so every row goes through the reference's flip branch)
+    ("../output/genotype_100markers_marker_vcf.txt", "step2_100markers_golden_noLOCO.txt"),
+    ("../output/genotype_100markers_marker_bgen.txt", "step2_100markers_golden_flipped.txt"),
 ]
 
 if __name__ == "__main__":

@@ -1,7 +1,9 @@
 """Step-2 single-variant score test + SPA pinned on the reference's OWN golden output:
 extdata/output/genotype_100markers_marker_plink.txt (32 variants x 23 columns), produced by the reference from
 extdata/output/example_binary.rda + example_binary.varianceRatio.txt + extdata/input/genotype_100markers.{bed,bim,fam}
-(all committed under tests/golden/ by make_golden.py).  The table prints 6 significant digits, hence 2e-5.
+(all committed under tests/golden/ by make_golden.py).  The table prints 6 significant digits, hence 2e-5.  Two more of the reference's tables on the same
+markers and model are pinned as well: its run without LOCO (genotype_100markers_marker_vcf.txt) and its run with the
+alleles exchanged (genotype_100markers_marker_bgen.txt).
 
 Note: the golden SE of the two SPA-adjusted variants equals |BETA|/|qnorm(p/2)| while this fork's source computes
 qnorm(p, upper tail) (SAIGE_test.cpp:523-526); the fixture wins (se_two_sided=True), the source's variant is kept
@@ -16,19 +18,28 @@ NUMERIC = ["AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "va
            "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het"]
 
 
-def golden_rows(golden_dir):
-    rows = [l.rstrip("\n").split("\t") for l in open(os.path.join(golden_dir, "step2_100markers_golden.txt"))]
+def golden_rows(golden_dir, name="step2_100markers_golden.txt"):
+    rows = [l.rstrip("\n").split("\t") for l in open(os.path.join(golden_dir, name))]
     return [dict(zip(rows[0], r)) for r in rows[1:]]
 
 
-def oracle_rows(golden_dir, **kw):
+def swap_alleles(bed):
+    """The same genotypes with A1 and A2 exchanged: homozygote codes 00 <-> 11, het (10) and missing (01) unchanged."""
+    lo, hi = bed & 0x55, (bed >> 1) & 0x55
+    hom = ~(lo ^ hi) & 0x55
+    return bed ^ (hom | (hom << 1))
+
+
+def oracle_rows(golden_dir, LOCO=True, swapped=False, **kw):
     from oracle import oracle as O
     from oracle import step2_oracle as S2
     from saige_gpu_b200.rdata import load_rda
     mod = load_rda(os.path.join(golden_dir, "example_binary.rda"))["modglmm"]
-    M = S2.read_model(mod, chrom=1, LOCO=True)
+    M = S2.read_model(mod, chrom=1, LOCO=LOCO)
     M["varRatio"] = float(open(os.path.join(golden_dir, "example_binary.varianceRatio.txt")).read().split()[0])
     bed, N0, M0, _ = O.read_bed(os.path.join(golden_dir, "step2_100markers"))
+    if swapped:
+        bed = swap_alleles(bed)
     fam = [l.split()[1] for l in open(os.path.join(golden_dir, "step2_100markers.fam"))]
     bim = [l.split() for l in open(os.path.join(golden_dir, "step2_100markers.bim"))]
     pos = np.array([fam.index(s) for s in M["sampleID"]])
@@ -104,6 +115,74 @@ def test_gpu_step2_reproduces_reference_golden_table(golden_dir, tmp_path):
             for r in spa:
                 assert abs(r["SE"] - abs(r["BETA"]) / stats.norm.isf(r["p.value"])) < 1e-9 * r["SE"]
     g.close()
+
+
+ALL_NUMERIC_ORACLE = (("AC_Allele2", "AC_Allele2"), ("AF_Allele2", "AF_Allele2"), ("MissingRate", "MissingRate"), ("BETA", "BETA"),
+                      ("SE", "SE"), ("Tstat", "Tstat"), ("var", "var"), ("p.value", "p_value"), ("p.value.NA", "p_value_NA"),
+                      ("AF_case", "AF_case"), ("AF_ctrl", "AF_ctrl"), ("N_case", "N_case"), ("N_ctrl", "N_ctrl"))
+
+
+@pytest.mark.parametrize("name,kw", [("step2_100markers_golden_noLOCO.txt", dict(LOCO=False)),
+                                     ("step2_100markers_golden_flipped.txt", dict(LOCO=True, swapped=True))])
+def test_oracle_reproduces_two_more_reference_tables(golden_dir, name, kw):
+    """genotype_100markers_marker_vcf.txt is the reference's run WITHOUT LOCO on the same markers and model;
+    genotype_100markers_marker_bgen.txt is its run with Allele1 / Allele2 exchanged (AF_Allele2 up to 0.99: every row
+    takes the flip branch of imputeGenoAndFlip, UTIL.cpp:58-135, and comes back with the sign of BETA / Tstat turned)."""
+    gold = golden_rows(golden_dir, name)
+    mine = oracle_rows(golden_dir, **kw)
+    assert [g["MarkerID"] for g in gold] == list(mine.keys()) and len(gold) == 32
+    for g in gold:
+        r = mine[g["MarkerID"]]
+        for col, oc in ALL_NUMERIC_ORACLE:
+            gv, mv = float(g[col]), float(r[oc])
+            assert abs(mv - gv) <= TOL_PRINT * max(abs(gv), 1e-300) + 1e-300, (g["MarkerID"], col, mv, gv)
+        assert str(r["Is_SPA"]).lower() == g["Is.SPA"]
+    if kw.get("swapped"):
+        base = {g["MarkerID"]: g for g in golden_rows(golden_dir)}
+        for g in gold:                      # the reference's own two tables are mirror images of each other
+            b = base[g["MarkerID"]]
+            assert abs(float(g["BETA"]) + float(b["BETA"])) <= TOL_PRINT * abs(float(b["BETA"]))
+            assert abs(float(g["AF_Allele2"]) + float(b["AF_Allele2"]) - 1.0) < 1e-5
+            assert (g["Allele1"], g["Allele2"]) == (b["Allele2"], b["Allele1"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,loco,swapped", [("step2_100markers_golden_noLOCO.txt", False, False),
+                                               ("step2_100markers_golden_flipped.txt", True, True)])
+def test_gpu_step2_reproduces_two_more_reference_tables(golden_dir, tmp_path, name, loco, swapped):
+    import shutil
+    from oracle import oracle as O
+    from saige_gpu_b200 import SaigeB200, step2
+    p = os.path.join(golden_dir, "step2_100markers")
+    q = str(tmp_path / "markers")
+    shutil.copyfile(p + ".fam", q + ".fam")
+    if swapped:
+        bed, _, _, _ = O.read_bed(p)
+        with open(q + ".bed", "wb") as f:
+            f.write(bytes([0x6C, 0x1B, 0x01]))
+            f.write(swap_alleles(bed).tobytes())
+        with open(q + ".bim", "w") as f:
+            for l in open(p + ".bim"):
+                t = l.split()
+                f.write("\t".join([t[0], t[1], t[2], t[3], t[5], t[4]]) + "\n")
+    else:
+        shutil.copyfile(p + ".bed", q + ".bed")
+        shutil.copyfile(p + ".bim", q + ".bim")
+    g = SaigeB200(device=0)
+    try:
+        rows = step2.SPAGMMATtest(g, q + ".bed", q + ".bim", q + ".fam", os.path.join(golden_dir, "example_binary.rda"),
+                                  os.path.join(golden_dir, "example_binary.varianceRatio.txt"), chrom="1", LOCO=loco, min_MAC=20)
+    finally:
+        g.close()
+    gold = golden_rows(golden_dir, name)
+    assert [r["MarkerID"] for r in rows] == [x["MarkerID"] for x in gold]
+    for r, x in zip(rows, gold):
+        for col in ("CHR", "POS", "Allele1", "Allele2"):
+            assert str(r[col]) == x[col]
+        for col in NUMERIC:
+            gv, mv = float(x[col]), float(r[col])
+            assert abs(mv - gv) <= TOL_PRINT * max(abs(gv), 1e-300) + 1e-300, (r["MarkerID"], col, mv, gv)
+        assert ("true" if r["Is.SPA"] else "false") == x["Is.SPA"]
 
 
 @pytest.mark.gpu
