@@ -38,6 +38,11 @@ FILES = [
     # allele there, AF_Allele2 up to 0.99, so every row goes through the reference's flip branch)
     ("../output/genotype_100markers_marker_vcf.txt", "step2_100markers_golden_noLOCO.txt"),
     ("../output/genotype_100markers_marker_bgen.txt", "step2_100markers_golden_flipped.txt"),
+    # a genome-wide-significant variant (p = 3.5e-7 after SPA): one-marker VCF of 10,000 samples, its model and result
+    ("nfam_1000_MAF0.2_nMarker1_nseed200.vcf", "positive_signal_1marker.vcf"),
+    ("../output/example_binary_positive_signal.rda", "positive_signal.rda"),
+    ("../output/example_binary_positive_signal.varianceRatio.txt", "positive_signal.varianceRatio.txt"),
+    ("../output/example_binary_positive_signal.assoc.step2.txt", "positive_signal_golden.txt"),
 ]
 
 if __name__ == "__main__":

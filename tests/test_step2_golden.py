@@ -185,6 +185,78 @@ def test_gpu_step2_reproduces_two_more_reference_tables(golden_dir, tmp_path, na
         assert ("true" if r["Is.SPA"] else "false") == x["Is.SPA"]
 
 
+def positive_signal_inputs(golden_dir):
+    """The reference's genome-wide-significant example: a one-marker VCF over 10,000 samples of which the model uses the
+    first 1,000 (the identity fast path with a .fam longer than the model), example_binary_positive_signal.rda and its
+    result row."""
+    lines = [l for l in open(os.path.join(golden_dir, "positive_signal_1marker.vcf")) if not l.startswith("##")]
+    ids = lines[0].rstrip("\n").split("\t")[9:]
+    rec = lines[1].rstrip("\n").split("\t")
+
+    def alt_count(gt):
+        a = gt.replace("|", "/").split("/")
+        return -1 if "." in a else sum(int(x) for x in a)
+    g = np.array([alt_count(x) for x in rec[9:]], dtype=np.int64)
+    gold_lines = open(os.path.join(golden_dir, "positive_signal_golden.txt")).read().splitlines()
+    gold = dict(zip(gold_lines[0].split("\t"), gold_lines[1].split("\t")))
+    vr = float(open(os.path.join(golden_dir, "positive_signal.varianceRatio.txt")).read().split()[0])
+    return ids, rec[:5], g, gold, vr
+
+
+# BETA / SE of this row come from the reference's Firth refit (is_Firth_beta, not built: DESIGN.md 5b); everything the
+# score test and the saddle-point approximation produce is compared
+POSITIVE_COLS = (("AC_Allele2", "AC_Allele2"), ("AF_Allele2", "AF_Allele2"), ("MissingRate", "MissingRate"), ("Tstat", "Tstat"),
+                 ("var", "var"), ("p.value", "p_value"), ("p.value.NA", "p_value_NA"), ("AF_case", "AF_case"), ("AF_ctrl", "AF_ctrl"),
+                 ("N_case", "N_case"), ("N_ctrl", "N_ctrl"))
+
+
+def test_oracle_reproduces_the_positive_signal_row(golden_dir):
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200.rdata import load_rda
+    ids, _, g, gold, vr = positive_signal_inputs(golden_dir)
+    mod = load_rda(os.path.join(golden_dir, "positive_signal.rda"))["modglmm"]
+    M = S2.read_model(mod, chrom=1, LOCO=True)
+    M["varRatio"] = vr
+    where = {s: i for i, s in enumerate(ids)}
+    pos = np.array([where[s] for s in M["sampleID"]])
+    assert len(ids) == 10000 and np.array_equal(pos, np.arange(1000))      # the model's samples are a prefix of the file's
+    r = S2.test_marker(M, g[pos].astype(np.float64), min_mac=0.5)
+    assert r["Is_SPA"] and gold["Is.SPA"] == "true"
+    assert float(gold["p.value"]) < 5e-7 < float(gold["p.value.NA"]) * 10          # SPA moves the p-value by 3x at 1e-7
+    for col, oc in POSITIVE_COLS:
+        gv, mv = float(gold[col]), float(r[oc])
+        assert abs(mv - gv) <= TOL_PRINT * max(abs(gv), 1e-300) + 1e-300, (col, mv, gv)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_positive_signal_row(golden_dir, tmp_path):
+    from saige_gpu_b200 import SaigeB200, step2
+    ids, rec, g, gold, _ = positive_signal_inputs(golden_dir)
+    q = str(tmp_path / "one")
+    n = len(ids)
+    code = np.array([3, 2, 0, 1], dtype=np.uint8)[np.where(g < 0, 3, g)]       # A1 = ALT: 0 copies -> 11, 1 -> 10, 2 -> 00, missing -> 01
+    code = np.concatenate([code, np.zeros((-n) % 4, dtype=np.uint8)]).reshape(-1, 4)
+    row = (code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)).astype(np.uint8)
+    with open(q + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + row.tobytes())
+    with open(q + ".bim", "w") as f:
+        f.write("\t".join([rec[0], rec[2], "0", rec[1], rec[4], rec[3]]) + "\n")      # A1 = ALT, A2 = REF
+    with open(q + ".fam", "w") as f:
+        for s in ids:
+            f.write("%s %s 0 0 0 -9\n" % (s, s))
+    gpu = SaigeB200(device=0)
+    try:
+        rows = step2.SPAGMMATtest(gpu, q + ".bed", q + ".bim", q + ".fam", os.path.join(golden_dir, "positive_signal.rda"),
+                                  os.path.join(golden_dir, "positive_signal.varianceRatio.txt"), chrom="1", LOCO=True, min_MAC=0.5)
+    finally:
+        gpu.close()
+    assert len(rows) == 1 and rows[0]["MarkerID"] == gold["MarkerID"] and rows[0]["Is.SPA"]
+    assert (str(rows[0]["Allele1"]), str(rows[0]["Allele2"])) == (gold["Allele1"], gold["Allele2"])
+    for col, _ in POSITIVE_COLS:
+        gv, mv = float(gold[col]), float(rows[0][col])
+        assert abs(mv - gv) <= TOL_PRINT * max(abs(gv), 1e-300) + 1e-300, (col, mv, gv)
+
+
 @pytest.mark.gpu
 def test_gpu_step2_synthetic_vs_oracle():
     """Bigger synthetic check with missing calls, allele flips, sample subset/reorder, binary + quantitative traits."""
