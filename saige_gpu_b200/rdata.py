@@ -18,6 +18,7 @@ import numpy as np
 NILVALUE_SXP, GLOBALENV_SXP, EMPTYENV_SXP, BASEENV_SXP = 254, 253, 242, 241
 REFSXP, PERSISTSXP, PACKAGESXP, NAMESPACESXP, BASENAMESPACE_SXP, MISSINGARG_SXP, UNBOUNDVALUE_SXP = 255, 247, 250, 249, 247, 251, 252
 ALTREP_SXP, ATTRLISTSXP, ATTRLANGSXP = 238, 239, 240
+BCODESXP, BCREPDEF, BCREPREF = 21, 244, 243
 NILSXP, SYMSXP, LISTSXP, CLOSXP, ENVSXP, PROMSXP, LANGSXP, CHARSXP, LGLSXP, INTSXP, REALSXP, CPLXSXP, STRSXP, VECSXP, EXPRSXP, RAWSXP, S4SXP = (
     0, 1, 2, 3, 4, 5, 6, 9, 10, 13, 14, 15, 16, 19, 20, 24, 25)
 
@@ -138,11 +139,52 @@ class _Reader:
         elif typ in (7, 8):      # SPECIALSXP / BUILTINSXP
             n = self.int()
             val = RObject("builtin " + self.bytes(n).decode())
+        elif typ == 22:          # EXTPTRSXP: a reference object holding (protected, tag)
+            val = RObject("externalptr")
+            self.refs.append(val)
+            self.item()
+            self.item()
+        elif typ == 23:          # WEAKREFSXP
+            val = RObject("weakref")
+            self.refs.append(val)
+        elif typ == BCODESXP:    # byte-compiled closure bodies (older model files keep family functions): parsed, not kept
+            self._bc_reps = [None] * self.int()
+            self._bc1()
+            val = RObject("bytecode")
         else:
             raise ValueError("unsupported SEXP type %d at byte %d" % (typ, self.p))
         if has_attr:
             attr = self.item()
         return self._with_attr(val, attr)
+
+    def _bc1(self):
+        # ReadBC1 (R serialize.c): the code vector, then the constant pool
+        self.item()
+        for _ in range(self.int()):
+            t = self.int()
+            if t == BCODESXP:
+                self._bc1()
+            elif t in (LANGSXP, LISTSXP, BCREPDEF, BCREPREF, ATTRLANGSXP, ATTRLISTSXP):
+                self._bclang(t)
+            else:
+                self.item()          # the type word is a prefix; a complete item follows
+
+    def _bclang(self, t):
+        # ReadBCLang: language objects of the constant pool, with back references between them
+        if t == BCREPREF:
+            self.int()
+            return
+        if t not in (BCREPDEF, LANGSXP, LISTSXP, ATTRLANGSXP, ATTRLISTSXP):
+            self.item()
+            return
+        if t == BCREPDEF:
+            self.int()               # position in the reps table
+            t = self.int()
+        if t in (ATTRLANGSXP, ATTRLISTSXP):
+            self.item()              # attributes
+        self.item()                  # tag
+        self._bclang(self.int())     # car
+        self._bclang(self.int())     # cdr
 
     def _altrep(self, cls, state):
         if cls in ("compact_intseq", "compact_realseq"):

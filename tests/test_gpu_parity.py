@@ -332,9 +332,12 @@ def test_full_step1_matches_oracle(pair10k, golden_dir, trait):
     vg, _ = step1.extractVarianceRatio(g, mg, fam_g, order)
     assert rel(vg, vo) < TOL_FIT
     if trait == "binary":
-        # scale-of-answer sanity against the reference's bundled example_binary.rda (other marker set, R's RNG):
-        # theta = (1, 0.3327), intercept-only alpha = -2.52; same cohort and phenotype here.
-        assert mg["theta"][0] == 1.0 and 0.05 < mg["theta"][1] < 1.5
+        # the reference's own result for this cohort / phenotype / covariates (extdata/output/example.rda):
+        # theta = (1, 0.32472724), alpha = (-2.97337569, 0.7511719, 0.91698671).  alpha is RNG-free up to the PCG
+        # tolerance; tau carries the Monte-Carlo error of R's 30 probes vs ours (tests/test_oracle_golden.py).
+        ref_alpha = np.array([-2.97337569, 0.7511719, 0.91698671])
+        assert mg["theta"][0] == 1.0 and abs(mg["theta"][1] - 0.32472724) / 0.32472724 < 0.08
+        assert np.max(np.abs(mg["coefficients"] - ref_alpha) / np.abs(ref_alpha)) < 5e-3
 
 
 @pytest.mark.parametrize("shape", [(5, 9), (37, 50), (255, 257), (256, 1024), (1025, 777), (3001, 130)])

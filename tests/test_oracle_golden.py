@@ -133,9 +133,13 @@ def test_loco_consistency(chr22):
     assert np.allclose(tot, o._crossprod_range(0, o.M, b), rtol=1e-10, atol=1e-9)
 
 
-def test_step1_scale_of_answer(o10k, golden_dir):
-    """Same cohort and phenotype as the reference's bundled example; different marker set and RNG, so only the
-    scale of the answer is comparable: example_binary.rda has theta = (1, 0.3327), varianceRatio.txt 0.9402."""
+def test_step1_against_the_reference_example_model(o10k, golden_dir):
+    """extdata/output/example.rda is the reference's own step-1 result for THIS cohort, phenotype (y_binary ~ x1 + x2)
+    and, judging by the agreement, this 10k-marker set: theta = (1, 0.32472724), coefficients = (-2.97337569, 0.7511719,
+    0.91698671) (read with saige_gpu_b200.rdata in the build container; the file itself is not committed).  The fixed
+    effects are RNG-free up to the PCG tolerance and must agree closely; tau carries the Monte-Carlo error of a 30-probe
+    Hutchinson trace drawn from R's RNG there and from numpy's here, a few percent.  example_binary.rda (intercept only,
+    128k-marker set whose .bed is not in the mount) has theta = (1, 0.3327), varianceRatio 0.9402."""
     rows = [l.split() for l in open(os.path.join(golden_dir, "pheno_1000samples.txt"))]
     col = {h: i for i, h in enumerate(rows[0])}
     y = np.array([float(r[col["y_binary"]]) for r in rows[1:]])
@@ -145,6 +149,27 @@ def test_step1_scale_of_answer(o10k, golden_dir):
     fit0 = O.glm_fit(y, X, O.Binomial)
     m = O.glmmkin_ai_PCG(o10k, fit0, (0, 0), U, trait="binary")
     assert m["converged"] and m["theta"][0] == 1.0
-    assert 0.2 < m["theta"][1] < 0.5                         # reference: 0.3327 / 0.3350 on its 128k-marker set
+    ref_theta1, ref_alpha = 0.32472724, np.array([-2.97337569, 0.7511719, 0.91698671])
+    assert np.max(np.abs(m["coefficients"] - ref_alpha) / np.abs(ref_alpha)) < 5e-3        # measured 1.9e-3
+    assert abs(m["theta"][1] - ref_theta1) / ref_theta1 < 0.08                             # measured 3.4e-2 (probe RNG)
     vr, _ = O.extractVarianceRatio(o10k, m, O.Binomial, np.random.default_rng(1).permutation(o10k.M)[:200])
-    assert 0.85 < vr < 1.05                                  # reference: 0.9402
+    assert 0.85 < vr < 1.05                                  # reference: 0.9402 (example_binary), 0.9417 (example_binary_new)
+
+
+def test_rda_reader_reads_every_reference_model():
+    """Older SAIGE model files carry byte-compiled closures and external pointers (glm objects); the reader has to get
+    past them.  Runs where the reference tree is mounted (the build container), skipped elsewhere."""
+    import glob
+    from saige_gpu_b200.rdata import load_rda
+    ref = "/root/reference/src/SAIGE/extdata/output"
+    files = [f for f in sorted(glob.glob(os.path.join(ref, "*.rda"))) if os.path.getsize(f) > 0]
+    if not files:
+        pytest.skip("reference tree not mounted")
+    want = {"example.rda": (1.0, 0.32472724), "example_binary.rda": (1.0, 0.33267713), "example_binary_fullGRM.rda": (1.0, 0.33499435),
+            "example_binary_positive_signal.rda": (1.0, 0.5576753), "example_quantitative_fullGRM.rda": (0.20143682, 0.48348784)}
+    for f in files:
+        m = load_rda(f)["modglmm"]
+        assert len(m["sampleID"]) in (20, 980, 1000) and len(m["theta"]) == 2
+        if os.path.basename(f) in want:
+            assert np.allclose(m["theta"], want[os.path.basename(f)], rtol=1e-7), f
+    assert len(files) >= 19
