@@ -111,14 +111,44 @@ def updateChrStartEndIndexVec(geno, chrVec):
     return LOCO, start, end
 
 
-class ProbeStream:
-    """Stand-in for R's RNG on the trace estimator: GetTrace re-seeds to 200 on every call (FG.cpp:3114) and then
-    draws 2*rbinom(N,1,0.5)-1 per run, so every call sees the same probe sequence.  Here the sequence is a fixed
-    N x nmax Rademacher matrix; `fresh()` returns a draw(n) callable that starts again at column 0."""
+def r_unif_rand(seed, n):
+    """n successive unif_rand() values of R's default generator (Mersenne-Twister) after set.seed(seed): the initial
+    scrambling of RNG_Init (50 + 625 steps of seed = 69069 seed + 1), the standard MT19937 stream scaled by
+    2.3283064365386963e-10, and R's fixup into the open interval.  set.seed(1); runif(3) = 0.2655087 0.3721239 0.5728534."""
+    s = np.uint32(seed)
+    words = np.empty(625, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        for _ in range(50):
+            s = np.uint32(np.uint32(69069) * s + np.uint32(1))
+        for j in range(625):
+            s = np.uint32(np.uint32(69069) * s + np.uint32(1))
+            words[j] = s
+    bg = np.random.MT19937()
+    st = bg.state
+    st["state"]["key"] = words[1:].copy()          # i_seed[0] is mti (forced to 624 by FixupSeeds), the rest is mt[]
+    st["state"]["pos"] = 624
+    bg.state = st
+    u = bg.random_raw(n).astype(np.float64) * 2.3283064365386963e-10
+    i2 = 2.328306437080797e-10
+    u = np.where(u <= 0.0, 0.5 * i2, u)
+    return np.where(1.0 - u <= 0.0, 1.0 - 0.5 * i2, u)
 
-    def __init__(self, N, nmax=130, seed=200):
-        rng = np.random.default_rng(seed)
-        self.U = np.asfortranarray(rng.integers(0, 2, size=(N, nmax)).astype(np.float64) * 2.0 - 1.0)
+
+class ProbeStream:
+    """The probe sequence of the trace estimator: GetTrace re-seeds to 200 on every call (FG.cpp:3114) and then draws
+    2*rbinom(N,1,0.5)-1 per run (`nb`, FG.cpp:3052), so every call sees the same sequence.  Here the sequence is a fixed
+    N x nmax Rademacher matrix; `fresh()` returns a draw(n) callable that starts again at column 0.
+    rng="numpy": numpy's default generator (what the parity tests share with the oracle);
+    rng="R": bit-for-bit the stream R produces -- rbinom(1, 0.5) consumes one unif_rand() and returns u >= 0.5
+    (nmath/rbinom.c, inversion branch), run r / sample i is draw r*N + i."""
+
+    def __init__(self, N, nmax=130, seed=200, rng="numpy"):
+        if rng == "R":
+            u = r_unif_rand(seed, N * nmax)
+            self.U = np.asfortranarray((2.0 * (u >= 0.5) - 1.0).reshape(nmax, N).T)
+        else:
+            gen = np.random.default_rng(seed)
+            self.U = np.asfortranarray(gen.integers(0, 2, size=(N, nmax)).astype(np.float64) * 2.0 - 1.0)
 
     def fresh(self):
         pos = [0]

@@ -95,3 +95,17 @@ def test_raw_bed_generator_is_plink_shaped():
     assert 0.012 < miss < 0.028
     f = ((codes == 0) * 2 + (codes == 2)).sum(1) / (2.0 * (codes != 1).sum(1))      # A1 frequency per marker
     assert f.min() > 0.02 and f.max() < 0.56 and f.std() > 0.05
+
+
+def test_r_probe_stream_matches_r():
+    """ProbeStream(rng="R") reproduces R's set.seed + rbinom(N, 1, 0.5) stream.  Known-answer check on R's documented
+    output  set.seed(1); runif(5) -> 0.2655087 0.3721239 0.5728534 0.9082078 0.2016819."""
+    import numpy as np
+    from saige_gpu_b200 import step1
+    assert np.allclose(step1.r_unif_rand(1, 5), [0.2655087, 0.3721239, 0.5728534, 0.9082078, 0.2016819], atol=5e-8)
+    u = step1.r_unif_rand(200, 12)
+    ps = step1.ProbeStream(4, nmax=3, seed=200, rng="R")
+    assert ps.U.shape == (4, 3) and set(np.unique(ps.U)) <= {-1.0, 1.0}
+    assert np.array_equal(ps.U[:, 0], 2.0 * (u[:4] >= 0.5) - 1.0) and np.array_equal(ps.U[:, 2], 2.0 * (u[8:12] >= 0.5) - 1.0)
+    d = ps.fresh()
+    assert np.array_equal(d(2), ps.U[:, :2]) and np.array_equal(d(1), ps.U[:, 2:3])

@@ -134,11 +134,11 @@ def test_loco_consistency(chr22):
 
 
 def test_step1_against_the_reference_example_model(o10k, golden_dir):
-    """extdata/output/example.rda is the reference's own step-1 result for THIS cohort, phenotype (y_binary ~ x1 + x2)
-    and, judging by the agreement, this 10k-marker set: theta = (1, 0.32472724), coefficients = (-2.97337569, 0.7511719,
-    0.91698671) (read with saige_gpu_b200.rdata in the build container; the file itself is not committed).  The fixed
-    effects are RNG-free up to the PCG tolerance and must agree closely; tau carries the Monte-Carlo error of a 30-probe
-    Hutchinson trace drawn from R's RNG there and from numpy's here, a few percent.  example_binary.rda (intercept only,
+    """extdata/output/example.rda is the reference's own step-1 result for THIS cohort and phenotype (y_binary ~ x1 + x2):
+    theta = (1, 0.32472724), coefficients = (-2.97337569, 0.7511719, 0.91698671) (read with saige_gpu_b200.rdata in the
+    build container; the file itself is not committed; marker set and version are not recorded).  The fixed effects
+    depend little on the probes and must agree closely; tau carries the Monte-Carlo error of a 30-probe Hutchinson
+    trace: 0.3137 with numpy probes, 0.3368 with R's own stream (step1.ProbeStream(rng="R")), the reference in between.  example_binary.rda (intercept only,
     128k-marker set whose .bed is not in the mount) has theta = (1, 0.3327), varianceRatio 0.9402."""
     rows = [l.split() for l in open(os.path.join(golden_dir, "pheno_1000samples.txt"))]
     col = {h: i for i, h in enumerate(rows[0])}
