@@ -160,10 +160,17 @@ int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *
                         const int32_t *pos_in_fam);
 /* mainMarkerInCPP loop body (Main.cpp:229-520) for n_markers raw PLINK rows (ceil(n_fam/4) bytes each, A1 = ALT):
  * getOneMarker -> filter -> imputeGenoAndFlip (best_guess) -> scoreTestFast -> SPA / SPA_fast (SAIGE_test.cpp:212-292,
- * 345-640).  out[n_markers x 20] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
- * p.value, p.value.NA, Is.SPA, AF_case, AF_ctrl, N_case, N_ctrl, N_case_hom, N_case_het, N_ctrl_hom, N_ctrl_het, var2.
+ * 345-640).  out[n_markers x 22] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
+ * p.value, p.value.NA, Is.SPA, AF_case, AF_ctrl, N_case, N_ctrl, N_case_hom, N_case_het, N_ctrl_hom, N_ctrl_het, var2,
+ * Is.Firth, Firth converged.
  * se_two_sided = 1: SE of SPA-adjusted variants = |BETA| / |qnorm(p/2)| (matches the reference's bundled golden tables);
  * 0: |BETA| / qnorm(p, upper) as this fork's source has it (SAIGE_test.cpp:523-526). */
+/* is_Firth_beta / pCutoffforFirth (SAIGE_test.cpp:573-633; fast_logistf_fit_simple :893-986): variants of a binary trait
+ * whose final p-value is <= p_cutoff get Firth's bias-reduced effect size from a two-column penalised logistic refit
+ * [1, gtilde] with the null model's offset (N doubles, NULL = zeros; readInGLMM.R:99-160).  se_from_fit = 1: SE is the
+ * refit's own standard error (what the reference's bundled positive-signal result holds); 0: |BETA| / |qnorm| of the
+ * p-value as this fork's source computes it (:632).  Off after sgb_step2_set_model. */
+int sgb_step2_set_firth(sgb_ctx *h, int enable, double p_cutoff, const double *offset, int se_from_fit);
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
 

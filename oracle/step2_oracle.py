@@ -13,8 +13,10 @@ Restates, in numpy fp64:
 
 Pinned by the reference's own golden table extdata/output/genotype_100markers_marker_plink.txt (32 variants, produced
 from extdata/output/example_binary.rda + extdata/input/genotype_100markers.{bed,bim,fam}) -- tests/test_step2_golden.py.
-Not implemented (not exercised by that fixture): efficient-resampling exact test for MAC <= 4 (ER_binary_func.cpp),
-Firth correction, conditional analysis, sparse-GRM variance, categorical variance ratios.
+Firth's bias-reduced effect size (is_Firth_beta, SAIGE_test.cpp:573-633, fast_logistf_fit_simple :893-986) is pinned by the
+BETA / SE of extdata/output/example_binary_positive_signal.assoc.step2.txt.
+Not implemented: efficient-resampling exact test for MAC <= 4 (ER_binary_func.cpp), conditional analysis, sparse-GRM
+variance, categorical variance ratios.
 """
 import numpy as np
 from scipy import stats
@@ -37,7 +39,14 @@ def read_model(modglmm, chrom=None, LOCO=True):
     trait = m["traitType"][0] if isinstance(m["traitType"], list) else str(m["traitType"])
     tau = np.asarray(m["theta"], dtype=np.float64).ravel()
     mu2 = mu * (1 - mu) if trait == "binary" else np.full(len(mu), 1.0 / tau[0])
-    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, y=np.asarray(m["y"], dtype=np.float64).ravel(),
+    # offset of the Firth refit (readInGLMM.R:99-101,134-160): the chromosome's own when LOCO stored one, else the model's, else 0
+    offset = m.get("offset")
+    if LOCO and chrom is not None and bool(np.asarray(m["LOCO"]).ravel()[0]):
+        lr = m["LOCOResult"][int(chrom) - 1]
+        if isinstance(lr, dict) and lr.get("offset") is not None:
+            offset = lr["offset"]
+    offset = np.zeros(len(mu)) if offset is None else np.asarray(offset, dtype=np.float64).ravel()
+    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, offset=offset, y=np.asarray(m["y"], dtype=np.float64).ravel(),
                 X=np.asarray(m["X"], dtype=np.float64), XV=np.asarray(noK["XV"]), XVX=np.asarray(noK["XVX"]),
                 XXVX_inv=np.asarray(noK["XXVX_inv"]), XVX_inv_XV=np.asarray(noK["XVX_inv_XV"]),
                 S_a=np.asarray(noK["S_a"]).ravel(), sampleID=list(m["sampleID"]))
@@ -159,7 +168,42 @@ def score_test_fast(M, G, idx):
     return dict(Beta=beta, seBeta=abs(beta) / np.sqrt(abs(stat)), pval=pval, Tstat=S, var1=var1, var2=var2)
 
 
-def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=2.0, se_two_sided=True):
+def firth_fit(gt, y, offset, maxit=50, maxstep=15, xconv=1e-5, gconv=1e-5):
+    """fast_logistf_fit_simple (SAIGE_test.cpp:893-986) for x = [1, gtilde], init 0: Firth's penalised-likelihood Newton
+    iteration with the hat values of sqrt(W) x.  Returns (beta_G, sebeta_G, converged)."""
+    x = np.column_stack([np.ones(len(gt)), gt])
+    beta = np.zeros(2)
+    pi = 1.0 / (np.exp(-x @ beta - offset) + 1.0)
+    it, conv, cov = 0, False, np.full((2, 2), np.nan)
+    while it <= maxit:
+        w = pi * (1 - pi)
+        xw = x * np.sqrt(w)[:, None]
+        fisher = xw.T @ xw
+        try:
+            cov = np.linalg.inv(fisher)
+        except np.linalg.LinAlgError:
+            break
+        if not np.all(np.isfinite(cov)) or np.linalg.det(fisher) <= 0:
+            break
+        h = np.einsum("ij,jk,ik->i", xw, cov, xw)
+        u = x.T @ ((y - pi) + h * (0.5 - pi))
+        delta = cov @ u
+        mx = np.max(np.abs(delta)) / maxstep
+        if mx > 1:
+            delta = delta / mx
+        it += 1
+        beta = beta + delta
+        pi = 1.0 / (np.exp(-x @ beta - offset) + 1.0)
+        if it == maxit or (np.max(np.abs(delta)) <= xconv and np.all(np.abs(u) <= gconv)):
+            conv = True
+            break
+    if np.any(np.isnan(cov)):
+        return np.nan, np.nan, conv
+    return float(beta[1]), float(np.sqrt(cov[1, 1])), conv
+
+
+def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=2.0, se_two_sided=True, is_Firth_beta=False,
+                pCutoffforFirth=0.01, firth_se_from_fit=True):
     """One pass of the mainMarkerInCPP loop body (Main.cpp:229-520).  Returns None when the marker is filtered."""
     test_marker.__test__ = False
     n = len(Graw)
@@ -201,12 +245,21 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
             # SE from the SPA p-value: the reference's bundled golden table corresponds to |qnorm(p/2)| (upstream SAIGE);
             # this fork's source has qnorm(p, upper tail) (SAIGE_test.cpp:523-526) -> se_two_sided=False
             se = abs(st["Beta"]) / abs(stats.norm.isf(pspa / 2 if se_two_sided else pspa))
+    beta, is_firth, firth_conv = st["Beta"], False, False
+    if is_Firth_beta and M["trait"] == "binary" and pval <= pCutoffforFirth:
+        # SAIGE_test.cpp:573-633.  firth_se_from_fit: SE = the fit's own sqrt(cov[1,1]) (what the reference's bundled
+        # positive-signal result holds); otherwise |beta| / |qnorm| of the p-value as this fork's source has it (:632)
+        gt = G - M["XXVX_inv"] @ (M["XV"] @ G)
+        beta, se_fit, firth_conv = firth_fit(gt, M["y"], M["offset"])
+        is_firth = True
+        se = se_fit if firth_se_from_fit else abs(beta) / abs(stats.norm.isf(pval / 2 if se_two_sided else pval))
     sgn = -1.0 if flip else 1.0
     y = M["y"]
     case, ctrl = y == 1, y == 0
     afc, aft = G[case].mean() / 2, G[ctrl].mean() / 2
     if flip:
         afc, aft = 1 - afc, 1 - aft
-    return dict(AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * st["Beta"], SE=se,
+    return dict(AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
                 Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa,
+                Is_Firth=is_firth, Firth_converged=firth_conv,
                 AF_case=afc, AF_ctrl=aft, N_case=int(case.sum()), N_ctrl=int(ctrl.sum()))

@@ -341,7 +341,7 @@ class SaigeB200:
     # ---- step 2: setSAIGEobjInCPP + mainMarkerInCPP ----
     STEP2_COLUMNS = ("tested", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA",
                      "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het",
-                     "var2")
+                     "var2", "Is.Firth", "Firth.converged")
 
     def setSAIGEobjInCPP(self, model, varRatio, SPAcutoff, pos_in_fam):
         """model: dict with mu, res, mu2, y, X, XVX, XXVX_inv, XVX_inv_XV, S_a, tau, trait (readInGLMM.R:39-170)."""
@@ -355,6 +355,13 @@ class SaigeB200:
         self._ck(self._L.sgb_step2_set_model(self._h, N, p, int(model["trait"] == "binary"), *[_p(a) for a in arrs],
                                              float(varRatio), float(SPAcutoff), _p(pos)))
         self._step2_N = N
+
+    def setFirth(self, is_Firth_beta, pCutoffforFirth=0.01, offset=None, se_from_fit=True):
+        """is_Firth_beta / pCutoffforFirth of SPAGMMATtest: Firth's bias-reduced BETA for binary-trait variants with
+        p <= cutoff; offset = the null model's offset vector (None = zeros)."""
+        off = None if offset is None else _f64(np.asarray(offset, dtype=np.float64).reshape(-1))
+        self._ck(self._L.sgb_step2_set_firth(self._h, int(bool(is_Firth_beta)), float(pCutoffforFirth),
+                                             None if off is None else _p(off), int(bool(se_from_fit))))
 
     def mainMarkerInCPP(self, bed_rows, n_fam, n_markers, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, se_two_sided=True):
         bed = np.ascontiguousarray(bed_rows, dtype=np.uint8)

@@ -3,7 +3,8 @@
 // Replaces, per marker, the body of mainMarkerInCPP (Main.cpp:229-520): PlinkClass::getOneMarker (PLINK.cpp:164-300,
 // alt-first), the MAF/MAC/missing-rate filter, imputeGenoAndFlip (UTIL.cpp:58-135, best_guess), scoreTestFast
 // (SAIGE_test.cpp:212-292) and, when |T|/sqrt(var1) > SPAcutoff on a binary trait, getMarkerPval's SPA / SPA_fast
-// branch (SAIGE_test.cpp:345-640, SPA.cpp:20-185, SPA_binary.cpp:21-330).  All arithmetic fp64, like the reference.
+// branch (SAIGE_test.cpp:345-640, SPA.cpp:20-185, SPA_binary.cpp:21-330) and, when asked for, Firth's bias-reduced
+// effect size of significant variants (fast_logistf_fit_simple, SAIGE_test.cpp:893-986).  All arithmetic fp64, like the reference.
 //
 // One CTA per variant.  The raw PLINK row (2 bits per .fam sample) is staged in shared memory; the per-sample model
 // vectors (mu, mu2, res, X, XVX_inv_XV, XXVX_inv: N x (3p + 3) doubles) are read through L2 by every CTA.
@@ -22,7 +23,7 @@
 
 #define S2_MAXP 16
 #define S2_THREADS 256
-#define S2_NOUT 20      // doubles per variant in the result table (see include/saige_b200.h)
+#define S2_NOUT 22      // doubles per variant in the result table (see include/saige_b200.h)
 
 struct s2_model {
     int64_t N; int p; int binary;
@@ -33,6 +34,10 @@ struct s2_model {
     int identity;            // pos[i] == i: the model's samples are the first N rows of the .fam, in order
     const uint32_t *ycase;   // identity only: bit 2j of word w set when sample 16w + j is a case (y == 1)
     double ncase_tot;        // number of cases in the model
+    // Firth's bias-reduced effect size for significant variants (is_Firth_beta, SAIGE_test.cpp:573-633)
+    const double *offset;    // N, the null model's offset (zeros when absent)
+    int firth, firth_se_from_fit;
+    double firth_cutoff;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sm)
@@ -329,15 +334,62 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             }
         }
     }
+    // ---- Firth's penalised-likelihood refit of the effect size (binary traits, p <= pCutoffforFirth) ----
+    // x = [1, gtilde], offset = the null model's; Newton steps with the modified score x^T((y - pi) + h (0.5 - pi)), h the hat
+    // values of sqrt(W) x; every quantity is a 2 x 2 / 2-vector block reduction over the samples (SAIGE_test.cpp:893-986)
+    double BetaOut = Beta, isFirth = 0.0, firthConv = 0.0;
+    if (M.firth && M.binary && pval <= M.firth_cutoff) {
+        isFirth = 1.0;
+        double b0 = 0.0, b1 = 0.0, c00 = nan(""), c01 = nan(""), c11 = nan("");
+        int iter = 0;
+        while (iter <= 50) {
+            double f00 = 0, f01 = 0, f11 = 0;
+            for (int64_t i = tid; i < N; i += S2_THREADS) {
+                const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
+                double gt = (double)g;
+                for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
+                const double pi = 1.0 / (exp(-(b0 + b1 * gt) - M.offset[i]) + 1.0), w = pi * (1.0 - pi);
+                f00 += w; f01 += w * gt; f11 += w * gt * gt;
+            }
+            f00 = block_sum(f00, red); f01 = block_sum(f01, red); f11 = block_sum(f11, red);
+            const double det = f00 * f11 - f01 * f01;
+            if (!(det > 0.0) || !(f00 > 0.0)) break;                      // inv_sympd fails
+            c00 = f11 / det; c01 = -f01 / det; c11 = f00 / det;
+            double u0 = 0, u1 = 0;
+            for (int64_t i = tid; i < N; i += S2_THREADS) {
+                const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
+                double gt = (double)g;
+                for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
+                const double pi = 1.0 / (exp(-(b0 + b1 * gt) - M.offset[i]) + 1.0), w = pi * (1.0 - pi);
+                const double hat = w * (c00 + 2.0 * c01 * gt + c11 * gt * gt);
+                const double r = (M.y[i] - pi) + hat * (0.5 - pi);
+                u0 += r; u1 += gt * r;
+            }
+            u0 = block_sum(u0, red); u1 = block_sum(u1, red);
+            double d0 = c00 * u0 + c01 * u1, d1 = c01 * u0 + c11 * u1;
+            const double mx = fmax(fabs(d0), fabs(d1)) / 15.0;
+            if (mx > 1.0) { d0 /= mx; d1 /= mx; }
+            iter++;
+            b0 += d0; b1 += d1;
+            if (iter == 50 || (fmax(fabs(d0), fabs(d1)) <= 1e-5 && fabs(u0) <= 1e-5 && fabs(u1) <= 1e-5)) { firthConv = 1.0; break; }
+        }
+        if (isnan(c00) || isnan(c01) || isnan(c11)) { BetaOut = nan(""); seBeta = nan(""); }
+        else {
+            BetaOut = b1;
+            // SE: the fit's own (what the reference's bundled positive-signal result holds) or |beta| / |qnorm| of the p-value
+            // as this fork's source has it (SAIGE_test.cpp:632)
+            seBeta = M.firth_se_from_fit ? sqrt(c11) : fabs(b1) / fabs(normcdfinv(se_two_sided ? pval * 0.5 : pval));
+        }
+    }
     if (tid == 0) {
         const double sgn = flip ? -1.0 : 1.0;
         double afc = ncase > 0 ? gcase / ncase / 2.0 : nan(""), aft = nctrl > 0 ? gctrl / nctrl / 2.0 : nan("");
         if (flip) { afc = 1.0 - afc; aft = 1.0 - aft; case_hom = ncase - case_het - case_hom; ctrl_hom = nctrl - ctrl_het - ctrl_hom; }
         o[0] = 1.0;            // tested
         o[1] = altCount; o[2] = altFreq; o[3] = missingRate;
-        o[4] = sgn * Beta; o[5] = seBeta; o[6] = sgn * S; o[7] = var1; o[8] = pval; o[9] = pval_noadj; o[10] = isSPA;
+        o[4] = sgn * BetaOut; o[5] = seBeta; o[6] = sgn * S; o[7] = var1; o[8] = pval; o[9] = pval_noadj; o[10] = isSPA;
         o[11] = afc; o[12] = aft; o[13] = ncase; o[14] = nctrl; o[15] = case_hom; o[16] = case_het; o[17] = ctrl_hom; o[18] = ctrl_het;
-        o[19] = var2;
+        o[19] = var2; o[20] = isFirth; o[21] = firthConv;
     }
 }
 
@@ -349,6 +401,7 @@ struct sgb_step2 {
     double *d_vec = nullptr;      // mu | mu2 | res | y | X | A | XXVXi
     int32_t *d_pos = nullptr;
     uint32_t *d_ycase = nullptr;
+    double *d_offset = nullptr;
     uint8_t *d_bed = nullptr; size_t bed_bytes = 0;
     double *d_out = nullptr; size_t out_elems = 0;
     uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
@@ -397,6 +450,22 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     CUDA_OK(h, cudaMalloc((void **)&s->d_ycase, sizeof(uint32_t) * yc.size()));
     CUDA_OK(h, cudaMemcpy(s->d_ycase, yc.data(), sizeof(uint32_t) * yc.size(), cudaMemcpyHostToDevice));
     M.ycase = s->d_ycase; M.ncase_tot = ncase;
+    if (s->d_offset) { cudaFree(s->d_offset); s->d_offset = nullptr; }
+    CUDA_OK(h, cudaMalloc((void **)&s->d_offset, sizeof(double) * N));
+    CUDA_OK(h, cudaMemset(s->d_offset, 0, sizeof(double) * N));
+    M.offset = s->d_offset; M.firth = 0; M.firth_se_from_fit = 1; M.firth_cutoff = 0.01;
+    return 0;
+}
+
+extern "C" int sgb_step2_set_firth(sgb_ctx *h, int enable, double p_cutoff, const double *offset, int se_from_fit)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    sgb_step2 *s = h->step2;
+    if (!s || !s->d_vec) return sgb_fail(h, "step2: call sgb_step2_set_model first");
+    if (enable && !(p_cutoff >= 0.0 && p_cutoff <= 1.0)) return sgb_fail(h, "step2: pCutoffforFirth=%g out of [0,1]", p_cutoff);
+    if (offset) CUDA_OK(h, cudaMemcpy(s->d_offset, offset, sizeof(double) * s->M.N, cudaMemcpyHostToDevice));
+    else CUDA_OK(h, cudaMemset(s->d_offset, 0, sizeof(double) * s->M.N));
+    s->M.firth = enable ? 1 : 0; s->M.firth_cutoff = p_cutoff; s->M.firth_se_from_fit = se_from_fit ? 1 : 0;
     return 0;
 }
 
@@ -486,6 +555,7 @@ void sgb_step2_free(sgb_ctx *h)
     if (s->d_vec) cudaFree(s->d_vec);
     if (s->d_pos) cudaFree(s->d_pos);
     if (s->d_ycase) cudaFree(s->d_ycase);
+    if (s->d_offset) cudaFree(s->d_offset);
     if (s->d_bed) cudaFree(s->d_bed);
     if (s->d_out) cudaFree(s->d_out);
     for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }

@@ -36,7 +36,14 @@ def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
     trait = m["traitType"][0] if isinstance(m["traitType"], list) else str(m["traitType"])
     tau = np.asarray(m["theta"], dtype=np.float64).ravel()
     mu2 = mu * (1 - mu) if trait == "binary" else np.full(len(mu), 1.0 / tau[0])
-    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, y=np.asarray(m["y"], dtype=np.float64).ravel(),
+    # offset of the Firth refit (readInGLMM.R:99-101, 134-160): the chromosome's own when LOCO stored one, else the model's
+    offset = m.get("offset")
+    if LOCO and has_loco and chrom != "":
+        c = int(str(chrom).replace("chr", ""))
+        if 1 <= c <= 22 and isinstance(m["LOCOResult"][c - 1], dict) and m["LOCOResult"][c - 1].get("offset") is not None:
+            offset = m["LOCOResult"][c - 1]["offset"]
+    offset = np.zeros(len(mu)) if offset is None else np.asarray(offset, dtype=np.float64).ravel()
+    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, offset=offset, y=np.asarray(m["y"], dtype=np.float64).ravel(),
                 X=np.asarray(m["X"], dtype=np.float64), XVX=np.asarray(noK["XVX"], dtype=np.float64),
                 XXVX_inv=np.asarray(noK["XXVX_inv"], dtype=np.float64),
                 XVX_inv_XV=np.asarray(noK["XVX_inv_XV"], dtype=np.float64), S_a=np.asarray(noK["S_a"], dtype=np.float64).ravel(),
@@ -54,7 +61,8 @@ def Get_Variance_Ratio(varianceRatioFile):
 
 def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioFile, SAIGEOutputFile=None, chrom="",
                  LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
-                 is_output_moreDetails=True, se_two_sided=True, rank=0, world=1):
+                 is_output_moreDetails=True, se_two_sided=True, rank=0, world=1, is_Firth_beta=False, pCutoffforFirth=0.01,
+                 firth_se_from_fit=True):
     """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the .bim
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
@@ -68,6 +76,7 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
         raise ValueError("%d samples of the null model are not in %s" % (len(missing), famFile))
     pos = np.array([where[s] for s in model["sampleID"]], dtype=np.int32)
     geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
+    geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
     raw = np.fromfile(bedFile, dtype=np.uint8)
     if raw[0] != 0x6C or raw[1] != 0x1B or raw[2] != 0x01:
         raise ValueError("%s is not a SNP-major PLINK .bed" % bedFile)
@@ -88,6 +97,7 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
             for name, v in zip(geno.STEP2_COLUMNS[1:19], r[1:19]):
                 row[name] = v
             row["Is.SPA"] = bool(r[10])
+            row["Is.Firth"], row["Firth.converged"] = bool(r[20]), bool(r[21])
             rows.append(row)
     if SAIGEOutputFile:
         cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]

@@ -203,9 +203,10 @@ def positive_signal_inputs(golden_dir):
     return ids, rec[:5], g, gold, vr
 
 
-# BETA / SE of this row come from the reference's Firth refit (is_Firth_beta, not built: DESIGN.md 5b); everything the
-# score test and the saddle-point approximation produce is compared
-POSITIVE_COLS = (("AC_Allele2", "AC_Allele2"), ("AF_Allele2", "AF_Allele2"), ("MissingRate", "MissingRate"), ("Tstat", "Tstat"),
+# BETA / SE of this row come from the reference's Firth refit (is_Firth_beta = TRUE, pCutoffforFirth 0.01): bias-reduced
+# effect size 1.05265 against the score-test estimate 1.15015, SE = the fit's own standard error
+POSITIVE_COLS = (("AC_Allele2", "AC_Allele2"), ("AF_Allele2", "AF_Allele2"), ("MissingRate", "MissingRate"), ("BETA", "BETA"), ("SE", "SE"),
+                 ("Tstat", "Tstat"),
                  ("var", "var"), ("p.value", "p_value"), ("p.value.NA", "p_value_NA"), ("AF_case", "AF_case"), ("AF_ctrl", "AF_ctrl"),
                  ("N_case", "N_case"), ("N_ctrl", "N_ctrl"))
 
@@ -220,8 +221,10 @@ def test_oracle_reproduces_the_positive_signal_row(golden_dir):
     where = {s: i for i, s in enumerate(ids)}
     pos = np.array([where[s] for s in M["sampleID"]])
     assert len(ids) == 10000 and np.array_equal(pos, np.arange(1000))      # the model's samples are a prefix of the file's
-    r = S2.test_marker(M, g[pos].astype(np.float64), min_mac=0.5)
-    assert r["Is_SPA"] and gold["Is.SPA"] == "true"
+    r = S2.test_marker(M, g[pos].astype(np.float64), min_mac=0.5, is_Firth_beta=True, pCutoffforFirth=0.01)
+    assert r["Is_SPA"] and gold["Is.SPA"] == "true" and r["Is_Firth"] and r["Firth_converged"]
+    plain = S2.test_marker(M, g[pos].astype(np.float64), min_mac=0.5)
+    assert abs(plain["BETA"] - 1.15015) < 1e-5 and not plain["Is_Firth"]            # Tstat / var, what the row would hold without Firth
     assert float(gold["p.value"]) < 5e-7 < float(gold["p.value.NA"]) * 10          # SPA moves the p-value by 3x at 1e-7
     for col, oc in POSITIVE_COLS:
         gv, mv = float(gold[col]), float(r[oc])
@@ -247,10 +250,12 @@ def test_gpu_reproduces_the_positive_signal_row(golden_dir, tmp_path):
     gpu = SaigeB200(device=0)
     try:
         rows = step2.SPAGMMATtest(gpu, q + ".bed", q + ".bim", q + ".fam", os.path.join(golden_dir, "positive_signal.rda"),
-                                  os.path.join(golden_dir, "positive_signal.varianceRatio.txt"), chrom="1", LOCO=True, min_MAC=0.5)
+                                  os.path.join(golden_dir, "positive_signal.varianceRatio.txt"), chrom="1", LOCO=True, min_MAC=0.5,
+                                  is_Firth_beta=True, pCutoffforFirth=0.01)
     finally:
         gpu.close()
     assert len(rows) == 1 and rows[0]["MarkerID"] == gold["MarkerID"] and rows[0]["Is.SPA"]
+    assert rows[0]["Is.Firth"] and rows[0]["Firth.converged"]
     assert (str(rows[0]["Allele1"]), str(rows[0]["Allele2"])) == (gold["Allele1"], gold["Allele2"])
     for col, _ in POSITIVE_COLS:
         gv, mv = float(gold[col]), float(rows[0][col])
@@ -310,4 +315,26 @@ def test_gpu_step2_synthetic_vs_oracle():
                 assert abs(got[col] - r[oc]) <= 1e-6 * abs(r[oc]) + 1e-300, (trait, m, col, got[col], r[oc])
             assert bool(got["Is.SPA"]) == bool(r["Is_SPA"])
         assert ntest > 300 and nflip > 50 and (nspa > 5 or trait == "quantitative")
+        # Firth's effect size for the variants with p <= 0.2 (a wide cutoff so that dozens of refits run), both SE forms
+        offset = rng.normal(scale=0.2, size=N)
+        M["offset"] = offset
+        for from_fit in (True, False):
+            g.setFirth(True, 0.2, offset, se_from_fit=from_fit)
+            outf = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 5.0, 0.15)
+            nfirth = 0
+            for m in range(nm):
+                r = S2.test_marker(M, S2.plink_marker(bed, n_fam, m, pos), min_mac=5.0, is_Firth_beta=True, pCutoffforFirth=0.2,
+                                   firth_se_from_fit=from_fit)
+                if r is None:
+                    continue
+                got = dict(zip(g.STEP2_COLUMNS, outf[m]))
+                assert bool(got["Is.Firth"]) == bool(r["Is_Firth"]) == (trait == "binary" and r["p_value"] <= 0.2), (trait, m)
+                if r["Is_Firth"]:
+                    nfirth += 1
+                    assert bool(got["Firth.converged"]) == bool(r["Firth_converged"])
+                for col, oc in (("BETA", "BETA"), ("SE", "SE"), ("p.value", "p_value")):
+                    assert abs(got[col] - r[oc]) <= 1e-6 * abs(r[oc]) + 1e-300, (trait, m, col, got[col], r[oc], from_fit)
+            assert nfirth > 30 or trait == "quantitative"
+        g.setFirth(False)
+        assert np.array_equal(np.nan_to_num(g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 5.0, 0.15)), np.nan_to_num(out))
         g.close()
