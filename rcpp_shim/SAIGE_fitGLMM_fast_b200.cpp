@@ -50,6 +50,9 @@ static sgb_ctx *ctx()
     return g_h;
 }
 
+// the same handle for the step-2 shim (SAIGE_step2_b200.cpp)
+sgb_ctx *saige_b200_ctx() { return ctx(); }
+
 // R's RNG is the probe source (set_seed(200) + rbinom, SAIGE_fitGLMM_fast.cpp:3040-3054, 3134-3137)
 static int draw_probes(void *, int64_t n, int count, double *out)
 {
