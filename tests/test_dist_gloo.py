@@ -81,3 +81,52 @@ def test_shards_are_balanced_per_chromosome():
             assert max(per) - min(per) <= sharding.SHARD_BLOCK
         sizes = [len(sharding.local_markers(M, r, world)) for r in range(world)]
         assert sum(sizes) == M and max(sizes) - min(sizes) <= sharding.SHARD_BLOCK
+
+
+def test_step2_variant_sharding_is_a_partition(tmp_path):
+    """Config 5 shards variants over ranks with no collective: SPAGMMATtest(rank, world) tests one contiguous range per
+    rank and the parts, concatenated in rank order, are the single-rank table.  Host logic only: the GPU call is replaced
+    by a stub that tags every row with its marker index."""
+    sys.path.insert(0, ROOT)
+    from saige_gpu_b200 import step2
+    gd = os.path.join(ROOT, "tests", "golden")
+    p = os.path.join(gd, "step2_100markers")
+    n_fam = len(open(p + ".fam").read().splitlines())
+    B0 = (n_fam + 3) // 4
+    body = np.fromfile(p + ".bed", dtype=np.uint8)[3:]
+
+    class Stub:
+        STEP2_COLUMNS = ("tested", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA",
+                         "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het",
+                         "var2", "Is.Firth", "Firth.converged")
+        calls = []
+
+        def setSAIGEobjInCPP(self, *a):
+            pass
+
+        def setFirth(self, *a, **k):
+            pass
+
+        def mainMarkerInCPP(self, rows, nf, nm, *a):
+            flat = np.asarray(rows).reshape(-1)[:nm * B0]
+            # recover where this contiguous chunk starts in the file body; keep every third marker "untested"
+            m0 = next(k for k in range(100 - nm + 1) if np.array_equal(body[k * B0:(k + nm) * B0], flat))
+            out = np.zeros((nm, len(self.STEP2_COLUMNS)))
+            for j in range(nm):
+                out[j, 0] = 0.0 if (m0 + j) % 3 == 0 else 1.0
+                out[j, 1] = m0 + j
+            self.calls.append(nm)
+            return out
+
+    def run(rank, world, chunk):
+        return step2.SPAGMMATtest(Stub(), p + ".bed", p + ".bim", p + ".fam", os.path.join(gd, "example_binary.rda"),
+                                  os.path.join(gd, "example_binary.varianceRatio.txt"), chrom="1", LOCO=True,
+                                  markers_per_chunk=chunk, rank=rank, world=world)
+    full = run(0, 1, 7)
+    assert [r["MarkerID"] for r in full] == ["rs%d" % (m + 1) for m in range(100) if m % 3]
+    for world in (2, 3, 8):
+        parts = [run(r, world, 7) for r in range(world)]
+        ids = [x["MarkerID"] for part in parts for x in part]
+        assert ids == [r["MarkerID"] for r in full]
+        sizes = [len(part) for part in parts]
+        assert max(sizes) - min(sizes) <= (100 + world - 1) // world      # contiguous, near-equal ranges
