@@ -372,12 +372,21 @@ def main():
         model = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim, LOCO=loco)
         g.sync()
         wall = max_over_ranks(time.time() - ts)
+        # variance ratio (FG.R:2152-2423): markers with MAC >= 20 in a fixed random order, the
+        # getSigma_G solves of a round as ONE multi-column PCG; timed apart from the fit
+        tv = time.time()
+        order = np.random.default_rng(SEED + 6).permutation(g.M)[:400]
+        vr, vr_list = step1.extractVarianceRatio(g, model, step1.Binomial, order)
+        vr_markers = len(vr_list)
+        g.sync()
+        vr_s = max_over_ranks(time.time() - tv)
         c = g.counters()
         step1_info = {"wall_s": wall, "load_synth_s": t_load, "tau": [float(v) for v in model["theta"]],
                       "converged": bool(model["converged"]), "outer_iterations": len(model["tau_path"]) - 1,
                       "pcg_solves": c["n_pcg_solves"], "pcg_iterations": c["n_pcg_iterations"],
                       "product_columns": c["n_crossprod_columns"], "products": c["n_crossprod_calls"], "LOCO": bool(loco),
                       "fit_s": tim.get("fit_s"), "loco_refits_s": tim.get("loco_s"),
+                      "variance_ratio": float(vr), "variance_ratio_markers": int(vr_markers), "variance_ratio_s": vr_s,
                       "note": "binary trait, 3 fixed-effect columns, nrun=30 probes, tolPCG=1e-5, full GRM, "
                               "22 leave-one-chromosome-out refits included; genotypes already resident (load_synth_s apart)"}
 
