@@ -475,7 +475,7 @@ static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n
     for (auto &s : sh) sTmax = std::max(sTmax, s.sT);
     int8_t *img = nullptr;
     int32_t *acc = nullptr;
-    const size_t img_bytes = k_umma_limb_bytes(16, sTmax);
+    const size_t img_bytes = k_umma_image_bytes(DG_BLOCK, sTmax);
     const size_t acc_elems = (size_t)round_up64(N, DG_BLOCK) * DG_BLOCK;
     CUDA_OK(h, cudaMalloc((void **)&img, img_bytes));
     CUDA_OK(h, cudaMalloc((void **)&acc, sizeof(int32_t) * acc_elems));
@@ -500,7 +500,7 @@ static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n
                 syrk_image_kernel<<<(unsigned)cdiv64(nblk * 1024, 256), 256, 0, h->stream>>>(s.gt, s.sT, DG_BLOCK * R, s.dig + (size_t)l * s.sT * 4, nblk, img);
                 h->cnt.n_kernel_launches++;
                 h->umma_accumulate = q > 0;            // shards after the first add to the int32 sums
-                rc = k_pk2_umma(h, s.gt, s.sT, rows, s.sT, img, 16, acc, SGB_PLANE_VALUE);
+                rc = k_pk2_umma_rows(h, s.gt, s.sT, rows, s.sT, img, DG_BLOCK, acc, SGB_PLANE_VALUE);
                 h->umma_accumulate = false;
                 d->tensor_ops += 2.0 * (double)rows * DG_BLOCK * (double)(s.sT * 4);
             }

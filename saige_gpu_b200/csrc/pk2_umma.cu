@@ -335,47 +335,80 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
 }
 
 // Limb split for the UMMA engine: V[len x k] -> stage images + per-column multiplier + exact limb column sums.
+// The B operand is s8, so a limb carries 8 bits: q = round(v 2^(53-E)) (|q| <= 2^54) is written with UMMA_LIMBS = 7 balanced
+// base-256 digits (7 x 8 = 56 bits, the same range as the 8 x 7 bits of the mma.sync engine; both engines hold the same
+// integer q, hence bit-identical results) -- 1/8 fewer accumulator columns and tensor work per right-hand side.
+// Accumulator column of (column c, limb l) is n = 7 c + l; the image keeps 8 n-rows per 1 KB core-matrix group.
 // One thread per (128-genotype block, TMEM column 0..31): the 4 genotype slots whose k-values share that column.
-__global__ void split_limbs_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int k, int ncolpad, int64_t nblk,
+#define UMMA_LIMBS 7
+__global__ void split_limbs_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int k, int ngroups, int64_t nblk,
                                         const unsigned long long *__restrict__ mx, int8_t *__restrict__ L,
                                         double *__restrict__ mult, int32_t *__restrict__ limbsum)
 {
-    const int c = blockIdx.y;                         // column (0..ncolpad-1); columns >= k are zero padding
+    const int c = blockIdx.y;                         // column 0..k-1
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t blk = u >> 5;
     const int col = (int)(u & 31), w = col >> 2, q = col & 3;
     const bool inb = blk < nblk;
-    const bool real = c < k;
-    unsigned long long mb = real ? mx[c] : 0ull;
+    unsigned long long mb = mx[c];
     int E = (int)((mb >> 52) & 0x7FF) - 1023;
     if (E < -1000) E = -1000;
     if (E > 1000) E = 1000;
-    if (u == 0 && real) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
+    if (u == 0) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
     // slot s of this column is genotype 16 w + {0,8,1,9}[q] + 2 s of the block (the order decode produces)
     const int64_t i0 = blk * UMMA_KBLK + 16 * w + ((q & 1) ? 8 : 0) + ((q & 2) ? 1 : 0);
     long long qv[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         int64_t i = i0 + 2 * s;
-        qv[s] = (inb && real && i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E)) : 0;
+        qv[s] = (inb && i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E)) : 0;
     }
-    uint32_t *base = reinterpret_cast<uint32_t *>(L + (blk * (int64_t)ncolpad + c) * 1024 + w * 128 + 4 * q);
 #pragma unroll
-    for (int l = 0; l < SGB_LIMBS; l++) {
+    for (int l = 0; l < UMMA_LIMBS; l++) {
         uint32_t word = 0;
         int ssum = 0;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            int d = (int)((qv[s] + 64) & 127) - 64;
-            qv[s] = (qv[s] - d) >> 7;
+            int d = (int)((qv[s] + 128) & 255) - 128;
+            qv[s] = (qv[s] - d) >> 8;
             word |= (uint32_t)(d & 255) << (8 * s);
             ssum += d;
         }
-        if (inb) base[l * 4] = word;                   // +16 bytes per limb row
+        const int n = UMMA_LIMBS * c + l;
+        if (inb) *reinterpret_cast<uint32_t *>(L + (blk * (int64_t)ngroups + (n >> 3)) * 1024 + w * 128 + (n & 7) * 16 + 4 * q) = word;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        if ((threadIdx.x & 31) == 0 && ssum && real) atomicAdd(&limbsum[c * SGB_LIMBS + l], ssum);
+        if ((threadIdx.x & 31) == 0 && ssum) atomicAdd(&limbsum[c * UMMA_LIMBS + l], ssum);
     }
+}
+
+// raw[r + c*ld] = (c0 * limbsum - sum_l acc[r][7c+l] 256^l) * mult[c];  the 7 accumulators are reset for the next product
+__global__ void recombine_umma_kernel(int32_t *__restrict__ acc, int64_t rows, int k, int npad, const double *__restrict__ mult,
+                                      const int32_t *__restrict__ limbsum, int c0, double *__restrict__ raw, int64_t ld)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * k) return;
+    int64_t r = idx / k;
+    int c = (int)(idx - r * k);
+    int32_t *p = acc + r * npad + UMMA_LIMBS * c;
+    long long x[UMMA_LIMBS];
+#pragma unroll
+    for (int l = 0; l < UMMA_LIMBS; l++) { x[l] = (long long)c0 * limbsum[c * UMMA_LIMBS + l] - (long long)p[l]; p[l] = 0; }
+    // exact integer sum (up to ~2^81), then ONE correctly rounded conversion: keep 62 leading bits plus a sticky bit, so the
+    // int64 -> fp64 conversion rounds like the exact value would (the mma.sync engine adds two exact halves, also correctly
+    // rounded: both engines return the same bits)
+    const long long l4 = x[0] + (x[1] << 8) + (x[2] << 16) + (x[3] << 24);
+    const long long h3 = x[4] + (x[5] << 8) + (x[6] << 16);
+    const __int128 T = ((__int128)h3 << 32) + (__int128)l4;
+    const bool neg = T < 0;
+    const unsigned __int128 a = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
+    const unsigned long long ahi = (unsigned long long)(a >> 64), alo = (unsigned long long)a;
+    const int bits = ahi ? 128 - __clzll((long long)ahi) : (alo ? 64 - __clzll((long long)alo) : 0);
+    const int shift = bits > 62 ? bits - 62 : 0;
+    unsigned long long m = (unsigned long long)(a >> shift);
+    if (shift && (a & ((((unsigned __int128)1) << shift) - 1))) m |= 1ull;
+    double v = scalbn((double)m, shift);
+    raw[r + (int64_t)c * ld] = (neg ? -v : v) * mult[c];
 }
 
 __global__ void colmax_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, unsigned long long *__restrict__ mx)
@@ -403,46 +436,62 @@ __global__ void colmax_umma_kernel(const double *__restrict__ V, int64_t len, in
                                                 cudaGetErrorString(e__));                               \
     } while (0)
 
-// bytes of the UMMA limb operand for k columns over `kbytes` packed bytes per row
-size_t k_umma_limb_bytes(int k, int64_t kbytes)
+static inline int umma_npad(int k) { return (UMMA_LIMBS * k + 15) & ~15; }        // accumulator columns: a multiple of 16
+
+// bytes of the UMMA limb operand for k columns (or `nrows` accumulator columns) over `kbytes` packed bytes per row
+size_t k_umma_image_bytes(int nrows, int64_t kbytes)
 {
-    int ncolpad = (k + 1) & ~1;
-    return (size_t)(kbytes / 32) * ncolpad * 1024;        // kbytes is a multiple of 64 => an even number of 128-genotype blocks
+    return (size_t)(kbytes / 32) * (size_t)(nrows / 8) * 1024;        // kbytes is a multiple of 64 => an even number of 128-genotype blocks
 }
+size_t k_umma_limb_bytes(int k, int64_t kbytes) { return k_umma_image_bytes(umma_npad(k), kbytes); }
 
 int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t kbytes, double *d_mult,
                        int32_t *d_limbsum)
 {
     unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);
     if (k > 1024) return sgb_fail(h, "too many columns (%d)", k);
-    const int ncolpad = (k + 1) & ~1;
+    const int npad = umma_npad(k);
     const int64_t nblk = kbytes / 32;
     CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
-    CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * SGB_LIMBS * k, h->stream));
+    CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * UMMA_LIMBS * k, h->stream));
+    // the padding rows (7k .. npad-1) of the last core-matrix group(s) must read as zero limbs
+    if (npad != UMMA_LIMBS * k) CUDA_OK(h, cudaMemsetAsync(L, 0, k_umma_image_bytes(npad, kbytes), h->stream));
     int gx = (int)cdiv64(len, 256 * 8);
     if (gx > 1024) gx = 1024;
     if (gx < 1) gx = 1;
     colmax_umma_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
     UMMA_LAUNCH_CHECK(h);
-    split_limbs_umma_kernel<<<dim3((unsigned)cdiv64(nblk * 32, 256), ncolpad), 256, 0, h->stream>>>(V, len, ld, k, ncolpad, nblk, mx, L,
-                                                                                                   d_mult, d_limbsum);
+    split_limbs_umma_kernel<<<dim3((unsigned)cdiv64(nblk * 32, 256), k), 256, 0, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L,
+                                                                                             d_mult, d_limbsum);
     UMMA_LAUNCH_CHECK(h);
     return 0;
 }
 
-// out[r][c*8+l] += ...   for all k columns, in passes of <= 16 columns (N <= 128)
-int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
-               int32_t *out, int plane)
+int k_recombine_umma(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
+                     double *raw, int64_t ld)
 {
-    if (rows_pad % UMMA_ROWS || kbytes % 64 || stride % 64)
-        return sgb_fail(h, "k_pk2_umma: unaligned operand (rows %lld, kbytes %lld, stride %lld)", (long long)rows_pad,
-                        (long long)kbytes, (long long)stride);
+    if (rows * k == 0) return 0;
+    recombine_umma_kernel<<<(unsigned)cdiv64(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, umma_npad(k), d_mult, d_limbsum,
+                                                                                   plane == SGB_PLANE_VALUE ? 2 : 1, raw, ld);
+    UMMA_LAUNCH_CHECK(h);
+    return 0;
+}
+
+// out[r][n] (+)= sum_k (c0 - plane(P[r][k])) * image[k][n]   for `nrows` accumulator columns (a multiple of 16; out has
+// ld = nrows), in balanced passes of N <= 128
+int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int nrows,
+                    int32_t *out, int plane)
+{
+    if (rows_pad % UMMA_ROWS || kbytes % 64 || stride % 64 || nrows % 16)
+        return sgb_fail(h, "k_pk2_umma: unaligned operand (rows %lld, kbytes %lld, stride %lld, columns %d)", (long long)rows_pad,
+                        (long long)kbytes, (long long)stride, nrows);
     umma_pools pool;
     if (plane == SGB_PLANE_VALUE) { pool.ax = 0x02000102u; pool.ay = 0x01020001u; pool.bx = 0x01020202u; pool.by = 0x00000101u; }
     else                          { pool.ax = 0x01000101u; pool.ay = 0x01010001u; pool.bx = 0x01010101u; pool.by = 0x00000101u; }
-    const int ncolpad = (k + 1) & ~1;
     const int64_t ksteps = kbytes / 64;
-    if (ksteps == 0 || rows_pad == 0 || k == 0) return 0;
+    if (ksteps == 0 || rows_pad == 0 || nrows == 0) return 0;
+    // int32 accumulation: |sum| <= 2 * 128 * (genotypes per row)
+    if (kbytes * 4 > ((int64_t)1 << 23)) return sgb_fail(h, "k_pk2_umma: %lld genotypes per row exceed the int32 accumulation bound", (long long)(kbytes * 4));
     const int64_t row_tiles = rows_pad / UMMA_ROWS;
     // split K only when there are too few row tiles to fill the machine
     int64_t kchunks = cdiv64((int64_t)h->sm_count * 4, row_tiles);
@@ -466,13 +515,12 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
 #else
     const int dbg = 0;
 #endif
-    // passes of <= 16 columns, balanced: 20 columns run as 10 + 10 (two HBM-bound passes) rather than 16 + 4 (one
-    // tensor-bound and one HBM-bound pass)
-    const int npass = (ncolpad + 15) / 16;
-    const int per_pass = (((ncolpad + npass - 1) / npass) + 1) & ~1;
-    for (int c0 = 0; c0 < ncolpad; c0 += per_pass) {
-        int nc = ncolpad - c0 < per_pass ? ncolpad - c0 : per_pass;      // columns this pass (even)
-        int N = nc * 8;
+    // balanced passes of N <= 128 accumulator columns (multiples of 16): 224 columns run as 112 + 112
+    const int npass = (nrows + 127) / 128;
+    const int per_pass = (((nrows + npass - 1) / npass) + 15) & ~15;
+    const int ngroups = nrows / 8;
+    for (int n0 = 0; n0 < nrows; n0 += per_pass) {
+        const int N = nrows - n0 < per_pass ? nrows - n0 : per_pass;
         // three A stages let the producers run a full step ahead of the MMAs; they fit 256 TMEM columns (2 CTAs per SM) for N <= 64
         int stages = (N <= 64) ? 3 : 2;
         if (force_stages == 2 || force_stages == 3) stages = force_stages;
@@ -480,21 +528,28 @@ int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
         int nb = (96 * 1024) / (UMMA_KSTEP * N);                // B ring depth (stages of 256 x N bytes)
         if (nb > UMMA_MAX_BSTAGES) nb = UMMA_MAX_BSTAGES;
         if (nb < 2) nb = 2;
-        // the limb image interleaves all ncolpad columns per k-block: this pass starts at column c0
-        const int8_t *Lp = L + (int64_t)c0 * 1024;
+        // the image interleaves all core-matrix groups per k-block: this pass starts at group n0 / 8
+        const int8_t *Lp = L + (int64_t)(n0 / 8) * 1024;
         for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {
             int64_t ny = row_tiles - y0 < 65535 ? row_tiles - y0 : 65535;
             dim3 grid((unsigned)kchunks, (unsigned)ny);
             if (stages == 3)
                 pk2_umma_kernel<3><<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
-                                                                           (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
-                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
+                                                                           (int64_t)ngroups * 1024, out + y0 * UMMA_ROWS * (int64_t)nrows,
+                                                                           nrows, n0, use_atomic, pool, tmem_cols, nb, dbg);
             else
                 pk2_umma_kernel<2><<<grid, UMMA_THREADS, (size_t)nb * UMMA_KSTEP * N, h->stream>>>(P + y0 * UMMA_ROWS * stride, stride, ksteps, (int)per, Lp, N,
-                                                                           (int64_t)ncolpad * 1024, out + y0 * UMMA_ROWS * (int64_t)(ncolpad * 8),
-                                                                           ncolpad * 8, c0 * 8, use_atomic, pool, tmem_cols, nb, dbg);
+                                                                           (int64_t)ngroups * 1024, out + y0 * UMMA_ROWS * (int64_t)nrows,
+                                                                           nrows, n0, use_atomic, pool, tmem_cols, nb, dbg);
             UMMA_LAUNCH_CHECK(h);
         }
     }
     return 0;
+}
+
+// k right-hand sides = 7 k accumulator columns (padded to a multiple of 16)
+int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
+               int32_t *out, int plane)
+{
+    return k_pk2_umma_rows(h, P, stride, rows_pad, kbytes, L, umma_npad(k), out, plane);
 }

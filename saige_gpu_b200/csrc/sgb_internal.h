@@ -126,6 +126,11 @@ int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, int kpad, const d
                 int plane, double *raw, int64_t ld);
 // tcgen05 path (pk2_umma.cu)
 size_t k_umma_limb_bytes(int k, int64_t kbytes);
+size_t k_umma_image_bytes(int nrows, int64_t kbytes);   // image of `nrows` accumulator columns (dense-GRM panels: 128)
+int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int nrows,
+                    int32_t *out, int plane);
+int k_recombine_umma(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
+                     double *raw, int64_t ld);
 int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t kbytes, double *d_mult,
                        int32_t *d_limbsum);
 int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,

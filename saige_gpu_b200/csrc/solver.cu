@@ -81,7 +81,8 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
         if (umma) SGB_TRY(k_pk2_umma(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
         else SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
-        SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, kpad, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
+        if (umma) SGB_TRY(k_recombine_umma(h, h->d_acc1, rowsG, k, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
+        else SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, kpad, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
     } else {
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
         SGB_TRY(k_rowdot_f64(h, dB, N, k, raw1, rowsG));
@@ -97,7 +98,8 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
         if (umma) SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
         else SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, kpad, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
+        if (umma) SGB_TRY(k_recombine_umma(h, h->d_acc2, rowsT, k, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
+        else SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, kpad, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
     } else {
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
         SGB_TRY(k_coldot_f64(h, D, nullptr, rowsG, k, raw2, rowsT));
@@ -132,7 +134,7 @@ int sgb_gt_times_cols(sgb_ctx *h, const double *D, int k, double *raw)
     double *sc = h->d_scal;
     SGB_TRY(k_split_limbs_umma(h, D, h->Mloc, rowsG, k, h->d_limb, h->sT, sc + SC_MULT2, h->d_limbsum + 8192));
     SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
-    SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, kpad, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw, rowsT));
+    SGB_TRY(k_recombine_umma(h, h->d_acc2, rowsT, k, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw, rowsT));
     return 0;
 }
 
@@ -158,10 +160,10 @@ static int diag_ranges(sgb_ctx *h, int nc, const std::vector<int64_t> &lo, const
         SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * kpad));
         SGB_TRY(k_split_limbs_umma(h, D1, h->Mloc, rowsG, nc, h->d_limb, h->sT, h->d_scal + SC_MULT1, h->d_limbsum));
         SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_VALUE));
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, kpad, h->d_scal + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, r1, rowsT));
+        SGB_TRY(k_recombine_umma(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, r1, rowsT));
         SGB_TRY(k_split_limbs_umma(h, D2, h->Mloc, rowsG, nc, h->d_limb, h->sT, h->d_scal + SC_MULT2, h->d_limbsum + 8192));
         SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, nc, h->d_acc2, SGB_PLANE_IS2));   // [g==2] plane
-        SGB_TRY(k_recombine(h, h->d_acc2, rowsT, nc, kpad, h->d_scal + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_IS2, r2, rowsT));
+        SGB_TRY(k_recombine_umma(h, h->d_acc2, rowsT, nc, h->d_scal + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_IS2, r2, rowsT));
     } else if (h->engine != SGB_ENGINE_F64) {
         SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, (size_t)nc * nblkM * 2048));
         SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * nc));

@@ -136,3 +136,43 @@ def test_decode_planes_cover_all_nine_nibbles():
         ind = sum(decode16(int(w), "is2"), [])
         g = geno[16 * wi + np.array([0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15])]
         assert val == list(2 - g) and ind == list(1 - (g == 2).astype(int)), order
+
+
+def test_tcgen05_engine_uses_seven_byte_limbs():
+    """pk2_umma.cu splits q = round(v 2^(53-E)) into 7 balanced base-256 digits (the B operand is s8) and recombines the
+    int32 column sums exactly, with one correctly rounded conversion at the end.  Emulated here with Python integers."""
+    rng = np.random.default_rng(3)
+
+    def digits(q):
+        out = []
+        for _ in range(7):
+            d = ((q + 128) & 255) - 128
+            q = (q - d) >> 8
+            out.append(d)
+        assert q == 0
+        return out
+    # range: |q| <= 2^54 (mantissa of the column maximum just below 2, plus rounding)
+    for q in [0, 1, -1, 127, 128, -128, -129, 2 ** 54, -(2 ** 54), 2 ** 54 - 1, 2 ** 53 + 12345, -(2 ** 53) - 7]:
+        d = digits(q)
+        assert all(-128 <= x <= 127 for x in d) and sum(x * 256 ** l for l, x in enumerate(d)) == q
+    qs = [int(x) for x in rng.integers(-2 ** 54, 2 ** 54, size=2000)]
+    assert all(sum(x * 256 ** l for l, x in enumerate(digits(q))) == q for q in qs)
+
+    def to_double(T):
+        # 62 leading bits + sticky, as recombine_umma_kernel does
+        neg, a = T < 0, abs(T)
+        bits = a.bit_length()
+        shift = max(bits - 62, 0)
+        m = a >> shift
+        if shift and (a & ((1 << shift) - 1)):
+            m |= 1
+        v = float(m) * 2.0 ** shift
+        return -v if neg else v
+    # sums of K products (2 - g) * digit over a long row, per limb, then the recombination
+    for _ in range(200):
+        K = int(rng.integers(1, 200000))
+        x = [int(rng.integers(-256 * K, 256 * K)) for _ in range(7)]
+        T = sum(v << (8 * l) for l, v in enumerate(x))
+        assert to_double(T) == float(T)                       # Python's int -> float is correctly rounded
+    for T in [2 ** 80 + 1, 2 ** 80 + 2 ** 27, 2 ** 80 + 2 ** 27 + 1, -(2 ** 81) - 3, 2 ** 53 + 1, 2 ** 62 + 2 ** 8 + 1]:
+        assert to_double(T) == float(T)
