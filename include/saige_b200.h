@@ -33,8 +33,9 @@ typedef struct sgb_ctx sgb_ctx;
 #define SGB_NCCL_ID_BYTES 128
 
 /* Which arithmetic engine computes GRM products.
- *   SGB_ENGINE_TENSOR : 2-bit genotypes decoded in registers to u8, right-hand sides split into signed 7-bit limbs,
- *                       exact int32 accumulation on the tensor cores, fp64 recombination (default).  Batches of
+ *   SGB_ENGINE_TENSOR : 2-bit genotypes decoded in registers to u8, right-hand sides split into signed int8 limbs of a
+ *                       55-bit fixed-point value (8 x 7 bits on the mma.sync kernel, 7 x 8 bits on the tcgen05 kernel),
+ *                       exact int32 accumulation on the tensor cores, exact recombination, one rounding (default).  Batches of
  *                       k >= 3 columns run on the tcgen05 kernel (A operand decoded straight into tensor memory,
  *                       accumulator in TMEM); k <= 2 on the HBM-bound mma.sync kernel.  Both give identical bits.
  *   SGB_ENGINE_F64    : plain fp64 FMA kernels (slow; the on-device cross-check of the tensor engine).
