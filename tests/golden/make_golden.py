@@ -52,3 +52,18 @@ if __name__ == "__main__":
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         os.chmod(os.path.join(HERE, dst), 0o644)
         print("copied", src, "->", dst)
+    # plink2's allele counts of the 22-chromosome set (128,868 markers), restricted to the 1000 markers of chr22_1000.bim:
+    # an independent tool's counts for a second genotype file (the .frq of the 10k set pins the first)
+    want = [l.split()[1] for l in open(os.path.join(HERE, "chr22_1000.bim"))]
+    rows = {}
+    for l in open(os.path.join(REF, "nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr.acount")):
+        t = l.split()
+        if t[0].startswith("#"):
+            header = l
+        else:
+            rows[t[1]] = l
+    with open(os.path.join(HERE, "chr22_1000.acount"), "w") as f:
+        f.write(header)
+        for mid in want:
+            f.write(rows[mid])
+    print("wrote chr22_1000.acount (%d markers)" % len(want))

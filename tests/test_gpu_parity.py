@@ -145,6 +145,16 @@ def test_diag_of_kin(pair10k, engine):
     g.set_engine("tensor")
 
 
+def test_plink2_allele_counts_through_gpu(gpu2, chr22, golden_dir):
+    """plink2's allele counts of the 22-chromosome set (shipped by the reference) against the GPU ingest."""
+    rows = [l.split() for l in open(os.path.join(golden_dir, "chr22_1000.acount"))][1:]
+    g = gpu2
+    g.setminMAFforGRM(0.0); g.setmaxMissingRateforGRM(1.0); g.setminMAC_VarianceRatio(20, -1, False)
+    p = chr22["prefix"]
+    g.setgeno(p + ".bed", p + ".bim", p + ".fam", np.arange(1, chr22["N0"] + 1), np.ones(chr22["N0"], np.uint8))
+    assert g.M == 1000 and np.array_equal(g.getAlleleCountVec(), np.array([int(r[4]) for r in rows]))
+
+
 def test_loco_products_and_diag(gpu2, chr22):
     gpu = gpu2
     from oracle import oracle as O

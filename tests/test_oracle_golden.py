@@ -115,6 +115,19 @@ def test_pcg_solves_sigma_system(o10k):
     assert r @ r <= 1e-5 and 1 <= it < 100
 
 
+def test_plink2_allele_counts_golden(chr22, golden_dir):
+    """Second decode pin, from an independent tool: the reference ships plink2's allele counts of its 22-chromosome set
+    (nfam_100_nindep_0_step1_includeMoreRareVariants_poly_22chr.acount); the rows of the 1000 markers in chr22_1000.bim
+    must equal the oracle's A1 counts exactly."""
+    rows = [l.split() for l in open(os.path.join(golden_dir, "chr22_1000.acount"))][1:]
+    bim = [l.split() for l in open(os.path.join(golden_dir, "chr22_1000.bim"))]
+    assert [r[1] for r in rows] == [b[1] for b in bim] and all(r[3] == b[4] for r, b in zip(rows, bim))     # ALT = A1 of the .bim
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.0, 1.0
+    o.setgeno(chr22["bed"], chr22["N0"], chr22["M0"], np.arange(1, chr22["N0"] + 1), np.ones(chr22["N0"], np.uint8))
+    assert o.M == 1000 and np.array_equal(o.ACVec, np.array([int(r[4]) for r in rows]))
+    assert all(int(r[5]) == 2 * chr22["N0"] for r in rows)                                                 # no missing calls
+
+
 def test_loco_consistency(chr22):
     o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.01, 0.15
     o.setgeno(chr22["bed"], chr22["N0"], chr22["M0"], np.arange(1, 1001), np.ones(1000, np.uint8))
