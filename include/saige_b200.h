@@ -172,6 +172,13 @@ int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *
  * refit's own standard error (what the reference's bundled positive-signal result holds); 0: |BETA| / |qnorm| of the
  * p-value as this fork's source computes it (:632).  Off after sgb_step2_set_model. */
 int sgb_step2_set_firth(sgb_ctx *h, int enable, double p_cutoff, const double *offset, int se_from_fit);
+/* max_MAC_for_ER (g_MACCutoffforER of setAssocTest_GlobalVarsInCPP, Main.cpp:68-110; R default 4): on a binary trait a
+ * variant whose minor allele count after imputation is <= max_mac_for_er and whose |T|/sqrt(var) exceeds SPAcutoff gets
+ * its p-value from the exact test over all case / control assignments of its carriers instead of the saddle-point
+ * approximation (Main.cpp:408-422, SAIGE_test.cpp:426-431, 592-620; SKATExactBin_Work, ER_binary_func.cpp:186-278), and
+ * SE = |BETA| / |qnorm(p/2)|; Is.SPA stays 0.  Negative: off (the state after sgb_step2_set_model).  Values above 10 are
+ * refused: the reference sizes the test for MAC <= 10 (ER_binary_func.cpp:26) and its Monte-Carlo regime is not built. */
+int sgb_step2_set_er(sgb_ctx *h, double max_mac_for_er);
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
 

@@ -15,9 +15,14 @@ Pinned by the reference's own golden table extdata/output/genotype_100markers_ma
 from extdata/output/example_binary.rda + extdata/input/genotype_100markers.{bed,bim,fam}) -- tests/test_step2_golden.py.
 Firth's bias-reduced effect size (is_Firth_beta, SAIGE_test.cpp:573-633, fast_logistf_fit_simple :893-986) is pinned by the
 BETA / SE of extdata/output/example_binary_positive_signal.assoc.step2.txt.
-Not implemented: efficient-resampling exact test for MAC <= 4 (ER_binary_func.cpp), conditional analysis, sparse-GRM
-variance, categorical variance ratios.
+Efficient resampling ("ER", the exact test of rare variants, MAC <= max_MAC_for_ER = 4; SAIGE_test.cpp:426-431, 592-620,
+ER_binary_func.cpp:23-278, Binary_HyperGeo.cpp:37-193, Binary_ComputeExact.cpp:26-470) is restated in `er_pvalue` and pinned on
+the reference's OWN compiled code: oracle/Makefile builds those Binary_*.cpp files (they carry a _STAND_ALONE_ switch) into
+oracle/_ref/libskat_exact_ref.so, and tests/golden/er_golden.json holds its outputs (tests/golden/make_er_golden.py).
+Not implemented: conditional analysis, sparse-GRM variance, categorical variance ratios.
 """
+import math
+
 import numpy as np
 from scipy import stats
 
@@ -149,6 +154,89 @@ def spa_pvalue(mu, gt, q, qinv, pval_noadj, idx_nz, fast, var2=None):
     return abs(p1) + abs(p2), conv
 
 
+def _lchoose(n, k):
+    """HyperGeo::lCombinations (Binary_HyperGeo.cpp:172-190): R's lchoose, except that k > n gives 0 (not -inf)."""
+    if k > n:
+        return 0.0
+    if k < 0:
+        return -math.inf
+    return math.lgamma(n + 1.0) - math.lgamma(k + 1.0) - math.lgamma(n - k + 1.0)
+
+
+def er_group_prob(p1, p2mean, n, ncase):
+    """SKATExactBin_ComputeProb_Group (ER_binary_func.cpp:23-85) + HyperGeo::Run / Get_lprob (Binary_HyperGeo.cpp:37-150):
+    P(j of the k carriers are cases | ncase cases among n), carriers binned into ten fitted-probability classes with the
+    class-mean odds as non-central hypergeometric weights, everybody else one class of weight 1."""
+    k = len(p1)
+    p1 = np.where(p1 >= 1, 0.999, p1)
+    p2odd = p2mean / (1 - p2mean)
+    groups, weights = [], []
+    for b in range(10):
+        a1, a2 = b / 10.0, (b + 1) / 10.0
+        sel = (p1 >= a1) & ((p1 < a2) if b < 9 else (p1 <= a2))
+        if sel.any():
+            pm = p1[sel].mean()
+            weights.append(pm / (1 - pm) / p2odd)
+            groups.append(int(sel.sum()))
+    last = [_lchoose(n - k, ncase - j) for j in range(k + 1)]          # weight of the last class is p2odd / p2odd = 1
+    ref = max([0.0] + [v for v in last if v > -math.inf])
+    kprob = [0.0] * (k + 1)
+
+    def rec(lprob, idx, used):
+        if idx == len(groups):
+            kprob[used] += math.exp(lprob + last[used] - ref)
+            return
+        for i in range(groups[idx] + 1):
+            if used + i <= ncase:
+                rec(lprob + _lchoose(groups[idx], i) + math.log(weights[idx]) * i, idx + 1, used + i)
+    rec(0.0, 0, 0)
+    tot = sum(kprob)
+    return np.array([v / tot for v in kprob])
+
+
+def er_pvalue(g1, p1, res1, p2mean, n, ncase, epsilon=1e-6):
+    """SKATExactBin_Work (ER_binary_func.cpp:186-278) for one variant (m = 1) + ComputeExact::Init / Run / GetPvalues
+    (Binary_ComputeExact.cpp:296-470) in the all-exact regime (2^k <= NResampling): every case/control assignment of the k
+    carriers is enumerated; statistic (sum_i g_i([i case] - p_i))^2; probability of an assignment with j cases =
+    prod(odds of its cases) / e_j(odds) * P(j); result = P(stat >= observed) - P(stat == observed) / 2 (ties within epsilon).
+    g1, p1, res1: genotype, fitted probability and residual of the carriers (observed cases: res1 > 0)."""
+    k = len(g1)
+    prob = er_group_prob(np.asarray(p1, dtype=np.float64), p2mean, n, ncase)
+    odds = p1 / (1 - p1)
+    z0sum = float(np.sum(-g1 * p1))
+    obs = [i for i in range(k) if res1[i] > 0]
+    Q = (z0sum + sum(g1[i] for i in obs)) ** 2
+    stat, fprob, size = [], [], []
+    denom = [0.0] * (k + 1)
+    for j in range(k + 1):
+        for S in _subsets(k, j):
+            stat.append((z0sum + sum(g1[i] for i in S)) ** 2)
+            w = 1.0
+            for i in S:
+                w *= odds[i]
+            fprob.append(w)
+            size.append(j)
+            denom[j] += w
+    fprob = [fprob[i] / denom[size[i]] * prob[size[i]] for i in range(len(fprob))]
+    tot = sum(fprob)
+    pval = same = 0.0
+    for s, w in zip(stat, fprob):
+        d = Q - s
+        if abs(d) <= epsilon:
+            d = 0.0
+        if d <= 0:
+            pval += w / tot
+            if d == 0:
+                same += w / tot
+    return pval - same / 2
+
+
+def _subsets(k, j):
+    """size-j subsets of range(k) in lexicographic order (SKAT_Exact_Recurse, Binary_ComputeExact.cpp:112-129)."""
+    import itertools
+    return itertools.combinations(range(k), j)
+
+
 def score_test_fast(M, G, idx):
     """scoreTestFast (SAIGE_test.cpp:212-292)."""
     g1, X1, A1, res1 = G[idx], M["X"][idx], M["XVX_inv_XV"][idx], M["res"][idx]
@@ -203,7 +291,7 @@ def firth_fit(gt, y, offset, maxit=50, maxstep=15, xconv=1e-5, gconv=1e-5):
 
 
 def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=2.0, se_two_sided=True, is_Firth_beta=False,
-                pCutoffforFirth=0.01, firth_se_from_fit=True):
+                pCutoffforFirth=0.01, firth_se_from_fit=True, max_MAC_for_ER=-1.0):
     """One pass of the mainMarkerInCPP loop body (Main.cpp:229-520).  Returns None when the marker is filtered."""
     test_marker.__test__ = False
     n = len(Graw)
@@ -232,7 +320,15 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     st = score_test_fast(M, G, idx)
     std_stat = abs(st["Tstat"]) / np.sqrt(st["var1"])
     pval, se, is_spa = st["pval"], st["seBeta"], False
-    if np.isfinite(std_stat) and std_stat > spa_cutoff and M["trait"] == "binary":
+    # exact test of rare variants (Main.cpp:408-422: MAC after imputation <= g_MACCutoffforER; SAIGE_test.cpp:426-431, 592-620)
+    mac_after = min(alt_count, 2 * n - alt_count)
+    is_er = (M["trait"] == "binary" and mac_after <= max_MAC_for_ER and (std_stat > spa_cutoff or np.isnan(std_stat)))
+    if is_er:
+        mu = M["mu"]
+        p2mean = float(np.delete(mu, idx).mean())
+        pval = er_pvalue(G[idx], mu[idx], M["res"][idx], p2mean, n, int((M["y"] == 1).sum()))
+        se = 0.0 if pval / 2 <= 0 else abs(st["Beta"]) / abs(stats.norm.ppf(pval / 2))
+    elif np.isfinite(std_stat) and std_stat > spa_cutoff and M["trait"] == "binary":
         gt = G - M["XXVX_inv"] @ (M["XV"] @ G)                      # getadjGFast
         m1 = float(M["mu"] @ gt)
         q = st["Tstat"] / np.sqrt(st["var1"] / st["var2"]) + m1
@@ -252,7 +348,7 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
         gt = G - M["XXVX_inv"] @ (M["XV"] @ G)
         beta, se_fit, firth_conv = firth_fit(gt, M["y"], M["offset"])
         is_firth = True
-        se = se_fit if firth_se_from_fit else abs(beta) / abs(stats.norm.isf(pval / 2 if se_two_sided else pval))
+        se = se_fit if firth_se_from_fit else abs(beta) / abs(stats.norm.isf(pval / 2 if (se_two_sided or is_er) else pval))
     sgn = -1.0 if flip else 1.0
     y = M["y"]
     case, ctrl = y == 1, y == 0
@@ -260,6 +356,6 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     if flip:
         afc, aft = 1 - afc, 1 - aft
     return dict(AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
-                Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa,
+                Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa, Is_ER=is_er,
                 Is_Firth=is_firth, Firth_converged=firth_conv,
                 AF_case=afc, AF_ctrl=aft, N_case=int(case.sum()), N_ctrl=int(ctrl.sum()))

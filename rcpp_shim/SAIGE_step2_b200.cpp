@@ -8,9 +8,9 @@
 // tests/test_step2_golden.py through saige_gpu_b200/step2.py, which follows this file.
 //
 // What the library covers: PLINK input, best-guess imputation, full-GRM variance ratio (t_varRatio_null[0]), binary and
-// quantitative traits, SPA / SPA_fast, Firth's effect size.  Sparse-GRM variance, categorical variance ratios,
-// conditional analysis, the exact test for MAC <= MACCutoffforER and the region tests keep the reference's code path:
-// the shim refuses those option combinations instead of silently ignoring them.
+// quantitative traits, SPA / SPA_fast, Firth's effect size, the exact test for MAC <= MACCutoffforER (<= 10).  Sparse-GRM
+// variance, categorical variance ratios, conditional analysis and the region tests keep the reference's code path: the
+// shim refuses those option combinations instead of silently ignoring them.
 #if defined(USE_SAIGE_B200)
 #include <RcppArmadillo.h>
 #include <string>
@@ -24,6 +24,7 @@ static void ck2(int rc) { if (rc) Rcpp::stop(std::string("saige_b200: ") + sgb_l
 
 // state the marker loop needs besides the library's (PlinkClass keeps the file; Main.cpp globals keep the cut-offs)
 extern double g_marker_minMAF_cutoff, g_marker_minMAC_cutoff, g_missingRate_cutoff;      // Main.cpp:60-70
+extern double g_MACCutoffforER;                  // Main.cpp:68, set by setAssocTest_GlobalVarsInCPP (Main.cpp:96-110) before the model
 static std::vector<int32_t> g_pos_in_fam;        // PlinkClass::m_posSampleInPlink, filled by setPLINKobjInCPP
 
 // [[Rcpp::export]]
@@ -47,6 +48,8 @@ void setSAIGEobjInCPP(arma::mat & t_XVX, arma::mat & t_XXVX_inv, arma::mat & t_X
                             t_tauvec.memptr(), t_varRatio_null[0], t_SPA_Cutoff, g_pos_in_fam.data()));
     // se_from_fit = 0: this fork's source back-calculates the SE from the p-value (SAIGE_test.cpp:632)
     ck2(sgb_step2_set_firth(saige_b200_ctx(), t_is_Firth_beta ? 1 : 0, t_pCutoffforFirth, t_offset.n_elem == (arma::uword)N ? t_offset.memptr() : nullptr, 0));
+    // exact test of rare variants (Main.cpp:408-422); t_resout is empty on this path (readInGLMM.R:123: no resampled residuals)
+    ck2(sgb_step2_set_er(saige_b200_ctx(), g_MACCutoffforER));
 }
 
 // The PLINK branch of mainMarkerInCPP (Main.cpp:149-560): one call per chunk of marker indices.  `readRawRows` stands for

@@ -363,6 +363,11 @@ class SaigeB200:
         self._ck(self._L.sgb_step2_set_firth(self._h, int(bool(is_Firth_beta)), float(pCutoffforFirth),
                                              None if off is None else _p(off), int(bool(se_from_fit))))
 
+    def setMaxMACforER(self, max_MAC_for_ER=4.0):
+        """max_MAC_for_ER of SPAGMMATtest / setAssocTest_GlobalVarsInCPP: binary-trait variants with MAC <= this get the
+        exact-test p-value (efficient resampling) when their score exceeds the SPA cutoff; negative = off."""
+        self._ck(self._L.sgb_step2_set_er(self._h, float(max_MAC_for_ER)))
+
     def mainMarkerInCPP(self, bed_rows, n_fam, n_markers, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, se_two_sided=True):
         bed = np.ascontiguousarray(bed_rows, dtype=np.uint8)
         if bed.size < ((n_fam + 3) // 4) * n_markers:

@@ -4,7 +4,9 @@
 // alt-first), the MAF/MAC/missing-rate filter, imputeGenoAndFlip (UTIL.cpp:58-135, best_guess), scoreTestFast
 // (SAIGE_test.cpp:212-292) and, when |T|/sqrt(var1) > SPAcutoff on a binary trait, getMarkerPval's SPA / SPA_fast
 // branch (SAIGE_test.cpp:345-640, SPA.cpp:20-185, SPA_binary.cpp:21-330) and, when asked for, Firth's bias-reduced
-// effect size of significant variants (fast_logistf_fit_simple, SAIGE_test.cpp:893-986).  All arithmetic fp64, like the reference.
+// effect size of significant variants (fast_logistf_fit_simple, SAIGE_test.cpp:893-986), and the exact test of rare
+// variants (MAC <= max_MAC_for_ER: Main.cpp:408-422, SAIGE_test.cpp:426-431, 592-620 -> er_exact.h).  All arithmetic fp64,
+// like the reference.
 //
 // One CTA per variant.  The raw PLINK row (2 bits per .fam sample) is staged in shared memory; the per-sample model
 // vectors (mu, mu2, res, X, XVX_inv_XV, XXVX_inv: N x (3p + 3) doubles) are read through L2 by every CTA.
@@ -20,6 +22,7 @@
 #include <thread>
 #include <vector>
 #include "sgb_internal.h"
+#include "er_exact.h"
 
 #define S2_MAXP 16
 #define S2_THREADS 256
@@ -38,6 +41,9 @@ struct s2_model {
     const double *offset;    // N, the null model's offset (zeros when absent)
     int firth, firth_se_from_fit;
     double firth_cutoff;
+    // exact test of rare variants (g_MACCutoffforER, Main.cpp:68,408): off when negative
+    double er_max_mac;
+    double mu_sum;           // sum of mu over the model's samples (mean fitted probability of a variant's non-carriers)
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sm)
@@ -78,6 +84,8 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     extern __shared__ uint8_t srow[];
     __shared__ double red[S2_THREADS / 32];
     __shared__ double Zs[S2_MAXP], Ws[S2_MAXP];
+    __shared__ int er_cnt, er_idx[SGB_ER_MAXK];
+    __shared__ double er_pv;
     const int64_t m = blockIdx.x;
     if (m >= nm) return;
     const int tid = threadIdx.x, p = M.p;
@@ -226,9 +234,48 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     double seBeta = fabs(Beta) / sqrt(fabs(stat));
     double pval = pval_noadj, isSPA = 0.0;
 
-    // ---- saddle-point approximation (binary traits) ----
     const double StdStat = fabs(S) / sqrt(var1);
-    if (M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff) {
+    // ---- exact test of rare variants (binary traits): MAC after imputation <= max_MAC_for_ER and a score beyond the SPA
+    // cutoff (Main.cpp:408-422, SAIGE_test.cpp:426-431).  The carriers (<= SGB_ER_MAXK of them, since every one holds at
+    // least one minor allele) are collected in sample order; one thread enumerates their case / control assignments ----
+    const double MACafter = fmin(altCount, 2.0 * (double)N - altCount);
+    const bool isER = M.binary && MACafter <= M.er_max_mac && nz <= (double)SGB_ER_MAXK && (StdStat > M.spa_cutoff || isnan(StdStat));
+    if (isER) {
+        if (tid == 0) er_cnt = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            if (s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG)) {
+                const int slot = atomicAdd(&er_cnt, 1);
+                if (slot < SGB_ER_MAXK) er_idx[slot] = (int)i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int k = er_cnt < SGB_ER_MAXK ? er_cnt : SGB_ER_MAXK;
+            for (int a = 1; a < k; a++) {                          // ascending sample index (iIndex of the reference)
+                const int v = er_idx[a];
+                int b = a - 1;
+                while (b >= 0 && er_idx[b] > v) { er_idx[b + 1] = er_idx[b]; b--; }
+                er_idx[b + 1] = v;
+            }
+            double g1[SGB_ER_MAXK], p1[SGB_ER_MAXK], r1[SGB_ER_MAXK], musum = 0.0;
+            for (int a = 0; a < k; a++) {
+                const int i = er_idx[a];
+                g1[a] = (double)s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
+                p1[a] = M.mu[i]; r1[a] = M.res[i];
+                musum += p1[a];
+            }
+            const double p2mean = (M.mu_sum - musum) / ((double)N - (double)k);
+            // NResampling 2e6, ExactMax 1e4, epsilon 1e-6 (SAIGE_test.cpp:599): 2^k <= 1024 assignments, all enumerated
+            er_pv = sgb_er_exact_pvalue(k, g1, p1, r1, p2mean, (double)N, M.ncase_tot, 1e-6);
+        }
+        __syncthreads();
+        pval = er_pv;
+        // SE from the exact p-value, |qnorm(p/2)| (SAIGE_test.cpp:606-614; quantile(0) overflows there -> 0)
+        seBeta = pval * 0.5 > 0.0 ? fabs(Beta) / fabs(normcdfinv(pval * 0.5)) : 0.0;
+    }
+    // ---- saddle-point approximation (binary traits) ----
+    else if (M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff) {
         // gtilde_i = g_i - XXVX_inv[i,:] . (XV g),  XV g = W  (getadjGFast, SAIGE_test.cpp:306-315)
         double m1p = 0, gpos = 0, gneg = 0, gmuNB = 0, sigNB = 0;
         for (int64_t i = tid; i < N; i += S2_THREADS) {
@@ -378,7 +425,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             BetaOut = b1;
             // SE: the fit's own (what the reference's bundled positive-signal result holds) or |beta| / |qnorm| of the p-value
             // as this fork's source has it (SAIGE_test.cpp:632)
-            seBeta = M.firth_se_from_fit ? sqrt(c11) : fabs(b1) / fabs(normcdfinv(se_two_sided ? pval * 0.5 : pval));
+            seBeta = M.firth_se_from_fit ? sqrt(c11) : fabs(b1) / fabs(normcdfinv((se_two_sided || isER) ? pval * 0.5 : pval));
         }
     }
     if (tid == 0) {
@@ -454,6 +501,18 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     CUDA_OK(h, cudaMalloc((void **)&s->d_offset, sizeof(double) * N));
     CUDA_OK(h, cudaMemset(s->d_offset, 0, sizeof(double) * N));
     M.offset = s->d_offset; M.firth = 0; M.firth_se_from_fit = 1; M.firth_cutoff = 0.01;
+    M.er_max_mac = -1.0; M.mu_sum = 0.0;
+    for (int64_t i = 0; i < N; i++) M.mu_sum += mu[i];
+    return 0;
+}
+
+extern "C" int sgb_step2_set_er(sgb_ctx *h, double max_mac_for_er)
+{
+    sgb_step2 *s = h->step2;
+    if (!s || !s->d_vec) return sgb_fail(h, "step2: call sgb_step2_set_model first");
+    if (max_mac_for_er > (double)SGB_ER_MAXK)
+        return sgb_fail(h, "step2: max_MAC_for_ER=%g is above %d (the exact test enumerates 2^carriers assignments)", max_mac_for_er, SGB_ER_MAXK);
+    s->M.er_max_mac = max_mac_for_er < 0 ? -1.0 : max_mac_for_er;
     return 0;
 }
 

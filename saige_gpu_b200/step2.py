@@ -62,7 +62,7 @@ def Get_Variance_Ratio(varianceRatioFile):
 def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioFile, SAIGEOutputFile=None, chrom="",
                  LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
                  is_output_moreDetails=True, se_two_sided=True, rank=0, world=1, is_Firth_beta=False, pCutoffforFirth=0.01,
-                 firth_se_from_fit=True):
+                 firth_se_from_fit=True, max_MAC_for_ER=4.0):
     """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the .bim
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
@@ -77,6 +77,7 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
     pos = np.array([where[s] for s in model["sampleID"]], dtype=np.int32)
     geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
     geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
+    geno.setMaxMACforER(max_MAC_for_ER)                 # exact test of rare variants (step2_SPAtests.R:126 --max_MAC_for_ER, default 4)
     raw = np.fromfile(bedFile, dtype=np.uint8)
     if raw[0] != 0x6C or raw[1] != 0x1B or raw[2] != 0x01:
         raise ValueError("%s is not a SNP-major PLINK .bed" % bedFile)
