@@ -33,6 +33,14 @@ class RObject:
         return "<R %s>" % self.kind
 
 
+class RList(dict):
+    """A named R list that carries an S3 class (e.g. obj.noK: class "SA_NULL", FG.R:589)."""
+
+    def __init__(self, *a, r_class=None, **kw):
+        super().__init__(*a, **kw)
+        self.r_class = r_class
+
+
 class _Reader:
     def __init__(self, data):
         self.b, self.p, self.refs = data, 0, []
@@ -208,6 +216,8 @@ class _Reader:
         if isinstance(val, list) and "names" in a and a["names"] is not None:
             names = list(a["names"])
             if len(names) == len(val) and all(n not in (None, "") for n in names):
+                if a.get("class"):
+                    return RList(zip(names, val), r_class=list(a["class"]))
                 return dict(zip(names, val))
         return val
 
@@ -234,3 +244,126 @@ def load_rda(path):
         r.bytes(n)               # native encoding
     top = r.item()
     return {str(k): v for k, v in top}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# writer: the counterpart of R's save(modglmm, file = modelOut) (FG.R:1297-1301), so that a null model fitted through the
+# Python mirror of fitNULLGLMM can be consumed by load() in the reference's step 2 (R/readInGLMM.R:39-45)
+# ---------------------------------------------------------------------------------------------------------------------
+class _Writer:
+    """Serialization format version 2 (what the reference's bundled .rda files use; every R >= 1.4 reads it), XDR."""
+
+    def __init__(self):
+        self.out, self.sym = [], {}
+
+    def int(self, v):
+        self.out.append(struct.pack(">i", v))
+
+    def length(self, n):
+        if n > 2147483647:
+            self.int(-1)
+            self.out.append(struct.pack(">II", n >> 32, n & 0xFFFFFFFF))
+        else:
+            self.int(n)
+
+    def charsxp(self, s):
+        if s is None:
+            self.int(CHARSXP)              # NA_character_
+            self.int(-1)
+            return
+        b = s.encode("utf-8")
+        levels = 64 if all(c < 128 for c in b) else 8          # ASCII_MASK / UTF8_MASK in the gp field
+        self.int(CHARSXP | (levels << 12))
+        self.int(len(b))
+        self.out.append(b)
+
+    def symbol(self, name):
+        if name in self.sym:                                   # later occurrences are back references
+            self.int((self.sym[name] << 8) | REFSXP)
+            return
+        self.sym[name] = len(self.sym) + 1
+        self.int(SYMSXP)
+        self.charsxp(name)
+
+    def attributes(self, attr):
+        for k, v in attr:
+            self.int(LISTSXP | 0x400)                          # pairlist node with a tag
+            self.symbol(k)
+            self.item(v)
+        self.int(NILVALUE_SXP)
+
+    def vector_header(self, typ, n, attr):
+        self.int(typ | (0x200 if attr else 0))
+        self.length(n)
+
+    def item(self, v, attr=None):
+        attr = list(attr) if attr else []
+        if v is None:
+            self.int(NILVALUE_SXP)
+            return
+        if isinstance(v, dict):
+            keys = list(v.keys())
+            cls = getattr(v, "r_class", None)
+            self.int(VECSXP | 0x200 | (0x100 if cls else 0))       # 0x100: is an object (has a class attribute)
+            self.length(len(keys))
+            for k in keys:
+                self.item(v[k])
+            self.attributes([("names", [str(k) for k in keys])] + ([("class", list(cls))] if cls else []) + attr)
+            return
+        if isinstance(v, (bool, np.bool_)):
+            v = np.array([v], dtype=np.bool_)
+        elif isinstance(v, (int, np.integer)):
+            v = np.array([v], dtype=np.int32)
+        elif isinstance(v, (float, np.floating)):
+            v = np.array([v], dtype=np.float64)
+        elif isinstance(v, str):
+            v = [v]
+        if isinstance(v, (list, tuple)):
+            if len(v) and all(isinstance(x, str) or x is None for x in v):
+                self.vector_header(STRSXP, len(v), attr)
+                for x in v:
+                    self.charsxp(x)
+            else:
+                self.vector_header(VECSXP, len(v), attr)
+                for x in v:
+                    self.item(x)
+            if attr:
+                self.attributes(attr)
+            return
+        if isinstance(v, np.ndarray):
+            if v.ndim >= 2:
+                attr = [("dim", np.array(v.shape, dtype=np.int32))] + attr
+            flat = np.asarray(v).reshape(-1, order="F")
+            if v.dtype == np.bool_ or v.dtype == np.int8:          # the reader returns logicals as int8 (NA = -1)
+                typ, data = LGLSXP, np.where(flat.astype(np.int64) < 0, -2147483648, flat.astype(np.int64)).astype(">i4")
+            elif np.issubdtype(v.dtype, np.integer):
+                typ, data = INTSXP, flat.astype(">i4")
+            elif np.issubdtype(v.dtype, np.floating):
+                typ, data = REALSXP, flat.astype(">f8")
+            else:
+                raise TypeError("cannot serialize an array of dtype %s" % v.dtype)
+            self.vector_header(typ, flat.size, attr)
+            self.out.append(data.tobytes())
+            if attr:
+                self.attributes(attr)
+            return
+        raise TypeError("cannot serialize %r" % type(v))
+
+
+def save_rda(path, objects, compress=True):
+    """save(<objects>, file = path): `objects` maps R object names to values.  dict -> named list, list of str -> character
+    vector, other list -> unnamed list, numpy arrays -> logical (bool / int8) / integer / double vectors and matrices
+    (column-major, `dim` attribute), scalars -> length-1 vectors, None -> NULL.  gzip-compressed like R's default."""
+    w = _Writer()
+    w.out.append(b"RDX2\nX\n")
+    w.int(2)
+    w.int(0x00030603)            # written by R 3.6.3 (any version R accepts); readable from R 2.3.0
+    w.int(0x00020300)
+    for name, v in objects.items():
+        w.int(LISTSXP | 0x400)
+        w.symbol(str(name))
+        w.item(v)
+    w.int(NILVALUE_SXP)
+    raw = b"".join(w.out)
+    with open(path, "wb") as f:
+        f.write(gzip.compress(raw, 6, mtime=0) if compress else raw)
