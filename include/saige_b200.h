@@ -179,6 +179,15 @@ int sgb_step2_set_firth(sgb_ctx *h, int enable, double p_cutoff, const double *o
  * SE = |BETA| / |qnorm(p/2)|; Is.SPA stays 0.  Negative: off (the state after sgb_step2_set_model).  Values above 10 are
  * refused: the reference sizes the test for MAC <= 10 (ER_binary_func.cpp:26) and its Monte-Carlo regime is not built. */
 int sgb_step2_set_er(sgb_ctx *h, double max_mac_for_er);
+/* Categorical variance ratios (t_varRatio_null with more than one entry, t_cateVarRatioMinMACVecExclude,
+ * t_cateVarRatioMaxMACVecInclude of setSAIGEobjInCPP; SAIGEClass::assignVarianceRatio, SAIGE_test.cpp:801-833): a variant
+ * with min_mac_exclude[c] < MAC <= max_mac_include[c] (MAC after imputation) uses ratios[c]; max_mac_include has n_cate - 1
+ * entries, the last category is open-ended, MAC below the first bound uses ratios[0].  The categories must tile the MAC axis
+ * (min_mac_exclude[c] == max_mac_include[c-1]), which is what fitNULLGLMM's defaults (10, 20.5) / (20.5) do.  One deviation,
+ * deliberate: MAC == min_mac_exclude[0] exactly matches no branch of the reference, which then keeps the previous marker's
+ * ratio (order-dependent); here it belongs to the first category.  n_cate == 1: the single ratio of sgb_step2_set_model. */
+int sgb_step2_set_variance_ratios(sgb_ctx *h, int n_cate, const double *ratios, const double *min_mac_exclude,
+                                  const double *max_mac_include);
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
 

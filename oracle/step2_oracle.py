@@ -237,7 +237,23 @@ def _subsets(k, j):
     return itertools.combinations(range(k), j)
 
 
-def score_test_fast(M, G, idx):
+def assign_variance_ratio(M, mac):
+    """assignVarianceRatio (SAIGE_test.cpp:801-833); M["varRatio"] a float, or one value per MAC category with
+    M["cateVarRatioMinMACVecExclude"] / M["cateVarRatioMaxMACVecInclude"].  MAC == the first bound exactly matches no branch
+    in the reference (it keeps the previous marker's value); by convention here: first category."""
+    vr = np.asarray(M["varRatio"], dtype=np.float64).reshape(-1)
+    if len(vr) == 1:
+        return float(vr[0])
+    lo, hi = list(M["cateVarRatioMinMACVecExclude"]), list(M["cateVarRatioMaxMACVecInclude"])
+    for i in range(len(hi)):
+        if lo[i] < mac <= hi[i]:
+            return float(vr[i])
+    if mac <= lo[0]:
+        return float(vr[0])
+    return float(vr[-1])
+
+
+def score_test_fast(M, G, idx, var_ratio=None):
     """scoreTestFast (SAIGE_test.cpp:212-292)."""
     g1, X1, A1, res1 = G[idx], M["X"][idx], M["XVX_inv_XV"][idx], M["res"][idx]
     Z = A1.T @ g1
@@ -248,7 +264,7 @@ def score_test_fast(M, G, idx):
         var2 = float(Z @ M["XVX"] @ Z) - float(Bv ** 2 @ mu21) + float(gt1 ** 2 @ mu21)
     else:
         var2 = float(Z @ M["XVX"] @ Z) * M["tau"][0] + float(g1 @ g1) - 2 * float(g1 @ Bv)
-    var1 = var2 * M["varRatio"]
+    var1 = var2 * (float(np.asarray(M["varRatio"]).reshape(-1)[0]) if var_ratio is None else var_ratio)
     S = (float(res1 @ gt1) - float((M["S_a"] - res1 @ X1) @ Z)) / M["tau"][0]
     stat = S * S / var1
     pval = 1.0 if var1 <= np.finfo(float).tiny or not np.isfinite(stat) else float(stats.chi2.sf(stat, 1))
@@ -317,7 +333,7 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     if flip:
         alt_freq, alt_count = 1 - alt_freq, 2 * n - alt_count
     idx = np.nonzero(G != 0)[0]
-    st = score_test_fast(M, G, idx)
+    st = score_test_fast(M, G, idx, assign_variance_ratio(M, min(alt_count, 2 * n - alt_count)))
     std_stat = abs(st["Tstat"]) / np.sqrt(st["var1"])
     pval, se, is_spa = st["pval"], st["seBeta"], False
     # exact test of rare variants (Main.cpp:408-422: MAC after imputation <= g_MACCutoffforER; SAIGE_test.cpp:426-431, 592-620)

@@ -8,8 +8,8 @@
 // tests/test_step2_golden.py through saige_gpu_b200/step2.py, which follows this file.
 //
 // What the library covers: PLINK input, best-guess imputation, full-GRM variance ratio (t_varRatio_null[0]), binary and
-// quantitative traits, SPA / SPA_fast, Firth's effect size, the exact test for MAC <= MACCutoffforER (<= 10).  Sparse-GRM
-// variance, categorical variance ratios, conditional analysis and the region tests keep the reference's code path: the
+// quantitative traits, SPA / SPA_fast, Firth's effect size, the exact test for MAC <= MACCutoffforER (<= 10), categorical
+// variance ratios.  Sparse-GRM variance, conditional analysis and the region tests keep the reference's code path: the
 // shim refuses those option combinations instead of silently ignoring them.
 #if defined(USE_SAIGE_B200)
 #include <RcppArmadillo.h>
@@ -37,9 +37,9 @@ void setSAIGEobjInCPP(arma::mat & t_XVX, arma::mat & t_XXVX_inv, arma::mat & t_X
                       arma::vec & t_valueVec, int t_dimNum, bool t_isCondition, std::vector<uint32_t> & t_condition_genoIndex,
                       bool t_is_Firth_beta, double t_pCutoffforFirth, arma::vec & t_offset, arma::vec & t_resout)
 {
-    if (t_flagSparseGRM || t_isCondition || t_varRatio_null.n_elem != 1 || t_impute_method != "best_guess")
-        Rcpp::stop("saige_b200: sparse-GRM variance, conditional analysis, categorical variance ratios and non-best-guess "
-                   "imputation are not provided by the B200 library; build without USE_SAIGE_B200 for these options");
+    if (t_flagSparseGRM || t_isCondition || t_impute_method != "best_guess")
+        Rcpp::stop("saige_b200: sparse-GRM variance, conditional analysis and non-best-guess imputation are not provided by "
+                   "the B200 library; build without USE_SAIGE_B200 for these options");
     const int64_t N = (int64_t)t_X.n_rows;
     const int p = (int)t_X.n_cols;
     arma::mat XVX_inv_XV_t = t_XVX_inv_XV;       // N x p already (readInGLMM.R:60-75 stores XVX_inv_XV as N x p)
@@ -50,6 +50,10 @@ void setSAIGEobjInCPP(arma::mat & t_XVX, arma::mat & t_XXVX_inv, arma::mat & t_X
     ck2(sgb_step2_set_firth(saige_b200_ctx(), t_is_Firth_beta ? 1 : 0, t_pCutoffforFirth, t_offset.n_elem == (arma::uword)N ? t_offset.memptr() : nullptr, 0));
     // exact test of rare variants (Main.cpp:408-422); t_resout is empty on this path (readInGLMM.R:123: no resampled residuals)
     ck2(sgb_step2_set_er(saige_b200_ctx(), g_MACCutoffforER));
+    // one ratio per MAC category (assignVarianceRatio, SAIGE_test.cpp:801-833)
+    if (t_varRatio_null.n_elem > 1)
+        ck2(sgb_step2_set_variance_ratios(saige_b200_ctx(), (int)t_varRatio_null.n_elem, t_varRatio_null.memptr(),
+                                          t_cateVarRatioMinMACVecExclude.memptr(), t_cateVarRatioMaxMACVecInclude.memptr()));
 }
 
 // The PLINK branch of mainMarkerInCPP (Main.cpp:149-560): one call per chunk of marker indices.  `readRawRows` stands for

@@ -352,9 +352,13 @@ class SaigeB200:
         pos = np.ascontiguousarray(pos_in_fam, dtype=np.int32)
         if len(pos) != N:
             raise SaigeB200Error("pos_in_fam must have one entry per model sample")
+        ratios = np.asarray(varRatio, dtype=np.float64).reshape(-1)
         self._ck(self._L.sgb_step2_set_model(self._h, N, p, int(model["trait"] == "binary"), *[_p(a) for a in arrs],
-                                             float(varRatio), float(SPAcutoff), _p(pos)))
+                                             float(ratios[0]), float(SPAcutoff), _p(pos)))
         self._step2_N = N
+        if len(ratios) > 1:
+            self.setVarianceRatios(ratios, model.get("cateVarRatioMinMACVecExclude", (10, 20.5)),
+                                   model.get("cateVarRatioMaxMACVecInclude", (20.5,)))
 
     def setFirth(self, is_Firth_beta, pCutoffforFirth=0.01, offset=None, se_from_fit=True):
         """is_Firth_beta / pCutoffforFirth of SPAGMMATtest: Firth's bias-reduced BETA for binary-trait variants with
@@ -362,6 +366,15 @@ class SaigeB200:
         off = None if offset is None else _f64(np.asarray(offset, dtype=np.float64).reshape(-1))
         self._ck(self._L.sgb_step2_set_firth(self._h, int(bool(is_Firth_beta)), float(pCutoffforFirth),
                                              None if off is None else _p(off), int(bool(se_from_fit))))
+
+    def setVarianceRatios(self, ratioVec_null, cateVarRatioMinMACVecExclude=(10, 20.5), cateVarRatioMaxMACVecInclude=(20.5,)):
+        """t_varRatio_null / t_cateVarRatio*Vec of setSAIGEobjInCPP: one ratio, or one per MAC category (assignVarianceRatio)."""
+        r = _f64(np.asarray(ratioVec_null, dtype=np.float64).reshape(-1))
+        lo = _f64(np.asarray(cateVarRatioMinMACVecExclude, dtype=np.float64).reshape(-1))
+        hi = _f64(np.asarray(cateVarRatioMaxMACVecInclude, dtype=np.float64).reshape(-1))
+        if len(r) > 1 and (len(lo) != len(r) or len(hi) != len(r) - 1):
+            raise SaigeB200Error("ERROR! The number of variance ratios are different from the length of cateVarRatioMinMACVecExclude")
+        self._ck(self._L.sgb_step2_set_variance_ratios(self._h, len(r), _p(r), _p(lo), _p(hi)))
 
     def setMaxMACforER(self, max_MAC_for_ER=4.0):
         """max_MAC_for_ER of SPAGMMATtest / setAssocTest_GlobalVarsInCPP: binary-trait variants with MAC <= this get the

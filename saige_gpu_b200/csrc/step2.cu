@@ -27,6 +27,7 @@
 #define S2_MAXP 16
 #define S2_THREADS 256
 #define S2_NOUT 22      // doubles per variant in the result table (see include/saige_b200.h)
+#define S2_MAXCATE 8    // MAC categories of the variance ratio (the reference's default has 2)
 
 struct s2_model {
     int64_t N; int p; int binary;
@@ -43,6 +44,10 @@ struct s2_model {
     double firth_cutoff;
     // exact test of rare variants (g_MACCutoffforER, Main.cpp:68,408): off when negative
     double er_max_mac;
+    // categorical variance ratios (assignVarianceRatio, SAIGE_test.cpp:801-833): category c covers cate_min[c] < MAC <=
+    // cate_max[c], the last one is open-ended; n_cate == 1: the single ratio `varRatio`
+    int n_cate;
+    double cate_ratio[S2_MAXCATE], cate_min[S2_MAXCATE], cate_max[S2_MAXCATE];
     double mu_sum;           // sum of mu over the model's samples (mean fitted probability of a variant's non-carriers)
 };
 
@@ -223,7 +228,15 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         // quantitative (SAIGE_test.cpp:246-248): ZtXVXZ*tau0 + g.g - 2 g.B ; mu2 = 1/tau0 constant => g.g = t1*tau0, g.B = zw*tau0
         var2 = zxz * M.tau0 + t1 * M.tau0 - 2.0 * zw * M.tau0;
     }
-    const double var1 = var2 * M.varRatio;
+    // variance ratio of this variant's MAC category (Main.cpp:395-404 -> assignVarianceRatio; MAC after imputation, Main.cpp:367)
+    const double MACafter = fmin(altCount, 2.0 * (double)N - altCount);
+    double varRatio = M.varRatio;
+    if (M.n_cate > 1) {
+        varRatio = M.cate_ratio[M.n_cate - 1];                          // above the last bound
+        for (int c = M.n_cate - 2; c >= 0; c--)
+            if (MACafter <= M.cate_max[c]) varRatio = M.cate_ratio[c];  // also MAC <= cate_min[0] -> first category
+    }
+    const double var1 = var2 * varRatio;
     const double S = (r0 - saz) / M.tau0;
     double stat = S * S / var1;
     double pval_noadj;
@@ -238,7 +251,6 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     // ---- exact test of rare variants (binary traits): MAC after imputation <= max_MAC_for_ER and a score beyond the SPA
     // cutoff (Main.cpp:408-422, SAIGE_test.cpp:426-431).  The carriers (<= SGB_ER_MAXK of them, since every one holds at
     // least one minor allele) are collected in sample order; one thread enumerates their case / control assignments ----
-    const double MACafter = fmin(altCount, 2.0 * (double)N - altCount);
     const bool isER = M.binary && MACafter <= M.er_max_mac && nz <= (double)SGB_ER_MAXK && (StdStat > M.spa_cutoff || isnan(StdStat));
     if (isER) {
         if (tid == 0) er_cnt = 0;
@@ -501,8 +513,29 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     CUDA_OK(h, cudaMalloc((void **)&s->d_offset, sizeof(double) * N));
     CUDA_OK(h, cudaMemset(s->d_offset, 0, sizeof(double) * N));
     M.offset = s->d_offset; M.firth = 0; M.firth_se_from_fit = 1; M.firth_cutoff = 0.01;
-    M.er_max_mac = -1.0; M.mu_sum = 0.0;
+    M.er_max_mac = -1.0; M.mu_sum = 0.0; M.n_cate = 1;
     for (int64_t i = 0; i < N; i++) M.mu_sum += mu[i];
+    return 0;
+}
+
+extern "C" int sgb_step2_set_variance_ratios(sgb_ctx *h, int n_cate, const double *ratios, const double *min_mac_exclude,
+                                             const double *max_mac_include)
+{
+    sgb_step2 *s = h->step2;
+    if (!s || !s->d_vec) return sgb_fail(h, "step2: call sgb_step2_set_model first");
+    if (n_cate < 1 || n_cate > S2_MAXCATE) return sgb_fail(h, "step2: %d variance-ratio categories, supported 1..%d", n_cate, S2_MAXCATE);
+    s2_model &M = s->M;
+    if (n_cate == 1) { M.n_cate = 1; M.varRatio = ratios[0]; return 0; }
+    for (int c = 0; c < n_cate; c++) {
+        if (c + 1 < n_cate && !(max_mac_include[c] > min_mac_exclude[c]))
+            return sgb_fail(h, "step2: variance-ratio category %d is empty (%g, %g]", c + 1, min_mac_exclude[c], max_mac_include[c]);
+        if (c > 0 && min_mac_exclude[c] != max_mac_include[c - 1])
+            return sgb_fail(h, "step2: variance-ratio categories must tile the MAC axis (category %d starts at %g, the one before ends at %g)",
+                            c + 1, min_mac_exclude[c], max_mac_include[c - 1]);
+        M.cate_ratio[c] = ratios[c]; M.cate_min[c] = min_mac_exclude[c];
+        M.cate_max[c] = c + 1 < n_cate ? max_mac_include[c] : INFINITY;
+    }
+    M.n_cate = n_cate; M.varRatio = ratios[0];
     return 0;
 }
 

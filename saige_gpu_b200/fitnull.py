@@ -21,7 +21,7 @@ What follows the reference, block by block:
   extractVarianceRatio (autosomal markers only unless includeNonautoMarkersforVarRatio)      FG.R:2152-2423
 
 Not provided (the reference's sparse-GRM machinery is out of scope): useSparseGRMtoFitNULL,
-useSparseGRMforVarRatio, isCateVarianceRatio, isLowMemLOCO.  They raise, they are never ignored.
+useSparseGRMforVarRatio, isLowMemLOCO.  They raise, they are never ignored.
 
 Randomness: the reference draws the Hutchinson probes, the variance-ratio hold-out set and the marker order from R's RNG
 (set.seed(1) in the CLI, set_seed(200) in GetTrace).  The probes reproduce R's stream bit for bit (step1.ProbeStream,
@@ -128,9 +128,11 @@ def _chr_number(c):
 
 
 def write_variance_ratio(path, ratio):
-    """write.table(varRatioTable, quote = F, col.names = F, row.names = F) of FG.R:2413-2417: `<ratio> null 1`."""
+    """write.table(varRatioTable, quote = F, col.names = F, row.names = F) of FG.R:2413-2417: `<ratio> null <category>`,
+    one line per MAC category."""
     with open(path, "w") as f:
-        f.write("%.15g null 1\n" % float(ratio))
+        for k, r in enumerate(np.asarray(ratio, dtype=np.float64).reshape(-1)):
+            f.write("%.15g null %d\n" % (float(r), k + 1))
 
 
 def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phenoFile="", phenoCol="", traitType="binary",
@@ -149,9 +151,9 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
     covarColList = list(covarColList or [])
     qCovarCol = list(qCovarCol or [])
     say = print if verbose else (lambda *a, **k: None)
-    if useSparseGRMtoFitNULL or useSparseGRMforVarRatio or isCateVarianceRatio or isLowMemLOCO:
-        raise NotImplementedError("sparse-GRM fitting / variance ratios, categorical variance ratios and isLowMemLOCO are "
-                                  "not provided by the B200 back end (full-GRM path only)")
+    if useSparseGRMtoFitNULL or useSparseGRMforVarRatio or isLowMemLOCO:
+        raise NotImplementedError("sparse-GRM fitting / variance ratios and isLowMemLOCO are not provided by the B200 back "
+                                  "end (full-GRM path only)")
     if nThreads > 1:
         raise SaigeInputError("setting threads via RcppParallel is not allowed")          # FG.R:785
     if traitType not in ("binary", "quantitative"):
@@ -261,7 +263,10 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
     rng = np.random.default_rng(seed)
     vr_idx = None
     if not skipVarianceRatioEstimation:
-        geno.setminMAC_VarianceRatio(20, -1, True)
+        if isCateVarianceRatio:       # FG.R:1082-1086: every marker inside the MAC categories is held out, random ones above
+            geno.setminMAC_VarianceRatio(min(cateVarRatioMinMACVecExclude), max(cateVarRatioMaxMACVecInclude), True)
+        else:
+            geno.setminMAC_VarianceRatio(20, -1, True)
         vr_idx = np.unique(rng.integers(0, len(bim_chr), size=1000)).astype(np.int32)       # FG.cpp:866-868: 1000 draws, unique
     geno.setminMAFforGRM(minMAFforGRM)
     geno.setmaxMissingRateforGRM(maxMissingRateforGRM)
@@ -342,13 +347,20 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
         else:
             chr_of = np.asarray(bim_chr)[qc]
             n_avail = geno.M
-        order = rng.permutation(n_avail)                                                       # sample(MACindex), FG.R:2233
-        if not includeNonautoMarkersforVarRatio:
-            order = order[(chr_of[order] >= 1) & (chr_of[order] <= 22)]                        # FG.R:2286
-        ratio, ratios = step1.extractVarianceRatio(geno, model, family, order, numMarkers=numMarkersForVarRatio,
-                                                   maxiterPCG=maxiterPCG, tolPCG=tolPCG, ratioCVcutoff=ratioCVcutoff)
+        auto = np.ones(n_avail, dtype=bool) if includeNonautoMarkersforVarRatio else (chr_of >= 1) & (chr_of <= 22)   # FG.R:2286
+        if isCateVarianceRatio:
+            mac = np.asarray(geno.getMACVec_forVarRatio() if use_vr else geno.getMACVec())
+            per_cat = step1.extractVarianceRatio_cate(geno, model, family, mac, auto, rng, cateVarRatioMinMACVecExclude,
+                                                      cateVarRatioMaxMACVecInclude, cateVarRatioIndexVec,
+                                                      numMarkers=numMarkersForVarRatio, maxiterPCG=maxiterPCG, tolPCG=tolPCG,
+                                                      ratioCVcutoff=ratioCVcutoff)
+            ratio = [r for r, _ in per_cat]
+        else:
+            order = rng.permutation(n_avail)                                                   # sample(MACindex), FG.R:2233
+            ratio, ratios = step1.extractVarianceRatio(geno, model, family, order[auto[order]], numMarkers=numMarkersForVarRatio,
+                                                       maxiterPCG=maxiterPCG, tolPCG=tolPCG, ratioCVcutoff=ratioCVcutoff)
         write_variance_ratio(varRatioFile, ratio)
-        say("varRatio_null", ratio, "from", len(ratios), "markers")
+        say("varRatio_null", ratio)
     if own_geno:
         geno.closeGenoFile_plink()                    # FG.R:1352; a handle passed in stays open for the caller (e.g. step 2)
     return dict(modglmm=modglmm, varianceRatio=ratio, modelFile=modelOut, varRatioFile=varRatioFile)

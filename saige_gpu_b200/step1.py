@@ -335,3 +335,32 @@ def extractVarianceRatio(geno, model, family, marker_order, numMarkers=30, maxit
         else:
             break
     return float(np.mean(ratios)), ratios
+
+
+def extractVarianceRatio_cate(geno, model, family, mac_of_marker, marker_ok, rng, cateVarRatioMinMACVecExclude=(10, 20.5),
+                              cateVarRatioMaxMACVecInclude=(20.5,), cateVarRatioIndexVec=None, numMarkers=30, **kw):
+    """The categorical branch of extractVarianceRatio (FG.R:2244-2280 + the per-category loop :2287-2411): one ratio per MAC
+    category, category k = (min[k], max[k]], the last one open-ended when max is one entry shorter; categories switched off
+    in cateVarRatioIndexVec get the ratio 1.  `mac_of_marker`: MAC of every candidate marker (the hold-out store or the GRM
+    store), `marker_ok`: which of them may be used (autosomes), `rng`: numpy generator standing for R's sample()."""
+    lo, hi = list(cateVarRatioMinMACVecExclude), list(cateVarRatioMaxMACVecInclude)
+    idxvec = [1] * len(lo) if cateVarRatioIndexVec is None else list(cateVarRatioIndexVec)
+    ncat = len(idxvec)
+    mac = np.asarray(mac_of_marker, dtype=np.float64)
+    out = []
+    for k in range(ncat):
+        if k < ncat - 1 or len(hi) == ncat:
+            sel, label = (mac > lo[k]) & (mac <= hi[k]), "%g< MAC <= %g" % (lo[k], hi[k])
+        else:
+            sel, label = mac > lo[k], "%g< MAC" % lo[k]
+        if idxvec[k] != 1:
+            out.append((1.0, []))
+            continue
+        members = np.nonzero(sel)[0]
+        if len(members) < numMarkers:
+            raise ValueError("ERROR! number of genetic variants in %s is lower than %d\nPlease include more markers in this MAC "
+                             "category in the plink file" % (label, numMarkers))
+        order = rng.permutation(members)
+        order = order[np.asarray(marker_ok)[order]]
+        out.append(extractVarianceRatio(geno, model, family, order, numMarkers=numMarkers, **kw))
+    return out

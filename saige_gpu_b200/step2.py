@@ -50,24 +50,39 @@ def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
                 sampleID=[str(s) for s in m["sampleID"]])
 
 
-def Get_Variance_Ratio(varianceRatioFile):
-    """readInGLMM.R:358-: first 'null' row of the step-1 variance-ratio file."""
+def Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude=(10, 20.5), cateVarRatioMaxMACVecInclude=(20.5,)):
+    """readInGLMM.R:358-435: the 'null' rows of the step-1 variance-ratio file (3 columns: value, null / sparse, category;
+    files of versions < 1.0.6 hold the values only).  One row: a float.  Several rows: categorical variance ratios, returned
+    as a list whose length must match the MAC category bounds."""
     rows = [l.split() for l in open(varianceRatioFile) if l.strip()]
-    for r in rows:
-        if len(r) < 2 or r[1] == "null":
-            return float(r[0])
-    return float(rows[0][0])
+    if not rows:
+        raise ValueError("variance ratio file %s is empty" % varianceRatioFile)
+    if len(rows[0]) == 3:
+        vals = [float(r[0]) for r in rows if r[1] == "null"]
+        if any(r[1] == "sparse" and not (0.9999 <= float(r[0]) <= 1.0001) for r in rows):
+            raise ValueError("sparse GRM is not specified but it was used for estimating variance ratios in Step 1")
+    else:
+        vals = [float(r[0]) for r in rows]
+    if len(vals) == 1:
+        return vals[0]
+    if len(vals) != len(cateVarRatioMinMACVecExclude):
+        raise ValueError("ERROR! The number of variance ratios are different from the length of cateVarRatioMinMACVecExclude")
+    if len(cateVarRatioMinMACVecExclude) != len(cateVarRatioMaxMACVecInclude) + 1:
+        raise ValueError("ERROR! The length of cateVarRatioMaxMACVecInclude does not match with the lenght of cateVarRatioMinMACVecExclude (-1)")
+    return vals
 
 
 def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioFile, SAIGEOutputFile=None, chrom="",
                  LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
                  is_output_moreDetails=True, se_two_sided=True, rank=0, world=1, is_Firth_beta=False, pCutoffforFirth=0.01,
-                 firth_se_from_fit=True, max_MAC_for_ER=4.0):
+                 firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
+                 cateVarRatioMaxMACVecInclude=(20.5,)):
     """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the .bim
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
     model = ReadModel(GMMATmodelFile, chrom, LOCO)
-    ratio = Get_Variance_Ratio(varianceRatioFile)
+    ratio = Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude)
+    model["cateVarRatioMinMACVecExclude"], model["cateVarRatioMaxMACVecInclude"] = cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude
     fam = [l.split()[1] for l in open(famFile)]
     bim = [l.split() for l in open(bimFile)]
     where = {s: i for i, s in enumerate(fam)}

@@ -254,7 +254,7 @@ def test_options_and_refusals(golden_dir, tmp_path):
     from saige_gpu_b200 import fitnull
     base = dict(plinkFile=os.path.join(golden_dir, "chr22_1000"), phenoFile=os.path.join(golden_dir, "pheno_1000samples.txt"),
                 phenoCol="y_binary", covarColList=["x1", "x2"], sampleIDColinphenoFile="IID", outputPrefix=str(tmp_path / "x"))
-    for bad in (dict(useSparseGRMtoFitNULL=True), dict(isCateVarianceRatio=True), dict(isLowMemLOCO=True)):
+    for bad in (dict(useSparseGRMtoFitNULL=True), dict(useSparseGRMforVarRatio=True), dict(isLowMemLOCO=True)):
         with pytest.raises(NotImplementedError):
             fitnull.fitNULLGLMM(OracleBackend(), **{**base, **bad})
     with pytest.raises(fitnull.SaigeInputError):
@@ -278,6 +278,42 @@ def test_options_and_refusals(golden_dir, tmp_path):
     assert m["isCovariateOffset"] is True and m["LOCO"] is False and "LOCOResult" not in m
     assert abs(np.mean(m["y"])) < 1e-12 and abs(np.std(m["y"]) - 1) < 0.01              # rank-based inverse normal scores
     assert m["theta"][0] > 0 and r["varianceRatio"] > 0
+
+
+def test_categorical_variance_ratios(golden_dir, bim22, tmp_path):
+    """isCateVarianceRatio: every marker with 10 <= MAC < 20.5 is held out of the GRM (FG.cpp:497-501), one ratio per MAC
+    category is estimated and written as `<ratio> null <k>`; step 2 picks the ratio by the variant's MAC."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import step1
+    from saige_gpu_b200.rdata import load_rda
+    from saige_gpu_b200.step2 import Get_Variance_Ratio
+    out = str(tmp_path / "cate")
+    be = OracleBackend()
+    r = _run(be, golden_dir, bim22, out, isCateVarianceRatio=True, LOCO=False)
+    lines = [l.split() for l in open(out + ".varianceRatio.txt")]
+    assert [l[1:] for l in lines] == [["null", "1"], ["null", "2"]]
+    vr = Get_Variance_Ratio(out + ".varianceRatio.txt")
+    assert isinstance(vr, list) and len(vr) == 2 and np.allclose(vr, r["varianceRatio"], rtol=1e-14)
+    assert all(0.5 < v < 1.5 for v in vr) and vr[0] != vr[1]
+    mac_vr = np.asarray(be.getMACVec_forVarRatio())
+    assert ((mac_vr >= 10) & (mac_vr < 20.5)).sum() > 300 and (mac_vr < 10).sum() == 0          # the whole category is in the hold-out store
+    assert (np.asarray(be.getMACVec()) >= 20.5).all() or (np.asarray(be.getMACVec()) < 10).any()  # ... and none of it in the GRM
+    with pytest.raises(ValueError):
+        Get_Variance_Ratio(out + ".varianceRatio.txt", (10, 20.5, 30), (20.5, 30))
+    # a category switched off gets 1; too few markers in a category is an error, as in the reference
+    m = load_rda(out + ".rda")["modglmm"]
+    model = dict(fitted_values=m["fitted.values"].ravel(), linear_predictors=m["linear.predictors"].ravel(), y=m["y"], X=m["X"],
+                 theta=m["theta"], obj_noK=dict(m["obj.noK"]), traitType="binary")
+    rng = np.random.default_rng(3)
+    pc = step1.extractVarianceRatio_cate(be, model, step1.Binomial, mac_vr, np.ones(len(mac_vr), bool), rng, (10, 20.5), (20.5,), [0, 1])
+    assert pc[0] == (1.0, []) and 0.5 < pc[1][0] < 1.5
+    with pytest.raises(ValueError):
+        step1.extractVarianceRatio_cate(be, model, step1.Binomial, mac_vr, np.ones(len(mac_vr), bool), rng, (10, 20.5), (20.5,),
+                                        numMarkers=5000)
+    # step 2 (oracle) with the two ratios: the ratio follows the variant's MAC category
+    M = S2.read_model(m, LOCO=False)
+    M.update(varRatio=vr, cateVarRatioMinMACVecExclude=(10, 20.5), cateVarRatioMaxMACVecInclude=(20.5,))
+    assert [S2.assign_variance_ratio(M, x) for x in (3, 10, 10.5, 20.5, 21, 900)] == [vr[0], vr[0], vr[0], vr[0], vr[1], vr[1]]
 
 
 # ---- through the C ABI ------------------------------------------------------------------------------------------------------

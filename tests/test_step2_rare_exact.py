@@ -209,3 +209,35 @@ def test_gpu_exact_test_of_rare_variants_vs_oracle(identity):
     with pytest.raises(SaigeB200Error):
         g.setMaxMACforER(11.0)
     g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_categorical_variance_ratios_vs_oracle():
+    """assignVarianceRatio (SAIGE_test.cpp:801-833): the kernel picks the variance ratio by the variant's MAC category."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import SaigeB200, SaigeB200Error
+    n_fam, N = 900, 800
+    M, pos, bed, nm = rare_variant_set(21, n_fam, N, identity=True)
+    g = SaigeB200(device=0)
+    for ratios, lo, hi in (([0.8, 1.1], (2, 4.5), (4.5,)), ([0.7, 0.9, 1.2], (1, 3, 5), (3, 5))):
+        M.update(varRatio=ratios, cateVarRatioMinMACVecExclude=lo, cateVarRatioMaxMACVecInclude=hi)
+        g.setSAIGEobjInCPP(M, ratios, 2.0, pos)
+        g.setMaxMACforER(4.0)                          # (the saddle point of a singleton rarely converges; the exact test is the reference's path)
+        out = g.mainMarkerInCPP(bed, n_fam, nm)
+        seen = set()
+        for m in range(nm):
+            r = S2.test_marker(M, S2.plink_marker(bed, n_fam, m, pos), max_MAC_for_ER=4.0)
+            got = dict(zip(g.STEP2_COLUMNS, out[m]))
+            seen.add(round(got["var"] / got["var2"], 12))
+            for col, oc in (("BETA", "BETA"), ("SE", "SE"), ("Tstat", "Tstat"), ("var", "var"), ("p.value", "p_value"),
+                            ("p.value.NA", "p_value_NA")):
+                assert abs(got[col] - r[oc]) <= 1e-6 * abs(r[oc]) + 1e-300, (ratios, m, col, got[col], r[oc])
+        assert seen == set(ratios)
+    with pytest.raises(SaigeB200Error):
+        g.setVarianceRatios([0.8, 1.1], (2, 4.5), (5.0,))          # categories do not tile the MAC axis
+    # back to a single ratio
+    M["varRatio"] = 0.91
+    g.setSAIGEobjInCPP(M, 0.91, 2.0, pos)
+    out = g.mainMarkerInCPP(bed, n_fam, nm)
+    assert np.allclose(out[:, 7] / out[:, 19], 0.91, rtol=1e-12)
+    g.close()
