@@ -298,11 +298,9 @@ static void symv_launch(sgb_ctx *h, const sgb_dense *d, const double *B, int64_t
 {
     // items are ordered [mirrored chunks (part A + B) ..., diagonal blocks (part A only)]
     const size_t smem_b = sizeof(double) * (size_t)KC * (DG_BLOCK + 2 * DG_CHUNK), smem_a = sizeof(double) * (size_t)KC * (DG_BLOCK + DG_CHUNK);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(dense_symv_kernel<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-        cudaFuncSetAttribute(dense_symv_kernel<KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-        attr_set = true;
+    if (sgb_first_on_device(h->device, SGB_SITE_SYMV_BASE + KC)) {
+        cudaFuncSetAttribute(dense_symv_kernel<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);       // a failure here
+        cudaFuncSetAttribute(dense_symv_kernel<KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);      // surfaces at the caller's launch check
     }
     if (d->n_items_b)
         dense_symv_kernel<KC, true><<<(unsigned)d->n_items_b, 256, smem_b, h->stream>>>(d->pool, d->d_items, 0, B, N, Y);

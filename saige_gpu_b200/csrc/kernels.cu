@@ -171,11 +171,8 @@ int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_
     if (nrows <= 0) return 0;
     int64_t B = (N + 3) / 4;
     if (!identity && B0 <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (sgb_first_on_device(h->device, SGB_SITE_REPACK))
             CUDA_OK(h, cudaFuncSetAttribute(repack_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
         repack_gather_kernel<<<(unsigned)nrows, 256, (size_t)B0, h->stream>>>(d_bed, B0, d_src_rows, d_fill, d_sub_idx, N, d_out, out_stride);
         LAUNCH_CHECK(h);
         return 0;

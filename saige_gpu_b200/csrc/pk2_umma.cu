@@ -503,17 +503,15 @@ int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_p
     // k-chunks of one row tile meet in `out` with atomics; a single chunk writes every element once (out was zeroed by
     // the previous recombine), unless the caller accumulates several launches (dense-GRM build over marker shards)
     const int use_atomic = (kchunks > 1 || h->umma_accumulate) ? 1 : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (sgb_first_on_device(h->device, SGB_SITE_UMMA)) {
         CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
     }
+#ifdef SGB_ABLATION          // timing experiments only (make ABLATION=1): the product build reads no environment
     static const int force_stages = getenv("SGB_UMMA_STAGES") ? atoi(getenv("SGB_UMMA_STAGES")) : 0;
-#ifdef SGB_ABLATION
     static const int dbg = getenv("SGB_UMMA_DBG") ? atoi(getenv("SGB_UMMA_DBG")) : 0;
 #else
-    const int dbg = 0;
+    const int force_stages = 0, dbg = 0;
 #endif
     // balanced passes of N <= 128 accumulator columns (multiples of 16): 224 columns run as 112 + 112
     const int npass = (nrows + 127) / 128;

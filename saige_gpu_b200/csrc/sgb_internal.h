@@ -174,6 +174,18 @@ int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d
 int k_grid_blocks(sgb_ctx *h, int64_t n);
 #define SGB_PART_BLOCKS 256   // partial-sum slots per column of the deterministic reductions
 
+// cudaFuncSetAttribute acts on the current device: every launch site that raises a kernel's dynamic shared-memory limit
+// does so once per device ordinal (a process may hold handles on several devices), not once per process
+enum sgb_attr_site { SGB_SITE_REPACK = 0, SGB_SITE_UMMA, SGB_SITE_STEP2, SGB_SITE_SYMV_BASE /* + KC, KC <= 8 */, SGB_SITE_COUNT = SGB_SITE_SYMV_BASE + 9 };
+inline bool sgb_first_on_device(int device, int site)
+{
+    static unsigned char done[SGB_SITE_COUNT][64];
+    if (device < 0 || device >= 64) return true;
+    if (done[site][device]) return false;
+    done[site][device] = 1;
+    return true;
+}
+
 // solver.cu / dist.cu / step2.cu / dense_grm.cu
 int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int loco);
 int sgb_gt_times_cols(sgb_ctx *h, const double *D, int k, double *raw);   // raw (ld rowsT) = G^T D (ld rowsG), tensor engine

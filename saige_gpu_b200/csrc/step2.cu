@@ -605,11 +605,9 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     size_t ob = s->out_elems * sizeof(double);
     SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, 2 * obytes));
     s->out_elems = ob / sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (sgb_first_on_device(h->device, SGB_SITE_STEP2)) {
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
-        attr_set = true;
     }
     int cur = 0;
     int64_t held_m0[2] = {-1, -1}, held_nm[2] = {0, 0};
