@@ -5,6 +5,8 @@ SAIGE_Test_main.R:61-420, R/readInGLMM.R:39-170 `ReadModel`, R/SAIGE_SPATest_Mar
 null model (.rda written by step 1), the variance ratio, the PLINK files; match model samples to .fam rows; stream
 marker rows to the C ABI (`sgb_step2_test_markers` = the body of mainMarkerInCPP, Main.cpp:149-560); write the result
 table with the reference's column names.  No numerical work happens here."""
+import os
+
 import numpy as np
 
 from .rdata import load_rda
@@ -76,15 +78,15 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
                  LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
                  is_output_moreDetails=True, se_two_sided=True, rank=0, world=1, is_Firth_beta=False, pCutoffforFirth=0.01,
                  firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
-                 cateVarRatioMaxMACVecInclude=(20.5,)):
-    """Returns the result table (list of dict rows); writes it tab-separated to SAIGEOutputFile when given.
+                 cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True):
+    """Returns the result table (list of dict rows; with return_rows=False only the number of tested variants, for scans
+    whose table should not be held in memory); writes it tab-separated to SAIGEOutputFile when given, chunk by chunk.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the .bim
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
     model = ReadModel(GMMATmodelFile, chrom, LOCO)
     ratio = Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude)
     model["cateVarRatioMinMACVecExclude"], model["cateVarRatioMaxMACVecInclude"] = cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude
     fam = [l.split()[1] for l in open(famFile)]
-    bim = [l.split() for l in open(bimFile)]
     where = {s: i for i, s in enumerate(fam)}
     missing = [s for s in model["sampleID"] if s not in where]
     if missing:
@@ -93,35 +95,96 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
     geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
     geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
     geno.setMaxMACforER(max_MAC_for_ER)                 # exact test of rare variants (step2_SPAtests.R:126 --max_MAC_for_ER, default 4)
-    raw = np.fromfile(bedFile, dtype=np.uint8)
-    if raw[0] != 0x6C or raw[1] != 0x1B or raw[2] != 0x01:
+    with open(bedFile, "rb") as f:
+        magic = f.read(3)
+    if magic != b"\x6c\x1b\x01":
         raise ValueError("%s is not a SNP-major PLINK .bed" % bedFile)
     n_fam, B0 = len(fam), (len(fam) + 3) // 4
-    body = raw[3:]
-    rows = []
-    per_rank = (len(bim) + world - 1) // world
-    lo, hi = min(len(bim), rank * per_rank), min(len(bim), (rank + 1) * per_rank)
-    for m0 in range(lo, hi, markers_per_chunk):
-        m1 = min(hi, m0 + markers_per_chunk)
-        res = geno.mainMarkerInCPP(body[m0 * B0:m1 * B0], n_fam, m1 - m0, min_MAF, min_MAC, max_missing, se_two_sided)
-        for j in range(m1 - m0):
-            r = res[j]
-            if r[0] != 1.0:
-                continue                                   # filtered: not written (Main.cpp:296 `continue`)
-            b = bim[m0 + j]
-            row = {"CHR": b[0], "POS": b[3], "MarkerID": b[1], "Allele1": b[5], "Allele2": b[4]}     # alt-first: A1 = ALT = Allele2
-            for name, v in zip(geno.STEP2_COLUMNS[1:19], r[1:19]):
-                row[name] = v
-            row["Is.SPA"] = bool(r[10])
-            row["Is.Firth"], row["Firth.converged"] = bool(r[20]), bool(r[21])
-            rows.append(row)
-    if SAIGEOutputFile:
-        cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
-        with open(SAIGEOutputFile, "w") as f:
-            f.write("\t".join(cols) + "\n")
-            for row in rows:
-                f.write("\t".join(_fmt(row[c]) for c in cols) + "\n")
-    return rows
+    n_bim = _count_lines(bimFile)
+    # the .bed is mapped, not read: a chunk of raw rows is paged in when it is handed to the library, so a rank touches only
+    # its own slice of a file that can be far larger than host memory (BASELINE config 5: 10M variants x 50 KB)
+    body = np.memmap(bedFile, dtype=np.uint8, mode="r", offset=3)
+    if body.size < n_bim * B0:
+        raise ValueError("%s holds fewer than %d markers x %d bytes" % (bedFile, n_bim, B0))
+    per_rank = (n_bim + world - 1) // world
+    lo, hi = min(n_bim, rank * per_rank), min(n_bim, (rank + 1) * per_rank)
+    cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
+    rows = [] if return_rows else None
+    out = open(SAIGEOutputFile, "w") if SAIGEOutputFile else None
+    n_tested = 0
+    try:
+        if out:
+            out.write("\t".join(cols) + "\n")
+        bim_iter = _bim_lines(bimFile, lo, hi)
+        for m0 in range(lo, hi, markers_per_chunk):
+            m1 = min(hi, m0 + markers_per_chunk)
+            bim = [next(bim_iter) for _ in range(m1 - m0)]
+            res = geno.mainMarkerInCPP(body[m0 * B0:m1 * B0], n_fam, m1 - m0, min_MAF, min_MAC, max_missing, se_two_sided)
+            keep = np.nonzero(res[:, 0] == 1.0)[0]      # the others were filtered: not written (Main.cpp:296 `continue`)
+            n_tested += len(keep)
+            if out and len(keep):
+                out.write(_format_chunk(res[keep], [bim[j] for j in keep], cols, geno.STEP2_COLUMNS))
+            if return_rows:
+                for j in keep:
+                    r, b = res[j], bim[j]
+                    row = {"CHR": b[0], "POS": b[3], "MarkerID": b[1], "Allele1": b[5], "Allele2": b[4]}     # alt-first: A1 = ALT = Allele2
+                    for name, v in zip(geno.STEP2_COLUMNS[1:19], r[1:19]):
+                        row[name] = v
+                    row["Is.SPA"] = bool(r[10])
+                    row["Is.Firth"], row["Firth.converged"] = bool(r[20]), bool(r[21])
+                    rows.append(row)
+    finally:
+        if out:
+            out.close()
+    return rows if return_rows else n_tested
+
+
+def _count_lines(path):
+    n, last = 0, b"\n"
+    with open(path, "rb") as f:
+        while True:
+            buf = f.read(1 << 24)
+            if not buf:
+                break
+            n += buf.count(b"\n")
+            last = buf[-1:]
+    return n + (0 if last == b"\n" else 1)
+
+
+def _bim_lines(path, lo, hi):
+    """.bim rows lo .. hi-1 (split), without holding the rest of the file."""
+    with open(path) as f:
+        for i, l in enumerate(f):
+            if i >= hi:
+                break
+            if i >= lo:
+                yield l.split()
+
+
+_INT_COLS = {"N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het"}
+
+
+def _format_chunk(res, bim, cols, table_cols):
+    """Tab-separated lines of one chunk, numbers with 6 significant digits like the reference's ofstream (Main.cpp:2437-2560);
+    formatted column-wise with numpy, one join per line."""
+    idx = {c: i for i, c in enumerate(table_cols)}
+    fields = []
+    for c in cols:
+        if c == "CHR":
+            fields.append([b[0] for b in bim])
+        elif c == "POS":
+            fields.append([b[3] for b in bim])
+        elif c == "MarkerID":
+            fields.append([b[1] for b in bim])
+        elif c == "Allele1":
+            fields.append([b[5] for b in bim])
+        elif c == "Allele2":
+            fields.append([b[4] for b in bim])
+        elif c == "Is.SPA":
+            fields.append(np.where(res[:, idx[c]] != 0, "true", "false").tolist())
+        else:
+            fields.append(np.char.mod("%.6g", res[:, idx[c]]).tolist())
+    return "".join("\t".join(t) + "\n" for t in zip(*fields))
 
 
 def _fmt(v):

@@ -107,6 +107,9 @@ def test_step2_variant_sharding_is_a_partition(tmp_path):
         def setFirth(self, *a, **k):
             pass
 
+        def setMaxMACforER(self, *a):
+            pass
+
         def mainMarkerInCPP(self, rows, nf, nm, *a):
             flat = np.asarray(rows).reshape(-1)[:nm * B0]
             # recover where this contiguous chunk starts in the file body; keep every third marker "untested"
@@ -130,3 +133,22 @@ def test_step2_variant_sharding_is_a_partition(tmp_path):
         assert ids == [r["MarkerID"] for r in full]
         sizes = [len(part) for part in parts]
         assert max(sizes) - min(sizes) <= (100 + world - 1) // world      # contiguous, near-equal ranges
+    # streamed to files, no table in memory: the rank files concatenated (header once) are the single-rank file
+    def run_file(rank, world, path):
+        return step2.SPAGMMATtest(Stub(), p + ".bed", p + ".bim", p + ".fam", os.path.join(gd, "example_binary.rda"),
+                                  os.path.join(gd, "example_binary.varianceRatio.txt"), SAIGEOutputFile=path, chrom="1", LOCO=True,
+                                  markers_per_chunk=7, rank=rank, world=world, return_rows=False)
+    assert run_file(0, 1, str(tmp_path / "all.txt")) == len(full)
+    whole = open(str(tmp_path / "all.txt")).read().splitlines()
+    assert len(whole) == len(full) + 1 and whole[0].split("\t")[:5] == ["CHR", "POS", "MarkerID", "Allele1", "Allele2"]
+    got = [whole[0]]
+    for r in range(3):
+        assert run_file(r, 3, str(tmp_path / ("part%d.txt" % r))) == len(parts_of(full, r, 3))
+        got += open(str(tmp_path / ("part%d.txt" % r))).read().splitlines()[1:]
+    assert got == whole
+
+
+def parts_of(full, rank, world, n=100):
+    per = (n + world - 1) // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+    return [r for r in full if lo <= int(r["MarkerID"][2:]) - 1 < hi]

@@ -75,6 +75,61 @@ def test_oracle_reproduces_reference_golden_table(golden_dir):
     assert sum(g["Is.SPA"] == "true" for g in gold) == 2                  # rs23, rs38 go through SPA_fast
 
 
+def test_driver_writes_the_reference_table_as_a_file(golden_dir, tmp_path):
+    """SPAGMMATtest's host side (model / ratio / .fam matching, mapped .bed, chunked writing, number formats) with the
+    device call answered by the oracle: the file it writes IS the reference's golden table, header and all 32 rows."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import step2
+    from saige_gpu_b200.api import SaigeB200
+
+    class OracleDevice:
+        STEP2_COLUMNS = SaigeB200.STEP2_COLUMNS
+
+        def setSAIGEobjInCPP(self, model, ratio, cutoff, pos):
+            self.M = dict(model, varRatio=ratio)
+            self.M["XV"] = (np.asarray(model["X"]) * np.asarray(model["mu2"])[:, None]).T
+            self.pos, self.cutoff = np.asarray(pos), cutoff
+
+        def setFirth(self, *a, **k):
+            pass
+
+        def setMaxMACforER(self, v):
+            self.er = v
+
+        def mainMarkerInCPP(self, rows, n_fam, nm, min_MAF, min_MAC, max_missing, se_two_sided):
+            out = np.full((nm, len(self.STEP2_COLUMNS)), np.nan)
+            body = np.asarray(rows)
+            for j in range(nm):
+                r = S2.test_marker(self.M, S2.plink_marker(body, n_fam, j, self.pos), min_MAF, min_MAC, max_missing, self.cutoff,
+                                   se_two_sided, max_MAC_for_ER=self.er)
+                out[j, 0] = 0.0 if r is None else 1.0
+                if r is None:
+                    continue
+                G = S2.plink_marker(body, n_fam, j, self.pos)
+                y = self.M["y"]
+                out[j, 1:13] = [r["AC_Allele2"], r["AF_Allele2"], r["MissingRate"], r["BETA"], r["SE"], r["Tstat"], r["var"],
+                                r["p_value"], r["p_value_NA"], float(r["Is_SPA"]), r["AF_case"], r["AF_ctrl"]]
+                out[j, 13:19] = [r["N_case"], r["N_ctrl"], np.sum((G == 2) & (y == 1)), np.sum((G == 1) & (y == 1)),
+                                 np.sum((G == 2) & (y == 0)), np.sum((G == 1) & (y == 0))]
+            return out
+
+    p = os.path.join(golden_dir, "step2_100markers")
+    path = str(tmp_path / "out.txt")
+    n = step2.SPAGMMATtest(OracleDevice(), p + ".bed", p + ".bim", p + ".fam", os.path.join(golden_dir, "example_binary.rda"),
+                           os.path.join(golden_dir, "example_binary.varianceRatio.txt"), SAIGEOutputFile=path, chrom="1", LOCO=True,
+                           min_MAC=20, markers_per_chunk=9, return_rows=False)
+    mine = [l.split("\t") for l in open(path).read().splitlines()]
+    gold = [l.split("\t") for l in open(os.path.join(golden_dir, "step2_100markers_golden.txt")).read().splitlines()]
+    assert n == 32 and len(mine) == len(gold) == 33 and mine[0] == gold[0]
+    for a, b in zip(mine[1:], gold[1:]):
+        for name, x, y in zip(gold[0], a, b):
+            if name in ("CHR", "POS", "MarkerID", "Allele1", "Allele2", "Is.SPA", "N_case", "N_ctrl", "N_case_hom", "N_case_het",
+                        "N_ctrl_hom", "N_ctrl_het", "AC_Allele2"):
+                assert x == y, (name, a[2], x, y)
+            else:
+                assert abs(float(x) - float(y)) <= TOL_PRINT * abs(float(y)) + 1e-300, (name, a[2], x, y)
+
+
 @pytest.mark.gpu
 def test_gpu_step2_reproduces_reference_golden_table(golden_dir, tmp_path):
     from saige_gpu_b200 import SaigeB200, step2
