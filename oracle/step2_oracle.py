@@ -32,9 +32,9 @@ EPS25 = np.finfo(np.float64).eps ** 0.25          # tol = eps^0.25 (SAIGE_test.c
 def read_model(modglmm, chrom=None, LOCO=True):
     """ReadModel (readInGLMM.R:39-170): returns the dict of arrays step 2 uses."""
     m = dict(modglmm)
-    mu = np.asarray(m["fitted.values"], dtype=np.float64).ravel()
-    res = np.asarray(m["residuals"], dtype=np.float64).ravel()
-    noK = m["obj.noK"]
+    mu = None if m.get("fitted.values") is None else np.asarray(m["fitted.values"], dtype=np.float64).ravel()
+    res = None if m.get("residuals") is None else np.asarray(m["residuals"], dtype=np.float64).ravel()
+    noK = m.get("obj.noK")
     if LOCO and chrom is not None and bool(np.asarray(m["LOCO"]).ravel()[0]):
         lr = m["LOCOResult"][int(chrom) - 1]
         if lr is not None and isinstance(lr, dict) and "fitted.values" in lr:

@@ -21,7 +21,7 @@ What follows the reference, block by block:
   extractVarianceRatio (autosomal markers only unless includeNonautoMarkersforVarRatio)      FG.R:2152-2423
 
 Not provided (the reference's sparse-GRM machinery is out of scope): useSparseGRMtoFitNULL,
-useSparseGRMforVarRatio, isLowMemLOCO.  They raise, they are never ignored.
+useSparseGRMforVarRatio.  They raise, they are never ignored.
 
 Randomness: the reference draws the Hutchinson probes, the variance-ratio hold-out set and the marker order from R's RNG
 (set.seed(1) in the CLI, set_seed(200) in GetTrace).  The probes reproduce R's stream bit for bit (step1.ProbeStream,
@@ -151,9 +151,8 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
     covarColList = list(covarColList or [])
     qCovarCol = list(qCovarCol or [])
     say = print if verbose else (lambda *a, **k: None)
-    if useSparseGRMtoFitNULL or useSparseGRMforVarRatio or isLowMemLOCO:
-        raise NotImplementedError("sparse-GRM fitting / variance ratios and isLowMemLOCO are not provided by the B200 back "
-                                  "end (full-GRM path only)")
+    if useSparseGRMtoFitNULL or useSparseGRMforVarRatio:
+        raise NotImplementedError("sparse-GRM fitting / variance ratios are not provided by the B200 back end (full-GRM path only)")
     if nThreads > 1:
         raise SaigeInputError("setting threads via RcppParallel is not allowed")          # FG.R:785
     if traitType not in ("binary", "quantitative"):
@@ -165,7 +164,7 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
         outputPrefix += "_FemaleOnly"
     elif MaleOnly:
         outputPrefix += "_MaleOnly"
-    modelOut = outputPrefix + ".rda"
+    modelOut = outputPrefix + ("_noLOCO.rda" if (LOCO and isLowMemLOCO and not skipModelFitting) else ".rda")     # FG.R:711-714
     if skipModelFitting and not os.path.exists(modelOut):
         raise SaigeInputError("skipModelFitting=TRUE but %s does not exist" % modelOut)
     varRatioFile = None
@@ -278,7 +277,8 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
     if not skipModelFitting:
         probes = step1.ProbeStream(N, nmax=nrun + 100, seed=200, rng=probe_rng)
         m = step1.glmmkin_ai_PCG(geno, fit0, probes, trait=traitType, tauInit=tauInit, maxiter=maxiter, tol=tol, nrun=nrun,
-                                 tolPCG=tolPCG, maxiterPCG=maxiterPCG, traceCVcutoff=traceCVcutoff, LOCO=LOCO, verbose=verbose)
+                                 tolPCG=tolPCG, maxiterPCG=maxiterPCG, traceCVcutoff=traceCVcutoff,
+                                 LOCO=LOCO and not isLowMemLOCO, verbose=verbose)
         Xfit = np.asarray(fit0["X"])
         Xout = Xorig if isCovariateOffset else Xfit
         tau = np.asarray(m["theta"], dtype=np.float64)
@@ -305,8 +305,8 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
             ("fitted.values", col(m["fitted_values"])), ("Y", col(m["Y"])), ("residuals", col(m["residuals"])),
             ("cov", np.asarray(m["cov"])), ("converged", bool(m["converged"])), ("sampleID", list(sampleID)),
             ("obj.noK", noK(np.asarray(m["fitted_values"]))), ("y", y), ("X", Xout), ("traitType", traitType),
-            ("isCovariateOffset", bool(isCovariateOffset)), ("LOCO", bool(LOCO))])
-        if LOCO:
+            ("isCovariateOffset", bool(isCovariateOffset)), ("LOCO", bool(LOCO and not isLowMemLOCO))])
+        if LOCO and not isLowMemLOCO:
             lres = []
             for e in m["LOCOResult"]:
                 if not e.get("isLOCO"):
@@ -323,6 +323,32 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
         modglmm["offset"] = col(offset)
         modglmm["useSparseGRMtoFitNULL"] = False
         save_rda(modelOut, {"modglmm": modglmm})
+        if LOCO and isLowMemLOCO:
+            # FG.R:1205-1290: the model without LOCO is on disk; every chromosome is refitted FROM THE MAIN FIT's alpha / eta
+            # (not from the previous chromosome's) and saved to its own <prefix>_chr<j>.rda, which holds that chromosome only
+            slim = dict(modglmm)
+            slim["LOCO"] = True
+            for k in ("Y", "linear.predictors", "coefficients", "cov", "fitted.values", "residuals", "obj.noK", "offset"):
+                del slim[k]                                   # `modglmm$Y = NULL` removes the element
+            geno.set_Diagof_StdGeno_LOCO()
+            eta0 = np.asarray(m["linear_predictors"], dtype=np.float64)
+            off0 = np.asarray(fit0["offset"], dtype=np.float64)
+            state = []
+            for j, (s0, e0) in enumerate(zip(step1.geno_start_vec(geno), step1.geno_end_vec(geno))):
+                if s0 == -1 or e0 == -1:
+                    state.append(dict(isLOCO=False))
+                    continue
+                geno.setStartEndIndex(s0, e0, j)
+                rl = step1.Get_Coef(geno, y, np.asfortranarray(Xfit), tau, family, alpha0, eta0, off0, maxiterPCG, tolPCG, maxiter, loco=True)
+                a = np.asarray(rl["alpha"], dtype=np.float64)
+                d = dict([("isLOCO", True), ("coefficients", col(back(a))), ("linear.predictors", col(rl["eta"])),
+                          ("fitted.values", col(rl["mu"])), ("Y", col(rl["Y"])), ("residuals", col(y - rl["mu"])),
+                          ("cov", np.asarray(rl["cov"])), ("obj.noK", noK(np.asarray(rl["mu"])))])
+                if not isCovariateOffset and hasCovariate:
+                    d["offset"] = col(Xfit[:, 1:] @ a[1:])
+                slim["LOCOResult"] = state + [d] + [[None]] * (21 - j)
+                save_rda("%s_chr%d.rda" % (outputPrefix, j + 1), {"modglmm": slim})
+                state.append([None])
     else:
         modglmm = load_rda(modelOut)["modglmm"]
         if modglmm.get("LOCO") is None:

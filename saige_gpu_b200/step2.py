@@ -19,9 +19,10 @@ OUT_COLUMNS = ["CHR", "POS", "MarkerID", "Allele1", "Allele2", "AC_Allele2", "AF
 def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
     """readInGLMM.R:39-170: the fields step 2 consumes; with LOCO the chromosome's refit replaces mu/res/obj.noK."""
     m = load_rda(GMMATmodelFile)["modglmm"]
-    mu = np.asarray(m["fitted.values"], dtype=np.float64).ravel()
-    res = np.asarray(m["residuals"], dtype=np.float64).ravel()
-    noK = m["obj.noK"]
+    # per-chromosome files of isLowMemLOCO (FG.R:1205-1290) carry the chromosome's refit only: the main fields are NULL
+    mu = None if m.get("fitted.values") is None else np.asarray(m["fitted.values"], dtype=np.float64).ravel()
+    res = None if m.get("residuals") is None else np.asarray(m["residuals"], dtype=np.float64).ravel()
+    noK = m.get("obj.noK")
     has_loco = bool(np.asarray(m.get("LOCO", [0])).ravel()[0])
     if LOCO:
         if not has_loco:
@@ -35,6 +36,8 @@ def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
                 mu = np.asarray(lr["fitted.values"], dtype=np.float64).ravel()
                 res = np.asarray(lr["residuals"], dtype=np.float64).ravel()
                 noK = lr["obj.noK"]
+    if mu is None or noK is None:
+        raise ValueError("%s holds no fit for chromosome %s (a per-chromosome model file of another chromosome?)" % (GMMATmodelFile, chrom))
     trait = m["traitType"][0] if isinstance(m["traitType"], list) else str(m["traitType"])
     tau = np.asarray(m["theta"], dtype=np.float64).ravel()
     mu2 = mu * (1 - mu) if trait == "binary" else np.full(len(mu), 1.0 / tau[0])

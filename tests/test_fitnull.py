@@ -254,7 +254,7 @@ def test_options_and_refusals(golden_dir, tmp_path):
     from saige_gpu_b200 import fitnull
     base = dict(plinkFile=os.path.join(golden_dir, "chr22_1000"), phenoFile=os.path.join(golden_dir, "pheno_1000samples.txt"),
                 phenoCol="y_binary", covarColList=["x1", "x2"], sampleIDColinphenoFile="IID", outputPrefix=str(tmp_path / "x"))
-    for bad in (dict(useSparseGRMtoFitNULL=True), dict(useSparseGRMforVarRatio=True), dict(isLowMemLOCO=True)):
+    for bad in (dict(useSparseGRMtoFitNULL=True), dict(useSparseGRMforVarRatio=True)):
         with pytest.raises(NotImplementedError):
             fitnull.fitNULLGLMM(OracleBackend(), **{**base, **bad})
     with pytest.raises(fitnull.SaigeInputError):
@@ -278,6 +278,33 @@ def test_options_and_refusals(golden_dir, tmp_path):
     assert m["isCovariateOffset"] is True and m["LOCO"] is False and "LOCOResult" not in m
     assert abs(np.mean(m["y"])) < 1e-12 and abs(np.std(m["y"]) - 1) < 0.01              # rank-based inverse normal scores
     assert m["theta"][0] > 0 and r["varianceRatio"] > 0
+
+
+def test_low_memory_loco_writes_one_model_per_chromosome(oracle_fit, golden_dir, bim22, tmp_path):
+    """isLowMemLOCO (FG.R:1205-1290): <prefix>_noLOCO.rda without LOCO results + <prefix>_chr<j>.rda holding chromosome j's
+    refit only; step 2 reads the chromosome's file.  Same model as the in-memory LOCO run up to the IRLS stopping rule
+    (each chromosome restarts from the main fit instead of from the previous chromosome)."""
+    from saige_gpu_b200 import step2
+    from saige_gpu_b200.rdata import load_rda
+    ref, _ = oracle_fit
+    out = str(tmp_path / "lowmem")
+    r = _run(OracleBackend(), golden_dir, bim22, out, isLowMemLOCO=True)
+    assert r["modelFile"] == out + "_noLOCO.rda" and not os.path.exists(out + ".rda")
+    main = load_rda(out + "_noLOCO.rda")["modglmm"]
+    assert main["LOCO"].tolist() == [0] and "LOCOResult" not in main
+    assert np.allclose(main["theta"], ref["modglmm"]["theta"], rtol=1e-12)
+    assert abs(r["varianceRatio"] - ref["varianceRatio"]) < 1e-9 * ref["varianceRatio"]
+    for j in (1, 7, 22):
+        m = load_rda("%s_chr%d.rda" % (out, j))["modglmm"]
+        assert m["LOCO"].tolist() == [1] and "fitted.values" not in m and "obj.noK" not in m and len(m["LOCOResult"]) == 22
+        assert [isinstance(x, dict) and "fitted.values" in x for x in m["LOCOResult"]] == [k == j - 1 for k in range(22)]
+        a, b = m["LOCOResult"][j - 1], ref["modglmm"]["LOCOResult"][j - 1]
+        assert np.allclose(a["fitted.values"], b["fitted.values"], rtol=5e-3)
+        assert set(b.keys()) - {"alpha0"} <= set(a.keys())
+        M = step2.ReadModel("%s_chr%d.rda" % (out, j), chrom=str(j), LOCO=True)
+        assert np.array_equal(M["mu"], a["fitted.values"].ravel()) and M["XVX"].shape == (3, 3)
+        with pytest.raises(ValueError):
+            step2.ReadModel("%s_chr%d.rda" % (out, j), chrom=str(j % 22 + 1), LOCO=True)
 
 
 def test_categorical_variance_ratios(golden_dir, bim22, tmp_path):
