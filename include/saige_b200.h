@@ -190,6 +190,15 @@ int sgb_step2_set_variance_ratios(sgb_ctx *h, int n_cate, const double *ratios, 
                                   const double *max_mac_include);
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
+/* The same marker loop for dosage rows (Unified_getOneMarker's VCF / BGEN branches, Main.cpp:584-700; VCF.cpp:120-256,
+ * BGEN.cpp:132-345): dosages[n_markers x n_file_samples] row-major doubles = copies of the tested allele per sample of the
+ * genotype file (hard calls as 0 / 1 / 2), negative or NaN = missing; pos_in_fam of sgb_step2_set_model indexes these rows.
+ * impute_method 1 best_guess / 2 mean / 3 minor, dosage_zerod_cutoff / dosage_zerod_mac_cutoff as in imputeGenoAndFlip
+ * (UTIL.cpp:58-135; R defaults 0.2 and 10).  N_*_hom / N_*_het count dosages in [1.5, 2] / [0.5, 1.5) (Main.cpp:510-525).
+ * Same out table as sgb_step2_test_markers.  The imputation-INFO filter of BGEN input (minInfo) is not built: INFO = 1. */
+int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t n_file_samples, int64_t n_markers, double min_maf,
+                           double min_mac, double max_missing, int se_two_sided, int impute_method,
+                           double dosage_zerod_cutoff, double dosage_zerod_mac_cutoff, double *out);
 
 /* ---- dense N x N GRM (BASELINE config 4) ---------------------------------------------------- */
 /* The reference fork ships no code for this step (docs/overview.md:19-21 describe a "full GRM" option of SAIGE-GPU; the

@@ -307,8 +307,10 @@ def firth_fit(gt, y, offset, maxit=50, maxstep=15, xconv=1e-5, gconv=1e-5):
 
 
 def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=2.0, se_two_sided=True, is_Firth_beta=False,
-                pCutoffforFirth=0.01, firth_se_from_fit=True, max_MAC_for_ER=-1.0):
-    """One pass of the mainMarkerInCPP loop body (Main.cpp:229-520).  Returns None when the marker is filtered."""
+                pCutoffforFirth=0.01, firth_se_from_fit=True, max_MAC_for_ER=-1.0, impute_method="best_guess",
+                dosage_zerod_cutoff=0.0, dosage_zerod_MAC_cutoff=0.0):
+    """One pass of the mainMarkerInCPP loop body (Main.cpp:229-520).  Returns None when the marker is filtered.
+    Graw: copies of the ALT allele per model sample, hard calls (0/1/2) or dosages in [0, 2]; negative = missing."""
     test_marker.__test__ = False
     n = len(Graw)
     miss = Graw < 0
@@ -327,7 +329,12 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
         G = 2 - G
         alt_freq = 1 - alt_freq
     if miss.any():
-        G[miss] = np.round(2 * alt_freq)
+        # best_guess: std::round (half away from zero); mean: 2 f; minor: 0 (UTIL.cpp:80-93)
+        impute_g = {"best_guess": math.floor(2 * alt_freq + 0.5), "mean": 2 * alt_freq, "minor": 0.0}[impute_method]
+        G[miss] = impute_g
+        mac = mac + impute_g * int(miss.sum())
+    if dosage_zerod_cutoff > 0 and mac <= dosage_zerod_MAC_cutoff:
+        G[np.abs(G) <= dosage_zerod_cutoff] = 0.0                  # arma clean() (UTIL.cpp:105-109): small dosages of rare variants
     alt_count = G.sum()
     alt_freq = alt_count / (2 * n)
     if flip:
@@ -371,7 +378,13 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     afc, aft = G[case].mean() / 2, G[ctrl].mean() / 2
     if flip:
         afc, aft = 1 - afc, 1 - aft
-    return dict(AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
+    # is_output_moreDetails (Main.cpp:510-525): dosage ranges [1.5, 2] / [0.5, 1.5) of the flipped, imputed vector
+    hom, het = (G >= 1.5) & (G <= 2), (G >= 0.5) & (G < 1.5)
+    n_case_hom, n_case_het = int((hom & case).sum()), int((het & case).sum())
+    n_ctrl_hom, n_ctrl_het = int((hom & ctrl).sum()), int((het & ctrl).sum())
+    if flip:
+        n_case_hom, n_ctrl_hom = int(case.sum()) - n_case_het - n_case_hom, int(ctrl.sum()) - n_ctrl_het - n_ctrl_hom
+    return dict(N_case_hom=n_case_hom, N_case_het=n_case_het, N_ctrl_hom=n_ctrl_hom, N_ctrl_het=n_ctrl_het, AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
                 Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa, Is_ER=is_er,
                 Is_Firth=is_firth, Firth_converged=firth_conv,
                 AF_case=afc, AF_ctrl=aft, N_case=int(case.sum()), N_ctrl=int(ctrl.sum()))

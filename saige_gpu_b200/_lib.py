@@ -87,6 +87,8 @@ _SIGS = {
     "sgb_step2_set_er": (C.c_int, [P, C.c_double]),
     "sgb_step2_set_variance_ratios": (C.c_int, [P, C.c_int, DP, DP, DP]),
     "sgb_step2_test_markers": (C.c_int, [P, P, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, DP]),
+    "sgb_step2_test_dosages": (C.c_int, [P, DP, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
+                                         C.c_double, DP]),
     "sgb_bench_crossprod_device": (C.c_int, [P, C.c_int, C.c_int, C.c_uint64, P, P]),
     "sgb_bench_fetch_result": (C.c_int, [P, C.c_int, DP, DP]),
     "sgb_dense_grm_build": (C.c_int, [P, C.c_int]),

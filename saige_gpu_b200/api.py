@@ -390,6 +390,18 @@ class SaigeB200:
                                                 float(max_missing), int(bool(se_two_sided)), _p(out)))
         return out
 
+    def mainMarkerInCPP_dosage(self, dosages, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, se_two_sided=True, impute_method=1,
+                               dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0):
+        """The marker loop for dosage rows (VCF / BGEN input): dosages[n_markers x n_file_samples], negative or NaN = missing."""
+        D = np.ascontiguousarray(dosages, dtype=np.float64)
+        if D.ndim != 2:
+            raise SaigeB200Error("dosages must be n_markers x n_file_samples")
+        out = np.zeros((D.shape[0], len(self.STEP2_COLUMNS)))
+        self._ck(self._L.sgb_step2_test_dosages(self._h, _p(D), D.shape[1], D.shape[0], float(min_MAF), float(min_MAC),
+                                                float(max_missing), int(bool(se_two_sided)), int(impute_method),
+                                                float(dosage_zerod_cutoff), float(dosage_zerod_MAC_cutoff), _p(out)))
+        return out
+
     # ---- dense N x N GRM (BASELINE config 4): tcgen05 build, stored-GRM products ----
     def buildDenseGRM(self, weight_limbs=7):
         """K = Z Z^T / M on the tensor cores from the loaded 2-bit store (collective when distributed)."""

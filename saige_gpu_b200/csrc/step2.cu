@@ -73,6 +73,23 @@ __device__ __forceinline__ int s2_geno(const uint8_t *srow, int32_t src, int fli
     return flip ? 2 - g : g;
 }
 
+// dosage input (VCF DS / BGEN): one row of doubles per variant in the file's sample order, negative or NaN = missing
+struct s2_dose {
+    const double *d;        // n_markers x stride
+    int64_t stride;         // samples per row in the file
+    int impute;             // 1 best_guess, 2 mean, 3 minor (UTIL.cpp:80-93)
+    double zerod_cutoff, zerod_mac_cutoff;      // dosages <= cutoff are zeroed when MAC <= mac cutoff (UTIL.cpp:105-109)
+};
+
+// dosage of model sample `src` after flip / imputation / zeroing (imputeGenoAndFlip, UTIL.cpp:58-135: flip, impute, clean)
+__device__ __forceinline__ double s2_dose_geno(const double *row, int32_t src, int flip, double imputeG, double zero_below)
+{
+    double g = row[src];
+    if (!(g >= 0.0)) g = imputeG;
+    else if (flip) g = 2.0 - g;
+    return fabs(g) <= zero_below ? 0.0 : g;          // zero_below < 0: zeroing off
+}
+
 struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + normal approximation of the zeros
     double NAmu, NAsigma;
     int fast;
@@ -81,11 +98,14 @@ struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + no
 // IDENT: the model's samples are the first N rows of the .fam in order (the usual case).  Then genotype classes are
 // counted 16 samples at a time with popcounts on the raw PLINK words (allele / missing counts and every case-control
 // tally), warps skip 32-sample groups that hold no minor allele, and no per-sample index or phenotype is read.
-template <bool IDENT>
+// DOSE: the genotypes are doubles read through L2 (s2_dose) instead of 2-bit codes staged in shared memory; always with the
+// sample index (IDENT = false).
+template <bool IDENT, bool DOSE>
 __global__ void __launch_bounds__(S2_THREADS)
 step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
-             double max_missing, int se_two_sided, double *__restrict__ out)
+             double max_missing, int se_two_sided, double *__restrict__ out, s2_dose DS)
 {
+    static_assert(!(IDENT && DOSE), "dosage rows are always indexed");
     extern __shared__ uint8_t srow[];
     __shared__ double red[S2_THREADS / 32];
     __shared__ double Zs[S2_MAXP], Ws[S2_MAXP];
@@ -96,8 +116,11 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     const int tid = threadIdx.x, p = M.p;
     const int64_t N = M.N;
     double *o = out + m * S2_NOUT;
-    for (int64_t b = tid; b < B0 + 8; b += S2_THREADS) srow[b] = b < B0 ? bed[m * B0 + b] : (uint8_t)0;      // 8 pad bytes: word-wise reads
-    __syncthreads();
+    const double *drow = DOSE ? DS.d + m * DS.stride : nullptr;
+    if (!DOSE) {
+        for (int64_t b = tid; b < B0 + 8; b += S2_THREADS) srow[b] = b < B0 ? bed[m * B0 + b] : (uint8_t)0;      // 8 pad bytes: word-wise reads
+        __syncthreads();
+    }
 
     // ---- getOneMarker: counts over the model's samples ----
     double altCounts0, nMiss;
@@ -119,6 +142,13 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         k2a = block_sum((double)c2, red); k1a = block_sum((double)c1, red); nMiss = block_sum((double)cm, red);
         k2c = block_sum((double)d2, red); k1c = block_sum((double)d1, red); kmc = block_sum((double)dm, red);
         altCounts0 = 2.0 * k2a + k1a;
+    } else if (DOSE) {
+        double c_alt = 0, c_miss = 0;
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            const double g = drow[M.pos[i]];
+            if (g >= 0.0) c_alt += g; else c_miss += 1.0;
+        }
+        altCounts0 = block_sum(c_alt, red); nMiss = block_sum(c_miss, red);
     } else {
         double c_alt = 0, c_miss = 0;
         for (int64_t i = tid; i < N; i += S2_THREADS) {
@@ -142,6 +172,17 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     const int flip = altFreq > 0.5;
     if (flip) altFreq = 1.0 - altFreq;
     const int imputeG = nMiss > 0 ? (int)round(2.0 * altFreq) : 0;
+    // dosage rows: the three imputation methods and the zeroing of small dosages of rare variants (UTIL.cpp:80-109)
+    double imputeGd = 0.0, zero_below = -1.0;
+    if (DOSE) {
+        if (nMiss > 0) imputeGd = DS.impute == 1 ? round(2.0 * altFreq) : (DS.impute == 2 ? 2.0 * altFreq : 0.0);
+        if (DS.zerod_cutoff > 0.0 && MAC0 + imputeGd * nMiss <= DS.zerod_mac_cutoff) zero_below = DS.zerod_cutoff;
+    }
+    // genotype of model sample i in the tested coding
+    auto GENO = [&](int64_t i) -> double {
+        if (DOSE) return s2_dose_geno(drow, M.pos[i], flip, imputeGd, zero_below);
+        return (double)s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
+    };
 
     // ---- one pass over the samples: every sum scoreTestFast needs + case/control tallies ----
     double zs[S2_MAXP], ws[S2_MAXP];
@@ -181,6 +222,28 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         ctrl_hom = h2t + (imputeG == 2 ? kmt : 0.0); ctrl_het = k1t + (imputeG == 1 ? kmt : 0.0);
         gcase = 2.0 * case_hom + case_het; gctrl = 2.0 * ctrl_hom + ctrl_het;
         gsum = gcase + gctrl; nz = case_hom + case_het + ctrl_hom + ctrl_het;
+    } else if (DOSE) {
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            const double gd = GENO(i);
+            const double yi = M.y[i];
+            const double hom = (gd >= 1.5 && gd <= 2.0) ? 1.0 : 0.0, het = (gd >= 0.5 && gd < 1.5) ? 1.0 : 0.0;      // Main.cpp:510-520
+            if (yi == 1.0) { ncase += 1; gcase += gd; case_hom += hom; case_het += het; }
+            else { nctrl += 1; gctrl += gd; ctrl_hom += hom; ctrl_het += het; }
+            if (gd != 0.0) {
+                const double m2 = M.mu2[i];
+                gsum += gd; nz += 1;
+                t1 += m2 * gd * gd;
+                r0 += M.res[i] * gd;
+                for (int j = 0; j < p; j++) {
+                    zs[j] += M.A[i + (int64_t)j * N] * gd;
+                    ws[j] += m2 * M.X[i + (int64_t)j * N] * gd;
+                }
+            }
+        }
+        t1 = block_sum(t1, red); r0 = block_sum(r0, red); gsum = block_sum(gsum, red); nz = block_sum(nz, red);
+        gcase = block_sum(gcase, red); ncase = block_sum(ncase, red); gctrl = block_sum(gctrl, red); nctrl = block_sum(nctrl, red);
+        case_hom = block_sum(case_hom, red); case_het = block_sum(case_het, red);
+        ctrl_hom = block_sum(ctrl_hom, red); ctrl_het = block_sum(ctrl_het, red);
     } else {
         for (int64_t i = tid; i < N; i += S2_THREADS) {
             const int g = s2_geno(srow, M.pos[i], flip, imputeG);
@@ -256,7 +319,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         if (tid == 0) er_cnt = 0;
         __syncthreads();
         for (int64_t i = tid; i < N; i += S2_THREADS) {
-            if (s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG)) {
+            if (GENO(i) != 0.0) {
                 const int slot = atomicAdd(&er_cnt, 1);
                 if (slot < SGB_ER_MAXK) er_idx[slot] = (int)i;
             }
@@ -273,7 +336,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             double g1[SGB_ER_MAXK], p1[SGB_ER_MAXK], r1[SGB_ER_MAXK], musum = 0.0;
             for (int a = 0; a < k; a++) {
                 const int i = er_idx[a];
-                g1[a] = (double)s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
+                g1[a] = GENO(i);
                 p1[a] = M.mu[i]; r1[a] = M.res[i];
                 musum += p1[a];
             }
@@ -291,13 +354,13 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         // gtilde_i = g_i - XXVX_inv[i,:] . (XV g),  XV g = W  (getadjGFast, SAIGE_test.cpp:306-315)
         double m1p = 0, gpos = 0, gneg = 0, gmuNB = 0, sigNB = 0;
         for (int64_t i = tid; i < N; i += S2_THREADS) {
-            const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
-            double gt = (double)g;
+            const double g = GENO(i);
+            double gt = g;
             for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
             const double mu = M.mu[i];
             m1p += mu * gt;
             if (gt > 0) gpos += gt; else if (gt < 0) gneg += gt;
-            if (g) { gmuNB += gt * mu; sigNB += mu * (1.0 - mu) * gt * gt; }
+            if (g != 0.0) { gmuNB += gt * mu; sigNB += mu * (1.0 - mu) * gt * gt; }
         }
         const double m1 = block_sum(m1p, red);
         gpos = block_sum(gpos, red); gneg = block_sum(gneg, red); gmuNB = block_sum(gmuNB, red); sigNB = block_sum(sigNB, red);
@@ -314,9 +377,9 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         auto cgf = [&](double t, double &k0, double &k1, double &k2, bool want0) {
             double a0 = 0, a1 = 0, a2 = 0;
             for (int64_t i = tid; i < N; i += S2_THREADS) {
-                const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
-                if (fast && !g) continue;
-                double gt = (double)g;
+                const double g = GENO(i);
+                if (fast && g == 0.0) continue;
+                double gt = g;
                 for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
                 const double mu = M.mu[i];
                 const double x = gt * t;
@@ -404,8 +467,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         while (iter <= 50) {
             double f00 = 0, f01 = 0, f11 = 0;
             for (int64_t i = tid; i < N; i += S2_THREADS) {
-                const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
-                double gt = (double)g;
+                double gt = GENO(i);
                 for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
                 const double pi = 1.0 / (exp(-(b0 + b1 * gt) - M.offset[i]) + 1.0), w = pi * (1.0 - pi);
                 f00 += w; f01 += w * gt; f11 += w * gt * gt;
@@ -416,8 +478,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             c00 = f11 / det; c01 = -f01 / det; c11 = f00 / det;
             double u0 = 0, u1 = 0;
             for (int64_t i = tid; i < N; i += S2_THREADS) {
-                const int g = s2_geno(srow, IDENT ? (int32_t)i : M.pos[i], flip, imputeG);
-                double gt = (double)g;
+                double gt = GENO(i);
                 for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
                 const double pi = 1.0 / (exp(-(b0 + b1 * gt) - M.offset[i]) + 1.0), w = pi * (1.0 - pi);
                 const double hat = w * (c00 + 2.0 * c01 * gt + c11 * gt * gt);
@@ -606,8 +667,8 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, 2 * obytes));
     s->out_elems = ob / sizeof(double);
     if (sgb_first_on_device(h->device, SGB_SITE_STEP2)) {
-        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
-        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
     }
     int cur = 0;
     int64_t held_m0[2] = {-1, -1}, held_nm[2] = {0, 0};
@@ -622,9 +683,9 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
         h->cnt.bytes_h2d += nm * B0;
         // dynamic smem: the raw row, padded so that the word-wise reads of the last (partial) word pair stay inside
         if (s->M.identity)
-            step2_kernel<true><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout);
+            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{});
         else
-            step2_kernel<false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout);
+            step2_kernel<false, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{});
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
         CUDA_OK(h, cudaMemcpyAsync(s->pout[cur], dout, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
@@ -635,6 +696,42 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     for (int i = 0; i < 2; i++)
         if (held_m0[i] >= 0) memcpy(out + (size_t)held_m0[i] * S2_NOUT, s->pout[i], sizeof(double) * held_nm[i] * S2_NOUT);
+    return 0;
+}
+
+// Dosage rows (VCF DS / GT, BGEN): same marker loop, genotypes read as doubles.  Chunks of <= 256 MB of rows go to the
+// device from the caller's (pageable) buffer; the transfer dominates (8 bytes per sample against 1/4 byte for hard calls),
+// so this first version keeps one buffer and no overlap.
+extern "C" int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t n_file_samples, int64_t n_markers,
+                                      double min_maf, double min_mac, double max_missing, int se_two_sided, int impute_method,
+                                      double dosage_zerod_cutoff, double dosage_zerod_mac_cutoff, double *out)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    sgb_step2 *s = h->step2;
+    if (!s || !s->d_vec) return sgb_fail(h, "step2: call sgb_step2_set_model first");
+    if (impute_method < 1 || impute_method > 3) return sgb_fail(h, "step2: impute_method %d (1 best_guess, 2 mean, 3 minor)", impute_method);
+    if (n_file_samples < 1) return sgb_fail(h, "step2: empty dosage rows");
+    if (n_markers <= 0) return 0;
+    const size_t row_bytes = sizeof(double) * (size_t)n_file_samples;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, (int64_t)(((size_t)256 << 20) / row_bytes)));
+    SGB_TRY(sgb_ensure(h, (void **)&s->d_bed, &s->bed_bytes, (size_t)chunk * row_bytes));
+    size_t ob = s->out_elems * sizeof(double);
+    SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, sizeof(double) * (size_t)chunk * S2_NOUT));
+    s->out_elems = ob / sizeof(double);
+    for (int64_t m0 = 0; m0 < n_markers; m0 += chunk) {
+        const int64_t nm = std::min(chunk, n_markers - m0);
+        CUDA_OK(h, cudaMemcpyAsync(s->d_bed, dosages + (size_t)m0 * n_file_samples, (size_t)nm * row_bytes, cudaMemcpyHostToDevice, h->stream));
+        h->cnt.bytes_h2d += nm * row_bytes;
+        s2_dose ds;
+        ds.d = reinterpret_cast<const double *>(s->d_bed); ds.stride = n_file_samples; ds.impute = impute_method;
+        ds.zerod_cutoff = dosage_zerod_cutoff; ds.zerod_mac_cutoff = dosage_zerod_mac_cutoff;
+        step2_kernel<false, true><<<(unsigned)nm, S2_THREADS, 0, h->stream>>>(s->M, nullptr, 0, nm, min_maf, min_mac, max_missing, se_two_sided, s->d_out, ds);
+        h->cnt.n_kernel_launches++;
+        CUDA_OK(h, cudaGetLastError());
+        CUDA_OK(h, cudaMemcpyAsync(out + (size_t)m0 * S2_NOUT, s->d_out, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
+        h->cnt.bytes_d2h += sizeof(double) * nm * S2_NOUT;
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
     return 0;
 }
 

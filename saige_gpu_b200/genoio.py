@@ -1,0 +1,171 @@
+"""Step-2 genotype inputs other than PLINK: VCF (GT or DS field) and BGEN v1.2 layout 2, decoded on the host into the
+dosage matrix `sgb_step2_test_dosages` consumes (copies of the tested allele per sample, doubles, negative = missing).
+
+Host-side mirror of the reference's readers (/root/reference/src/SAIGE/src/VCF.cpp:120-256 `VcfClass::getOneMarker`, which
+goes through the savvy library, and src/BGEN.cpp:132-345 `BgenClass::Parse2`, :360-520 `getOneMarker`):
+  * VCF, GT: dosage = number of ALT alleles of the call, missing when an allele is `.`; DS: the number itself, `.` missing.
+    Allele1 = REF, Allele2 = ALT (the tested allele).
+  * BGEN: zlib-compressed probability blocks of unphased diploid biallelic variants, 8 or 16 bits per probability;
+    P(AA), P(AB) of the FIRST allele A are stored, dosage of the first allele = 2 P(AA) + P(AB) (BGEN.cpp:218-223).
+    AlleleOrder "ref-first" (the reader's default, BGEN.cpp:485-486): first allele = REF, tested allele = second;
+    "alt-first": the first allele is the tested one.  Missing samples carry ploidy byte bit 7.
+Both yield chunks (info rows, dosage matrix) so a scan never holds the whole file.  Only formats; no statistics here."""
+import gzip
+import struct
+import zlib
+
+import numpy as np
+
+
+def _open_text(path):
+    with open(path, "rb") as f:
+        gz = f.read(2) == b"\x1f\x8b"
+    return gzip.open(path, "rt") if gz else open(path, "rt")
+
+
+def vcf_samples(path):
+    with _open_text(path) as f:
+        for line in f:
+            if line.startswith("#CHROM"):
+                return line.rstrip("\n").split("\t")[9:]
+    raise ValueError("%s: no #CHROM header line" % path)
+
+
+def iter_vcf(path, field="DS", chunk=1000):
+    """Yields (info, D): info = list of (CHR, POS, ID, REF, ALT), D = len(info) x n_samples doubles (negative = missing)."""
+    if field not in ("GT", "DS"):
+        raise ValueError("vcfField should be 'DS' or 'GT'")
+    info, rows = [], []
+    gt_lut = {}
+    with _open_text(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            if "," in t[4]:
+                raise NotImplementedError("%s: multi-allelic record %s (split it into biallelic records first)" % (path, t[2]))
+            fmt = t[8].split(":")
+            if field not in fmt:
+                raise ValueError("%s: record %s has no %s field" % (path, t[2], field))
+            k = fmt.index(field)
+            vals = t[9:] if len(fmt) == 1 else [x.split(":")[k] if x.count(":") >= k else "." for x in t[9:]]
+            if field == "GT":
+                row = np.empty(len(vals))
+                for i, v in enumerate(vals):
+                    d = gt_lut.get(v)
+                    if d is None:
+                        al = v.replace("|", "/").split("/")
+                        d = -1.0 if "." in al else float(sum(a != "0" for a in al))
+                        gt_lut[v] = d
+                    row[i] = d
+            else:
+                row = np.array([-1.0 if v in (".", "") else float(v) for v in vals])
+            info.append((t[0], t[1], t[2], t[3], t[4]))
+            rows.append(row)
+            if len(rows) == chunk:
+                yield info, np.vstack(rows)
+                info, rows = [], []
+    if rows:
+        yield info, np.vstack(rows)
+
+
+def read_sample_file(path):
+    """One ID per line without header (SPAGMMATtest's sampleFile), or an Oxford .sample file (two header lines, ID_2)."""
+    lines = [l.split() for l in open(path) if l.strip()]
+    if lines and lines[0][0] == "ID_1":
+        return [l[1] if len(l) > 1 else l[0] for l in lines[2:]]
+    return [l[0] for l in lines]
+
+
+class BgenFile:
+    def __init__(self, path):
+        self.path = path
+        self.f = open(path, "rb")
+        offset, hlen, self.M, self.N = struct.unpack("<IIII", self.f.read(16))
+        if self.f.read(4) not in (b"bgen", b"\0\0\0\0"):
+            raise ValueError("%s is not a BGEN file" % path)
+        self.f.seek(4 + hlen - 4)
+        flags, = struct.unpack("<I", self.f.read(4))
+        self.compression, self.layout, has_ids = flags & 3, (flags >> 2) & 15, flags >> 31
+        if self.layout != 2:
+            raise NotImplementedError("%s: BGEN layout %d (only v1.2, layout 2, is read; BGEN.cpp has the same limit)" % (path, self.layout))
+        if self.compression not in (0, 1):
+            raise NotImplementedError("%s: zstd-compressed BGEN is not read" % path)
+        self.samples = None
+        if has_ids:
+            self.f.seek(4 + hlen)
+            _, n = struct.unpack("<II", self.f.read(8))
+            self.samples = []
+            for _ in range(n):
+                l, = struct.unpack("<H", self.f.read(2))
+                self.samples.append(self.f.read(l).decode())
+        self.f.seek(4 + offset)
+
+    def _str(self, nbytes):
+        l, = struct.unpack("<H" if nbytes == 2 else "<I", self.f.read(nbytes))
+        return self.f.read(l).decode()
+
+    def variants(self, allele_order="ref-first", chunk=1000):
+        """Yields (info, D) like iter_vcf; D = copies of the tested allele (second allele for ref-first, first for alt-first)."""
+        if allele_order not in ("ref-first", "alt-first"):
+            raise ValueError("AlleleOrder should be 'ref-first' or 'alt-first'")
+        info, rows = [], []
+        for _ in range(self.M):
+            self._str(2)                      # variant identifier
+            rsid, chrom = self._str(2), self._str(2)
+            pos, K = struct.unpack("<IH", self.f.read(6))
+            alleles = [self._str(4) for _ in range(K)]
+            C, = struct.unpack("<I", self.f.read(4))
+            if self.compression:
+                D, = struct.unpack("<I", self.f.read(4))
+                blk = zlib.decompress(self.f.read(C - 4))
+                if len(blk) != D:
+                    raise ValueError("%s: variant %s inflates to %d bytes, header says %d" % (self.path, rsid, len(blk), D))
+            else:
+                blk = self.f.read(C)
+            if K != 2:
+                raise NotImplementedError("%s: variant %s has %d alleles" % (self.path, rsid, K))
+            n, k, pmin, pmax = struct.unpack("<IHBB", blk[:8])
+            if n != self.N or k != 2:
+                raise ValueError("%s: variant %s block is inconsistent with the header" % (self.path, rsid))
+            pm = np.frombuffer(blk, dtype=np.uint8, count=n, offset=8)
+            phased, bits = blk[8 + n], blk[9 + n]
+            missing = pm >= 128
+            if phased or np.any((pm & 63)[~missing] != 2):
+                raise NotImplementedError("%s: variant %s is phased or not diploid (BGEN.cpp:172-177 stops on these too)" % (self.path, rsid))
+            if bits == 8:
+                p = np.frombuffer(blk, dtype=np.uint8, count=2 * n, offset=10 + n).astype(np.float64) / 255.0
+            elif bits == 16:
+                p = np.frombuffer(blk, dtype="<u2", count=2 * n, offset=10 + n).astype(np.float64) / 65535.0
+            else:
+                raise NotImplementedError("%s: %d-bit probabilities (8 and 16 are read; the reference reads 8 only)" % (self.path, bits))
+            first = 2.0 * p[0::2] + p[1::2]                 # copies of the first allele (BGEN.cpp:218-223)
+            d = first if allele_order == "alt-first" else 2.0 - first
+            d = np.where(missing, -1.0, d)
+            ref, alt = (alleles[1], alleles[0]) if allele_order == "alt-first" else (alleles[0], alleles[1])
+            info.append((chrom, str(pos), rsid, ref, alt))
+            rows.append(d)
+            if len(rows) == chunk:
+                yield info, np.vstack(rows)
+                info, rows = [], []
+        if rows:
+            yield info, np.vstack(rows)
+
+    def close(self):
+        self.f.close()
+
+
+def hardcalls_to_bed_rows(D):
+    """Integral dosage rows -> raw PLINK rows (2 bits per sample, A1 = the tested allele: 00 = 2 copies, 10 = 1, 11 = 0,
+    01 = missing; PLINK.hpp:48-56).  Raises when a dosage is not 0 / 1 / 2 / missing: fractional dosages need the dosage entry."""
+    D = np.asarray(D)
+    g = np.where(D < 0, -1, np.rint(D)).astype(np.int64)
+    if np.any((D >= 0) & (np.abs(D - g) > 1e-12)) or g.max(initial=0) > 2:
+        raise ValueError("fractional dosages cannot be packed as hard calls")
+    code = np.array([3, 2, 0, 1], dtype=np.uint8)[g]          # 0 -> 11, 1 -> 10, 2 -> 00, -1 -> 01
+    nm, n = code.shape
+    B0 = (n + 3) // 4
+    pad = np.full((nm, B0 * 4), 3, dtype=np.uint8)
+    pad[:, :n] = code
+    q = pad.reshape(nm, B0, 4)
+    return (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8).reshape(-1)

@@ -9,6 +9,7 @@ import os
 
 import numpy as np
 
+from . import genoio
 from .rdata import load_rda
 
 OUT_COLUMNS = ["CHR", "POS", "MarkerID", "Allele1", "Allele2", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE",
@@ -77,40 +78,65 @@ def Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude=(10, 20.5
     return vals
 
 
-def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioFile, SAIGEOutputFile=None, chrom="",
+IMPUTE_METHODS = {"best_guess": 1, "mean": 2, "minor": 3}
+
+
+def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", varianceRatioFile="", SAIGEOutputFile=None, chrom="",
                  LOCO=True, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, SPAcutoff=2.0, markers_per_chunk=10000,
                  is_output_moreDetails=True, se_two_sided=True, rank=0, world=1, is_Firth_beta=False, pCutoffforFirth=0.01,
                  firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
-                 cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True):
+                 cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True, vcfFile="", vcfField="DS", bgenFile="", sampleFile="",
+                 AlleleOrder="alt-first", impute_method="best_guess", dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0):
     """Returns the result table (list of dict rows; with return_rows=False only the number of tested variants, for scans
     whose table should not be held in memory); writes it tab-separated to SAIGEOutputFile when given, chunk by chunk.
-    Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the .bim
+    Genotypes: PLINK (bedFile / bimFile / famFile; raw 2-bit rows go to the device), or vcfFile (+ vcfField "DS" / "GT"), or
+    bgenFile (+ sampleFile when the file holds no sample identifiers): rows of dosages go to the device (genoio.py).
+    AlleleOrder applies to PLINK and BGEN as in the reference ("alt-first": the first allele is the tested one).
+    Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the variants
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
+    if impute_method not in IMPUTE_METHODS:
+        raise ValueError("impute_method should be 'best_guess', 'mean' or 'minor'.")
+    if AlleleOrder not in ("alt-first", "ref-first"):
+        raise ValueError("AlleleOrder should be 'alt-first' or 'ref-first'")
+    if sum(bool(x) for x in (bedFile, vcfFile, bgenFile)) != 1:
+        raise ValueError("give exactly one of bedFile (+ bimFile, famFile), vcfFile, bgenFile")
     model = ReadModel(GMMATmodelFile, chrom, LOCO)
     ratio = Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude)
     model["cateVarRatioMinMACVecExclude"], model["cateVarRatioMaxMACVecInclude"] = cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude
-    fam = [l.split()[1] for l in open(famFile)]
-    where = {s: i for i, s in enumerate(fam)}
-    missing = [s for s in model["sampleID"] if s not in where]
+    if bedFile:
+        ids = [l.split()[1] for l in open(famFile)]
+    elif vcfFile:
+        ids = genoio.vcf_samples(vcfFile)
+    else:
+        bg = genoio.BgenFile(bgenFile)
+        ids = genoio.read_sample_file(sampleFile) if sampleFile else bg.samples
+        if ids is None:
+            raise ValueError("%s holds no sample identifiers: give sampleFile" % bgenFile)
+        if len(ids) != bg.N:
+            raise ValueError("sampleFile lists %d samples, %s holds %d" % (len(ids), bgenFile, bg.N))
+    where = {}
+    for i, sid in enumerate(ids):
+        where.setdefault(sid, i)
+    missing = [sid for sid in model["sampleID"] if sid not in where]
     if missing:
-        raise ValueError("%d samples of the null model are not in %s" % (len(missing), famFile))
-    pos = np.array([where[s] for s in model["sampleID"]], dtype=np.int32)
+        raise ValueError("%d samples of the null model are not in the genotype file" % len(missing))
+    pos = np.array([where[sid] for sid in model["sampleID"]], dtype=np.int32)
     geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
     geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
     geno.setMaxMACforER(max_MAC_for_ER)                 # exact test of rare variants (step2_SPAtests.R:126 --max_MAC_for_ER, default 4)
-    with open(bedFile, "rb") as f:
-        magic = f.read(3)
-    if magic != b"\x6c\x1b\x01":
-        raise ValueError("%s is not a SNP-major PLINK .bed" % bedFile)
-    n_fam, B0 = len(fam), (len(fam) + 3) // 4
-    n_bim = _count_lines(bimFile)
-    # the .bed is mapped, not read: a chunk of raw rows is paged in when it is handed to the library, so a rank touches only
-    # its own slice of a file that can be far larger than host memory (BASELINE config 5: 10M variants x 50 KB)
-    body = np.memmap(bedFile, dtype=np.uint8, mode="r", offset=3)
-    if body.size < n_bim * B0:
-        raise ValueError("%s holds fewer than %d markers x %d bytes" % (bedFile, n_bim, B0))
-    per_rank = (n_bim + world - 1) // world
-    lo, hi = min(n_bim, rank * per_rank), min(n_bim, (rank + 1) * per_rank)
+    if bedFile:
+        source = _plink_chunks(geno, bedFile, bimFile, len(ids), AlleleOrder, rank, world, markers_per_chunk,
+                               (min_MAF, min_MAC, max_missing, se_two_sided))
+    else:
+        if vcfFile:
+            n_var = sum(1 for l in genoio._open_text(vcfFile) if not l.startswith("#"))
+            it = genoio.iter_vcf(vcfFile, vcfField, markers_per_chunk)
+        else:
+            n_var, it = bg.M, bg.variants(AlleleOrder, markers_per_chunk)
+        per_rank = (n_var + world - 1) // world
+        source = _dosage_chunks(geno, it, min(n_var, rank * per_rank), min(n_var, (rank + 1) * per_rank),
+                                (min_MAF, min_MAC, max_missing, se_two_sided, IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
+                                 dosage_zerod_MAC_cutoff))
     cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
     rows = [] if return_rows else None
     out = open(SAIGEOutputFile, "w") if SAIGEOutputFile else None
@@ -118,19 +144,15 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
     try:
         if out:
             out.write("\t".join(cols) + "\n")
-        bim_iter = _bim_lines(bimFile, lo, hi)
-        for m0 in range(lo, hi, markers_per_chunk):
-            m1 = min(hi, m0 + markers_per_chunk)
-            bim = [next(bim_iter) for _ in range(m1 - m0)]
-            res = geno.mainMarkerInCPP(body[m0 * B0:m1 * B0], n_fam, m1 - m0, min_MAF, min_MAC, max_missing, se_two_sided)
+        for info, res in source:                         # info rows: (CHR, POS, MarkerID, Allele1, Allele2)
             keep = np.nonzero(res[:, 0] == 1.0)[0]      # the others were filtered: not written (Main.cpp:296 `continue`)
             n_tested += len(keep)
             if out and len(keep):
-                out.write(_format_chunk(res[keep], [bim[j] for j in keep], cols, geno.STEP2_COLUMNS))
+                out.write(_format_chunk(res[keep], [info[j] for j in keep], cols, geno.STEP2_COLUMNS))
             if return_rows:
                 for j in keep:
-                    r, b = res[j], bim[j]
-                    row = {"CHR": b[0], "POS": b[3], "MarkerID": b[1], "Allele1": b[5], "Allele2": b[4]}     # alt-first: A1 = ALT = Allele2
+                    r, b = res[j], info[j]
+                    row = {"CHR": b[0], "POS": b[1], "MarkerID": b[2], "Allele1": b[3], "Allele2": b[4]}
                     for name, v in zip(geno.STEP2_COLUMNS[1:19], r[1:19]):
                         row[name] = v
                     row["Is.SPA"] = bool(r[10])
@@ -140,6 +162,46 @@ def SPAGMMATtest(geno, bedFile, bimFile, famFile, GMMATmodelFile, varianceRatioF
         if out:
             out.close()
     return rows if return_rows else n_tested
+
+
+def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args):
+    with open(bedFile, "rb") as f:
+        magic = f.read(3)
+    if magic != b"\x6c\x1b\x01":
+        raise ValueError("%s is not a SNP-major PLINK .bed" % bedFile)
+    B0 = (n_fam + 3) // 4
+    n_bim = _count_lines(bimFile)
+    # the .bed is mapped, not read: a chunk of raw rows is paged in when it is handed to the library, so a rank touches only
+    # its own slice of a file that can be far larger than host memory (BASELINE config 5: 10M variants x 50 KB)
+    body = np.memmap(bedFile, dtype=np.uint8, mode="r", offset=3)
+    if body.size < n_bim * B0:
+        raise ValueError("%s holds fewer than %d markers x %d bytes" % (bedFile, n_bim, B0))
+    per_rank = (n_bim + world - 1) // world
+    lo, hi = min(n_bim, rank * per_rank), min(n_bim, (rank + 1) * per_rank)
+    bim_iter = _bim_lines(bimFile, lo, hi)
+    for m0 in range(lo, hi, markers_per_chunk):
+        m1 = min(hi, m0 + markers_per_chunk)
+        bim = [next(bim_iter) for _ in range(m1 - m0)]
+        raw = body[m0 * B0:m1 * B0]
+        if AlleleOrder == "alt-first":                  # A1 of the .bim is the tested allele: Allele1 = A2, Allele2 = A1
+            info = [(b[0], b[3], b[1], b[5], b[4]) for b in bim]
+        else:                                           # ref-first: A2 is the tested allele; homozygote codes 00 <-> 11 exchanged
+            lo_b, hi_b = raw & 0x55, (raw >> 1) & 0x55
+            hom = ~(lo_b ^ hi_b) & 0x55
+            raw = raw ^ (hom | (hom << 1))
+            info = [(b[0], b[3], b[1], b[4], b[5]) for b in bim]
+        yield info, geno.mainMarkerInCPP(raw, n_fam, m1 - m0, *args)
+
+
+def _dosage_chunks(geno, it, lo, hi, args):
+    seen = 0
+    for info, D in it:
+        a, b = max(lo - seen, 0), min(hi - seen, len(info))
+        seen += len(info)
+        if a < b:
+            yield info[a:b], geno.mainMarkerInCPP_dosage(D[a:b], *args)
+        if seen >= hi:
+            break
 
 
 def _count_lines(path):
@@ -164,7 +226,7 @@ def _bim_lines(path, lo, hi):
                 yield l.split()
 
 
-_INT_COLS = {"N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het"}
+_INFO_COLS = ["CHR", "POS", "MarkerID", "Allele1", "Allele2"]
 
 
 def _format_chunk(res, bim, cols, table_cols):
@@ -173,16 +235,9 @@ def _format_chunk(res, bim, cols, table_cols):
     idx = {c: i for i, c in enumerate(table_cols)}
     fields = []
     for c in cols:
-        if c == "CHR":
-            fields.append([b[0] for b in bim])
-        elif c == "POS":
-            fields.append([b[3] for b in bim])
-        elif c == "MarkerID":
-            fields.append([b[1] for b in bim])
-        elif c == "Allele1":
-            fields.append([b[5] for b in bim])
-        elif c == "Allele2":
-            fields.append([b[4] for b in bim])
+        if c in _INFO_COLS:
+            k = _INFO_COLS.index(c)
+            fields.append([b[k] for b in bim])
         elif c == "Is.SPA":
             fields.append(np.where(res[:, idx[c]] != 0, "true", "false").tolist())
         else:

@@ -38,6 +38,12 @@ FILES = [
     # allele there, AF_Allele2 up to 0.99, so every row goes through the reference's flip branch)
     ("../output/genotype_100markers_marker_vcf.txt", "step2_100markers_golden_noLOCO.txt"),
     ("../output/genotype_100markers_marker_bgen.txt", "step2_100markers_golden_flipped.txt"),
+    # the VCF and BGEN copies themselves (the files those two tables were produced from) + two small files with missing calls
+    ("genotype_100markers.vcf.gz", "step2_100markers.vcf.gz"),
+    ("genotype_100markers.bgen", "step2_100markers.bgen"),
+    ("genotype_10markers.missingness.vcf.gz", "missing_10markers.vcf.gz"),
+    ("genotype_10markers.missingness.bgen", "missing_10markers.bgen"),
+    ("dosage_10markers.vcf.gz", "dosage_10markers.vcf.gz"),
     # a genome-wide-significant variant (p = 3.5e-7 after SPA): one-marker VCF of 10,000 samples, its model and result
     ("nfam_1000_MAF0.2_nMarker1_nseed200.vcf", "positive_signal_1marker.vcf"),
     ("../output/example_binary_positive_signal.rda", "positive_signal.rda"),

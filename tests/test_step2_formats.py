@@ -1,0 +1,239 @@
+"""Step-2 inputs other than PLINK: VCF (GT / DS) and BGEN v1.2 read on the host (saige_gpu_b200/genoio.py), tested as dosage
+rows by `sgb_step2_test_dosages`.
+
+Pins: the reference ships the same 100 markers as .bed, .vcf.gz and .bgen together with the result tables its step 2
+produced from the VCF copy (LOCO off) and from the BGEN copy (AlleleOrder alt-first on a ref-first file: alleles exchanged).
+CPU: the readers give the .bed's genotypes bit for bit, and the driver (device calls answered by the oracle) turns the real
+files into those tables.  GPU: the dosage kernel against the oracle on fractional dosages (three imputation methods, zeroing
+of small dosages, flips, the exact test, Firth), the real files through the kernel, and dosage rows of hard calls against
+the 2-bit kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import OracleDevice
+
+TOL_PRINT = 2e-5          # the golden tables print 6 significant digits
+NUMERIC = ["AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA", "AF_case", "AF_ctrl",
+           "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het"]
+
+
+def bed_genotypes(prefix):
+    from oracle import oracle as O
+    bed, N0, M0, _ = O.read_bed(prefix)
+    B0 = (N0 + 3) // 4
+    codes = ((bed.reshape(M0, B0)[:, :, None] >> np.array([0, 2, 4, 6])) & 3).reshape(M0, -1)[:, :N0]
+    return np.array([2.0, -1.0, 1.0, 0.0])[codes]            # copies of A1; -1 missing
+
+
+def test_readers_reproduce_the_bed(golden_dir):
+    from saige_gpu_b200 import genoio
+    g = bed_genotypes(os.path.join(golden_dir, "step2_100markers"))
+    fam = [l.split()[1] for l in open(os.path.join(golden_dir, "step2_100markers.fam"))]
+    bim = [l.split() for l in open(os.path.join(golden_dir, "step2_100markers.bim"))]
+    vcf = os.path.join(golden_dir, "step2_100markers.vcf.gz")
+    assert genoio.vcf_samples(vcf) == fam
+    chunks = list(genoio.iter_vcf(vcf, "GT", chunk=33))
+    assert [len(i) for i, _ in chunks] == [33, 33, 33, 1]
+    info = [x for i, _ in chunks for x in i]
+    D = np.vstack([d for _, d in chunks])
+    assert np.array_equal(D, g)                                # ALT copies of the VCF = A1 copies of the .bed
+    assert [(c, p, i) for c, p, i, _, _ in info] == [(b[0], b[3], b[1]) for b in bim]
+    assert [(r, a) for _, _, _, r, a in info] == [(b[5], b[4]) for b in bim]          # REF = A2, ALT = A1
+    with pytest.raises(ValueError):
+        next(genoio.iter_vcf(vcf, "DS"))                       # the file has no DS field
+    bg = genoio.BgenFile(os.path.join(golden_dir, "step2_100markers.bgen"))
+    assert (bg.M, bg.N, bg.layout, bg.compression, bg.samples) == (100, len(fam), 2, 1, None)
+    i2, D2 = next(bg.variants("ref-first", chunk=1000))
+    assert np.array_equal(D2, g) and i2 == info                # second allele of the BGEN = A1 of the .bed
+    bg = genoio.BgenFile(os.path.join(golden_dir, "step2_100markers.bgen"))
+    i3, D3 = next(bg.variants("alt-first", chunk=1000))
+    assert np.array_equal(D3, 2 - g) and [(r, a) for _, _, _, r, a in i3] == [(a, r) for _, _, _, r, a in info]
+    # missing calls: ./. in the VCF = ploidy-byte flag in the BGEN
+    _, Dv = next(genoio.iter_vcf(os.path.join(golden_dir, "missing_10markers.vcf.gz"), "GT"))
+    _, Db = next(genoio.BgenFile(os.path.join(golden_dir, "missing_10markers.bgen")).variants("ref-first"))
+    assert np.array_equal(Dv, Db) and (Dv < 0).sum() == 6
+    _, Dd = next(genoio.iter_vcf(os.path.join(golden_dir, "dosage_10markers.vcf.gz"), "DS"))
+    assert Dd.shape == (10, 1000) and Dd.min() == 0 and Dd.max() == 2
+    # hard calls pack back into the raw PLINK rows of the .bed
+    raw = np.fromfile(os.path.join(golden_dir, "step2_100markers.bed"), dtype=np.uint8)[3:]
+    assert np.array_equal(genoio.hardcalls_to_bed_rows(D), raw)
+    with pytest.raises(ValueError):
+        genoio.hardcalls_to_bed_rows(np.array([[0.0, 0.4]]))
+
+
+def _compare_with_golden(path, golden_path):
+    mine = [l.split("\t") for l in open(path).read().splitlines()]
+    gold = [l.split("\t") for l in open(golden_path).read().splitlines()]
+    assert len(mine) == len(gold) == 33 and mine[0] == gold[0]
+    for a, b in zip(mine[1:], gold[1:]):
+        for name, x, y in zip(gold[0], a, b):
+            if name in NUMERIC:
+                assert abs(float(x) - float(y)) <= TOL_PRINT * abs(float(y)) + 1e-300, (name, a[2], x, y)
+            else:
+                assert x == y, (name, a[2], x, y)
+
+
+def _sample_file(golden_dir, tmp_path):
+    p = str(tmp_path / "bgen_samples.txt")
+    with open(p, "w") as f:
+        f.write("".join(l.split()[1] + "\n" for l in open(os.path.join(golden_dir, "step2_100markers.fam"))))
+    return p
+
+
+CASES = [("vcf", dict(vcfField="GT", LOCO=False), "step2_100markers_golden_noLOCO.txt"),
+         ("bgen", dict(AlleleOrder="alt-first", LOCO=True), "step2_100markers_golden_flipped.txt"),
+         ("bgen", dict(AlleleOrder="ref-first", LOCO=True), "step2_100markers_golden.txt"),
+         ("plink", dict(AlleleOrder="ref-first", LOCO=True), "step2_100markers_golden_flipped.txt")]
+
+
+def _run_case(device, golden_dir, tmp_path, kind, kw, out):
+    from saige_gpu_b200 import step2
+    p = os.path.join(golden_dir, "step2_100markers")
+    src = dict(vcf=dict(vcfFile=p + ".vcf.gz"), bgen=dict(bgenFile=p + ".bgen", sampleFile=_sample_file(golden_dir, tmp_path)),
+               plink=dict(bedFile=p + ".bed", bimFile=p + ".bim", famFile=p + ".fam"))[kind]
+    return step2.SPAGMMATtest(device, GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"),
+                              varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), SAIGEOutputFile=out,
+                              chrom="1", min_MAC=20, markers_per_chunk=17, return_rows=False, **src, **kw)
+
+
+@pytest.mark.parametrize("kind,kw,golden", CASES)
+def test_driver_turns_the_reference_files_into_the_reference_tables(golden_dir, tmp_path, kind, kw, golden):
+    out = str(tmp_path / "out.txt")
+    assert _run_case(OracleDevice(), golden_dir, tmp_path, kind, kw, out) == 32
+    _compare_with_golden(out, os.path.join(golden_dir, golden))
+
+
+def test_variant_sharding_of_dosage_inputs(golden_dir, tmp_path):
+    from saige_gpu_b200 import step2
+    p = os.path.join(golden_dir, "step2_100markers")
+    common = dict(GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"), vcfFile=p + ".vcf.gz", vcfField="GT",
+                  varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), chrom="1", min_MAC=20, markers_per_chunk=9)
+    full = [r["MarkerID"] for r in step2.SPAGMMATtest(OracleDevice(), **common)]
+    parts = [[r["MarkerID"] for r in step2.SPAGMMATtest(OracleDevice(), rank=r, world=3, **common)] for r in range(3)]
+    assert sum(parts, []) == full and len(full) == 32
+    with pytest.raises(ValueError):
+        step2.SPAGMMATtest(OracleDevice(), bedFile=p + ".bed", **common)           # two genotype sources
+    with pytest.raises(ValueError):
+        step2.SPAGMMATtest(OracleDevice(), impute_method="median", **common)
+
+
+def dosage_set(seed, n_file=900, N=800, nm=180):
+    """Binary-trait model + fractional dosages: common and rare variants, major-allele-coded ones (flip), missing entries (as
+    -1 and as NaN), rare variants whose small dosages get zeroed, carriers enriched among cases for the rare ones."""
+    from test_step2_rare_exact import rare_variant_set
+    rng = np.random.default_rng(seed)
+    M, pos, _, _ = rare_variant_set(seed, n_file, N, identity=False)
+    cases = np.nonzero(M["y"] == 1)[0]
+    D = np.zeros((nm, n_file))
+    for m in range(nm):
+        kind = m % 6
+        if kind in (0, 1):                                    # common, imputed-looking dosages
+            f = rng.uniform(0.05, 0.5)
+            g = rng.binomial(2, f, size=n_file).astype(np.float64)
+            D[m] = np.clip(g + rng.normal(scale=0.08, size=n_file) * (rng.uniform(size=n_file) < 0.5), 0, 2)
+        elif kind == 2:                                       # major allele tested: flip
+            g = rng.binomial(2, rng.uniform(0.6, 0.95), size=n_file).astype(np.float64)
+            D[m] = np.clip(g - np.abs(rng.normal(scale=0.05, size=n_file)), 0, 2)
+        else:                                                 # rare: a few carriers (mostly cases) + dust below the zeroing cutoff
+            k = 1 + m % 5
+            car = pos[rng.choice(cases, size=k, replace=False)]
+            D[m, car] = rng.uniform(0.6, 1.0, size=k) * rng.choice([1.0, 2.0], size=k, p=[0.8, 0.2])
+            dust = rng.choice(n_file, size=12, replace=False)
+            D[m, dust] = np.maximum(D[m, dust], rng.uniform(0.01, 0.15, size=12))
+        if m % 4 == 1:
+            miss = rng.choice(n_file, size=9, replace=False)
+            D[m, miss[:5]] = -1.0
+            D[m, miss[5:]] = np.nan
+    return M, pos, D
+
+
+def test_oracle_dosage_semantics():
+    """imputeGenoAndFlip on dosages (UTIL.cpp:58-135): the three imputation values, zeroing only for rare variants."""
+    from oracle import step2_oracle as S2
+    M, pos, D = dosage_set(31)
+    n_zeroed = n_er = 0
+    for m in range(D.shape[0]):
+        G = np.where(np.isnan(D[m, pos]), -1.0, D[m, pos])
+        r0 = S2.test_marker(M, G, max_MAC_for_ER=4.0)
+        rz = S2.test_marker(M, G, max_MAC_for_ER=4.0, dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0)
+        assert r0 is not None and rz is not None
+        n_er += bool(rz["Is_ER"])
+        if rz["AC_Allele2"] != r0["AC_Allele2"]:
+            n_zeroed += 1
+            assert r0["AC_Allele2"] <= 10 + 1e-9 and rz["AC_Allele2"] < r0["AC_Allele2"]
+        if (G < 0).any():
+            acs = [S2.test_marker(M, G, impute_method=k)["AC_Allele2"] for k in ("best_guess", "mean", "minor")]
+            assert len(set(np.round(acs, 9))) >= 2                 # the imputed value enters the allele count
+    assert n_zeroed > 60 and n_er > 20
+
+
+# ---- through the C ABI ------------------------------------------------------------------------------------------------------
+ALL_COLS = (("AC_Allele2", 1), ("AF_Allele2", 2), ("MissingRate", 3), ("BETA", 4), ("SE", 5), ("Tstat", 6), ("var", 7), ("p.value", 8),
+            ("p.value.NA", 9), ("Is.SPA", 10), ("AF_case", 11), ("AF_ctrl", 12), ("N_case", 13), ("N_ctrl", 14), ("N_case_hom", 15),
+            ("N_case_het", 16), ("N_ctrl_hom", 17), ("N_ctrl_het", 18), ("Is.Firth", 20), ("Firth.converged", 21))
+
+
+@pytest.mark.gpu
+def test_gpu_dosage_kernel_vs_oracle():
+    from saige_gpu_b200 import SaigeB200
+    M, pos, D = dosage_set(32)
+    g, o = SaigeB200(device=0), OracleDevice()
+    for dev in (g, o):
+        dev.setSAIGEobjInCPP(M, M["varRatio"], 2.0, pos)
+        dev.setMaxMACforER(4.0)
+    o.M["offset"] = M["offset"]
+    for method in (1, 2, 3):
+        for firth in (False, True):
+            g.setFirth(firth, 0.05, M["offset"], se_from_fit=True)
+            o.setFirth(firth, 0.05, M["offset"], se_from_fit=True)
+            a = g.mainMarkerInCPP_dosage(D, 0.0, 0.5, 0.15, True, method, 0.2, 10.0)
+            b = o.mainMarkerInCPP_dosage(D, 0.0, 0.5, 0.15, True, method, 0.2, 10.0)
+            assert np.array_equal(a[:, 0], b[:, 0]) and a[:, 0].all()
+            for name, c in ALL_COLS:
+                err = np.abs(a[:, c] - b[:, c]) / np.maximum(np.abs(b[:, c]), 1e-300)
+                err[(a[:, c] == b[:, c])] = 0.0
+                assert np.nanmax(err) <= 1e-6, (method, firth, name, int(np.nanargmax(err)), a[np.nanargmax(err), c], b[np.nanargmax(err), c])
+            assert (a[:, 10] == 1).sum() > 10 and (not firth or (a[:, 20] == 1).sum() > 10)
+    # zeroing off / filters on (Firth and the exact test off: without zeroing a rare variant can have more than ten
+    # fractional carriers, where the product falls back to the saddle point)
+    for dev in (g, o):
+        dev.setFirth(False)
+        dev.setMaxMACforER(-1.0)
+    a = g.mainMarkerInCPP_dosage(D, 0.01, 3.0, 0.005, True, 1, 0.0, 0.0)
+    b = o.mainMarkerInCPP_dosage(D, 0.01, 3.0, 0.005, True, 1, 0.0, 0.0)
+    assert np.array_equal(a[:, 0], b[:, 0]) and 0 < a[:, 0].sum() < len(a)
+    t = a[:, 0] == 1
+    assert np.allclose(a[t][:, [4, 6, 7, 9]], b[t][:, [4, 6, 7, 9]], rtol=1e-6, atol=0)
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,kw,golden", CASES)
+def test_gpu_reference_files_reproduce_the_reference_tables(golden_dir, tmp_path, kind, kw, golden):
+    from saige_gpu_b200 import SaigeB200
+    g = SaigeB200(device=0)
+    out = str(tmp_path / "out.txt")
+    assert _run_case(g, golden_dir, tmp_path, kind, kw, out) == 32
+    _compare_with_golden(out, os.path.join(golden_dir, golden))
+    g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_dosage_rows_of_hard_calls_equal_the_two_bit_kernel(golden_dir):
+    from saige_gpu_b200 import SaigeB200, step2
+    p = os.path.join(golden_dir, "step2_100markers")
+    g = SaigeB200(device=0)
+    common = dict(GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"),
+                  varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), chrom="1", min_MAC=1,
+                  is_Firth_beta=True, pCutoffforFirth=0.1)
+    a = step2.SPAGMMATtest(g, p + ".bed", p + ".bim", p + ".fam", **common)
+    b = step2.SPAGMMATtest(g, vcfFile=p + ".vcf.gz", vcfField="GT", **common)
+    assert len(a) == len(b) > 60
+    for x, y in zip(a, b):
+        assert x["MarkerID"] == y["MarkerID"] and x["Allele2"] == y["Allele2"]
+        for k in NUMERIC:
+            assert abs(x[k] - y[k]) <= 1e-9 * abs(x[k]) + 1e-300, (x["MarkerID"], k, x[k], y[k])
+        assert x["Is.SPA"] == y["Is.SPA"] and x["Is.Firth"] == y["Is.Firth"]
+    g.close()

@@ -80,38 +80,7 @@ def test_driver_writes_the_reference_table_as_a_file(golden_dir, tmp_path):
     device call answered by the oracle: the file it writes IS the reference's golden table, header and all 32 rows."""
     from oracle import step2_oracle as S2
     from saige_gpu_b200 import step2
-    from saige_gpu_b200.api import SaigeB200
-
-    class OracleDevice:
-        STEP2_COLUMNS = SaigeB200.STEP2_COLUMNS
-
-        def setSAIGEobjInCPP(self, model, ratio, cutoff, pos):
-            self.M = dict(model, varRatio=ratio)
-            self.M["XV"] = (np.asarray(model["X"]) * np.asarray(model["mu2"])[:, None]).T
-            self.pos, self.cutoff = np.asarray(pos), cutoff
-
-        def setFirth(self, *a, **k):
-            pass
-
-        def setMaxMACforER(self, v):
-            self.er = v
-
-        def mainMarkerInCPP(self, rows, n_fam, nm, min_MAF, min_MAC, max_missing, se_two_sided):
-            out = np.full((nm, len(self.STEP2_COLUMNS)), np.nan)
-            body = np.asarray(rows)
-            for j in range(nm):
-                r = S2.test_marker(self.M, S2.plink_marker(body, n_fam, j, self.pos), min_MAF, min_MAC, max_missing, self.cutoff,
-                                   se_two_sided, max_MAC_for_ER=self.er)
-                out[j, 0] = 0.0 if r is None else 1.0
-                if r is None:
-                    continue
-                G = S2.plink_marker(body, n_fam, j, self.pos)
-                y = self.M["y"]
-                out[j, 1:13] = [r["AC_Allele2"], r["AF_Allele2"], r["MissingRate"], r["BETA"], r["SE"], r["Tstat"], r["var"],
-                                r["p_value"], r["p_value_NA"], float(r["Is_SPA"]), r["AF_case"], r["AF_ctrl"]]
-                out[j, 13:19] = [r["N_case"], r["N_ctrl"], np.sum((G == 2) & (y == 1)), np.sum((G == 1) & (y == 1)),
-                                 np.sum((G == 2) & (y == 0)), np.sum((G == 1) & (y == 0))]
-            return out
+    from conftest import OracleDevice
 
     p = os.path.join(golden_dir, "step2_100markers")
     path = str(tmp_path / "out.txt")
