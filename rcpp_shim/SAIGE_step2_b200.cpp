@@ -7,7 +7,8 @@
 // NOT COMPILED IN THIS REPOSITORY'S CI (no R / Rcpp in the build container).  The C ABI it calls is exercised by
 // tests/test_step2_golden.py through saige_gpu_b200/step2.py, which follows this file.
 //
-// What the library covers: PLINK input, best-guess imputation, full-GRM variance ratio (t_varRatio_null[0]), binary and
+// What the library covers: PLINK input (raw 2-bit rows; best-guess imputation), BGEN / VCF input (dosage rows; best_guess /
+// mean / minor imputation, zeroing of small dosages), full-GRM variance ratio (t_varRatio_null[0]), binary and
 // quantitative traits, SPA / SPA_fast, Firth's effect size, the exact test for MAC <= MACCutoffforER (<= 10), categorical
 // variance ratios.  Sparse-GRM variance, conditional analysis and the region tests keep the reference's code path: the
 // shim refuses those option combinations instead of silently ignoring them.
@@ -37,9 +38,9 @@ void setSAIGEobjInCPP(arma::mat & t_XVX, arma::mat & t_XXVX_inv, arma::mat & t_X
                       arma::vec & t_valueVec, int t_dimNum, bool t_isCondition, std::vector<uint32_t> & t_condition_genoIndex,
                       bool t_is_Firth_beta, double t_pCutoffforFirth, arma::vec & t_offset, arma::vec & t_resout)
 {
-    if (t_flagSparseGRM || t_isCondition || t_impute_method != "best_guess")
-        Rcpp::stop("saige_b200: sparse-GRM variance, conditional analysis and non-best-guess imputation are not provided by "
-                   "the B200 library; build without USE_SAIGE_B200 for these options");
+    if (t_flagSparseGRM || t_isCondition)
+        Rcpp::stop("saige_b200: sparse-GRM variance and conditional analysis are not provided by the B200 library; build "
+                   "without USE_SAIGE_B200 for these options");
     const int64_t N = (int64_t)t_X.n_rows;
     const int p = (int)t_X.n_cols;
     arma::mat XVX_inv_XV_t = t_XVX_inv_XV;       // N x p already (readInGLMM.R:60-75 stores XVX_inv_XV as N x p)
@@ -59,19 +60,35 @@ void setSAIGEobjInCPP(arma::mat & t_XVX, arma::mat & t_XXVX_inv, arma::mat & t_X
 // The PLINK branch of mainMarkerInCPP (Main.cpp:149-560): one call per chunk of marker indices.  `readRawRows` stands for
 // the seek + read of PlinkClass::getOneMarker (PLINK.cpp:164-300) without the decode: ceil(n_fam / 4) bytes per marker.
 std::vector<uint8_t> plink_read_raw_rows(const std::vector<std::string> & t_genoIndex, int64_t & n_fam);   // PLINK.cpp side
+// thin wrappers over the reference's own reader objects and globals (Main.cpp:60-75, 584-700)
+int64_t saige_b200_model_n();
+int saige_b200_impute_method();
+void saige_b200_read_dosages(const std::string & t_genoType, std::vector<std::string> & prev, std::vector<std::string> & cur, int64_t j, double *dst);
+extern double g_dosage_zerod_cutoff, g_dosage_zerod_MAC_cutoff;
 
 // [[Rcpp::export]]
 Rcpp::DataFrame mainMarkerInCPP(std::string & t_genoType, std::string & t_traitType, std::vector<std::string> & t_genoIndex_prev,
                                 std::vector<std::string> & t_genoIndex, bool t_isMoreOutput, bool t_isImputation, bool t_isFirth)
 {
-    if (t_genoType != "plink") Rcpp::stop("saige_b200: only PLINK input goes through the B200 library");
-    int64_t n_fam = 0;
-    std::vector<uint8_t> rows = plink_read_raw_rows(t_genoIndex, n_fam);
     const int64_t q = (int64_t)t_genoIndex.size();
     arma::mat out(22, q);                          // column-major 22 x q == row-major q x 22 of the C ABI
     // se_two_sided = 0: qnorm(p, upper tail) as in this fork's source (SAIGE_test.cpp:523-526)
-    ck2(sgb_step2_test_markers(saige_b200_ctx(), rows.data(), n_fam, q, g_marker_minMAF_cutoff, g_marker_minMAC_cutoff,
-                               g_missingRate_cutoff, 0, out.memptr()));
+    if (t_genoType == "plink") {
+        int64_t n_fam = 0;
+        std::vector<uint8_t> rows = plink_read_raw_rows(t_genoIndex, n_fam);
+        ck2(sgb_step2_test_markers(saige_b200_ctx(), rows.data(), n_fam, q, g_marker_minMAF_cutoff, g_marker_minMAC_cutoff,
+                                   g_missingRate_cutoff, 0, out.memptr()));
+    } else {
+        // bgen / vcf: the reference's readers (BgenClass::getOneMarker, VcfClass::getOneMarker) already deliver one dosage
+        // vector per marker in model-sample order with -1 for missing; they are stacked and tested as one batch.  The model
+        // was set with the identity sample map in this case (the readers did the matching).
+        const int64_t n = saige_b200_model_n();
+        arma::mat D(n, q);                         // column-major n x q == row-major q x n
+        for (int64_t j = 0; j < q; j++) saige_b200_read_dosages(t_genoType, t_genoIndex_prev, t_genoIndex, j, D.colptr(j));   // Unified_getOneMarker
+        ck2(sgb_step2_test_dosages(saige_b200_ctx(), D.memptr(), n, q, g_marker_minMAF_cutoff, g_marker_minMAC_cutoff,
+                                   g_missingRate_cutoff, 0, saige_b200_impute_method() /* 1 best_guess, 2 mean, 3 minor */,
+                                   g_dosage_zerod_cutoff, g_dosage_zerod_MAC_cutoff, out.memptr()));
+    }
     // rows with out(0, j) == 0 were filtered (Main.cpp:296 `continue`); the others fill the vectors of Main.cpp:520-560
     std::vector<double> altCounts, altFreq, missingRate, Beta, seBeta, Tstat, varT, pval, pvalNA, AF_case, AF_ctrl;
     std::vector<bool> isSPA;
