@@ -125,8 +125,12 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
     geno.setMaxMACforER(max_MAC_for_ER)                 # exact test of rare variants (step2_SPAtests.R:126 --max_MAC_for_ER, default 4)
     if bedFile:
+        # raw 2-bit rows are tested as they are (best-guess imputation is an integer); the other two imputation methods give
+        # fractional genotypes, so those rows are decoded here and go through the dosage entry
         source = _plink_chunks(geno, bedFile, bimFile, len(ids), AlleleOrder, rank, world, markers_per_chunk,
-                               (min_MAF, min_MAC, max_missing, se_two_sided))
+                               (min_MAF, min_MAC, max_missing, se_two_sided),
+                               None if impute_method == "best_guess" else (IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
+                                                                           dosage_zerod_MAC_cutoff))
     else:
         if vcfFile:
             n_var = sum(1 for l in genoio._open_text(vcfFile) if not l.startswith("#"))
@@ -164,7 +168,7 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     return rows if return_rows else n_tested
 
 
-def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args):
+def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args, as_dosage=None):
     with open(bedFile, "rb") as f:
         magic = f.read(3)
     if magic != b"\x6c\x1b\x01":
@@ -190,7 +194,12 @@ def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, marke
             hom = ~(lo_b ^ hi_b) & 0x55
             raw = raw ^ (hom | (hom << 1))
             info = [(b[0], b[3], b[1], b[4], b[5]) for b in bim]
-        yield info, geno.mainMarkerInCPP(raw, n_fam, m1 - m0, *args)
+        if as_dosage is None:
+            yield info, geno.mainMarkerInCPP(raw, n_fam, m1 - m0, *args)
+        else:
+            codes = ((np.asarray(raw).reshape(m1 - m0, B0)[:, :, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(m1 - m0, -1)
+            D = np.array([2.0, -1.0, 1.0, 0.0])[codes[:, :n_fam]]          # PLINK.hpp:48-56: copies of A1, 01 = missing
+            yield info, geno.mainMarkerInCPP_dosage(D, *args, *as_dosage)
 
 
 def _dosage_chunks(geno, it, lo, hi, args):

@@ -119,6 +119,49 @@ def test_variant_sharding_of_dosage_inputs(golden_dir, tmp_path):
         step2.SPAGMMATtest(OracleDevice(), impute_method="median", **common)
 
 
+def test_plink_rows_with_mean_or_minor_imputation_go_through_the_dosage_entry(tmp_path):
+    """A model written with rdata.save_rda + a synthetic .bed with missing calls: the driver decodes the rows for the two
+    imputation methods that give fractional genotypes; best_guess keeps the raw 2-bit rows."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import step2
+    from saige_gpu_b200.rdata import RList, save_rda
+    from test_step2_rare_exact import rare_variant_set
+    n_fam, N = 300, 260
+    M, pos, bed, nm = rare_variant_set(41, n_fam, N, identity=False)
+    ids = ["s%d" % i for i in range(n_fam)]
+    p = str(tmp_path / "syn")
+    open(p + ".bed", "wb").write(b"\x6c\x1b\x01" + bed.tobytes())
+    open(p + ".fam", "w").write("".join("f %s 0 0 0 -9\n" % i for i in ids))
+    open(p + ".bim", "w").write("".join("1\tv%d\t0\t%d\tA\tG\n" % (m, m + 1) for m in range(nm)))
+    noK = RList([(k, np.asarray(M[k])) for k in ("XV", "XVX", "XXVX_inv")] + [("XVX_inv", np.linalg.inv(M["XVX"])), ("S_a", M["S_a"]),
+                ("XVX_inv_XV", M["XVX_inv_XV"]), ("V", M["mu2"])], r_class=["SA_NULL"])
+    save_rda(p + ".rda", {"modglmm": dict([("theta", M["tau"]), ("fitted.values", M["mu"].reshape(-1, 1)), ("residuals", M["res"].reshape(-1, 1)),
+                                          ("sampleID", [ids[k] for k in pos]), ("obj.noK", noK), ("y", M["y"]), ("X", M["X"]),
+                                          ("traitType", "binary"), ("LOCO", False), ("offset", M["offset"].reshape(-1, 1))])})
+    open(p + ".varianceRatio.txt", "w").write("%.15g null 1\n" % M["varRatio"])
+    calls = []
+
+    class Dev(OracleDevice):
+        def mainMarkerInCPP(self, *a, **k):
+            calls.append("2bit")
+            return super().mainMarkerInCPP(*a, **k)
+
+        def mainMarkerInCPP_dosage(self, *a, **k):
+            calls.append("dosage")
+            return super().mainMarkerInCPP_dosage(*a, **k)
+
+    for method in ("best_guess", "mean", "minor"):
+        calls.clear()
+        rows = step2.SPAGMMATtest(Dev(), p + ".bed", p + ".bim", p + ".fam", p + ".rda", p + ".varianceRatio.txt", LOCO=False,
+                                  impute_method=method, markers_per_chunk=100, dosage_zerod_cutoff=0.0)
+        assert set(calls) == ({"2bit"} if method == "best_guess" else {"dosage"}) and len(rows) == nm
+        M2 = dict(M, varRatio=M["varRatio"])
+        for m in (2, 7, 12, 57):                                  # markers with missing calls (m % 5 == 2)
+            r = S2.test_marker(M2, S2.plink_marker(bed, n_fam, m, pos), impute_method=method, max_MAC_for_ER=4.0)
+            assert abs(rows[m]["p.value"] - r["p_value"]) <= 1e-9 * r["p_value"] and abs(rows[m]["AC_Allele2"] - r["AC_Allele2"]) < 1e-9
+    assert rows[2]["MissingRate"] > 0
+
+
 def dosage_set(seed, n_file=900, N=800, nm=180):
     """Binary-trait model + fractional dosages: common and rare variants, major-allele-coded ones (flip), missing entries (as
     -1 and as NaN), rare variants whose small dosages get zeroed, carriers enriched among cases for the rare ones."""
