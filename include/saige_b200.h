@@ -161,9 +161,9 @@ int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *
                         const int32_t *pos_in_fam);
 /* mainMarkerInCPP loop body (Main.cpp:229-520) for n_markers raw PLINK rows (ceil(n_fam/4) bytes each, A1 = ALT):
  * getOneMarker -> filter -> imputeGenoAndFlip (best_guess) -> scoreTestFast -> SPA / SPA_fast (SAIGE_test.cpp:212-292,
- * 345-640).  out[n_markers x 22] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
+ * 345-640).  out[n_markers x 28] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
  * p.value, p.value.NA, Is.SPA, AF_case, AF_ctrl, N_case, N_ctrl, N_case_hom, N_case_het, N_ctrl_hom, N_ctrl_het, var2,
- * Is.Firth, Firth converged.
+ * Is.Firth, Firth converged, BETA_c, SE_c, Tstat_c, var_c, p.value_c, p.value.NA_c (NaN without sgb_step2_set_condition).
  * se_two_sided = 1: SE of SPA-adjusted variants = |BETA| / |qnorm(p/2)| (matches the reference's bundled golden tables);
  * 0: |BETA| / qnorm(p, upper) as this fork's source has it (SAIGE_test.cpp:523-526). */
 /* is_Firth_beta / pCutoffforFirth (SAIGE_test.cpp:573-633; fast_logistf_fit_simple :893-986): variants of a binary trait
@@ -179,6 +179,16 @@ int sgb_step2_set_firth(sgb_ctx *h, int enable, double p_cutoff, const double *o
  * SE = |BETA| / |qnorm(p/2)|; Is.SPA stays 0.  Negative: off (the state after sgb_step2_set_model).  Values above 10 are
  * refused: the reference sizes the test for MAC <= 10 (ER_binary_func.cpp:26) and its Monte-Carlo regime is not built. */
 int sgb_step2_set_er(sgb_ctx *h, double max_mac_for_er);
+/* Conditional analysis (--condition; assign_conditionMarkers_factors, Main.cpp:2002-2179, and the t_isCondition block of
+ * getMarkerPval, SAIGE_test.cpp:640-790): with gtilde_k the covariate-adjusted genotype of conditioning marker k and v_k its
+ * variance ratio, P2[N x n_cond] (column-major) = sqrt(v_k) gtilde_k % mu2 * tau0, VarInv = pinv(P1 P2) with P1 row k =
+ * sqrt(v_k) gtilde_k^T, Tstat_cond[k] the marker's score, XtP2[p x n_cond] = XXVX_inv^T P2.  Every tested variant then also
+ * reports BETA_c, SE_c, Tstat_c, var_c, p.value_c, p.value.NA_c (out columns 22..27): T_c = T - G1P2 VarInv Tstat_cond,
+ * var_c = var - G1P2 VarInv G1P2^T, G1P2 = sqrt(v) gtilde^T P2, and the saddle-point approximation on T_c when
+ * T_c^2 / var_c > SPAcutoff^2.  The bundled conditional golden table reports the adjusted p-value itself (this fork's
+ * source prints half of it, SAIGE_test.cpp:752): the fixture wins.  n_cond = 0 switches it off; at most 4 markers. */
+int sgb_step2_set_condition(sgb_ctx *h, int n_cond, const double *P2, const double *XtP2, const double *VarInv,
+                            const double *Tstat_cond);
 /* Categorical variance ratios (t_varRatio_null with more than one entry, t_cateVarRatioMinMACVecExclude,
  * t_cateVarRatioMaxMACVecInclude of setSAIGEobjInCPP; SAIGEClass::assignVarianceRatio, SAIGE_test.cpp:801-833): a variant
  * with min_mac_exclude[c] < MAC <= max_mac_include[c] (MAC after imputation) uses ratios[c]; max_mac_include has n_cate - 1

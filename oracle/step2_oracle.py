@@ -253,6 +253,43 @@ def assign_variance_ratio(M, mac):
     return float(vr[-1])
 
 
+def impute_and_flip(Graw, impute_method="best_guess", dosage_zerod_cutoff=0.0, dosage_zerod_MAC_cutoff=0.0):
+    """getOneMarker's counts + imputeGenoAndFlip (UTIL.cpp:58-135) for one marker: (G in the tested coding, flip, MAC)."""
+    n = len(Graw)
+    miss = Graw < 0
+    cnt = n - int(miss.sum())
+    alt_freq = float(Graw[~miss].sum()) / cnt / 2 if cnt > 0 else 0.0
+    mac = min(alt_freq, 1 - alt_freq) * n * (1 - miss.sum() / n) * 2
+    G = Graw.copy()
+    flip = alt_freq > 0.5
+    if flip:
+        G = 2 - G
+        alt_freq = 1 - alt_freq
+    if miss.any():
+        impute_g = {"best_guess": math.floor(2 * alt_freq + 0.5), "mean": 2 * alt_freq, "minor": 0.0}[impute_method]
+        G[miss] = impute_g
+        mac = mac + impute_g * int(miss.sum())
+    if dosage_zerod_cutoff > 0 and mac <= dosage_zerod_MAC_cutoff:
+        G[np.abs(G) <= dosage_zerod_cutoff] = 0.0
+    return G, flip, min(G.sum(), 2 * n - G.sum())
+
+
+def condition_factors(M, cond_Graw, **impute_kw):
+    """assign_conditionMarkers_factors (Main.cpp:2002-2179): for every conditioning marker the covariate-adjusted genotype
+    gtilde (tested coding), P1 row = sqrt(vr) gtilde, P2 column = sqrt(vr) gtilde % mu2 tau0 (the is_region branch of
+    getMarkerPval, SAIGE_test.cpp:780-783), its score; VarInv = pinv(P1 P2)."""
+    P1, P2, T = [], [], []
+    for Graw in cond_Graw:
+        G, _, mac = impute_and_flip(np.asarray(Graw, dtype=np.float64), **impute_kw)
+        vr = assign_variance_ratio(M, mac)
+        gt = G - M["XXVX_inv"] @ (M["XV"] @ G)
+        P1.append(np.sqrt(vr) * gt)
+        P2.append(np.sqrt(vr) * gt * M["mu2"] * M["tau"][0])
+        T.append(score_test_fast(M, G, np.nonzero(G != 0)[0], vr)["Tstat"])
+    P1, P2 = np.array(P1), np.array(P2).T
+    return dict(P2=P2, VarInv=np.linalg.pinv(P1 @ P2), Tstat=np.array(T))
+
+
 def score_test_fast(M, G, idx, var_ratio=None):
     """scoreTestFast (SAIGE_test.cpp:212-292)."""
     g1, X1, A1, res1 = G[idx], M["X"][idx], M["XVX_inv_XV"][idx], M["res"][idx]
@@ -308,7 +345,7 @@ def firth_fit(gt, y, offset, maxit=50, maxstep=15, xconv=1e-5, gconv=1e-5):
 
 def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=2.0, se_two_sided=True, is_Firth_beta=False,
                 pCutoffforFirth=0.01, firth_se_from_fit=True, max_MAC_for_ER=-1.0, impute_method="best_guess",
-                dosage_zerod_cutoff=0.0, dosage_zerod_MAC_cutoff=0.0):
+                dosage_zerod_cutoff=0.0, dosage_zerod_MAC_cutoff=0.0, cond=None):
     """One pass of the mainMarkerInCPP loop body (Main.cpp:229-520).  Returns None when the marker is filtered.
     Graw: copies of the ALT allele per model sample, hard calls (0/1/2) or dosages in [0, 2]; negative = missing."""
     test_marker.__test__ = False
@@ -373,6 +410,34 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
         is_firth = True
         se = se_fit if firth_se_from_fit else abs(beta) / abs(stats.norm.isf(pval / 2 if (se_two_sided or is_er) else pval))
     sgn = -1.0 if flip else 1.0
+    extra = {}
+    if cond is not None:
+        # t_isCondition (SAIGE_test.cpp:640-790).  p.value_c = the adjusted p-value itself, SE_c = |BETA_c| / |qnorm(p/2)|: what
+        # the reference's bundled conditional table holds (this fork's source prints half the SPA p-value, :752)
+        vr_val = assign_variance_ratio(M, min(alt_count, 2 * n - alt_count))
+        gt = G - M["XXVX_inv"] @ (M["XV"] @ G)
+        g1p2 = np.sqrt(vr_val) * (gt @ cond["P2"])
+        Tc = st["Tstat"] - float(g1p2 @ cond["VarInv"] @ cond["Tstat"])
+        vc = st["var1"] - float(g1p2 @ cond["VarInv"] @ g1p2)
+        stat_c = Tc * Tc / vc
+        if vc <= np.finfo(float).tiny or not np.isfinite(stat_c):
+            p_na_c, stat_c = 1.0, 0.0
+        else:
+            p_na_c = float(stats.chi2.sf(stat_c, 1))
+        beta_c = Tc / vc
+        with np.errstate(divide="ignore", invalid="ignore"):
+            se_c = abs(beta_c) / np.sqrt(stat_c)
+        p_c = p_na_c
+        if M["trait"] == "binary" and stat_c > spa_cutoff ** 2:
+            m1 = float(M["mu"] @ gt)
+            q_c = Tc / np.sqrt(vc / st["var2"]) + m1
+            qinv_c = -abs(q_c - m1) + m1 if q_c - m1 > 0 else (m1 if q_c == m1 else abs(q_c - m1) + m1)
+            fast = (n - len(idx)) / n >= 0.5
+            pspa_c, conv_c = spa_pvalue(M["mu"], gt, q_c, qinv_c, p_na_c, idx, fast, st["var2"])
+            if conv_c and pspa_c != 0:
+                p_c = pspa_c
+                se_c = abs(beta_c) / abs(stats.norm.isf(pspa_c / 2))
+        extra = dict(BETA_c=sgn * beta_c, SE_c=se_c, Tstat_c=sgn * Tc, var_c=vc, p_value_c=p_c, p_value_NA_c=p_na_c)
     y = M["y"]
     case, ctrl = y == 1, y == 0
     afc, aft = G[case].mean() / 2, G[ctrl].mean() / 2
@@ -384,7 +449,7 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     n_ctrl_hom, n_ctrl_het = int((hom & ctrl).sum()), int((het & ctrl).sum())
     if flip:
         n_case_hom, n_ctrl_hom = int(case.sum()) - n_case_het - n_case_hom, int(ctrl.sum()) - n_ctrl_het - n_ctrl_hom
-    return dict(N_case_hom=n_case_hom, N_case_het=n_case_het, N_ctrl_hom=n_ctrl_hom, N_ctrl_het=n_ctrl_het, AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
+    return dict(**extra, N_case_hom=n_case_hom, N_case_het=n_case_het, N_ctrl_hom=n_ctrl_hom, N_ctrl_het=n_ctrl_het, AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
                 Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa, Is_ER=is_er,
                 Is_Firth=is_firth, Firth_converged=firth_conv,
                 AF_case=afc, AF_ctrl=aft, N_case=int(case.sum()), N_ctrl=int(ctrl.sum()))

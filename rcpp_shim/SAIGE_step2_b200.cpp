@@ -38,9 +38,11 @@ void setSAIGEobjInCPP(arma::mat & t_XVX, arma::mat & t_XXVX_inv, arma::mat & t_X
                       arma::vec & t_valueVec, int t_dimNum, bool t_isCondition, std::vector<uint32_t> & t_condition_genoIndex,
                       bool t_is_Firth_beta, double t_pCutoffforFirth, arma::vec & t_offset, arma::vec & t_resout)
 {
-    if (t_flagSparseGRM || t_isCondition)
-        Rcpp::stop("saige_b200: sparse-GRM variance and conditional analysis are not provided by the B200 library; build "
-                   "without USE_SAIGE_B200 for these options");
+    if (t_flagSparseGRM)
+        Rcpp::stop("saige_b200: sparse-GRM variance is not provided by the B200 library; build without USE_SAIGE_B200 for it");
+    // conditional analysis: assign_conditionMarkers_factors (Main.cpp:2002-2179) keeps its reference body up to the call of
+    // assignConditionFactors, which in the B200 build forwards P2Mat, XXVX_inv^T P2Mat, VarInvMat and TstatVec to
+    // sgb_step2_set_condition; the _c columns come back in rows 22..27 of the result table
     const int64_t N = (int64_t)t_X.n_rows;
     const int p = (int)t_X.n_cols;
     arma::mat XVX_inv_XV_t = t_XVX_inv_XV;       // N x p already (readInGLMM.R:60-75 stores XVX_inv_XV as N x p)
@@ -71,7 +73,7 @@ Rcpp::DataFrame mainMarkerInCPP(std::string & t_genoType, std::string & t_traitT
                                 std::vector<std::string> & t_genoIndex, bool t_isMoreOutput, bool t_isImputation, bool t_isFirth)
 {
     const int64_t q = (int64_t)t_genoIndex.size();
-    arma::mat out(22, q);                          // column-major 22 x q == row-major q x 22 of the C ABI
+    arma::mat out(28, q);                          // column-major 28 x q == row-major q x 28 of the C ABI (rows 22..27: conditional results)
     // se_two_sided = 0: qnorm(p, upper tail) as in this fork's source (SAIGE_test.cpp:523-526)
     if (t_genoType == "plink") {
         int64_t n_fam = 0;

@@ -85,6 +85,7 @@ _SIGS = {
     "sgb_step2_set_model": (C.c_int, [P, I64, C.c_int, C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, C.c_double, C.c_double, P]),
     "sgb_step2_set_firth": (C.c_int, [P, C.c_int, C.c_double, DP, C.c_int]),
     "sgb_step2_set_er": (C.c_int, [P, C.c_double]),
+    "sgb_step2_set_condition": (C.c_int, [P, C.c_int, DP, DP, DP, DP]),
     "sgb_step2_set_variance_ratios": (C.c_int, [P, C.c_int, DP, DP, DP]),
     "sgb_step2_test_markers": (C.c_int, [P, P, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, DP]),
     "sgb_step2_test_dosages": (C.c_int, [P, DP, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,

@@ -341,7 +341,7 @@ class SaigeB200:
     # ---- step 2: setSAIGEobjInCPP + mainMarkerInCPP ----
     STEP2_COLUMNS = ("tested", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA",
                      "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het",
-                     "var2", "Is.Firth", "Firth.converged")
+                     "var2", "Is.Firth", "Firth.converged", "BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "p.value.NA_c")
 
     def setSAIGEobjInCPP(self, model, varRatio, SPAcutoff, pos_in_fam):
         """model: dict with mu, res, mu2, y, X, XVX, XXVX_inv, XVX_inv_XV, S_a, tau, trait (readInGLMM.R:39-170)."""
@@ -375,6 +375,18 @@ class SaigeB200:
         if len(r) > 1 and (len(lo) != len(r) or len(hi) != len(r) - 1):
             raise SaigeB200Error("ERROR! The number of variance ratios are different from the length of cateVarRatioMinMACVecExclude")
         self._ck(self._L.sgb_step2_set_variance_ratios(self._h, len(r), _p(r), _p(lo), _p(hi)))
+
+    def setCondition(self, P2=None, XtP2=None, VarInv=None, Tstat_cond=None):
+        """assignConditionFactors: P2 (N x q), XtP2 = XXVX_inv^T P2 (p x q), VarInv (q x q), Tstat_cond (q); no argument = off."""
+        if P2 is None:
+            self._ck(self._L.sgb_step2_set_condition(self._h, 0, None, None, None, None))
+            return
+        P2, XtP2, VarInv = _f64(np.asarray(P2, dtype=np.float64)), _f64(np.asarray(XtP2, dtype=np.float64)), _f64(np.asarray(VarInv, dtype=np.float64))
+        T = _f64(np.asarray(Tstat_cond, dtype=np.float64).reshape(-1))
+        q = len(T)
+        if P2.shape != (self._step2_N, q) or VarInv.shape != (q, q) or XtP2.shape[1] != q:
+            raise SaigeB200Error("condition factors have inconsistent shapes")
+        self._ck(self._L.sgb_step2_set_condition(self._h, q, _p(P2), _p(XtP2), _p(VarInv), _p(T)))
 
     def setMaxMACforER(self, max_MAC_for_ER=4.0):
         """max_MAC_for_ER of SPAGMMATtest / setAssocTest_GlobalVarsInCPP: binary-trait variants with MAC <= this get the

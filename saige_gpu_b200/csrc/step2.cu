@@ -26,7 +26,8 @@
 
 #define S2_MAXP 16
 #define S2_THREADS 256
-#define S2_NOUT 22      // doubles per variant in the result table (see include/saige_b200.h)
+#define S2_NOUT 28      // doubles per variant in the result table (see include/saige_b200.h)
+#define S2_MAXCOND 4    // conditioning markers
 #define S2_MAXCATE 8    // MAC categories of the variance ratio (the reference's default has 2)
 
 struct s2_model {
@@ -49,6 +50,11 @@ struct s2_model {
     int n_cate;
     double cate_ratio[S2_MAXCATE], cate_min[S2_MAXCATE], cate_max[S2_MAXCATE];
     double mu_sum;           // sum of mu over the model's samples (mean fitted probability of a variant's non-carriers)
+    // conditional analysis (assignConditionFactors, Main.cpp:2002-2179): P2 = sqrt(vr) gtilde_cond % mu2 tau0 (N x n_cond, device),
+    // XtP2 = XXVX_inv^T P2 (p x n_cond), VarInv = pinv(P1 P2), VT = VarInv Tstat_cond
+    int n_cond;
+    const double *P2;
+    double XtP2[S2_MAXP * S2_MAXCOND], VarInv[S2_MAXCOND * S2_MAXCOND], VT[S2_MAXCOND];
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sm)
@@ -100,8 +106,10 @@ struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + no
 // tally), warps skip 32-sample groups that hold no minor allele, and no per-sample index or phenotype is read.
 // DOSE: the genotypes are doubles read through L2 (s2_dose) instead of 2-bit codes staged in shared memory; always with the
 // sample index (IDENT = false).
+// The hard-call fast path keeps three CTAs per SM (<= 85 registers, as before the conditional / dosage code was added: the
+// rarely taken branches spill, the popcount passes do not).
 template <bool IDENT, bool DOSE>
-__global__ void __launch_bounds__(S2_THREADS)
+__global__ void __launch_bounds__(S2_THREADS, IDENT ? 3 : 2)
 step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
              double max_missing, int se_two_sided, double *__restrict__ out, s2_dose DS)
 {
@@ -349,8 +357,47 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         // SE from the exact p-value, |qnorm(p/2)| (SAIGE_test.cpp:606-614; quantile(0) overflows there -> 0)
         seBeta = pval * 0.5 > 0.0 ? fabs(Beta) / fabs(normcdfinv(pval * 0.5)) : 0.0;
     }
-    // ---- saddle-point approximation (binary traits) ----
-    else if (M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff) {
+    // ---- conditional analysis (t_isCondition, SAIGE_test.cpp:640-660): score and variance after projecting out the
+    // conditioning markers.  gtilde^T P2 = g^T P2 - W^T (XXVX_inv^T P2): one pass over the non-zero genotypes ----
+    double Tc = nan(""), vc = nan(""), Beta_c = nan(""), se_c = nan(""), pval_c = nan(""), pval_noadj_c = nan(""), stat_c = 0.0;
+    if (M.n_cond > 0) {
+        double cp[S2_MAXCOND];
+#pragma unroll
+        for (int c = 0; c < S2_MAXCOND; c++) cp[c] = 0.0;
+        for (int64_t i = tid; i < N; i += S2_THREADS) {
+            const double g = GENO(i);
+            if (g != 0.0)
+                for (int c = 0; c < M.n_cond; c++) cp[c] += M.P2[i + (int64_t)c * N] * g;
+        }
+        double g1p2[S2_MAXCOND];
+        const double srv = sqrt(varRatio);
+        for (int c = 0; c < M.n_cond; c++) {
+            double v = block_sum(cp[c], red);
+            for (int j = 0; j < p; j++) v -= Ws[j] * M.XtP2[j + c * p];
+            g1p2[c] = srv * v;
+        }
+        Tc = S; vc = var1;
+        for (int c = 0; c < M.n_cond; c++) {
+            Tc -= g1p2[c] * M.VT[c];
+            double acc = 0.0;
+            for (int d = 0; d < M.n_cond; d++) acc += M.VarInv[c + d * M.n_cond] * g1p2[d];
+            vc -= g1p2[c] * acc;
+        }
+        stat_c = Tc * Tc / vc;
+        if (vc <= 2.2250738585072014e-308) { pval_noadj_c = 1.0; stat_c = 0.0; }
+        else if (isfinite(stat_c)) pval_noadj_c = erfc(sqrt(stat_c * 0.5));
+        else { pval_noadj_c = 1.0; stat_c = 0.0; }
+        Beta_c = Tc / vc;
+        se_c = fabs(Beta_c) / sqrt(stat_c);
+        pval_c = pval_noadj_c;
+    }
+    // ---- saddle-point approximation (binary traits): the marginal test when |T|/sqrt(var) > cutoff and the exact test did
+    // not take the variant, the conditional test when its own statistic exceeds cutoff^2 (SAIGE_test.cpp:699).  The
+    // reference runs the conditional SPA on whatever the marginal block left behind (its NAmu / NAsigma are only set
+    // there); here the shared quantities are computed whenever either test needs them ----
+    const bool spa_u = !isER && M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff;
+    const bool spa_c = M.n_cond > 0 && M.binary && stat_c > M.spa_cutoff * M.spa_cutoff;
+    if (spa_u || spa_c) {
         // gtilde_i = g_i - XXVX_inv[i,:] . (XV g),  XV g = W  (getadjGFast, SAIGE_test.cpp:306-315)
         double m1p = 0, gpos = 0, gneg = 0, gmuNB = 0, sigNB = 0;
         for (int64_t i = tid; i < N; i += S2_THREADS) {
@@ -366,9 +413,6 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         gpos = block_sum(gpos, red); gneg = block_sum(gneg, red); gmuNB = block_sum(gmuNB, red); sigNB = block_sum(sigNB, red);
         const int fast = ((double)N - nz) / (double)N >= 0.5;
         const double NAmu = m1 - gmuNB, NAsigma = var2 - sigNB;
-        const double q = S / sqrt(var1 / var2) + m1;
-        double qinv;
-        if (q - m1 > 0) qinv = -fabs(q - m1) + m1; else if (q - m1 == 0) qinv = m1; else qinv = fabs(q - m1) + m1;
         const double tol = 1.220703125e-4;          // eps^0.25 (SAIGE_test.cpp:515-516)
 
         // CGF sums at t over the samples that enter exactly: all samples (SPA) or the non-zero genotypes (SPA_fast)
@@ -393,66 +437,83 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             k0 = want0 ? block_sum(a0, red) : 0.0; k1 = block_sum(a1, red); k2 = block_sum(a2, red);
             if (fast) { k0 += NAmu * t + 0.5 * NAsigma * t * t; k1 += NAmu + NAsigma * t; k2 += NAsigma; }
         };
-        double pside[2]; bool conv_all = true, saddle_all = true;
-        for (int side = 0; side < 2; side++) {
-            const double qq = side == 0 ? q : qinv;
-            double root; bool conv = true;
-            if (qq >= gpos || qq <= gneg) root = INFINITY;
-            else {
-                // getroot_K1[_fast]_Binom (SPA_binary.cpp:70-140, 214-270), init 0, maxiter 1000
-                double t = 0.0, k0, k1, k2, prevJump = INFINITY;
-                cgf(t, k0, k1, k2, false);
-                double K1e = k1 - qq;
-                int rep = 1;
-                while (true) {
-                    double tnew = t - K1e / k2;
-                    if (isnan(tnew)) { conv = false; break; }
-                    if (fabs(tnew - t) < tol) { conv = true; break; }
-                    if (rep == 1000) { conv = false; break; }
-                    double n0, n1, n2;
-                    cgf(tnew, n0, n1, n2, false);
-                    double newK1 = n1 - qq;
-                    const bool changed = fast ? (K1e * newK1 < 0) : ((K1e > 0) - (K1e < 0)) != ((newK1 > 0) - (newK1 < 0));
-                    if (changed) {
-                        if (fabs(tnew - t) > prevJump - tol) {
-                            const double d = newK1 - K1e;
-                            tnew = t + ((d > 0) - (d < 0)) * prevJump / 2;
-                            cgf(tnew, n0, n1, n2, false);
-                            newK1 = n1 - qq;
-                            prevJump = prevJump / 2;
-                        } else prevJump = fabs(tnew - t);
+        // SPA / SPA_fast (SPA.cpp:20-185) for the statistic q: both tails; false when a root or a saddle point fails
+        auto spa = [&](double q, double pnoadj, double &pspa) -> bool {
+            double qinv;
+            if (q - m1 > 0) qinv = -fabs(q - m1) + m1; else if (q - m1 == 0) qinv = m1; else qinv = fabs(q - m1) + m1;
+            double pside[2]; bool conv_all = true, saddle_all = true;
+            for (int side = 0; side < 2; side++) {
+                const double qq = side == 0 ? q : qinv;
+                double root; bool conv = true;
+                if (qq >= gpos || qq <= gneg) root = INFINITY;
+                else {
+                    // getroot_K1[_fast]_Binom (SPA_binary.cpp:70-140, 214-270), init 0, maxiter 1000
+                    double t = 0.0, k0, k1, k2, prevJump = INFINITY;
+                    cgf(t, k0, k1, k2, false);
+                    double K1e = k1 - qq;
+                    int rep = 1;
+                    while (true) {
+                        double tnew = t - K1e / k2;
+                        if (isnan(tnew)) { conv = false; break; }
+                        if (fabs(tnew - t) < tol) { conv = true; break; }
+                        if (rep == 1000) { conv = false; break; }
+                        double n0, n1, n2;
+                        cgf(tnew, n0, n1, n2, false);
+                        double newK1 = n1 - qq;
+                        const bool changed = fast ? (K1e * newK1 < 0) : ((K1e > 0) - (K1e < 0)) != ((newK1 > 0) - (newK1 < 0));
+                        if (changed) {
+                            if (fabs(tnew - t) > prevJump - tol) {
+                                const double d = newK1 - K1e;
+                                tnew = t + ((d > 0) - (d < 0)) * prevJump / 2;
+                                cgf(tnew, n0, n1, n2, false);
+                                newK1 = n1 - qq;
+                                prevJump = prevJump / 2;
+                            } else prevJump = fabs(tnew - t);
+                        }
+                        rep++; t = tnew; K1e = newK1; k2 = n2;
                     }
-                    rep++; t = tnew; K1e = newK1; k2 = n2;
+                    root = t;
                 }
-                root = t;
-            }
-            if (!conv) { conv_all = false; break; }
-            // Get_Saddle_Prob[_fast]_Binom (SPA_binary.cpp:146-214, 276-330): Lugannani-Rice
-            double k0, k1, k2;
-            double ps = 0.0; bool isSaddle = false;
-            if (isfinite(root)) {
-                cgf(root, k0, k1, k2, true);
-                const double temp1 = root * qq - k0;
-                if (isfinite(k0) && isfinite(k2) && temp1 >= 0 && k2 >= 0) {
-                    const double w = ((root > 0) - (root < 0)) * sqrt(2.0 * temp1), v = root * sqrt(k2);
-                    if (w != 0) {
-                        const double Zt = w + log(v / w) / w;
-                        ps = Zt > 0 ? 0.5 * erfc(Zt * 0.7071067811865476) : -0.5 * erfc(-Zt * 0.7071067811865476);
-                        isSaddle = true;
+                if (!conv) { conv_all = false; break; }
+                // Get_Saddle_Prob[_fast]_Binom (SPA_binary.cpp:146-214, 276-330): Lugannani-Rice
+                double k0, k1, k2;
+                double ps = 0.0; bool isSaddle = false;
+                if (isfinite(root)) {
+                    cgf(root, k0, k1, k2, true);
+                    const double temp1 = root * qq - k0;
+                    if (isfinite(k0) && isfinite(k2) && temp1 >= 0 && k2 >= 0) {
+                        const double w = ((root > 0) - (root < 0)) * sqrt(2.0 * temp1), v = root * sqrt(k2);
+                        if (w != 0) {
+                            const double Zt = w + log(v / w) / w;
+                            ps = Zt > 0 ? 0.5 * erfc(Zt * 0.7071067811865476) : -0.5 * erfc(-Zt * 0.7071067811865476);
+                            isSaddle = true;
+                        }
                     }
                 }
+                if (!isSaddle) { saddle_all = false; ps = pnoadj / 2; }
+                pside[side] = ps;
             }
-            if (!isSaddle) { saddle_all = false; ps = pval_noadj / 2; }
-            pside[side] = ps;
-        }
-        if (conv_all) {
-            const double pspa = fabs(pside[0]) + fabs(pside[1]);
-            if (saddle_all && pspa != 0) {
+            if (!conv_all) return false;
+            pspa = fabs(pside[0]) + fabs(pside[1]);
+            return saddle_all && pspa != 0;
+        };
+        if (spa_u) {
+            double pspa;
+            if (spa(S / sqrt(var1 / var2) + m1, pval_noadj, pspa)) {
                 isSPA = 1.0; pval = pspa;
                 // SE from the SPA p-value.  se_two_sided: |qnorm(p/2)| (what produced the reference's bundled golden tables);
                 // otherwise qnorm(p, upper tail) as written in this fork's source (SAIGE_test.cpp:523-526).
                 const double qv = fabs(normcdfinv(se_two_sided ? pspa * 0.5 : pspa));
                 seBeta = fabs(Beta) / qv;
+            }
+        }
+        if (spa_c) {
+            // the reference's bundled conditional table reports the adjusted p-value itself and SE = |BETA_c| / |qnorm(p/2)|
+            // (this fork's source prints half of it, SAIGE_test.cpp:752: the fixture wins)
+            double pspa;
+            if (spa(Tc / sqrt(vc / var2) + m1, pval_noadj_c, pspa)) {
+                pval_c = pspa;
+                se_c = fabs(Beta_c) / fabs(normcdfinv(pspa * 0.5));
             }
         }
     }
@@ -510,6 +571,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         o[4] = sgn * BetaOut; o[5] = seBeta; o[6] = sgn * S; o[7] = var1; o[8] = pval; o[9] = pval_noadj; o[10] = isSPA;
         o[11] = afc; o[12] = aft; o[13] = ncase; o[14] = nctrl; o[15] = case_hom; o[16] = case_het; o[17] = ctrl_hom; o[18] = ctrl_het;
         o[19] = var2; o[20] = isFirth; o[21] = firthConv;
+        o[22] = sgn * Beta_c; o[23] = se_c; o[24] = sgn * Tc; o[25] = vc; o[26] = pval_c; o[27] = pval_noadj_c;
     }
 }
 
@@ -522,6 +584,7 @@ struct sgb_step2 {
     int32_t *d_pos = nullptr;
     uint32_t *d_ycase = nullptr;
     double *d_offset = nullptr;
+    double *d_P2 = nullptr;
     uint8_t *d_bed = nullptr; size_t bed_bytes = 0;
     double *d_out = nullptr; size_t out_elems = 0;
     uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
@@ -541,6 +604,7 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     sgb_step2 *s = h->step2;
     if (s->d_vec) { cudaFree(s->d_vec); s->d_vec = nullptr; }
     if (s->d_pos) { cudaFree(s->d_pos); s->d_pos = nullptr; }
+    if (s->d_P2) { cudaFree(s->d_P2); s->d_P2 = nullptr; }
     const size_t nvec = (size_t)N * (4 + 3 * p);
     CUDA_OK(h, cudaMalloc((void **)&s->d_vec, sizeof(double) * nvec));
     CUDA_OK(h, cudaMalloc((void **)&s->d_pos, sizeof(int32_t) * N));
@@ -574,7 +638,7 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     CUDA_OK(h, cudaMalloc((void **)&s->d_offset, sizeof(double) * N));
     CUDA_OK(h, cudaMemset(s->d_offset, 0, sizeof(double) * N));
     M.offset = s->d_offset; M.firth = 0; M.firth_se_from_fit = 1; M.firth_cutoff = 0.01;
-    M.er_max_mac = -1.0; M.mu_sum = 0.0; M.n_cate = 1;
+    M.er_max_mac = -1.0; M.mu_sum = 0.0; M.n_cate = 1; M.n_cond = 0; M.P2 = nullptr;
     for (int64_t i = 0; i < N; i++) M.mu_sum += mu[i];
     return 0;
 }
@@ -597,6 +661,30 @@ extern "C" int sgb_step2_set_variance_ratios(sgb_ctx *h, int n_cate, const doubl
         M.cate_max[c] = c + 1 < n_cate ? max_mac_include[c] : INFINITY;
     }
     M.n_cate = n_cate; M.varRatio = ratios[0];
+    return 0;
+}
+
+extern "C" int sgb_step2_set_condition(sgb_ctx *h, int n_cond, const double *P2, const double *XtP2, const double *VarInv,
+                                       const double *Tstat_cond)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    sgb_step2 *s = h->step2;
+    if (!s || !s->d_vec) return sgb_fail(h, "step2: call sgb_step2_set_model first");
+    if (n_cond < 0 || n_cond > S2_MAXCOND) return sgb_fail(h, "step2: %d conditioning markers, supported 0..%d", n_cond, S2_MAXCOND);
+    s2_model &M = s->M;
+    if (s->d_P2) { cudaFree(s->d_P2); s->d_P2 = nullptr; }
+    M.n_cond = 0; M.P2 = nullptr;
+    if (n_cond == 0) return 0;
+    CUDA_OK(h, cudaMalloc((void **)&s->d_P2, sizeof(double) * (size_t)M.N * n_cond));
+    CUDA_OK(h, cudaMemcpy(s->d_P2, P2, sizeof(double) * (size_t)M.N * n_cond, cudaMemcpyHostToDevice));
+    for (int i = 0; i < M.p * n_cond; i++) M.XtP2[i] = XtP2[i];
+    for (int i = 0; i < n_cond * n_cond; i++) M.VarInv[i] = VarInv[i];
+    for (int c = 0; c < n_cond; c++) {
+        double v = 0.0;
+        for (int d = 0; d < n_cond; d++) v += VarInv[c + d * n_cond] * Tstat_cond[d];
+        M.VT[c] = v;
+    }
+    M.n_cond = n_cond; M.P2 = s->d_P2;
     return 0;
 }
 
@@ -743,6 +831,7 @@ void sgb_step2_free(sgb_ctx *h)
     if (s->d_pos) cudaFree(s->d_pos);
     if (s->d_ycase) cudaFree(s->d_ycase);
     if (s->d_offset) cudaFree(s->d_offset);
+    if (s->d_P2) cudaFree(s->d_P2);
     if (s->d_bed) cudaFree(s->d_bed);
     if (s->d_out) cudaFree(s->d_out);
     for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }

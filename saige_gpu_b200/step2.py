@@ -79,6 +79,57 @@ def Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude=(10, 20.5
 
 
 IMPUTE_METHODS = {"best_guess": 1, "mean": 2, "minor": 3}
+COND_COLUMNS = ["BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "p.value.NA_c"]
+
+
+def _impute_and_flip(Graw, impute_method, zerod_cutoff, zerod_mac_cutoff):
+    """Host copy of getOneMarker's counts + imputeGenoAndFlip (UTIL.cpp:58-135) for the handful of conditioning markers."""
+    n = len(Graw)
+    miss = ~(Graw >= 0)
+    cnt = n - int(miss.sum())
+    af = float(Graw[~miss].sum()) / cnt / 2 if cnt > 0 else 0.0
+    mac = min(af, 1 - af) * n * (1 - miss.sum() / n) * 2
+    G = np.where(miss, 0.0, Graw)
+    if af > 0.5:
+        G, af = 2 - G, 1 - af
+    if miss.any():
+        g0 = {"best_guess": np.floor(2 * af + 0.5), "mean": 2 * af, "minor": 0.0}[impute_method]
+        G[miss] = g0
+        mac += g0 * int(miss.sum())
+    if zerod_cutoff > 0 and mac <= zerod_mac_cutoff:
+        G[np.abs(G) <= zerod_cutoff] = 0.0
+    return G, min(G.sum(), 2 * n - G.sum())
+
+
+def _pick_ratio(ratio, mac, lo, hi):
+    r = np.asarray(ratio, dtype=np.float64).reshape(-1)
+    if len(r) == 1:
+        return float(r[0])
+    for i in range(len(hi)):
+        if mac <= hi[i]:
+            return float(r[i])
+    return float(r[-1])
+
+
+def condition_factors(model, ratio, cond_rows, impute_method="best_guess", zerod_cutoff=0.2, zerod_mac_cutoff=10.0,
+                      cate_lo=(10, 20.5), cate_hi=(20.5,)):
+    """assign_conditionMarkers_factors (Main.cpp:2002-2179) on the host, as in the reference: for each conditioning marker
+    (dosage row in model-sample order) gtilde = G - XXVX_inv (XV G), P1 row = sqrt(vr) gtilde, P2 column = sqrt(vr) gtilde %
+    mu2 tau0, its score T = (res.G - S_a.Z) / tau0; VarInv = pinv(P1 P2).  Returns what sgb_step2_set_condition takes."""
+    X, mu2, tau0 = model["X"], model["mu2"], float(model["tau"][0])
+    XV = (X * mu2[:, None]).T
+    P1, P2, T = [], [], []
+    for row in cond_rows:
+        G, mac = _impute_and_flip(np.asarray(row, dtype=np.float64), impute_method, zerod_cutoff, zerod_mac_cutoff)
+        if G.sum() == 0:
+            raise ValueError("ERROR: Conditioning marker is monomorphic")
+        vr = _pick_ratio(ratio, mac, cate_lo, cate_hi)
+        gt = G - model["XXVX_inv"] @ (XV @ G)
+        P1.append(np.sqrt(vr) * gt)
+        P2.append(np.sqrt(vr) * gt * mu2 * tau0)
+        T.append((float(model["res"] @ G) - float(model["S_a"] @ (model["XVX_inv_XV"].T @ G))) / tau0)
+    P1, P2 = np.array(P1), np.array(P2).T
+    return dict(P2=P2, XtP2=model["XXVX_inv"].T @ P2, VarInv=np.linalg.pinv(P1 @ P2), Tstat_cond=np.array(T))
 
 
 def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", varianceRatioFile="", SAIGEOutputFile=None, chrom="",
@@ -86,12 +137,14 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                  is_output_moreDetails=True, se_two_sided=True, rank=0, world=1, is_Firth_beta=False, pCutoffforFirth=0.01,
                  firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
                  cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True, vcfFile="", vcfField="DS", bgenFile="", sampleFile="",
-                 AlleleOrder="alt-first", impute_method="best_guess", dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0):
+                 AlleleOrder="alt-first", impute_method="best_guess", dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0,
+                 condition=""):
     """Returns the result table (list of dict rows; with return_rows=False only the number of tested variants, for scans
     whose table should not be held in memory); writes it tab-separated to SAIGEOutputFile when given, chunk by chunk.
     Genotypes: PLINK (bedFile / bimFile / famFile; raw 2-bit rows go to the device), or vcfFile (+ vcfField "DS" / "GT"), or
     bgenFile (+ sampleFile when the file holds no sample identifiers): rows of dosages go to the device (genoio.py).
     AlleleOrder applies to PLINK and BGEN as in the reference ("alt-first": the first allele is the tested one).
+    condition = "chr:pos:ref:alt,..." (at most 4 markers of the same genotype file): conditional analysis, six more columns.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the variants
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
     if impute_method not in IMPUTE_METHODS:
@@ -124,6 +177,16 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
     geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
     geno.setMaxMACforER(max_MAC_for_ER)                 # exact test of rare variants (step2_SPAtests.R:126 --max_MAC_for_ER, default 4)
+    if condition:
+        wanted = [c.strip() for c in condition.split(",") if c.strip()]
+        found = _find_markers(bedFile, bimFile, len(ids), vcfFile, vcfField, bgenFile, AlleleOrder, wanted)
+        if any(w not in found for w in wanted):
+            raise ValueError("conditioning marker(s) %s not found in the genotype file" % ", ".join(w for w in wanted if w not in found))
+        f = condition_factors(model, ratio, [found[w][pos] for w in wanted], impute_method, dosage_zerod_cutoff,
+                              dosage_zerod_MAC_cutoff, cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude)
+        geno.setCondition(f["P2"], f["XtP2"], f["VarInv"], f["Tstat_cond"])
+    else:
+        geno.setCondition()
     if bedFile:
         # raw 2-bit rows are tested as they are (best-guess imputation is an integer); the other two imputation methods give
         # fractional genotypes, so those rows are decoded here and go through the dosage entry
@@ -142,6 +205,9 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                                 (min_MAF, min_MAC, max_missing, se_two_sided, IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
                                  dosage_zerod_MAC_cutoff))
     cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
+    if condition:                                       # writeOutfile_single (Main.cpp:2437-2560): the _c columns follow Is.SPA
+        k = cols.index("Is.SPA") + 1
+        cols = cols[:k] + COND_COLUMNS + cols[k:]
     rows = [] if return_rows else None
     out = open(SAIGEOutputFile, "w") if SAIGEOutputFile else None
     n_tested = 0
@@ -161,11 +227,42 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                         row[name] = v
                     row["Is.SPA"] = bool(r[10])
                     row["Is.Firth"], row["Firth.converged"] = bool(r[20]), bool(r[21])
+                    if condition:
+                        for name, v in zip(COND_COLUMNS, r[22:28]):
+                            row[name] = v
                     rows.append(row)
     finally:
         if out:
             out.close()
     return rows if return_rows else n_tested
+
+
+def _find_markers(bedFile, bimFile, n_fam, vcfFile, vcfField, bgenFile, AlleleOrder, wanted):
+    """Dosage rows (file sample order) of the markers named chr:pos:ref:alt (extract_genoIndex_condition, R/SAIGE_Test_main.R:357)."""
+    wanted, found = set(wanted), {}
+    if bedFile:
+        B0 = (n_fam + 3) // 4
+        body = np.memmap(bedFile, dtype=np.uint8, mode="r", offset=3)
+        with open(bimFile) as f:
+            for m, l in enumerate(f):
+                b = l.split()
+                ref, alt = (b[5], b[4]) if AlleleOrder == "alt-first" else (b[4], b[5])
+                key = "%s:%s:%s:%s" % (b[0], b[3], ref, alt)
+                if key in wanted:
+                    raw = np.asarray(body[m * B0:(m + 1) * B0])
+                    codes = ((raw[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(-1)[:n_fam]
+                    d = np.array([2.0, -1.0, 1.0, 0.0])[codes]
+                    found[key] = d if AlleleOrder == "alt-first" else np.where(d < 0, -1.0, 2.0 - d)
+        return found
+    it = genoio.iter_vcf(vcfFile, vcfField, 256) if vcfFile else genoio.BgenFile(bgenFile).variants(AlleleOrder, 256)
+    for info, D in it:
+        for j, (c, p_, _, ref, alt) in enumerate(info):
+            key = "%s:%s:%s:%s" % (c, p_, ref, alt)
+            if key in wanted:
+                found[key] = D[j]
+        if len(found) == len(wanted):
+            break
+    return found
 
 
 def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args, as_dosage=None):

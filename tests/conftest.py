@@ -58,10 +58,13 @@ class OracleDevice:
     host side (file formats, sample matching, chunking, sharding, output) runs without a GPU.  Never imported by the product."""
     STEP2_COLUMNS = ("tested", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA",
                      "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het",
-                     "var2", "Is.Firth", "Firth.converged")
+                     "var2", "Is.Firth", "Firth.converged", "BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "p.value.NA_c")
 
     def __init__(self):
-        self.er, self.firth = -1.0, dict(is_Firth_beta=False)
+        self.er, self.firth, self.cond = -1.0, dict(is_Firth_beta=False), None
+
+    def setCondition(self, P2=None, XtP2=None, VarInv=None, Tstat_cond=None):
+        self.cond = None if P2 is None else dict(P2=np.asarray(P2), VarInv=np.asarray(VarInv), Tstat=np.asarray(Tstat_cond))
 
     def setSAIGEobjInCPP(self, model, ratio, cutoff, pos):
         self.M = dict(model, varRatio=ratio)
@@ -78,7 +81,7 @@ class OracleDevice:
         from oracle import step2_oracle as S2
         out = np.full((nm, len(self.STEP2_COLUMNS)), np.nan)
         for j in range(nm):
-            r = S2.test_marker(self.M, G_of(j), spa_cutoff=self.cutoff, max_MAC_for_ER=self.er, **self.firth, **kw)
+            r = S2.test_marker(self.M, G_of(j), spa_cutoff=self.cutoff, max_MAC_for_ER=self.er, cond=self.cond, **self.firth, **kw)
             out[j, 0] = 0.0 if r is None else 1.0
             if r is None:
                 continue
@@ -86,6 +89,8 @@ class OracleDevice:
                             r["p_value"], r["p_value_NA"], float(r["Is_SPA"]), r["AF_case"], r["AF_ctrl"]]
             out[j, 13:19] = [r["N_case"], r["N_ctrl"], r["N_case_hom"], r["N_case_het"], r["N_ctrl_hom"], r["N_ctrl_het"]]
             out[j, 20:22] = [float(r["Is_Firth"]), float(r["Firth_converged"])]
+            if self.cond is not None:
+                out[j, 22:28] = [r["BETA_c"], r["SE_c"], r["Tstat_c"], r["var_c"], r["p_value_c"], r["p_value_NA_c"]]
         return out
 
     def mainMarkerInCPP(self, rows, n_fam, nm, min_MAF=0.0, min_MAC=0.5, max_missing=0.15, se_two_sided=True):

@@ -38,6 +38,8 @@ FILES = [
     # allele there, AF_Allele2 up to 0.99, so every row goes through the reference's flip branch)
     ("../output/genotype_100markers_marker_vcf.txt", "step2_100markers_golden_noLOCO.txt"),
     ("../output/genotype_100markers_marker_bgen.txt", "step2_100markers_golden_flipped.txt"),
+    # conditional analysis of the same markers on rs13 and rs79 (--condition=1:13:A:C,1:79:A:C, extdata/cmd.sh:128-139)
+    ("../output/genotype_100markers_marker_vcf_cond.txt", "step2_100markers_golden_cond.txt"),
     # the VCF and BGEN copies themselves (the files those two tables were produced from) + two small files with missing calls
     ("genotype_100markers.vcf.gz", "step2_100markers.vcf.gz"),
     ("genotype_100markers.bgen", "step2_100markers.bgen"),

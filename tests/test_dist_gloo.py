@@ -110,6 +110,9 @@ def test_step2_variant_sharding_is_a_partition(tmp_path):
         def setMaxMACforER(self, *a):
             pass
 
+        def setCondition(self, *a):
+            pass
+
         def mainMarkerInCPP(self, rows, nf, nm, *a):
             flat = np.asarray(rows).reshape(-1)[:nm * B0]
             # recover where this contiguous chunk starts in the file body; keep every third marker "untested"

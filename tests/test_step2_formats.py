@@ -105,6 +105,64 @@ def test_driver_turns_the_reference_files_into_the_reference_tables(golden_dir, 
     _compare_with_golden(out, os.path.join(golden_dir, golden))
 
 
+COND_NUM = ["BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "p.value.NA_c"]
+
+
+def _compare_cond_golden(path, golden_path):
+    """The reference's conditional table (--condition=1:13:A:C,1:79:A:C).  Tstat_c / BETA_c are differences of nearly equal
+    numbers for some rows: compared on the scale of the marginal score; the conditioning marker itself (rs79) is 0 / 0."""
+    mine = [l.split("\t") for l in open(path).read().splitlines()]
+    gold = [l.split("\t") for l in open(golden_path).read().splitlines()]
+    assert len(mine) == len(gold) == 33 and mine[0] == gold[0]
+    for a, b in zip(mine[1:], gold[1:]):
+        da, db = dict(zip(gold[0], a)), dict(zip(gold[0], b))
+        for name in gold[0]:
+            x, y = da[name], db[name]
+            if name in NUMERIC:
+                assert abs(float(x) - float(y)) <= TOL_PRINT * abs(float(y)) + 1e-300, (name, da["MarkerID"], x, y)
+            elif name in COND_NUM:
+                if da["MarkerID"] == "rs79":
+                    continue
+                scale = {"Tstat_c": abs(float(db["Tstat"])), "BETA_c": abs(float(db["Tstat"])) / float(db["var_c"])}.get(name, abs(float(y)))
+                assert abs(float(x) - float(y)) <= TOL_PRINT * scale + 1e-300, (name, da["MarkerID"], x, y)
+            else:
+                assert x == y, (name, da["MarkerID"], x, y)
+
+
+def _run_cond(device, golden_dir, out):
+    from saige_gpu_b200 import step2
+    p = os.path.join(golden_dir, "step2_100markers")
+    return step2.SPAGMMATtest(device, vcfFile=p + ".vcf.gz", vcfField="GT", GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"),
+                              varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), SAIGEOutputFile=out,
+                              chrom="1", LOCO=True, min_MAC=20, markers_per_chunk=40, return_rows=False,
+                              condition="1:13:A:C,1:79:A:C")
+
+
+def test_conditional_analysis_reproduces_the_reference_table(golden_dir, tmp_path):
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import step2
+    out = str(tmp_path / "cond.txt")
+    assert _run_cond(OracleDevice(), golden_dir, out) == 32
+    _compare_cond_golden(out, os.path.join(golden_dir, "step2_100markers_golden_cond.txt"))
+    # the same condition given through the PLINK copy finds the same markers; an unknown marker is an error
+    p = os.path.join(golden_dir, "step2_100markers")
+    a = step2._find_markers(p + ".bed", p + ".bim", 10000, "", "", "", "alt-first", ["1:13:A:C", "1:79:A:C"])
+    b = step2._find_markers("", "", 0, p + ".vcf.gz", "GT", "", "alt-first", ["1:13:A:C", "1:79:A:C"])
+    assert set(a) == set(b) == {"1:13:A:C", "1:79:A:C"} and all(np.array_equal(a[k], b[k]) for k in a)
+    with pytest.raises(ValueError):
+        step2.SPAGMMATtest(OracleDevice(), vcfFile=p + ".vcf.gz", vcfField="GT", GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"),
+                           varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), chrom="1", condition="1:13:A:T")
+    # the product's host-side factors (step2.condition_factors) against the oracle's
+    model = step2.ReadModel(os.path.join(golden_dir, "example_binary.rda"), "1", True)
+    pos = np.arange(1000)
+    rows = [a["1:13:A:C"][pos], a["1:79:A:C"][pos]]
+    f = step2.condition_factors(model, 0.94, rows)
+    M = dict(model, trait="binary", varRatio=0.94, XV=(model["X"] * model["mu2"][:, None]).T)
+    fo = S2.condition_factors(M, rows)
+    assert np.allclose(f["P2"], fo["P2"], rtol=1e-12) and np.allclose(f["VarInv"], fo["VarInv"], rtol=1e-10)
+    assert np.allclose(f["Tstat_cond"], fo["Tstat"], rtol=1e-10) and np.allclose(f["XtP2"], model["XXVX_inv"].T @ fo["P2"], rtol=1e-10)
+
+
 def test_variant_sharding_of_dosage_inputs(golden_dir, tmp_path):
     from saige_gpu_b200 import step2
     p = os.path.join(golden_dir, "step2_100markers")
@@ -260,6 +318,57 @@ def test_gpu_reference_files_reproduce_the_reference_tables(golden_dir, tmp_path
     out = str(tmp_path / "out.txt")
     assert _run_case(g, golden_dir, tmp_path, kind, kw, out) == 32
     _compare_with_golden(out, os.path.join(golden_dir, golden))
+    g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_conditional_analysis(golden_dir, tmp_path):
+    """The reference's conditional table through the kernel, then GPU vs oracle on synthetic sets: hard calls (identity and
+    indexed sample maps) and fractional dosages, with the exact test and categorical variance ratios switched on."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import SaigeB200, step2
+    from test_step2_rare_exact import rare_variant_set
+    g = SaigeB200(device=0)
+    out = str(tmp_path / "cond.txt")
+    assert _run_cond(g, golden_dir, out) == 32
+    _compare_cond_golden(out, os.path.join(golden_dir, "step2_100markers_golden_cond.txt"))
+    cols = [("Tstat", 6), ("var", 7), ("p.value", 8), ("BETA_c", 22), ("SE_c", 23), ("Tstat_c", 24), ("var_c", 25), ("p.value_c", 26),
+            ("p.value.NA_c", 27)]
+
+    def check(a, b, skip):
+        for name, c in cols:
+            ok = np.ones(len(a), bool)
+            ok[skip] = False
+            scale = np.abs(b[:, 6]) if name == "Tstat_c" else (np.abs(b[:, 6]) / b[:, 25] if name == "BETA_c" else np.abs(b[:, c]))
+            err = np.abs(a[:, c] - b[:, c]) / np.maximum(scale, 1e-300)
+            err[(a[:, c] == b[:, c]) | ~ok] = 0.0
+            assert np.nanmax(err) <= 1e-6, (name, int(np.nanargmax(err)), a[np.nanargmax(err), c], b[np.nanargmax(err), c])
+        assert np.sum(np.abs(a[ok][:, 24]) ** 2 / a[ok][:, 25] > 4) > 10          # the conditional SPA ran on some variants
+
+    for identity in (True, False):
+        M, pos, bed, nm = rare_variant_set(51 + identity, 900, 800, identity)
+        M.update(varRatio=[0.8, 1.05], cateVarRatioMinMACVecExclude=(2, 4.5), cateVarRatioMaxMACVecInclude=(4.5,))
+        model = dict(M, res=M["res"], XVX_inv_XV=M["XVX_inv_XV"])
+        cond_m = [6, 13]                                                         # markers with 7 minor alleles
+        rows = [S2.plink_marker(bed, 900, m, pos) for m in cond_m]
+        f = step2.condition_factors(model, M["varRatio"], rows, cate_lo=(2, 4.5), cate_hi=(4.5,))
+        o = OracleDevice()
+        for dev in (g, o):
+            dev.setSAIGEobjInCPP(M, M["varRatio"], 2.0, pos)
+            dev.setMaxMACforER(4.0)
+            dev.setCondition(f["P2"], f["XtP2"], f["VarInv"], f["Tstat_cond"])
+        check(g.mainMarkerInCPP(bed, 900, nm), o.mainMarkerInCPP(bed, 900, nm), cond_m)
+    M, pos, D = dosage_set(53)
+    rows = [np.where(np.isnan(D[m, pos]), -1.0, D[m, pos]) for m in (0, 6)]
+    f = step2.condition_factors(dict(M), M["varRatio"], rows)
+    o = OracleDevice()
+    for dev in (g, o):
+        dev.setSAIGEobjInCPP(M, M["varRatio"], 2.0, pos)
+        dev.setMaxMACforER(4.0)
+        dev.setCondition(f["P2"], f["XtP2"], f["VarInv"], f["Tstat_cond"])
+    check(g.mainMarkerInCPP_dosage(D), o.mainMarkerInCPP_dosage(D), [0, 6])
+    g.setCondition()
+    assert np.isnan(g.mainMarkerInCPP_dosage(D)[:, 22:28]).all()
     g.close()
 
 
