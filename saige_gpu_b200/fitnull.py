@@ -259,6 +259,10 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
     if own_geno:
         from .api import SaigeB200
         geno = SaigeB200(device=0)
+    # marker-sharded multi-GPU runs (one process per GPU, the same call on every rank): all ranks compute, rank 0 writes --
+    # the reference's `if (comm.rank(comm = 0) == 0) save(...)` (FG.R:1297-1301)
+    writer = getattr(geno, "rank", 0) == 0
+    save = save_rda if writer else (lambda *a, **k: None)
     rng = np.random.default_rng(seed)
     vr_idx = None
     if not skipVarianceRatioEstimation:
@@ -322,7 +326,7 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
             modglmm["LOCOResult"] = lres
         modglmm["offset"] = col(offset)
         modglmm["useSparseGRMtoFitNULL"] = False
-        save_rda(modelOut, {"modglmm": modglmm})
+        save(modelOut, {"modglmm": modglmm})
         if LOCO and isLowMemLOCO:
             # FG.R:1205-1290: the model without LOCO is on disk; every chromosome is refitted FROM THE MAIN FIT's alpha / eta
             # (not from the previous chromosome's) and saved to its own <prefix>_chr<j>.rda, which holds that chromosome only
@@ -347,7 +351,7 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
                 if not isCovariateOffset and hasCovariate:
                     d["offset"] = col(Xfit[:, 1:] @ a[1:])
                 slim["LOCOResult"] = state + [d] + [[None]] * (21 - j)
-                save_rda("%s_chr%d.rda" % (outputPrefix, j + 1), {"modglmm": slim})
+                save("%s_chr%d.rda" % (outputPrefix, j + 1), {"modglmm": slim})
                 state.append([None])
     else:
         modglmm = load_rda(modelOut)["modglmm"]
@@ -385,7 +389,8 @@ def fitNULLGLMM(geno=None, plinkFile="", bedFile="", bimFile="", famFile="", phe
             order = rng.permutation(n_avail)                                                   # sample(MACindex), FG.R:2233
             ratio, ratios = step1.extractVarianceRatio(geno, model, family, order[auto[order]], numMarkers=numMarkersForVarRatio,
                                                        maxiterPCG=maxiterPCG, tolPCG=tolPCG, ratioCVcutoff=ratioCVcutoff)
-        write_variance_ratio(varRatioFile, ratio)
+        if writer:
+            write_variance_ratio(varRatioFile, ratio)
         say("varRatio_null", ratio)
     if own_geno:
         geno.closeGenoFile_plink()                    # FG.R:1352; a handle passed in stays open for the caller (e.g. step 2)

@@ -266,6 +266,13 @@ def test_options_and_refusals(golden_dir, tmp_path):
     open(str(tmp_path / "x.varianceRatio.txt"), "w").write("0.9 null 1\n")
     with pytest.raises(fitnull.SaigeInputError):
         fitnull.fitNULLGLMM(OracleBackend(), **base)                                   # would overwrite the ratio file
+    # a rank other than 0 of a marker-sharded run computes but writes nothing (FG.R:1297-1301: rank 0 saves)
+    be = OracleBackend()
+    be.rank = 1
+    r1 = fitnull.fitNULLGLMM(be, **{**base, "outputPrefix": str(tmp_path / "rank1"), "LOCO": False, "probe_rng": "numpy",
+                                    "bedFile": os.path.join(golden_dir, "grm10k.bed"), "bimFile": os.path.join(golden_dir, "grm10k.bim"),
+                                    "famFile": os.path.join(golden_dir, "grm10k.fam"), "plinkFile": ""})
+    assert r1["varianceRatio"] > 0 and not os.path.exists(str(tmp_path / "rank1.rda")) and not os.path.exists(str(tmp_path / "rank1.varianceRatio.txt"))
     # quantitative trait with inverse normalisation, covariates as offset, a sample include file, no LOCO
     inc = str(tmp_path / "inc.txt")
     ids = [l.split()[4] for l in open(os.path.join(golden_dir, "pheno_1000samples.txt"))][1:]
