@@ -138,13 +138,15 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                  firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
                  cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True, vcfFile="", vcfField="DS", bgenFile="", sampleFile="",
                  AlleleOrder="alt-first", impute_method="best_guess", dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0,
-                 condition=""):
+                 condition="", is_overwrite_output=True):
     """Returns the result table (list of dict rows; with return_rows=False only the number of tested variants, for scans
     whose table should not be held in memory); writes it tab-separated to SAIGEOutputFile when given, chunk by chunk.
     Genotypes: PLINK (bedFile / bimFile / famFile; raw 2-bit rows go to the device), or vcfFile (+ vcfField "DS" / "GT"), or
     bgenFile (+ sampleFile when the file holds no sample identifiers): rows of dosages go to the device (genoio.py).
     AlleleOrder applies to PLINK and BGEN as in the reference ("alt-first": the first allele is the tested one).
     condition = "chr:pos:ref:alt,..." (at most 4 markers of the same genotype file): conditional analysis, six more columns.
+    is_overwrite_output=False: restart from `<SAIGEOutputFile>.index`, the reference's record of finished chunks
+    (R/Util.R:441-595), appending to the existing table; a finished analysis is left alone.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the variants
     and writes its own part; there is no collective, the parts are concatenated in rank order."""
     if impute_method not in IMPUTE_METHODS:
@@ -190,10 +192,10 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     if bedFile:
         # raw 2-bit rows are tested as they are (best-guess imputation is an integer); the other two imputation methods give
         # fractional genotypes, so those rows are decoded here and go through the dosage entry
-        source = _plink_chunks(geno, bedFile, bimFile, len(ids), AlleleOrder, rank, world, markers_per_chunk,
-                               (min_MAF, min_MAC, max_missing, se_two_sided),
-                               None if impute_method == "best_guess" else (IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
-                                                                           dosage_zerod_MAC_cutoff))
+        source = lambda skip: _plink_chunks(geno, bedFile, bimFile, len(ids), AlleleOrder, rank, world, markers_per_chunk,
+                                            (min_MAF, min_MAC, max_missing, se_two_sided),
+                                            None if impute_method == "best_guess" else (IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
+                                                                                        dosage_zerod_MAC_cutoff), skip)
     else:
         if vcfFile:
             n_var = sum(1 for l in genoio._open_text(vcfFile) if not l.startswith("#"))
@@ -201,20 +203,25 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
         else:
             n_var, it = bg.M, bg.variants(AlleleOrder, markers_per_chunk)
         per_rank = (n_var + world - 1) // world
-        source = _dosage_chunks(geno, it, min(n_var, rank * per_rank), min(n_var, (rank + 1) * per_rank),
-                                (min_MAF, min_MAC, max_missing, se_two_sided, IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
-                                 dosage_zerod_MAC_cutoff))
+        source = lambda skip: _dosage_chunks(geno, it, min(n_var, rank * per_rank), min(n_var, (rank + 1) * per_rank),
+                                             (min_MAF, min_MAC, max_missing, se_two_sided, IMPUTE_METHODS[impute_method],
+                                              dosage_zerod_cutoff, dosage_zerod_MAC_cutoff), skip)
     cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
     if condition:                                       # writeOutfile_single (Main.cpp:2437-2560): the _c columns follow Is.SPA
         k = cols.index("Is.SPA") + 1
         cols = cols[:k] + COND_COLUMNS + cols[k:]
     rows = [] if return_rows else None
-    out = open(SAIGEOutputFile, "w") if SAIGEOutputFile else None
-    n_tested = 0
+    done_chunks, index_path = 0, (SAIGEOutputFile + ".index") if SAIGEOutputFile else None
+    if SAIGEOutputFile and not is_overwrite_output and os.path.exists(SAIGEOutputFile):
+        done_chunks, finished = _read_index(SAIGEOutputFile, index_path, markers_per_chunk)
+        if finished:
+            return [] if return_rows else 0              # "The analysis has been finished!" (SAIGE_SPATest_Marker.R:68)
+    out = open(SAIGEOutputFile, "a" if done_chunks else "w") if SAIGEOutputFile else None
+    n_tested, indexed = 0, done_chunks > 0
     try:
-        if out:
+        if out and not done_chunks:
             out.write("\t".join(cols) + "\n")
-        for info, res in source:                         # info rows: (CHR, POS, MarkerID, Allele1, Allele2)
+        for i_chunk, (info, res) in enumerate(source(done_chunks), start=done_chunks + 1):      # info rows: (CHR, POS, MarkerID, Allele1, Allele2)
             keep = np.nonzero(res[:, 0] == 1.0)[0]      # the others were filtered: not written (Main.cpp:296 `continue`)
             n_tested += len(keep)
             if out and len(keep):
@@ -231,6 +238,16 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                         for name, v in zip(COND_COLUMNS, r[22:28]):
                             row[name] = v
                     rows.append(row)
+            if out:
+                out.flush()
+                _write_index(index_path, markers_per_chunk, i_chunk, start=(i_chunk == 1))
+                indexed = True
+        if out:
+            if not indexed:                              # an empty slice of variants: header only
+                with open(index_path, "w") as f:
+                    f.write(_INDEX_MSG[0] + "\n" + _INDEX_MSG[1] + "\n" + (_INDEX_MSG[2] % markers_per_chunk) + "\n")
+            with open(index_path, "a") as f:
+                f.write(_INDEX_MSG[4] + "\n")
     finally:
         if out:
             out.close()
@@ -265,7 +282,37 @@ def _find_markers(bedFile, bimFile, n_fam, vcfFile, vcfField, bgenFile, AlleleOr
     return found
 
 
-def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args, as_dosage=None):
+_INDEX_MSG = ["This is the output index file for SAIGE package to record the end point in case users want to restart the analysis. "
+              "Please do not modify this file.", "This is a Marker level analysis.", "nEachChunk = %d",
+              "Have completed the analysis of chunk %d", "Have completed the analyses of all chunks."]
+
+
+def _read_index(out_path, index_path, n_each):
+    """checkOutputFile (R/Util.R:441-520): (number of finished chunks, analysis finished?)."""
+    if not os.path.exists(index_path):
+        raise ValueError("'OutputFile' of '%s' has existed. Please use another 'OutputFile' or specify is_overwrite_output=TRUE "
+                         "to overwrite the OutputFile." % out_path)
+    lines = [l.rstrip("\n") for l in open(index_path) if l.strip()]
+    if len(lines) < 3 or lines[0] != _INDEX_MSG[0] or lines[1] != _INDEX_MSG[1] or lines[2] != _INDEX_MSG[2] % n_each:
+        raise ValueError("'OutputFileIndex' of '%s' is not as expected. Probably, it has been modified by user, which is not "
+                         "permitted. Please remove the existing files of 'OutputFile' and 'OutputFileIndex' or specify "
+                         "is_overwrite_output=TRUE to overwrite the OutputFile." % index_path)
+    finished = lines[-1] == _INDEX_MSG[4]
+    last = lines[-2] if finished else lines[-1]
+    prefix = _INDEX_MSG[3][:-2]
+    done = int(last[len(prefix):]) if last.startswith(prefix) else 0
+    return done, finished
+
+
+def _write_index(index_path, n_each, i_chunk, start):
+    """writeOutputFileIndex (R/Util.R:570-595)."""
+    with open(index_path, "w" if start else "a") as f:
+        if start:
+            f.write(_INDEX_MSG[0] + "\n" + _INDEX_MSG[1] + "\n" + (_INDEX_MSG[2] % n_each) + "\n")
+        f.write((_INDEX_MSG[3] % i_chunk) + "\n")
+
+
+def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args, as_dosage=None, skip=0):
     with open(bedFile, "rb") as f:
         magic = f.read(3)
     if magic != b"\x6c\x1b\x01":
@@ -279,6 +326,7 @@ def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, marke
         raise ValueError("%s holds fewer than %d markers x %d bytes" % (bedFile, n_bim, B0))
     per_rank = (n_bim + world - 1) // world
     lo, hi = min(n_bim, rank * per_rank), min(n_bim, (rank + 1) * per_rank)
+    lo = min(hi, lo + skip * markers_per_chunk)          # restart: the first `skip` chunks are already in the output file
     bim_iter = _bim_lines(bimFile, lo, hi)
     for m0 in range(lo, hi, markers_per_chunk):
         m1 = min(hi, m0 + markers_per_chunk)
@@ -299,13 +347,15 @@ def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, marke
             yield info, geno.mainMarkerInCPP_dosage(D, *args, *as_dosage)
 
 
-def _dosage_chunks(geno, it, lo, hi, args):
-    seen = 0
+def _dosage_chunks(geno, it, lo, hi, args, skip=0):
+    seen = n_yield = 0
     for info, D in it:
         a, b = max(lo - seen, 0), min(hi - seen, len(info))
         seen += len(info)
         if a < b:
-            yield info[a:b], geno.mainMarkerInCPP_dosage(D[a:b], *args)
+            n_yield += 1
+            if n_yield > skip:                           # restart: chunks already in the output file are read past, not tested
+                yield info[a:b], geno.mainMarkerInCPP_dosage(D[a:b], *args)
         if seen >= hi:
             break
 

@@ -99,6 +99,49 @@ def test_driver_writes_the_reference_table_as_a_file(golden_dir, tmp_path):
                 assert abs(float(x) - float(y)) <= TOL_PRINT * abs(float(y)) + 1e-300, (name, a[2], x, y)
 
 
+def test_restart_from_the_index_file(golden_dir, tmp_path):
+    """is_overwrite_output = FALSE (R/Util.R:441-595): the .index file records finished chunks; an interrupted scan is resumed
+    after the last recorded chunk and ends with the table an uninterrupted scan writes; a finished scan is left alone."""
+    from saige_gpu_b200 import step2
+    from conftest import OracleDevice
+    p = os.path.join(golden_dir, "step2_100markers")
+    common = dict(bedFile=p + ".bed", bimFile=p + ".bim", famFile=p + ".fam", GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"),
+                  varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), chrom="1", LOCO=True, min_MAC=20,
+                  markers_per_chunk=16, return_rows=False)
+    whole = str(tmp_path / "whole.txt")
+    assert step2.SPAGMMATtest(OracleDevice(), SAIGEOutputFile=whole, **common) == 32
+    idx = open(whole + ".index").read().splitlines()
+    ref_idx = open(os.path.join(golden_dir, "..", "golden", "step2_100markers_golden.txt")).readline()      # (fixture present)
+    assert idx[0].startswith("This is the output index file for SAIGE package") and idx[1] == "This is a Marker level analysis."
+    assert idx[2] == "nEachChunk = 16" and idx[3:] == ["Have completed the analysis of chunk %d" % i for i in range(1, 8)] + [
+        "Have completed the analyses of all chunks."] and ref_idx
+
+    class Dies(OracleDevice):
+        calls = 0
+
+        def mainMarkerInCPP(self, *a, **k):
+            Dies.calls += 1
+            if Dies.calls == 4:
+                raise RuntimeError("power cut")
+            return super().mainMarkerInCPP(*a, **k)
+
+    part = str(tmp_path / "part.txt")
+    with pytest.raises(RuntimeError):
+        step2.SPAGMMATtest(Dies(), SAIGEOutputFile=part, **common)
+    assert open(part + ".index").read().splitlines()[-1] == "Have completed the analysis of chunk 3"
+    n_before = len(open(part).read().splitlines())
+    n_more = step2.SPAGMMATtest(OracleDevice(), SAIGEOutputFile=part, is_overwrite_output=False, **common)
+    assert n_before - 1 + n_more == 32 and open(part).read() == open(whole).read()
+    assert open(part + ".index").read() == open(whole + ".index").read()
+    assert step2.SPAGMMATtest(OracleDevice(), SAIGEOutputFile=part, is_overwrite_output=False, **common) == 0       # finished: untouched
+    assert open(part).read() == open(whole).read()
+    with pytest.raises(ValueError):
+        step2.SPAGMMATtest(OracleDevice(), SAIGEOutputFile=part, is_overwrite_output=False, **{**common, "markers_per_chunk": 10})
+    os.remove(part + ".index")
+    with pytest.raises(ValueError):
+        step2.SPAGMMATtest(OracleDevice(), SAIGEOutputFile=part, is_overwrite_output=False, **common)
+
+
 @pytest.mark.gpu
 def test_gpu_step2_reproduces_reference_golden_table(golden_dir, tmp_path):
     from saige_gpu_b200 import SaigeB200, step2
