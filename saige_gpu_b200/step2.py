@@ -138,13 +138,16 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                  firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
                  cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True, vcfFile="", vcfField="DS", bgenFile="", sampleFile="",
                  AlleleOrder="alt-first", impute_method="best_guess", dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0,
-                 condition="", is_overwrite_output=True):
+                 condition="", is_overwrite_output=True, idstoIncludeFile="", rangestoIncludeFile="", restrict_to_chrom=False):
     """Returns the result table (list of dict rows; with return_rows=False only the number of tested variants, for scans
     whose table should not be held in memory); writes it tab-separated to SAIGEOutputFile when given, chunk by chunk.
     Genotypes: PLINK (bedFile / bimFile / famFile; raw 2-bit rows go to the device), or vcfFile (+ vcfField "DS" / "GT"), or
     bgenFile (+ sampleFile when the file holds no sample identifiers): rows of dosages go to the device (genoio.py).
     AlleleOrder applies to PLINK and BGEN as in the reference ("alt-first": the first allele is the tested one).
     condition = "chr:pos:ref:alt,..." (at most 4 markers of the same genotype file): conditional analysis, six more columns.
+    idstoIncludeFile (one marker ID or chr:pos:ref:alt per line) / rangestoIncludeFile (chromosome, start, end per line):
+    only these variants are tested (R/Geno.R:282-335); restrict_to_chrom=True also drops variants of other chromosomes than
+    `chrom`, as the reference's PLINK branch does (Geno.R:178-180).
     is_overwrite_output=False: restart from `<SAIGEOutputFile>.index`, the reference's record of finished chunks
     (R/Util.R:441-595), appending to the existing table; a finished analysis is left alone.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the variants
@@ -189,19 +192,22 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
         geno.setCondition(f["P2"], f["XtP2"], f["VarInv"], f["Tstat_cond"])
     else:
         geno.setCondition()
+    keep_marker = _marker_filter(idstoIncludeFile, rangestoIncludeFile, str(chrom) if restrict_to_chrom else "")
     if bedFile:
         # raw 2-bit rows are tested as they are (best-guess imputation is an integer); the other two imputation methods give
         # fractional genotypes, so those rows are decoded here and go through the dosage entry
         source = lambda skip: _plink_chunks(geno, bedFile, bimFile, len(ids), AlleleOrder, rank, world, markers_per_chunk,
                                             (min_MAF, min_MAC, max_missing, se_two_sided),
                                             None if impute_method == "best_guess" else (IMPUTE_METHODS[impute_method], dosage_zerod_cutoff,
-                                                                                        dosage_zerod_MAC_cutoff), skip)
+                                                                                        dosage_zerod_MAC_cutoff), skip, keep_marker)
     else:
         if vcfFile:
             n_var = sum(1 for l in genoio._open_text(vcfFile) if not l.startswith("#"))
             it = genoio.iter_vcf(vcfFile, vcfField, markers_per_chunk)
         else:
             n_var, it = bg.M, bg.variants(AlleleOrder, markers_per_chunk)
+        if keep_marker is not None:
+            it = _filtered(it, keep_marker)              # (ranks then share the file's variants, not the selected ones)
         per_rank = (n_var + world - 1) // world
         source = lambda skip: _dosage_chunks(geno, it, min(n_var, rank * per_rank), min(n_var, (rank + 1) * per_rank),
                                              (min_MAF, min_MAC, max_missing, se_two_sided, IMPUTE_METHODS[impute_method],
@@ -312,7 +318,43 @@ def _write_index(index_path, n_each, i_chunk, start):
         f.write((_INDEX_MSG[3] % i_chunk) + "\n")
 
 
-def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args, as_dosage=None, skip=0):
+def _marker_filter(idstoIncludeFile, rangestoIncludeFile, chrom):
+    """None when every variant is tested, else keep(CHR, POS, ID, REF, ALT) (R/Geno.R:282-335; ID or chr:pos:ref:alt)."""
+    ids = ranges = None
+    if idstoIncludeFile:
+        ids = {l.split()[0] for l in open(idstoIncludeFile) if l.strip()}
+    if rangestoIncludeFile:
+        ranges = []
+        for l in open(rangestoIncludeFile):
+            t = l.split()
+            if t:
+                if len(t) != 3:
+                    raise ValueError("rangestoIncludeFile should only include three columns.")
+                ranges.append((t[0], float(t[1]), float(t[2])))
+    if ids is None and ranges is None and not chrom:
+        return None
+
+    def keep(c, pos, mid, ref, alt):
+        if chrom and str(c) != chrom:
+            return False
+        if ids is None and ranges is None:
+            return True
+        if ids is not None and (mid in ids or "%s:%s:%s:%s" % (c, pos, ref, alt) in ids):
+            return True
+        return ranges is not None and any(str(c) == rc and lo <= float(pos) <= hi for rc, lo, hi in ranges)
+    return keep
+
+
+def _filtered(it, keep):
+    for info, D in it:
+        sel = [j for j, x in enumerate(info) if keep(*x)]
+        if sel:
+            yield [info[j] for j in sel], D[sel]
+        else:
+            yield [], D[:0]
+
+
+def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, markers_per_chunk, args, as_dosage=None, skip=0, keep=None):
     with open(bedFile, "rb") as f:
         magic = f.read(3)
     if magic != b"\x6c\x1b\x01":
@@ -324,14 +366,31 @@ def _plink_chunks(geno, bedFile, bimFile, n_fam, AlleleOrder, rank, world, marke
     body = np.memmap(bedFile, dtype=np.uint8, mode="r", offset=3)
     if body.size < n_bim * B0:
         raise ValueError("%s holds fewer than %d markers x %d bytes" % (bedFile, n_bim, B0))
-    per_rank = (n_bim + world - 1) // world
-    lo, hi = min(n_bim, rank * per_rank), min(n_bim, (rank + 1) * per_rank)
+    sel = None
+    if keep is not None:                                # selected variants: their rows are gathered chunk by chunk
+        sel, sel_bim = [], []
+        with open(bimFile) as f:
+            for m, l in enumerate(f):
+                b = l.split()
+                ref, alt = (b[5], b[4]) if AlleleOrder == "alt-first" else (b[4], b[5])
+                if keep(b[0], b[3], b[1], ref, alt):
+                    sel.append(m)
+                    sel_bim.append(b)
+        n_items = len(sel)
+    else:
+        n_items = n_bim
+    per_rank = (n_items + world - 1) // world
+    lo, hi = min(n_items, rank * per_rank), min(n_items, (rank + 1) * per_rank)
     lo = min(hi, lo + skip * markers_per_chunk)          # restart: the first `skip` chunks are already in the output file
-    bim_iter = _bim_lines(bimFile, lo, hi)
+    bim_iter = _bim_lines(bimFile, lo, hi) if sel is None else None
     for m0 in range(lo, hi, markers_per_chunk):
         m1 = min(hi, m0 + markers_per_chunk)
-        bim = [next(bim_iter) for _ in range(m1 - m0)]
-        raw = body[m0 * B0:m1 * B0]
+        if sel is None:
+            bim = [next(bim_iter) for _ in range(m1 - m0)]
+            raw = body[m0 * B0:m1 * B0]
+        else:
+            bim = sel_bim[m0:m1]
+            raw = np.concatenate([body[m * B0:(m + 1) * B0] for m in sel[m0:m1]]) if m1 > m0 else body[:0]
         if AlleleOrder == "alt-first":                  # A1 of the .bim is the tested allele: Allele1 = A2, Allele2 = A1
             info = [(b[0], b[3], b[1], b[5], b[4]) for b in bim]
         else:                                           # ref-first: A2 is the tested allele; homozygote codes 00 <-> 11 exchanged

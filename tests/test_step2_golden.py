@@ -142,6 +142,32 @@ def test_restart_from_the_index_file(golden_dir, tmp_path):
         step2.SPAGMMATtest(OracleDevice(), SAIGEOutputFile=part, is_overwrite_output=False, **common)
 
 
+def test_marker_selection_files(golden_dir, tmp_path):
+    """idstoIncludeFile / rangestoIncludeFile (R/Geno.R:282-335) for PLINK rows (gathered) and dosage rows (filtered)."""
+    from saige_gpu_b200 import step2
+    from conftest import OracleDevice
+    p = os.path.join(golden_dir, "step2_100markers")
+    ids, rng_ = str(tmp_path / "ids.txt"), str(tmp_path / "ranges.txt")
+    open(ids, "w").write("rs14\n1:26:A:C\nrs_not_there\n")
+    open(rng_, "w").write("1 50 60\n2 1 1000\n")
+    base = dict(GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"), chrom="1", LOCO=True, min_MAC=20, markers_per_chunk=3,
+                varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"))
+    plink = dict(bedFile=p + ".bed", bimFile=p + ".bim", famFile=p + ".fam")
+    full = {r["MarkerID"]: r for r in step2.SPAGMMATtest(OracleDevice(), **plink, **base)}
+    want = [m for m in full if m in ("rs14", "rs26") or 50 <= int(m[2:]) <= 60]
+    for src in (plink, dict(vcfFile=p + ".vcf.gz", vcfField="GT")):
+        got = step2.SPAGMMATtest(OracleDevice(), idstoIncludeFile=ids, rangestoIncludeFile=rng_, **src, **base)
+        assert [r["MarkerID"] for r in got] == want and len(want) >= 4
+        for r in got:
+            assert r["p.value"] == full[r["MarkerID"]]["p.value"] and r["Tstat"] == full[r["MarkerID"]]["Tstat"]
+        two = [step2.SPAGMMATtest(OracleDevice(), idstoIncludeFile=ids, rangestoIncludeFile=rng_, rank=k, world=2, **src, **base) for k in (0, 1)]
+        assert [r["MarkerID"] for part in two for r in part] == want
+    assert step2.SPAGMMATtest(OracleDevice(), restrict_to_chrom=True, **plink, **{**base, "chrom": "2", "LOCO": False}) == []
+    open(rng_, "w").write("1 50\n")
+    with pytest.raises(ValueError):
+        step2.SPAGMMATtest(OracleDevice(), rangestoIncludeFile=rng_, **plink, **base)
+
+
 @pytest.mark.gpu
 def test_gpu_step2_reproduces_reference_golden_table(golden_dir, tmp_path):
     from saige_gpu_b200 import SaigeB200, step2
