@@ -314,6 +314,44 @@ def test_low_memory_loco_writes_one_model_per_chromosome(oracle_fit, golden_dir,
             step2.ReadModel("%s_chr%d.rda" % (out, j), chrom=str(j % 22 + 1), LOCO=True)
 
 
+def test_phenotype_file_variants_sex_filter_and_categorical_covariate(golden_dir, tmp_path):
+    """A gzipped comma-separated phenotype file with missing entries, a categorical covariate (qCovarCol -> treatment
+    contrasts), FemaleOnly (output prefix gets _FemaleOnly, FG.R:790-800) and a covariate that fails checkPerfectSep."""
+    from saige_gpu_b200 import fitnull
+    rows = [l.split() for l in open(os.path.join(golden_dir, "pheno_1000samples.txt"))]
+    hdr, body = rows[0], rows[1:]
+    rng = np.random.default_rng(7)
+    site = rng.choice(["north", "south", "west"], size=len(body))
+    yb = np.array([r[hdr.index("y_binary")] for r in body])
+    rare = np.where((rng.uniform(size=len(body)) < 0.01) & (yb == "0"), "1", "0")          # only controls carry it: an empty 2 x 2 cell
+    path = str(tmp_path / "pheno.csv.gz")
+    with gzip.open(path, "wt") as f:
+        f.write(",".join(hdr + ["site", "rare"]) + "\n")
+        for i, r in enumerate(body):
+            r = list(r)
+            if i % 97 == 0:
+                r[hdr.index("x1")] = "NA"                                                   # incomplete case: dropped
+            f.write(",".join(r + [site[i], rare[i]]) + "\n")
+    out = str(tmp_path / "sex")
+    r = fitnull.fitNULLGLMM(OracleBackend(), plinkFile=os.path.join(golden_dir, "grm10k"), phenoFile=path, phenoCol="y_binary",
+                            covarColList=["x1", "site", "rare"], qCovarCol=["site"], sampleIDColinphenoFile="IID", traitType="binary",
+                            outputPrefix=out, LOCO=False, sexCol="x2", FemaleCode=1, FemaleOnly=True, minCovariateCount=1,
+                            probe_rng="numpy", skipVarianceRatioEstimation=True)
+    assert r["modelFile"] == out + "_FemaleOnly.rda" and os.path.exists(r["modelFile"])
+    m = r["modglmm"]
+    x2 = {row[hdr.index("IID")]: row[hdr.index("x2")] for row in body}
+    assert all(x2[s] == "1" for s in m["sampleID"]) and 400 < len(m["sampleID"]) < 600
+    assert not any(body[i][hdr.index("IID")] in m["sampleID"] for i in range(0, len(body), 97))
+    assert m["X"].shape[1] == 4 and m["coefficients"].shape == (4, 1)          # intercept, x1, sitesouth, sitewest; `rare` dropped
+    assert m["theta"][0] == 1.0 and np.all(np.isfinite(m["coefficients"]))
+    with pytest.raises(fitnull.SaigeInputError):
+        fitnull.fitNULLGLMM(OracleBackend(), plinkFile=os.path.join(golden_dir, "grm10k"), phenoFile=path, phenoCol="y_binary",
+                            covarColList=["x1"], sampleIDColinphenoFile="IID", outputPrefix=out, FemaleOnly=True, MaleOnly=True)
+    with pytest.raises(fitnull.SaigeInputError):
+        fitnull.fitNULLGLMM(OracleBackend(), plinkFile=os.path.join(golden_dir, "grm10k"), phenoFile=path, phenoCol="y_binary",
+                            covarColList=["x1", "site"], sampleIDColinphenoFile="IID", outputPrefix=out)       # `site` is not numeric
+
+
 def test_categorical_variance_ratios(golden_dir, bim22, tmp_path):
     """isCateVarianceRatio: every marker with 10 <= MAC < 20.5 is held out of the GRM (FG.cpp:497-501), one ratio per MAC
     category is estimated and written as `<ratio> null <k>`; step 2 picks the ratio by the variant's MAC."""

@@ -63,6 +63,70 @@ def test_readers_reproduce_the_bed(golden_dir):
         genoio.hardcalls_to_bed_rows(np.array([[0.0, 0.4]]))
 
 
+def write_bgen(path, D1, bits=8, compress=True, sample_ids=None, missing=None):
+    """A BGEN v1.2 layout-2 file (unphased diploid biallelic) from first-allele dosages that are exactly representable:
+    D1[m, i] in {0, 1, 2} or, with fractions, P(AA) = 0, P(AB) = d for d <= 1 / P(AA) = d - 1, P(AB) = 2 - d for d > 1."""
+    import struct
+    import zlib
+    nm, n = D1.shape
+    scale = (1 << bits) - 1
+    flags = (1 if compress else 0) | (2 << 2) | ((1 << 31) if sample_ids else 0)
+    blocks = b""
+    if sample_ids:
+        body = b"".join(struct.pack("<H", len(x)) + x.encode() for x in sample_ids)
+        blocks = struct.pack("<II", 8 + len(body), n) + body
+    var = b""
+    for m in range(nm):
+        d = D1[m]
+        paa = np.where(d > 1, d - 1, 0.0)
+        pab = np.where(d > 1, 2 - d, d)
+        pm = np.full(n, 2, dtype=np.uint8)
+        if missing is not None:
+            pm[missing[m]] |= 0x80
+        pr = np.empty(2 * n, dtype="<u2" if bits == 16 else np.uint8)
+        pr[0::2] = np.rint(paa * scale)
+        pr[1::2] = np.rint(pab * scale)
+        if missing is not None:
+            pr[0::2][missing[m]] = 0
+            pr[1::2][missing[m]] = 0
+        data = struct.pack("<IHBB", n, 2, 2, 2) + pm.tobytes() + bytes([0, bits]) + pr.tobytes()
+        ident = ("v%d" % m).encode()
+        head = (struct.pack("<H", len(ident)) + ident) * 2 + struct.pack("<H", 1) + b"7" + struct.pack("<IH", 100 + m, 2)
+        head += struct.pack("<I", 1) + b"G" + struct.pack("<I", 1) + b"T"
+        if compress:
+            z = zlib.compress(data)
+            var += head + struct.pack("<II", len(z) + 4, len(data)) + z
+        else:
+            var += head + struct.pack("<I", len(data)) + data
+    header = struct.pack("<IIII", 20 + len(blocks), 20, nm, n) + b"bgen" + struct.pack("<I", flags)
+    open(path, "wb").write(header + blocks + var)
+
+
+@pytest.mark.parametrize("bits,compress,with_ids", [(8, True, False), (16, True, True), (16, False, True), (8, False, False)])
+def test_bgen_variants_of_the_format(tmp_path, bits, compress, with_ids):
+    """16-bit probabilities, uncompressed blocks, embedded sample identifiers, fractional dosages, missing samples."""
+    from saige_gpu_b200 import genoio
+    rng = np.random.default_rng(bits + compress)
+    n, nm = 57, 9
+    scale = (1 << bits) - 1
+    D1 = rng.integers(0, 2 * scale + 1, size=(nm, n)) / scale                 # first-allele dosages on the file's grid
+    missing = rng.uniform(size=(nm, n)) < 0.05
+    ids = ["id%d" % i for i in range(n)] if with_ids else None
+    path = str(tmp_path / "t.bgen")
+    write_bgen(path, D1, bits, compress, ids, missing)
+    bg = genoio.BgenFile(path)
+    assert (bg.M, bg.N, bg.compression, bg.samples) == (nm, n, int(compress), ids)
+    got = [d for _, d in bg.variants("alt-first", chunk=4)]
+    assert [len(d) for d in got] == [4, 4, 1]
+    A = np.vstack(got)
+    assert np.array_equal(A < 0, missing) and np.allclose(A[~missing], D1[~missing], rtol=0, atol=2e-16 * 4)
+    info, B = next(genoio.BgenFile(path).variants("ref-first", chunk=100))
+    assert np.allclose(B[~missing], 2 - D1[~missing], rtol=0, atol=1e-15) and info[0] == ("7", "100", "v0", "G", "T")
+    open(path, "r+b").write(b"\x00\x00")
+    with pytest.raises(Exception):
+        list(genoio.BgenFile(path).variants())
+
+
 def _compare_with_golden(path, golden_path):
     mine = [l.split("\t") for l in open(path).read().splitlines()]
     gold = [l.split("\t") for l in open(golden_path).read().splitlines()]
