@@ -210,6 +210,20 @@ int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t n_file_sam
                            double min_mac, double max_missing, int se_two_sided, int impute_method,
                            double dosage_zerod_cutoff, double dosage_zerod_mac_cutoff, double *out);
 
+/* ---- BGEN input for step 2 (host side) ------------------------------------------------------------------------- */
+/* BgenClass::setBgenObj / getOneMarker / Parse2 (BGEN.cpp:25-130, 360-520, 132-345): BGEN v1.2 layout 2, zlib or plain
+ * blocks, unphased diploid biallelic variants, 8- or 16-bit probabilities.  sgb_bgen_read decodes the next <= max_variants
+ * variants into dosages[n x n_samples] (row-major; copies of the tested allele: the first allele when alt_first, else the
+ * second, which is the reader's ref-first default; -1 = missing), ready for sgb_step2_test_dosages, and writes one
+ * "CHR\tPOS\tID\tREF\tALT\n" line per variant into info_buf.  Blocks are read sequentially and inflated / decoded by
+ * n_threads host threads.  Errors: sgb_last_error(NULL).  No device work: these entry points run without a GPU. */
+typedef struct sgb_bgen sgb_bgen;
+int sgb_bgen_open(const char *path, sgb_bgen **out, int64_t *n_samples, int64_t *n_variants, int *has_sample_ids);
+int sgb_bgen_sample_id(sgb_bgen *b, int64_t i, char *buf, int buflen);
+int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, int n_threads, double *dosages, char *info_buf,
+                  int64_t info_len, int64_t *n_read);
+void sgb_bgen_close(sgb_bgen *b);
+
 /* ---- dense N x N GRM (BASELINE config 4) ---------------------------------------------------- */
 /* The reference fork ships no code for this step (docs/overview.md:19-21 describe a "full GRM" option of SAIGE-GPU; the
  * GCTA-style files extdata/output/nfam_*_GRM.grm.bin give the output format).  K_ij = (1/M) sum_m z_mi z_mj with the same

@@ -155,6 +155,57 @@ class BgenFile:
         self.f.close()
 
 
+class BgenNative:
+    """The scan path: the library's host-side reader (csrc/bgen_reader.cu: sequential block reads, multi-threaded inflate +
+    decode).  Same interface as BgenFile, which stays as the independent pure-Python implementation the tests compare it with."""
+
+    def __init__(self, path, n_threads=0):
+        import ctypes as C
+        import os
+        from . import _lib
+        self._L, self._C = _lib.lib(), C
+        h, n, m, ids = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int()
+        if self._L.sgb_bgen_open(path.encode(), C.byref(h), C.byref(n), C.byref(m), C.byref(ids)):
+            raise ValueError(self._L.sgb_last_error(None).decode())
+        self._h, self.N, self.M, self.path = h, n.value, m.value, path
+        self.n_threads = n_threads or min(16, os.cpu_count() or 1)
+        self.samples = None
+        if ids.value:
+            buf = C.create_string_buffer(1 << 16)
+            self.samples = []
+            for i in range(self.N):
+                if self._L.sgb_bgen_sample_id(h, i, buf, len(buf)):
+                    raise ValueError(self._L.sgb_last_error(None).decode())
+                self.samples.append(buf.value.decode())
+
+    def variants(self, allele_order="ref-first", chunk=1000):
+        if allele_order not in ("ref-first", "alt-first"):
+            raise ValueError("AlleleOrder should be 'ref-first' or 'alt-first'")
+        C = self._C
+        info_buf = C.create_string_buffer(chunk * 1024)
+        while True:
+            D = np.empty((chunk, self.N))
+            got = C.c_int64()
+            if self._L.sgb_bgen_read(self._h, chunk, int(allele_order == "alt-first"), self.n_threads, D.ctypes.data, info_buf,
+                                     len(info_buf), C.byref(got)):
+                raise ValueError(self._L.sgb_last_error(None).decode())
+            if got.value == 0:
+                return
+            info = [tuple(l.split("\t")) for l in info_buf.value.decode().split("\n") if l]
+            yield info, D[:got.value]
+
+    def close(self):
+        if self._h:
+            self._L.sgb_bgen_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def hardcalls_to_bed_rows(D):
     """Integral dosage rows -> raw PLINK rows (2 bits per sample, A1 = the tested allele: 00 = 2 copies, 10 = 1, 11 = 0,
     01 = missing; PLINK.hpp:48-56).  Raises when a dosage is not 0 / 1 / 2 / missing: fractional dosages need the dosage entry."""

@@ -166,7 +166,7 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     elif vcfFile:
         ids = genoio.vcf_samples(vcfFile)
     else:
-        bg = genoio.BgenFile(bgenFile)
+        bg = genoio.BgenNative(bgenFile)               # the library's multi-threaded host reader
         ids = genoio.read_sample_file(sampleFile) if sampleFile else bg.samples
         if ids is None:
             raise ValueError("%s holds no sample identifiers: give sampleFile" % bgenFile)

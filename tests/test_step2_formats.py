@@ -54,6 +54,11 @@ def test_readers_reproduce_the_bed(golden_dir):
     _, Dv = next(genoio.iter_vcf(os.path.join(golden_dir, "missing_10markers.vcf.gz"), "GT"))
     _, Db = next(genoio.BgenFile(os.path.join(golden_dir, "missing_10markers.bgen")).variants("ref-first"))
     assert np.array_equal(Dv, Db) and (Dv < 0).sum() == 6
+    for f in ("step2_100markers.bgen", "missing_10markers.bgen"):          # native reader == Python reader on the reference's files
+        for order in ("ref-first", "alt-first"):
+            ia, da = next(genoio.BgenNative(os.path.join(golden_dir, f)).variants(order, chunk=1000))
+            ib, db = next(genoio.BgenFile(os.path.join(golden_dir, f)).variants(order, chunk=1000))
+            assert ia == ib and np.array_equal(da, db)
     _, Dd = next(genoio.iter_vcf(os.path.join(golden_dir, "dosage_10markers.vcf.gz"), "DS"))
     assert Dd.shape == (10, 1000) and Dd.min() == 0 and Dd.max() == 2
     # hard calls pack back into the raw PLINK rows of the .bed
@@ -122,9 +127,21 @@ def test_bgen_variants_of_the_format(tmp_path, bits, compress, with_ids):
     assert np.array_equal(A < 0, missing) and np.allclose(A[~missing], D1[~missing], rtol=0, atol=2e-16 * 4)
     info, B = next(genoio.BgenFile(path).variants("ref-first", chunk=100))
     assert np.allclose(B[~missing], 2 - D1[~missing], rtol=0, atol=1e-15) and info[0] == ("7", "100", "v0", "G", "T")
+    # the library's native reader (multi-threaded inflate / decode) against the pure-Python one: bit for bit
+    for order in ("alt-first", "ref-first"):
+        nat = genoio.BgenNative(path, n_threads=3)
+        assert (nat.M, nat.N, nat.samples) == (nm, n, ids)
+        ref_chunks = list(genoio.BgenFile(path).variants(order, chunk=4))
+        nat_chunks = list(nat.variants(order, chunk=4))
+        assert len(nat_chunks) == len(ref_chunks) == 3
+        for (ia, da), (ib, db) in zip(nat_chunks, ref_chunks):
+            assert ia == ib and np.array_equal(da, db)
+        nat.close()
     open(path, "r+b").write(b"\x00\x00")
     with pytest.raises(Exception):
         list(genoio.BgenFile(path).variants())
+    with pytest.raises(ValueError):
+        list(genoio.BgenNative(path).variants())           # a damaged offset field: refused, with a message, not read as data
 
 
 def _compare_with_golden(path, golden_path):
