@@ -41,25 +41,30 @@ def iter_vcf(path, field="DS", chunk=1000):
         for line in f:
             if line.startswith("#"):
                 continue
-            t = line.rstrip("\n").split("\t")
+            t = line.rstrip("\n").split("\t", 9)            # fixed fields + the sample part as one string
+            if len(t) < 10:
+                raise ValueError("%s: record %s has no sample columns" % (path, t[2] if len(t) > 2 else "?"))
             if "," in t[4]:
                 raise NotImplementedError("%s: multi-allelic record %s (split it into biallelic records first)" % (path, t[2]))
             fmt = t[8].split(":")
             if field not in fmt:
                 raise ValueError("%s: record %s has no %s field" % (path, t[2], field))
             k = fmt.index(field)
-            vals = t[9:] if len(fmt) == 1 else [x.split(":")[k] if x.count(":") >= k else "." for x in t[9:]]
-            if field == "GT":
-                row = np.empty(len(vals))
-                for i, v in enumerate(vals):
-                    d = gt_lut.get(v)
-                    if d is None:
-                        al = v.replace("|", "/").split("/")
-                        d = -1.0 if "." in al else float(sum(a != "0" for a in al))
-                        gt_lut[v] = d
-                    row[i] = d
-            else:
-                row = np.array([-1.0 if v in (".", "") else float(v) for v in vals])
+            row = _gt_fast(t[9]) if (field == "GT" and len(fmt) == 1) else None
+            if row is None:
+                cells = t[9].split("\t")
+                vals = cells if len(fmt) == 1 else [x.split(":")[k] if x.count(":") >= k else "." for x in cells]
+                if field == "GT":
+                    row = np.empty(len(vals))
+                    for i, v in enumerate(vals):
+                        d = gt_lut.get(v)
+                        if d is None:
+                            al = v.replace("|", "/").split("/")
+                            d = -1.0 if "." in al else float(sum(a != "0" for a in al))
+                            gt_lut[v] = d
+                        row[i] = d
+                else:
+                    row = np.array([-1.0 if v in (".", "") else float(v) for v in vals])
             info.append((t[0], t[1], t[2], t[3], t[4]))
             rows.append(row)
             if len(rows) == chunk:
@@ -67,6 +72,19 @@ def iter_vcf(path, field="DS", chunk=1000):
                 info, rows = [], []
     if rows:
         yield info, np.vstack(rows)
+
+
+def _gt_fast(body):
+    """Biallelic diploid GT-only records whose calls are all 3 characters (`0/1`, `1|1`, `./.`): the sample part of the line
+    is a regular n x 4 byte grid, decoded with numpy instead of a Python loop over samples.  None when the record is not regular."""
+    if (len(body) + 1) % 4:
+        return None
+    a = np.frombuffer((body + "\t").encode("ascii", "replace"), dtype=np.uint8).reshape(-1, 4)
+    x, y = a[:, 0], a[:, 2]
+    if not (np.all((a[:, 1] == 47) | (a[:, 1] == 124)) and np.all(a[:, 3] == 9)
+            and np.all(((x == 48) | (x == 49) | (x == 46)) & ((y == 48) | (y == 49) | (y == 46)))):
+        return None
+    return np.where((x == 46) | (y == 46), -1.0, (x == 49).astype(np.float64) + (y == 49))
 
 
 def read_sample_file(path):
