@@ -31,8 +31,9 @@ def vcf_samples(path):
     raise ValueError("%s: no #CHROM header line" % path)
 
 
-def iter_vcf(path, field="DS", chunk=1000):
-    """Yields (info, D): info = list of (CHR, POS, ID, REF, ALT), D = len(info) x n_samples doubles (negative = missing)."""
+def iter_vcf(path, field="DS", chunk=1000, only=None):
+    """Yields (info, D): info = list of (CHR, POS, ID, REF, ALT), D = len(info) x n_samples doubles (negative = missing).
+    only: a set of "chr:pos:ref:alt" keys -- other records are passed over after their first five fields."""
     if field not in ("GT", "DS"):
         raise ValueError("vcfField should be 'DS' or 'GT'")
     info, rows = [], []
@@ -41,6 +42,10 @@ def iter_vcf(path, field="DS", chunk=1000):
         for line in f:
             if line.startswith("#"):
                 continue
+            if only is not None:
+                h5 = line.split("\t", 5)
+                if len(h5) < 6 or "%s:%s:%s:%s" % (h5[0], h5[1], h5[3], h5[4]) not in only:
+                    continue
             t = line.rstrip("\n").split("\t", 9)            # fixed fields + the sample part as one string
             if len(t) < 10:
                 raise ValueError("%s: record %s has no sample columns" % (path, t[2] if len(t) > 2 else "?"))
@@ -123,8 +128,9 @@ class BgenFile:
         l, = struct.unpack("<H" if nbytes == 2 else "<I", self.f.read(nbytes))
         return self.f.read(l).decode()
 
-    def variants(self, allele_order="ref-first", chunk=1000):
-        """Yields (info, D) like iter_vcf; D = copies of the tested allele (second allele for ref-first, first for alt-first)."""
+    def variants(self, allele_order="ref-first", chunk=1000, only=None):
+        """Yields (info, D) like iter_vcf; D = copies of the tested allele (second allele for ref-first, first for alt-first).
+        only: a set of "chr:pos:ref:alt" keys -- the blocks of every other variant are skipped without being inflated."""
         if allele_order not in ("ref-first", "alt-first"):
             raise ValueError("AlleleOrder should be 'ref-first' or 'alt-first'")
         info, rows = [], []
@@ -134,6 +140,11 @@ class BgenFile:
             pos, K = struct.unpack("<IH", self.f.read(6))
             alleles = [self._str(4) for _ in range(K)]
             C, = struct.unpack("<I", self.f.read(4))
+            if only is not None and K == 2:
+                ref, alt = (alleles[1], alleles[0]) if allele_order == "alt-first" else (alleles[0], alleles[1])
+                if "%s:%d:%s:%s" % (chrom, pos, ref, alt) not in only:
+                    self.f.seek(C, 1)
+                    continue
             if self.compression:
                 D, = struct.unpack("<I", self.f.read(4))
                 blk = zlib.decompress(self.f.read(C - 4))

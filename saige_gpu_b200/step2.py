@@ -158,6 +158,9 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
         raise ValueError("AlleleOrder should be 'alt-first' or 'ref-first'")
     if sum(bool(x) for x in (bedFile, vcfFile, bgenFile)) != 1:
         raise ValueError("give exactly one of bedFile (+ bimFile, famFile), vcfFile, bgenFile")
+    if bedFile:                                        # R/Geno.R:159-164
+        bimFile = bimFile or bedFile[:-3] + "bim"
+        famFile = famFile or bedFile[:-3] + "fam"
     model = ReadModel(GMMATmodelFile, chrom, LOCO)
     ratio = Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude)
     model["cateVarRatioMinMACVecExclude"], model["cateVarRatioMaxMACVecInclude"] = cateVarRatioMinMACVecExclude, cateVarRatioMaxMACVecInclude
@@ -182,6 +185,9 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     geno.setSAIGEobjInCPP(model, ratio, SPAcutoff, pos)
     geno.setFirth(is_Firth_beta, pCutoffforFirth, model["offset"], firth_se_from_fit)
     geno.setMaxMACforER(max_MAC_for_ER)                 # exact test of rare variants (step2_SPAtests.R:126 --max_MAC_for_ER, default 4)
+    if not bedFile or impute_method != "best_guess":
+        # dosage rows cost 8 bytes per sample (2-bit rows: 1/4 byte): chunks of at most 256 MB of rows
+        markers_per_chunk = max(1, min(markers_per_chunk, (1 << 28) // (8 * len(ids))))
     if condition:
         wanted = [c.strip() for c in condition.split(",") if c.strip()]
         found = _find_markers(bedFile, bimFile, len(ids), vcfFile, vcfField, bgenFile, AlleleOrder, wanted)
@@ -277,7 +283,8 @@ def _find_markers(bedFile, bimFile, n_fam, vcfFile, vcfField, bgenFile, AlleleOr
                     d = np.array([2.0, -1.0, 1.0, 0.0])[codes]
                     found[key] = d if AlleleOrder == "alt-first" else np.where(d < 0, -1.0, 2.0 - d)
         return found
-    it = genoio.iter_vcf(vcfFile, vcfField, 256) if vcfFile else genoio.BgenFile(bgenFile).variants(AlleleOrder, 256)
+    it = (genoio.iter_vcf(vcfFile, vcfField, 256, only=wanted) if vcfFile
+          else genoio.BgenFile(bgenFile).variants(AlleleOrder, 256, only=wanted))
     for info, D in it:
         for j, (c, p_, _, ref, alt) in enumerate(info):
             key = "%s:%s:%s:%s" % (c, p_, ref, alt)

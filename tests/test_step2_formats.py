@@ -230,6 +230,9 @@ def test_conditional_analysis_reproduces_the_reference_table(golden_dir, tmp_pat
     a = step2._find_markers(p + ".bed", p + ".bim", 10000, "", "", "", "alt-first", ["1:13:A:C", "1:79:A:C"])
     b = step2._find_markers("", "", 0, p + ".vcf.gz", "GT", "", "alt-first", ["1:13:A:C", "1:79:A:C"])
     assert set(a) == set(b) == {"1:13:A:C", "1:79:A:C"} and all(np.array_equal(a[k], b[k]) for k in a)
+    c = step2._find_markers("", "", 0, "", "", p + ".bgen", "ref-first", ["1:13:A:C", "1:79:A:C"])       # other blocks are skipped, not inflated
+    assert set(c) == set(a) and all(np.array_equal(a[k], c[k]) for k in a)
+    assert step2._find_markers("", "", 0, "", "", p + ".bgen", "alt-first", ["1:13:A:C"]) == {}             # alleles the other way round
     with pytest.raises(ValueError):
         step2.SPAGMMATtest(OracleDevice(), vcfFile=p + ".vcf.gz", vcfField="GT", GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"),
                            varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"), chrom="1", condition="1:13:A:T")
