@@ -12,6 +12,7 @@ goes through the savvy library, and src/BGEN.cpp:132-345 `BgenClass::Parse2`, :3
 Both yield chunks (info rows, dosage matrix) so a scan never holds the whole file.  Only formats; no statistics here."""
 import gzip
 import struct
+import warnings
 import zlib
 
 import numpy as np
@@ -55,7 +56,9 @@ def iter_vcf(path, field="DS", chunk=1000, only=None):
             if field not in fmt:
                 raise ValueError("%s: record %s has no %s field" % (path, t[2], field))
             k = fmt.index(field)
-            row = _gt_fast(t[9]) if (field == "GT" and len(fmt) == 1) else None
+            row = None
+            if len(fmt) == 1:
+                row = _gt_fast(t[9]) if field == "GT" else _ds_fast(t[9])
             if row is None:
                 cells = t[9].split("\t")
                 vals = cells if len(fmt) == 1 else [x.split(":")[k] if x.count(":") >= k else "." for x in cells]
@@ -90,6 +93,20 @@ def _gt_fast(body):
             and np.all(((x == 48) | (x == 49) | (x == 46)) & ((y == 48) | (y == 49) | (y == 46)))):
         return None
     return np.where((x == 46) | (y == 46), -1.0, (x == 49).astype(np.float64) + (y == 49))
+
+
+def _ds_fast(body):
+    """DS-only records without missing entries: the sample part parsed by numpy's C text reader.  None otherwise (a `.`
+    entry, or anything the reader does not consume to the end, sends the record to the per-sample path)."""
+    if "\t.\t" in body or body.startswith(".\t") or body.endswith("\t.") or body == ".":
+        return None
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = np.fromstring(body, dtype=np.float64, sep="\t")
+    except ValueError:
+        return None
+    return a if a.size == body.count("\t") + 1 else None
 
 
 def read_sample_file(path):
