@@ -426,6 +426,25 @@ def _dosage_chunks(geno, it, lo, hi, args, skip=0):
             break
 
 
+def merge_rank_outputs(part_files, out_file):
+    """Concatenates the per-rank result tables of a variant-sharded scan in rank order (header once): with contiguous
+    slices per rank this is the table a single-rank scan writes.  Returns the number of result rows."""
+    n = 0
+    with open(out_file, "w") as out:
+        for k, p in enumerate(part_files):
+            with open(p) as f:
+                header = f.readline()
+                if k == 0:
+                    out.write(header)
+                elif header != first_header:
+                    raise ValueError("%s has a different header than %s" % (p, part_files[0]))
+                first_header = header
+                for line in f:
+                    out.write(line)
+                    n += 1
+    return n
+
+
 def _count_lines(path):
     n, last = 0, b"\n"
     with open(path, "rb") as f:

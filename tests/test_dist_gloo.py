@@ -149,6 +149,8 @@ def test_step2_variant_sharding_is_a_partition(tmp_path):
         assert run_file(r, 3, str(tmp_path / ("part%d.txt" % r))) == len(parts_of(full, r, 3))
         got += open(str(tmp_path / ("part%d.txt" % r))).read().splitlines()[1:]
     assert got == whole
+    n = step2.merge_rank_outputs([str(tmp_path / ("part%d.txt" % r)) for r in range(3)], str(tmp_path / "merged.txt"))
+    assert n == len(full) and open(str(tmp_path / "merged.txt")).read() == open(str(tmp_path / "all.txt")).read()
 
 
 def parts_of(full, rank, world, n=100):
