@@ -440,7 +440,8 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
         extra = dict(BETA_c=sgn * beta_c, SE_c=se_c, Tstat_c=sgn * Tc, var_c=vc, p_value_c=p_c, p_value_NA_c=p_na_c)
     y = M["y"]
     case, ctrl = y == 1, y == 0
-    afc, aft = G[case].mean() / 2, G[ctrl].mean() / 2
+    afc = G[case].mean() / 2 if case.any() else np.nan
+    aft = G[ctrl].mean() / 2 if ctrl.any() else np.nan
     if flip:
         afc, aft = 1 - afc, 1 - aft
     # is_output_moreDetails (Main.cpp:510-525): dosage ranges [1.5, 2] / [0.5, 1.5) of the flipped, imputed vector

@@ -218,10 +218,14 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
         source = lambda skip: _dosage_chunks(geno, it, min(n_var, rank * per_rank), min(n_var, (rank + 1) * per_rank),
                                              (min_MAF, min_MAC, max_missing, se_two_sided, IMPUTE_METHODS[impute_method],
                                               dosage_zerod_cutoff, dosage_zerod_MAC_cutoff), skip)
-    cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
-    if condition:                                       # writeOutfile_single (Main.cpp:2437-2560): the _c columns follow Is.SPA
+    # header of openOutfile_single (Main.cpp:2392-2425): binary traits carry p.value.NA, Is.SPA and the case / control
+    # columns, quantitative traits end with N; the _c columns of a conditional analysis follow p.value (/ Is.SPA)
+    if model["trait"] == "binary":
+        cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
         k = cols.index("Is.SPA") + 1
-        cols = cols[:k] + COND_COLUMNS + cols[k:]
+        cols = cols[:k] + (COND_COLUMNS if condition else []) + cols[k:]
+    else:
+        cols = OUT_COLUMNS[:13] + (COND_COLUMNS[:5] if condition else []) + ["N"]
     rows = [] if return_rows else None
     done_chunks, index_path = 0, (SAIGEOutputFile + ".index") if SAIGEOutputFile else None
     if SAIGEOutputFile and not is_overwrite_output and os.path.exists(SAIGEOutputFile):
@@ -479,6 +483,8 @@ def _format_chunk(res, bim, cols, table_cols):
         if c in _INFO_COLS:
             k = _INFO_COLS.index(c)
             fields.append([b[k] for b in bim])
+        elif c == "N":                                  # quantitative traits: the number of model samples (Main.cpp:526-527)
+            fields.append(np.char.mod("%.6g", res[:, idx["N_case"]] + res[:, idx["N_ctrl"]]).tolist())
         elif c == "Is.SPA":
             fields.append(np.where(res[:, idx[c]] != 0, "true", "false").tolist())
         else:

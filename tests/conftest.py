@@ -88,6 +88,8 @@ class OracleDevice:
             out[j, 1:13] = [r["AC_Allele2"], r["AF_Allele2"], r["MissingRate"], r["BETA"], r["SE"], r["Tstat"], r["var"],
                             r["p_value"], r["p_value_NA"], float(r["Is_SPA"]), r["AF_case"], r["AF_ctrl"]]
             out[j, 13:19] = [r["N_case"], r["N_ctrl"], r["N_case_hom"], r["N_case_het"], r["N_ctrl_hom"], r["N_ctrl_het"]]
+            if self.M["trait"] != "binary":               # the kernel counts y == 1 as "cases" and everybody else as "controls"
+                out[j, 13:15] = [float(np.sum(self.M["y"] == 1)), float(np.sum(self.M["y"] != 1))]
             out[j, 20:22] = [float(r["Is_Firth"]), float(r["Firth_converged"])]
             if self.cond is not None:
                 out[j, 22:28] = [r["BETA_c"], r["SE_c"], r["Tstat_c"], r["var_c"], r["p_value_c"], r["p_value_NA_c"]]

@@ -304,6 +304,55 @@ def test_plink_rows_with_mean_or_minor_imputation_go_through_the_dosage_entry(tm
     assert rows[2]["MissingRate"] > 0
 
 
+def test_quantitative_trait_table_layout(tmp_path):
+    """openOutfile_single / writeOutfile_single for a quantitative trait (Main.cpp:2392-2425, 2437-2560): no p.value.NA /
+    Is.SPA / case-control columns, N at the end; with a condition the five _c columns precede N."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import step2
+    from saige_gpu_b200.rdata import RList, save_rda
+    from test_step2_rare_exact import pack_bed
+    rng = np.random.default_rng(8)
+    n_fam, N, nm = 240, 200, 40
+    pos = rng.permutation(n_fam)[:N]
+    G = rng.binomial(2, rng.uniform(0.1, 0.5, size=(nm, 1)), size=(nm, n_fam))
+    X = np.column_stack([np.ones(N), rng.normal(size=N)])
+    y = X @ np.array([0.2, 0.5]) + rng.normal(size=N)
+    mu = X @ np.linalg.lstsq(X, y, rcond=None)[0]
+    tau = np.array([0.8, 0.3])
+    mu2 = np.full(N, 1 / tau[0])
+    XV = (X * mu2[:, None]).T
+    XVX = X.T @ XV.T
+    XVXi = np.linalg.inv(XVX)
+    ids = ["q%d" % i for i in range(n_fam)]
+    p = str(tmp_path / "q")
+    open(p + ".bed", "wb").write(b"\x6c\x1b\x01" + pack_bed(G).tobytes())
+    open(p + ".fam", "w").write("".join("f %s 0 0 0 -9\n" % i for i in ids))
+    open(p + ".bim", "w").write("".join("3\tq%d\t0\t%d\tT\tC\n" % (m, 10 * m + 5) for m in range(nm)))
+    noK = RList([("XV", XV), ("XVX", XVX), ("XXVX_inv", X @ XVXi), ("XVX_inv", XVXi), ("S_a", (X * (y - mu)[:, None]).sum(0)),
+                 ("XVX_inv_XV", (X @ XVXi) * mu2[:, None]), ("V", mu2)], r_class=["SA_NULL"])
+    save_rda(p + ".rda", {"modglmm": dict([("theta", tau), ("fitted.values", mu.reshape(-1, 1)), ("residuals", (y - mu).reshape(-1, 1)),
+                                          ("sampleID", [ids[k] for k in pos]), ("obj.noK", noK), ("y", y), ("X", X),
+                                          ("traitType", "quantitative"), ("LOCO", False)])})
+    open(p + ".varianceRatio.txt", "w").write("0.97 null 1\n")
+    out = p + ".txt"
+    n = step2.SPAGMMATtest(OracleDevice(), p + ".bed", GMMATmodelFile=p + ".rda", varianceRatioFile=p + ".varianceRatio.txt",
+                           SAIGEOutputFile=out, LOCO=False, return_rows=False)           # .bim / .fam default to the .bed prefix
+    lines = [l.split("\t") for l in open(out).read().splitlines()]
+    assert n == nm and lines[0] == ["CHR", "POS", "MarkerID", "Allele1", "Allele2", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE",
+                                    "Tstat", "var", "p.value", "N"]
+    M = dict(mu=mu, res=y - mu, mu2=mu2, tau=tau, trait="quantitative", y=y, X=X, XV=XV, XVX=XVX, XXVX_inv=X @ XVXi,
+             XVX_inv_XV=(X @ XVXi) * mu2[:, None], S_a=(X * (y - mu)[:, None]).sum(0), varRatio=0.97)
+    for m in (0, 17, 39):
+        r = S2.test_marker(M, G[m, pos].astype(float))
+        row = dict(zip(lines[0], lines[1 + m]))
+        assert row["MarkerID"] == "q%d" % m and row["Allele1"] == "C" and row["Allele2"] == "T" and row["N"] == str(N)
+        assert abs(float(row["p.value"]) - r["p_value"]) <= 2e-5 * r["p_value"] and abs(float(row["BETA"]) - r["BETA"]) <= 2e-5 * abs(r["BETA"])
+    step2.SPAGMMATtest(OracleDevice(), p + ".bed", GMMATmodelFile=p + ".rda", varianceRatioFile=p + ".varianceRatio.txt",
+                       SAIGEOutputFile=out, LOCO=False, return_rows=False, condition="3:5:C:T")
+    hdr = open(out).readline().rstrip("\n").split("\t")
+    assert hdr[12:] == ["p.value", "BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "N"]
+
+
 def dosage_set(seed, n_file=900, N=800, nm=180):
     """Binary-trait model + fractional dosages: common and rare variants, major-allele-coded ones (flip), missing entries (as
     -1 and as NaN), rare variants whose small dosages get zeroed, carriers enriched among cases for the rare ones."""
