@@ -229,6 +229,17 @@ def test_covariate_transform_does_not_change_the_model(oracle_fit, golden_dir, b
     assert r3["modglmm"]["LOCO"] is False and abs(r3["modglmm"]["theta"][1] - 0.3137) < 1e-3      # the value DESIGN.md quotes for this set
 
 
+def test_skip_model_fitting_reuses_the_written_model(oracle_fit, golden_dir, bim22):
+    """skipModelFitting = TRUE (FG.R:1303-1313): the .rda on disk is loaded and only the variance ratio is estimated again;
+    same hold-out set and marker order (same seed) -> the same ratio to the last digit."""
+    r, out = oracle_fit
+    before = open(out + ".rda", "rb").read()
+    r2 = _run(OracleBackend(), golden_dir, bim22, out, skipModelFitting=True)
+    assert open(out + ".rda", "rb").read() == before                       # the model file is not rewritten
+    assert r2["varianceRatio"] == r["varianceRatio"]
+    assert np.array_equal(r2["modglmm"]["theta"], r["modglmm"]["theta"])
+
+
 def test_step2_consumes_the_written_model(oracle_fit, golden_dir):
     """The hand-over: the oracle's step 2 reads the .rda / varianceRatio.txt this run wrote (ReadModel's fields, LOCO swap)."""
     from oracle import oracle as O
