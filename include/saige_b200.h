@@ -205,7 +205,8 @@ int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, i
  * genotype file (hard calls as 0 / 1 / 2), negative or NaN = missing; pos_in_fam of sgb_step2_set_model indexes these rows.
  * impute_method 1 best_guess / 2 mean / 3 minor, dosage_zerod_cutoff / dosage_zerod_mac_cutoff as in imputeGenoAndFlip
  * (UTIL.cpp:58-135; R defaults 0.2 and 10).  N_*_hom / N_*_het count dosages in [1.5, 2] / [0.5, 1.5) (Main.cpp:510-525).
- * Same out table as sgb_step2_test_markers.  The imputation-INFO filter of BGEN input (minInfo) is not built: INFO = 1. */
+ * Same out table as sgb_step2_test_markers.  The imputation-INFO filter of BGEN input (minInfo) is applied by the caller
+ * before this call, from the scores sgb_bgen_read returns. */
 int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t n_file_samples, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, int impute_method,
                            double dosage_zerod_cutoff, double dosage_zerod_mac_cutoff, double *out);
@@ -216,12 +217,14 @@ int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t n_file_sam
  * variants into dosages[n x n_samples] (row-major; copies of the tested allele: the first allele when alt_first, else the
  * second, which is the reader's ref-first default; -1 = missing), ready for sgb_step2_test_dosages, and writes one
  * "CHR\tPOS\tID\tREF\tALT\n" line per variant into info_buf.  Blocks are read sequentially and inflated / decoded by
- * n_threads host threads.  Errors: sgb_last_error(NULL).  No device work: these entry points run without a GPU. */
+ * n_threads host threads.  info_scores (n doubles or NULL): the imputation INFO score of each variant over the samples flagged
+ * in in_model (n_samples bytes; NULL = all) that are not missing (BGEN.cpp:275-345), for the minInfo filter of imputed data.
+ * Errors: sgb_last_error(NULL).  No device work: these entry points run without a GPU. */
 typedef struct sgb_bgen sgb_bgen;
 int sgb_bgen_open(const char *path, sgb_bgen **out, int64_t *n_samples, int64_t *n_variants, int *has_sample_ids);
 int sgb_bgen_sample_id(sgb_bgen *b, int64_t i, char *buf, int buflen);
-int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, int n_threads, double *dosages, char *info_buf,
-                  int64_t info_len, int64_t *n_read);
+int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, int n_threads, const uint8_t *in_model,
+                  double *dosages, double *info_scores, char *info_buf, int64_t info_len, int64_t *n_read);
 void sgb_bgen_close(sgb_bgen *b);
 
 /* ---- dense N x N GRM (BASELINE config 4) ---------------------------------------------------- */

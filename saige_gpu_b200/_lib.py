@@ -90,7 +90,7 @@ _SIGS = {
     "sgb_step2_test_markers": (C.c_int, [P, P, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, DP]),
     "sgb_bgen_open": (C.c_int, [C.c_char_p, C.POINTER(P), C.POINTER(I64), C.POINTER(I64), C.POINTER(C.c_int)]),
     "sgb_bgen_sample_id": (C.c_int, [P, I64, C.c_char_p, C.c_int]),
-    "sgb_bgen_read": (C.c_int, [P, I64, C.c_int, C.c_int, DP, C.c_char_p, I64, C.POINTER(I64)]),
+    "sgb_bgen_read": (C.c_int, [P, I64, C.c_int, C.c_int, P, DP, DP, C.c_char_p, I64, C.POINTER(I64)]),
     "sgb_bgen_close": (None, [P]),
     "sgb_step2_test_dosages": (C.c_int, [P, DP, I64, I64, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
                                          C.c_double, DP]),

@@ -91,7 +91,11 @@ extern "C" int sgb_bgen_sample_id(sgb_bgen *b, int64_t i, char *buf, int buflen)
 struct bgen_block { std::vector<unsigned char> z; uint32_t raw_len = 0; std::string rsid; };
 
 // one variant: inflate (when compressed) and decode into dst[n_samples]; returns an error text or nullptr
-static const char *decode_block(const sgb_bgen *b, bgen_block &blk, int alt_first, double *dst, std::vector<unsigned char> &scratch)
+// in_model / info: when info is given, the imputation INFO score over the flagged, non-missing samples (all samples when
+// in_model is NULL): theta = sum e / 2n, INFO = 1 - sum(f - e^2) / (2 n theta (1 - theta)) with e = 2 P(AA) + P(AB),
+// f = 4 P(AA) + P(AB); 1 when theta is 0 or 1 (BGEN.cpp:275-345)
+static const char *decode_block(const sgb_bgen *b, bgen_block &blk, int alt_first, double *dst, std::vector<unsigned char> &scratch,
+                                const uint8_t *in_model, double *info)
 {
     const unsigned char *p = blk.z.data();
     size_t len = blk.z.size();
@@ -113,6 +117,7 @@ static const char *decode_block(const sgb_bgen *b, bgen_block &blk, int alt_firs
     if (bits != 8 && bits != 16) return "probabilities are neither 8 nor 16 bits";
     if (len < 10 + N + 2 * N * (size_t)(bits / 8)) return "probability block too short";
     const double scale = bits == 8 ? 255.0 : 65535.0;
+    double sum_e = 0.0, sum_f = 0.0, cnt = 0.0;
     for (size_t i = 0; i < N; i++) {
         if (pm[i] & 0x80) { dst[i] = -1.0; continue; }
         if ((pm[i] & 63) != 2) return "not diploid";
@@ -121,12 +126,17 @@ static const char *decode_block(const sgb_bgen *b, bgen_block &blk, int alt_firs
         else { uint16_t a, c; memcpy(&a, pr + 4 * i, 2); memcpy(&c, pr + 4 * i + 2, 2); paa = a / scale; pab = c / scale; }
         const double first = 2.0 * paa + pab;
         dst[i] = alt_first ? first : 2.0 - first;
+        if (info && (!in_model || in_model[i])) { sum_e += first; sum_f += (4.0 * paa + pab) - first * first; cnt += 1.0; }
+    }
+    if (info) {
+        const double theta = cnt > 0 ? sum_e / (2.0 * cnt) : 0.0;
+        *info = (theta == 0.0 || theta == 1.0) ? 1.0 : 1.0 - sum_f / (2.0 * cnt * theta * (1.0 - theta));
     }
     return nullptr;
 }
 
-extern "C" int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, int n_threads, double *dosages, char *info_buf,
-                             int64_t info_len, int64_t *n_read)
+extern "C" int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, int n_threads, const uint8_t *in_model,
+                             double *dosages, double *info_scores, char *info_buf, int64_t info_len, int64_t *n_read)
 {
     *n_read = 0;
     if (!b || !b->f) return sgb_fail(nullptr, "bgen: not open");
@@ -161,7 +171,8 @@ extern "C" int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, i
         for (;;) {
             const int64_t v = next.fetch_add(1);
             if (v >= want) break;
-            const char *e = decode_block(b, blocks[(size_t)v], alt_first, dosages + (size_t)v * (size_t)b->n_samples, scratch);
+            const char *e = decode_block(b, blocks[(size_t)v], alt_first, dosages + (size_t)v * (size_t)b->n_samples, scratch,
+                                         in_model, info_scores ? info_scores + v : nullptr);
             if (e) { errs[(size_t)t] = std::string(e) + " (variant " + blocks[(size_t)v].rsid + ")"; break; }
         }
     };

@@ -145,9 +145,11 @@ class BgenFile:
         l, = struct.unpack("<H" if nbytes == 2 else "<I", self.f.read(nbytes))
         return self.f.read(l).decode()
 
-    def variants(self, allele_order="ref-first", chunk=1000, only=None):
+    def variants(self, allele_order="ref-first", chunk=1000, only=None, info_for=None):
         """Yields (info, D) like iter_vcf; D = copies of the tested allele (second allele for ref-first, first for alt-first).
-        only: a set of "chr:pos:ref:alt" keys -- the blocks of every other variant are skipped without being inflated."""
+        only: a set of "chr:pos:ref:alt" keys -- the blocks of every other variant are skipped without being inflated.
+        info_for: boolean mask of samples; the imputation INFO scores (BGEN.cpp:275-345) of a chunk are then in self.last_info."""
+        scores = []
         if allele_order not in ("ref-first", "alt-first"):
             raise ValueError("AlleleOrder should be 'ref-first' or 'alt-first'")
         info, rows = [], []
@@ -186,15 +188,23 @@ class BgenFile:
             else:
                 raise NotImplementedError("%s: %d-bit probabilities (8 and 16 are read; the reference reads 8 only)" % (self.path, bits))
             first = 2.0 * p[0::2] + p[1::2]                 # copies of the first allele (BGEN.cpp:218-223)
+            if info_for is not None:
+                use = np.asarray(info_for, dtype=bool) & ~missing
+                cnt = float(use.sum())
+                theta = first[use].sum() / (2 * cnt) if cnt else 0.0
+                ff = (4.0 * p[0::2] + p[1::2])[use] - first[use] ** 2
+                scores.append(1.0 if theta in (0.0, 1.0) else 1.0 - ff.sum() / (2 * cnt * theta * (1 - theta)))
             d = first if allele_order == "alt-first" else 2.0 - first
             d = np.where(missing, -1.0, d)
             ref, alt = (alleles[1], alleles[0]) if allele_order == "alt-first" else (alleles[0], alleles[1])
             info.append((chrom, str(pos), rsid, ref, alt))
             rows.append(d)
             if len(rows) == chunk:
+                self.last_info = np.array(scores)
                 yield info, np.vstack(rows)
-                info, rows = [], []
+                info, rows, scores = [], [], []
         if rows:
+            self.last_info = np.array(scores)
             yield info, np.vstack(rows)
 
     def close(self):
@@ -224,20 +234,25 @@ class BgenNative:
                     raise ValueError(self._L.sgb_last_error(None).decode())
                 self.samples.append(buf.value.decode())
 
-    def variants(self, allele_order="ref-first", chunk=1000):
+    def variants(self, allele_order="ref-first", chunk=1000, info_for=None):
+        """info_for: boolean mask of samples; the INFO scores of the chunk just yielded are then in self.last_info."""
         if allele_order not in ("ref-first", "alt-first"):
             raise ValueError("AlleleOrder should be 'ref-first' or 'alt-first'")
         C = self._C
         info_buf = C.create_string_buffer(chunk * 1024)
+        mask = None if info_for is None else np.ascontiguousarray(info_for, dtype=np.uint8)
         while True:
             D = np.empty((chunk, self.N))
+            scores = np.empty(chunk) if mask is not None else None
             got = C.c_int64()
-            if self._L.sgb_bgen_read(self._h, chunk, int(allele_order == "alt-first"), self.n_threads, D.ctypes.data, info_buf,
-                                     len(info_buf), C.byref(got)):
+            if self._L.sgb_bgen_read(self._h, chunk, int(allele_order == "alt-first"), self.n_threads,
+                                     None if mask is None else mask.ctypes.data, D.ctypes.data,
+                                     None if scores is None else scores.ctypes.data, info_buf, len(info_buf), C.byref(got)):
                 raise ValueError(self._L.sgb_last_error(None).decode())
             if got.value == 0:
                 return
             info = [tuple(l.split("\t")) for l in info_buf.value.decode().split("\n") if l]
+            self.last_info = None if scores is None else scores[:got.value]
             yield info, D[:got.value]
 
     def close(self):

@@ -138,7 +138,8 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                  firth_se_from_fit=True, max_MAC_for_ER=4.0, cateVarRatioMinMACVecExclude=(10, 20.5),
                  cateVarRatioMaxMACVecInclude=(20.5,), return_rows=True, vcfFile="", vcfField="DS", bgenFile="", sampleFile="",
                  AlleleOrder="alt-first", impute_method="best_guess", dosage_zerod_cutoff=0.2, dosage_zerod_MAC_cutoff=10.0,
-                 condition="", is_overwrite_output=True, idstoIncludeFile="", rangestoIncludeFile="", restrict_to_chrom=False):
+                 condition="", is_overwrite_output=True, idstoIncludeFile="", rangestoIncludeFile="", restrict_to_chrom=False,
+                 is_imputed_data=False, minInfo=0.0):
     """Returns the result table (list of dict rows; with return_rows=False only the number of tested variants, for scans
     whose table should not be held in memory); writes it tab-separated to SAIGEOutputFile when given, chunk by chunk.
     Genotypes: PLINK (bedFile / bimFile / famFile; raw 2-bit rows go to the device), or vcfFile (+ vcfField "DS" / "GT"), or
@@ -148,6 +149,9 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     idstoIncludeFile (one marker ID or chr:pos:ref:alt per line) / rangestoIncludeFile (chromosome, start, end per line):
     only these variants are tested (R/Geno.R:282-335); restrict_to_chrom=True also drops variants of other chromosomes than
     `chrom`, as the reference's PLINK branch does (Geno.R:178-180).
+    is_imputed_data=True: the table holds `imputationInfo` in place of `MissingRate` and variants whose INFO score (BGEN:
+    computed from the probabilities over the model's samples, BGEN.cpp:275-345; 1 for PLINK / VCF) is below minInfo are
+    not tested (Main.cpp:351).
     is_overwrite_output=False: restart from `<SAIGEOutputFile>.index`, the reference's record of finished chunks
     (R/Util.R:441-595), appending to the existing table; a finished analysis is left alone.
     Multi-GPU (BASELINE config 5): variants are sharded, rank r of `world` tests the r-th contiguous slice of the variants
@@ -211,7 +215,13 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
             n_var = sum(1 for l in genoio._open_text(vcfFile) if not l.startswith("#"))
             it = genoio.iter_vcf(vcfFile, vcfField, markers_per_chunk)
         else:
-            n_var, it = bg.M, bg.variants(AlleleOrder, markers_per_chunk)
+            n_var = bg.M
+            if is_imputed_data:
+                in_model = np.zeros(bg.N, dtype=bool)
+                in_model[pos] = True
+                it = _with_info_scores(bg, bg.variants(AlleleOrder, markers_per_chunk, info_for=in_model), minInfo)
+            else:
+                it = bg.variants(AlleleOrder, markers_per_chunk)
         if keep_marker is not None:
             it = _filtered(it, keep_marker)              # (ranks then share the file's variants, not the selected ones)
         per_rank = (n_var + world - 1) // world
@@ -221,11 +231,13 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
     # header of openOutfile_single (Main.cpp:2392-2425): binary traits carry p.value.NA, Is.SPA and the case / control
     # columns, quantitative traits end with N; the _c columns of a conditional analysis follow p.value (/ Is.SPA)
     if model["trait"] == "binary":
-        cols = OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19]
+        cols = list(OUT_COLUMNS if is_output_moreDetails else OUT_COLUMNS[:19])
         k = cols.index("Is.SPA") + 1
         cols = cols[:k] + (COND_COLUMNS if condition else []) + cols[k:]
     else:
         cols = OUT_COLUMNS[:13] + (COND_COLUMNS[:5] if condition else []) + ["N"]
+    if is_imputed_data:                                 # t_isImputation (Main.cpp:2395-2400)
+        cols[cols.index("MissingRate")] = "imputationInfo"
     rows = [] if return_rows else None
     done_chunks, index_path = 0, (SAIGEOutputFile + ".index") if SAIGEOutputFile else None
     if SAIGEOutputFile and not is_overwrite_output and os.path.exists(SAIGEOutputFile):
@@ -250,6 +262,8 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                         row[name] = v
                     row["Is.SPA"] = bool(r[10])
                     row["Is.Firth"], row["Firth.converged"] = bool(r[20]), bool(r[21])
+                    if is_imputed_data:
+                        row["imputationInfo"] = float(b[5]) if len(b) > 5 else 1.0
                     if condition:
                         for name, v in zip(COND_COLUMNS, r[22:28]):
                             row[name] = v
@@ -356,9 +370,17 @@ def _marker_filter(idstoIncludeFile, rangestoIncludeFile, chrom):
     return keep
 
 
+def _with_info_scores(bg, it, min_info):
+    """Appends the INFO score of every variant to its info row and drops the variants below min_info (Main.cpp:351)."""
+    for info, D in it:
+        sc = bg.last_info
+        sel = [j for j in range(len(info)) if not sc[j] < min_info]
+        yield [tuple(info[j]) + (float(sc[j]),) for j in sel], (D if len(sel) == len(info) else D[sel])
+
+
 def _filtered(it, keep):
     for info, D in it:
-        sel = [j for j, x in enumerate(info) if keep(*x)]
+        sel = [j for j, x in enumerate(info) if keep(*x[:5])]
         if sel:
             yield [info[j] for j in sel], D[sel]
         else:
@@ -483,6 +505,8 @@ def _format_chunk(res, bim, cols, table_cols):
         if c in _INFO_COLS:
             k = _INFO_COLS.index(c)
             fields.append([b[k] for b in bim])
+        elif c == "imputationInfo":
+            fields.append([("%.6g" % b[5]) if len(b) > 5 else "1" for b in bim])
         elif c == "N":                                  # quantitative traits: the number of model samples (Main.cpp:526-527)
             fields.append(np.char.mod("%.6g", res[:, idx["N_case"]] + res[:, idx["N_ctrl"]]).tolist())
         elif c == "Is.SPA":

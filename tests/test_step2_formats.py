@@ -127,6 +127,19 @@ def test_bgen_variants_of_the_format(tmp_path, bits, compress, with_ids):
     assert np.array_equal(A < 0, missing) and np.allclose(A[~missing], D1[~missing], rtol=0, atol=2e-16 * 4)
     info, B = next(genoio.BgenFile(path).variants("ref-first", chunk=100))
     assert np.allclose(B[~missing], 2 - D1[~missing], rtol=0, atol=1e-15) and info[0] == ("7", "100", "v0", "G", "T")
+    # imputation INFO score over a subset of samples (BGEN.cpp:275-345), checked against the formula written out
+    mask = rng.uniform(size=n) < 0.7
+    bgp, bgn = genoio.BgenFile(path), genoio.BgenNative(path, n_threads=2)
+    for (_, _), (_, _) in zip(bgp.variants("ref-first", chunk=nm, info_for=mask), bgn.variants("ref-first", chunk=nm, info_for=mask)):
+        assert np.allclose(bgp.last_info, bgn.last_info, rtol=1e-12, atol=1e-14) and bgp.last_info.shape == (nm,)
+        for m in range(nm):
+            use = mask & ~missing[m]
+            e = D1[m, use]
+            paa = np.where(e > 1, e - 1, 0.0)
+            f = 4 * paa + np.where(e > 1, 2 - e, e)
+            theta = e.sum() / (2 * use.sum())
+            assert abs(bgn.last_info[m] - (1 - (f - e * e).sum() / (2 * use.sum() * theta * (1 - theta)))) < 1e-9
+        assert np.all(bgn.last_info <= 1 + 1e-12)
     # the library's native reader (multi-threaded inflate / decode) against the pure-Python one: bit for bit
     for order in ("alt-first", "ref-first"):
         nat = genoio.BgenNative(path, n_threads=3)
@@ -245,6 +258,35 @@ def test_conditional_analysis_reproduces_the_reference_table(golden_dir, tmp_pat
     fo = S2.condition_factors(M, rows)
     assert np.allclose(f["P2"], fo["P2"], rtol=1e-12) and np.allclose(f["VarInv"], fo["VarInv"], rtol=1e-10)
     assert np.allclose(f["Tstat_cond"], fo["Tstat"], rtol=1e-10) and np.allclose(f["XtP2"], model["XXVX_inv"].T @ fo["P2"], rtol=1e-10)
+
+
+def test_imputed_data_columns_and_info_filter(golden_dir, tmp_path):
+    """is_imputed_data / minInfo: hard calls have INFO = 1 (every variant kept, `imputationInfo` column = 1); a file with
+    uncertain calls loses its low-INFO variants."""
+    from saige_gpu_b200 import step2
+    p = os.path.join(golden_dir, "step2_100markers")
+    base = dict(GMMATmodelFile=os.path.join(golden_dir, "example_binary.rda"), chrom="1", LOCO=True, min_MAC=20,
+                varianceRatioFile=os.path.join(golden_dir, "example_binary.varianceRatio.txt"))
+    out = str(tmp_path / "imp.txt")
+    rows = step2.SPAGMMATtest(OracleDevice(), bgenFile=p + ".bgen", sampleFile=_sample_file(golden_dir, tmp_path), AlleleOrder="ref-first",
+                              is_imputed_data=True, minInfo=0.3, SAIGEOutputFile=out, **base)
+    assert len(rows) == 32 and all(abs(r["imputationInfo"] - 1.0) < 1e-12 for r in rows)
+    hdr = open(out).readline().rstrip("\n").split("\t")
+    assert hdr[7] == "imputationInfo" and "MissingRate" not in hdr and open(out).read().splitlines()[1].split("\t")[7] == "1"
+    # uncertain calls: blur half of the variants of a small synthetic file, keep the model's samples in front
+    rng = np.random.default_rng(3)
+    ids = [l.split()[1] for l in open(p + ".fam")][:1000]
+    g = rng.binomial(2, 0.3, size=(12, 1000)).astype(np.float64)
+    blur = g.copy()
+    blur[::2] = np.clip(np.rint((g[::2] * 0.3 + 0.6 * 0.7) * 255) / 255, 0, 2)           # shrunk towards the mean: low INFO
+    path = str(tmp_path / "imp.bgen")
+    write_bgen(path, blur, 8, True, ids)
+    kept = step2.SPAGMMATtest(OracleDevice(), bgenFile=path, AlleleOrder="alt-first", is_imputed_data=True, minInfo=0.8,
+                              **{**base, "min_MAC": 1})
+    allv = step2.SPAGMMATtest(OracleDevice(), bgenFile=path, AlleleOrder="alt-first", is_imputed_data=True, minInfo=0.0,
+                              **{**base, "min_MAC": 1})
+    assert [r["MarkerID"] for r in kept] == ["v%d" % m for m in range(1, 12, 2)] and len(allv) == 12
+    assert all(r["imputationInfo"] < 0.8 for r in allv[::2]) and all(r["imputationInfo"] > 0.99 for r in allv[1::2])
 
 
 def test_variant_sharding_of_dosage_inputs(golden_dir, tmp_path):
