@@ -319,7 +319,7 @@ class _Writer:
         elif isinstance(v, str):
             v = [v]
         if isinstance(v, (list, tuple)):
-            if len(v) and all(isinstance(x, str) or x is None for x in v):
+            if any(isinstance(x, str) for x in v) and all(isinstance(x, str) or x is None for x in v):      # [None] is list(NULL)
                 self.vector_header(STRSXP, len(v), attr)
                 for x in v:
                     self.charsxp(x)

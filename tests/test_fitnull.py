@@ -424,3 +424,47 @@ def test_gpu_fitnullglmm_matches_oracle_backed_run_and_feeds_step2(oracle_fit, g
     assert len(rows) == 32 and all(0 < r["p.value"] <= 1 for r in rows)
     assert load_rda(out + ".rda")["modglmm"]["theta"][1] == a["theta"][1]
     g.close()
+
+
+def test_rda_writer_round_trip_property():
+    """Property test (hypothesis): any nesting of the value types a model file holds survives save_rda -> load_rda."""
+    import tempfile
+    from hypothesis import given, settings, strategies as st
+    from saige_gpu_b200.rdata import load_rda, save_rda
+
+    names = st.text(alphabet="abcXYZ._0123456789é", min_size=1, max_size=8).filter(lambda s: s not in ("",))
+    floats = st.floats(allow_nan=False, allow_infinity=True, width=64)
+    leaf = st.one_of(
+        st.lists(floats, min_size=0, max_size=6).map(lambda v: np.array(v, dtype=np.float64)),
+        st.lists(st.integers(-2 ** 31 + 1, 2 ** 31 - 1), min_size=0, max_size=6).map(lambda v: np.array(v, dtype=np.int32)),
+        st.lists(st.sampled_from([1, 0, -1]), min_size=1, max_size=5).map(lambda v: np.array(v, dtype=np.int8)),
+        st.lists(st.one_of(st.none(), st.text(alphabet="abc é\t", max_size=5)), min_size=1, max_size=4).filter(
+            lambda v: any(isinstance(x, str) for x in v)),
+        st.tuples(st.integers(1, 3), st.integers(1, 3)).flatmap(
+            lambda s: st.lists(floats, min_size=s[0] * s[1], max_size=s[0] * s[1]).map(lambda v: np.array(v).reshape(s))),
+        st.none())
+    tree = st.recursive(leaf, lambda kids: st.one_of(st.dictionaries(names, kids, min_size=1, max_size=4),
+                                                     st.lists(st.dictionaries(names, kids, min_size=1, max_size=2), min_size=1, max_size=3)),
+                        max_leaves=12)
+
+    def same(a, b):
+        if isinstance(a, dict):
+            return isinstance(b, dict) and list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, list):
+            return isinstance(b, list) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(a, np.ndarray):
+            return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+        if isinstance(a, str):
+            return a == b
+        return a is None and b is None
+
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "p.rda")
+
+        @settings(max_examples=60, deadline=None)
+        @given(st.dictionaries(names, tree, min_size=1, max_size=3))
+        def check(obj):
+            save_rda(path, obj)
+            back = load_rda(path)
+            assert same(obj, back), (obj, back)
+        check()
