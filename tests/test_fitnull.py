@@ -231,12 +231,12 @@ def test_covariate_transform_does_not_change_the_model(oracle_fit, golden_dir, b
 
 def test_skip_model_fitting_reuses_the_written_model(oracle_fit, golden_dir, bim22):
     """skipModelFitting = TRUE (FG.R:1303-1313): the .rda on disk is loaded and only the variance ratio is estimated again;
-    same hold-out set and marker order (same seed) -> the same ratio to the last digit."""
+    same hold-out set and marker order (same seed) -> the same ratio."""
     r, out = oracle_fit
     before = open(out + ".rda", "rb").read()
     r2 = _run(OracleBackend(), golden_dir, bim22, out, skipModelFitting=True)
     assert open(out + ".rda", "rb").read() == before                       # the model file is not rewritten
-    assert r2["varianceRatio"] == r["varianceRatio"]
+    assert abs(r2["varianceRatio"] - r["varianceRatio"]) < 1e-12 * r["varianceRatio"]        # (the oracle's OpenMP sums are not ordered)
     assert np.array_equal(r2["modglmm"]["theta"], r["modglmm"]["theta"])
 
 
