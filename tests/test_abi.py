@@ -109,3 +109,11 @@ def test_r_probe_stream_matches_r():
     assert np.array_equal(ps.U[:, 0], 2.0 * (u[:4] >= 0.5) - 1.0) and np.array_equal(ps.U[:, 2], 2.0 * (u[8:12] >= 0.5) - 1.0)
     d = ps.fresh()
     assert np.array_equal(d(2), ps.U[:, :2]) and np.array_equal(d(1), ps.U[:, 2:3])
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 (and as C++) with no project or CUDA include."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "saige_b200.h")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr])
+    subprocess.check_call(["g++", "-fsyntax-only", "-x", "c++", "-Wall", "-Werror", hdr])
