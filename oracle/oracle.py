@@ -51,6 +51,7 @@ def lib():
         L.orc_diag_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.orc_synth_bed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 

@@ -105,19 +105,26 @@ int orc_setgeno(orc_geno *g, const uint8_t *bed, int64_t N0, int64_t M0, const i
     g->mac_vr = (int32_t *)malloc(sizeof(int32_t) * (vr_cap + 1));
     g->ac_vr = (int32_t *)malloc(sizeof(int32_t) * (vr_cap + 1));
     g->index_vr = (int32_t *)malloc(sizeof(int32_t) * (vr_cap + 1));
-    int *tmp = (int *)malloc(sizeof(int) * (N0 + 4));
     uint8_t *invr = (uint8_t *)calloc(M0 + 1, 1);
-    if (!g->geno || !g->afreq || !g->invstd || !g->mac || !g->ac || !g->qc_mask || !g->geno_vr || !tmp || !invr) return -1;
+    /* per raw marker: decision (bit 0 = GRM, bit 1 = variance-ratio store), imputation fill, statistics.  The marker
+     * loop of the reference is sequential (Fg->cpp:897-953); its iterations are independent except for the running
+     * output indices, so it is restated as: statistics of every marker (parallel), prefix count, re-pack (parallel). */
+    uint8_t *dec = (uint8_t *)calloc(M0 + 1, 1);
+    int32_t *fillv = (int32_t *)malloc(sizeof(int32_t) * (M0 + 1)), *acv = (int32_t *)malloc(sizeof(int32_t) * (M0 + 1));
+    int32_t *macv = (int32_t *)malloc(sizeof(int32_t) * (M0 + 1));
+    float *fv = (float *)malloc(sizeof(float) * (M0 + 1)), *isv = (float *)malloc(sizeof(float) * (M0 + 1));
+    int64_t *dstq = (int64_t *)malloc(sizeof(int64_t) * (M0 + 1));
+    if (!g->geno || !g->afreq || !g->invstd || !g->mac || !g->ac || !g->qc_mask || !g->geno_vr || !invr || !dec || !fillv ||
+        !acv || !macv || !fv || !isv || !dstq) return -1;
     for (int64_t j = 0; j < n_vr; j++)
         if (vr_idx[j] >= 0 && vr_idx[j] < M0) invr[vr_idx[j]] = 1;
 
-    int64_t Mq = 0, Mv = 0;
+#pragma omp parallel for schedule(static)
     for (int64_t m = 0; m < M0; m++) {
         const uint8_t *row = bed + m * B0;
         int alleleCount = 0, numMissing = 0;
         for (int64_t i = 0; i < N0; i++) {
             int gv = bed_code_to_geno((row[i >> 2] >> ((i & 3) << 1)) & 3);
-            tmp[i] = gv;
             if (indicator[i]) { if (gv == 3) numMissing++; else alleleCount += gv; }
         }
         /* Fg->cpp:438-447 -- float arithmetic, in this order */
@@ -139,28 +146,37 @@ int orc_setgeno(orc_geno *g, const uint8_t *bed, int64_t N0, int64_t M0, const i
             }
             if (passVR) passQC = 0;
         }
-        if (passQC || passVR) {                             /* Fg->cpp:551-576 */
-            uint8_t *dst = passQC ? g->geno + Mq * g->B : g->geno_vr + Mv * g->B;
-            memset(dst, 0, g->B);
-            for (int64_t k = 0; k < N; k++) {
-                int gv = tmp[sub_idx[k] - 1];
-                if (gv == 3) gv = fill;
-                dst[k >> 2] |= (uint8_t)(geno_to_code(gv) << ((k & 3) << 1));
-            }
-        }
         float Std = sqrtf(2 * altFreq * (1 - altFreq));    /* Fg->cpp:916-921 */
-        float invStd = (Std == 0) ? 0.f : 1 / Std;
-        if (passQC) {
-            g->afreq[Mq] = altFreq; g->invstd[Mq] = invStd; g->mac[Mq] = mac; g->ac[Mq] = alleleCount;
-            g->qc_mask[m] = 1; Mq++;
+        dec[m] = (uint8_t)((passQC ? 1 : 0) | ((isVarRatio && passVR) ? 2 : 0));
+        fillv[m] = fill; acv[m] = alleleCount; macv[m] = mac; fv[m] = altFreq; isv[m] = (Std == 0) ? 0.f : 1 / Std;
+    }
+    int64_t Mq = 0, Mv = 0;
+    for (int64_t m = 0; m < M0; m++) {
+        dstq[m] = -1;
+        if (dec[m] & 1) {
+            g->afreq[Mq] = fv[m]; g->invstd[Mq] = isv[m]; g->mac[Mq] = macv[m]; g->ac[Mq] = acv[m];
+            g->qc_mask[m] = 1; dstq[m] = Mq++;
         }
-        if (isVarRatio && passVR) {
-            g->afreq_vr[Mv] = altFreq; g->invstd_vr[Mv] = invStd; g->mac_vr[Mv] = mac; g->ac_vr[Mv] = alleleCount;
-            g->index_vr[Mv] = (int32_t)m; Mv++;
+        if (dec[m] & 2) {
+            g->afreq_vr[Mv] = fv[m]; g->invstd_vr[Mv] = isv[m]; g->mac_vr[Mv] = macv[m]; g->ac_vr[Mv] = acv[m];
+            g->index_vr[Mv] = (int32_t)m; dstq[m] = Mv++;
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M0; m++) {
+        if (!dec[m]) continue;                              /* Fg->cpp:551-576 */
+        const uint8_t *row = bed + m * B0;
+        uint8_t *dst = (dec[m] & 1) ? g->geno + dstq[m] * g->B : g->geno_vr + dstq[m] * g->B;
+        memset(dst, 0, g->B);
+        for (int64_t k = 0; k < N; k++) {
+            int64_t src = sub_idx[k] - 1;
+            int gv = bed_code_to_geno((row[src >> 2] >> ((src & 3) << 1)) & 3);
+            if (gv == 3) gv = fillv[m];
+            dst[k >> 2] |= (uint8_t)(geno_to_code(gv) << ((k & 3) << 1));
         }
     }
     g->M = Mq; g->Mvr = Mv;
-    free(tmp); free(invr);
+    free(invr); free(dec); free(fillv); free(acv); free(macv); free(fv); free(isv); free(dstq);
     return 0;
 }
 
@@ -292,13 +308,33 @@ void orc_diag_range(orc_geno *g, int64_t m0, int64_t m1, int mode, double *out)
         for (int64_t i = 0; i < N; i++) out[i] = acc[i];
         free(acc);
     } else {
-        for (int64_t m = m0; m < m1; m++) {
-            const uint8_t *row = g->geno + m * g->B;
-            double f, s; marker_fs64(g, m, &f, &s);
-            double lut[4] = {(2 - 2 * f) * s, 0.0, (1 - 2 * f) * s, (0 - 2 * f) * s};
-            for (int64_t i = 0; i < N; i++) { double z = lut[(row[i >> 2] >> ((i & 3) << 1)) & 3]; out[i] += z * z; }
+        /* fp64 mode: marker blocks in parallel, partial sums added as the threads finish (the result depends on
+         * the schedule only through the rounding of fp64 sums, ~1e-16 relative) */
+#pragma omp parallel
+        {
+            double *acc = (double *)calloc(N, sizeof(double));
+#pragma omp for schedule(static)
+            for (int64_t m = m0; m < m1; m++) {
+                const uint8_t *row = g->geno + m * g->B;
+                double f, s; marker_fs64(g, m, &f, &s);
+                double lut[4] = {(2 - 2 * f) * s, 0.0, (1 - 2 * f) * s, (0 - 2 * f) * s};
+                for (int64_t i = 0; i < N; i++) { double z = lut[(row[i >> 2] >> ((i & 3) << 1)) & 3]; acc[i] += z * z; }
+            }
+#pragma omp critical
+            for (int64_t i = 0; i < N; i++) out[i] += acc[i];
+            free(acc);
         }
     }
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU-baseline legs of bench.py set the count explicitly */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int orc_num_threads(void)

@@ -1,11 +1,14 @@
-"""Multi-GPU parity check, launched with torchrun (one rank per GPU):
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+"""Multi-GPU parity worker, launched by tests/test_gpu_multi.py under torchrun (one rank per GPU):
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_worker.py
 Every rank loads the bundled 10k-marker set (markers sharded block-cyclically inside the library), then GRM products,
-LOCO products, the GRM diagonal, a multi-RHS PCG and a full binary step-1 fit are compared with the CPU oracle."""
+LOCO products, the GRM diagonal, a multi-RHS PCG, a full binary step-1 fit, the dense-GRM build / product / PCG are
+compared with the CPU oracle, a larger synthetic set is checked against the oracle at production row lengths, and a
+rank-sharded step-2 scan is compared with the single-rank table (BASELINE config 5: variants sharded, no collective)."""
 import os, sys
 import numpy as np
 import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+os.environ.pop("OMP_NUM_THREADS", None)          # torchrun pins it to 1; the oracle may use the host's cores
 from oracle import oracle as O
 from saige_gpu_b200 import SaigeB200, step1
 
@@ -65,10 +68,58 @@ g.setGRMMode("packed")
 assert list(itd) == list(ito)
 res["dense_pcg"] = rel(Xd, Xo)
 assert info["stored_bytes"] <= 8 * 128 * 128 * 8 * 9 / 2 and (world == 1 or info["stored_bytes"] < 8 * 128 * 128 * 8 * 9 / 2), info
-pcg_keys = ("pcg", "tau", "alpha", "dense_pcg")
+# ---- a synthetic set at production row lengths (20k samples x 60k markers), same generator on both sides ----
+from saige_gpu_b200 import synth, step2
+Ns, Ms, SEED = 20_000, 60_000, 20260117
+_, t0, t1 = synth.thresholds(Ms, SEED)
+g.setgeno_synth(Ns, Ms, SEED, t0, t1)
+beds = O.synth_bed(Ns, Ms, SEED)
+os_ = O.OracleGeno(); os_.minMAF, os_.maxMissing = 0.01, 0.15
+os_.setgeno(beds, Ns, Ms, np.arange(1, Ns + 1), np.ones(Ns, np.uint8))
+assert np.array_equal(g.getAlleleCountVec(), os_.ACVec)
+Bs = rng.normal(size=(Ns, 3))
+res["synth_crossprod"] = rel(g.getCrossprodMatAndKin(Bs), os_.getCrossprodMatAndKin(Bs))
+res["synth_crossprod_k1"] = rel(g.getCrossprodMatAndKin(Bs[:, 0]), os_.getCrossprodMatAndKin(Bs[:, 0]))
+res["synth_diag"] = rel(g.get_DiagofKin(), os_.get_DiagofKin())
+chrs_s = synth.chromosomes(Ms)[g.getQCdMarkerIndex()]
+_, ss, es = O.updateChrStartEndIndexVec(chrs_s)
+os_.setStartEndIndexVec(ss, es); step1.set_loco_ranges(g, chrs_s)
+for j in (0, 10, 21):
+    os_.setStartEndIndex(ss[j], es[j], j); g.setStartEndIndex(ss[j], es[j], j)
+    res["synth_loco%d" % j] = rel(g.getCrossprodMatAndKin_LOCO(Bs[:, 0]), os_.getCrossprodMatAndKin_LOCO(Bs[:, 0]))
+ws = rng.uniform(0.05, 0.25, size=Ns)
+Xs, its = g.getPCG1ofSigmaAndVector(ws, tau, Bs, 500, 1e-5, return_iter=True)
+Xso, itso = os_.pcg_multi(ws, tau, Bs, 500, 1e-5)
+assert list(its) == list(itso), (its, itso)
+res["synth_pcg"] = rel(Xs, Xso)
+
+# ---- step 2: the rank's contiguous slice of the variants, no collective; slices concatenated == single-rank table ----
+gd = os.path.join(ROOT, "tests", "golden")
+p2 = os.path.join(gd, "step2_100markers")
+def scan(r, w):
+    return step2.SPAGMMATtest(g, p2 + ".bed", p2 + ".bim", p2 + ".fam", os.path.join(gd, "example_binary.rda"),
+                              os.path.join(gd, "example_binary.varianceRatio.txt"), chrom="1", LOCO=True,
+                              markers_per_chunk=7, rank=r, world=w)
+mine = scan(rank, world)
+parts = [None] * world
+dist.all_gather_object(parts, mine)
+step2_ok = True
+if rank == 0:
+    full = scan(0, 1)
+    cat = [r for part in parts for r in part]
+    step2_ok = len(cat) == len(full) and all(a.keys() == b.keys() and all(
+        (a[k] == b[k]) or (isinstance(a[k], float) and isinstance(b[k], float) and np.isnan(a[k]) and np.isnan(b[k]))
+        for k in a) for a, b in zip(cat, full))
+    assert len(full) > 20
+
+pcg_keys = ("pcg", "tau", "alpha", "dense_pcg", "synth_pcg")
 worst_mv = max(v for k, v in res.items() if k not in pcg_keys)
-ok = worst_mv < 1e-10 and res["dense_pcg"] < 1e-6 and res["pcg"] < 1e-6 and res["tau"] < 1e-6 and res["alpha"] < 1e-6
-print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e tau %.2e alpha %.2e allreduces %d -> %s"
-      % (rank, world, g.Mloc, worst_mv, res["pcg"], res["tau"], res["alpha"], g.counters()["n_allreduce"], "OK" if ok else "FAIL"), flush=True)
+ok = (worst_mv < 1e-10 and res["dense_pcg"] < 1e-6 and res["pcg"] < 1e-6 and res["tau"] < 1e-6 and res["alpha"] < 1e-6
+      and res["synth_pcg"] < 1e-6 and step2_ok)
+print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e/%.2e tau %.2e alpha %.2e step2 %s allreduces %d -> %s"
+      % (rank, world, g.Mloc, worst_mv, res["pcg"], res["synth_pcg"], res["tau"], res["alpha"], step2_ok,
+         g.counters()["n_allreduce"], "OK" if ok else "FAIL"), flush=True)
+if not ok:
+    print({k: v for k, v in res.items() if v > 1e-10}, flush=True)
 g.close(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
