@@ -86,29 +86,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(N, M, threads_note=True, target_s=12.0):
-    """Reference CPU matvec (fp32, reference operation order) on a bounded marker sample of the same workload."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(N, M, target_s=12.0, msample=8192, steps=None, warmup=1):
+    """Reference CPU matvec (fp32, reference operation order: the marker loop of parallelCrossProdOpenMP, FG.cpp:1576-1598) on a
+    bounded marker sample of the same workload, on ALL host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, so the
+    thread count is set explicitly through the oracle.  One "sample step" = one matvec over `msample` markers x all N samples;
+    the full-workload figure is that time scaled linearly in M (the loop is a sum over markers) and says so."""
     from oracle import oracle as O
+    O.lib().orc_set_num_threads(host_cores())
     cores = O.lib().orc_num_threads()
-    msample = 2048
     bed = O.synth_bed(N, msample, SEED)
     g = O.OracleGeno(mode=O.REF32)
     g.minMAF, g.maxMissing = 0.01, 0.15
     g.setgeno(bed, N, msample, np.arange(1, N + 1), np.ones(N, np.uint8))
     b = np.random.default_rng(1).integers(0, 2, N) * 2.0 - 1.0
-    g.getCrossprodMatAndKin(b)                      # warm-up
-    reps, t0 = 0, time.time()
-    while True:
+    for _ in range(max(1, warmup)):
         g.getCrossprodMatAndKin(b)
-        reps += 1
-        if time.time() - t0 > target_s or reps >= 50:
+    times = []
+    t0 = time.time()
+    while True:
+        t1 = time.perf_counter()
+        g.getCrossprodMatAndKin(b)
+        times.append(time.perf_counter() - t1)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.time() - t0 > target_s or len(times) >= 50:
             break
-    per_sample = (time.time() - t0) / reps
-    per_matvec = per_sample * (M / g.M)
+    per_sample = float(np.sum(times)) / len(times)
+    scale = M / g.M
+    per_matvec = per_sample * scale
     return {"value": 1.0 / per_matvec, "unit": "matvecs/s", "cores": int(cores), "kind": "port",
-            "sample": "%d of %d markers x %d samples, fp32 reference-order matvec (oracle ref32 mode, OpenMP), "
-                      "%d reps, scaled linearly in M" % (g.M, M, N, reps),
-            "s_per_sample_matvec": per_sample}
+            "sample": "%d of %d markers x %d samples, fp32 reference-order matvec (oracle ref32 mode, OpenMP, %d threads), "
+                      "%d timed sample steps, scaled linearly in M (x%.1f)" % (g.M, M, N, cores, len(times), scale),
+            "extrapolated": True, "scale_in_markers": scale, "sample_steps": len(times),
+            "s_per_sample_matvec": per_sample, "s_per_sample_matvec_median": float(np.median(times)),
+            "s_timed_total": float(np.sum(times))}
 
 
 def reference_gpu_kernel(N, M, msample=4096):
@@ -178,13 +197,17 @@ def step1_c1_beside(device):
 
 
 def run_reference(args, N, M, rank, world):
+    """--impl reference: the reference's CPU matvec on the host cores (rank 0 only; other ranks exit without work).  A step is one
+    matvec over a 32,768-marker sample of the workload (all N samples); exactly --warmup + --steps of them run."""
     if rank != 0:
         return
-    cb = cpu_baseline(N, M, target_s=max(2.0, 1.5 * args.steps))
+    cb = cpu_baseline(N, M, msample=32768 if N <= 200_000 else 8192, steps=max(1, args.steps), warmup=max(1, args.warmup))
     line = {"impl": "reference", "metric": "grm_matvecs_per_s", "value": cb["value"], "unit": "matvecs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_samples": N, "n_markers": M, "k": 1},
+            "extrapolated": True,
+            "ms_per_sample_step": 1e3 * cb["s_per_sample_matvec"], "timed_region_s": cb["s_timed_total"],
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

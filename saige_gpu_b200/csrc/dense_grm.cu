@@ -97,7 +97,7 @@ __global__ void syrk_image_kernel(const uint8_t *__restrict__ Gt, int64_t sT, in
     const int l = (int)(t & 7), w = (int)((t >> 3) & 7), c = (int)((t >> 6) & 15);
     const int64_t blk = t >> 10;
     if (blk >= nblk) return;
-    const uint32_t wv = *reinterpret_cast<const uint32_t *>(Gt + (row0 + 8 * c + l) * sT + blk * 32 + w * 4);
+    const uint32_t wv = *reinterpret_cast<const uint32_t *>(Gt + sgb_tiled_off(row0 + 8 * c + l, blk * 32 + w * 4, sT));
     const uint32_t hi = wv >> 16;
     // value plane of the pair-ternary coding: byte = 2 - genotype (kernels.cu decode16)
     const uint32_t h0 = dg_prmt(0x02000102u, 0x01020001u, wv);     // positions 0,2,4,6

@@ -90,6 +90,16 @@ int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n)
     return 0;
 }
 
+int sgb_allreduce_sum_i32(sgb_ctx *h, int32_t *d, int64_t n)
+{
+    if (h->world <= 1) return 0;
+    if (!h->dist || !h->dist->comm) return sgb_fail(h, "allreduce requested but NCCL communicator is not initialised");
+    ncclResult_t r = g_nccl.AllReduce(d, d, (size_t)n, ncclInt32, ncclSum, h->dist->comm, h->stream);
+    if (r != ncclSuccess) return sgb_fail(h, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    h->cnt.n_allreduce++;
+    return 0;
+}
+
 // in-place broadcast of a device buffer from `root` (dense-GRM build: every rank needs every marker shard)
 int sgb_broadcast_bytes(sgb_ctx *h, void *d, size_t bytes, int root)
 {

@@ -116,7 +116,7 @@ int k_count_markers(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, int64_t nmark,
 // re-pack kept markers in phenotype-sample order with imputation, into the device coding (FG.cpp:551-576)
 __global__ void repack_kernel(const uint8_t *__restrict__ bed, int64_t B0, const int32_t *__restrict__ src_rows,
                               const int32_t *__restrict__ fill, const int32_t *__restrict__ sub_idx, int identity,
-                              int64_t N, uint8_t *__restrict__ out, int64_t out_stride)
+                              int64_t N, uint8_t *__restrict__ out, int64_t out_row0, int64_t out_stride, int tiled)
 {
     int64_t r = blockIdx.y;
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,14 +134,14 @@ __global__ void repack_kernel(const uint8_t *__restrict__ bed, int64_t B0, const
             gq[j] = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fl));
         }
     }
-    out[r * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
+    out[tiled ? sgb_tiled_off(out_row0 + r, b, out_stride) : (out_row0 + r) * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
 }
 
 // gather variant: the raw row is staged in shared memory once, then every output byte gathers its 4 samples from it
 __global__ void __launch_bounds__(256) repack_gather_kernel(const uint8_t *__restrict__ bed, int64_t B0,
                                                             const int32_t *__restrict__ src_rows, const int32_t *__restrict__ fill,
                                                             const int32_t *__restrict__ sub_idx, int64_t N,
-                                                            uint8_t *__restrict__ out, int64_t out_stride)
+                                                            uint8_t *__restrict__ out, int64_t out_row0, int64_t out_stride, int tiled)
 {
     extern __shared__ uint8_t srow[];
     const int64_t r = blockIdx.x;
@@ -161,19 +161,20 @@ __global__ void __launch_bounds__(256) repack_gather_kernel(const uint8_t *__res
                 gq[j] = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fl));
             }
         }
-        out[r * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
+        out[tiled ? sgb_tiled_off(out_row0 + r, b, out_stride) : (out_row0 + r) * out_stride + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
     }
 }
 
 int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_rows, const int32_t *d_fill,
-             int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_stride)
+             int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_row0, int64_t out_stride,
+             int tiled)
 {
     if (nrows <= 0) return 0;
     int64_t B = (N + 3) / 4;
     if (!identity && B0 <= 200 * 1024) {
         if (sgb_first_on_device(h->device, SGB_SITE_REPACK))
             CUDA_OK(h, cudaFuncSetAttribute(repack_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        repack_gather_kernel<<<(unsigned)nrows, 256, (size_t)B0, h->stream>>>(d_bed, B0, d_src_rows, d_fill, d_sub_idx, N, d_out, out_stride);
+        repack_gather_kernel<<<(unsigned)nrows, 256, (size_t)B0, h->stream>>>(d_bed, B0, d_src_rows, d_fill, d_sub_idx, N, d_out, out_row0, out_stride, tiled);
         LAUNCH_CHECK(h);
         return 0;
     }
@@ -181,13 +182,14 @@ int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_
         int64_t nr = nrows - r0 < 65535 ? nrows - r0 : 65535;
         dim3 grid((unsigned)cdiv(B, 256), (unsigned)nr);
         repack_kernel<<<grid, 256, 0, h->stream>>>(d_bed, B0, d_src_rows + r0, d_fill + r0, d_sub_idx, identity, N,
-                                                    d_out + r0 * out_stride, out_stride);
+                                                    d_out, out_row0 + r0, out_stride, tiled);
         LAUNCH_CHECK(h);
     }
     return 0;
 }
 
-// marker-major -> sample-major copy.  CTA tile: 128 markers x 256 samples.
+// marker-major -> sample-major copy.  CTA tile: 128 markers x 256 samples = one (panel, slab) block of the tiled
+// marker-major store, read as 8 KB of consecutive bytes.
 __global__ void __launch_bounds__(256) transpose_kernel(const uint8_t *__restrict__ G, int64_t sG, int64_t Mloc,
                                                         uint8_t *__restrict__ Gt, int64_t sT, int64_t N)
 {
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const uint8_t *__restric
     for (int idx = threadIdx.x; idx < 128 * 16; idx += 256) {
         int r = idx >> 4, q = idx & 15;
         uint32_t v = 0;
-        if (m0 + r < Mloc && b0 + 4 * q < sG) v = *reinterpret_cast<const uint32_t *>(G + (m0 + r) * sG + b0 + 4 * q);
+        if (m0 + r < Mloc && b0 + 4 * q < sG) v = *reinterpret_cast<const uint32_t *>(G + sgb_tiled_off(m0 + r, b0 + 4 * q, sG));
         *reinterpret_cast<uint32_t *>(&tile[r][4 * q]) = v;
     }
     __syncthreads();
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const uint8_t *__restric
         }
         o[w] = acc;
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(Gt + i * sT + (m0 >> 2));
+    uint4 *dst = reinterpret_cast<uint4 *>(Gt + sgb_tiled_off(i, m0 >> 2, sT));      // 32 bytes inside one 64-byte slab row
     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
     dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
@@ -262,7 +264,7 @@ __global__ void synth_kernel(int mode, int64_t y0, uint64_t seed, const uint32_t
                 cnt += gq[j];
             }
         }
-        if (mode) G[r * sG + b] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
+        if (mode) G[sgb_tiled_off(r, b, sG)] = (uint8_t)sgb_pack4(gq[0], gq[1], gq[2], gq[3]);
     }
     if (!mode) {
 #pragma unroll
@@ -326,122 +328,169 @@ __device__ __forceinline__ void mma_u8s8(int32_t (&c)[4], uint32_t a0, uint32_t 
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ uint4 ldg_stream(const uint8_t *p)
+// ---- mbarrier + bulk-copy (TMA engine, UBLKCP) primitives of the sweep kernel ----
+__device__ __forceinline__ uint32_t smem_u32k(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_k(uint64_t *bar, uint32_t count)
 {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32k(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait_k(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32k(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_k(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32k(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_k(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32k(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_k(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32k(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32k(bar))
+                 : "memory");
 }
 
-// out[r][c*8+l] += sum over this CTA's k-chunk of  P[r][.] * L[c][.][l]
-//   P      : packed rows, `stride` bytes each (multiple of 64), rows padded to a multiple of 128*MT
-//   L      : limb fragments, per column c: nblk blocks of 2048 bytes; block = 256 genotypes x 8 limbs laid out
-//            [mma pair(4)][lane(32)][mma of the pair(2)][b0/b1(2)][byte(4)]: one coalesced 16-byte load per lane and
-//            MMA pair brings the B fragments {b0,b1} of MMAs 2q and 2q+1
-//   grid   : x = k-chunks, y = row tiles of 128*MT rows;  8 warps, each MT m16 tiles
-template <int MT, int NT>
-__global__ void __launch_bounds__(256, (MT * NT <= 8) ? 2 : 1)   // <=128 regs for the k=1 path, 255 for wide tiles
-pk2_gemm_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t kblocks_total, int kblocks_per_chunk,
-                const int8_t *__restrict__ L, int64_t Lcol_stride, int c0, int ncol_total, int32_t *__restrict__ out,
-                pk2_pools pool)
+// out[r][(c0+n)*8+l] += sum_k P[r][k] * L[c0+n][k][l]     -- the GRM sweep for k <= 2 right-hand sides (HBM-bound)
+//   P      : packed rows in the TILED layout (sgb_tiled_off): 128-row panels, 8 KB (panel, k-slab) blocks
+//   L      : limb fragments, per column c: ksteps blocks of 2048 bytes; block = 256 genotypes x 8 limbs laid out
+//            [mma pair(4)][lane(32)][mma of the pair(2)][b0/b1(2)][byte(4)]: one 16-byte load per lane and MMA pair
+//            brings the B fragments {b0,b1} of MMAs 2q and 2q+1
+// Persistent CTAs (2 per SM): 8 consumer warps + 1 producer warp.  Work unit = (256-row tile, group of KS k-slabs); the
+// units of the whole matrix are dealt to the CTAs as contiguous ranges, so a CTA walks along the slabs of a tile and then
+// on to the next tile, flushing its int32 accumulators with RED.ADD when the tile changes (integers: order independent).
+// Producer: one lane issues cp.async.bulk copies -- per stage KS*8 KB CONTIGUOUS bytes of each of the two panels plus the
+// limb fragments -- onto an mbarrier with expect_tx; STAGES-deep ring, "empty" barriers released by one arrive per warp.
+// Consumers: conflict-free 128-bit LDS of (row g / g+8, bytes 16t..) = the A fragments' packed form, prmt decode, IMMA.
+template <int NT, int KS, int STAGES>
+__global__ void __launch_bounds__(288, 2)
+pk2_stream_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t tiles, int64_t ksteps, const int8_t *__restrict__ L,
+                  int64_t Lcol_stride, int c0, int ncol_total, int32_t *__restrict__ out, pk2_pools pool)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int64_t row0 = ((int64_t)blockIdx.y * 8 + warp) * (16 * MT);
-    const int64_t kb0 = (int64_t)blockIdx.x * kblocks_per_chunk;
-    int64_t kb1 = kb0 + kblocks_per_chunk;
-    if (kb1 > kblocks_total) kb1 = kblocks_total;
-
+    constexpr int WARPS = 8, MT = 2, RT = WARPS * MT * 16, PANELS = RT / SGB_PANEL_ROWS;
+    constexpr uint32_t A_STAGE = (uint32_t)PANELS * KS * SGB_SLAB_BYTES, B_STAGE = (uint32_t)NT * KS * 2048, STAGE = A_STAGE + B_STAGE;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[STAGES], empty[STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t KG = (ksteps + KS - 1) / KS, units = tiles * KG;
+    const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init_k(&full[i], 1); mbar_init_k(&empty[i], WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    if (warp == WARPS) {
+        // ================= producer: one lane feeds the ring through the TMA engine =================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int64_t u = u0; u < u1; u++) {
+                const int64_t tile = u / KG, kg = u - tile * KG;
+                const int nks = (int)((kg + 1) * KS <= ksteps ? KS : ksteps - kg * KS);
+                if (u - u0 >= STAGES) mbar_wait_k(&empty[st], ph ^ 1);
+                uint8_t *dst = smem + (size_t)st * STAGE;
+                mbar_expect_tx_k(&full[st], (uint32_t)nks * (PANELS * SGB_SLAB_BYTES + NT * 2048));
+#pragma unroll
+                for (int p = 0; p < PANELS; p++)
+                    bulk_g2s_k(dst + p * (KS * SGB_SLAB_BYTES), P + ((tile * PANELS + p) * SGB_PANEL_ROWS) * stride + kg * KS * SGB_SLAB_BYTES,
+                               (uint32_t)nks * SGB_SLAB_BYTES, &full[st]);
+#pragma unroll
+                for (int n = 0; n < NT; n++)
+                    bulk_g2s_k(dst + A_STAGE + n * (KS * 2048), L + (int64_t)(c0 + n) * Lcol_stride + kg * KS * 2048, (uint32_t)nks * 2048, &full[st]);
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+    // ================= consumers =================
     int32_t acc[MT][NT][4];
 #pragma unroll
     for (int a = 0; a < MT; a++)
 #pragma unroll
-        for (int b = 0; b < NT; b++)
+        for (int n = 0; n < NT; n++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
-
-    const uint8_t *pa = P + (row0 + g) * stride + kb0 * SGB_KSTEP_BYTES + 16 * t;
-    const int8_t *pl = L + (int64_t)c0 * Lcol_stride + kb0 * 2048 + lane * 16;
-
-    uint4 raw[MT][2];
+            for (int c = 0; c < 4; c++) acc[a][n][c] = 0;
+    const int r0 = warp * MT * 16, panel = r0 >> 7, rp = r0 & 127;
+    const int g = lane >> 2, t = lane & 3;
+    const int ncols8 = ncol_total * 8;
+    // C fragment: c0 (row g, limb 2t) c1 (row g, limb 2t+1) c2 (row g+8, limb 2t) c3 (row g+8, limb 2t+1)
+    auto flush = [&](int64_t tile) {
 #pragma unroll
-    for (int a = 0; a < MT; a++) {
-        raw[a][0] = ldg_stream(pa + (int64_t)(16 * a) * stride);
-        raw[a][1] = ldg_stream(pa + (int64_t)(16 * a + 8) * stride);
-    }
-
-#pragma unroll 1
-    for (int64_t kb = kb0; kb < kb1; kb++) {
-        uint4 bf[NT][4];
+        for (int a = 0; a < MT; a++)
 #pragma unroll
-        for (int n = 0; n < NT; n++) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(pl + (int64_t)n * Lcol_stride + (kb - kb0) * 2048);
-#pragma unroll
-            for (int j = 0; j < 4; j++) bf[n][j] = __ldg(q + 32 * j);       // [mma pair j][lane] : 512 B per warp load
-        }
-        const bool more = kb + 1 < kb1;
-        const uint8_t *pn = pa + (kb + 1 - kb0) * SGB_KSTEP_BYTES;
-#pragma unroll
-        for (int a = 0; a < MT; a++) {
-            // consume this m-tile's 2 x 16 bytes, then immediately refill the same registers for the next k-step
-            const uint32_t wl[4] = {raw[a][0].x, raw[a][0].y, raw[a][0].z, raw[a][0].w};
-            const uint32_t wh[4] = {raw[a][1].x, raw[a][1].y, raw[a][1].z, raw[a][1].w};
-            if (more) {
-                raw[a][0] = ldg_stream(pn + (int64_t)(16 * a) * stride);
-                raw[a][1] = ldg_stream(pn + (int64_t)(16 * a + 8) * stride);
+            for (int n = 0; n < NT; n++) {
+                int32_t *o = out + (tile * RT + r0 + 16 * a + g) * ncols8 + (c0 + n) * 8 + 2 * t;
+                if (acc[a][n][0]) atomicAdd(o, acc[a][n][0]);
+                if (acc[a][n][1]) atomicAdd(o + 1, acc[a][n][1]);
+                if (acc[a][n][2]) atomicAdd(o + 8 * ncols8, acc[a][n][2]);
+                if (acc[a][n][3]) atomicAdd(o + 8 * ncols8 + 1, acc[a][n][3]);
+                acc[a][n][0] = acc[a][n][1] = acc[a][n][2] = acc[a][n][3] = 0;
             }
+    };
+    int st = 0;
+    uint32_t ph = 0;
+    int64_t cur_tile = u0 < u1 ? u0 / KG : 0;
+    for (int64_t u = u0; u < u1; u++) {
+        const int64_t tile = u / KG, kg = u - tile * KG;
+        const int nks = (int)((kg + 1) * KS <= ksteps ? KS : ksteps - kg * KS);
+        if (tile != cur_tile) { flush(cur_tile); cur_tile = tile; }
+        mbar_wait_k(&full[st], ph);
+        const uint8_t *sa = smem + (size_t)st * STAGE + panel * (KS * SGB_SLAB_BYTES) + rp * 64 + lane * 16;
+        const uint8_t *sb = smem + (size_t)st * STAGE + A_STAGE + lane * 16;
+        for (int ks = 0; ks < nks; ks++) {
+            uint4 bf[NT][4];
 #pragma unroll
-            for (int wi = 0; wi < 4; wi++) {
-                uint32_t dl[4], dh[4];
-                decode16(wl[wi], pool, dl);
-                decode16(wh[wi], pool, dh);
+            for (int n = 0; n < NT; n++)
 #pragma unroll
-                for (int n = 0; n < NT; n++) {
-                    mma_u8s8(acc[a][n], dl[0], dh[0], dl[1], dh[1], bf[n][wi].x, bf[n][wi].y);
-                    mma_u8s8(acc[a][n], dl[2], dh[2], dl[3], dh[3], bf[n][wi].z, bf[n][wi].w);
+                for (int j = 0; j < 4; j++) bf[n][j] = *reinterpret_cast<const uint4 *>(sb + n * (KS * 2048) + ks * 2048 + j * 512);
+#pragma unroll
+            for (int a = 0; a < MT; a++) {
+                const uint4 lo = *reinterpret_cast<const uint4 *>(sa + ks * SGB_SLAB_BYTES + (16 * a) * 64);
+                const uint4 hi = *reinterpret_cast<const uint4 *>(sa + ks * SGB_SLAB_BYTES + (16 * a + 8) * 64);
+                const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+                    uint32_t dl[4], dh[4];
+                    decode16(wl[wi], pool, dl);
+                    decode16(wh[wi], pool, dh);
+#pragma unroll
+                    for (int n = 0; n < NT; n++) {
+                        mma_u8s8(acc[a][n], dl[0], dh[0], dl[1], dh[1], bf[n][wi].x, bf[n][wi].y);
+                        mma_u8s8(acc[a][n], dl[2], dh[2], dl[3], dh[3], bf[n][wi].z, bf[n][wi].w);
+                    }
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_k(&empty[st]);
+        if (++st == STAGES) { st = 0; ph ^= 1; }
     }
-
-    // C fragment: c0 (row g, limb 2t) c1 (row g, limb 2t+1) c2 (row g+8, limb 2t) c3 (row g+8, limb 2t+1)
-    const int ncols8 = ncol_total * 8;
-#pragma unroll
-    for (int a = 0; a < MT; a++)
-#pragma unroll
-        for (int n = 0; n < NT; n++) {
-            int32_t *o = out + (row0 + 16 * a + g) * ncols8 + (c0 + n) * 8 + 2 * t;
-            if (acc[a][n][0]) atomicAdd(o, acc[a][n][0]);
-            if (acc[a][n][1]) atomicAdd(o + 1, acc[a][n][1]);
-            if (acc[a][n][2]) atomicAdd(o + 8 * ncols8, acc[a][n][2]);
-            if (acc[a][n][3]) atomicAdd(o + 8 * ncols8 + 1, acc[a][n][3]);
-        }
+    if (u0 < u1) flush(cur_tile);
 }
 
-template <int MT, int NT>
-static int launch_pk2(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kblocks, const int8_t *L,
+template <int NT, int KS, int STAGES>
+static int launch_pk2(sgb_ctx *h, int site, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t ksteps, const int8_t *L,
                       int64_t Lcol_stride, int c0, int ncol_total, int32_t *out, pk2_pools pool)
 {
-    const int64_t rows_per_cta = 128 * MT;
-    int64_t row_tiles = rows_pad / rows_per_cta;
-    // aim for >= ~16 CTAs per SM worth of tiles, each at least 8 k-steps long
-    int64_t want_tiles = (int64_t)h->sm_count * 16;      // measured: 8..64 tiles per SM are within 2 % of each other
-    int64_t kchunks = cdiv(want_tiles, row_tiles);
-    if (kchunks < 1) kchunks = 1;
-    int64_t per = cdiv(kblocks, kchunks);
-    if (per < 8) per = 8;
-    if (per > kblocks) per = kblocks;
-    kchunks = cdiv(kblocks, per);
-    for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {
-        int64_t ny = row_tiles - y0 < 65535 ? row_tiles - y0 : 65535;
-        dim3 grid((unsigned)kchunks, (unsigned)ny);
-        pk2_gemm_kernel<MT, NT><<<grid, 256, 0, h->stream>>>(P + y0 * rows_per_cta * stride, stride, kblocks, (int)per, L,
-                                                              Lcol_stride, c0, ncol_total,
-                                                              out + y0 * rows_per_cta * ncol_total * 8, pool);
-        LAUNCH_CHECK(h);
-    }
+    constexpr int RT = 256;
+    constexpr size_t smem = (size_t)STAGES * ((RT / SGB_PANEL_ROWS) * KS * SGB_SLAB_BYTES + NT * KS * 2048);
+    auto kern = pk2_stream_kernel<NT, KS, STAGES>;
+    if (sgb_first_on_device(h->device, site)) CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles = rows_pad / RT, KG = (ksteps + KS - 1) / KS;
+    int64_t grid = (int64_t)h->sm_count * 2;            // persistent: 2 CTAs per SM
+    if (grid > tiles * KG) grid = tiles * KG;
+    kern<<<(unsigned)grid, 288, smem, h->stream>>>(P, stride, tiles, ksteps, L, Lcol_stride, c0, ncol_total, out, pool);
+    LAUNCH_CHECK(h);
     return 0;
 }
 
@@ -452,19 +501,38 @@ int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
     pk2_pools pool;
     if (plane == SGB_PLANE_VALUE) { pool.ax = 0x02000102u; pool.ay = 0x01020001u; pool.bx = 0x01020202u; pool.by = 0x00000101u; }
     else                          { pool.ax = 0x01000101u; pool.ay = 0x01010001u; pool.bx = 0x01010101u; pool.by = 0x00000101u; }
-    if (rows_pad % SGB_ROW_ALIGN || kbytes % SGB_KSTEP_BYTES || stride % SGB_KSTEP_BYTES)
+    if (rows_pad % SGB_ROW_ALIGN || kbytes != stride || stride % SGB_KSTEP_BYTES)
         return sgb_fail(h, "k_pk2_gemm: unaligned operand (rows %lld, kbytes %lld, stride %lld)", (long long)rows_pad,
                         (long long)kbytes, (long long)stride);
-    int64_t kblocks = kbytes / SGB_KSTEP_BYTES;
-    if (kblocks == 0 || rows_pad == 0 || ncol == 0) return 0;
-    int64_t Lcs = kblocks * 2048;
+    int64_t ksteps = kbytes / SGB_KSTEP_BYTES;
+    if (ksteps == 0 || rows_pad == 0 || ncol == 0) return 0;
+    // int32 accumulation: |sum| <= 2 * 64 * (genotypes per row)
+    if (kbytes * 4 > ((int64_t)1 << 24)) return sgb_fail(h, "k_pk2_gemm: %lld genotypes per row exceed the int32 accumulation bound", (long long)(kbytes * 4));
+    int64_t Lcs = ksteps * 2048;
     int c = 0;
     while (c < ncol) {
-        int rem = ncol - c;
-        if (rem >= 4) { SGB_TRY((launch_pk2<4, 4>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 4; }
-        else if (rem >= 2) { SGB_TRY((launch_pk2<4, 2>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 2; }
-        else { SGB_TRY((launch_pk2<4, 1>(h, P, stride, rows_pad, kblocks, L, Lcs, c, ncol, out, pool))); c += 1; }
+        if (ncol - c >= 2) { SGB_TRY((launch_pk2<2, 2, 2>(h, SGB_SITE_STREAM2, P, stride, rows_pad, ksteps, L, Lcs, c, ncol, out, pool))); c += 2; }
+        else { SGB_TRY((launch_pk2<1, 2, 3>(h, SGB_SITE_STREAM1, P, stride, rows_pad, ksteps, L, Lcs, c, ncol, out, pool))); c += 1; }
     }
+    return 0;
+}
+
+// rows of a tiled matrix -> row-major [nrows][nbytes] (variance-ratio markers, Get_OneSNP_Geno)
+__global__ void gather_rows_kernel(const uint8_t *__restrict__ P, int64_t stride, const int64_t *__restrict__ rows, int64_t nbytes,
+                                   uint8_t *__restrict__ out)
+{
+    const int64_t r = rows[blockIdx.y];
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)blockIdx.y * nbytes + b] = P[sgb_tiled_off(r, b, stride)];
+}
+
+int k_gather_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, const int64_t *d_rows, int nrows, int64_t nbytes, uint8_t *d_out)
+{
+    if (nrows <= 0 || nbytes <= 0) return 0;
+    int gx = (int)cdiv(nbytes, 256);
+    if (gx > 64) gx = 64;
+    gather_rows_kernel<<<dim3(gx, nrows), 256, 0, h->stream>>>(P, stride, d_rows, nbytes, d_out);
+    LAUNCH_CHECK(h);
     return 0;
 }
 
@@ -591,13 +659,12 @@ __global__ void rowdot_f64_kernel(const uint8_t *__restrict__ G, int64_t sG, int
     int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (m >= Mloc) return;
     int lane = threadIdx.x & 31;
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(G + m * sG);
     int64_t nw = (N + 15) >> 4;
     for (int c = 0; c < k; c++) {
         const double *b = B + (int64_t)c * ldb;
         double s1 = 0.0, s2 = 0.0;
         for (int64_t w = lane; w < nw; w += 32) {
-            uint32_t x = row[w];
+            uint32_t x = *reinterpret_cast<const uint32_t *>(G + sgb_tiled_off(m, 4 * w, sG));
             int64_t i0 = w << 4;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -636,7 +703,7 @@ __global__ void coldot_f64_kernel(const uint8_t *__restrict__ G, int64_t sG, int
     for (int j = 0; j < 16; j++) acc[j] = 0.0;
     const double *d1 = D1 + (int64_t)c * ldd, *d2 = D2 ? D2 + (int64_t)c * ldd : nullptr;
     for (int64_t m = m0; m < m1; m++) {
-        uint32_t x = *reinterpret_cast<const uint32_t *>(G + m * sG + 4 * w);
+        uint32_t x = *reinterpret_cast<const uint32_t *>(G + sgb_tiled_off(m, 4 * w, sG));
         if (!x) continue;
         double a1 = d1[m], a2 = D2 ? d2[m] : 2.0 * a1;
 #pragma unroll

@@ -181,7 +181,7 @@ __device__ __forceinline__ void umma_issue_loop(int nsteps, int nb, int N, uint3
 
 // grid: x = k-chunks, y = 128-row tiles.  block: 320 threads (8 producer warps, MMA warp, bulk-copy warp).
 // dynamic smem: nb B stages of 256 x N bytes.
-//   P        packed rows (pair-ternary), `stride` bytes each (multiple of 64); rows padded to a multiple of 128
+//   P        packed rows (pair-ternary) in the TILED layout (sgb_tiled_off), `stride` bytes per row (multiple of 64); rows padded to a multiple of 128
 //   L        limb operand as an image of the smem stage: [k-block of 128][N/8][k/16 (8)][n%8 (8)][k%16 (16)] int8
 //   out      int32 [rows][ldo]; this launch covers columns [n0, n0 + N)
 // Warp-specialised pipeline, UMMA_STAGES deep:
@@ -238,14 +238,15 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
         const int grp = warp >> 2, q4 = warp & 3;
         const int64_t row = (int64_t)blockIdx.y * UMMA_ROWS + q4 * 32 + (tid & 31);
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;         // this warp's TMEM lane quarter
-        const uint8_t *prow = P + row * stride + ks0 * 64;
+        // tiled store: this CTA's 128-row tile is one panel; k-slab s of the panel is 8 KB on, the thread's row 64 bytes in
+        const uint8_t *prow = P + (int64_t)blockIdx.y * UMMA_ROWS * stride + ks0 * SGB_SLAB_BYTES + (int64_t)(q4 * 32 + (tid & 31)) * 64;
         u32x8 pf[UMMA_PF][2];
 #pragma unroll
         for (int i = 0; i < UMMA_PF; i++) {
 #pragma unroll
             for (int j = 0; j < 8; j++) { pf[i][0].v[j] = 0; pf[i][1].v[j] = 0; }
             const int sp = grp + i * UMMA_PGROUPS;
-            if (sp < nsteps) { pf[i][0] = ldg_stream_256(prow + (int64_t)sp * 64); pf[i][1] = ldg_stream_256(prow + (int64_t)sp * 64 + 32); }
+            if (sp < nsteps) { pf[i][0] = ldg_stream_256(prow + (int64_t)sp * SGB_SLAB_BYTES); pf[i][1] = ldg_stream_256(prow + (int64_t)sp * SGB_SLAB_BYTES + 32); }
         }
         // the prefetch ring is indexed statically (loop unrolled by UMMA_PF): shifting a register queue would make every
         // step wait for ALL loads in flight
@@ -272,13 +273,13 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
                         tmem_st_x32(tmem_base + lane_base + st * UMMA_A_COLS + hf * 32, a);
                     }
                     if (s + UMMA_PF * UMMA_PGROUPS < nsteps && !(dbg & 4)) {
-                        pf[j][0] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * 64);
-                        pf[j][1] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * 64 + 32);
+                        pf[j][0] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * SGB_SLAB_BYTES);
+                        pf[j][1] = ldg_stream_256(prow + (int64_t)(s + UMMA_PF * UMMA_PGROUPS) * SGB_SLAB_BYTES + 32);
                     }
                     // the register prefetch holds ~100 KB per SM in flight, not enough to cover DRAM latency at full rate:
                     // group 0 also pulls the row's 128-byte line `l2_ahead` steps further on into L2 (one instruction)
-                    if (grp == 0 && s + l2_ahead < nsteps)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(s + l2_ahead) * 64));
+                    if (grp == 0 && !(tid & 1) && s + l2_ahead < nsteps)          // even lanes: one 128-byte line covers two rows
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(s + l2_ahead) * SGB_SLAB_BYTES));
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     // 128 per-thread arrives on one mbarrier serialise (~470 cycles per step measured): one per warp instead

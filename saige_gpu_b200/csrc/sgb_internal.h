@@ -11,6 +11,18 @@
 #define SGB_ROW_ALIGN 512    // row padding of both genotype copies (CTA tile of the tensor kernel)
 #define SGB_SHARD_BLOCK 1024 // markers per block of the block-cyclic marker->rank map
 
+// TILED genotype store (both copies).  A matrix of `rows` x `stride` packed bytes (rows a multiple of 128, stride a multiple
+// of 64) is stored as 128-row PANELS; inside a panel the 64-byte k-slabs (256 genotypes of every row) follow each other, and
+// inside a slab the 128 rows' 64 bytes are contiguous: one (panel, slab) block = 8 KB of consecutive addresses.  A CTA of the
+// sweep kernels therefore streams long contiguous runs (cp.async.bulk of 16 KB per panel and stage) instead of 64-byte
+// segments scattered over 128+ DRAM pages, which is what held the row-major store at 0.84 of the HBM peak.
+#define SGB_PANEL_ROWS 128
+#define SGB_SLAB_BYTES 8192  // SGB_PANEL_ROWS * SGB_KSTEP_BYTES
+__host__ __device__ __forceinline__ int64_t sgb_tiled_off(int64_t row, int64_t byte, int64_t stride)
+{
+    return (row >> 7) * (stride << 7) + (byte >> 6) * SGB_SLAB_BYTES + ((row & 127) << 6) + (byte & 63);
+}
+
 struct sgb_dist;             // NCCL state (dist.cu)
 struct sgb_step2;            // step-2 model state (step2.cu)
 struct sgb_dense;            // stored dense GRM (dense_grm.cu)
@@ -41,8 +53,9 @@ struct sgb_ctx {
 
     // device genotype store, device coding: 2 bits per genotype = number of A1 copies (0,1,2), sample i of a
     // marker in the pair-ternary nibble coding of kernels.cu (sgb_pack4); all padding is genotype 0.
-    uint8_t *dG = nullptr;   int64_t sG = 0, rowsG = 0;   // marker-major  [rowsG][sG],  rowsG>=Mloc
-    uint8_t *dGt = nullptr;  int64_t sT = 0, rowsT = 0;   // sample-major  [rowsT][sT],  rowsT>=N
+    // both copies in the TILED layout (sgb_tiled_off): element (row, byte) of a rows x stride matrix
+    uint8_t *dG = nullptr;   int64_t sG = 0, rowsG = 0;   // marker-major  rowsG x sG,  rowsG>=Mloc
+    uint8_t *dGt = nullptr;  int64_t sT = 0, rowsT = 0;   // sample-major  rowsT x sT,  rowsT>=N
     double *d_f2 = nullptr;  // 2*f_m      per local marker
     double *d_s = nullptr;   // 1/sqrt(2f(1-f)) per local marker
     double *d_s2 = nullptr;  // s_m^2
@@ -110,7 +123,9 @@ int sgb_ensure_f64(sgb_ctx *h, double **p, size_t *cur_elems, size_t need_elems)
 int k_count_markers(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, int64_t nmark, const uint8_t *d_indmask,
                     int32_t *d_ac, int32_t *d_nmiss);
 int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_rows, const int32_t *d_fill,
-             int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_stride);
+             int64_t nrows, const int32_t *d_sub_idx, int identity, int64_t N, uint8_t *d_out, int64_t out_row0, int64_t out_stride,
+             int tiled);   // tiled: d_out is a tiled store (sgb_tiled_off), else row-major with out_stride bytes per row
+int k_gather_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, const int64_t *d_rows, int nrows, int64_t nbytes, uint8_t *d_out);
 int k_transpose(sgb_ctx *h);   // dG -> dGt
 int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, int32_t *d_ac);
 
@@ -176,7 +191,7 @@ int k_grid_blocks(sgb_ctx *h, int64_t n);
 
 // cudaFuncSetAttribute acts on the current device: every launch site that raises a kernel's dynamic shared-memory limit
 // does so once per device ordinal (a process may hold handles on several devices), not once per process
-enum sgb_attr_site { SGB_SITE_REPACK = 0, SGB_SITE_UMMA, SGB_SITE_STEP2, SGB_SITE_SYMV_BASE /* + KC, KC <= 8 */, SGB_SITE_COUNT = SGB_SITE_SYMV_BASE + 9 };
+enum sgb_attr_site { SGB_SITE_REPACK = 0, SGB_SITE_UMMA, SGB_SITE_STEP2, SGB_SITE_STREAM1, SGB_SITE_STREAM2, SGB_SITE_SYMV_BASE /* + KC, KC <= 8 */, SGB_SITE_COUNT = SGB_SITE_SYMV_BASE + 9 };
 inline bool sgb_first_on_device(int device, int site)
 {
     static unsigned char done[SGB_SITE_COUNT][64];
@@ -194,6 +209,7 @@ int sgb_diag_loco_device(sgb_ctx *h);
 int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const double *dB, int k, int maxiter, double tol,
                    int loco, double *dX, int32_t *iters);
 int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n);
+int sgb_allreduce_sum_i32(sgb_ctx *h, int32_t *d, int64_t n);
 int sgb_dist_init(sgb_ctx *h, int rank, int world, const void *id128);
 void sgb_dist_destroy(sgb_ctx *h);
 int sgb_dist_unique_id(void *id128, std::string &err);

@@ -319,26 +319,39 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     CUDA_OK(h, cudaMemcpy(d_sub, sub, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
 
     // ---- pass 1: counts for every raw marker ----
-    // When the raw .bed fits beside the two packed copies it is uploaded ONCE and kept on the device for the re-pack.
+    // One rank: when the raw .bed fits beside the two packed copies it is uploaded ONCE and kept on the device for the
+    // re-pack.  Several ranks: the chunks are dealt round-robin, every rank reads and counts 1/world of the file and the
+    // (allele count, missing count) vectors meet in one int32 allreduce -- the reference's SPMD ranks each read the whole
+    // file (FG.cpp:897-953).
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(M0, ((int64_t)256 << 20) / B0));
     size_t free_b = 0, total_b = 0;
     CUDA_OK(h, cudaMemGetInfo(&free_b, &total_b));
     const size_t raw_total = (size_t)M0 * B0;
-    const bool keep_raw = raw_total * 3 + ((size_t)4 << 30) < free_b;      // raw + marker-major + sample-major copies + slack
+    const bool keep_raw = h->world == 1 && raw_total * 3 + ((size_t)4 << 30) < free_b;      // raw + marker-major + sample-major copies + slack
     uint8_t *d_raw = nullptr; int32_t *d_ac = nullptr, *d_nm = nullptr;
     CUDA_OK(h, cudaMalloc((void **)&d_raw, keep_raw ? raw_total : (size_t)chunk * B0));
     CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * M0));
     CUDA_OK(h, cudaMalloc((void **)&d_nm, sizeof(int32_t) * M0));
+    if (h->world > 1) {
+        CUDA_OK(h, cudaMemsetAsync(d_ac, 0, sizeof(int32_t) * M0, h->stream));
+        CUDA_OK(h, cudaMemsetAsync(d_nm, 0, sizeof(int32_t) * M0, h->stream));
+    }
     stager st;
     SGB_TRY(st.init(h, (size_t)64 << 20));
     std::vector<int32_t> ac_raw(M0), nm_raw(M0);
-    for (int64_t m0 = 0; m0 < M0; m0 += chunk) {
+    int64_t ci = 0;
+    for (int64_t m0 = 0; m0 < M0; m0 += chunk, ci++) {
+        if (h->world > 1 && ci % h->world != h->rank) continue;
         int64_t m1 = std::min(M0, m0 + chunk);
         uint8_t *dst = keep_raw ? d_raw + (size_t)m0 * B0 : d_raw;
         int rc = st.push(rd, m0, m1, dst);
         if (rc) { st.destroy(); return rc; }
         SGB_TRY(k_count_markers(h, dst, B0, m1 - m0, d_indmask, d_ac + m0, d_nm + m0));
         if (!keep_raw) CUDA_OK(h, cudaStreamSynchronize(h->stream));      // the chunk buffer is reused
+    }
+    if (h->world > 1) {
+        SGB_TRY(sgb_allreduce_sum_i32(h, d_ac, M0));
+        SGB_TRY(sgb_allreduce_sum_i32(h, d_nm, M0));
     }
     CUDA_OK(h, cudaMemcpyAsync(ac_raw.data(), d_ac, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaMemcpyAsync(nm_raw.data(), d_nm, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
@@ -385,14 +398,27 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
         }
         if (rows.empty() && vrows.empty()) continue;
         const uint8_t *d_chunk = keep_raw ? d_raw + (size_t)m0 * B0 : d_raw;
-        if (!keep_raw) {                              // second upload of this chunk (raw .bed too large to keep)
-            int rc = st.push(rd, m0, m1, d_raw);
-            if (rc) { st.destroy(); return rc; }
+        if (!keep_raw) {
+            // second read, of the rows this rank keeps only: runs of needed raw markers (gaps below 64 markers are read
+            // through) go to their place in the chunk buffer, so a rank moves ~1/world of the file here as well
+            size_t ia = 0, ib = 0;
+            int64_t run0 = -1, run1 = -1;
+            while (ia < rows.size() || ib < vrows.size() || run0 >= 0) {
+                int64_t nxt = -1;
+                if (ia < rows.size() && (ib >= vrows.size() || rows[ia] <= vrows[ib])) nxt = rows[ia++];
+                else if (ib < vrows.size()) nxt = vrows[ib++];
+                if (nxt >= 0 && run0 >= 0 && nxt < run1 + 64) { run1 = nxt + 1; continue; }
+                if (run0 >= 0) {
+                    int rc = st.push(rd, m0 + run0, m0 + run1, d_raw + (size_t)run0 * B0);
+                    if (rc) { st.destroy(); return rc; }
+                }
+                if (nxt >= 0) { run0 = nxt; run1 = nxt + 1; } else run0 = -1;
+            }
         }
         if (!rows.empty()) {
             CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
             CUDA_OK(h, cudaMemcpyAsync(d_fill, fills.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
-            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG + lrow * h->sG, h->sG));
+            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG, lrow, h->sG, 1));
             CUDA_OK(h, cudaStreamSynchronize(h->stream));
             lrow += (int64_t)rows.size();
         }
@@ -400,7 +426,7 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
             if (!d_vr) CUDA_OK(h, cudaMalloc((void **)&d_vr, (size_t)std::min<int64_t>(chunk, M0) * B));
             CUDA_OK(h, cudaMemcpyAsync(d_rows, vrows.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
             CUDA_OK(h, cudaMemcpyAsync(d_fill, vfills.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
-            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, B));
+            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, 0, B, 0));
             CUDA_OK(h, cudaMemcpyAsync(h->vr_packed.data() + (size_t)vrow * B, d_vr, (size_t)vrows.size() * B, cudaMemcpyDeviceToHost, h->stream));
             CUDA_OK(h, cudaStreamSynchronize(h->stream));
             vrow += (int64_t)vrows.size();
@@ -540,7 +566,10 @@ extern "C" int sgb_get_one_snp_geno(sgb_ctx *h, int64_t idx, int32_t *out)
     bool mine = owns(h, idx);
     if (mine) {
         int64_t r = std::lower_bound(h->loc2glob.begin(), h->loc2glob.end(), idx) - h->loc2glob.begin();
-        CUDA_OK(h, cudaMemcpyAsync(row.data(), h->dG + r * h->sG, B, cudaMemcpyDeviceToHost, h->stream));
+        // row r of the tiled store: 64 bytes in every 8 KB (panel, slab) block of its panel
+        row.resize((size_t)h->sG);
+        CUDA_OK(h, cudaMemcpy2DAsync(row.data(), SGB_KSTEP_BYTES, h->dG + sgb_tiled_off(r, 0, h->sG), SGB_SLAB_BYTES, SGB_KSTEP_BYTES,
+                                     (size_t)(h->sG / SGB_KSTEP_BYTES), cudaMemcpyDeviceToHost, h->stream));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
         h->cnt.bytes_d2h += B;
     }
