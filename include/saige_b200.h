@@ -52,6 +52,20 @@ int sgb_create_dist(int device, int rank, int world, const void *id128, sgb_ctx 
 void sgb_destroy(sgb_ctx *h);                       /* closeGenoFile_plink (FG.cpp:1191-1209) + ~gpuSymMatMult */
 const char *sgb_last_error(sgb_ctx *h);             /* h may be NULL: error of the last failed sgb_create* */
 int sgb_set_engine(sgb_ctx *h, int engine);
+/* verbose != 0: every PCG solve prints the reference's stdout lines, one per right-hand side in the order the reference's
+ * sequential solves would ("iter from getPCG1ofSigmaAndVector <n>", "pcg did not converge. You may increase maxiter
+ * number." -- FG.cpp:2794-2798), so log scrapers written for the reference keep working.  Off by default. */
+int sgb_set_verbose(sgb_ctx *h, int verbose);
+/* Tolerance-driven precision of WIDE batches (k >= 3 columns, the tensor-bound tcgen05 kernel): every right-hand-side value
+ * is the fixed-point integer round(v 2^(8 n - 3 - E)) (E = exponent of the column maximum) written with n signed 8-bit
+ * digits, so the tensor work of a batch is proportional to n.
+ *   n = 7 (default): 55-bit values -- the same integers as the k <= 2 kernel, results exact up to one rounding of the input
+ *                    (2^-54 of the column maximum), bit-identical across engines;
+ *   n = 6 / 5      : 2^-46 / 2^-38 of the column maximum per input element (measured on GRM products: <= 1e-13 / <= 4e-11 of
+ *                    the largest output), inside the 1e-10 gate of the GRM product and far inside the PCG tolerance.
+ * k <= 2 products (HBM-bound) always carry the full 55 bits.  rel_tol variant: the smallest n with 2^-(8n-2) * 16 <= rel_tol. */
+int sgb_set_rhs_limbs(sgb_ctx *h, int n);
+int sgb_set_product_tolerance(sgb_ctx *h, double rel_tol);
 int sgb_device_sync(sgb_ctx *h);
 
 /* ---- configuration set through exports before setgeno ------------------------------------------- */

@@ -38,6 +38,9 @@ _SIGS = {
     "sgb_destroy": (None, [P]),
     "sgb_last_error": (C.c_char_p, [P]),
     "sgb_set_engine": (C.c_int, [P, C.c_int]),
+    "sgb_set_rhs_limbs": (C.c_int, [P, C.c_int]),
+    "sgb_set_verbose": (C.c_int, [P, C.c_int]),
+    "sgb_set_product_tolerance": (C.c_int, [P, C.c_double]),
     "sgb_device_sync": (C.c_int, [P]),
     "sgb_set_min_maf_for_grm": (C.c_int, [P, C.c_float]),
     "sgb_set_max_missing_rate_for_grm": (C.c_int, [P, C.c_float]),

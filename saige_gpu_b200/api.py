@@ -75,6 +75,17 @@ class SaigeB200:
     def set_engine(self, engine):
         self._ck(self._L.sgb_set_engine(self._h, {"tensor": 0, "f64": 1, "umma": 2, "imma": 3}[engine]))
 
+    def set_verbose(self, on=True):
+        """Print the reference's PCG log lines (FG.cpp:2794-2798) from every solve."""
+        self._ck(self._L.sgb_set_verbose(self._h, 1 if on else 0))
+
+    def set_rhs_limbs(self, n):
+        """Digits (5..7) per right-hand-side value of wide batches on the tcgen05 kernel; 7 = full 55-bit values."""
+        self._ck(self._L.sgb_set_rhs_limbs(self._h, int(n)))
+
+    def set_product_tolerance(self, rel_tol):
+        self._ck(self._L.sgb_set_product_tolerance(self._h, float(rel_tol)))
+
     def sync(self):
         self._ck(self._L.sgb_device_sync(self._h))
 

@@ -84,6 +84,7 @@ int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n)
 {
     if (h->world <= 1) return 0;
     if (!h->dist || !h->dist->comm) return sgb_fail(h, "allreduce requested but NCCL communicator is not initialised");
+    SGB_RANGE("nccl_allreduce");
     ncclResult_t r = g_nccl.AllReduce(d, d, (size_t)n, ncclDouble, ncclSum, h->dist->comm, h->stream);
     if (r != ncclSuccess) return sgb_fail(h, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
     h->cnt.n_allreduce++;

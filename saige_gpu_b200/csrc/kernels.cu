@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include "sgb_internal.h"
+#include "recombine.cuh"
 
 #define LAUNCH_CHECK(h)                                                                               \
     do {                                                                                              \
@@ -600,17 +601,19 @@ __global__ void split_limbs_kernel(const double *__restrict__ V, int64_t len, in
 }
 
 int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult,
-                  int32_t *d_limbsum)
+                  int32_t *d_limbsum, int have_stats)
 {
     unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);   // k <= 1024 slots
     if (k > 1024) return sgb_fail(h, "too many columns (%d)", k);
-    CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
-    int gx = (int)cdiv(len, 256 * 8);
-    if (gx > 1024) gx = 1024;
-    if (gx < 1) gx = 1;
-    colmax_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
-    LAUNCH_CHECK(h);
-    CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * SGB_LIMBS * k, h->stream));
+    if (!have_stats) {          // the fused product path (k_col_stats / k_recomb_post1) has left the column maxima and zeroed limb sums
+        CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
+        int gx = (int)cdiv(len, 256 * 8);
+        if (gx > 1024) gx = 1024;
+        if (gx < 1) gx = 1;
+        colmax_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
+        LAUNCH_CHECK(h);
+        CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * SGB_LIMBS * k, h->stream));
+    }
     split_limbs_kernel<<<dim3((unsigned)cdiv(nblk, 4), k), 256, 0, h->stream>>>(V, len, ld, nblk, mx, L, d_mult, d_limbsum);
     LAUNCH_CHECK(h);
     return 0;
@@ -624,19 +627,7 @@ __global__ void recombine_kernel(int32_t *__restrict__ acc, int64_t rows, int k,
     if (idx >= rows * k) return;
     int64_t r = idx / k;
     int c = (int)(idx - r * k);
-    int4 *p = reinterpret_cast<int4 *>(acc + (r * kpad + c) * 8);
-    int4 lo = p[0], hi = p[1];
-    p[0] = make_int4(0, 0, 0, 0);
-    p[1] = make_int4(0, 0, 0, 0);
-    // acc = sum (c0 - plane) * limb  ->  sum plane * limb = c0 * (column limb sum) - acc
-    const int4 *ls = reinterpret_cast<const int4 *>(limbsum + c * 8);
-    int4 s0 = ls[0], s1 = ls[1];
-    lo.x = c0 * s0.x - lo.x; lo.y = c0 * s0.y - lo.y; lo.z = c0 * s0.z - lo.z; lo.w = c0 * s0.w - lo.w;
-    hi.x = c0 * s1.x - hi.x; hi.y = c0 * s1.y - hi.y; hi.z = c0 * s1.z - hi.z; hi.w = c0 * s1.w - hi.w;
-    long long l4 = (long long)lo.x + ((long long)lo.y << 7) + ((long long)lo.z << 14) + ((long long)lo.w << 21);
-    long long h4 = (long long)hi.x + ((long long)hi.y << 7) + ((long long)hi.z << 14) + ((long long)hi.w << 21);
-    double v = (double)h4 * 268435456.0 + (double)l4;    // 128^4 = 2^28; both halves exact (< 2^53)
-    raw[r + (int64_t)c * ld] = v * mult[c];
+    raw[r + (int64_t)c * ld] = sgb_recombine_imma(acc, r, c, kpad, limbsum, c0) * mult[c];
 }
 
 int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, int kpad, const double *d_mult, const int32_t *d_limbsum,
@@ -645,6 +636,186 @@ int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, int kpad, const d
     if (rows * k == 0) return 0;
     recombine_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, kpad, d_mult, d_limbsum,
                                                                            plane == SGB_PLANE_VALUE ? 2 : 1, raw, ld);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused small kernels of a product: 7 launches per k-column product instead of ~19 (at 8 GPUs the dozen 5 us kernels
+// around the two sweeps were 12 % of a product).  Column statistics finish inside the kernel that produces them: every
+// block leaves its partial (sum, max |.|), takes a ticket, and the LAST block of a column reduces the partials in fixed
+// block order -- the same order finish_partials_kernel uses, so results are bit-identical to the unfused path.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_max_256(unsigned long long m, unsigned long long *sm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o);
+        m = x > m ? x : m;
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = m;
+    __syncthreads();
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t = sm[i] > t ? sm[i] : t;
+    return t;
+}
+
+// tail of a statistics kernel: returns true in the last block of column c (all threads), after which psum/pmax of the
+// column are complete and visible
+__device__ __forceinline__ bool stats_ticket(double s, unsigned long long m, int c, double *psum, unsigned long long *pmax,
+                                             unsigned int *ticket, int *last_flag)
+{
+    if (threadIdx.x == 0) {
+        psum[(int64_t)c * SGB_PART_BLOCKS + blockIdx.x] = s;
+        pmax[(int64_t)c * SGB_PART_BLOCKS + blockIdx.x] = m;
+        __threadfence();
+        unsigned int t = atomicAdd(&ticket[c], 1u);
+        *last_flag = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    return *last_flag != 0;
+}
+__device__ __forceinline__ double sum_partials_v(const double *part, int nblk)
+{
+    const volatile double *p = part;
+    double t = 0.0;
+    for (int i = 0; i < nblk; i++) t += p[i];
+    return t;
+}
+__device__ __forceinline__ unsigned long long max_partials_v(const unsigned long long *part, int nblk)
+{
+    const volatile unsigned long long *p = part;
+    unsigned long long t = 0;
+    for (int i = 0; i < nblk; i++) t = p[i] > t ? p[i] : t;
+    return t;
+}
+
+// colsum[c] = sum V[:,c]; mx[c] = bits(max |V[:,c]|); the limb sums of the coming split are zeroed
+__global__ void __launch_bounds__(256) col_stats_kernel(const double *__restrict__ V, int64_t len, int64_t ld, double *__restrict__ psum,
+                                                        unsigned long long *__restrict__ pmax, unsigned int *__restrict__ ticket,
+                                                        double *__restrict__ colsum, unsigned long long *__restrict__ mx,
+                                                        int32_t *__restrict__ limbsum, int nlimb)
+{
+    __shared__ double sm[8];
+    __shared__ unsigned long long smx[8];
+    __shared__ int last;
+    const int c = blockIdx.y;
+    const double *v = V + (int64_t)c * ld;
+    double s = 0.0;
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        double x = v[i];
+        s += x;
+        unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
+        m = b > m ? b : m;
+    }
+    s = block_sum_256(s, sm);
+    m = block_max_256(m, smx);
+    if (!stats_ticket(s, m, c, psum, pmax, ticket, &last)) return;
+    if (threadIdx.x == 0) { colsum[c] = sum_partials_v(psum + (int64_t)c * SGB_PART_BLOCKS, gridDim.x); ticket[c] = 0; }
+    if (threadIdx.x == 32) mx[c] = max_partials_v(pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + nlimb) limbsum[c * nlimb + threadIdx.x - 64] = 0;
+}
+
+int k_col_stats(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, double *d_colsum, int32_t *d_limbsum, int nlimb)
+{
+    unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);
+    int nb = k_grid_blocks(h, len);
+    col_stats_kernel<<<dim3(nb, k), 256, 0, h->stream>>>(V, len, ld, h->d_red, reinterpret_cast<unsigned long long *>(h->d_red) + 1024 * SGB_PART_BLOCKS,
+                                                         h->d_ticket, d_colsum, mx, d_limbsum, nlimb);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// sweep-1 epilogue: D[m,c] = s_m^2 (recombine(acc[m,c]) mult_c - 2f_m sumb_c), zeroed inside [mask_lo, mask_hi) (the
+// left-out chromosome); t_c = sum_m 2f_m D[m,c]; mx[c] = bits(max |D[:,c]|); limb sums of the sweep-2 split zeroed;
+// the accumulators (padding rows included) are reset.  NL = 8: mma.sync engine, 5..7: tcgen05 engine.
+template <int NL>
+__global__ void __launch_bounds__(256) recomb_post1_kernel(int32_t *__restrict__ acc, int64_t rows_pad, int64_t Mloc, int pad,
+                                                           const double *__restrict__ mult, const int32_t *__restrict__ limbsum, int c0,
+                                                           const double *__restrict__ f2, const double *__restrict__ s2,
+                                                           const double *__restrict__ colsum, int64_t mask_lo, int64_t mask_hi,
+                                                           double *__restrict__ D, int64_t ld, double *__restrict__ psum,
+                                                           unsigned long long *__restrict__ pmax, unsigned int *__restrict__ ticket,
+                                                           double *__restrict__ t_out, double *__restrict__ t_out2,
+                                                           unsigned long long *__restrict__ mx, int32_t *__restrict__ limbsum2, int nlimb2)
+{
+    __shared__ double sm[8];
+    __shared__ unsigned long long smx[8];
+    __shared__ int last;
+    const int c = blockIdx.y;
+    const double sb = colsum[c], mu = mult[c];
+    double t = 0.0;
+    unsigned long long m = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += (int64_t)gridDim.x * blockDim.x) {
+        double v = sgb_recombine<NL>(acc, r, c, pad, limbsum, c0) * mu;      // padding rows: zeroes their accumulators
+        if (r < Mloc) {
+            double d = s2[r] * (v - f2[r] * sb);
+            if (r >= mask_lo && r < mask_hi) d = 0.0;
+            D[r + (int64_t)c * ld] = d;
+            t += f2[r] * d;
+            unsigned long long b = (unsigned long long)__double_as_longlong(fabs(d));
+            m = b > m ? b : m;
+        }
+    }
+    t = block_sum_256(t, sm);
+    m = block_max_256(m, smx);
+    if (!stats_ticket(t, m, c, psum, pmax, ticket, &last)) return;
+    if (threadIdx.x == 0) {
+        double tt = sum_partials_v(psum + (int64_t)c * SGB_PART_BLOCKS, gridDim.x);
+        t_out[c] = tt;
+        if (t_out2) t_out2[c] = tt;
+        ticket[c] = 0;
+    }
+    if (threadIdx.x == 32) mx[c] = max_partials_v(pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + nlimb2) limbsum2[c * nlimb2 + threadIdx.x - 64] = 0;
+}
+
+int k_recomb_post1(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, int pad, const double *d_mult, const int32_t *d_limbsum,
+                   const double *d_colsum, int64_t mask_lo, int64_t mask_hi, double *D, int64_t ld, double *d_t, double *d_t2,
+                   int32_t *d_limbsum2, int nlimb2)
+{
+    unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);
+    double *psum = h->d_red;
+    unsigned long long *pmax = reinterpret_cast<unsigned long long *>(h->d_red) + 1024 * SGB_PART_BLOCKS;
+    // the partial-sum pattern over the first Mloc rows must not depend on the padding: blocks as for Mloc elements
+    int nb = k_grid_blocks(h, h->Mloc);
+    dim3 grid(nb, k);
+#define RP1(NLV) recomb_post1_kernel<NLV><<<grid, 256, 0, h->stream>>>(acc, rows_pad, h->Mloc, pad, d_mult, d_limbsum, 2, h->d_f2, h->d_s2, d_colsum, \
+                                                                       mask_lo, mask_hi, D, ld, psum, pmax, h->d_ticket, d_t, d_t2, mx, d_limbsum2, nlimb2)
+    switch (nl) { case 8: RP1(8); break; case 7: RP1(7); break; case 6: RP1(6); break; case 5: RP1(5); break;
+                  default: return sgb_fail(h, "recomb_post1: unsupported limb count %d", nl); }
+#undef RP1
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// sweep-2 epilogue.  Y != null: Y[i,c] = (recombine(acc[i,c]) mult_c - t_c) inv_m  (single GPU);  else raw[i,c] = recombine mult_c
+template <int NL>
+__global__ void __launch_bounds__(256) recomb_post2_kernel(int32_t *__restrict__ acc, int64_t rows_pad, int64_t N, int pad,
+                                                           const double *__restrict__ mult, const int32_t *__restrict__ limbsum, int c0,
+                                                           const double *__restrict__ t, double inv_m, double *__restrict__ Y, int64_t ldy,
+                                                           double *__restrict__ raw, int64_t ldr)
+{
+    const int c = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_pad) return;
+    double v = sgb_recombine<NL>(acc, i, c, pad, limbsum, c0) * mult[c];
+    if (Y) { if (i < N) Y[i + (int64_t)c * ldy] = (v - t[c]) * inv_m; }
+    else raw[i + (int64_t)c * ldr] = v;
+}
+
+int k_recomb_post2(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, int pad, const double *d_mult, const int32_t *d_limbsum,
+                   const double *d_t, double inv_m, double *Y, int64_t ldy, double *raw, int64_t ldr)
+{
+    dim3 grid((unsigned)cdiv(rows_pad, 256), k);
+#define RP2(NLV) recomb_post2_kernel<NLV><<<grid, 256, 0, h->stream>>>(acc, rows_pad, h->N, pad, d_mult, d_limbsum, 2, d_t, inv_m, Y, ldy, raw, ldr)
+    switch (nl) { case 8: RP2(8); break; case 7: RP2(7); break; case 6: RP2(6); break; case 5: RP2(5); break;
+                  default: return sgb_fail(h, "recomb_post2: unsupported limb count %d", nl); }
+#undef RP2
     LAUNCH_CHECK(h);
     return 0;
 }

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include "sgb_internal.h"
+#include "recombine.cuh"
 
 #define UMMA_ROWS 128            // rows per CTA tile = TMEM lanes = MMA M
 #define UMMA_KSTEP 256           // genotypes per pipeline step  (64 packed bytes per row, 8 MMAs of K=32)
@@ -341,7 +342,8 @@ pk2_umma_kernel(const uint8_t *__restrict__ P, int64_t stride, int64_t ksteps_to
 // integer q, hence bit-identical results) -- 1/8 fewer accumulator columns and tensor work per right-hand side.
 // Accumulator column of (column c, limb l) is n = 7 c + l; the image keeps 8 n-rows per 1 KB core-matrix group.
 // One thread per (128-genotype block, TMEM column 0..31): the 4 genotype slots whose k-values share that column.
-#define UMMA_LIMBS 7
+#define UMMA_LIMBS 7             // digits of the full-precision split (the dense-GRM build and the diagonals always use it)
+template <int NL>
 __global__ void split_limbs_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, int k, int ngroups, int64_t nblk,
                                         const unsigned long long *__restrict__ mx, int8_t *__restrict__ L,
                                         double *__restrict__ mult, int32_t *__restrict__ limbsum)
@@ -355,17 +357,19 @@ __global__ void split_limbs_umma_kernel(const double *__restrict__ V, int64_t le
     int E = (int)((mb >> 52) & 0x7FF) - 1023;
     if (E < -1000) E = -1000;
     if (E > 1000) E = 1000;
-    if (u == 0) mult[c] = mb ? scalbn(1.0, E - 53) : 0.0;
+    // |v| < 2^(E+1)  =>  |q| <= 2^(8 NL - 2), inside the range of NL balanced base-256 digits; NL = 7: 53 - E as on the mma.sync engine
+    constexpr int SH = 8 * NL - 3;
+    if (u == 0) mult[c] = mb ? scalbn(1.0, E - SH) : 0.0;
     // slot s of this column is genotype 16 w + {0,8,1,9}[q] + 2 s of the block (the order decode produces)
     const int64_t i0 = blk * UMMA_KBLK + 16 * w + ((q & 1) ? 8 : 0) + ((q & 2) ? 1 : 0);
     long long qv[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         int64_t i = i0 + 2 * s;
-        qv[s] = (inb && i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], 53 - E)) : 0;
+        qv[s] = (inb && i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], SH - E)) : 0;
     }
 #pragma unroll
-    for (int l = 0; l < UMMA_LIMBS; l++) {
+    for (int l = 0; l < NL; l++) {
         uint32_t word = 0;
         int ssum = 0;
 #pragma unroll
@@ -375,15 +379,16 @@ __global__ void split_limbs_umma_kernel(const double *__restrict__ V, int64_t le
             word |= (uint32_t)(d & 255) << (8 * s);
             ssum += d;
         }
-        const int n = UMMA_LIMBS * c + l;
+        const int n = NL * c + l;
         if (inb) *reinterpret_cast<uint32_t *>(L + (blk * (int64_t)ngroups + (n >> 3)) * 1024 + w * 128 + (n & 7) * 16 + 4 * q) = word;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        if ((threadIdx.x & 31) == 0 && ssum) atomicAdd(&limbsum[c * UMMA_LIMBS + l], ssum);
+        if ((threadIdx.x & 31) == 0 && ssum) atomicAdd(&limbsum[c * NL + l], ssum);
     }
 }
 
-// raw[r + c*ld] = (c0 * limbsum - sum_l acc[r][7c+l] 256^l) * mult[c];  the 7 accumulators are reset for the next product
+// raw[r + c*ld] = (c0 * limbsum - sum_l acc[r][NL c+l] 256^l) * mult[c];  the accumulators are reset for the next product
+template <int NL>
 __global__ void recombine_umma_kernel(int32_t *__restrict__ acc, int64_t rows, int k, int npad, const double *__restrict__ mult,
                                       const int32_t *__restrict__ limbsum, int c0, double *__restrict__ raw, int64_t ld)
 {
@@ -391,25 +396,7 @@ __global__ void recombine_umma_kernel(int32_t *__restrict__ acc, int64_t rows, i
     if (idx >= rows * k) return;
     int64_t r = idx / k;
     int c = (int)(idx - r * k);
-    int32_t *p = acc + r * npad + UMMA_LIMBS * c;
-    long long x[UMMA_LIMBS];
-#pragma unroll
-    for (int l = 0; l < UMMA_LIMBS; l++) { x[l] = (long long)c0 * limbsum[c * UMMA_LIMBS + l] - (long long)p[l]; p[l] = 0; }
-    // exact integer sum (up to ~2^81), then ONE correctly rounded conversion: keep 62 leading bits plus a sticky bit, so the
-    // int64 -> fp64 conversion rounds like the exact value would (the mma.sync engine adds two exact halves, also correctly
-    // rounded: both engines return the same bits)
-    const long long l4 = x[0] + (x[1] << 8) + (x[2] << 16) + (x[3] << 24);
-    const long long h3 = x[4] + (x[5] << 8) + (x[6] << 16);
-    const __int128 T = ((__int128)h3 << 32) + (__int128)l4;
-    const bool neg = T < 0;
-    const unsigned __int128 a = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
-    const unsigned long long ahi = (unsigned long long)(a >> 64), alo = (unsigned long long)a;
-    const int bits = ahi ? 128 - __clzll((long long)ahi) : (alo ? 64 - __clzll((long long)alo) : 0);
-    const int shift = bits > 62 ? bits - 62 : 0;
-    unsigned long long m = (unsigned long long)(a >> shift);
-    if (shift && (a & ((((unsigned __int128)1) << shift) - 1))) m |= 1ull;
-    double v = scalbn((double)m, shift);
-    raw[r + (int64_t)c * ld] = (neg ? -v : v) * mult[c];
+    raw[r + (int64_t)c * ld] = sgb_recombine_umma<NL>(acc, r, c, npad, limbsum, c0) * mult[c];
 }
 
 __global__ void colmax_umma_kernel(const double *__restrict__ V, int64_t len, int64_t ld, unsigned long long *__restrict__ mx)
@@ -437,33 +424,42 @@ __global__ void colmax_umma_kernel(const double *__restrict__ V, int64_t len, in
                                                 cudaGetErrorString(e__));                               \
     } while (0)
 
-static inline int umma_npad(int k) { return (UMMA_LIMBS * k + 15) & ~15; }        // accumulator columns: a multiple of 16
+static inline int umma_npad(int k, int nl) { return (nl * k + 15) & ~15; }        // accumulator columns: a multiple of 16
+int k_umma_npad(int k, int nl) { return umma_npad(k, nl); }
 
 // bytes of the UMMA limb operand for k columns (or `nrows` accumulator columns) over `kbytes` packed bytes per row
 size_t k_umma_image_bytes(int nrows, int64_t kbytes)
 {
     return (size_t)(kbytes / 32) * (size_t)(nrows / 8) * 1024;        // kbytes is a multiple of 64 => an even number of 128-genotype blocks
 }
-size_t k_umma_limb_bytes(int k, int64_t kbytes) { return k_umma_image_bytes(umma_npad(k), kbytes); }
+size_t k_umma_limb_bytes(int k, int64_t kbytes) { return k_umma_image_bytes(umma_npad(k, UMMA_LIMBS), kbytes); }
 
+// nl = digits per value (5..7); have_stats: the column maxima are already in d_scal and the limb sums zeroed (fused product path)
 int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t kbytes, double *d_mult,
-                       int32_t *d_limbsum)
+                       int32_t *d_limbsum, int nl, int have_stats)
 {
     unsigned long long *mx = reinterpret_cast<unsigned long long *>(h->d_scal + 2048);
     if (k > 1024) return sgb_fail(h, "too many columns (%d)", k);
-    const int npad = umma_npad(k);
+    if (nl < 5 || nl > 7) return sgb_fail(h, "unsupported limb count %d", nl);
+    const int npad = umma_npad(k, nl);
     const int64_t nblk = kbytes / 32;
-    CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
-    CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * UMMA_LIMBS * k, h->stream));
-    // the padding rows (7k .. npad-1) of the last core-matrix group(s) must read as zero limbs
-    if (npad != UMMA_LIMBS * k) CUDA_OK(h, cudaMemsetAsync(L, 0, k_umma_image_bytes(npad, kbytes), h->stream));
-    int gx = (int)cdiv64(len, 256 * 8);
-    if (gx > 1024) gx = 1024;
-    if (gx < 1) gx = 1;
-    colmax_umma_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
-    UMMA_LAUNCH_CHECK(h);
-    split_limbs_umma_kernel<<<dim3((unsigned)cdiv64(nblk * 32, 256), k), 256, 0, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L,
-                                                                                             d_mult, d_limbsum);
+    if (!have_stats) {
+        CUDA_OK(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * k, h->stream));
+        CUDA_OK(h, cudaMemsetAsync(d_limbsum, 0, sizeof(int32_t) * nl * k, h->stream));
+    }
+    // the padding rows (nl k .. npad-1) of the last core-matrix group(s) must read as zero limbs
+    if (npad != nl * k) CUDA_OK(h, cudaMemsetAsync(L, 0, k_umma_image_bytes(npad, kbytes), h->stream));
+    if (!have_stats) {
+        int gx = (int)cdiv64(len, 256 * 8);
+        if (gx > 1024) gx = 1024;
+        if (gx < 1) gx = 1;
+        colmax_umma_kernel<<<dim3(gx, k), 256, 0, h->stream>>>(V, len, ld, mx);
+        UMMA_LAUNCH_CHECK(h);
+    }
+    dim3 grid((unsigned)cdiv64(nblk * 32, 256), k);
+    if (nl == 7) split_limbs_umma_kernel<7><<<grid, 256, 0, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
+    else if (nl == 6) split_limbs_umma_kernel<6><<<grid, 256, 0, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
+    else split_limbs_umma_kernel<5><<<grid, 256, 0, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
     UMMA_LAUNCH_CHECK(h);
     return 0;
 }
@@ -472,7 +468,7 @@ int k_recombine_umma(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double
                      double *raw, int64_t ld)
 {
     if (rows * k == 0) return 0;
-    recombine_umma_kernel<<<(unsigned)cdiv64(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, umma_npad(k), d_mult, d_limbsum,
+    recombine_umma_kernel<UMMA_LIMBS><<<(unsigned)cdiv64(rows * k, 256), 256, 0, h->stream>>>(acc, rows, k, umma_npad(k, UMMA_LIMBS), d_mult, d_limbsum,
                                                                                    plane == SGB_PLANE_VALUE ? 2 : 1, raw, ld);
     UMMA_LAUNCH_CHECK(h);
     return 0;
@@ -546,9 +542,9 @@ int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_p
     return 0;
 }
 
-// k right-hand sides = 7 k accumulator columns (padded to a multiple of 16)
+// k right-hand sides = nl k accumulator columns (padded to a multiple of 16)
 int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
-               int32_t *out, int plane)
+               int32_t *out, int plane, int nl)
 {
-    return k_pk2_umma_rows(h, P, stride, rows_pad, kbytes, L, umma_npad(k), out, plane);
+    return k_pk2_umma_rows(h, P, stride, rows_pad, kbytes, L, umma_npad(k, nl), out, plane);
 }

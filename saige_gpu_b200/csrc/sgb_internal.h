@@ -1,15 +1,26 @@
 // Internal declarations of libsaige_b200.so (not part of the ABI; the ABI is include/saige_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>     // header-only: ranges are no-ops unless a profiler injects itself (nsys / ncu --nvtx)
 #include <stdint.h>
 #include <string>
 #include <vector>
 #include "saige_b200.h"
 
+// NVTX range around a host-side phase (sweeps, collective, PCG iteration, ingest passes): SGB_RANGE("name");
+struct sgb_nvtx_range {
+    explicit sgb_nvtx_range(const char *name) { nvtxRangePushA(name); }
+    ~sgb_nvtx_range() { nvtxRangePop(); }
+};
+#define SGB_RANGE_CAT2(a, b) a##b
+#define SGB_RANGE_CAT(a, b) SGB_RANGE_CAT2(a, b)
+#define SGB_RANGE(name) sgb_nvtx_range SGB_RANGE_CAT(nvtx_range_, __LINE__)(name)
+
 #define SGB_LIMBS 8          // signed base-128 digits per fp64 value (55-bit fixed point: round(v * 2^(53-E)))
 #define SGB_KSTEP_BYTES 64   // packed bytes (256 genotypes) consumed per k-step of the tensor kernel
 #define SGB_ROW_ALIGN 512    // row padding of both genotype copies (CTA tile of the tensor kernel)
 #define SGB_SHARD_BLOCK 1024 // markers per block of the block-cyclic marker->rank map
+#define SGB_PART_BLOCKS 256   // partial-sum slots per column of the deterministic reductions
 
 // TILED genotype store (both copies).  A matrix of `rows` x `stride` packed bytes (rows a multiple of 128, stride a multiple
 // of 64) is stored as 128-row PANELS; inside a panel the 64-byte k-slabs (256 genotypes of every row) follow each other, and
@@ -32,6 +43,7 @@ struct sgb_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int engine = SGB_ENGINE_TENSOR;
+    int verbose = 0;                                  // print the reference's PCG log lines (sgb_set_verbose)
     int sm_count = 148;
 
     // configuration (FG.cpp:35,99,57-59)
@@ -87,6 +99,9 @@ struct sgb_ctx {
     double *d_ku = nullptr; size_t ku_elems = 0;      // [U | K.U]
     int64_t ku_cols = 0;                              // 0 = nothing cached
     int32_t *d_limbsum = nullptr;                     // [2][1024][8] column limb sums of the current split
+    double *d_red = nullptr;                          // [2][1024][SGB_PART_BLOCKS] per-block partial (sums | maxima) of the fused statistics
+    unsigned int *d_ticket = nullptr;                 // [1024] last-block tickets (zero between kernels)
+    int rhs_limbs = 7;                                // base-256 digits per right-hand-side value on the tcgen05 engine (sgb_set_rhs_limbs)
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_sweep_ms[2] = {0.f, 0.f};
@@ -135,7 +150,14 @@ int k_pk2_gemm(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, i
                int ncol, int32_t *out, int plane);
 // limb preparation: V[len x k] (ld) -> fragments [k][nblk][2048] + per-column multiplier (2^(E-53)) in d_mult[k]
 int k_split_limbs(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t nblk, double *d_mult,
-                  int32_t *d_limbsum);
+                  int32_t *d_limbsum, int have_stats = 0);
+// fused product epilogues (nl = 8: mma.sync engine, 5..7: tcgen05 engine with nl digits)
+int k_col_stats(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, double *d_colsum, int32_t *d_limbsum, int nlimb);
+int k_recomb_post1(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, int pad, const double *d_mult, const int32_t *d_limbsum,
+                   const double *d_colsum, int64_t mask_lo, int64_t mask_hi, double *D, int64_t ld, double *d_t, double *d_t2,
+                   int32_t *d_limbsum2, int nlimb2);
+int k_recomb_post2(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, int pad, const double *d_mult, const int32_t *d_limbsum,
+                   const double *d_t, double inv_m, double *Y, int64_t ldy, double *raw, int64_t ldr);
 // raw[r + c*ld] = recombine(acc[r][c*8..]) * mult[c]; acc zeroed
 int k_recombine(sgb_ctx *h, int32_t *acc, int64_t rows, int k, int kpad, const double *d_mult, const int32_t *d_limbsum,
                 int plane, double *raw, int64_t ld);
@@ -147,9 +169,10 @@ int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_p
 int k_recombine_umma(sgb_ctx *h, int32_t *acc, int64_t rows, int k, const double *d_mult, const int32_t *d_limbsum, int plane,
                      double *raw, int64_t ld);
 int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int k, int8_t *L, int64_t kbytes, double *d_mult,
-                       int32_t *d_limbsum);
+                       int32_t *d_limbsum, int nl = 7, int have_stats = 0);
 int k_pk2_umma(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_pad, int64_t kbytes, const int8_t *L, int k,
-               int32_t *out, int plane);
+               int32_t *out, int plane, int nl = 7);
+int k_umma_npad(int k, int nl);
 
 // f64 engine
 int k_rowdot_f64(sgb_ctx *h, const double *B, int64_t ldb, int k, double *out, int64_t ldo);   // out[m,c]=sum_i g_mi B[i,c]
@@ -187,7 +210,6 @@ int k_rademacher_fill(sgb_ctx *h, double *B, int64_t n, uint64_t seed);
 int k_axpby(sgb_ctx *h, double a, const double *x, double b, const double *y, int64_t n, double *out);
 int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d_count);
 int k_grid_blocks(sgb_ctx *h, int64_t n);
-#define SGB_PART_BLOCKS 256   // partial-sum slots per column of the deterministic reductions
 
 // cudaFuncSetAttribute acts on the current device: every launch site that raises a kernel's dynamic shared-memory limit
 // does so once per device ordinal (a process may hold handles on several devices), not once per process

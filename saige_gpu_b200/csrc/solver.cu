@@ -4,6 +4,7 @@
 // the host sees only scalars (dot products, tau) and the p x p covariance algebra.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -63,56 +64,68 @@ int sgb_crossprod_device(sgb_ctx *h, const double *dB, int k, double *dY, int lo
     double *sc = h->d_scal;
     const bool tensor = h->engine != SGB_ENGINE_F64;
     const bool umma = (h->engine == SGB_ENGINE_UMMA && k >= 2) || (h->engine == SGB_ENGINE_TENSOR && k >= 3);   // wide batches: tcgen05
-    const int kpad = umma ? ((k + 1) & ~1) : k;                     // accumulator columns (UMMA N is a multiple of 16)
-    if (tensor) {
-        size_t lb = umma ? std::max(k_umma_limb_bytes(k, h->sG), k_umma_limb_bytes(k, h->sT)) : (size_t)k * std::max(nblkN, nblkM) * 2048;
-        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, lb));
-        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc1, &h->acc1_elems, (size_t)rowsG * 8 * kpad));
-        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * 8 * kpad));
-    }
     h->cnt.n_crossprod_calls++; h->cnt.n_crossprod_columns += k;
-
-    SGB_TRY(k_colsum(h, dB, N, N, k, sc + SC_COLSUM));
-    // ---- sweep 1: raw1[m,c] = g_m . b_c over the marker-major copy ----
+    SGB_RANGE("grm_product");
     if (tensor) {
-        if (umma) SGB_TRY(k_split_limbs_umma(h, dB, N, N, k, h->d_limb, h->sG, sc + SC_MULT1, h->d_limbsum));
-        else SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1, h->d_limbsum));
+        // ---- tensor engines: 7 launches per product (statistics, split, sweep, epilogue+statistics, split, sweep, epilogue) ----
+        const int nl = umma ? h->rhs_limbs : 8;                           // digits per value: 8 x 7 bits (mma.sync) or nl x 8 bits (tcgen05)
+        const int pad = umma ? k_umma_npad(k, nl) : k;                    // accumulator columns per row (IMMA: x 8)
+        const size_t accw = umma ? (size_t)pad : (size_t)8 * k;
+        size_t lb = umma ? std::max(k_umma_image_bytes(pad, h->sG), k_umma_image_bytes(pad, h->sT)) : (size_t)k * std::max(nblkN, nblkM) * 2048;
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_limb, &h->limb_bytes, lb));
+        // accumulators: every epilogue zeroes what its sweep wrote, so they are all-zero between products
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc1, &h->acc1_elems, (size_t)rowsG * accw));
+        SGB_TRY(ensure_zeroed_i32(h, &h->d_acc2, &h->acc2_elems, (size_t)rowsT * accw));
+        int32_t *ls1 = h->d_limbsum, *ls2 = h->d_limbsum + 8192;
+        SGB_TRY(k_col_stats(h, dB, N, N, k, sc + SC_COLSUM, ls1, nl));
+        // ---- sweep 1: acc1[m,c] = sum_i (2 - g_mi) q_ic over the marker-major copy ----
+        if (umma) SGB_TRY(k_split_limbs_umma(h, dB, N, N, k, h->d_limb, h->sG, sc + SC_MULT1, ls1, nl, 1));
+        else SGB_TRY(k_split_limbs(h, dB, N, N, k, h->d_limb, nblkN, sc + SC_MULT1, ls1, 1));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
-        if (umma) SGB_TRY(k_pk2_umma(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
-        else SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
+        {
+            SGB_RANGE("sweep1_marker_major");
+            if (umma) SGB_TRY(k_pk2_umma(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE, nl));
+            else SGB_TRY(k_pk2_gemm(h, h->dG, h->sG, rowsG, h->sG, h->d_limb, k, h->d_acc1, SGB_PLANE_VALUE));
+        }
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
-        if (umma) SGB_TRY(k_recombine_umma(h, h->d_acc1, rowsG, k, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
-        else SGB_TRY(k_recombine(h, h->d_acc1, rowsG, k, kpad, sc + SC_MULT1, h->d_limbsum, SGB_PLANE_VALUE, raw1, rowsG));
+        // ---- D = s^2 (G b - 2f sum b), left-out chromosome zeroed; t = sum_m 2f D (also appended to raw2 for the allreduce) ----
+        SGB_TRY(k_recomb_post1(h, nl, h->d_acc1, rowsG, k, pad, sc + SC_MULT1, ls1, sc + SC_COLSUM, lo, hi, D, rowsG, sc + SC_T,
+                               h->world > 1 ? raw2 + rowsT * k : nullptr, ls2, nl));
+        // ---- sweep 2: acc2[i,c] = sum_m (2 - g_mi) q'_mc over the sample-major copy ----
+        if (umma) SGB_TRY(k_split_limbs_umma(h, D, h->Mloc, rowsG, k, h->d_limb, h->sT, sc + SC_MULT2, ls2, nl, 1));
+        else SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2, ls2, 1));
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
+        {
+            SGB_RANGE("sweep2_sample_major");
+            if (umma) SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE, nl));
+            else SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
+        }
+        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
+        if (h->world > 1) {
+            // one sum-allreduce per (multi-)product: the N x k partial and the k centring scalars travel together
+            SGB_TRY(k_recomb_post2(h, nl, h->d_acc2, rowsT, k, pad, sc + SC_MULT2, ls2, nullptr, 0.0, nullptr, 0, raw2, rowsT));
+            SGB_TRY(sgb_allreduce_sum(h, raw2, rowsT * k + k));
+            SGB_TRY(k_sweep2_post(h, raw2, rowsT, k, raw2 + rowsT * k, 1.0 / mdiv, dY, N));
+        } else {
+            SGB_TRY(k_recomb_post2(h, nl, h->d_acc2, rowsT, k, pad, sc + SC_MULT2, ls2, sc + SC_T, 1.0 / mdiv, dY, N, nullptr, 0));
+        }
     } else {
+        SGB_TRY(k_colsum(h, dB, N, N, k, sc + SC_COLSUM));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[0], h->stream));
         SGB_TRY(k_rowdot_f64(h, dB, N, k, raw1, rowsG));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[1], h->stream));
-    }
-    // ---- D = s^2 (raw1 - 2f sum b), left-out chromosome zeroed; t = sum_m 2f D ----
-    SGB_TRY(k_sweep1_post(h, raw1, rowsG, k, sc + SC_COLSUM, lo, hi, D, sc + SC_T));
-    // ---- sweep 2: raw2[i,c] = sum_m g_mi D[m,c] over the sample-major copy ----
-    if (tensor) {
-        if (umma) SGB_TRY(k_split_limbs_umma(h, D, h->Mloc, rowsG, k, h->d_limb, h->sT, sc + SC_MULT2, h->d_limbsum + 8192));
-        else SGB_TRY(k_split_limbs(h, D, h->Mloc, rowsG, k, h->d_limb, nblkM, sc + SC_MULT2, h->d_limbsum + 8192));
-        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
-        if (umma) SGB_TRY(k_pk2_umma(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
-        else SGB_TRY(k_pk2_gemm(h, h->dGt, h->sT, rowsT, h->sT, h->d_limb, k, h->d_acc2, SGB_PLANE_VALUE));
-        if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
-        if (umma) SGB_TRY(k_recombine_umma(h, h->d_acc2, rowsT, k, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
-        else SGB_TRY(k_recombine(h, h->d_acc2, rowsT, k, kpad, sc + SC_MULT2, h->d_limbsum + 8192, SGB_PLANE_VALUE, raw2, rowsT));
-    } else {
+        SGB_TRY(k_sweep1_post(h, raw1, rowsG, k, sc + SC_COLSUM, lo, hi, D, sc + SC_T));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[2], h->stream));
         SGB_TRY(k_coldot_f64(h, D, nullptr, rowsG, k, raw2, rowsT));
         if (h->time_sweeps) CUDA_OK(h, cudaEventRecord(h->ev[3], h->stream));
+        const double *tvec = sc + SC_T;
+        if (h->world > 1) {
+            CUDA_OK(h, cudaMemcpyAsync(raw2 + rowsT * k, sc + SC_T, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
+            SGB_TRY(sgb_allreduce_sum(h, raw2, rowsT * k + k));
+            tvec = raw2 + rowsT * k;
+        }
+        SGB_TRY(k_sweep2_post(h, raw2, rowsT, k, tvec, 1.0 / mdiv, dY, N));
     }
-    const double *tvec = sc + SC_T;
-    if (h->world > 1) {
-        // one sum-allreduce per (multi-)product: the N x k partial and the k centring scalars travel together
-        CUDA_OK(h, cudaMemcpyAsync(raw2 + rowsT * k, sc + SC_T, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
-        SGB_TRY(sgb_allreduce_sum(h, raw2, rowsT * k + k));
-        tvec = raw2 + rowsT * k;
-    }
-    SGB_TRY(k_sweep2_post(h, raw2, rowsT, k, tvec, 1.0 / mdiv, dY, N));
     if (h->time_sweeps) {
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
         cudaEventElapsedTime(&h->last_sweep_ms[0], h->ev[0], h->ev[1]);
@@ -252,7 +265,9 @@ int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const doubl
     std::vector<int> act, it(k, 0);
     for (int c = 0; c < k; c++) if (h->h_scal[c] > tol) act.push_back(c);
     int cur = 0, iter = 0;
+    SGB_RANGE("pcg_solve");
     while (!act.empty() && iter < maxiter) {
+        SGB_RANGE("pcg_iteration");
         iter++;
         int na = (int)act.size();
         CUDA_OK(h, cudaMemcpyAsync(h->d_idx, act.data(), sizeof(int) * na, cudaMemcpyHostToDevice, h->stream));
@@ -276,6 +291,15 @@ int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const doubl
         act.swap(next);
     }
     for (int c = 0; c < k; c++) { h->cnt.n_pcg_solves++; h->cnt.n_pcg_iterations += it[c]; if (iters) iters[c] = it[c]; }
+    if (h->verbose) {
+        // the reference's log lines, one per right-hand side in the order its sequential solves would print them
+        // (FG.cpp:2794-2798); downstream log scrapers read them
+        for (int c = 0; c < k; c++) {
+            if (it[c] >= maxiter) printf("pcg did not converge. You may increase maxiter number.\n");
+            printf("iter from getPCG1ofSigmaAndVector %d\n", it[c]);
+        }
+        fflush(stdout);
+    }
     return 0;
 }
 

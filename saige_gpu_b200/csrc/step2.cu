@@ -588,7 +588,7 @@ struct sgb_step2 {
     uint8_t *d_bed = nullptr; size_t bed_bytes = 0;
     double *d_out = nullptr; size_t out_elems = 0;
     uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
-    double *pout[2] = {nullptr, nullptr};
+    double *pout[2] = {nullptr, nullptr}; size_t pout_bytes = 0;      // capacities tracked apart: the chunk length depends on n_fam
     cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
@@ -738,16 +738,16 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)256 << 20) / B0));
     const size_t cbytes = (size_t)chunk * B0, obytes = sizeof(double) * (size_t)chunk * S2_NOUT;
     if (!s->pin[0] || s->pin_bytes < cbytes) {
-        for (int i = 0; i < 2; i++) {
-            if (s->pin[i]) cudaFreeHost(s->pin[i]);
-            if (s->pout[i]) cudaFreeHost(s->pout[i]);
-            s->pin[i] = nullptr; s->pout[i] = nullptr;
-        }
-        for (int i = 0; i < 2; i++) {
-            CUDA_OK(h, cudaMallocHost((void **)&s->pin[i], cbytes));
-            CUDA_OK(h, cudaMallocHost((void **)&s->pout[i], obytes));
-        }
+        for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); s->pin[i] = nullptr; }
+        s->pin_bytes = 0;
+        for (int i = 0; i < 2; i++) CUDA_OK(h, cudaMallocHost((void **)&s->pin[i], cbytes));
         s->pin_bytes = cbytes;
+    }
+    if (!s->pout[0] || s->pout_bytes < obytes) {      // a later call with fewer samples per row has MORE markers per chunk
+        for (int i = 0; i < 2; i++) { if (s->pout[i]) cudaFreeHost(s->pout[i]); s->pout[i] = nullptr; }
+        s->pout_bytes = 0;
+        for (int i = 0; i < 2; i++) CUDA_OK(h, cudaMallocHost((void **)&s->pout[i], obytes));
+        s->pout_bytes = obytes;
     }
     for (int i = 0; i < 2; i++) if (!s->ev[i]) CUDA_OK(h, cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
     SGB_TRY(sgb_ensure(h, (void **)&s->d_bed, &s->bed_bytes, 2 * cbytes));

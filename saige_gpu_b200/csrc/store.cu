@@ -69,6 +69,9 @@ static int create_common(int device, sgb_ctx **out)
     if (cudaMalloc((void **)&h->d_scal, sizeof(double) * 8192) != cudaSuccess ||
         cudaMalloc((void **)&h->d_idx, sizeof(int) * 8192) != cudaSuccess ||
         cudaMalloc((void **)&h->d_limbsum, sizeof(int32_t) * 16384) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_red, sizeof(double) * 2 * 1024 * SGB_PART_BLOCKS) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_ticket, sizeof(unsigned int) * 1024) != cudaSuccess ||
+        cudaMemset(h->d_ticket, 0, sizeof(unsigned int) * 1024) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_scal, sizeof(double) * 8192) != cudaSuccess) {
         delete h;
         return sgb_fail(nullptr, "scalar scratch allocation failed");
@@ -119,7 +122,7 @@ extern "C" void sgb_destroy(sgb_ctx *h)
     sgb_dist_destroy(h);
     sgb_step2_free(h);
     free_store(h);
-    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx, h->d_limbsum, h->d_ku};
+    void *ptrs[] = {h->ws, h->d_acc1, h->d_acc2, h->d_limb, h->d_tmp, h->d_scal, h->d_io, h->d_bench, h->d_pcg, h->d_ai, h->d_idx, h->d_limbsum, h->d_ku, h->d_red, h->d_ticket};
     for (auto p : ptrs) if (p) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -133,6 +136,21 @@ extern "C" int sgb_set_engine(sgb_ctx *h, int engine)
     h->engine = engine;
     h->diag_ready = false; h->diag_loco_ready = false; h->ku_cols = 0;
     return 0;
+}
+extern "C" int sgb_set_verbose(sgb_ctx *h, int verbose) { h->verbose = verbose; return 0; }
+extern "C" int sgb_set_rhs_limbs(sgb_ctx *h, int n)
+{
+    if (n < 5 || n > 7) return sgb_fail(h, "sgb_set_rhs_limbs: %d digits not supported (5, 6 or 7)", n);
+    if (n != h->rhs_limbs) h->ku_cols = 0;          // the cached K.U was computed at another precision
+    h->rhs_limbs = n;
+    return 0;
+}
+extern "C" int sgb_set_product_tolerance(sgb_ctx *h, double rel_tol)
+{
+    if (!(rel_tol >= 0)) return sgb_fail(h, "sgb_set_product_tolerance: bad tolerance");
+    int n = 7;
+    for (int c = 5; c <= 7; c++) if (ldexp(16.0, -(8 * c - 2)) <= rel_tol) { n = c; break; }
+    return sgb_set_rhs_limbs(h, n);
 }
 extern "C" int sgb_device_sync(sgb_ctx *h) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaStreamSynchronize(h->stream)); return 0; }
 extern "C" int sgb_set_min_maf_for_grm(sgb_ctx *h, float v) { h->minMAF = v; return 0; }
@@ -319,6 +337,7 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     CUDA_OK(h, cudaMemcpy(d_sub, sub, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
 
     // ---- pass 1: counts for every raw marker ----
+    nvtxRangePushA("setgeno_pass1_count");
     // One rank: when the raw .bed fits beside the two packed copies it is uploaded ONCE and kept on the device for the
     // re-pack.  Several ranks: the chunks are dealt round-robin, every rank reads and counts 1/world of the file and the
     // (allele count, missing count) vectors meet in one int32 allreduce -- the reference's SPMD ranks each read the whole
@@ -357,6 +376,7 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     CUDA_OK(h, cudaMemcpyAsync(nm_raw.data(), d_nm, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
 
+    nvtxRangePop();
     // ---- host QC (fp32, reference order) ----
     h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
     h->afreq_vr.clear(); h->invstd_vr.clear(); h->mac_vr.clear(); h->ac_vr.clear(); h->index_vr.clear();
@@ -384,6 +404,7 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     h->vr_packed.assign((size_t)h->Mvr * B, 0);
 
     // ---- pass 2: re-pack kept rows ----
+    SGB_RANGE("setgeno_pass2_repack");
     uint8_t *d_vr = nullptr; int32_t *d_rows = nullptr, *d_fill = nullptr;
     CUDA_OK(h, cudaMalloc((void **)&d_rows, sizeof(int32_t) * chunk));
     CUDA_OK(h, cudaMalloc((void **)&d_fill, sizeof(int32_t) * chunk));
