@@ -286,14 +286,19 @@ def main():
     launches = g.counters()["n_kernel_launches"]
     total_ms = max_over_ranks(float(ms.sum()))
     value = K / (total_ms * 1e-3)
+    # per-step list = max over ranks of every step (one straggler step must be visible, not own the number silently)
+    step_list = [max_over_ranks(float(v)) for v in ms]
+    step_median = float(np.median(step_list))
     sweep_ms = float(mk.sum()) / (2 * K)                   # average duration of one pk2_gemm launch
     bytes_launch = Mloc * Bbytes                           # algorithmic bytes of one sweep: the packed shard, once
     peak, peak_src = measured_hbm_peak()
-    traffic = None
+    # dram__bytes_read + write of ONE launch of the sweep kernel from the committed ncu --set full capture of this command
+    # (profiles/r02_traffic.json names the capture); null when no capture exists for this workload / GPU count
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
-        if tj and tj["n_gpus"] == world and args.engine == "tensor":
-            traffic = tj["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("%s@%d" % (args.workload, world))
+        if tj and args.engine == "tensor":
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
     achieved = bytes_launch / (sweep_ms * 1e-3) / 1e9
@@ -302,13 +307,26 @@ def main():
     # ---- batched products (the Hutchinson probes + phenotype ride in ONE multi-vector product) ----
     batched = []
     for kb in sorted(set([4, 8, args.k_batch])):
-        g.bench_crossprod_device(kb, 1)
-        barrier()
-        msb, _ = g.bench_crossprod_device(kb, max(3, K // 2))
-        barrier()
-        bms = max_over_ranks(float(msb.mean()))
-        batched.append({"k": kb, "ms_per_product": bms, "columns_per_s": kb / (bms * 1e-3),
-                        "kernel": "pk2_umma_kernel (tcgen05, tensor-bound)" if args.engine == "tensor" else args.engine})
+        row = {"k": kb, "kernel": "pk2_umma_kernel (tcgen05)" if args.engine == "tensor" else args.engine}
+        for digits in (7, 5):
+            g.set_rhs_limbs(digits)
+            g.bench_crossprod_device(kb, 1)
+            barrier()
+            msb, _ = g.bench_crossprod_device(kb, max(3, K // 2))
+            barrier()
+            bms = max_over_ranks(float(msb.mean()))
+            npad = (digits * kb + 15) // 16 * 16
+            alg_bytes = 2 * Mloc * Bbytes + 16 * N * kb + 16 * Mloc * (kb + 1)
+            row["digits%d" % digits] = {
+                "ms_per_product": bms, "columns_per_s": kb / (bms * 1e-3),
+                "hbm_frac_algorithmic": alg_bytes / (bms * 1e-3) / 1e9 / measured_hbm_peak()[0],
+                "algorithmic_int8_ops": 2 * 2.0 * Mloc * N * kb,            # one pass, one int8 MAC pair per genotype and column
+                "issued_int8_ops": 2 * 2.0 * Mloc * N * npad,               # what the limb split makes the tensor pipe do
+                "issued_tops": 2 * 2.0 * Mloc * N * npad / (bms * 1e-3) / 1e12}
+        g.set_rhs_limbs(7)
+        row["ms_per_product"] = row["digits7"]["ms_per_product"]
+        row["note"] = "digits7 = exact 55-bit right-hand sides (bit-identical to the k=1 kernel); digits5 = sgb_set_product_tolerance(1e-10)"
+        batched.append(row)
 
     # ---- end-to-end leg: the public C-ABI call on pinned host vectors ----
     hb = torch.empty(N, dtype=torch.float64).pin_memory()
@@ -328,7 +346,7 @@ def main():
     t_e2e = max_over_ranks(time.perf_counter() - t_e2e0)
     barrier()
     e2e_value = K / t_e2e
-    checksum = float(hy.sum())
+    y_norm2 = float(np.sqrt(float((hy.double() ** 2).sum())))      # ||K b||_2 of the fixed probe b: must agree across N
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- extras on rank 0: CPU baseline beside it, step-1 wall time ----
@@ -440,7 +458,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "grm_matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "ms_per_step_median": step_median, "ms_per_step_list": step_list, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int8 tensor-core limbs, exact int32 accumulate, fp64 recombine" if args.engine == "tensor" else "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "n_samples": N, "n_markers": M, "markers_per_gpu": int(Mloc), "k": 1,
@@ -448,10 +466,10 @@ def main():
                        "sharding": "block-cyclic markers, 1 NCCL allreduce of N fp64 per product" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
-                    "api": "sgb_get_crossprod_mat_and_kin (host pinned vectors)", "checksum": checksum},
+                    "api": "sgb_get_crossprod_mat_and_kin (host pinned vectors)", "y_norm2": y_norm2},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "pk2_gemm_kernel", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "pk2_stream_kernel<1,2,3>", "peak_source": peak_src,
                          "bytes_per_launch": int(bytes_launch), "avg_launch_ms": sweep_ms,
                          "sweep1_ms": float(mk[:, 0].mean()), "sweep2_ms": float(mk[:, 1].mean()),
                          "whole_product_frac": bytes_alg_product / (total_ms / K * 1e-3) / 1e9 / peak},

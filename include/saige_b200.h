@@ -212,6 +212,11 @@ int sgb_step2_set_condition(sgb_ctx *h, int n_cond, const double *P2, const doub
  * ratio (order-dependent); here it belongs to the first category.  n_cate == 1: the single ratio of sgb_step2_set_model. */
 int sgb_step2_set_variance_ratios(sgb_ctx *h, int n_cate, const double *ratios, const double *min_mac_exclude,
                                   const double *max_mac_include);
+/* enable != 0 (default): the score sums of a chunk of variants are computed as ONE skinny GEMM on the tensor engine (packed
+ * 2-bit variant rows x the 2p+3 model columns, exact integer accumulation) and only the variants that need a pass of their
+ * own (saddle-point approximation, exact test, Firth, conditional analysis) run the per-variant kernel.  0: every variant
+ * through the per-variant kernel (the round-1 path, kept as the on-device cross-check). */
+int sgb_step2_set_batched(sgb_ctx *h, int enable);
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
 /* The same marker loop for dosage rows (Unified_getOneMarker's VCF / BGEN branches, Main.cpp:584-700; VCF.cpp:120-256,

@@ -75,6 +75,10 @@ class SaigeB200:
     def set_engine(self, engine):
         self._ck(self._L.sgb_set_engine(self._h, {"tensor": 0, "f64": 1, "umma": 2, "imma": 3}[engine]))
 
+    def setStep2Batched(self, on=True):
+        """Step-2 score sums as one tensor-engine GEMM per chunk (default) or every variant through the per-variant kernel."""
+        self._ck(self._L.sgb_step2_set_batched(self._h, 1 if on else 0))
+
     def set_verbose(self, on=True):
         """Print the reference's PCG log lines (FG.cpp:2794-2798) from every solve."""
         self._ck(self._L.sgb_set_verbose(self._h, 1 if on else 0))

@@ -502,7 +502,7 @@ int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_p
     const int use_atomic = (kchunks > 1 || h->umma_accumulate) ? 1 : 0;
     if (sgb_first_on_device(h->device, SGB_SITE_UMMA)) {
         CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(pk2_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
 #ifdef SGB_ABLATION          // timing experiments only (make ABLATION=1): the product build reads no environment
     static const int force_stages = getenv("SGB_UMMA_STAGES") ? atoi(getenv("SGB_UMMA_STAGES")) : 0;
@@ -510,19 +510,24 @@ int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_p
 #else
     const int force_stages = 0, dbg = 0;
 #endif
-    // balanced passes of N <= 128 accumulator columns (multiples of 16): 224 columns run as 112 + 112
-    const int npass = (nrows + 127) / 128;
+    // Balanced passes of N <= 256 accumulator columns (multiples of 16).  Measured (profiles/r02_sweep_digits*.txt, ncu
+    // r02_pk2_umma_k31_d5): with the A operand in tensor memory an M = 128, K = 32 MMA costs about N/2 + 25 cycles, so two
+    // N = 112 passes (k = 31 at 7 digits) take 2 x 8.0 ms where ONE N = 224 pass needs ~ 11: wide batches run as few passes as
+    // the 512 TMEM columns allow (3 A stages of 64 columns + N <= 256 accumulator columns, one CTA per SM); N <= 128 keeps
+    // two CTAs per SM on 256 columns each.
+    const int npass = (nrows + 255) / 256;
     const int per_pass = (((nrows + npass - 1) / npass) + 15) & ~15;
     const int ngroups = nrows / 8;
     for (int n0 = 0; n0 < nrows; n0 += per_pass) {
         const int N = nrows - n0 < per_pass ? nrows - n0 : per_pass;
-        // three A stages let the producers run a full step ahead of the MMAs; they fit 256 TMEM columns (2 CTAs per SM) for N <= 64
-        int stages = (N <= 64) ? 3 : 2;
+        // three A stages let the producers run a full step ahead of the MMAs
+        int stages = (N <= 64 || N > 128) ? 3 : 2;
         if (force_stages == 2 || force_stages == 3) stages = force_stages;
         int tmem_cols = stages * UMMA_A_COLS + N <= 256 ? 256 : 512;
         int nb = (96 * 1024) / (UMMA_KSTEP * N);                // B ring depth (stages of 256 x N bytes)
         if (nb > UMMA_MAX_BSTAGES) nb = UMMA_MAX_BSTAGES;
         if (nb < 2) nb = 2;
+        if (tmem_cols == 512 && nb < 3) nb = 3;                  // > 114 KB of shared memory: exactly one CTA (one 512-column allocation) per SM
         // the image interleaves all core-matrix groups per k-block: this pass starts at group n0 / 8
         const int8_t *Lp = L + (int64_t)(n0 / 8) * 1024;
         for (int64_t y0 = 0; y0 < row_tiles; y0 += 65535) {

@@ -111,7 +111,8 @@ struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + no
 template <bool IDENT, bool DOSE>
 __global__ void __launch_bounds__(S2_THREADS, IDENT ? 3 : 2)
 step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
-             double max_missing, int se_two_sided, double *__restrict__ out, s2_dose DS)
+             double max_missing, int se_two_sided, double *__restrict__ out, s2_dose DS, const int *__restrict__ list,
+             const int *__restrict__ list_count)
 {
     static_assert(!(IDENT && DOSE), "dosage rows are always indexed");
     extern __shared__ uint8_t srow[];
@@ -119,7 +120,9 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     __shared__ double Zs[S2_MAXP], Ws[S2_MAXP];
     __shared__ int er_cnt, er_idx[SGB_ER_MAXK];
     __shared__ double er_pv;
-    const int64_t m = blockIdx.x;
+    // batched path: only the variants the score-sum pass flagged (SPA / exact test / Firth / conditional) come here
+    if (list && (int)blockIdx.x >= *list_count) return;
+    const int64_t m = list ? (int64_t)list[blockIdx.x] : (int64_t)blockIdx.x;
     if (m >= nm) return;
     const int tid = threadIdx.x, p = M.p;
     const int64_t N = M.N;
@@ -576,6 +579,217 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Batched score sums on the tensor engine ("the score statistics are a skinny GEMM over a variant batch").
+//
+// For a chunk of variants the sums scoreTestFast needs,
+//     Z = A^T g (p)   W = (mu2 X)^T g (p)   R0 = res.g   T1 = sum mu2 g^2 = mu2.g + 2 mu2.[g == 2]
+// are "packed 2-bit rows x (2p + 2) fp64 columns" on the VALUE plane plus one column on the [g == 2] plane: the same
+// contraction as a GRM sweep, with variants as rows and samples as the contraction index.  The chunk is re-packed on the
+// device into the pair-ternary tiled store (missing calls filled with the variant's best-guess genotype, raw alt-allele
+// coding), pk2_umma_kernel / pk2_stream_kernel contract it against limb images of the model columns that are built once
+// per model, and one thread per variant finishes the test.  Allele flips are applied algebraically to the sums
+// (g' = 2 - g is linear; [g' == 2] = 1 - g + [g == 2]).  Only variants that need a pass of their own -- saddle-point
+// approximation (|z| > SPAcutoff), exact test, Firth, conditional analysis -- go through step2_kernel afterwards.
+// ---------------------------------------------------------------------------------------------------
+// identity-ordered raw rows for a model whose samples are a subset / permutation of the .fam
+__global__ void s2_gather_kernel(const uint8_t *__restrict__ bed, int64_t B0, const int32_t *__restrict__ pos, int64_t N,
+                                 int64_t B, uint8_t *__restrict__ out)
+{
+    const int64_t m = blockIdx.y;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint8_t *row = bed + m * B0;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = 4 * b + j;
+        uint32_t code = 3u;                                  // padding: hom ref = genotype 0 of the tested (first) allele
+        if (i < N) { const int32_t src = pos[i]; code = (row[src >> 2] >> ((src & 3) << 1)) & 3u; }
+        v |= code << (2 * j);
+    }
+    out[m * B + b] = (uint8_t)v;
+}
+
+// class counts of one variant over the model's samples: hom-alt / het / missing among all and among cases (popcounts)
+__global__ void __launch_bounds__(256) s2_count_kernel(const uint8_t *__restrict__ bed, int64_t B0, int64_t N,
+                                                       const uint32_t *__restrict__ ycase, int32_t *__restrict__ cnt)
+{
+    __shared__ int sm[6][8];
+    const int64_t m = blockIdx.x;
+    const int64_t nw = (N + 15) >> 4;
+    const uint8_t *row = bed + m * B0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 3) == 0);
+    int c[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t w = threadIdx.x; w < nw; w += 256) {
+        uint32_t x;
+        if (aligned && 4 * w + 4 <= B0) x = *reinterpret_cast<const uint32_t *>(row + 4 * w);
+        else { x = 0; for (int j = 0; j < 4; j++) if (4 * w + j < B0) x |= (uint32_t)row[4 * w + j] << (8 * j); }
+        uint32_t valid = 0x55555555u;
+        if (w == nw - 1 && (N & 15)) valid &= (1u << (2 * (N & 15))) - 1u;
+        const uint32_t L = x & 0x55555555u, H = (x >> 1) & 0x55555555u;
+        const uint32_t homalt = ~L & ~H & valid, het = H & ~L & valid, miss = L & ~H & valid;      // PLINK.hpp:48-56, alt-first
+        const uint32_t yc = ycase[w];
+        c[0] += __popc(homalt); c[1] += __popc(het); c[2] += __popc(miss);
+        c[3] += __popc(homalt & yc); c[4] += __popc(het & yc); c[5] += __popc(miss & yc);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
+        if ((threadIdx.x & 31) == 0) sm[q][threadIdx.x >> 5] = c[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        int t = 0;
+        for (int i = 0; i < 8; i++) t += sm[threadIdx.x][i];
+        cnt[m * 6 + threadIdx.x] = t;
+    }
+}
+
+struct s2_head { double altFreq0, missingRate, altFreq; int pass, flip, imputeG; };
+// getOneMarker's frequencies, the filter of Main.cpp:296 and imputeGenoAndFlip's decisions from the class counts
+__device__ __forceinline__ s2_head s2_head_of(const int32_t *c, int64_t N, double min_maf, double min_mac, double max_missing)
+{
+    s2_head h;
+    const double k2a = c[0], k1a = c[1], nMiss = c[2];
+    const double altCounts0 = 2.0 * k2a + k1a, cntv = (double)N - nMiss;
+    h.altFreq0 = cntv > 0 ? altCounts0 / cntv / 2.0 : 0.0;
+    h.missingRate = nMiss / (double)N;
+    const double MAF = fmin(h.altFreq0, 1.0 - h.altFreq0);
+    const double MAC0 = MAF * (double)N * (1.0 - h.missingRate) * 2.0;
+    h.pass = !(h.missingRate > max_missing || MAF < min_maf || MAC0 < min_mac);
+    h.flip = h.altFreq0 > 0.5;
+    h.altFreq = h.flip ? 1.0 - h.altFreq0 : h.altFreq0;
+    h.imputeG = nMiss > 0 ? (int)round(2.0 * h.altFreq) : 0;
+    return h;
+}
+
+// raw PLINK rows -> pair-ternary tiled store (rows = variants, contraction index = model samples), raw alt-allele coding,
+// missing calls = the best-guess genotype of the variant; rows beyond nm and samples beyond N are genotype 0.
+// One thread per 32-bit word (16 samples); byte translation through a shared-memory table [fill][byte].
+__global__ void __launch_bounds__(256) s2_repack_kernel(const uint8_t *__restrict__ bed, int64_t B0, int64_t N, int64_t nm,
+                                                        const int32_t *__restrict__ cnt, double min_maf, double min_mac,
+                                                        double max_missing, uint8_t *__restrict__ out, int64_t stride)
+{
+    __shared__ uint8_t lut[3][256];
+    for (int idx = threadIdx.x; idx < 768; idx += 256) {
+        const int fill = idx >> 8, byte = idx & 255;
+        int g[4];
+        for (int j = 0; j < 4; j++) {
+            const int code = (byte >> (2 * j)) & 3;
+            g[j] = code == 0 ? 2 : (code == 2 ? 1 : (code == 3 ? 0 : fill));
+        }
+        lut[fill][byte] = (uint8_t)((g[0] + 3 * g[1]) | ((g[2] + 3 * g[3]) << 4));
+    }
+    __syncthreads();
+    const int64_t m = blockIdx.y;
+    const int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (4 * w >= stride) return;
+    uint32_t o = 0;
+    if (m < nm) {
+        const s2_head hd = s2_head_of(cnt + m * 6, N, min_maf, min_mac, max_missing);
+        const int fill_raw = hd.flip ? 2 - hd.imputeG : hd.imputeG;
+        const uint8_t *row = bed + m * B0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t b = 4 * w + j;
+            uint32_t byte = b < B0 ? row[b] : 0xFFu;
+            const int64_t i0 = 4 * b;
+            if (i0 + 4 > N) {                                     // samples beyond N: code 11 = genotype 0
+                for (int q = 0; q < 4; q++) if (i0 + q >= N) byte |= 3u << (2 * q);
+            }
+            o |= (uint32_t)lut[fill_raw][byte] << (8 * j);
+        }
+    }
+    *reinterpret_cast<uint32_t *>(out + sgb_tiled_off(m, 4 * w, stride)) = o;
+}
+
+// One thread per variant: scoreTestFast from the batched sums.  rawV [rows_pad x kv] (ld rows_pad): columns
+// A (p) | mu2 X (p) | res | mu2 over the value plane, rawI [rows_pad]: mu2 over the [g == 2] plane.  csum[kv]: the
+// columns' sums over all samples (flip algebra).  Variants that need their own pass are appended to `list`.
+__global__ void __launch_bounds__(128) s2_finish_kernel(s2_model M, const int32_t *__restrict__ cnt, const double *__restrict__ rawV,
+                                                        const double *__restrict__ rawI, int64_t ld, const double *__restrict__ csum,
+                                                        int64_t nm, double min_maf, double min_mac, double max_missing,
+                                                        double *__restrict__ out, int *__restrict__ list, int *__restrict__ list_count)
+{
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nm) return;
+    const int p = M.p;
+    const int64_t N = M.N;
+    double *o = out + m * S2_NOUT;
+    const int32_t *c = cnt + m * 6;
+    const s2_head hd = s2_head_of(c, N, min_maf, min_mac, max_missing);
+    if (!hd.pass) {
+        for (int q = 0; q < S2_NOUT; q++) o[q] = nan("");
+        o[0] = 0.0; o[2] = hd.altFreq0; o[3] = hd.missingRate;
+        return;
+    }
+    const int flip = hd.flip, imputeG = hd.imputeG;
+    const double k2a = c[0], k1a = c[1], nMiss = c[2], k2c = c[3], k1c = c[4], kmc = c[5];
+    // tallies in the flipped / imputed coding (same algebra as step2_kernel's identity path)
+    const double ncase = M.ncase_tot, nctrl = (double)N - ncase;
+    const double k2t = k2a - k2c, k1t = k1a - k1c, kmt = nMiss - kmc;
+    const double h2c = flip ? ncase - k2c - k1c - kmc : k2c, h2t = flip ? nctrl - k2t - k1t - kmt : k2t;
+    double case_hom = h2c + (imputeG == 2 ? kmc : 0.0), case_het = k1c + (imputeG == 1 ? kmc : 0.0);
+    double ctrl_hom = h2t + (imputeG == 2 ? kmt : 0.0), ctrl_het = k1t + (imputeG == 1 ? kmt : 0.0);
+    const double gcase = 2.0 * case_hom + case_het, gctrl = 2.0 * ctrl_hom + ctrl_het;
+    const double gsum = gcase + gctrl, nz = case_hom + case_het + ctrl_hom + ctrl_het;
+    // sums in the tested coding
+    double Z[S2_MAXP], W[S2_MAXP];
+    for (int j = 0; j < p; j++) {
+        const double zr = rawV[m + (int64_t)j * ld], wr = rawV[m + (int64_t)(p + j) * ld];
+        Z[j] = flip ? 2.0 * csum[j] - zr : zr;
+        W[j] = flip ? 2.0 * csum[p + j] - wr : wr;
+    }
+    const double rr = rawV[m + (int64_t)(2 * p) * ld], mr = rawV[m + (int64_t)(2 * p + 1) * ld], ir = rawI[m];
+    const double r0 = flip ? 2.0 * csum[2 * p] - rr : rr;
+    const double t1 = flip ? 4.0 * csum[2 * p + 1] - 3.0 * mr + 2.0 * ir : mr + 2.0 * ir;
+    double altCount = gsum, altFreq = altCount / (2.0 * (double)N);
+    if (flip) { altFreq = 1.0 - altFreq; altCount = 2.0 * (double)N - altCount; }
+    double zxz = 0, zw = 0, saz = 0;
+    for (int a = 0; a < p; a++) {
+        double acc = 0;
+        for (int b = 0; b < p; b++) acc += M.XVX[a + b * p] * Z[b];
+        zxz += Z[a] * acc;
+        zw += Z[a] * W[a];
+        saz += M.S_a[a] * Z[a];
+    }
+    const double var2 = M.binary ? zxz + t1 - 2.0 * zw : zxz * M.tau0 + t1 * M.tau0 - 2.0 * zw * M.tau0;
+    const double MACafter = fmin(altCount, 2.0 * (double)N - altCount);
+    double varRatio = M.varRatio;
+    if (M.n_cate > 1) {
+        varRatio = M.cate_ratio[M.n_cate - 1];
+        for (int q = M.n_cate - 2; q >= 0; q--)
+            if (MACafter <= M.cate_max[q]) varRatio = M.cate_ratio[q];
+    }
+    const double var1 = var2 * varRatio;
+    const double S = (r0 - saz) / M.tau0;
+    double stat = S * S / var1;
+    double pval_noadj;
+    if (var1 <= 2.2250738585072014e-308) pval_noadj = 1.0;
+    else if (isfinite(stat)) pval_noadj = erfc(sqrt(stat * 0.5));
+    else { pval_noadj = 1.0; stat = 0.0; }
+    const double Beta = S / var1;
+    const double seBeta = fabs(Beta) / sqrt(fabs(stat));
+    const double StdStat = fabs(S) / sqrt(var1);
+    const bool isER = M.binary && MACafter <= M.er_max_mac && nz <= (double)SGB_ER_MAXK && (StdStat > M.spa_cutoff || isnan(StdStat));
+    const bool spa_u = !isER && M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff;
+    const bool firth = M.firth && M.binary && pval_noadj <= M.firth_cutoff;
+    if (isER || spa_u || firth || M.n_cond > 0) {
+        list[atomicAdd(list_count, 1)] = (int)m;          // step2_kernel writes this row
+        return;
+    }
+    const double sgn = flip ? -1.0 : 1.0;
+    double afc = ncase > 0 ? gcase / ncase / 2.0 : nan(""), aft = nctrl > 0 ? gctrl / nctrl / 2.0 : nan("");
+    if (flip) { afc = 1.0 - afc; aft = 1.0 - aft; case_hom = ncase - case_het - case_hom; ctrl_hom = nctrl - ctrl_het - ctrl_hom; }
+    o[0] = 1.0; o[1] = altCount; o[2] = altFreq; o[3] = hd.missingRate;
+    o[4] = sgn * Beta; o[5] = seBeta; o[6] = sgn * S; o[7] = var1; o[8] = pval_noadj; o[9] = pval_noadj; o[10] = 0.0;
+    o[11] = afc; o[12] = aft; o[13] = ncase; o[14] = nctrl; o[15] = case_hom; o[16] = case_het; o[17] = ctrl_hom; o[18] = ctrl_het;
+    o[19] = var2; o[20] = 0.0; o[21] = 0.0;
+    for (int q = 22; q < S2_NOUT; q++) o[q] = nan("");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 struct sgb_step2 {
@@ -590,6 +804,22 @@ struct sgb_step2 {
     uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
     double *pout[2] = {nullptr, nullptr}; size_t pout_bytes = 0;      // capacities tracked apart: the chunk length depends on n_fam
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // batched score sums (tensor engine): limb images of the model columns, built once per model
+    int kv = 0;                           // value-plane columns: A (p) | mu2 X (p) | res | mu2
+    int64_t stride = 0;                   // packed bytes per variant row of the tiled chunk store (multiple of 64)
+    double *d_V = nullptr;                // N x kv model columns (device)
+    double *d_csum = nullptr;             // kv column sums over all samples
+    int8_t *d_Lv = nullptr, *d_Li = nullptr;          // limb images: tcgen05 (kv columns, value plane) and mma.sync (mu2, [g==2] plane)
+    double *d_multv = nullptr, *d_multi = nullptr;    // fixed-point multipliers of the images
+    int32_t *d_lsv = nullptr, *d_lsi = nullptr;       // exact limb column sums
+    uint8_t *d_gath = nullptr; size_t gath_bytes = 0; // identity-ordered raw rows (models on a subset / permutation of the .fam)
+    uint8_t *d_tiled = nullptr; size_t tiled_bytes = 0;
+    int32_t *d_accv = nullptr; size_t accv_elems = 0; // int32 limb accumulators (zero between chunks)
+    int32_t *d_acci = nullptr; size_t acci_elems = 0;
+    double *d_raw = nullptr; size_t raw_elems = 0;    // recombined sums: [rows_pad x kv] | [rows_pad]
+    int32_t *d_cnt = nullptr; size_t cnt_elems = 0;   // class counts, 6 per variant
+    int *d_list = nullptr; size_t list_elems = 0;     // [count | variant indices] of the flagged variants
+    bool batched = true;                  // sgb_step2_set_batched(0): every variant through step2_kernel (cross-check)
 };
 
 extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *mu, const double *res,
@@ -640,6 +870,45 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
     M.offset = s->d_offset; M.firth = 0; M.firth_se_from_fit = 1; M.firth_cutoff = 0.01;
     M.er_max_mac = -1.0; M.mu_sum = 0.0; M.n_cate = 1; M.n_cond = 0; M.P2 = nullptr;
     for (int64_t i = 0; i < N; i++) M.mu_sum += mu[i];
+
+    // ---- batched score sums: model columns A | mu2 X | res | mu2, their sums, and their limb images (once per model) ----
+    {
+        const int kv = 2 * p + 2;
+        s->kv = kv;
+        s->stride = ((N + 3) / 4 + SGB_KSTEP_BYTES - 1) / SGB_KSTEP_BYTES * SGB_KSTEP_BYTES;
+        void **olds[] = {(void **)&s->d_V, (void **)&s->d_csum, (void **)&s->d_Lv, (void **)&s->d_Li, (void **)&s->d_multv,
+                         (void **)&s->d_multi, (void **)&s->d_lsv, (void **)&s->d_lsi};
+        for (auto q : olds) { if (*q) cudaFree(*q); *q = nullptr; }
+        std::vector<double> V((size_t)N * kv), cs(kv, 0.0);
+        for (int j = 0; j < p; j++)
+            for (int64_t i = 0; i < N; i++) {
+                V[(size_t)j * N + i] = XVX_inv_XV[(size_t)j * N + i];
+                V[(size_t)(p + j) * N + i] = mu2[i] * X[(size_t)j * N + i];
+            }
+        for (int64_t i = 0; i < N; i++) { V[(size_t)(2 * p) * N + i] = res[i]; V[(size_t)(2 * p + 1) * N + i] = mu2[i]; }
+        for (int c = 0; c < kv; c++) { double t = 0.0; for (int64_t i = 0; i < N; i++) t += V[(size_t)c * N + i]; cs[c] = t; }
+        const size_t img = k_umma_image_bytes(k_umma_npad(kv, 7), s->stride), frag = (size_t)(s->stride / SGB_KSTEP_BYTES) * 2048;
+        CUDA_OK(h, cudaMalloc((void **)&s->d_V, sizeof(double) * V.size()));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_csum, sizeof(double) * kv));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_Lv, img));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_Li, frag));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_multv, sizeof(double) * kv));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_multi, sizeof(double)));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_lsv, sizeof(int32_t) * 8 * kv));
+        CUDA_OK(h, cudaMalloc((void **)&s->d_lsi, sizeof(int32_t) * 8));
+        CUDA_OK(h, cudaMemcpyAsync(s->d_V, V.data(), sizeof(double) * V.size(), cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(h, cudaMemcpyAsync(s->d_csum, cs.data(), sizeof(double) * kv, cudaMemcpyHostToDevice, h->stream));
+        SGB_TRY(k_split_limbs_umma(h, s->d_V, N, N, kv, s->d_Lv, s->stride, s->d_multv, s->d_lsv, 7, 0));
+        SGB_TRY(k_split_limbs(h, s->d_V + (size_t)(2 * p + 1) * N, N, N, 1, s->d_Li, s->stride / SGB_KSTEP_BYTES, s->d_multi, s->d_lsi, 0));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+extern "C" int sgb_step2_set_batched(sgb_ctx *h, int enable)
+{
+    if (!h->step2) h->step2 = new sgb_step2();
+    h->step2->batched = enable != 0;
     return 0;
 }
 
@@ -713,7 +982,7 @@ extern "C" int sgb_step2_set_firth(sgb_ctx *h, int enable, double p_cutoff, cons
 // pageable -> pinned staging copy on 4 host threads (one thread tops out near 10 GB/s, below what the kernel consumes)
 static void s2_par_copy(uint8_t *dst, const uint8_t *src, size_t n)
 {
-    const int nt = n > ((size_t)8 << 20) ? 4 : 1;
+    const int nt = n > ((size_t)8 << 20) ? 8 : 1;
     if (nt == 1) { memcpy(dst, src, n); return; }
     std::vector<std::thread> th;
     const size_t per = (n + nt - 1) / nt;
@@ -758,22 +1027,69 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
     }
+    // batched path: chunk = a multiple of the row alignment of the tiled store; scratch for the tensor-engine sums
+    const bool batched = s->batched;
+    const int64_t N = s->M.N, Bm = (N + 3) / 4;
+    const int64_t rows_pad = (chunk + SGB_ROW_ALIGN - 1) / SGB_ROW_ALIGN * SGB_ROW_ALIGN;
+    const int kv = s->kv, npadv = k_umma_npad(kv, 7);
+    if (batched) {
+        if (!s->M.identity) SGB_TRY(sgb_ensure(h, (void **)&s->d_gath, &s->gath_bytes, (size_t)chunk * Bm));
+        SGB_TRY(sgb_ensure(h, (void **)&s->d_tiled, &s->tiled_bytes, (size_t)rows_pad * s->stride));
+        size_t b;
+        b = s->accv_elems * 4; if (b < (size_t)rows_pad * npadv * 4) { SGB_TRY(sgb_ensure(h, (void **)&s->d_accv, &b, (size_t)rows_pad * npadv * 4)); s->accv_elems = b / 4; CUDA_OK(h, cudaMemsetAsync(s->d_accv, 0, b, h->stream)); }
+        b = s->acci_elems * 4; if (b < (size_t)rows_pad * 8 * 4) { SGB_TRY(sgb_ensure(h, (void **)&s->d_acci, &b, (size_t)rows_pad * 8 * 4)); s->acci_elems = b / 4; CUDA_OK(h, cudaMemsetAsync(s->d_acci, 0, b, h->stream)); }
+        SGB_TRY(sgb_ensure_f64(h, &s->d_raw, &s->raw_elems, (size_t)rows_pad * (kv + 1)));
+        b = s->cnt_elems * 4; SGB_TRY(sgb_ensure(h, (void **)&s->d_cnt, &b, (size_t)chunk * 6 * 4)); s->cnt_elems = b / 4;
+        b = s->list_elems * 4; SGB_TRY(sgb_ensure(h, (void **)&s->d_list, &b, (size_t)(chunk + 1) * 4)); s->list_elems = b / 4;
+    }
+    // rows in page-locked memory (cudaHostAlloc / cudaHostRegister by the caller) go to the device straight from the caller's
+    // buffer; pageable rows pass through the pinned double buffer (a host memcpy at ~13 GB/s: the e2e limit of that case)
+    cudaPointerAttributes pattr;
+    const bool rows_pinned = cudaPointerGetAttributes(&pattr, bed_rows) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
     int cur = 0;
     int64_t held_m0[2] = {-1, -1}, held_nm[2] = {0, 0};
     for (int64_t m0 = 0; m0 < n_markers; m0 += chunk, cur ^= 1) {
         const int64_t nm = std::min(chunk, n_markers - m0);
         CUDA_OK(h, cudaEventSynchronize(s->ev[cur]));                      // buffers `cur` are free again (chunk c-2 done)
         if (held_m0[cur] >= 0) memcpy(out + (size_t)held_m0[cur] * S2_NOUT, s->pout[cur], sizeof(double) * held_nm[cur] * S2_NOUT);
-        s2_par_copy(s->pin[cur], bed_rows + (size_t)m0 * B0, (size_t)nm * B0);
+        if (!rows_pinned) s2_par_copy(s->pin[cur], bed_rows + (size_t)m0 * B0, (size_t)nm * B0);
         uint8_t *db = s->d_bed + cur * cbytes;
         double *dout = s->d_out + cur * (size_t)chunk * S2_NOUT;
-        CUDA_OK(h, cudaMemcpyAsync(db, s->pin[cur], (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(h, cudaMemcpyAsync(db, rows_pinned ? bed_rows + (size_t)m0 * B0 : s->pin[cur], (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
         h->cnt.bytes_h2d += nm * B0;
-        // dynamic smem: the raw row, padded so that the word-wise reads of the last (partial) word pair stay inside
-        if (s->M.identity)
-            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{});
+        if (batched) {
+            SGB_RANGE("step2_chunk_batched");
+            const uint8_t *rows = db;
+            int64_t Brow = B0;
+            if (!s->M.identity) {          // model samples gathered into identity order once; every later pass is the identity path
+                s2_gather_kernel<<<dim3((unsigned)((Bm + 255) / 256), (unsigned)nm), 256, 0, h->stream>>>(db, B0, s->M.pos, N, Bm, s->d_gath);
+                h->cnt.n_kernel_launches++;
+                rows = s->d_gath; Brow = Bm;
+            }
+            const int64_t rp = (nm + SGB_ROW_ALIGN - 1) / SGB_ROW_ALIGN * SGB_ROW_ALIGN;
+            s2_count_kernel<<<(unsigned)nm, 256, 0, h->stream>>>(rows, Brow, N, s->M.ycase, s->d_cnt);
+            s2_repack_kernel<<<dim3((unsigned)((s->stride / 4 + 255) / 256), (unsigned)rp), 256, 0, h->stream>>>(rows, Brow, N, nm, s->d_cnt, min_maf, min_mac,
+                                                                                                              max_missing, s->d_tiled, s->stride);
+            h->cnt.n_kernel_launches += 2;
+            CUDA_OK(h, cudaGetLastError());
+            double *rawV = s->d_raw, *rawI = s->d_raw + (size_t)rows_pad * kv;
+            SGB_TRY(k_pk2_umma(h, s->d_tiled, s->stride, rp, s->stride, s->d_Lv, kv, s->d_accv, SGB_PLANE_VALUE, 7));
+            SGB_TRY(k_recombine_umma(h, s->d_accv, rp, kv, s->d_multv, s->d_lsv, SGB_PLANE_VALUE, rawV, rows_pad));
+            SGB_TRY(k_pk2_gemm(h, s->d_tiled, s->stride, rp, s->stride, s->d_Li, 1, s->d_acci, SGB_PLANE_IS2));
+            SGB_TRY(k_recombine(h, s->d_acci, rp, 1, 1, s->d_multi, s->d_lsi, SGB_PLANE_IS2, rawI, rows_pad));
+            CUDA_OK(h, cudaMemsetAsync(s->d_list, 0, sizeof(int), h->stream));
+            s2_model Mi = s->M; Mi.identity = 1;
+            s2_finish_kernel<<<(unsigned)((nm + 127) / 128), 128, 0, h->stream>>>(Mi, s->d_cnt, rawV, rawI, rows_pad, s->d_csum, nm, min_maf, min_mac,
+                                                                                max_missing, dout, s->d_list + 1, s->d_list);
+            // the flagged variants (saddle point, exact test, Firth, conditional): one CTA each, empty CTAs beyond the count
+            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)Brow + 8, h->stream>>>(Mi, rows, Brow, nm, min_maf, min_mac, max_missing, se_two_sided,
+                                                                                              dout, s2_dose{}, s->d_list + 1, s->d_list);
+            h->cnt.n_kernel_launches += 2;
+        } else if (s->M.identity)
+            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{}, nullptr, nullptr);
         else
-            step2_kernel<false, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{});
+            step2_kernel<false, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{}, nullptr, nullptr);
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
         CUDA_OK(h, cudaMemcpyAsync(s->pout[cur], dout, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
@@ -813,7 +1129,7 @@ extern "C" int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t
         s2_dose ds;
         ds.d = reinterpret_cast<const double *>(s->d_bed); ds.stride = n_file_samples; ds.impute = impute_method;
         ds.zerod_cutoff = dosage_zerod_cutoff; ds.zerod_mac_cutoff = dosage_zerod_mac_cutoff;
-        step2_kernel<false, true><<<(unsigned)nm, S2_THREADS, 0, h->stream>>>(s->M, nullptr, 0, nm, min_maf, min_mac, max_missing, se_two_sided, s->d_out, ds);
+        step2_kernel<false, true><<<(unsigned)nm, S2_THREADS, 0, h->stream>>>(s->M, nullptr, 0, nm, min_maf, min_mac, max_missing, se_two_sided, s->d_out, ds, nullptr, nullptr);
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
         CUDA_OK(h, cudaMemcpyAsync(out + (size_t)m0 * S2_NOUT, s->d_out, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
@@ -834,6 +1150,9 @@ void sgb_step2_free(sgb_ctx *h)
     if (s->d_P2) cudaFree(s->d_P2);
     if (s->d_bed) cudaFree(s->d_bed);
     if (s->d_out) cudaFree(s->d_out);
+    void *more[] = {s->d_V, s->d_csum, s->d_Lv, s->d_Li, s->d_multv, s->d_multi, s->d_lsv, s->d_lsi, s->d_gath, s->d_tiled, s->d_accv, s->d_acci,
+                    s->d_raw, s->d_cnt, s->d_list};
+    for (auto q : more) if (q) cudaFree(q);
     for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }
     delete s;
     h->step2 = nullptr;

@@ -1,0 +1,99 @@
+"""The batched step-2 path (score sums of a variant chunk as one tensor-engine GEMM, per-variant kernel only for flagged
+variants) against the per-variant kernel of round 1 and against the oracle's marker loop."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(rng, N, p, trait):
+    X = np.column_stack([np.ones(N), rng.normal(size=(N, p - 1))])
+    if trait == "binary":
+        beta = np.concatenate([[-1.8], rng.normal(scale=0.3, size=p - 1)])
+        mu = 1 / (1 + np.exp(-(X @ beta + rng.normal(scale=0.3, size=N))))
+        y = (rng.uniform(size=N) < mu).astype(np.float64)
+        tau = np.array([1.0, 0.4]); mu2 = mu * (1 - mu)
+    else:
+        y = X @ rng.normal(scale=0.3, size=p) + rng.normal(size=N)
+        mu = X @ np.linalg.lstsq(X, y, rcond=None)[0]
+        tau = np.array([0.7, 0.3]); mu2 = np.full(N, 1 / tau[0])
+    res = y - mu
+    XV = (X * mu2[:, None]).T
+    XVX = X.T @ XV.T
+    XVXi = np.linalg.inv(XVX)
+    return dict(mu=mu, res=res, mu2=mu2, tau=tau, trait=trait, y=y, X=X, XV=XV, XVX=XVX, XXVX_inv=X @ XVXi,
+                XVX_inv_XV=(X @ XVXi) * mu2[:, None], S_a=(X * res[:, None]).sum(0), varRatio=0.93)
+
+
+def _bed_with_flips(n_fam, nm, seed, miss):
+    from oracle import oracle as O
+    bed = O.synth_bed(n_fam, nm, seed=seed, miss_rate=miss)
+    B0 = (n_fam + 3) // 4
+    rows = bed.reshape(nm, B0).copy()
+    for m in range(0, nm, 3):                 # every third marker major-allele coded -> the flip branch
+        r = rows[m]
+        lo, hi = r & 0x55, (r >> 1) & 0x55
+        hom = ~(lo ^ hi) & 0x55
+        rows[m] = r ^ (hom | (hom << 1))
+    return rows.reshape(-1)
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+@pytest.mark.parametrize("identity", [True, False])
+def test_batched_equals_per_variant_kernel(trait, identity):
+    from saige_gpu_b200 import SaigeB200
+    rng = np.random.default_rng(21)
+    n_fam, nm, p = 2051, 1500, 3
+    N = n_fam if identity else 1777
+    bed = _bed_with_flips(n_fam, nm, 4, 0.01)
+    pos = np.arange(N, dtype=np.int32) if identity else rng.permutation(n_fam)[:N].astype(np.int32)
+    M = _model(rng, N, p, trait)
+    g = SaigeB200(device=0)
+    try:
+        g.setSAIGEobjInCPP(M, 0.93, 2.0, pos)
+        g.setMaxMACforER(4.0)
+        g.setStep2Batched(False)
+        ref = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 0.5, 0.15)
+        g.setStep2Batched(True)
+        out = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 0.5, 0.15)
+    finally:
+        g.close()
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    assert np.array_equal(out[:, 0], ref[:, 0]) and np.array_equal(out[:, 10], ref[:, 10])        # tested, Is.SPA
+    a, b = np.nan_to_num(out), np.nan_to_num(ref)
+    scale = np.maximum(np.abs(b), 1e-300)
+    worst = np.max(np.abs(a - b) / scale)
+    assert worst < 1e-9, worst
+    assert (ref[:, 0] == 1).sum() > 1000
+    if trait == "binary":
+        assert ref[:, 10].sum() > 20
+
+
+def test_batched_vs_oracle_larger_cohort():
+    """20,011 samples (ragged: not a multiple of 4, 16 or 256) x 600 variants incl. rare ones, identity map."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import SaigeB200
+    rng = np.random.default_rng(33)
+    n_fam, nm, p = 20011, 600, 4
+    bed = _bed_with_flips(n_fam, nm, 8, 0.005)
+    pos = np.arange(n_fam, dtype=np.int32)
+    M = _model(rng, n_fam, p, "binary")
+    g = SaigeB200(device=0)
+    try:
+        g.setSAIGEobjInCPP(M, 0.93, 2.0, pos)
+        out = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 0.5, 0.15)
+    finally:
+        g.close()
+    nspa = 0
+    for m in range(0, nm, 7):
+        r = S2.test_marker(M, S2.plink_marker(bed, n_fam, m, pos), min_mac=0.5)
+        assert (r is not None) == (out[m, 0] == 1.0), m
+        if r is None:
+            continue
+        got = dict(zip(SaigeB200.STEP2_COLUMNS, out[m]))
+        nspa += bool(r["Is_SPA"])
+        for col, oc in (("AC_Allele2", "AC_Allele2"), ("AF_Allele2", "AF_Allele2"), ("BETA", "BETA"), ("SE", "SE"), ("Tstat", "Tstat"),
+                        ("var", "var"), ("p.value", "p_value"), ("p.value.NA", "p_value_NA")):
+            assert abs(got[col] - r[oc]) <= 1e-6 * abs(r[oc]) + 1e-300, (m, col, got[col], r[oc])
+        assert bool(got["Is.SPA"]) == bool(r["Is_SPA"])
+    assert nspa >= 2

@@ -23,8 +23,13 @@ M = dict(mu=mu, res=res, mu2=mu2, tau=np.array([1.0, 0.3]), trait="binary", y=y,
 g = SaigeB200()
 g.setSAIGEobjInCPP(M, 0.95, spa_cutoff, np.arange(N, dtype=np.int32))
 g.mainMarkerInCPP(bed[: ((N + 3) // 4) * 256], N, 256)
-g.mainMarkerInCPP(bed, N, nm)          # sizes the pinned staging buffers
-t = time.time(); out = g.mainMarkerInCPP(bed, N, nm); dt = time.time() - t
-print("AF in [%g, %g], SPA cutoff %g: " % (flo, fhi, spa_cutoff), end="")
-print("N=%d variants=%d : %.3f s -> %.0f variants/s (%.1f GB/s of genotype bytes), SPA-adjusted %d, tested %d"
-      % (N, nm, dt, nm / dt, bed.nbytes / dt / 1e9, int(out[:, 10].sum()), int(out[:, 0].sum())))
+import torch
+pinned = torch.from_numpy(bed).pin_memory().numpy()          # the same rows in page-locked memory (no staging copy in the library)
+for label, rows in (("pageable rows", bed), ("pinned rows", pinned)):
+    for batched in (True, False):
+        g.setStep2Batched(batched)
+        g.mainMarkerInCPP(rows, N, nm)          # sizes the staging buffers
+        t = time.time(); out = g.mainMarkerInCPP(rows, N, nm); dt = time.time() - t
+        print("AF in [%g, %g], SPA cutoff %g, %s, %s: " % (flo, fhi, spa_cutoff, label, "batched GEMM sums" if batched else "per-variant kernel"), end="")
+        print("N=%d variants=%d : %.3f s -> %.0f variants/s (%.1f GB/s of genotype bytes), SPA-adjusted %d, tested %d"
+              % (N, nm, dt, nm / dt, bed.nbytes / dt / 1e9, int(out[:, 10].sum()), int(out[:, 0].sum())))
