@@ -226,6 +226,9 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-GRM build sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step1", action="store_true", help="skip the step-1 wall-time extra")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the full-size setgeno leg (host-resident .bed in /dev/shm)")
+    ap.add_argument("--no-step2", action="store_true", help="skip the step-2 leg")
+    ap.add_argument("--c4-full", action="store_true", help="run BASELINE config 4 at its named shape (default when --gpus >= 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     N, M = WORKLOADS[args.workload]
@@ -249,6 +252,14 @@ def main():
     else:
         g = SaigeB200(device=local_rank, engine=args.engine)
     torch.cuda.set_device(local_rank)
+
+    def new_context():
+        """A second library context on the same rank layout (its own NCCL communicator)."""
+        if world > 1:
+            ids2 = [SaigeB200.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids2, src=0)
+            return SaigeB200(device=local_rank, rank=rank, world=world, nccl_id=ids2[0], engine=args.engine)
+        return SaigeB200(device=local_rank, engine=args.engine)
 
     def barrier():
         g.sync()
@@ -358,26 +369,67 @@ def main():
             cb["reference_gpu_kernel"] = reference_gpu_kernel(N, M)
         except Exception as e:                      # the reference class prints and returns codes; never fail the bench on it
             cb["reference_gpu_kernel"] = {"error": str(e)}
+    # ---- setgeno at full size from a host-resident .bed: the file body lives in /dev/shm, generated once by all
+    # ranks together (device generator, bit-identical to the genotypes of the timed store); every rank then runs the sharded
+    # ingest (count pass over its 1/world of the file, int32 allreduce, QC, second read of the rows it owns) ----
     ingest_info = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # setgeno from a host-resident PLINK .bed body (QC + imputation + re-pack + transpose on the GPU), bounded sample
-        n_i, m_i = N, 32768
-        bed_i = synth.raw_bed(n_i, m_i, SEED, miss_rate=0.01)
-        gi = SaigeB200(device=local_rank)
-        gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
-        gi.setgeno_mem(bed_i, n_i, 512, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))        # warm-up on the first 512 markers
-        ti = time.time()
-        gi.setgeno_mem(bed_i, n_i, m_i, np.arange(1, n_i + 1), np.ones(n_i, np.uint8))
-        ti = time.time() - ti
-        ingest_info = {"bed_gbytes": bed_i.nbytes / 1e9, "seconds": ti, "gb_per_s": bed_i.nbytes / 1e9 / ti,
-                       "sample": "%d samples x %d markers, 1%% missing calls, host-resident .bed body" % (n_i, m_i)}
-        gi.close()
+    if not args.no_ingest:
+        shm = "/dev/shm/sgb_bench_%s.bed" % os.environ.get("MASTER_PORT", str(os.getpid()))
+        try:
+            nbytes = Bbytes * M
+            if rank == 0:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < nbytes + (8 << 30):
+                    raise RuntimeError("/dev/shm has %.0f GB free, the .bed body needs %.0f" % (st.f_bavail * st.f_frsize / 1e9, nbytes / 1e9))
+                with open(shm, "wb") as f:
+                    f.truncate(nbytes)
+            if world > 1:
+                dist.barrier()
+            mm = np.memmap(shm, dtype=np.uint8, mode="r+")
+            ma, mb = M * rank // world, M * (rank + 1) // world
+            tg = time.time()
+            g.synth_bed_rows(N, ma, mb, SEED, t0, t1, 0.0, out=mm[ma * Bbytes:mb * Bbytes])
+            tg = time.time() - tg
+            if world > 1:
+                dist.barrier()
+            gi = new_context()
+            gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
+            ones = np.ones(N, np.uint8); ids = np.arange(1, N + 1)
+            gi.setgeno_mem(mm, N, min(M, 4096), ids, ones)          # warm-up: allocations, first kernel loads
+            barrier()
+            ti = time.time()
+            gi.setgeno_mem(mm, N, M, ids, ones)
+            gi.sync()
+            ti = max_over_ranks(time.time() - ti)
+            same = bool(gi.M == g.M and np.array_equal(gi.getAlleleCountVec(), g.getAlleleCountVec()))
+            yi = np.asarray(gi.getCrossprodMatAndKin(hb.numpy())).ravel()
+            ingest_info = {"bed_gbytes": nbytes / 1e9, "seconds": ti, "gb_per_s": nbytes / 1e9 / ti, "n_gpus": world,
+                           "h2d_gbytes_this_rank": gi.counters()["bytes_h2d"] / 1e9, "generate_s": tg,
+                           "allele_counts_equal_synth_store": same,
+                           "product_rel_diff_vs_synth_store": float(np.max(np.abs(yi - hy.numpy())) / np.max(np.abs(hy.numpy()))),
+                           "sample": "FULL workload: %d samples x %d markers, host-resident .bed body in /dev/shm (pageable), "
+                                     "QC + imputation + re-pack + transpose on the GPU, sharded over %d rank(s)" % (N, M, world)}
+            gi.close()
+            del mm
+        except Exception as e:
+            ingest_info = {"error": "%s: %s" % (type(e).__name__, e)}
+        finally:
+            if world > 1:
+                dist.barrier()
+            if rank == 0 and os.path.exists(shm):
+                os.unlink(shm)
+
+    # ---- BASELINE config 5 row: single-variant score test + SPA, variants sharded over the ranks (no collective): every rank
+    # tests its own 65,536 synthetic variants x N samples from pinned host rows through the C ABI ----
     step2_info = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # BASELINE config 5 row: single-variant score test + SPA through the C ABI from pageable host rows, bounded sample
-        n2, m2 = N, 8192
+    if not args.no_step2:
+        n2, m2 = N, 65536 if N >= 100_000 else 262144
         rng2 = np.random.default_rng(SEED + 9)
-        bed2 = synth.raw_bed(n2, m2, SEED + 9, miss_rate=0.005)
+        f2 = np.random.default_rng(SEED + 10 + rank).uniform(0.05, 0.5, size=m2)
+        s0 = np.floor((1 - f2) ** 2 * 4294967296.0).astype(np.uint64).clip(0, 4294967295).astype(np.uint32)
+        s1 = np.floor((1 - f2 * f2) * 4294967296.0).astype(np.uint64).clip(0, 4294967295).astype(np.uint32)
+        rows2 = torch.empty(((n2 + 3) // 4) * m2, dtype=torch.uint8).pin_memory()
+        g.synth_bed_rows(n2, 0, m2, SEED + 11 + rank, s0, s1, 0.005, out=rows2.numpy())
         X2 = np.column_stack([np.ones(n2), rng2.normal(size=(n2, 2))])
         mu_ = 1 / (1 + np.exp(-(X2 @ np.array([-2.2, 0.4, -0.3]) + rng2.normal(scale=0.3, size=n2))))
         y2 = (rng2.uniform(size=n2) < mu_).astype(np.float64)
@@ -387,12 +439,22 @@ def main():
                    XXVX_inv=X2 @ XVXi, XVX_inv_XV=(X2 @ XVXi) * v2[:, None], S_a=(y2 - mu_) @ X2)
         g2 = SaigeB200(device=local_rank)
         g2.setSAIGEobjInCPP(mdl, 0.95, 2.0, np.arange(n2, dtype=np.int32))
-        g2.mainMarkerInCPP(bed2, n2, m2)                       # sizes the pinned staging buffers
-        t2 = time.time(); o2 = g2.mainMarkerInCPP(bed2, n2, m2); t2 = time.time() - t2
-        step2_info = {"variants_per_s": m2 / t2, "gb_per_s_raw_rows": bed2.nbytes / t2 / 1e9, "spa_adjusted": int(o2[:, 10].sum()),
-                      "sample": "%d samples x %d variants (AF ~ U(0.05, 0.5), 0.5%% missing), binary trait, 3 covariate columns, "
-                                "SPA cutoff 2, host-resident PLINK rows" % (n2, m2)}
+        g2.mainMarkerInCPP(rows2.numpy(), n2, m2)                       # sizes the staging buffers
+        barrier()
+        t2 = time.time(); o2 = g2.mainMarkerInCPP(rows2.numpy(), n2, m2); t2 = max_over_ranks(time.time() - t2)
+        g2.setSAIGEobjInCPP(mdl, 0.95, 1e9, np.arange(n2, dtype=np.int32))      # no variant takes the saddle-point branch
+        g2.mainMarkerInCPP(rows2.numpy(), n2, m2)
+        barrier()
+        t3 = time.time(); g2.mainMarkerInCPP(rows2.numpy(), n2, m2); t3 = max_over_ranks(time.time() - t3)
+        step2_info = {"variants_per_s": world * m2 / t2, "gb_per_s_raw_rows": world * rows2.numel() / t2 / 1e9,
+                      "variants_per_s_without_spa": world * m2 / t3, "gb_per_s_raw_rows_without_spa": world * rows2.numel() / t3 / 1e9,
+                      "spa_adjusted_rank0": int(o2[:, 10].sum()), "variants_per_rank": m2, "n_gpus": world,
+                      "sample": "%d samples x %d variants PER RANK (AF ~ U(0.05, 0.5), 0.5%% missing), binary trait, 3 covariate columns, "
+                                "SPA cutoff 2 (~5%% of the variants take the saddle-point branch), pinned host PLINK rows; score sums as one "
+                                "tensor-engine GEMM per 1 GB chunk, per-variant kernel for flagged variants; 'without_spa' = same rows, cutoff 1e9 "
+                                "(PCIe-bound)" % (n2, m2)}
         g2.close()
+        del rows2
     step1_info = None
     if not args.no_step1:
         # polygenic liability (h2 ~ 0.3) from 200 causal markers read back through Get_OneSNP_StdGeno
@@ -429,7 +491,25 @@ def main():
                       "fit_s": tim.get("fit_s"), "loco_refits_s": tim.get("loco_s"),
                       "variance_ratio": float(vr), "variance_ratio_markers": int(vr_markers), "variance_ratio_s": vr_s,
                       "note": "binary trait, 3 fixed-effect columns, nrun=30 probes, tolPCG=1e-5, full GRM, "
-                              "22 leave-one-chromosome-out refits included; genotypes already resident (load_synth_s apart)"}
+                              "22 leave-one-chromosome-out refits included; genotypes already resident (load_synth_s apart); "
+                              "wide batches at 7 digits (exact 55-bit right-hand sides)"}
+        if ingest_info and "seconds" in ingest_info:
+            step1_info["setgeno_s"] = ingest_info["seconds"]
+            step1_info["wall_with_setgeno_s"] = wall + ingest_info["seconds"]
+        # the same fit with the tolerance-driven digit count of wide batches (sgb_set_product_tolerance(1e-10) = 5 digits)
+        g.set_product_tolerance(1e-10)
+        barrier()
+        ts5 = time.time()
+        tim5 = {}
+        model5 = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim5, LOCO=loco)
+        g.sync()
+        wall5 = max_over_ranks(time.time() - ts5)
+        g.set_rhs_limbs(7)
+        step1_info["digits5"] = {"wall_s": wall5, "fit_s": tim5.get("fit_s"), "loco_refits_s": tim5.get("loco_s"),
+                                 "tau": [float(v) for v in model5["theta"]],
+                                 "tau_rel_diff_vs_digits7": float(abs(model5["theta"][1] - model["theta"][1]) / abs(model["theta"][1])),
+                                 "alpha_rel_diff_vs_digits7": float(np.max(np.abs(model5["coefficients"] - model["coefficients"]) /
+                                                                           np.abs(model["coefficients"])))}
 
     dense_info = None
     if not args.no_dense and N < (1 << 18):
@@ -455,6 +535,45 @@ def main():
                                    "frac": dops / (dms * 1e-3) / 1e12 / world / tpeak, "peak_source": tsrc},
                       "full_build_estimate_s": 7 * 2.0 * M * 128 * 128 * nbr * (nbr + 1) / 2 / (dops / (dms * 1e-3))}
 
+    c4_info = None
+    if not args.no_dense and (args.c4_full or world >= 4):
+        # BASELINE config 4 at its named shape: 100,000 samples x 500,000 markers, the fp64 N x N GRM built on the tcgen05 int8
+        # path, block-rows dealt over the ranks (marker shards exchanged once with ncclBroadcast), then PCG on the stored matrix
+        N4, M4 = 100_000, 500_000
+        g4 = new_context()
+        _, u0, u1 = synth.thresholds(M4, SEED + 4)
+        g4.setminMAFforGRM(0.01); g4.setmaxMissingRateforGRM(0.15)
+        g4.setgeno_synth(N4, M4, SEED + 4, u0, u1)
+        barrier()
+        tb = time.time()
+        info4 = g4.buildDenseGRM(7)
+        g4.sync()
+        tb = max_over_ranks(time.time() - tb)
+        rng4 = np.random.default_rng(SEED + 4)
+        B4 = np.asfortranarray(rng4.normal(size=(N4, 4)))
+        want = g4.getCrossprodMatAndKin(B4)                      # on-the-fly product from the 2-bit store
+        g4.setGRMMode("dense")
+        got = g4.getCrossprodMatAndKin(B4)
+        prod = {}
+        for kk in (1, 4):
+            g4.bench_crossprod_device(kk, 2)
+            barrier()
+            msd, _ = g4.bench_crossprod_device(kk, 5)
+            prod["k%d_ms" % kk] = max_over_ranks(float(msd.mean()))
+        w4 = rng4.uniform(0.05, 0.25, size=N4)
+        barrier()
+        tp = time.time()
+        X4, it4 = g4.getPCG1ofSigmaAndVector(w4, np.array([1.0, 0.3]), B4, 500, 1e-5, return_iter=True)
+        tp = max_over_ranks(time.time() - tp)
+        g4.setGRMMode("packed")
+        X4p, it4p = g4.getPCG1ofSigmaAndVector(w4, np.array([1.0, 0.3]), B4, 500, 1e-5, return_iter=True)
+        c4_info = {"workload": "c4_100kx500k", "n_gpus": world, "weight_limbs": 7, "build_wall_s": tb, "build_device_ms_this_rank": info4["build_ms"],
+                   "stored_gbytes_this_rank": info4["stored_bytes"] / 1e9, "int8_tops_aggregate": world * info4["int8_ops"] / (info4["build_ms"] * 1e-3) / 1e12,
+                   "stored_product_ms": prod, "product_rel_diff_vs_on_the_fly": float(np.max(np.abs(got - want)) / np.max(np.abs(want))),
+                   "pcg_on_stored_grm": {"columns": 4, "iterations": [int(v) for v in it4], "wall_s": tp,
+                                         "iterations_on_the_fly": [int(v) for v in it4p],
+                                         "solution_rel_diff_vs_on_the_fly": float(np.max(np.abs(X4 - X4p)) / np.max(np.abs(X4p)))}}
+        g4.close()
     if rank == 0:
         line = {
             "metric": "grm_matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -478,6 +597,7 @@ def main():
             "ingest": ingest_info,
             "step1": step1_info,
             "dense_grm": dense_info,
+            "c4_dense_grm": c4_info,
             "step2": step2_info,
         }
         print(json.dumps(line))

@@ -87,6 +87,10 @@ int sgb_setgeno(sgb_ctx *h, const char *bedfile, const char *bimfile, const char
 int sgb_setgeno_mem(sgb_ctx *h, const uint8_t *bed_body, int64_t n_fam, int64_t n_bim,
                     const int32_t *subSampleInGeno, int64_t n_sub, const uint8_t *indicator,
                     int isDiagofKinSetAsOne, const int32_t *vr_rand_idx, int64_t n_vr_idx);
+/* Bench / test input: raw PLINK .bed rows (no magic bytes) of synthetic markers [m0, m1) of the same generator, written to
+ * the host buffer `out` ((m1 - m0) * ceil(N/4) bytes); t0 / t1: thresholds of those markers.  Not part of the reference. */
+int sgb_synth_bed_rows(sgb_ctx *h, int64_t N, int64_t m0, int64_t m1, uint64_t seed, const uint32_t *t0, const uint32_t *t1,
+                       double miss_rate, uint8_t *out);
 /* Bench/test workload generator: counter-based synthetic genotypes written straight into the
  * device layout; t0/t1 are per-marker uint32 thresholds.  Bit-identical to oracle/saige_oracle.c:orc_synth_bed. */
 int sgb_setgeno_synth(sgb_ctx *h, int64_t n_samples, int64_t n_markers, uint64_t seed,

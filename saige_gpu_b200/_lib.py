@@ -49,6 +49,7 @@ _SIGS = {
     "sgb_setgeno": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, P, I64, P, I64, C.c_int, P, I64]),
     "sgb_setgeno_mem": (C.c_int, [P, P, I64, I64, P, I64, P, C.c_int, P, I64]),
     "sgb_setgeno_synth": (C.c_int, [P, I64, I64, C.c_uint64, P, P]),
+    "sgb_synth_bed_rows": (C.c_int, [P, I64, I64, I64, C.c_uint64, P, P, C.c_double, P]),
     "sgb_get_total_marker": (I64, [P]),
     "sgb_get_num_qc_markers": (I64, [P]),
     "sgb_get_num_local_markers": (I64, [P]),

@@ -135,6 +135,20 @@ class SaigeB200:
         self._ck(self._L.sgb_setgeno_synth(self._h, n_samples, n_markers, seed, _p(t0), _p(t1)))
         self._dims()
 
+    def synth_bed_rows(self, n_samples, m0, m1, seed, t0, t1, miss_rate=0.0, out=None):
+        """Raw PLINK .bed rows of the synthetic markers [m0, m1) (t0 / t1: thresholds of ALL markers or of that slice) into
+        `out` (a writable uint8 buffer, e.g. a slice of a shared memory map) or a new array.  Bench / test input."""
+        t0 = np.ascontiguousarray(t0, dtype=np.uint32)
+        t1 = np.ascontiguousarray(t1, dtype=np.uint32)
+        if len(t0) != m1 - m0:
+            t0, t1 = np.ascontiguousarray(t0[m0:m1]), np.ascontiguousarray(t1[m0:m1])
+        nbytes = ((n_samples + 3) // 4) * (m1 - m0)
+        if out is None:
+            out = np.empty(nbytes, dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.size >= nbytes and out.flags["C_CONTIGUOUS"]
+        self._ck(self._L.sgb_synth_bed_rows(self._h, n_samples, m0, m1, seed, _p(t0), _p(t1), float(miss_rate), _p(out)))
+        return out
+
     def _dims(self):
         L, h = self._L, self._h
         self.N = L.sgb_get_nnomissing(h)

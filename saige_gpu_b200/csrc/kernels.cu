@@ -274,6 +274,42 @@ __global__ void synth_kernel(int mode, int64_t y0, uint64_t seed, const uint32_t
     }
 }
 
+// raw PLINK .bed rows (SNP-major, 00 = two copies of A1, 10 = one, 11 = none, 01 = missing) of the synthetic markers
+// [m0, m0 + gridDim.y): the same integer hash and coding as oracle/saige_oracle.c:orc_synth_bed, one byte per thread
+__global__ void synth_bed_kernel(int64_t m0, uint64_t seed, const uint32_t *__restrict__ t0, const uint32_t *__restrict__ t1,
+                                 uint32_t miss_thr, int64_t N, uint8_t *__restrict__ out)
+{
+    const int64_t r = blockIdx.y, m = m0 + r, B0 = (N + 3) >> 2;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B0) return;
+    const uint32_t a0 = t0[m], a1 = t1[m];
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = 4 * b + j;
+        if (i < N) {
+            const uint32_t u = mix32(seed, (uint64_t)m, (uint64_t)i, 0);
+            const int gv = (u >= a0) + (u >= a1);
+            uint32_t code = gv == 2 ? 0u : (gv == 1 ? 2u : 3u);
+            if (miss_thr && mix32(seed, (uint64_t)m, (uint64_t)i, 1) < miss_thr) code = 1u;
+            v |= code << (2 * j);
+        }
+    }
+    out[r * B0 + b] = (uint8_t)v;
+}
+
+int k_synth_bed(sgb_ctx *h, int64_t m0, int64_t nm, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, uint32_t miss_thr,
+                int64_t N, uint8_t *d_out)
+{
+    const int64_t B0 = (N + 3) / 4;
+    for (int64_t y0 = 0; y0 < nm; y0 += 65535) {
+        const int64_t ny = nm - y0 < 65535 ? nm - y0 : 65535;
+        synth_bed_kernel<<<dim3((unsigned)cdiv(B0, 256), (unsigned)ny), 256, 0, h->stream>>>(m0 + y0, seed, d_t0, d_t1, miss_thr, N, d_out + y0 * B0);
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
 int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, int32_t *d_ac)
 {
     // mode selected by d_ac: non-null => count pass over all M0 raw markers; null => fill local rows (h->ws holds rows)

@@ -143,6 +143,8 @@ int k_repack(sgb_ctx *h, const uint8_t *d_bed, int64_t B0, const int32_t *d_src_
 int k_gather_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, const int64_t *d_rows, int nrows, int64_t nbytes, uint8_t *d_out);
 int k_transpose(sgb_ctx *h);   // dG -> dGt
 int k_synth(sgb_ctx *h, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, int32_t *d_ac);
+int k_synth_bed(sgb_ctx *h, int64_t m0, int64_t nm, uint64_t seed, const uint32_t *d_t0, const uint32_t *d_t1, uint32_t miss_thr,
+                int64_t N, uint8_t *d_out);
 
 // tensor engine: out[r][c*8+l] += sum_k P[r][k] * L[c][k][l]  (int32, exact)
 enum { SGB_PLANE_VALUE = 0, SGB_PLANE_IS2 = 1 };   // which function of the genotype the decode feeds the MMA

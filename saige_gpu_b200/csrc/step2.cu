@@ -1002,9 +1002,11 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     if (n_markers <= 0) return 0;
     const int64_t B0 = (n_fam + 3) / 4;
     if (B0 > 200 * 1024) return sgb_fail(h, "step2: more than 819,200 samples in the .fam are not supported yet");
-    // chunks of <= 256 MB of raw rows (several waves of CTAs each), double-buffered through pinned memory: the host copy of chunk c+1 and the
-    // D2H of chunk c-1's results overlap the kernel of chunk c
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)256 << 20) / B0));
+    // chunks of <= 1 GB of raw rows, double-buffered: the H2D of chunk c+1 and the D2H of chunk c-1's results overlap the kernels
+    // of chunk c.  The chunk is this large for the flagged variants: a saddle-point variant keeps one CTA busy for milliseconds
+    // (~20 passes over all samples), so the per-variant kernel only fills the machine (444 resident CTAs) when a chunk holds
+    // >= ~10^4 variants of which ~5 % are flagged (measured: 43 us per flagged variant with 256 MB chunks at N = 200k)
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)1 << 30) / B0));
     const size_t cbytes = (size_t)chunk * B0, obytes = sizeof(double) * (size_t)chunk * S2_NOUT;
     if (!s->pin[0] || s->pin_bytes < cbytes) {
         for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); s->pin[i] = nullptr; }

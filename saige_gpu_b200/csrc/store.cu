@@ -504,6 +504,38 @@ extern "C" int sgb_setgeno_mem(sgb_ctx *h, const uint8_t *bed_body, int64_t n_fa
     return setgeno_impl(h, rd, n_fam, n_bim, sub, n_sub, indicator, diagOne, vr_idx, n_vr);
 }
 
+// Bench / test input: raw PLINK .bed rows of the synthetic markers [m0, m1) written to a HOST buffer (generated on the device in
+// 256 MB pieces, bit-identical to the oracle's generator).  t0 / t1 hold the thresholds of those markers only.
+extern "C" int sgb_synth_bed_rows(sgb_ctx *h, int64_t N, int64_t m0, int64_t m1, uint64_t seed, const uint32_t *t0, const uint32_t *t1,
+                                  double miss_rate, uint8_t *out)
+{
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (N <= 0 || m1 < m0) return sgb_fail(h, "synth_bed_rows: bad dimensions");
+    const int64_t nm = m1 - m0, B0 = (N + 3) / 4;
+    if (nm == 0) return 0;
+    const int64_t piece = std::max<int64_t>(1, ((int64_t)256 << 20) / B0);
+    uint32_t *d_t0 = nullptr, *d_t1 = nullptr; uint8_t *d_buf = nullptr, *pin = nullptr;
+    CUDA_OK(h, cudaMalloc((void **)&d_t0, sizeof(uint32_t) * nm));
+    CUDA_OK(h, cudaMalloc((void **)&d_t1, sizeof(uint32_t) * nm));
+    CUDA_OK(h, cudaMalloc((void **)&d_buf, (size_t)std::min(piece, nm) * B0));
+    CUDA_OK(h, cudaMallocHost((void **)&pin, (size_t)std::min(piece, nm) * B0));
+    CUDA_OK(h, cudaMemcpy(d_t0, t0, sizeof(uint32_t) * nm, cudaMemcpyHostToDevice));
+    CUDA_OK(h, cudaMemcpy(d_t1, t1, sizeof(uint32_t) * nm, cudaMemcpyHostToDevice));
+    const uint32_t thr = (uint32_t)(miss_rate * 4294967296.0);
+    int rc = 0;
+    for (int64_t p0 = 0; p0 < nm && !rc; p0 += piece) {
+        const int64_t np = std::min(piece, nm - p0);
+        // the hash is keyed by the GLOBAL marker index; the threshold arrays are local to [m0, m1)
+        rc = k_synth_bed(h, m0 + p0, np, seed, d_t0 - m0, d_t1 - m0, thr, N, d_buf);
+        if (rc) break;
+        if (cudaMemcpyAsync(pin, d_buf, (size_t)np * B0, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = sgb_fail(h, "synth_bed_rows: copy failed"); break; }
+        memcpy(out + (size_t)p0 * B0, pin, (size_t)np * B0);
+    }
+    cudaFree(d_t0); cudaFree(d_t1); cudaFree(d_buf); cudaFreeHost(pin);
+    return rc;
+}
+
 extern "C" int sgb_setgeno_synth(sgb_ctx *h, int64_t N, int64_t M0, uint64_t seed, const uint32_t *t0, const uint32_t *t1)
 {
     CUDA_OK(h, cudaSetDevice(h->device));
