@@ -179,9 +179,13 @@ int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *
                         const int32_t *pos_in_fam);
 /* mainMarkerInCPP loop body (Main.cpp:229-520) for n_markers raw PLINK rows (ceil(n_fam/4) bytes each, A1 = ALT):
  * getOneMarker -> filter -> imputeGenoAndFlip (best_guess) -> scoreTestFast -> SPA / SPA_fast (SAIGE_test.cpp:212-292,
- * 345-640).  out[n_markers x 28] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
+ * 345-640).  out[n_markers x 32] row-major: tested(0/1), AC_Allele2, AF_Allele2, MissingRate, BETA, SE, Tstat, var,
  * p.value, p.value.NA, Is.SPA, AF_case, AF_ctrl, N_case, N_ctrl, N_case_hom, N_case_het, N_ctrl_hom, N_ctrl_het, var2,
- * Is.Firth, Firth converged, BETA_c, SE_c, Tstat_c, var_c, p.value_c, p.value.NA_c (NaN without sgb_step2_set_condition).
+ * Is.Firth, Firth converged, BETA_c, SE_c, Tstat_c, var_c, p.value_c, p.value.NA_c (NaN without sgb_step2_set_condition),
+ * then the NATURAL LOGS of p.value, p.value.NA, p.value_c, p.value.NA_c: finite where the p-value itself underflows a double
+ * (stat > ~1490).  There the reference switches to log-scale p-values and prints them as "%.1fE%d" strings
+ * (SAIGE_test.cpp:255-284, 531-582); the log columns carry that case: the saddle-point branch, the standard errors and the
+ * Firth cut-off use them, and the table writer prints mantissa / exponent from them when p.value == 0.
  * se_two_sided = 1: SE of SPA-adjusted variants = |BETA| / |qnorm(p/2)| (matches the reference's bundled golden tables);
  * 0: |BETA| / qnorm(p, upper) as this fork's source has it (SAIGE_test.cpp:523-526). */
 /* is_Firth_beta / pCutoffforFirth (SAIGE_test.cpp:573-633; fast_logistf_fit_simple :893-986): variants of a binary trait

@@ -24,7 +24,7 @@ Not implemented: conditional analysis, sparse-GRM variance, categorical variance
 import math
 
 import numpy as np
-from scipy import stats
+from scipy import special, stats
 
 EPS25 = np.finfo(np.float64).eps ** 0.25          # tol = eps^0.25 (SAIGE_test.cpp:515-516)
 
@@ -121,11 +121,24 @@ def _saddle_prob(zeta, K0f, K2f, q):
         v = zeta * np.sqrt(k2)
         if w != 0:
             Z = w + np.log(v / w) / w
+            _saddle_prob.last_log = float(special.log_ndtr(-abs(Z)))       # log |p| (R::pnorm(..., logp), SPA_binary.cpp:190-200)
             return (stats.norm.sf(Z) if Z > 0 else -stats.norm.cdf(Z)), True
+    _saddle_prob.last_log = -np.inf
     return 0.0, False
 
 
-def spa_pvalue(mu, gt, q, qinv, pval_noadj, idx_nz, fast, var2=None):
+def log_erfc(x):
+    """log erfc(x), finite where erfc underflows: log of the chi-square(1) upper tail at stat = 2 x^2 (R::pchisq(..., log = TRUE),
+    SAIGE_test.cpp:274)."""
+    return float(np.log(special.erfc(x))) if x < 20 else float(np.log(special.erfcx(x)) - x * x)
+
+
+def qnorm_from_logp(logp):
+    """|qnorm(p, lower = FALSE, log.p = TRUE)| (SAIGE_test.cpp:531)."""
+    return abs(float(special.ndtri_exp(logp)))
+
+
+def spa_pvalue(mu, gt, q, qinv, pval_noadj, idx_nz, fast, var2=None, logp_noadj=None):
     """SPA / SPA_fast (SPA.cpp:20-185)."""
     gpos, gneg = gt[gt > 0].sum(), gt[gt < 0].sum()
     if fast:
@@ -142,15 +155,22 @@ def spa_pvalue(mu, gt, q, qinv, pval_noadj, idx_nz, fast, var2=None):
         K2f = lambda t: _K2(t, mu, gt)
     r1, _, c1 = _getroot(K1f(q), K2f, q, gpos, gneg, EPS25, fast=fast)
     r2, _, c2 = _getroot(K1f(qinv), K2f, qinv, gpos, gneg, EPS25, fast=fast)
+    if logp_noadj is None:
+        with np.errstate(divide="ignore"):
+            logp_noadj = float(np.log(pval_noadj))
+    spa_pvalue.last_log = logp_noadj
     if not (c1 and c2):
         return pval_noadj, False
     conv = True
     p1, s1 = _saddle_prob(r1, K0f, K2f, q)
+    l1 = _saddle_prob.last_log
     p2, s2 = _saddle_prob(r2, K0f, K2f, qinv)
+    l2 = _saddle_prob.last_log
     if not s1:
-        conv, p1 = False, pval_noadj / 2
+        conv, p1, l1 = False, pval_noadj / 2, logp_noadj - np.log(2.0)
     if not s2:
-        conv, p2 = False, pval_noadj / 2
+        conv, p2, l2 = False, pval_noadj / 2, logp_noadj - np.log(2.0)
+    spa_pvalue.last_log = float(np.logaddexp(l1, l2))                  # add_logp (SPA.cpp:95)
     return abs(p1) + abs(p2), conv
 
 
@@ -304,9 +324,11 @@ def score_test_fast(M, G, idx, var_ratio=None):
     var1 = var2 * (float(np.asarray(M["varRatio"]).reshape(-1)[0]) if var_ratio is None else var_ratio)
     S = (float(res1 @ gt1) - float((M["S_a"] - res1 @ X1) @ Z)) / M["tau"][0]
     stat = S * S / var1
-    pval = 1.0 if var1 <= np.finfo(float).tiny or not np.isfinite(stat) else float(stats.chi2.sf(stat, 1))
+    ok = not (var1 <= np.finfo(float).tiny or not np.isfinite(stat))
+    pval = float(stats.chi2.sf(stat, 1)) if ok else 1.0
+    logp = log_erfc(np.sqrt(stat / 2)) if ok else 0.0                  # the log-scale p-value of SAIGE_test.cpp:273-283
     beta = S / var1
-    return dict(Beta=beta, seBeta=abs(beta) / np.sqrt(abs(stat)), pval=pval, Tstat=S, var1=var1, var2=var2)
+    return dict(Beta=beta, seBeta=abs(beta) / np.sqrt(abs(stat)), pval=pval, logp=logp, Tstat=S, var1=var1, var2=var2)
 
 
 def firth_fit(gt, y, offset, maxit=50, maxstep=15, xconv=1e-5, gconv=1e-5):
@@ -380,6 +402,8 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     st = score_test_fast(M, G, idx, assign_variance_ratio(M, min(alt_count, 2 * n - alt_count)))
     std_stat = abs(st["Tstat"]) / np.sqrt(st["var1"])
     pval, se, is_spa = st["pval"], st["seBeta"], False
+    logp = st["logp"]
+    islog = st["pval"] == 0                                             # ispvallog: the p-value underflowed (SAIGE_test.cpp:270-284)
     # exact test of rare variants (Main.cpp:408-422: MAC after imputation <= g_MACCutoffforER; SAIGE_test.cpp:426-431, 592-620)
     mac_after = min(alt_count, 2 * n - alt_count)
     is_er = (M["trait"] == "binary" and mac_after <= max_MAC_for_ER and (std_stat > spa_cutoff or np.isnan(std_stat)))
@@ -388,27 +412,28 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
         p2mean = float(np.delete(mu, idx).mean())
         pval = er_pvalue(G[idx], mu[idx], M["res"][idx], p2mean, n, int((M["y"] == 1).sum()))
         se = 0.0 if pval / 2 <= 0 else abs(st["Beta"]) / abs(stats.norm.ppf(pval / 2))
+        logp = float(np.log(pval))
     elif np.isfinite(std_stat) and std_stat > spa_cutoff and M["trait"] == "binary":
         gt = G - M["XXVX_inv"] @ (M["XV"] @ G)                      # getadjGFast
         m1 = float(M["mu"] @ gt)
         q = st["Tstat"] / np.sqrt(st["var1"] / st["var2"]) + m1
         qinv = -abs(q - m1) + m1 if q - m1 > 0 else (m1 if q == m1 else abs(q - m1) + m1)
         fast = (n - len(idx)) / n >= 0.5
-        pspa, conv = spa_pvalue(M["mu"], gt, q, qinv, st["pval"], idx, fast, st["var2"])
-        if conv and pspa != 0:
+        pspa, conv = spa_pvalue(M["mu"], gt, q, qinv, st["pval"], idx, fast, st["var2"], st["logp"])
+        if conv and (pspa != 0 or islog):                              # SAIGE_test.cpp:541: only the linear scale un-converges on 0
             is_spa = True
-            pval = pspa
+            pval, logp = pspa, spa_pvalue.last_log
             # SE from the SPA p-value: the reference's bundled golden table corresponds to |qnorm(p/2)| (upstream SAIGE);
             # this fork's source has qnorm(p, upper tail) (SAIGE_test.cpp:523-526) -> se_two_sided=False
-            se = abs(st["Beta"]) / abs(stats.norm.isf(pspa / 2 if se_two_sided else pspa))
+            se = abs(st["Beta"]) / qnorm_from_logp(logp - np.log(2.0) if se_two_sided else logp)
     beta, is_firth, firth_conv = st["Beta"], False, False
-    if is_Firth_beta and M["trait"] == "binary" and pval <= pCutoffforFirth:
+    if is_Firth_beta and M["trait"] == "binary" and logp <= np.log(pCutoffforFirth):
         # SAIGE_test.cpp:573-633.  firth_se_from_fit: SE = the fit's own sqrt(cov[1,1]) (what the reference's bundled
         # positive-signal result holds); otherwise |beta| / |qnorm| of the p-value as this fork's source has it (:632)
         gt = G - M["XXVX_inv"] @ (M["XV"] @ G)
         beta, se_fit, firth_conv = firth_fit(gt, M["y"], M["offset"])
         is_firth = True
-        se = se_fit if firth_se_from_fit else abs(beta) / abs(stats.norm.isf(pval / 2 if (se_two_sided or is_er) else pval))
+        se = se_fit if firth_se_from_fit else abs(beta) / qnorm_from_logp(logp - np.log(2.0) if (se_two_sided or is_er) else logp)
     sgn = -1.0 if flip else 1.0
     extra = {}
     if cond is not None:
@@ -451,6 +476,7 @@ def test_marker(M, Graw, min_maf=0.0, min_mac=0.5, max_missing=0.15, spa_cutoff=
     if flip:
         n_case_hom, n_ctrl_hom = int(case.sum()) - n_case_het - n_case_hom, int(ctrl.sum()) - n_ctrl_het - n_ctrl_hom
     return dict(**extra, N_case_hom=n_case_hom, N_case_het=n_case_het, N_ctrl_hom=n_ctrl_hom, N_ctrl_het=n_ctrl_het, AC_Allele2=alt_count, AF_Allele2=alt_freq, MissingRate=missing_rate, BETA=sgn * beta, SE=se,
-                Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], Is_SPA=is_spa, Is_ER=is_er,
+                Tstat=sgn * st["Tstat"], var=st["var1"], p_value=pval, p_value_NA=st["pval"], log_p_value=logp, log_p_value_NA=st["logp"],
+                Is_SPA=is_spa, Is_ER=is_er,
                 Is_Firth=is_firth, Firth_converged=firth_conv,
                 AF_case=afc, AF_ctrl=aft, N_case=int(case.sum()), N_ctrl=int(ctrl.sum()))

@@ -370,7 +370,8 @@ class SaigeB200:
     # ---- step 2: setSAIGEobjInCPP + mainMarkerInCPP ----
     STEP2_COLUMNS = ("tested", "AC_Allele2", "AF_Allele2", "MissingRate", "BETA", "SE", "Tstat", "var", "p.value", "p.value.NA",
                      "Is.SPA", "AF_case", "AF_ctrl", "N_case", "N_ctrl", "N_case_hom", "N_case_het", "N_ctrl_hom", "N_ctrl_het",
-                     "var2", "Is.Firth", "Firth.converged", "BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "p.value.NA_c")
+                     "var2", "Is.Firth", "Firth.converged", "BETA_c", "SE_c", "Tstat_c", "var_c", "p.value_c", "p.value.NA_c",
+                     "log.p.value", "log.p.value.NA", "log.p.value_c", "log.p.value.NA_c")
 
     def setSAIGEobjInCPP(self, model, varRatio, SPAcutoff, pos_in_fam):
         """model: dict with mu, res, mu2, y, X, XVX, XXVX_inv, XVX_inv_XV, S_a, tau, trait (readInGLMM.R:39-170)."""

@@ -330,7 +330,7 @@ static void shard_markers(const sgb_ctx *h, int q, std::vector<int64_t> &glob)
 {
     glob.clear();
     for (int64_t g = 0; g < h->M; g++)
-        if ((g / SGB_SHARD_BLOCK) % h->world == q) glob.push_back(g);
+        if (sgb_owner_of(h, g) == q) glob.push_back(g);
 }
 
 static int dense_build(sgb_ctx *h, int limbs, int64_t first_block_row, int64_t n_block_rows)

@@ -62,6 +62,7 @@ struct sgb_ctx {
     std::vector<uint8_t> qc_mask;
     std::vector<uint8_t> vr_packed;          // Mvr x ceil(N/4), device coding (value bits), host resident
     std::vector<int64_t> loc2glob;           // local row -> global QC'd marker index (monotone)
+    std::vector<int32_t> qc2raw;             // QC'd marker index -> raw (.bim) marker index: the rank map is defined on RAW markers
 
     // device genotype store, device coding: 2 bits per genotype = number of A1 copies (0,1,2), sample i of a
     // marker in the pair-ternary nibble coding of kernels.cu (sgb_pack4); all padding is genotype 0.
@@ -232,6 +233,9 @@ int sgb_diag_device(sgb_ctx *h);
 int sgb_diag_loco_device(sgb_ctx *h);
 int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const double *dB, int k, int maxiter, double tol,
                    int loco, double *dX, int32_t *iters);
+// rank that stores QC'd marker gidx: raw markers are dealt block-cyclically (SGB_SHARD_BLOCK), so a rank's rows of BOTH ingest
+// passes come from the same 1/world of the file and chromosomes stay balanced over the ranks
+inline int sgb_owner_of(const sgb_ctx *h, int64_t gidx) { return (int)(((int64_t)h->qc2raw[(size_t)gidx] / SGB_SHARD_BLOCK) % h->world); }
 int sgb_allreduce_sum(sgb_ctx *h, double *d, int64_t n);
 int sgb_allreduce_sum_i32(sgb_ctx *h, int32_t *d, int64_t n);
 int sgb_dist_init(sgb_ctx *h, int rank, int world, const void *id128);

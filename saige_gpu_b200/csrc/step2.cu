@@ -26,7 +26,7 @@
 
 #define S2_MAXP 16
 #define S2_THREADS 256
-#define S2_NOUT 28      // doubles per variant in the result table (see include/saige_b200.h)
+#define S2_NOUT 32      // doubles per variant in the result table (see include/saige_b200.h)
 #define S2_MAXCOND 4    // conditioning markers
 #define S2_MAXCATE 8    // MAC categories of the variance ratio (the reference's default has 2)
 
@@ -68,6 +68,27 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
 #pragma unroll
     for (int i = 0; i < S2_THREADS / 32; i++) t += sm[i];
     return t;
+}
+
+// log of the chi-square(1) upper tail at stat = 2 x^2, i.e. log erfc(x), finite where erfc underflows (x > 26.5): the reference
+// switches to R::pchisq(..., log = TRUE) there and prints "%.1fE%d" strings (SAIGE_test.cpp:255-284)
+__device__ __forceinline__ double s2_log_erfc(double x) { return x < 20.0 ? log(erfc(x)) : log(erfcx(x)) - x * x; }
+// |z| whose upper normal tail is exp(lp): qnorm(p, lower = FALSE, log.p = TRUE) of the reference (SAIGE_test.cpp:531)
+__device__ __forceinline__ double s2_qnorm_from_logp(double lp)
+{
+    if (lp > -700.0) return fabs(normcdfinv(exp(lp)));
+    double z = sqrt(-2.0 * lp);
+    for (int it = 0; it < 8; it++) {
+        const double x = z * 0.7071067811865476;
+        const double lt = -0.6931471805599453 + log(erfcx(x)) - x * x;      // log of the upper tail at z
+        z += (lt - lp) * 1.2533141373155001 * erfcx(x);                     // Newton: d/dz log tail = -density / tail
+    }
+    return z;
+}
+__device__ __forceinline__ double s2_logaddexp(double a, double b)
+{
+    const double hi = fmax(a, b), lo = fmin(a, b);
+    return isinf(hi) ? hi : hi + log1p(exp(lo - hi));
 }
 
 // genotype of model sample i after flip / imputation: copies of the (possibly flipped) ALT allele
@@ -313,13 +334,13 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     const double var1 = var2 * varRatio;
     const double S = (r0 - saz) / M.tau0;
     double stat = S * S / var1;
-    double pval_noadj;
+    double pval_noadj, lp_noadj = 0.0;                                       // p-value and its natural log (finite when p underflows)
     if (var1 <= 2.2250738585072014e-308) pval_noadj = 1.0;
-    else if (isfinite(stat)) pval_noadj = erfc(sqrt(stat * 0.5));            // chi-square(1) upper tail
+    else if (isfinite(stat)) { pval_noadj = erfc(sqrt(stat * 0.5)); lp_noadj = s2_log_erfc(sqrt(stat * 0.5)); }   // chi-square(1) upper tail
     else { pval_noadj = 1.0; stat = 0.0; }
     const double Beta = S / var1;
     double seBeta = fabs(Beta) / sqrt(fabs(stat));
-    double pval = pval_noadj, isSPA = 0.0;
+    double pval = pval_noadj, lp = lp_noadj, isSPA = 0.0;
 
     const double StdStat = fabs(S) / sqrt(var1);
     // ---- exact test of rare variants (binary traits): MAC after imputation <= max_MAC_for_ER and a score beyond the SPA
@@ -356,13 +377,14 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             er_pv = sgb_er_exact_pvalue(k, g1, p1, r1, p2mean, (double)N, M.ncase_tot, 1e-6);
         }
         __syncthreads();
-        pval = er_pv;
+        pval = er_pv; lp = log(er_pv);
         // SE from the exact p-value, |qnorm(p/2)| (SAIGE_test.cpp:606-614; quantile(0) overflows there -> 0)
         seBeta = pval * 0.5 > 0.0 ? fabs(Beta) / fabs(normcdfinv(pval * 0.5)) : 0.0;
     }
     // ---- conditional analysis (t_isCondition, SAIGE_test.cpp:640-660): score and variance after projecting out the
     // conditioning markers.  gtilde^T P2 = g^T P2 - W^T (XXVX_inv^T P2): one pass over the non-zero genotypes ----
     double Tc = nan(""), vc = nan(""), Beta_c = nan(""), se_c = nan(""), pval_c = nan(""), pval_noadj_c = nan(""), stat_c = 0.0;
+    double lp_c = nan(""), lp_noadj_c = nan("");
     if (M.n_cond > 0) {
         double cp[S2_MAXCOND];
 #pragma unroll
@@ -387,12 +409,13 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             vc -= g1p2[c] * acc;
         }
         stat_c = Tc * Tc / vc;
+        lp_noadj_c = 0.0;
         if (vc <= 2.2250738585072014e-308) { pval_noadj_c = 1.0; stat_c = 0.0; }
-        else if (isfinite(stat_c)) pval_noadj_c = erfc(sqrt(stat_c * 0.5));
+        else if (isfinite(stat_c)) { pval_noadj_c = erfc(sqrt(stat_c * 0.5)); lp_noadj_c = s2_log_erfc(sqrt(stat_c * 0.5)); }
         else { pval_noadj_c = 1.0; stat_c = 0.0; }
         Beta_c = Tc / vc;
         se_c = fabs(Beta_c) / sqrt(stat_c);
-        pval_c = pval_noadj_c;
+        pval_c = pval_noadj_c; lp_c = lp_noadj_c;
     }
     // ---- saddle-point approximation (binary traits): the marginal test when |T|/sqrt(var) > cutoff and the exact test did
     // not take the variant, the conditional test when its own statistic exceeds cutoff^2 (SAIGE_test.cpp:699).  The
@@ -441,10 +464,12 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             if (fast) { k0 += NAmu * t + 0.5 * NAsigma * t * t; k1 += NAmu + NAsigma * t; k2 += NAsigma; }
         };
         // SPA / SPA_fast (SPA.cpp:20-185) for the statistic q: both tails; false when a root or a saddle point fails
-        auto spa = [&](double q, double pnoadj, double &pspa) -> bool {
+        // log-scale twin of every probability: the reference runs this branch with logp = TRUE when the unadjusted p-value
+        // underflowed (SPA.cpp:20-110, Get_Saddle_Prob_Binom's R::pnorm(..., logp)); here both scales are always carried
+        auto spa = [&](double q, double pnoadj, double lpnoadj, double &pspa, double &lpspa) -> bool {
             double qinv;
             if (q - m1 > 0) qinv = -fabs(q - m1) + m1; else if (q - m1 == 0) qinv = m1; else qinv = fabs(q - m1) + m1;
-            double pside[2]; bool conv_all = true, saddle_all = true;
+            double pside[2], lside[2]; bool conv_all = true, saddle_all = true;
             for (int side = 0; side < 2; side++) {
                 const double qq = side == 0 ? q : qinv;
                 double root; bool conv = true;
@@ -480,7 +505,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
                 if (!conv) { conv_all = false; break; }
                 // Get_Saddle_Prob[_fast]_Binom (SPA_binary.cpp:146-214, 276-330): Lugannani-Rice
                 double k0, k1, k2;
-                double ps = 0.0; bool isSaddle = false;
+                double ps = 0.0, lps = -INFINITY; bool isSaddle = false;
                 if (isfinite(root)) {
                     cgf(root, k0, k1, k2, true);
                     const double temp1 = root * qq - k0;
@@ -489,34 +514,38 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
                         if (w != 0) {
                             const double Zt = w + log(v / w) / w;
                             ps = Zt > 0 ? 0.5 * erfc(Zt * 0.7071067811865476) : -0.5 * erfc(-Zt * 0.7071067811865476);
+                            lps = -0.6931471805599453 + s2_log_erfc(fabs(Zt) * 0.7071067811865476);      // log |ps|
                             isSaddle = true;
                         }
                     }
                 }
-                if (!isSaddle) { saddle_all = false; ps = pnoadj / 2; }
-                pside[side] = ps;
+                if (!isSaddle) { saddle_all = false; ps = pnoadj / 2; lps = lpnoadj - 0.6931471805599453; }
+                pside[side] = ps; lside[side] = lps;
             }
             if (!conv_all) return false;
             pspa = fabs(pside[0]) + fabs(pside[1]);
-            return saddle_all && pspa != 0;
+            lpspa = s2_logaddexp(lside[0], lside[1]);
+            // a vanished adjusted p-value un-converges the test only on the linear scale (SAIGE_test.cpp:541): when the
+            // unadjusted p-value already underflowed the reference is on the log scale and keeps the saddle-point result
+            return saddle_all && (pspa != 0 || pnoadj == 0);
         };
         if (spa_u) {
-            double pspa;
-            if (spa(S / sqrt(var1 / var2) + m1, pval_noadj, pspa)) {
-                isSPA = 1.0; pval = pspa;
+            double pspa, lpspa;
+            if (spa(S / sqrt(var1 / var2) + m1, pval_noadj, lp_noadj, pspa, lpspa)) {
+                isSPA = 1.0; pval = pspa; lp = lpspa;
                 // SE from the SPA p-value.  se_two_sided: |qnorm(p/2)| (what produced the reference's bundled golden tables);
                 // otherwise qnorm(p, upper tail) as written in this fork's source (SAIGE_test.cpp:523-526).
-                const double qv = fabs(normcdfinv(se_two_sided ? pspa * 0.5 : pspa));
+                const double qv = s2_qnorm_from_logp(se_two_sided ? lpspa - 0.6931471805599453 : lpspa);
                 seBeta = fabs(Beta) / qv;
             }
         }
         if (spa_c) {
             // the reference's bundled conditional table reports the adjusted p-value itself and SE = |BETA_c| / |qnorm(p/2)|
             // (this fork's source prints half of it, SAIGE_test.cpp:752: the fixture wins)
-            double pspa;
-            if (spa(Tc / sqrt(vc / var2) + m1, pval_noadj_c, pspa)) {
-                pval_c = pspa;
-                se_c = fabs(Beta_c) / fabs(normcdfinv(pspa * 0.5));
+            double pspa, lpspa;
+            if (spa(Tc / sqrt(vc / var2) + m1, pval_noadj_c, lp_noadj_c, pspa, lpspa)) {
+                pval_c = pspa; lp_c = lpspa;
+                se_c = fabs(Beta_c) / s2_qnorm_from_logp(lpspa - 0.6931471805599453);
             }
         }
     }
@@ -524,7 +553,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     // x = [1, gtilde], offset = the null model's; Newton steps with the modified score x^T((y - pi) + h (0.5 - pi)), h the hat
     // values of sqrt(W) x; every quantity is a 2 x 2 / 2-vector block reduction over the samples (SAIGE_test.cpp:893-986)
     double BetaOut = Beta, isFirth = 0.0, firthConv = 0.0;
-    if (M.firth && M.binary && pval <= M.firth_cutoff) {
+    if (M.firth && M.binary && lp <= log(M.firth_cutoff)) {            // on the log scale: also right when p underflowed (SAIGE_test.cpp:572-582)
         isFirth = 1.0;
         double b0 = 0.0, b1 = 0.0, c00 = nan(""), c01 = nan(""), c11 = nan("");
         int iter = 0;
@@ -562,7 +591,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
             BetaOut = b1;
             // SE: the fit's own (what the reference's bundled positive-signal result holds) or |beta| / |qnorm| of the p-value
             // as this fork's source has it (SAIGE_test.cpp:632)
-            seBeta = M.firth_se_from_fit ? sqrt(c11) : fabs(b1) / fabs(normcdfinv((se_two_sided || isER) ? pval * 0.5 : pval));
+            seBeta = M.firth_se_from_fit ? sqrt(c11) : fabs(b1) / s2_qnorm_from_logp((se_two_sided || isER) ? lp - 0.6931471805599453 : lp);
         }
     }
     if (tid == 0) {
@@ -575,6 +604,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         o[11] = afc; o[12] = aft; o[13] = ncase; o[14] = nctrl; o[15] = case_hom; o[16] = case_het; o[17] = ctrl_hom; o[18] = ctrl_het;
         o[19] = var2; o[20] = isFirth; o[21] = firthConv;
         o[22] = sgn * Beta_c; o[23] = se_c; o[24] = sgn * Tc; o[25] = vc; o[26] = pval_c; o[27] = pval_noadj_c;
+        o[28] = lp; o[29] = lp_noadj; o[30] = lp_c; o[31] = lp_noadj_c;
     }
 }
 
@@ -765,16 +795,16 @@ __global__ void __launch_bounds__(128) s2_finish_kernel(s2_model M, const int32_
     const double var1 = var2 * varRatio;
     const double S = (r0 - saz) / M.tau0;
     double stat = S * S / var1;
-    double pval_noadj;
+    double pval_noadj, lp_noadj = 0.0;
     if (var1 <= 2.2250738585072014e-308) pval_noadj = 1.0;
-    else if (isfinite(stat)) pval_noadj = erfc(sqrt(stat * 0.5));
+    else if (isfinite(stat)) { pval_noadj = erfc(sqrt(stat * 0.5)); lp_noadj = s2_log_erfc(sqrt(stat * 0.5)); }
     else { pval_noadj = 1.0; stat = 0.0; }
     const double Beta = S / var1;
     const double seBeta = fabs(Beta) / sqrt(fabs(stat));
     const double StdStat = fabs(S) / sqrt(var1);
     const bool isER = M.binary && MACafter <= M.er_max_mac && nz <= (double)SGB_ER_MAXK && (StdStat > M.spa_cutoff || isnan(StdStat));
     const bool spa_u = !isER && M.binary && isfinite(StdStat) && StdStat > M.spa_cutoff;
-    const bool firth = M.firth && M.binary && pval_noadj <= M.firth_cutoff;
+    const bool firth = M.firth && M.binary && lp_noadj <= log(M.firth_cutoff);
     if (isER || spa_u || firth || M.n_cond > 0) {
         list[atomicAdd(list_count, 1)] = (int)m;          // step2_kernel writes this row
         return;
@@ -787,6 +817,7 @@ __global__ void __launch_bounds__(128) s2_finish_kernel(s2_model M, const int32_
     o[11] = afc; o[12] = aft; o[13] = ncase; o[14] = nctrl; o[15] = case_hom; o[16] = case_het; o[17] = ctrl_hom; o[18] = ctrl_het;
     o[19] = var2; o[20] = 0.0; o[21] = 0.0;
     for (int q = 22; q < S2_NOUT; q++) o[q] = nan("");
+    o[28] = lp_noadj; o[29] = lp_noadj;
 }
 
 // ---------------------------------------------------------------------------------------------------

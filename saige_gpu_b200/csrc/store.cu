@@ -189,7 +189,8 @@ static qc_out qc_marker(const sgb_ctx *h, int64_t N, int alleleCount, int numMis
     return o;
 }
 
-static bool owns(const sgb_ctx *h, int64_t gidx) { return (gidx / SGB_SHARD_BLOCK) % h->world == h->rank; }
+static bool owns_raw(const sgb_ctx *h, int64_t m) { return (m / SGB_SHARD_BLOCK) % h->world == h->rank; }     // raw marker m
+static bool owns(const sgb_ctx *h, int64_t gidx) { return sgb_owner_of(h, gidx) == h->rank; }                    // QC'd marker
 
 // allocate the device store for Mloc local markers and upload the per-marker fp64 constants
 static int alloc_store(sgb_ctx *h)
@@ -338,19 +339,21 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
 
     // ---- pass 1: counts for every raw marker ----
     nvtxRangePushA("setgeno_pass1_count");
-    // One rank: when the raw .bed fits beside the two packed copies it is uploaded ONCE and kept on the device for the
-    // re-pack.  Several ranks: the chunks are dealt round-robin, every rank reads and counts 1/world of the file and the
+    // The rank map is block-cyclic over RAW markers (blocks of SGB_SHARD_BLOCK), so the rows a rank will keep lie inside the
+    // same 1/world of the file it counts: every rank reads its blocks ONCE, keeps them on the device for the re-pack, and the
     // (allele count, missing count) vectors meet in one int32 allreduce -- the reference's SPMD ranks each read the whole
-    // file (FG.cpp:897-953).
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(M0, ((int64_t)256 << 20) / B0));
+    // file (FG.cpp:897-953).  Only when the raw rows do not fit beside the two packed copies they are read a second time.
+    const int64_t chunk = std::max<int64_t>(SGB_SHARD_BLOCK, std::min<int64_t>(M0, ((int64_t)256 << 20) / B0) / SGB_SHARD_BLOCK * SGB_SHARD_BLOCK);
+    int64_t M0mine = 0;                                                    // raw markers of this rank's blocks
+    for (int64_t b0 = 0; b0 < M0; b0 += SGB_SHARD_BLOCK) if (owns_raw(h, b0)) M0mine += std::min<int64_t>(SGB_SHARD_BLOCK, M0 - b0);
     size_t free_b = 0, total_b = 0;
     CUDA_OK(h, cudaMemGetInfo(&free_b, &total_b));
-    const size_t raw_total = (size_t)M0 * B0;
-    const bool keep_raw = h->world == 1 && raw_total * 3 + ((size_t)4 << 30) < free_b;      // raw + marker-major + sample-major copies + slack
+    const size_t raw_mine = (size_t)M0mine * B0;
+    const bool keep_raw = raw_mine * 3 + ((size_t)4 << 30) < free_b;      // raw + marker-major + sample-major copies + slack
     uint8_t *d_raw = nullptr; int32_t *d_ac = nullptr, *d_nm = nullptr;
-    CUDA_OK(h, cudaMalloc((void **)&d_raw, keep_raw ? raw_total : (size_t)chunk * B0));
-    CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * M0));
-    CUDA_OK(h, cudaMalloc((void **)&d_nm, sizeof(int32_t) * M0));
+    CUDA_OK(h, cudaMalloc((void **)&d_raw, keep_raw ? std::max<size_t>(raw_mine, 1) : (size_t)chunk * B0));
+    CUDA_OK(h, cudaMalloc((void **)&d_ac, sizeof(int32_t) * std::max<int64_t>(M0, 1)));
+    CUDA_OK(h, cudaMalloc((void **)&d_nm, sizeof(int32_t) * std::max<int64_t>(M0, 1)));
     if (h->world > 1) {
         CUDA_OK(h, cudaMemsetAsync(d_ac, 0, sizeof(int32_t) * M0, h->stream));
         CUDA_OK(h, cudaMemsetAsync(d_nm, 0, sizeof(int32_t) * M0, h->stream));
@@ -358,29 +361,42 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     stager st;
     SGB_TRY(st.init(h, (size_t)64 << 20));
     std::vector<int32_t> ac_raw(M0), nm_raw(M0);
-    int64_t ci = 0;
-    for (int64_t m0 = 0; m0 < M0; m0 += chunk, ci++) {
-        if (h->world > 1 && ci % h->world != h->rank) continue;
-        int64_t m1 = std::min(M0, m0 + chunk);
-        uint8_t *dst = keep_raw ? d_raw + (size_t)m0 * B0 : d_raw;
-        int rc = st.push(rd, m0, m1, dst);
-        if (rc) { st.destroy(); return rc; }
-        SGB_TRY(k_count_markers(h, dst, B0, m1 - m0, d_indmask, d_ac + m0, d_nm + m0));
+    // runs of consecutive owned raw markers inside a chunk (one run = the whole chunk on a single rank)
+    auto owned_runs = [&](int64_t m0, int64_t m1, std::vector<std::pair<int64_t, int64_t>> &runs) {
+        runs.clear();
+        for (int64_t b0 = m0; b0 < m1; b0 += SGB_SHARD_BLOCK) {
+            if (!owns_raw(h, b0)) continue;
+            const int64_t b1 = std::min(m1, b0 + SGB_SHARD_BLOCK);
+            if (!runs.empty() && runs.back().second == b0) runs.back().second = b1; else runs.emplace_back(b0, b1);
+        }
+    };
+    std::vector<std::pair<int64_t, int64_t>> runs;
+    std::vector<int64_t> raw_slot(keep_raw ? (size_t)((M0 + SGB_SHARD_BLOCK - 1) / SGB_SHARD_BLOCK) : 0, -1);   // raw block -> first row in d_raw
+    int64_t kept = 0;
+    for (int64_t m0 = 0; m0 < M0; m0 += chunk) {
+        const int64_t m1 = std::min(M0, m0 + chunk);
+        owned_runs(m0, m1, runs);
+        for (auto &r : runs) {
+            uint8_t *dst = keep_raw ? d_raw + (size_t)kept * B0 : d_raw + (size_t)(r.first - m0) * B0;
+            int rc = st.push(rd, r.first, r.second, dst);
+            if (rc) { st.destroy(); return rc; }
+            SGB_TRY(k_count_markers(h, dst, B0, r.second - r.first, d_indmask, d_ac + r.first, d_nm + r.first));
+            if (keep_raw) {
+                for (int64_t b0 = r.first; b0 < r.second; b0 += SGB_SHARD_BLOCK) raw_slot[(size_t)(b0 / SGB_SHARD_BLOCK)] = kept + (b0 - r.first);
+                kept += r.second - r.first;
+            }
+        }
         if (!keep_raw) CUDA_OK(h, cudaStreamSynchronize(h->stream));      // the chunk buffer is reused
     }
     if (h->world > 1) {
         SGB_TRY(sgb_allreduce_sum_i32(h, d_ac, M0));
         SGB_TRY(sgb_allreduce_sum_i32(h, d_nm, M0));
     }
-    CUDA_OK(h, cudaMemcpyAsync(ac_raw.data(), d_ac, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(h, cudaMemcpyAsync(nm_raw.data(), d_nm, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(h, cudaStreamSynchronize(h->stream));
-
     nvtxRangePop();
     // ---- host QC (fp32, reference order) ----
     h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
     h->afreq_vr.clear(); h->invstd_vr.clear(); h->mac_vr.clear(); h->ac_vr.clear(); h->index_vr.clear();
-    h->qc_mask.assign(M0, 0); h->loc2glob.clear();
+    h->qc_mask.assign(M0, 0); h->loc2glob.clear(); h->qc2raw.clear();
     std::vector<int32_t> fill_raw(M0, 0);
     std::vector<int8_t> kind(M0, 0);      // 1 = GRM store, 2 = VR store
     for (int64_t m = 0; m < M0; m++) {
@@ -390,7 +406,8 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
             int64_t gidx = (int64_t)h->afreq.size();
             h->afreq.push_back(q.afreq); h->invstd.push_back(q.invstd); h->mac.push_back(q.mac); h->ac.push_back(q.ac);
             h->qc_mask[m] = 1; kind[m] = 1;
-            if (owns(h, gidx)) h->loc2glob.push_back(gidx);
+            h->qc2raw.push_back((int32_t)m);
+            if (owns_raw(h, m)) h->loc2glob.push_back(gidx);
         }
         if (h->isVarRatio && q.passVR) {
             h->afreq_vr.push_back(q.afreq); h->invstd_vr.push_back(q.invstd); h->mac_vr.push_back(q.mac); h->ac_vr.push_back(q.ac);
@@ -408,50 +425,62 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
     uint8_t *d_vr = nullptr; int32_t *d_rows = nullptr, *d_fill = nullptr;
     CUDA_OK(h, cudaMalloc((void **)&d_rows, sizeof(int32_t) * chunk));
     CUDA_OK(h, cudaMalloc((void **)&d_fill, sizeof(int32_t) * chunk));
-    int64_t gidx = 0, lrow = 0, vrow = 0;
+    int64_t lrow = 0, vrow = 0;
     std::vector<int32_t> rows, fills, vrows, vfills;
+    // A hold-out marker of the variance ratio is needed by every rank (the host-side store is replicated) but its raw row sits
+    // on ONE rank's device: the owner re-packs it and the packed rows are summed over the ranks below (zeros elsewhere).
     for (int64_t m0 = 0; m0 < M0; m0 += chunk) {
         int64_t m1 = std::min(M0, m0 + chunk);
-        rows.clear(); fills.clear(); vrows.clear(); vfills.clear();
-        for (int64_t m = m0; m < m1; m++) {
-            if (kind[m] == 1) { if (owns(h, gidx)) { rows.push_back((int32_t)(m - m0)); fills.push_back(fill_raw[m]); } gidx++; }
-            else if (kind[m] == 2) { vrows.push_back((int32_t)(m - m0)); vfills.push_back(fill_raw[m]); }
-        }
-        if (rows.empty() && vrows.empty()) continue;
-        const uint8_t *d_chunk = keep_raw ? d_raw + (size_t)m0 * B0 : d_raw;
-        if (!keep_raw) {
-            // second read, of the rows this rank keeps only: runs of needed raw markers (gaps below 64 markers are read
-            // through) go to their place in the chunk buffer, so a rank moves ~1/world of the file here as well
-            size_t ia = 0, ib = 0;
-            int64_t run0 = -1, run1 = -1;
-            while (ia < rows.size() || ib < vrows.size() || run0 >= 0) {
-                int64_t nxt = -1;
-                if (ia < rows.size() && (ib >= vrows.size() || rows[ia] <= vrows[ib])) nxt = rows[ia++];
-                else if (ib < vrows.size()) nxt = vrows[ib++];
-                if (nxt >= 0 && run0 >= 0 && nxt < run1 + 64) { run1 = nxt + 1; continue; }
-                if (run0 >= 0) {
-                    int rc = st.push(rd, m0 + run0, m0 + run1, d_raw + (size_t)run0 * B0);
-                    if (rc) { st.destroy(); return rc; }
+        owned_runs(m0, m1, runs);
+        for (auto &r : runs) {
+            rows.clear(); fills.clear(); vrows.clear(); vfills.clear();
+            for (int64_t m = r.first; m < r.second; m++) {
+                if (kind[m] == 1) { rows.push_back((int32_t)(m - r.first)); fills.push_back(fill_raw[m]); }
+                else if (kind[m] == 2) { vrows.push_back((int32_t)(m - r.first)); vfills.push_back(fill_raw[m]); }
+            }
+            if (rows.empty() && vrows.empty()) continue;
+            const uint8_t *d_chunk;
+            if (keep_raw) d_chunk = d_raw + (size_t)raw_slot[(size_t)(r.first / SGB_SHARD_BLOCK)] * B0;
+            else {                                     // second read of this run (raw rows too large to keep on the device)
+                int rc = st.push(rd, r.first, r.second, d_raw);
+                if (rc) { st.destroy(); return rc; }
+                d_chunk = d_raw;
+            }
+            if (!rows.empty()) {
+                CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+                CUDA_OK(h, cudaMemcpyAsync(d_fill, fills.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+                SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG, lrow, h->sG, 1));
+                CUDA_OK(h, cudaStreamSynchronize(h->stream));
+                lrow += (int64_t)rows.size();
+            }
+            if (!vrows.empty()) {
+                if (!d_vr) CUDA_OK(h, cudaMalloc((void **)&d_vr, (size_t)std::min<int64_t>(chunk, M0) * B));
+                CUDA_OK(h, cudaMemcpyAsync(d_rows, vrows.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
+                CUDA_OK(h, cudaMemcpyAsync(d_fill, vfills.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
+                SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, 0, B, 0));
+                // position of these hold-out markers in the (replicated) host store: their rank among all kind == 2 markers
+                for (size_t j = 0; j < vrows.size(); j++) {
+                    const int64_t m = r.first + vrows[j];
+                    const int64_t slot = std::lower_bound(h->index_vr.begin(), h->index_vr.end(), (int32_t)m) - h->index_vr.begin();
+                    CUDA_OK(h, cudaMemcpyAsync(h->vr_packed.data() + (size_t)slot * B, d_vr + j * B, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
                 }
-                if (nxt >= 0) { run0 = nxt; run1 = nxt + 1; } else run0 = -1;
+                CUDA_OK(h, cudaStreamSynchronize(h->stream));
+                vrow += (int64_t)vrows.size();
             }
         }
-        if (!rows.empty()) {
-            CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
-            CUDA_OK(h, cudaMemcpyAsync(d_fill, fills.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
-            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)rows.size(), d_sub, identity, N, h->dG, lrow, h->sG, 1));
-            CUDA_OK(h, cudaStreamSynchronize(h->stream));
-            lrow += (int64_t)rows.size();
-        }
-        if (!vrows.empty()) {
-            if (!d_vr) CUDA_OK(h, cudaMalloc((void **)&d_vr, (size_t)std::min<int64_t>(chunk, M0) * B));
-            CUDA_OK(h, cudaMemcpyAsync(d_rows, vrows.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
-            CUDA_OK(h, cudaMemcpyAsync(d_fill, vfills.data(), sizeof(int32_t) * vrows.size(), cudaMemcpyHostToDevice, h->stream));
-            SGB_TRY(k_repack(h, d_chunk, B0, d_rows, d_fill, (int64_t)vrows.size(), d_sub, identity, N, d_vr, 0, B, 0));
-            CUDA_OK(h, cudaMemcpyAsync(h->vr_packed.data() + (size_t)vrow * B, d_vr, (size_t)vrows.size() * B, cudaMemcpyDeviceToHost, h->stream));
-            CUDA_OK(h, cudaStreamSynchronize(h->stream));
-            vrow += (int64_t)vrows.size();
-        }
+    }
+    (void)vrow;
+    if (h->world > 1 && h->Mvr > 0) {
+        // replicate the hold-out store: byte-wise sum over the ranks (every row is non-zero on exactly one rank)
+        const size_t nb = h->vr_packed.size(), nw = (nb + 3) / 4;
+        int32_t *d_sum = nullptr;
+        CUDA_OK(h, cudaMalloc((void **)&d_sum, nw * 4));
+        CUDA_OK(h, cudaMemsetAsync(d_sum, 0, nw * 4, h->stream));
+        CUDA_OK(h, cudaMemcpyAsync(d_sum, h->vr_packed.data(), nb, cudaMemcpyHostToDevice, h->stream));
+        SGB_TRY(sgb_allreduce_sum_i32(h, d_sum, (int64_t)nw));
+        CUDA_OK(h, cudaMemcpyAsync(h->vr_packed.data(), d_sum, nb, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d_sum);
     }
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     st.destroy();
@@ -556,7 +585,7 @@ extern "C" int sgb_setgeno_synth(sgb_ctx *h, int64_t N, int64_t M0, uint64_t see
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
     h->afreq_vr.clear(); h->invstd_vr.clear(); h->mac_vr.clear(); h->ac_vr.clear(); h->index_vr.clear();
-    h->qc_mask.assign(M0, 0); h->loc2glob.clear(); h->vr_packed.clear();
+    h->qc_mask.assign(M0, 0); h->loc2glob.clear(); h->vr_packed.clear(); h->qc2raw.clear();
     bool save_vr = h->isVarRatio; h->isVarRatio = false;
     std::vector<int64_t> rows;
     for (int64_t m = 0; m < M0; m++) {
@@ -565,7 +594,8 @@ extern "C" int sgb_setgeno_synth(sgb_ctx *h, int64_t N, int64_t M0, uint64_t see
         int64_t gidx = (int64_t)h->afreq.size();
         h->afreq.push_back(q.afreq); h->invstd.push_back(q.invstd); h->mac.push_back(q.mac); h->ac.push_back(q.ac);
         h->qc_mask[m] = 1;
-        if (owns(h, gidx)) { h->loc2glob.push_back(gidx); rows.push_back(m); }
+        h->qc2raw.push_back((int32_t)m);
+        if (owns_raw(h, m)) { h->loc2glob.push_back(gidx); rows.push_back(m); }
     }
     h->isVarRatio = save_vr;
     h->M = (int64_t)h->afreq.size(); h->Mvr = 0; h->Mloc = (int64_t)h->loc2glob.size();

@@ -267,6 +267,8 @@ def SPAGMMATtest(geno, bedFile="", bimFile="", famFile="", GMMATmodelFile="", va
                     if condition:
                         for name, v in zip(COND_COLUMNS, r[22:28]):
                             row[name] = v
+                    if len(r) > 29:
+                        row["log.p.value"], row["log.p.value.NA"] = float(r[28]), float(r[29])
                     rows.append(row)
             if out:
                 out.flush()
@@ -511,9 +513,30 @@ def _format_chunk(res, bim, cols, table_cols):
             fields.append(np.char.mod("%.6g", res[:, idx["N_case"]] + res[:, idx["N_ctrl"]]).tolist())
         elif c == "Is.SPA":
             fields.append(np.where(res[:, idx[c]] != 0, "true", "false").tolist())
+        elif c in _LOGP_OF and ("log." + c) in idx:
+            # p-values that underflow a double are printed from their logarithm, mantissa and exponent, as the reference does
+            # (SAIGE_test.cpp:273-283: "%.1fE%d")
+            txt = np.char.mod("%.6g", res[:, idx[c]]).tolist()
+            lp = res[:, idx["log." + c]]
+            for j in np.nonzero((res[:, idx[c]] == 0) & np.isfinite(lp))[0]:
+                txt[j] = format_logp(lp[j])
+            fields.append(txt)
         else:
             fields.append(np.char.mod("%.6g", res[:, idx[c]]).tolist())
     return "".join("\t".join(t) + "\n" for t in zip(*fields))
+
+
+_LOGP_OF = ("p.value", "p.value.NA", "p.value_c", "p.value.NA_c")
+
+
+def format_logp(logp):
+    """The reference's string for a p-value known by its natural log only (SAIGE_test.cpp:273-283, 553-561)."""
+    log10p = logp / np.log(10.0)
+    exponent = int(np.floor(log10p))
+    fraction = 10.0 ** (log10p - exponent)
+    if fraction >= 9.95:
+        fraction, exponent = 1.0, exponent + 1
+    return "%.1fE%d" % (fraction, exponent)
 
 
 def _fmt(v):

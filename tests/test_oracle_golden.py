@@ -186,3 +186,18 @@ def test_rda_reader_reads_every_reference_model():
         if os.path.basename(f) in want:
             assert np.allclose(m["theta"], want[os.path.basename(f)], rtol=1e-7), f
     assert len(files) >= 19
+
+
+def test_log_scale_pvalue_helpers():
+    """The oracle's log p-value pieces against independent formulas, and the reference's mantissa / exponent string."""
+    from scipy import stats
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import step2
+    for stat in (0.5, 30.0, 700.0, 1489.0, 1500.0, 5000.0, 2.0e5):
+        want = np.log(2.0) + stats.norm.logsf(np.sqrt(stat))               # chi-square(1) tail = 2 * upper normal tail
+        assert abs(S2.log_erfc(np.sqrt(stat / 2)) - want) <= 1e-12 * abs(want)
+    for logp in (-1.0, -50.0, -700.0, -1000.0, -1.0e5):
+        z = S2.qnorm_from_logp(logp)
+        assert abs(stats.norm.logsf(z) - logp) <= 1e-10 * abs(logp)
+    assert step2.format_logp(np.log(1.2) - 412 * np.log(10.0)) == "1.2E-412"
+    assert step2.format_logp(np.log(9.96) - 400 * np.log(10.0)) == "1.0E-399"           # fraction >= 9.95 rolls over (SAIGE_test.cpp:277-280)

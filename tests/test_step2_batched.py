@@ -97,3 +97,56 @@ def test_batched_vs_oracle_larger_cohort():
             assert abs(got[col] - r[oc]) <= 1e-6 * abs(r[oc]) + 1e-300, (m, col, got[col], r[oc])
         assert bool(got["Is.SPA"]) == bool(r["Is_SPA"])
     assert nspa >= 2
+
+
+def _strong_signal_bed(rng, n, y, nm):
+    """nm variants whose alternate allele is strongly enriched in the upper half of y (hard calls, no missing)."""
+    hi = y > np.median(y)
+    rows = np.zeros((nm, (n + 3) // 4), dtype=np.uint8)
+    for m in range(nm):
+        f = np.where(hi, 0.45, 0.05 + 0.02 * (m % 5))
+        g = (rng.uniform(size=n) < f).astype(int) + (rng.uniform(size=n) < f).astype(int)
+        code = np.array([3, 2, 0], dtype=np.uint8)[g]                      # 0 copies -> 11, 1 -> 10, 2 -> 00
+        code = np.concatenate([code, np.full((-n) % 4, 3, dtype=np.uint8)]).reshape(-1, 4)
+        rows[m] = code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)
+    return rows.reshape(-1)
+
+
+@pytest.mark.parametrize("trait", ["quantitative", "binary"])
+def test_pvalues_below_the_double_range_come_back_on_the_log_scale(trait):
+    """stat > 1490: the p-value underflows a double; the reference switches to log p-values and "%.1fE%d" strings
+    (SAIGE_test.cpp:255-284, 531-582).  The kernel's log columns against the oracle, SE and the Firth trigger included."""
+    from oracle import step2_oracle as S2
+    from saige_gpu_b200 import SaigeB200, step2
+    rng = np.random.default_rng(77)
+    n, nm, p = 30011, 24, 3
+    M = _model(rng, n, p, trait)
+    bed = _strong_signal_bed(rng, n, M["y"] if trait == "quantitative" else M["y"] + 0.01 * rng.normal(size=n), nm)
+    if trait == "binary":                       # cases carry the allele: |z| far beyond the cutoff, saddle-point branch on the log scale
+        bed = _strong_signal_bed(rng, n, M["y"], nm)
+    M["offset"] = np.zeros(n)
+    pos = np.arange(n, dtype=np.int32)
+    g = SaigeB200(device=0)
+    try:
+        g.setSAIGEobjInCPP(M, 0.93, 2.0, pos)
+        g.setFirth(True, 0.01, M["offset"], se_from_fit=False)
+        out = g.mainMarkerInCPP(bed, n, nm, 0.0, 0.5, 0.15)
+    finally:
+        g.close()
+    cols = {c: i for i, c in enumerate(SaigeB200.STEP2_COLUMNS)}
+    nlog = 0
+    for m in range(nm):
+        r = S2.test_marker(M, S2.plink_marker(bed, n, m, pos), min_mac=0.5, is_Firth_beta=True, pCutoffforFirth=0.01, firth_se_from_fit=False)
+        row = out[m]
+        assert row[0] == 1.0
+        for gc, oc in (("log.p.value", "log_p_value"), ("log.p.value.NA", "log_p_value_NA"), ("SE", "SE"), ("BETA", "BETA"), ("Tstat", "Tstat")):
+            assert abs(row[cols[gc]] - r[oc]) <= 1e-6 * abs(r[oc]) + 1e-300, (trait, m, gc, row[cols[gc]], r[oc])
+        assert bool(row[cols["Is.SPA"]]) == bool(r["Is_SPA"]) and bool(row[cols["Is.Firth"]]) == bool(r["Is_Firth"])
+        if r["p_value_NA"] == 0.0:
+            nlog += 1
+            assert row[cols["p.value.NA"]] == 0.0 and np.isfinite(row[cols["log.p.value.NA"]]) and row[cols["log.p.value.NA"]] < -708
+            assert np.isfinite(row[cols["SE"]]) and row[cols["SE"]] > 0
+            txt = step2.format_logp(row[cols["log.p.value"]])
+            mant, expo = txt.split("E")
+            assert 1.0 <= float(mant) < 10.0 and int(expo) < -307
+    assert nlog >= nm // 2, nlog
