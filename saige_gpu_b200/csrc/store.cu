@@ -392,6 +392,9 @@ static int setgeno_impl(sgb_ctx *h, chunk_reader &rd, int64_t N0, int64_t M0, co
         SGB_TRY(sgb_allreduce_sum_i32(h, d_ac, M0));
         SGB_TRY(sgb_allreduce_sum_i32(h, d_nm, M0));
     }
+    CUDA_OK(h, cudaMemcpyAsync(ac_raw.data(), d_ac, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(nm_raw.data(), d_nm, sizeof(int32_t) * M0, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
     nvtxRangePop();
     // ---- host QC (fp32, reference order) ----
     h->afreq.clear(); h->invstd.clear(); h->mac.clear(); h->ac.clear();
