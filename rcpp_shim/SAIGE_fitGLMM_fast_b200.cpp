@@ -43,10 +43,12 @@ static sgb_ctx *ctx()
         if (rank == 0 && sgb_nccl_unique_id(&id[0])) Rcpp::stop(sgb_last_error(nullptr));
         id = bcast(id, Named("rank.source", 0));
         if (sgb_create_dist(device, rank, world, &id[0], &g_h)) Rcpp::stop(sgb_last_error(nullptr));
+        sgb_set_verbose(g_h, rank == 0 ? 1 : 0);      // the reference's "iter from getPCG1ofSigmaAndVector" lines (FG.cpp:2794-2798)
         return g_h;
     }
 #endif
     if (sgb_create(device, &g_h)) Rcpp::stop(sgb_last_error(nullptr));
+    sgb_set_verbose(g_h, 1);                          // the reference's "iter from getPCG1ofSigmaAndVector" lines (FG.cpp:2794-2798)
     return g_h;
 }
 

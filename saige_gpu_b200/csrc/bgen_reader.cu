@@ -148,6 +148,7 @@ extern "C" int sgb_bgen_read(sgb_bgen *b, int64_t max_variants, int alt_first, i
         std::string vid, rsid, chrom, a0, a1;
         uint32_t pos, C, D = 0; uint16_t K;
         bool ok = rd_str(b->f, 2, vid) && rd_str(b->f, 2, rsid) && rd_str(b->f, 2, chrom) && rd(b->f, &pos, 4) && rd(b->f, &K, 2);
+        if (ok && rsid == ".") rsid = vid;            // BGEN.cpp: RSID = (rsID == ".") ? snpID : rsID
         if (ok && K != 2) return sgb_fail(nullptr, "bgen: %s: variant %s has %d alleles", b->path.c_str(), rsid.c_str(), (int)K);
         ok = ok && rd_str(b->f, 4, a0) && rd_str(b->f, 4, a1) && rd(b->f, &C, 4);
         if (ok && b->compression) { ok = rd(b->f, &D, 4) && C >= 4; C -= 4; }

@@ -154,8 +154,10 @@ class BgenFile:
             raise ValueError("AlleleOrder should be 'ref-first' or 'alt-first'")
         info, rows = [], []
         for _ in range(self.M):
-            self._str(2)                      # variant identifier
+            vid = self._str(2)                # variant identifier
             rsid, chrom = self._str(2), self._str(2)
+            if rsid == ".":                   # BGEN.cpp: RSID = (rsID == ".") ? snpID : rsID
+                rsid = vid
             pos, K = struct.unpack("<IH", self.f.read(6))
             alleles = [self._str(4) for _ in range(K)]
             C, = struct.unpack("<I", self.f.read(4))

@@ -7,6 +7,8 @@ marker rows to the C ABI (`sgb_step2_test_markers` = the body of mainMarkerInCPP
 table with the reference's column names.  No numerical work happens here."""
 import os
 
+import re
+
 import numpy as np
 
 from . import genoio
@@ -30,7 +32,7 @@ def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
             raise ValueError("LOCO is TRUE but the null model file .rda does not contain LOCO results")
         if chrom == "":
             raise ValueError("chrom needs to be specified in order to apply Leave-one-chromosome-out")
-        c = int(str(chrom).replace("chr", ""))
+        c = chrom_number(chrom)
         if 1 <= c <= 22:
             lr = m["LOCOResult"][c - 1]
             if isinstance(lr, dict) and "fitted.values" in lr:
@@ -45,7 +47,7 @@ def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
     # offset of the Firth refit (readInGLMM.R:99-101, 134-160): the chromosome's own when LOCO stored one, else the model's
     offset = m.get("offset")
     if LOCO and has_loco and chrom != "":
-        c = int(str(chrom).replace("chr", ""))
+        c = chrom_number(chrom)
         if 1 <= c <= 22 and isinstance(m["LOCOResult"][c - 1], dict) and m["LOCOResult"][c - 1].get("offset") is not None:
             offset = m["LOCOResult"][c - 1]["offset"]
     offset = np.zeros(len(mu)) if offset is None else np.asarray(offset, dtype=np.float64).ravel()
@@ -54,6 +56,13 @@ def ReadModel(GMMATmodelFile, chrom="", LOCO=True):
                 XXVX_inv=np.asarray(noK["XXVX_inv"], dtype=np.float64),
                 XVX_inv_XV=np.asarray(noK["XVX_inv_XV"], dtype=np.float64), S_a=np.asarray(noK["S_a"], dtype=np.float64).ravel(),
                 sampleID=[str(s) for s in m["sampleID"]])
+
+
+def chrom_number(chrom):
+    """getChromNumber (R/readInGLMM.R:4-20): 'chr' stripped case-insensitively, digits only; anything that is not 1..22 (X, Y, MT,
+    empty) gives 0 = no leave-one-chromosome-out refit, i.e. the genome-wide fit is used as the reference does."""
+    digits = re.sub(r"[^0-9]", "", re.sub(r"(?i)chr", "", str(chrom)))
+    return int(digits) if digits else 0
 
 
 def Get_Variance_Ratio(varianceRatioFile, cateVarRatioMinMACVecExclude=(10, 20.5), cateVarRatioMaxMACVecInclude=(20.5,)):

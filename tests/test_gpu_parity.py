@@ -426,3 +426,22 @@ def test_error_paths(gpu2, golden_dir):
         g.Get_OneSNP_Geno(g.M)
     with pytest.raises(SaigeB200Error, match="setStartEndIndex"):
         g.getCrossprodMatAndKin_LOCO(np.zeros(g.N))
+
+
+def test_reference_pcg_log_lines(pair10k, capfd):
+    """sgb_set_verbose: every solve prints the reference's stdout lines (FG.cpp:2794-2798), one per right-hand side, so that
+    log scrapers written for the reference keep working although the solves are batched."""
+    g, o = pair10k
+    rng = np.random.default_rng(3)
+    B = rng.normal(size=(o.N, 3))
+    w = rng.uniform(0.05, 0.25, size=o.N)
+    g.set_verbose(True)
+    try:
+        _, it = g.getPCG1ofSigmaAndVector(w, np.array([1.0, 0.3]), B, 500, 1e-5, return_iter=True)
+        _, it2 = g.getPCG1ofSigmaAndVector(w, np.array([1.0, 0.3]), B[:, 0], 2, 1e-5, return_iter=True)      # hits maxiter
+    finally:
+        g.set_verbose(False)
+    lines = [l for l in capfd.readouterr().out.splitlines() if l.strip()]
+    want = ["iter from getPCG1ofSigmaAndVector %d" % v for v in it]
+    want += ["pcg did not converge. You may increase maxiter number.", "iter from getPCG1ofSigmaAndVector 2"]
+    assert lines == want, lines

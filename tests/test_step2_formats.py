@@ -564,3 +564,10 @@ def test_gpu_dosage_rows_of_hard_calls_equal_the_two_bit_kernel(golden_dir):
             assert abs(x[k] - y[k]) <= 1e-9 * abs(x[k]) + 1e-300, (x["MarkerID"], k, x[k], y[k])
         assert x["Is.SPA"] == y["Is.SPA"] and x["Is.Firth"] == y["Is.Firth"]
     g.close()
+
+
+def test_chromosome_argument_is_parsed_like_the_reference():
+    """getChromNumber (R/readInGLMM.R:1-20): CHR stripped case-insensitively, digits kept; not 1..22 -> no LOCO refit."""
+    from saige_gpu_b200.step2 import chrom_number
+    assert [chrom_number(c) for c in ("1", "chr7", "CHR22", "Chr03", 5)] == [1, 7, 22, 3, 5]
+    assert [chrom_number(c) for c in ("X", "chrX", "MT", "")] == [0, 0, 0, 0]
