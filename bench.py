@@ -64,7 +64,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
+
+    def mark(self):
+        """Samples before this call (warm-up: the sampler is started early so that its fork does not land in the timed steps)
+        are discarded."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -74,6 +79,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        self.rows = [r for r in self.rows if r[-1] >= getattr(self, "t_mark", 0.0)] or self.rows[-1:]
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -286,12 +292,13 @@ def main():
     # ---- device-resident leg ("value") ----
     W, K = args.warmup, args.steps
     barrier()
+    sampler = ClockSampler(local_rank)        # sampled from the first timed step to the end of the e2e leg (all GPU-busy)
+    if rank == 0:
+        sampler.start()                       # started before the warm-up: the fork of nvidia-smi must not perturb rank 0's first timed step
     g.bench_crossprod_device(1, W)                         # warm-up (also sizes every scratch buffer)
     g.reset_counters()
     barrier()
-    sampler = ClockSampler(local_rank)        # sampled from here to the end of the e2e leg (all GPU-busy)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ms, mk = g.bench_crossprod_device(1, K)
     barrier()
     launches = g.counters()["n_kernel_launches"]
@@ -372,52 +379,66 @@ def main():
     # ---- setgeno at full size from a host-resident .bed: the file body lives in /dev/shm, generated once by all
     # ranks together (device generator, bit-identical to the genotypes of the timed store); every rank then runs the sharded
     # ingest (count pass over its 1/world of the file, int32 allreduce, QC, second read of the rows it owns) ----
+    def all_ok(ok):
+        """Collective agreement (min over ranks): a leg is skipped on EVERY rank when any rank cannot run it."""
+        t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t[0] > 0.5)
+
     ingest_info = None
     if not args.no_ingest:
         shm = "/dev/shm/sgb_bench_%s.bed" % os.environ.get("MASTER_PORT", str(os.getpid()))
+        nbytes = Bbytes * M
+        why, mm, gi = None, None, None
         try:
-            nbytes = Bbytes * M
             if rank == 0:
                 st = os.statvfs("/dev/shm")
                 if st.f_bavail * st.f_frsize < nbytes + (8 << 30):
                     raise RuntimeError("/dev/shm has %.0f GB free, the .bed body needs %.0f" % (st.f_bavail * st.f_frsize / 1e9, nbytes / 1e9))
                 with open(shm, "wb") as f:
                     f.truncate(nbytes)
-            if world > 1:
-                dist.barrier()
-            mm = np.memmap(shm, dtype=np.uint8, mode="r+")
-            ma, mb = M * rank // world, M * (rank + 1) // world
-            tg = time.time()
-            g.synth_bed_rows(N, ma, mb, SEED, t0, t1, 0.0, out=mm[ma * Bbytes:mb * Bbytes])
-            tg = time.time() - tg
-            if world > 1:
-                dist.barrier()
-            gi = new_context()
-            gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
-            ones = np.ones(N, np.uint8); ids = np.arange(1, N + 1)
-            gi.setgeno_mem(mm, N, min(M, 4096), ids, ones)          # warm-up: allocations, first kernel loads
-            barrier()
-            ti = time.time()
-            gi.setgeno_mem(mm, N, M, ids, ones)
-            gi.sync()
-            ti = max_over_ranks(time.time() - ti)
-            same = bool(gi.M == g.M and np.array_equal(gi.getAlleleCountVec(), g.getAlleleCountVec()))
-            yi = np.asarray(gi.getCrossprodMatAndKin(hb.numpy())).ravel()
-            ingest_info = {"bed_gbytes": nbytes / 1e9, "seconds": ti, "gb_per_s": nbytes / 1e9 / ti, "n_gpus": world,
-                           "h2d_gbytes_this_rank": gi.counters()["bytes_h2d"] / 1e9, "generate_s": tg,
-                           "allele_counts_equal_synth_store": same,
-                           "product_rel_diff_vs_synth_store": float(np.max(np.abs(yi - hy.numpy())) / np.max(np.abs(hy.numpy()))),
-                           "sample": "FULL workload: %d samples x %d markers, host-resident .bed body in /dev/shm (pageable), "
-                                     "QC + imputation + re-pack + transpose on the GPU, sharded over %d rank(s)" % (N, M, world)}
-            gi.close()
-            del mm
         except Exception as e:
-            ingest_info = {"error": "%s: %s" % (type(e).__name__, e)}
-        finally:
-            if world > 1:
-                dist.barrier()
-            if rank == 0 and os.path.exists(shm):
-                os.unlink(shm)
+            why = "%s: %s" % (type(e).__name__, e)
+        if all_ok(why is None):
+            tg = time.time()
+            try:
+                mm = np.memmap(shm, dtype=np.uint8, mode="r+")
+                ma, mb = M * rank // world, M * (rank + 1) // world
+                g.synth_bed_rows(N, ma, mb, SEED, t0, t1, 0.0, out=mm[ma * Bbytes:mb * Bbytes])
+            except Exception as e:
+                why = "%s: %s" % (type(e).__name__, e)
+            tg = time.time() - tg
+            if all_ok(why is None):
+                try:
+                    gi = new_context()
+                    gi.setminMAFforGRM(0.01); gi.setmaxMissingRateforGRM(0.15)
+                    ones = np.ones(N, np.uint8); ids = np.arange(1, N + 1)
+                    gi.setgeno_mem(mm, N, min(M, 4096), ids, ones)          # warm-up: allocations, first kernel loads
+                    barrier()
+                    ti = time.time()
+                    gi.setgeno_mem(mm, N, M, ids, ones)
+                    gi.sync()
+                    ti = max_over_ranks(time.time() - ti)
+                    same = bool(gi.M == g.M and np.array_equal(gi.getAlleleCountVec(), g.getAlleleCountVec()))
+                    yi = np.asarray(gi.getCrossprodMatAndKin(hb.numpy())).ravel()
+                    ingest_info = {"bed_gbytes": nbytes / 1e9, "seconds": ti, "gb_per_s": nbytes / 1e9 / ti, "n_gpus": world,
+                                   "h2d_gbytes_this_rank": gi.counters()["bytes_h2d"] / 1e9, "generate_s": tg,
+                                   "allele_counts_equal_synth_store": same,
+                                   "product_rel_diff_vs_synth_store": float(np.max(np.abs(yi - hy.numpy())) / np.max(np.abs(hy.numpy()))),
+                                   "sample": "FULL workload: %d samples x %d markers, host-resident .bed body in /dev/shm (pageable), "
+                                             "QC + imputation + re-pack + transpose on the GPU, sharded over %d rank(s)" % (N, M, world)}
+                except Exception as e:                       # a failure inside the collective ingest cannot be agreed on; report it
+                    why = "%s: %s" % (type(e).__name__, e)
+                if gi is not None:
+                    gi.close()
+        if ingest_info is None:
+            ingest_info = {"error": why or "skipped: another rank could not run this leg"}
+        del mm
+        if world > 1:
+            dist.barrier()
+        if rank == 0 and os.path.exists(shm):
+            os.unlink(shm)
 
     # ---- BASELINE config 5 row: single-variant score test + SPA, variants sharded over the ranks (no collective): every rank
     # tests its own 65,536 synthetic variants x N samples from pinned host rows through the C ABI ----

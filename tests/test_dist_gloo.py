@@ -157,3 +157,22 @@ def parts_of(full, rank, world, n=100):
     per = (n + world - 1) // world
     lo, hi = rank * per, min(n, (rank + 1) * per)
     return [r for r in full if lo <= int(r["MarkerID"][2:]) - 1 < hi]
+
+
+def test_rank_map_is_defined_on_raw_markers():
+    """A rank stores the QC-passing markers of its raw 1024-marker blocks: the QC indices of all ranks partition 0..M-1,
+    stay ascending per rank, and coincide with `local_markers` when every marker passes."""
+    from saige_gpu_b200 import sharding
+    rng = np.random.default_rng(0)
+    qc = rng.uniform(size=10_000) < 0.9
+    M = int(qc.sum())
+    for world in (1, 2, 3, 8):
+        parts = [sharding.local_markers_qc(qc, r, world) for r in range(world)]
+        assert all(np.all(np.diff(p) > 0) for p in parts if len(p) > 1)
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(M))
+        raw = np.nonzero(qc)[0]
+        for r, p in enumerate(parts):
+            assert np.all((raw[p] // sharding.SHARD_BLOCK) % world == r)
+    ones = np.ones(5000, dtype=bool)
+    assert np.array_equal(sharding.local_markers_qc(ones, 1, 4), sharding.local_markers(5000, 1, 4))
