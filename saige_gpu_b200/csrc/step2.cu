@@ -129,11 +129,15 @@ struct s2_cgf {          // binomial CGF pieces over the non-zero genotypes + no
 // sample index (IDENT = false).
 // The hard-call fast path keeps three CTAs per SM (<= 85 registers, as before the conditional / dosage code was added: the
 // rarely taken branches spill, the popcount passes do not).
+// Per-CTA scratch of the saddle-point branch (batched path: one slot per persistent CTA): gtilde of every sample, and for
+// SPA_fast the compact list of (gtilde, mu) pairs of the samples with a non-zero genotype, in sample order.  The Newton
+// passes then stream 16 bytes per evaluated sample instead of decoding the genotype and gathering p + 1 model values.
+struct s2_spa_scratch { double *gt; double2 *nz; };
+
 template <bool IDENT, bool DOSE>
-__global__ void __launch_bounds__(S2_THREADS, IDENT ? 3 : 2)
-step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
-             double max_missing, int se_two_sided, double *__restrict__ out, s2_dose DS, const int *__restrict__ list,
-             const int *__restrict__ list_count)
+__device__ __forceinline__ void step2_variant(const s2_model &M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, int64_t m, double min_maf,
+                                              double min_mac, double max_missing, int se_two_sided, double *__restrict__ out, const s2_dose &DS,
+                                              s2_spa_scratch scr)
 {
     static_assert(!(IDENT && DOSE), "dosage rows are always indexed");
     extern __shared__ uint8_t srow[];
@@ -141,9 +145,7 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     __shared__ double Zs[S2_MAXP], Ws[S2_MAXP];
     __shared__ int er_cnt, er_idx[SGB_ER_MAXK];
     __shared__ double er_pv;
-    // batched path: only the variants the score-sum pass flagged (SPA / exact test / Firth / conditional) come here
-    if (list && (int)blockIdx.x >= *list_count) return;
-    const int64_t m = list ? (int64_t)list[blockIdx.x] : (int64_t)blockIdx.x;
+    __shared__ int nz_warp[S2_THREADS / 32];
     if (m >= nm) return;
     const int tid = threadIdx.x, p = M.p;
     const int64_t N = M.N;
@@ -426,18 +428,39 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
     if (spa_u || spa_c) {
         // gtilde_i = g_i - XXVX_inv[i,:] . (XV g),  XV g = W  (getadjGFast, SAIGE_test.cpp:306-315)
         double m1p = 0, gpos = 0, gneg = 0, gmuNB = 0, sigNB = 0;
-        for (int64_t i = tid; i < N; i += S2_THREADS) {
-            const double g = GENO(i);
-            double gt = g;
-            for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
-            const double mu = M.mu[i];
-            m1p += mu * gt;
-            if (gt > 0) gpos += gt; else if (gt < 0) gneg += gt;
-            if (g != 0.0) { gmuNB += gt * mu; sigNB += mu * (1.0 - mu) * gt * gt; }
+        const int fast = ((double)N - nz) / (double)N >= 0.5;
+        const bool use_scr = scr.gt != nullptr;
+        int nnz = 0;                                     // entries of scr.nz (fast mode with scratch)
+        // the loop runs over whole 256-sample blocks so that the compaction's block scan sees uniform control flow
+        for (int64_t i0 = 0; i0 < N; i0 += S2_THREADS) {
+            const int64_t i = i0 + tid;
+            double g = 0.0, gt = 0.0, mu = 0.0;
+            if (i < N) {
+                g = GENO(i);
+                gt = g;
+                for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
+                mu = M.mu[i];
+                m1p += mu * gt;
+                if (gt > 0) gpos += gt; else if (gt < 0) gneg += gt;
+                if (g != 0.0) { gmuNB += gt * mu; sigNB += mu * (1.0 - mu) * gt * gt; }
+                if (use_scr && !fast) scr.gt[i] = gt;
+            }
+            if (use_scr && fast) {
+                // deterministic compaction in sample order: ballot inside the warp, exclusive scan over the 8 warps
+                const bool keep = i < N && g != 0.0;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if ((tid & 31) == 0) nz_warp[tid >> 5] = __popc(bal);
+                __syncthreads();
+                int base = nnz, total = 0;
+#pragma unroll
+                for (int w = 0; w < S2_THREADS / 32; w++) { if (w < (tid >> 5)) base += nz_warp[w]; total += nz_warp[w]; }
+                if (keep) scr.nz[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = make_double2(gt, mu);
+                nnz += total;
+                __syncthreads();
+            }
         }
         const double m1 = block_sum(m1p, red);
         gpos = block_sum(gpos, red); gneg = block_sum(gneg, red); gmuNB = block_sum(gmuNB, red); sigNB = block_sum(sigNB, red);
-        const int fast = ((double)N - nz) / (double)N >= 0.5;
         const double NAmu = m1 - gmuNB, NAsigma = var2 - sigNB;
         const double tol = 1.220703125e-4;          // eps^0.25 (SAIGE_test.cpp:515-516)
 
@@ -446,12 +469,19 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         // reciprocal per sample there (fp64 exp / log / divide are long software sequences)
         auto cgf = [&](double t, double &k0, double &k1, double &k2, bool want0) {
             double a0 = 0, a1 = 0, a2 = 0;
-            for (int64_t i = tid; i < N; i += S2_THREADS) {
-                const double g = GENO(i);
-                if (fast && g == 0.0) continue;
-                double gt = g;
-                for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
-                const double mu = M.mu[i];
+            const int64_t nit = use_scr && fast ? (int64_t)nnz : N;
+            for (int64_t i = tid; i < nit; i += S2_THREADS) {
+                double gt, mu;
+                if (use_scr) {
+                    if (fast) { const double2 v = scr.nz[i]; gt = v.x; mu = v.y; }
+                    else { gt = scr.gt[i]; mu = M.mu[i]; }
+                } else {
+                    const double g = GENO(i);
+                    if (fast && g == 0.0) continue;
+                    gt = g;
+                    for (int j = 0; j < p; j++) gt -= M.XXVXi[i + (int64_t)j * N] * Ws[j];
+                    mu = M.mu[i];
+                }
                 const double x = gt * t;
                 const double e = exp(-x);
                 const double den = (1.0 - mu) * e + mu;
@@ -605,6 +635,37 @@ step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm
         o[19] = var2; o[20] = isFirth; o[21] = firthConv;
         o[22] = sgn * Beta_c; o[23] = se_c; o[24] = sgn * Tc; o[25] = vc; o[26] = pval_c; o[27] = pval_noadj_c;
         o[28] = lp; o[29] = lp_noadj; o[30] = lp_c; o[31] = lp_noadj_c;
+    }
+}
+
+// one CTA per variant (per-variant path, dosage rows)
+template <bool IDENT, bool DOSE>
+__global__ void __launch_bounds__(S2_THREADS, IDENT ? 3 : 2)
+step2_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
+             double max_missing, int se_two_sided, double *__restrict__ out, s2_dose DS)
+{
+    step2_variant<IDENT, DOSE>(M, bed, B0, nm, (int64_t)blockIdx.x, min_maf, min_mac, max_missing, se_two_sided, out, DS, s2_spa_scratch{nullptr, nullptr});
+}
+
+// batched path: persistent CTAs pull the flagged variants (saddle point / exact test / Firth / conditional) off a list; a
+// saddle-point variant keeps a CTA busy for milliseconds, so dynamic assignment also balances the tail of a chunk
+__global__ void __launch_bounds__(S2_THREADS, 3)
+step2_flagged_kernel(s2_model M, const uint8_t *__restrict__ bed, int64_t B0, int64_t nm, double min_maf, double min_mac,
+                     double max_missing, int se_two_sided, double *__restrict__ out, const int *__restrict__ list,
+                     const int *__restrict__ list_count, int *__restrict__ next, double *__restrict__ scratch, int64_t slot_doubles)
+{
+    __shared__ int cur;
+    s2_spa_scratch scr;
+    scr.gt = scratch + (int64_t)blockIdx.x * slot_doubles;
+    scr.nz = reinterpret_cast<double2 *>(scr.gt + ((M.N + 1) & ~(int64_t)1));
+    const int count = *list_count;
+    for (;;) {
+        __syncthreads();                                  // the previous variant's shared state is no longer read
+        if (threadIdx.x == 0) cur = atomicAdd(next, 1);
+        __syncthreads();
+        const int idx = cur;
+        if (idx >= count) break;
+        step2_variant<true, false>(M, bed, B0, nm, (int64_t)list[idx], min_maf, min_mac, max_missing, se_two_sided, out, s2_dose{}, scr);
     }
 }
 
@@ -849,7 +910,8 @@ struct sgb_step2 {
     int32_t *d_acci = nullptr; size_t acci_elems = 0;
     double *d_raw = nullptr; size_t raw_elems = 0;    // recombined sums: [rows_pad x kv] | [rows_pad]
     int32_t *d_cnt = nullptr; size_t cnt_elems = 0;   // class counts, 6 per variant
-    int *d_list = nullptr; size_t list_elems = 0;     // [count | variant indices] of the flagged variants
+    int *d_list = nullptr; size_t list_elems = 0;     // [count | next | variant indices] of the flagged variants
+    double *d_spa = nullptr; size_t spa_bytes = 0;    // saddle-point scratch: one slot (2 N doubles) per persistent CTA
     bool batched = true;                  // sgb_step2_set_batched(0): every variant through step2_kernel (cross-check)
 };
 
@@ -1059,12 +1121,15 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     if (sgb_first_on_device(h->device, SGB_SITE_STEP2)) {
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
         CUDA_OK(h, cudaFuncSetAttribute(step2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+        CUDA_OK(h, cudaFuncSetAttribute(step2_flagged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
     }
     // batched path: chunk = a multiple of the row alignment of the tiled store; scratch for the tensor-engine sums
     const bool batched = s->batched;
     const int64_t N = s->M.N, Bm = (N + 3) / 4;
     const int64_t rows_pad = (chunk + SGB_ROW_ALIGN - 1) / SGB_ROW_ALIGN * SGB_ROW_ALIGN;
     const int kv = s->kv, npadv = k_umma_npad(kv, 7);
+    const int flag_ctas = h->sm_count * 3;                               // persistent CTAs of the flagged-variant kernel (3 per SM)
+    const int64_t slot_doubles = 2 * ((N + 1) & ~(int64_t)1) + 2;        // gtilde of N samples + N/2 (gtilde, mu) pairs
     if (batched) {
         if (!s->M.identity) SGB_TRY(sgb_ensure(h, (void **)&s->d_gath, &s->gath_bytes, (size_t)chunk * Bm));
         SGB_TRY(sgb_ensure(h, (void **)&s->d_tiled, &s->tiled_bytes, (size_t)rows_pad * s->stride));
@@ -1073,7 +1138,8 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
         b = s->acci_elems * 4; if (b < (size_t)rows_pad * 8 * 4) { SGB_TRY(sgb_ensure(h, (void **)&s->d_acci, &b, (size_t)rows_pad * 8 * 4)); s->acci_elems = b / 4; CUDA_OK(h, cudaMemsetAsync(s->d_acci, 0, b, h->stream)); }
         SGB_TRY(sgb_ensure_f64(h, &s->d_raw, &s->raw_elems, (size_t)rows_pad * (kv + 1)));
         b = s->cnt_elems * 4; SGB_TRY(sgb_ensure(h, (void **)&s->d_cnt, &b, (size_t)chunk * 6 * 4)); s->cnt_elems = b / 4;
-        b = s->list_elems * 4; SGB_TRY(sgb_ensure(h, (void **)&s->d_list, &b, (size_t)(chunk + 1) * 4)); s->list_elems = b / 4;
+        b = s->list_elems * 4; SGB_TRY(sgb_ensure(h, (void **)&s->d_list, &b, (size_t)(chunk + 2) * 4)); s->list_elems = b / 4;
+        SGB_TRY(sgb_ensure(h, (void **)&s->d_spa, &s->spa_bytes, (size_t)flag_ctas * slot_doubles * sizeof(double)));
     }
     // rows in page-locked memory (cudaHostAlloc / cudaHostRegister by the caller) go to the device straight from the caller's
     // buffer; pageable rows pass through the pinned double buffer (a host memcpy at ~13 GB/s: the e2e limit of that case)
@@ -1111,18 +1177,18 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
             SGB_TRY(k_recombine_umma(h, s->d_accv, rp, kv, s->d_multv, s->d_lsv, SGB_PLANE_VALUE, rawV, rows_pad));
             SGB_TRY(k_pk2_gemm(h, s->d_tiled, s->stride, rp, s->stride, s->d_Li, 1, s->d_acci, SGB_PLANE_IS2));
             SGB_TRY(k_recombine(h, s->d_acci, rp, 1, 1, s->d_multi, s->d_lsi, SGB_PLANE_IS2, rawI, rows_pad));
-            CUDA_OK(h, cudaMemsetAsync(s->d_list, 0, sizeof(int), h->stream));
+            CUDA_OK(h, cudaMemsetAsync(s->d_list, 0, 2 * sizeof(int), h->stream));
             s2_model Mi = s->M; Mi.identity = 1;
             s2_finish_kernel<<<(unsigned)((nm + 127) / 128), 128, 0, h->stream>>>(Mi, s->d_cnt, rawV, rawI, rows_pad, s->d_csum, nm, min_maf, min_mac,
-                                                                                max_missing, dout, s->d_list + 1, s->d_list);
-            // the flagged variants (saddle point, exact test, Firth, conditional): one CTA each, empty CTAs beyond the count
-            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)Brow + 8, h->stream>>>(Mi, rows, Brow, nm, min_maf, min_mac, max_missing, se_two_sided,
-                                                                                              dout, s2_dose{}, s->d_list + 1, s->d_list);
+                                                                                max_missing, dout, s->d_list + 2, s->d_list);
+            // the flagged variants (saddle point, exact test, Firth, conditional): persistent CTAs pull them off the list
+            step2_flagged_kernel<<<(unsigned)std::min<int64_t>(flag_ctas, nm), S2_THREADS, (size_t)Brow + 8, h->stream>>>(
+                Mi, rows, Brow, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s->d_list + 2, s->d_list, s->d_list + 1, s->d_spa, slot_doubles);
             h->cnt.n_kernel_launches += 2;
         } else if (s->M.identity)
-            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{}, nullptr, nullptr);
+            step2_kernel<true, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{});
         else
-            step2_kernel<false, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{}, nullptr, nullptr);
+            step2_kernel<false, false><<<(unsigned)nm, S2_THREADS, (size_t)B0 + 8, h->stream>>>(s->M, db, B0, nm, min_maf, min_mac, max_missing, se_two_sided, dout, s2_dose{});
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
         CUDA_OK(h, cudaMemcpyAsync(s->pout[cur], dout, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
@@ -1162,7 +1228,7 @@ extern "C" int sgb_step2_test_dosages(sgb_ctx *h, const double *dosages, int64_t
         s2_dose ds;
         ds.d = reinterpret_cast<const double *>(s->d_bed); ds.stride = n_file_samples; ds.impute = impute_method;
         ds.zerod_cutoff = dosage_zerod_cutoff; ds.zerod_mac_cutoff = dosage_zerod_mac_cutoff;
-        step2_kernel<false, true><<<(unsigned)nm, S2_THREADS, 0, h->stream>>>(s->M, nullptr, 0, nm, min_maf, min_mac, max_missing, se_two_sided, s->d_out, ds, nullptr, nullptr);
+        step2_kernel<false, true><<<(unsigned)nm, S2_THREADS, 0, h->stream>>>(s->M, nullptr, 0, nm, min_maf, min_mac, max_missing, se_two_sided, s->d_out, ds);
         h->cnt.n_kernel_launches++;
         CUDA_OK(h, cudaGetLastError());
         CUDA_OK(h, cudaMemcpyAsync(out + (size_t)m0 * S2_NOUT, s->d_out, sizeof(double) * nm * S2_NOUT, cudaMemcpyDeviceToHost, h->stream));
@@ -1184,7 +1250,7 @@ void sgb_step2_free(sgb_ctx *h)
     if (s->d_bed) cudaFree(s->d_bed);
     if (s->d_out) cudaFree(s->d_out);
     void *more[] = {s->d_V, s->d_csum, s->d_Lv, s->d_Li, s->d_multv, s->d_multi, s->d_lsv, s->d_lsi, s->d_gath, s->d_tiled, s->d_accv, s->d_acci,
-                    s->d_raw, s->d_cnt, s->d_list};
+                    s->d_raw, s->d_cnt, s->d_list, s->d_spa};
     for (auto q : more) if (q) cudaFree(q);
     for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }
     delete s;

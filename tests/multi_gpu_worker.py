@@ -93,6 +93,30 @@ Xso, itso = os_.pcg_multi(ws, tau, Bs, 500, 1e-5)
 assert list(its) == list(itso), (its, itso)
 res["synth_pcg"] = rel(Xs, Xso)
 
+# ---- sharded ingest with everything the QC path has: 2 % missing calls, a phenotyped subset in shuffled order, a variance-ratio
+# hold-out set (its rows live on ONE rank's device and are replicated by an allreduce), 12,345 raw markers over `world` ranks ----
+N1, M1 = 1237, 12_345
+bed1 = O.synth_bed(N1, M1, seed=77, miss_rate=0.02)
+rng1 = np.random.default_rng(4)
+keep = np.sort(rng1.choice(N1, size=1001, replace=False))
+sub = rng1.permutation(keep) + 1
+ind = np.zeros(N1, np.uint8); ind[keep] = 1
+vr = np.unique(rng1.integers(0, M1, size=400))
+o1 = O.OracleGeno(); o1.minMAF, o1.maxMissing, o1.isVarRatio = 0.06, 0.03, True
+o1.setgeno(bed1, N1, M1, sub, ind, vr_rand_idx=vr)
+g.setminMAFforGRM(0.06); g.setmaxMissingRateforGRM(0.03); g.setminMAC_VarianceRatio(20, -1, True)
+g.reset_counters()
+g.setgeno_mem(bed1, N1, M1, sub, ind, vr_rand_idx=vr)
+ingest_ok = ((g.N, g.M, g.Mvr) == (o1.N, o1.M, o1.Mvr) and o1.Mvr > 50 and np.array_equal(g.getAlleleCountVec(), o1.ACVec)
+             and np.array_equal(g.getQCdMarkerIndex(), o1.qc_mask) and np.array_equal(g.getIndexVec_forVarRatio(), o1.markerIndexVec_forVarRatio)
+             and all(np.array_equal(g.Get_OneSNP_Geno(i), o1.Get_OneSNP_Geno(i)) for i in range(0, o1.M, 397))
+             and all(np.array_equal(g.Get_OneSNP_Geno_forVarRatio(i), o1.Get_OneSNP_Geno(i, vr=True)) for i in range(0, o1.Mvr, 7)))
+# every rank read only its blocks of the file (one pass), not the whole body
+ingest_ok = ingest_ok and (world == 1 or g.counters()["bytes_h2d"] < 0.75 * bed1.nbytes)
+b1 = rng1.normal(size=o1.N)
+res["ingest_crossprod"] = rel(g.getCrossprodMatAndKin(b1), o1.getCrossprodMatAndKin(b1))
+g.setminMAC_VarianceRatio(20, -1, False)
+
 # ---- step 2: the rank's contiguous slice of the variants, no collective; slices concatenated == single-rank table ----
 gd = os.path.join(ROOT, "tests", "golden")
 p2 = os.path.join(gd, "step2_100markers")
@@ -115,9 +139,9 @@ if rank == 0:
 pcg_keys = ("pcg", "tau", "alpha", "dense_pcg", "synth_pcg")
 worst_mv = max(v for k, v in res.items() if k not in pcg_keys)
 ok = (worst_mv < 1e-10 and res["dense_pcg"] < 1e-6 and res["pcg"] < 1e-6 and res["tau"] < 1e-6 and res["alpha"] < 1e-6
-      and res["synth_pcg"] < 1e-6 and step2_ok)
-print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e/%.2e tau %.2e alpha %.2e step2 %s allreduces %d -> %s"
-      % (rank, world, g.Mloc, worst_mv, res["pcg"], res["synth_pcg"], res["tau"], res["alpha"], step2_ok,
+      and res["synth_pcg"] < 1e-6 and step2_ok and ingest_ok)
+print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e/%.2e tau %.2e alpha %.2e step2 %s ingest %s allreduces %d -> %s"
+      % (rank, world, g.Mloc, worst_mv, res["pcg"], res["synth_pcg"], res["tau"], res["alpha"], step2_ok, ingest_ok,
          g.counters()["n_allreduce"], "OK" if ok else "FAIL"), flush=True)
 if not ok:
     print({k: v for k, v in res.items() if v > 1e-10}, flush=True)
