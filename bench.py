@@ -444,7 +444,7 @@ def main():
     # tests its own 65,536 synthetic variants x N samples from pinned host rows through the C ABI ----
     step2_info = None
     if not args.no_step2:
-        n2, m2 = N, 65536 if N >= 100_000 else 262144
+        n2, m2 = N, 131072 if N >= 100_000 else 262144      # 8 ranks x 131,072 = 1.05 M variants of config 5 per timed call
         rng2 = np.random.default_rng(SEED + 9)
         f2 = np.random.default_rng(SEED + 10 + rank).uniform(0.05, 0.5, size=m2)
         s0 = np.floor((1 - f2) ** 2 * 4294967296.0).astype(np.uint64).clip(0, 4294967295).astype(np.uint32)

@@ -225,6 +225,9 @@ int sgb_step2_set_variance_ratios(sgb_ctx *h, int n_cate, const double *ratios, 
  * own (saddle-point approximation, exact test, Firth, conditional analysis) run the per-variant kernel.  0: every variant
  * through the per-variant kernel (the round-1 path, kept as the on-device cross-check). */
 int sgb_step2_set_batched(sgb_ctx *h, int enable);
+/* Raw-row bytes per pipeline chunk of sgb_step2_test_markers (default 1 GB: a chunk must hold ~10^4 variants for the flagged
+ * variants to fill the machine; smaller values bound the device / pinned staging memory, and let tests cross chunk borders). */
+int sgb_step2_set_chunk_bytes(sgb_ctx *h, int64_t bytes);
 int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64_t n_fam, int64_t n_markers, double min_maf,
                            double min_mac, double max_missing, int se_two_sided, double *out);
 /* The same marker loop for dosage rows (Unified_getOneMarker's VCF / BGEN branches, Main.cpp:584-700; VCF.cpp:120-256,

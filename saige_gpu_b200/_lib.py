@@ -41,6 +41,7 @@ _SIGS = {
     "sgb_set_rhs_limbs": (C.c_int, [P, C.c_int]),
     "sgb_set_verbose": (C.c_int, [P, C.c_int]),
     "sgb_step2_set_batched": (C.c_int, [P, C.c_int]),
+    "sgb_step2_set_chunk_bytes": (C.c_int, [P, I64]),
     "sgb_set_product_tolerance": (C.c_int, [P, C.c_double]),
     "sgb_device_sync": (C.c_int, [P]),
     "sgb_set_min_maf_for_grm": (C.c_int, [P, C.c_float]),

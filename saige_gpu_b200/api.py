@@ -79,6 +79,10 @@ class SaigeB200:
         """Step-2 score sums as one tensor-engine GEMM per chunk (default) or every variant through the per-variant kernel."""
         self._ck(self._L.sgb_step2_set_batched(self._h, 1 if on else 0))
 
+    def setStep2ChunkBytes(self, nbytes):
+        """Raw-row bytes per pipeline chunk of the step-2 marker loop (default 1 GB)."""
+        self._ck(self._L.sgb_step2_set_chunk_bytes(self._h, int(nbytes)))
+
     def set_verbose(self, on=True):
         """Print the reference's PCG log lines (FG.cpp:2794-2798) from every solve."""
         self._ck(self._L.sgb_set_verbose(self._h, 1 if on else 0))

@@ -913,6 +913,7 @@ struct sgb_step2 {
     int *d_list = nullptr; size_t list_elems = 0;     // [count | next | variant indices] of the flagged variants
     double *d_spa = nullptr; size_t spa_bytes = 0;    // saddle-point scratch: one slot (2 N doubles) per persistent CTA
     bool batched = true;                  // sgb_step2_set_batched(0): every variant through step2_kernel (cross-check)
+    int64_t chunk_bytes = (int64_t)1 << 30;   // raw rows per chunk (sgb_step2_set_chunk_bytes)
 };
 
 extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, const double *mu, const double *res,
@@ -995,6 +996,14 @@ extern "C" int sgb_step2_set_model(sgb_ctx *h, int64_t N, int p, int binary, con
         SGB_TRY(k_split_limbs(h, s->d_V + (size_t)(2 * p + 1) * N, N, N, 1, s->d_Li, s->stride / SGB_KSTEP_BYTES, s->d_multi, s->d_lsi, 0));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
     }
+    return 0;
+}
+
+extern "C" int sgb_step2_set_chunk_bytes(sgb_ctx *h, int64_t bytes)
+{
+    if (bytes < 1) return sgb_fail(h, "step2: chunk size must be positive");
+    if (!h->step2) h->step2 = new sgb_step2();
+    h->step2->chunk_bytes = bytes;
     return 0;
 }
 
@@ -1099,7 +1108,7 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     // of chunk c.  The chunk is this large for the flagged variants: a saddle-point variant keeps one CTA busy for milliseconds
     // (~20 passes over all samples), so the per-variant kernel only fills the machine (444 resident CTAs) when a chunk holds
     // >= ~10^4 variants of which ~5 % are flagged (measured: 43 us per flagged variant with 256 MB chunks at N = 200k)
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, ((int64_t)1 << 30) / B0));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, s->chunk_bytes / B0));
     const size_t cbytes = (size_t)chunk * B0, obytes = sizeof(double) * (size_t)chunk * S2_NOUT;
     if (!s->pin[0] || s->pin_bytes < cbytes) {
         for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); s->pin[i] = nullptr; }

@@ -93,3 +93,24 @@ def test_diag_matches_oracle(pair):
         o.setStartEndIndex(s[j], e[j], j)
         g.setStartEndIndex(s[j], e[j], j)
         assert rel(g.getDiagOfSigma_LOCO(w, tau), o.getDiagOfSigma(w, tau, loco=True)) < 1e-10, j
+
+
+@pytest.mark.parametrize("digits,tol", [(7, 1e-10), (5, 1e-10)])
+def test_wide_batch_matches_oracle(pair, digits, tol):
+    """31 columns (one N = 224 / N = 160 tcgen05 pass per sweep): every column is a known combination of the two columns the
+    oracle multiplied in test_product_matches_oracle, so K's linearity gives the oracle answer for all 31 without 31 CPU products."""
+    g, N = pair["g"], pair["N"]
+    if "Yo" not in pair:
+        pytest.skip("needs test_product_matches_oracle")
+    B, Yo = pair["B"], pair["Yo"]
+    rng = np.random.default_rng(14)
+    C = rng.normal(size=(2, 31)) * 10.0 ** rng.integers(-2, 3, size=31)
+    C[:, 0], C[:, 1] = (1.0, 0.0), (0.0, 1.0)
+    g.set_rhs_limbs(digits)
+    try:
+        Y = g.getCrossprodMatAndKin(np.asfortranarray(B @ C))
+    finally:
+        g.set_rhs_limbs(7)
+    want = Yo @ C
+    worst = max(rel(Y[:, c], want[:, c]) for c in range(31))
+    assert worst < tol, (digits, worst)

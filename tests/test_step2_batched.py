@@ -150,3 +150,28 @@ def test_pvalues_below_the_double_range_come_back_on_the_log_scale(trait):
             mant, expo = txt.split("E")
             assert 1.0 <= float(mant) < 10.0 and int(expo) < -307
     assert nlog >= nm // 2, nlog
+
+
+@pytest.mark.parametrize("identity", [True, False])
+def test_chunk_borders_do_not_change_a_row(identity):
+    """The double-buffered chunk pipeline (H2D of chunk c+1 and D2H of chunk c-1 behind the kernels of chunk c): many small
+    chunks, a ragged last one and a second call on the same handle with another chunk size give the one-chunk table bit for bit."""
+    from saige_gpu_b200 import SaigeB200
+    rng = np.random.default_rng(5)
+    n_fam, nm, p = 3001, 2500, 3
+    N = n_fam if identity else 2222
+    bed = _bed_with_flips(n_fam, nm, 6, 0.01)
+    pos = np.arange(N, dtype=np.int32) if identity else rng.permutation(n_fam)[:N].astype(np.int32)
+    M = _model(rng, N, p, "binary")
+    g = SaigeB200(device=0)
+    try:
+        g.setSAIGEobjInCPP(M, 0.93, 2.0, pos)
+        one = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 0.5, 0.15)
+        B0 = (n_fam + 3) // 4
+        for rows_per_chunk in (600, 37, 1024):
+            g.setStep2ChunkBytes(rows_per_chunk * B0)
+            out = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 0.5, 0.15)
+            assert np.array_equal(np.nan_to_num(out, nan=-7.0), np.nan_to_num(one, nan=-7.0)), rows_per_chunk
+    finally:
+        g.close()
+    assert one[:, 10].sum() > 30 and (one[:, 0] == 1).sum() > 2000
