@@ -32,6 +32,9 @@ WORKLOADS = {
     "small_20kx50k": (20_000, 50_000),
 }
 SEED = 20260117
+# ||K b||_2 of the fixed e2e probe vector on one GPU (profiles/r02_bench_1gpu.json): every GPU count must reproduce it -- the
+# sharded sums differ only in the order of exact integer additions and one fp64 allreduce
+Y_NORM2 = {"c3_200kx500k": 528.53549922164}
 
 
 def measured_hbm_peak():
@@ -613,7 +616,10 @@ def main():
                        "sharding": "block-cyclic markers, 1 NCCL allreduce of N fp64 per product" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
-                    "api": "sgb_get_crossprod_mat_and_kin (host pinned vectors)", "y_norm2": y_norm2},
+                    "api": "sgb_get_crossprod_mat_and_kin (host pinned vectors)", "y_norm2": y_norm2,
+                    "y_norm2_single_gpu": Y_NORM2.get(args.workload),
+                    "y_norm2_equal_across_gpu_counts": (abs(y_norm2 - Y_NORM2[args.workload]) <= 1e-11 * Y_NORM2[args.workload]
+                                                        if args.workload in Y_NORM2 else None)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "pk2_stream_kernel<1,2,3>", "peak_source": peak_src,
