@@ -491,6 +491,15 @@ def main():
         y, _, X = synth.phenotype(N, SEED, gterm=gterm)
         probes = step1.ProbeStream(N, nmax=70, seed=200)
         fit0 = step1.glm_fit(y, X, step1.Binomial)
+        # time spent INSIDE the C-ABI calls (device work + the host<->device copies of the exports' arguments and results) vs in
+        # the Python mirror of the R driver between them (IRLS algebra, score-test matrices): the latter is the reference's
+        # unchanged R code in a deployment
+        abi = {"s": 0.0, "calls": 0}
+        for name in ("getCoefficients", "getAIScore", "fitglmmaiRPCG", "set_Diagof_StdGeno_LOCO"):
+            def timed(*a, _f=getattr(g, name), **k):
+                t_ = time.perf_counter(); r_ = _f(*a, **k); abi["s"] += time.perf_counter() - t_; abi["calls"] += 1
+                return r_
+            setattr(g, name, timed)
         g.reset_counters()
         barrier()
         ts = time.time()
@@ -499,6 +508,7 @@ def main():
         model = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim, LOCO=loco)
         g.sync()
         wall = max_over_ranks(time.time() - ts)
+        abi_s, abi_calls = abi["s"], abi["calls"]
         # variance ratio (FG.R:2152-2423): markers with MAC >= 20 in a fixed random order, the
         # getSigma_G solves of a round as ONE multi-column PCG; timed apart from the fit
         tv = time.time()
@@ -513,6 +523,7 @@ def main():
                       "pcg_solves": c["n_pcg_solves"], "pcg_iterations": c["n_pcg_iterations"],
                       "product_columns": c["n_crossprod_columns"], "products": c["n_crossprod_calls"], "LOCO": bool(loco),
                       "fit_s": tim.get("fit_s"), "loco_refits_s": tim.get("loco_s"),
+                      "inside_abi_calls_s": abi_s, "abi_calls": abi_calls, "host_mirror_between_calls_s": max(0.0, (tim.get("fit_s") or 0) + (tim.get("loco_s") or 0) - abi_s),
                       "variance_ratio": float(vr), "variance_ratio_markers": int(vr_markers), "variance_ratio_s": vr_s,
                       "note": "binary trait, 3 fixed-effect columns, nrun=30 probes, tolPCG=1e-5, full GRM, "
                               "22 leave-one-chromosome-out refits included; genotypes already resident (load_synth_s apart); "

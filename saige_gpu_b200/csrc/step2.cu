@@ -1108,7 +1108,8 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     // of chunk c.  The chunk is this large for the flagged variants: a saddle-point variant keeps one CTA busy for milliseconds
     // (~20 passes over all samples), so the per-variant kernel only fills the machine (444 resident CTAs) when a chunk holds
     // >= ~10^4 variants of which ~5 % are flagged (measured: 43 us per flagged variant with 256 MB chunks at N = 200k)
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_markers, s->chunk_bytes / B0));
+    // at most 65,024 variants per chunk: the re-pack / gather kernels index the variant with blockIdx.y (<= 65,535)
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_markers, s->chunk_bytes / B0), 65024));
     const size_t cbytes = (size_t)chunk * B0, obytes = sizeof(double) * (size_t)chunk * S2_NOUT;
     if (!s->pin[0] || s->pin_bytes < cbytes) {
         for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); s->pin[i] = nullptr; }

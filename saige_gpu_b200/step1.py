@@ -258,7 +258,9 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
         # score-test matrices of chromosome j are output only: they are computed on a host thread while the GPU already
         # solves chromosome j+1 (numpy and the ctypes call both release the GIL).
         pending = []
-        with ThreadPoolExecutor(max_workers=1) as pool:
+        # several workers: at 8 GPUs a chromosome's solves take ~25 ms, about what one score-test matrix set costs on a host
+        # core, so a single worker would become the critical path of the refit phase
+        with ThreadPoolExecutor(max_workers=4) as pool:
             for j, (s, e) in enumerate(zip(geno_start_vec(geno), geno_end_vec(geno))):
                 if s == -1 or e == -1:
                     out["LOCOResult"].append(dict(isLOCO=False))

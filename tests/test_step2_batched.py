@@ -175,3 +175,26 @@ def test_chunk_borders_do_not_change_a_row(identity):
     finally:
         g.close()
     assert one[:, 10].sum() > 30 and (one[:, 0] == 1).sum() > 2000
+
+
+def test_more_variants_than_a_grid_dimension():
+    """Small cohorts put > 65,535 variants into one 1 GB chunk: the chunk is capped so that the per-variant grid dimension of the
+    re-pack kernel stays legal.  70,000 variants x 403 samples, batched = per-variant kernel on a sample of rows."""
+    from saige_gpu_b200 import SaigeB200
+    rng = np.random.default_rng(8)
+    n_fam, nm, p = 403, 70_000, 2
+    bed = _bed_with_flips(n_fam, nm, 12, 0.0)
+    pos = np.arange(n_fam, dtype=np.int32)
+    M = _model(rng, n_fam, p, "quantitative")
+    g = SaigeB200(device=0)
+    try:
+        g.setSAIGEobjInCPP(M, 0.93, 2.0, pos)
+        out = g.mainMarkerInCPP(bed, n_fam, nm, 0.0, 0.5, 0.15)
+        g.setStep2Batched(False)
+        B0 = (n_fam + 3) // 4
+        tail = g.mainMarkerInCPP(bed[(nm - 3000) * B0:], n_fam, 3000, 0.0, 0.5, 0.15)
+    finally:
+        g.close()
+    a, b = np.nan_to_num(out[nm - 3000:]), np.nan_to_num(tail)
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) < 1e-9
+    assert (out[:, 0] == 1).sum() > 60_000
