@@ -24,7 +24,7 @@ else:
     print("full build: %.1f ms device (%.2f s wall), %.1f GB stored, %.0f TOPS" % (
         info["build_ms"], wall, info["stored_bytes"] / 1e9, info["int8_ops"] / info["build_ms"] / 1e9))
     rng = np.random.default_rng(0)
-    for k in (1, 4, 31):
+    for k in (1, 2, 4, 8, 31):
         B = rng.normal(size=(N, k))
         want = g.getCrossprodMatAndKin(B)
         g.setGRMMode("dense")
@@ -33,4 +33,4 @@ else:
         g.setGRMMode("packed")
         mp, _ = g.bench_crossprod_device(k, 3); mp, _ = g.bench_crossprod_device(k, 5)
         print("k=%2d stored-GRM product %.3f ms (%.0f GB/s of stored matrix), packed product %.3f ms, max rel diff %.2e" % (
-            k, ms.mean(), info["stored_bytes"] * ((k + 3) // 4) / ms.mean() / 1e6, mp.mean(), np.abs(got - want).max() / np.abs(want).max()))
+            k, ms.mean(), info["stored_bytes"] * (1 if k <= 2 else (k + 7) // 8) / ms.mean() / 1e6, mp.mean(), np.abs(got - want).max() / np.abs(want).max()))
