@@ -495,52 +495,77 @@ def main():
         # the Python mirror of the R driver between them (IRLS algebra, score-test matrices): the latter is the reference's
         # unchanged R code in a deployment
         abi = {"s": 0.0, "calls": 0}
-        for name in ("getCoefficients", "getAIScore", "fitglmmaiRPCG", "set_Diagof_StdGeno_LOCO"):
+        for name in ("getCoefficients", "getAIScore", "fitglmmaiRPCG", "set_Diagof_StdGeno_LOCO", "glmmkin_ai_PCG"):
             def timed(*a, _f=getattr(g, name), **k):
                 t_ = time.perf_counter(); r_ = _f(*a, **k); abi["s"] += time.perf_counter() - t_; abi["calls"] += 1
                 return r_
             setattr(g, name, timed)
-        g.reset_counters()
-        barrier()
-        ts = time.time()
-        tim = {}
-        loco = step1.set_loco_ranges(g, synth.chromosomes(M)[g.getQCdMarkerIndex()])   # config 3: LOCO on, 22 chromosomes
-        model = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim, LOCO=loco)
-        g.sync()
-        wall = max_over_ranks(time.time() - ts)
-        abi_s, abi_calls = abi["s"], abi["calls"]
-        # variance ratio (FG.R:2152-2423): markers with MAC >= 20 in a fixed random order, the
-        # getSigma_G solves of a round as ONE multi-column PCG; timed apart from the fit
-        tv = time.time()
         order = np.random.default_rng(SEED + 6).permutation(g.M)[:400]
-        vr, vr_list = step1.extractVarianceRatio(g, model, step1.Binomial, order)
-        vr_markers = len(vr_list)
-        g.sync()
-        vr_s = max_over_ranks(time.time() - tv)
-        c = g.counters()
-        step1_info = {"wall_s": wall, "load_synth_s": t_load, "tau": [float(v) for v in model["theta"]],
-                      "converged": bool(model["converged"]), "outer_iterations": len(model["tau_path"]) - 1,
+
+        def run_fit(native):
+            """One whole step-1 fit (22 LOCO refits included) + the variance ratio; native = the R driver loops inside the library
+            (sgb_glmmkin_ai_pcg, sgb_variance_ratio_markers), else through the per-export mirror of the unchanged R code."""
+            abi["s"], abi["calls"] = 0.0, 0
+            g.reset_counters()
+            barrier()
+            ts = time.time()
+            tim = {}
+            loco = step1.set_loco_ranges(g, synth.chromosomes(M)[g.getQCdMarkerIndex()])   # config 3: LOCO on, 22 chromosomes
+            model = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim, LOCO=loco, native_loops=native)
+            g.sync()
+            wall = max_over_ranks(time.time() - ts)
+            abi_s, abi_calls = abi["s"], abi["calls"]
+            c = g.counters()
+            # variance ratio (SURVEY 8f row 1, FG.R:2152-2423): markers with MAC >= 20 in a fixed random order, the
+            # getSigma_G solves of a round as ONE multi-column PCG; timed apart from the fit
+            tv = time.time()
+            vr, vr_list = step1.extractVarianceRatio(g, model, step1.Binomial, order, native_loops=native)
+            g.sync()
+            vr_s = max_over_ranks(time.time() - tv)
+            return dict(model=model, wall=wall, tim=tim, abi_s=abi_s, abi_calls=abi_calls, c=c, vr=vr, vr_n=len(vr_list), vr_s=vr_s,
+                        loco=loco)
+
+        rn = run_fit(True)
+        model, c, tim = rn["model"], rn["c"], rn["tim"]
+        step1_info = {"wall_s": rn["wall"], "load_synth_s": t_load, "tau": [float(v) for v in model["theta"]],
+                      "converged": bool(model["converged"]), "outer_iterations": int(model["n_outer"]),
                       "pcg_solves": c["n_pcg_solves"], "pcg_iterations": c["n_pcg_iterations"],
-                      "product_columns": c["n_crossprod_columns"], "products": c["n_crossprod_calls"], "LOCO": bool(loco),
-                      "fit_s": tim.get("fit_s"), "loco_refits_s": tim.get("loco_s"),
-                      "inside_abi_calls_s": abi_s, "abi_calls": abi_calls, "host_mirror_between_calls_s": max(0.0, (tim.get("fit_s") or 0) + (tim.get("loco_s") or 0) - abi_s),
-                      "variance_ratio": float(vr), "variance_ratio_markers": int(vr_markers), "variance_ratio_s": vr_s,
+                      "product_columns": c["n_crossprod_columns"], "products": c["n_crossprod_calls"], "LOCO": bool(rn["loco"]),
+                      "inside_abi_calls_s": rn["abi_s"], "abi_calls": rn["abi_calls"],
+                      "host_between_calls_s": max(0.0, rn["wall"] - rn["abi_s"]),
+                      "h2d_mbytes": c["bytes_h2d"] / 1e6, "d2h_mbytes": c["bytes_d2h"] / 1e6,
+                      "variance_ratio": float(rn["vr"]), "variance_ratio_markers": int(rn["vr_n"]), "variance_ratio_s": rn["vr_s"],
+                      "wall_with_variance_ratio_s": rn["wall"] + rn["vr_s"],
+                      "driver": "R driver loops inside the library: glmmkin.ai_PCG_Rcpp_Binary as one call (sgb_glmmkin_ai_pcg: Get_Coef "
+                                "IRLS, AI-REML steps, 22 LOCO refits on device-resident vectors, first probe batch resident), "
+                                "extractVarianceRatio's marker loop as one call per round (sgb_variance_ratio_markers); the score-test "
+                                "matrices of the result list on host threads",
                       "note": "binary trait, 3 fixed-effect columns, nrun=30 probes, tolPCG=1e-5, full GRM, "
                               "22 leave-one-chromosome-out refits included; genotypes already resident (load_synth_s apart); "
                               "wide batches at 7 digits (exact 55-bit right-hand sides)"}
         if ingest_info and "seconds" in ingest_info:
             step1_info["setgeno_s"] = ingest_info["seconds"]
-            step1_info["wall_with_setgeno_s"] = wall + ingest_info["seconds"]
+            step1_info["wall_with_setgeno_s"] = rn["wall"] + ingest_info["seconds"]
+        # the same fit through the per-export mirror of the UNCHANGED R driver (one ABI call per Rcpp export, the IRLS algebra and the
+        # variance-ratio marker loop in the host language between them)
+        rm = run_fit(False)
+        mm = rm["model"]
+        step1_info["r_mirror"] = {"wall_s": rm["wall"], "fit_s": rm["tim"].get("fit_s"), "loco_refits_s": rm["tim"].get("loco_s"),
+                                  "inside_abi_calls_s": rm["abi_s"], "abi_calls": rm["abi_calls"],
+                                  "host_mirror_between_calls_s": max(0.0, rm["wall"] - rm["abi_s"]),
+                                  "h2d_mbytes": rm["c"]["bytes_h2d"] / 1e6, "d2h_mbytes": rm["c"]["bytes_d2h"] / 1e6,
+                                  "variance_ratio_s": rm["vr_s"], "tau": [float(v) for v in mm["theta"]],
+                                  "pcg_iterations": rm["c"]["n_pcg_iterations"],
+                                  "tau_abs_diff_vs_library_loops": float(np.max(np.abs(mm["theta"] - model["theta"]))),
+                                  "alpha_rel_diff_vs_library_loops": float(np.max(np.abs(mm["coefficients"] - model["coefficients"]) /
+                                                                                  np.abs(mm["coefficients"]))),
+                                  "variance_ratio_rel_diff_vs_library_loops": float(abs(rm["vr"] - rn["vr"]) / abs(rm["vr"]))}
         # the same fit with the tolerance-driven digit count of wide batches (sgb_set_product_tolerance(1e-10) = 5 digits)
         g.set_product_tolerance(1e-10)
-        barrier()
-        ts5 = time.time()
-        tim5 = {}
-        model5 = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", timings=tim5, LOCO=loco)
-        g.sync()
-        wall5 = max_over_ranks(time.time() - ts5)
+        r5 = run_fit(True)
         g.set_rhs_limbs(7)
-        step1_info["digits5"] = {"wall_s": wall5, "fit_s": tim5.get("fit_s"), "loco_refits_s": tim5.get("loco_s"),
+        model5 = r5["model"]
+        step1_info["digits5"] = {"wall_s": r5["wall"], "variance_ratio_s": r5["vr_s"],
                                  "tau": [float(v) for v in model5["theta"]],
                                  "tau_rel_diff_vs_digits7": float(abs(model5["theta"][1] - model["theta"][1]) / abs(model["theta"][1])),
                                  "alpha_rel_diff_vs_digits7": float(np.max(np.abs(model5["coefficients"] - model["coefficients"]) /

@@ -166,6 +166,59 @@ int sgb_get_sigma_x(sgb_ctx *h, const double *w, const double *tau, const double
                     int maxiterPCG, double tolPCG, int loco, double *Sigma_iX);
 int sgb_get_sigma_g(sgb_ctx *h, const double *w, const double *tau, const double *Gmat, int k,
                     int maxiterPCG, double tolPCG, int loco, double *Sigma_iG);
+/* ---- driver loops of SAIGE_fitGLMM_fast.R ("FG.R") as single calls (optional: the exports above stay the drop-in) ----
+ * The R functions below call the exports above in a loop and do O(N) vector algebra in between (IRLS working vector,
+ * covariate adjustment of a marker); with 8 GPUs that host-side algebra and the N-vector round trips cost more than the
+ * products.  These entry points run the same loop with every N-vector resident on the device; an R driver that wants them
+ * replaces the body of the named R function by one .Call, nothing else changes.
+ *
+ * Get_Coef / Get_Coef_LOCO (FG.R:2-35, 42-73).  family 0 = binomial(logit) with R's own clamping (logit_linkinv /
+ * logit_mu_eta of stats/src/family.c: |eta| > 30), 1 = gaussian(identity).  eta0 and the returned eta INCLUDE the offset.
+ * Outputs as the R list: Y, W, eta, mu, Sigma_iY (N), Sigma_iX (N x p), alpha (p), cov (p x p); n_iter = getCoefficients
+ * calls made (<= maxiter).  Any output pointer except alpha / cov may be NULL. */
+int sgb_get_coef(sgb_ctx *h, int family, const double *y, const double *X, int p, const double *offset, const double *tau,
+                 const double *alpha0, const double *eta0, int maxiter, int maxiterPCG, double tolPCG, int loco,
+                 double *Y, double *alpha, double *eta, double *W, double *cov, double *Sigma_iY, double *Sigma_iX,
+                 double *mu, int32_t *n_iter);
+/* The leave-one-chromosome-out refit loop (FG.R:255-292): for every chromosome c of setStartEndIndexVec that has a range,
+ * setStartEndIndex(start_c, end_c, c) and Get_Coef_LOCO starting from the previous chromosome's (alpha, eta).  Column / slot c
+ * of Y, eta, mu (N x nchr), alpha (p x nchr), cov (p*p x nchr), n_iter (nchr) is written for those chromosomes only.
+ * Requires sgb_set_diag_of_stdgeno_loco. */
+/* on_chrom (may be NULL) is called from the calling thread as soon as the outputs of chromosome `chrom` are complete in the
+ * caller's arrays (chrom = -1: the genome-wide fit of sgb_glmmkin_ai_pcg), so the caller can start its own per-chromosome work
+ * (ScoreTest_NULL_Model, FG.R:283-288) on another thread while the next refit runs on the GPU. */
+typedef void (*sgb_chrom_done_fn)(void *user, int chrom);
+int sgb_get_coef_loco_all(sgb_ctx *h, int family, const double *y, const double *X, int p, const double *offset,
+                          const double *tau, const double *alpha0, const double *eta0, int maxiter, int maxiterPCG,
+                          double tolPCG, double *Y, double *alpha, double *eta, double *cov, double *mu, int32_t *n_iter,
+                          sgb_chrom_done_fn on_chrom, void *chrom_user);
+/* glmmkin.ai_PCG_Rcpp_Binary / glmmkin.ai_PCG_Rcpp_Quantitative after setgeno (FG.R:127-304, 340-549) as ONE call: the first
+ * Get_Coef + getAIScore[_q], the outer loop of Get_Coef + fitglmmaiRPCG[_q] with its three stopping rules, the final Get_Coef
+ * and, with loco != 0, set_Diagof_StdGeno_LOCO and the refit loop of sgb_get_coef_loco_all.  quantitative = 0: binomial family,
+ * tau[0] fixed at 1; 1: gaussian.  alpha_fit0 / eta_fit0: coefficients and linear predictors of the glm fit0 (eta includes the
+ * offset); tauInit[2] as the R argument.  Outputs: tau_out[2], alpha (p), eta, mu, Y (N), cov (p x p), converged (i < maxiter),
+ * n_outer (iterations of the outer loop); the *_loco outputs are laid out as in sgb_get_coef_loco_all and may be NULL when
+ * loco = 0.  Probes come from `probes` exactly as in sgb_get_ai_score (sgb_set_probe_stream_fixed applies). */
+int sgb_glmmkin_ai_pcg(sgb_ctx *h, int quantitative, const double *y, const double *X, int p, const double *offset,
+                       const double *alpha_fit0, const double *eta_fit0, const double *tauInit, int maxiter, double tol,
+                       int nrun, double tolPCG, int maxiterPCG, double traceCVcutoff, int loco, sgb_probe_fn probes,
+                       void *user, double *tau_out, double *alpha, double *eta, double *mu, double *Y, double *cov,
+                       int32_t *converged, int32_t *n_outer, double *Y_loco, double *alpha_loco, double *eta_loco,
+                       double *cov_loco, double *mu_loco, int32_t *n_iter_loco, sgb_chrom_done_fn on_chrom, void *chrom_user);
+/* The marker loop of extractVarianceRatio (FG.R:2298-2378) for a batch of markers: Get_OneSNP_Geno[_forVarRatio], flip to
+ * the minor allele, AC, G = G0 - XXVX_inv (XV G0), Sigma^-1 G as one multi-column solve, and
+ *   var1[j] = (G' Sigma_iG - G' Sigma_iX (X' Sigma_iX)^-1 X' Sigma_iG) / AC,   var2null[j] = sum mu2 g^2 (g = G / sqrt(AC);
+ * mu2 = NULL: sum g^2, the quantitative trait).  marker_idx: 0-based indices into the GRM store (from_vr_store = 0) or the
+ * variance-ratio hold-out store (1).  XV is p x N, XXVX_inv and Sigma_iX N x p, all column-major as R holds them. */
+int sgb_variance_ratio_markers(sgb_ctx *h, const int64_t *marker_idx, int nmark, int from_vr_store, const double *w,
+                               const double *tau, const double *X, int p, const double *XV, const double *XXVX_inv,
+                               const double *Sigma_iX, const double *mu2, int maxiterPCG, double tolPCG, double *var1,
+                               double *var2null, double *AC);
+/* GetTrace re-seeds R's generator to 200 before drawing its probes (FG.cpp:3114), so the first nrun probe vectors are the same
+ * in every call for a given N.  on = 1 lets getAIScore / fitglmmaiRPCG reuse the device-resident copy of that first batch (and
+ * its cached K.U) without calling `probes` for it; the callback still serves the +10 retry batches, after being asked once for
+ * the skipped columns so that its stream position is right.  Default 0: every batch comes from the callback. */
+int sgb_set_probe_stream_fixed(sgb_ctx *h, int on);
 double sgb_cal_cv(const double *x, int n);                                   /* calCV (FG.cpp:3104) */
 double sgb_inner_product(const double *x, const double *y, int64_t n);      /* innerProduct */
 
@@ -295,6 +348,7 @@ typedef struct {
     int64_t n_allreduce;            /* NCCL allreduces issued */
     int64_t bytes_h2d, bytes_d2h;
     int64_t n_probe_product_reuse;  /* getAIScore calls that reused the cached K.U of the Hutchinson probes */
+    int64_t n_probe_batches_resident; /* first probe batches taken from the device copy (sgb_set_probe_stream_fixed) */
 } sgb_counters;
 int sgb_get_counters(sgb_ctx *h, sgb_counters *out);
 int sgb_reset_counters(sgb_ctx *h);

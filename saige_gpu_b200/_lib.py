@@ -13,12 +13,14 @@ NCCL_ID_BYTES = 128
 ENGINE_TENSOR, ENGINE_F64, ENGINE_UMMA = 0, 1, 2
 
 PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double))
+CHROM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
 
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_crossprod_calls", "n_crossprod_columns", "n_pcg_solves",
                                          "n_pcg_iterations", "n_kernel_launches", "n_allreduce",
-                                         "bytes_h2d", "bytes_d2h", "n_probe_product_reuse")]
+                                         "bytes_h2d", "bytes_d2h", "n_probe_product_reuse",
+                                         "n_probe_batches_resident")]
 
 
 class SaigeB200Error(RuntimeError):
@@ -86,6 +88,16 @@ _SIGS = {
                                         C.c_double, C.c_double, PROBE_FN, P]),
     "sgb_get_sigma_x": (C.c_int, [P, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_int, DP]),
     "sgb_get_sigma_g": (C.c_int, [P, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_int, DP]),
+    "sgb_get_coef": (C.c_int, [P, C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_int,
+                               DP, DP, DP, DP, DP, DP, DP, DP, P]),
+    "sgb_get_coef_loco_all": (C.c_int, [P, C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, C.c_int, C.c_int, C.c_double,
+                                        DP, DP, DP, DP, DP, P, CHROM_FN, P]),
+    "sgb_glmmkin_ai_pcg": (C.c_int, [P, C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, C.c_int, C.c_double, C.c_int, C.c_double,
+                                     C.c_int, C.c_double, C.c_int, PROBE_FN, P, DP, DP, DP, DP, DP, DP, P, P, DP, DP, DP, DP, DP, P,
+                                     CHROM_FN, P]),
+    "sgb_variance_ratio_markers": (C.c_int, [P, P, C.c_int, C.c_int, DP, DP, DP, C.c_int, DP, DP, DP, DP, C.c_int, C.c_double,
+                                             DP, DP, DP]),
+    "sgb_set_probe_stream_fixed": (C.c_int, [P, C.c_int]),
     "sgb_cal_cv": (C.c_double, [DP, C.c_int]),
     "sgb_inner_product": (C.c_double, [DP, DP, I64]),
     "sgb_step2_set_model": (C.c_int, [P, I64, C.c_int, C.c_int, DP, DP, DP, DP, DP, DP, DP, DP, DP, DP, C.c_double, C.c_double, P]),

@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import SaigeB200Error, PROBE_FN
+from ._lib import SaigeB200Error, PROBE_FN, CHROM_FN
 
 
 def _f64(a):
@@ -216,6 +216,7 @@ class SaigeB200:
         s = np.ascontiguousarray(startIndex_vec, dtype=np.int32)
         e = np.ascontiguousarray(endIndex_vec, dtype=np.int32)
         self._ck(self._L.sgb_set_start_end_index_vec(self._h, _p(s), _p(e), len(s)))
+        self._loco_start, self._loco_end = [int(v) for v in s], [int(v) for v in e]
 
     def setStartEndIndex(self, startIndex, endIndex, chromIndex):
         self._ck(self._L.sgb_set_start_end_index(self._h, int(startIndex), int(endIndex), int(chromIndex)))
@@ -307,6 +308,107 @@ class SaigeB200:
 
     def getCoefficients_LOCO(self, Yvec, Xmat, wVec, tauVec, maxiterPCG, tolPCG):
         return self.getCoefficients(Yvec, Xmat, wVec, tauVec, maxiterPCG, tolPCG, True)
+
+    # ---- driver loops of SAIGE_fitGLMM_fast.R as single calls (optional; see include/saige_b200.h) ----
+    FAMILY = {"binomial": 0, "gaussian": 1}
+
+    def Get_Coef(self, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, loco=False):
+        """Get_Coef / Get_Coef_LOCO (FG.R:2-35, 42-73) with the IRLS loop on the device; returns the R list."""
+        X = _f64(np.asarray(X).reshape(self.N, -1))
+        p = X.shape[1]
+        y, off, tau, a0, e0 = _f64(y), _f64(offset), _f64(tau), _f64(alpha0), _f64(eta0)
+        Y, eta, W, mu, SiY = (np.empty(self.N) for _ in range(5))
+        SiX, cov, alpha = np.empty((self.N, p), order="F"), np.empty((p, p), order="F"), np.empty(p)
+        nit = np.zeros(1, dtype=np.int32)
+        self._ck(self._L.sgb_get_coef(self._h, self.FAMILY[getattr(family, "name", family)], _p(y), _p(X), p, _p(off), _p(tau),
+                                      _p(a0), _p(e0), int(maxiter), int(maxiterPCG), float(tolPCG), int(loco), _p(Y), _p(alpha),
+                                      _p(eta), _p(W), _p(cov), _p(SiY), _p(SiX), _p(mu), _p(nit)))
+        return dict(Y=Y, alpha=alpha, eta=eta, W=W, cov=cov, sqrtW=np.sqrt(W), Sigma_iY=SiY, Sigma_iX=SiX, mu=mu, n_iter=int(nit[0]))
+
+    @staticmethod
+    def _chrom_cb(on_chrom, view):
+        """ctypes callback that hands chromosome c's finished outputs (view(c) -> dict) to on_chrom(c, dict)."""
+        if on_chrom is None:
+            return C.cast(None, CHROM_FN)
+
+        def cb(user, c):
+            try:
+                on_chrom(int(c), view(int(c)))
+            except Exception:      # never let an exception cross the C boundary
+                pass
+        return CHROM_FN(cb)
+
+    def Get_Coef_LOCO_all(self, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, on_chrom=None):
+        """The leave-one-chromosome-out refit loop (FG.R:255-292) as one call; returns one dict per chromosome of
+        setStartEndIndexVec (None where the chromosome has no range).  on_chrom(c, dict) is called as soon as chromosome c is
+        done, while the next one runs on the GPU."""
+        X = _f64(np.asarray(X).reshape(self.N, -1))
+        p = X.shape[1]
+        nchr = len(self._loco_start)
+        y, off, tau, a0, e0 = _f64(y), _f64(offset), _f64(tau), _f64(alpha0), _f64(eta0)
+        Y, eta, mu = (np.zeros((self.N, nchr), order="F") for _ in range(3))
+        alpha, cov = np.zeros((p, nchr), order="F"), np.zeros((p * p, nchr), order="F")
+        nit = np.zeros(nchr, dtype=np.int32)
+
+        def view(c):
+            return dict(Y=Y[:, c], alpha=alpha[:, c].copy(), eta=eta[:, c], mu=mu[:, c],
+                        cov=cov[:, c].reshape(p, p, order="F").copy(), n_iter=int(nit[c]))
+        cb = self._chrom_cb(on_chrom, view)
+        self._ck(self._L.sgb_get_coef_loco_all(self._h, self.FAMILY[getattr(family, "name", family)], _p(y), _p(X), p, _p(off),
+                                               _p(tau), _p(a0), _p(e0), int(maxiter), int(maxiterPCG), float(tolPCG), _p(Y),
+                                               _p(alpha), _p(eta), _p(cov), _p(mu), _p(nit), cb, None))
+        return [None if (s == -1 or e == -1) else view(c) for c, (s, e) in enumerate(zip(self._loco_start, self._loco_end))]
+
+    def glmmkin_ai_PCG(self, trait, y, X, offset, alpha_fit0, eta_fit0, tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG,
+                       traceCVcutoff, LOCO, draw, on_chrom=None):
+        """glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549) as one call (sgb_glmmkin_ai_pcg).
+        on_chrom(c, dict): called when the genome-wide fit (c = -1) / chromosome c's refit is complete, while the GPU goes on."""
+        X = _f64(np.asarray(X).reshape(self.N, -1))
+        p = X.shape[1]
+        N = self.N
+        y, off, a0, e0, ti = _f64(y), _f64(offset), _f64(alpha_fit0), _f64(eta_fit0), _f64(tauInit)
+        tau, alpha, cov = np.zeros(2), np.zeros(p), np.zeros((p, p), order="F")
+        eta, mu, Y = np.empty(N), np.empty(N), np.empty(N)
+        conv, nout = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        nchr = len(self._loco_start) if LOCO else 0
+        Yl, el, ml = (np.zeros((N, max(nchr, 1)), order="F") for _ in range(3))
+        al, cl, nl = np.zeros((p, max(nchr, 1)), order="F"), np.zeros((p * p, max(nchr, 1)), order="F"), np.zeros(max(nchr, 1), dtype=np.int32)
+        cb = self._probe_cb(draw)
+
+        def view(c):
+            if c < 0:
+                return dict(theta=tau, coefficients=alpha, linear_predictors=eta, fitted_values=mu, Y=Y, cov=cov,
+                            converged=bool(conv[0]), n_outer=int(nout[0]))
+            return dict(Y=Yl[:, c], alpha=al[:, c].copy(), eta=el[:, c], mu=ml[:, c], cov=cl[:, c].reshape(p, p, order="F").copy(),
+                        n_iter=int(nl[c]))
+        ccb = self._chrom_cb(on_chrom, view)
+        self._ck(self._L.sgb_glmmkin_ai_pcg(self._h, int(trait == "quantitative"), _p(y), _p(X), p, _p(off), _p(a0), _p(e0), _p(ti),
+                                            int(maxiter), float(tol), int(nrun), float(tolPCG), int(maxiterPCG), float(traceCVcutoff),
+                                            int(bool(LOCO)), cb, None, _p(tau), _p(alpha), _p(eta), _p(mu), _p(Y), _p(cov), _p(conv),
+                                            _p(nout), _p(Yl), _p(al), _p(el), _p(cl), _p(ml), _p(nl), ccb, None))
+        out = dict(view(-1), loco=None)
+        if LOCO:
+            out["loco"] = [None if (s == -1 or e == -1) else view(c) for c, (s, e) in enumerate(zip(self._loco_start, self._loco_end))]
+        return out
+
+    def varianceRatioMarkers(self, marker_idx, from_vr_store, wVec, tauVec, Xmat, XV, XXVX_inv, Sigma_iX, mu2, maxiterPCG, tolPCG):
+        """The marker loop of extractVarianceRatio (FG.R:2298-2378) for a batch of markers: (var1, var2null, AC)."""
+        idx = np.ascontiguousarray(marker_idx, dtype=np.int64)
+        X = _f64(np.asarray(Xmat).reshape(self.N, -1))
+        p = X.shape[1]
+        XV = _f64(np.asarray(XV).reshape(p, self.N))
+        XX, SiX = _f64(np.asarray(XXVX_inv).reshape(self.N, p)), _f64(np.asarray(Sigma_iX).reshape(self.N, p))
+        w, tau = _f64(wVec), _f64(tauVec)
+        m2 = None if mu2 is None else _f64(mu2)
+        v1, v2, ac = np.zeros(len(idx)), np.zeros(len(idx)), np.zeros(len(idx))
+        self._ck(self._L.sgb_variance_ratio_markers(self._h, _p(idx), len(idx), int(bool(from_vr_store)), _p(w), _p(tau), _p(X), p,
+                                                    _p(XV), _p(XX), _p(SiX), None if m2 is None else _p(m2), int(maxiterPCG),
+                                                    float(tolPCG), _p(v1), _p(v2), _p(ac)))
+        return v1, v2, ac
+
+    def setProbeStreamFixed(self, on=True):
+        """The first nrun probes are the same in every GetTrace call (set_seed(200), FG.cpp:3114): keep them on the device."""
+        self._ck(self._L.sgb_set_probe_stream_fixed(self._h, 1 if on else 0))
 
     def _ai_args(self, Yvec, Xmat, wVec, tauVec, Sigma_iY, Sigma_iX, cov):
         X = _f64(np.asarray(Xmat).reshape(self.N, -1))

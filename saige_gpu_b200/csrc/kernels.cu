@@ -1372,3 +1372,104 @@ int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d
     LAUNCH_CHECK(h);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// resident driver loops (sgb_get_coef, sgb_variance_ratio_markers): the O(N) algebra the R driver does between exports
+// ---------------------------------------------------------------------------------------------------
+// The IRLS update of Get_Coef (FG.R:4-8, 21-26): eta = eta_in (+ offset), mu = linkinv(eta), Y = eta - offset + (y - mu) / mu.eta,
+// W = (mu.eta / sqrt(variance(mu)))^2.  Binomial: R's logit_linkinv / logit_mu_eta (stats/src/family.c) with their |eta| > 30 clamps.
+__global__ void irls_update_kernel(int family, const double *eta_in /* may alias eta_out */, int add_offset, const double *__restrict__ y,
+                                   const double *__restrict__ offset, int64_t N, double *eta_out, double *__restrict__ mu_out,
+                                   double *__restrict__ Y, double *__restrict__ W)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double off = offset[i];
+    const double eta = add_offset ? eta_in[i] + off : eta_in[i];
+    double mu, me, var;
+    if (family == 0) {
+        const double eps = 2.220446049250313e-16;
+        const double e = exp(eta);
+        const double tmp = eta < -30.0 ? eps : (eta > 30.0 ? 1.0 / eps : e);
+        mu = tmp / (1.0 + tmp);
+        const double opexp = 1.0 + e;
+        me = (eta > 30.0 || eta < -30.0) ? eps : e / (opexp * opexp);
+        var = mu * (1.0 - mu);
+    } else {
+        mu = eta; me = 1.0; var = 1.0;
+    }
+    const double sqrtW = me / sqrt(var);
+    eta_out[i] = eta;
+    mu_out[i] = mu;
+    Y[i] = eta - off + (y[i] - mu) / me;
+    W[i] = sqrtW * sqrtW;
+}
+
+int k_irls_update(sgb_ctx *h, int family, const double *eta_in, int add_offset, const double *y, const double *offset, double *eta_out,
+                  double *mu, double *Y, double *W)
+{
+    irls_update_kernel<<<(unsigned)cdiv(h->N, 256), 256, 0, h->stream>>>(family, eta_in, add_offset, y, offset, h->N, eta_out, mu, Y, W);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// Out[i + j*N] = genotype of sample i in packed row rows[j] of P (device coding; tiled store or row-major rows of `stride`
+// bytes), 0 for rows[j] < 0 (a marker another rank owns: the sum-allreduce that follows fills it in)
+__global__ void decode_marker_cols_kernel(const uint8_t *__restrict__ P, int tiled, int64_t stride, const int64_t *__restrict__ rows,
+                                          int64_t N, double *__restrict__ Out)
+{
+    const int j = blockIdx.y;
+    const int64_t r = rows[j];
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // packed byte = samples 4b .. 4b+3
+    if (4 * b >= N) return;
+    int g[4] = {0, 0, 0, 0};
+    if (r >= 0) {
+        const uint32_t v = P[tiled ? sgb_tiled_off(r, b, stride) : r * stride + b];
+        sgb_unpack_nibble(v & 15u, g[0], g[1]);
+        sgb_unpack_nibble(v >> 4, g[2], g[3]);
+    }
+    double *o = Out + (int64_t)j * N + 4 * b;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (4 * b + q < N) o[q] = (double)g[q];
+}
+
+int k_decode_marker_cols(sgb_ctx *h, const uint8_t *P, int tiled, int64_t stride, const int64_t *d_rows, int ncol, double *Out)
+{
+    if (ncol == 0) return 0;
+    decode_marker_cols_kernel<<<dim3((unsigned)cdiv(cdiv(h->N, 4), 256), ncol), 256, 0, h->stream>>>(P, tiled, stride, d_rows, h->N, Out);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// G[:,j] = 2 - G[:,j] where flip[j] (FG.R:2318-2320)
+__global__ void flip_cols_kernel(double *__restrict__ G, const int *__restrict__ flip, int64_t N)
+{
+    const int j = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && flip[j]) G[i + (int64_t)j * N] = 2.0 - G[i + (int64_t)j * N];
+}
+
+int k_flip_cols(sgb_ctx *h, double *G, const int *d_flip, int ncol)
+{
+    if (ncol == 0) return 0;
+    flip_cols_kernel<<<dim3((unsigned)cdiv(h->N, 256), ncol), 256, 0, h->stream>>>(G, d_flip, h->N);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// Out[:,j] = v .* In[:,j]
+__global__ void rowscale_cols_kernel(const double *__restrict__ v, const double *__restrict__ In, int64_t N, double *__restrict__ Out)
+{
+    const int j = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) Out[i + (int64_t)j * N] = v[i] * In[i + (int64_t)j * N];
+}
+
+int k_rowscale_cols(sgb_ctx *h, const double *v, const double *In, int ncol, double *Out)
+{
+    if (ncol == 0) return 0;
+    rowscale_cols_kernel<<<dim3((unsigned)cdiv(h->N, 256), ncol), 256, 0, h->stream>>>(v, In, h->N, Out);
+    LAUNCH_CHECK(h);
+    return 0;
+}

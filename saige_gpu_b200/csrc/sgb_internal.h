@@ -16,6 +16,16 @@ struct sgb_nvtx_range {
 #define SGB_RANGE_CAT(a, b) SGB_RANGE_CAT2(a, b)
 #define SGB_RANGE(name) sgb_nvtx_range SGB_RANGE_CAT(nvtx_range_, __LINE__)(name)
 
+// Host-side phase timer, on when the environment has SGB_PROFILE=1: synchronises the stream on entry and exit of the scope and
+// prints "[sgb] <name>: <ms>" to stderr (nested scopes indent).  Off: two predictable branches.  tools/profile_step1_host.py reads it.
+struct sgb_ctx;
+struct sgb_prof_scope {
+    sgb_ctx *h; const char *name; double t0; bool on;
+    sgb_prof_scope(sgb_ctx *h, const char *name);
+    ~sgb_prof_scope();
+};
+#define SGB_PROF(h, name) sgb_prof_scope SGB_RANGE_CAT(prof_scope_, __LINE__)(h, name)
+
 #define SGB_LIMBS 8          // signed base-128 digits per fp64 value (55-bit fixed point: round(v * 2^(53-E)))
 #define SGB_KSTEP_BYTES 64   // packed bytes (256 genotypes) consumed per k-step of the tensor kernel
 #define SGB_ROW_ALIGN 512    // row padding of both genotype copies (CTA tile of the tensor kernel)
@@ -79,6 +89,7 @@ struct sgb_ctx {
     double *d_diag = nullptr;        // sum_m z_mi^2 over all markers (N), lazily computed (FG.cpp:665-704)
     bool diag_ready = false;
     double *d_diag_loco = nullptr;   // N x nchr: full - per-chromosome (FG.cpp:4934-4958)
+    size_t diag_loco_elems = 0;
     std::vector<int64_t> msub_by_chr;
     bool diag_loco_ready = false;
 
@@ -99,6 +110,7 @@ struct sgb_ctx {
     // GetTrace, FG.cpp:3114), so the nrun-column product is computed once per (genotypes, GRM mode) and checked bitwise
     double *d_ku = nullptr; size_t ku_elems = 0;      // [U | K.U]
     int64_t ku_cols = 0;                              // 0 = nothing cached
+    int probe_stream_fixed = 0;                       // sgb_set_probe_stream_fixed: the cached first batch stands for the callback's
     int32_t *d_limbsum = nullptr;                     // [2][1024][8] column limb sums of the current split
     double *d_red = nullptr;                          // [2][1024][SGB_PART_BLOCKS] per-block partial (sums | maxima) of the fused statistics
     unsigned int *d_ticket = nullptr;                 // [1024] last-block tickets (zero between kernels)
@@ -209,6 +221,11 @@ int k_pair_dots(sgb_ctx *h, const double *A, int64_t lda, const double *B, int64
 int k_project(sgb_ctx *h, const double *In, const double *SiX, int p, const double *d_C, int ncol, double *Out);
 int k_eta(sgb_ctx *h, const double *Y, const double *SiY, const double *SiX, int p, const double *d_alpha,
           const double *w, double tau0, double *eta);
+int k_irls_update(sgb_ctx *h, int family, const double *eta_in, int add_offset, const double *y, const double *offset, double *eta_out,
+                  double *mu, double *Y, double *W);
+int k_decode_marker_cols(sgb_ctx *h, const uint8_t *P, int tiled, int64_t stride, const int64_t *d_rows, int ncol, double *Out);
+int k_flip_cols(sgb_ctx *h, double *G, const int *d_flip, int ncol);
+int k_rowscale_cols(sgb_ctx *h, const double *v, const double *In, int ncol, double *Out);
 int k_rademacher_fill(sgb_ctx *h, double *B, int64_t n, uint64_t seed);
 int k_axpby(sgb_ctx *h, double a, const double *x, double b, const double *y, int64_t n, double *out);
 int k_count_diff(sgb_ctx *h, const double *a, const double *b, int64_t n, int *d_count);

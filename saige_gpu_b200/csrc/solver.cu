@@ -214,6 +214,7 @@ int sgb_diag_loco_device(sgb_ctx *h)
     NEED_LOADED(h);
     int nc = (int)h->startVec.size();
     if (nc == 0) return sgb_fail(h, "set_Diagof_StdGeno_LOCO: call setStartEndIndexVec first");
+    SGB_PROF(h, "set_Diagof_StdGeno_LOCO");
     SGB_TRY(sgb_diag_device(h));
     std::vector<int64_t> lo(nc, 0), hi(nc, 0);
     h->msub_by_chr.assign(nc, 0);
@@ -222,9 +223,16 @@ int sgb_diag_loco_device(sgb_ctx *h)
             loco_local_range(h, h->startVec[c], h->endVec[c], &lo[c], &hi[c]);
             h->msub_by_chr[c] = h->endVec[c] - h->startVec[c] + 1;
         }
-    if (h->d_diag_loco) { cudaFree(h->d_diag_loco); h->d_diag_loco = nullptr; }
-    CUDA_OK(h, cudaMalloc((void **)&h->d_diag_loco, sizeof(double) * h->N * nc));
-    SGB_TRY(diag_ranges(h, nc, lo, hi, h->d_diag_loco));
+    {
+        SGB_PROF(h, "diag_loco alloc");
+        size_t bytes = h->diag_loco_elems * sizeof(double);
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_diag_loco, &bytes, sizeof(double) * h->N * nc));
+        h->diag_loco_elems = bytes / sizeof(double);
+    }
+    {
+        SGB_PROF(h, "diag_ranges (all chromosomes)");
+        SGB_TRY(diag_ranges(h, nc, lo, hi, h->d_diag_loco));
+    }
     for (int c = 0; c < nc; c++)
         SGB_TRY(k_axpby(h, 1.0, h->d_diag, -1.0, h->d_diag_loco + (int64_t)c * h->N, h->N, h->d_diag_loco + (int64_t)c * h->N));
     h->diag_loco_ready = true;
@@ -266,6 +274,7 @@ int sgb_pcg_device(sgb_ctx *h, const double *d_w, const double *tau, const doubl
     for (int c = 0; c < k; c++) if (h->h_scal[c] > tol) act.push_back(c);
     int cur = 0, iter = 0;
     SGB_RANGE("pcg_solve");
+    SGB_PROF(h, "pcg_solve");
     while (!act.empty() && iter < maxiter) {
         SGB_RANGE("pcg_iteration");
         iter++;
@@ -573,6 +582,20 @@ extern "C" int sgb_get_coefficients(sgb_ctx *h, const double *Y, const double *X
     return 0;
 }
 
+// Device scratch of the AI step: dB right-hand sides [PY | U...] (column 0 = Sigma_iY on entry), dK = K.[...], dS = Sigma^-1 [...],
+// dPr projected; kb = widest batch in columns; dC 4096 doubles
+struct ai_scratch { double *dB, *dK, *dS, *dPr, *dC; int kb; };
+static size_t ai_scratch_elems(int64_t N, int nrun) { return (size_t)N * 4 * (std::max(nrun, 10) + 2) + 4096; }
+static void ai_scratch_take(arena *a, int64_t N, int nrun, ai_scratch *sc)
+{
+    sc->kb = std::max(nrun, 10) + 2;               // widest batch: [U | APY | PY]
+    sc->dB = a->take((size_t)N * sc->kb); sc->dK = a->take((size_t)N * sc->kb); sc->dS = a->take((size_t)N * sc->kb);
+    sc->dPr = a->take((size_t)N * sc->kb); sc->dC = a->take(4096);
+}
+static int ai_score_core(sgb_ctx *h, bool quant, const double *dw, const double *dY, const double *dX, const double *dSiX, int p,
+                         const double *tau, const double *cov_in, int nrun, int maxiterPCG, double tolPCG, double traceCVcutoff,
+                         sgb_probe_fn probes, void *user, const ai_scratch &sc, double *out8, double *PY_out);
+
 // Shared body of getAIScore / getAIScore_q.  out: YPAPY, YPA0PY, Trace0, Trace1, AI00, AI01, AI11, nrun used.
 static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *X, int p, const double *w, const double *tau,
                          const double *Sigma_iY, const double *Sigma_iX, const double *cov_in, int nrun, int maxiterPCG,
@@ -584,20 +607,29 @@ static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *
     if (nrun < 2 || nrun > 500) return sgb_fail(h, "getAIScore: nrun=%d out of range [2,500]", nrun);
     if (!probes) return sgb_fail(h, "getAIScore: probe callback is NULL (probes are drawn by the caller's RNG)");
     const int64_t N = h->N;
-    const int kb = std::max(nrun, 10) + 2;         // widest batch: [U | APY | PY]
     arena a;
-    SGB_TRY(arena_begin(h, (size_t)N * (2 + 2 * p + 4 * kb) + 4096, &a));
+    SGB_TRY(arena_begin(h, (size_t)N * (2 + 2 * p) + ai_scratch_elems(N, nrun), &a));
     double *dw = a.take(N), *dY = a.take(N), *dX = a.take((size_t)N * p), *dSiX = a.take((size_t)N * p);
-    double *dB = a.take((size_t)N * kb);           // right-hand sides   [PY | U...] then [U... | APY | PY]
-    double *dK = a.take((size_t)N * kb);           // K.[PY | U...]
-    double *dS = a.take((size_t)N * kb);           // Sigma^-1 [...]
-    double *dPr = a.take((size_t)N * kb);          // projected
-    double *dC = a.take(4096);
+    ai_scratch sc;
+    ai_scratch_take(&a, N, nrun, &sc);
     SGB_TRY(up(h, dw, w, N));
     SGB_TRY(up(h, dY, Y, N));
     SGB_TRY(up(h, dX, X, (size_t)N * p));
     SGB_TRY(up(h, dSiX, Sigma_iX, (size_t)N * p));
-    SGB_TRY(up(h, dB, Sigma_iY, N));               // dB[:,0] = Sigma_iY for now
+    SGB_TRY(up(h, sc.dB, Sigma_iY, N));            // dB[:,0] = Sigma_iY for now
+    return ai_score_core(h, quant, dw, dY, dX, dSiX, p, tau, cov_in, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, sc, out8, PY_out);
+}
+
+// The AI step on device-resident inputs (the host wrapper above uploads them; sgb_glmmkin_ai_pcg takes them from its Get_Coef)
+static int ai_score_core(sgb_ctx *h, bool quant, const double *dw, const double *dY, const double *dX, const double *dSiX, int p,
+                         const double *tau, const double *cov_in, int nrun, int maxiterPCG, double tolPCG, double traceCVcutoff,
+                         sgb_probe_fn probes, void *user, const ai_scratch &sc, double *out8, double *PY_out)
+{
+    const int64_t N = h->N;
+    const int kb = sc.kb;
+    double *dB = sc.dB, *dK = sc.dK, *dS = sc.dS, *dPr = sc.dPr, *dC = sc.dC;
+    SGB_RANGE("ai_score");
+    SGB_PROF(h, "AI step (getAIScore / fitglmmaiRPCG)");
     std::vector<double> covm(cov_in, cov_in + p * p);
     std::vector<int> pairs;
     std::vector<double> d;
@@ -617,29 +649,45 @@ static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *
     std::vector<double> C = matmul_pp(covm, p, d.data(), 1);
     SGB_TRY(up(h, dC, C.data(), p));
     SGB_TRY(k_project(h, dB, dSiX, p, dC, 1, dB));            // dB[:,0] = PY
-    SGB_TRY(down(h, PY_out, dB, N));
+    if (PY_out) SGB_TRY(down(h, PY_out, dB, N));
 
     std::vector<double> t1, t0;
     double YPAPY = 0, YPA0PY = 0, AI00 = 0, AI01 = 0, AI11 = 0;
     int nstart = 0, nend = nrun;
     std::vector<double> hostU;
     bool first = true;
+    int skipped_cols = 0;                          // first-batch columns taken from the resident copy instead of the callback
     while (true) {
         const int nu = nend - nstart;
-        hostU.resize((size_t)N * nu);
-        if (probes(user, N, nu, hostU.data())) return sgb_fail(h, "getAIScore: probe callback failed");
+        // sgb_set_probe_stream_fixed: the first batch is the same in every call (set_seed(200), FG.cpp:3114) -> resident copy
+        const bool resident = first && h->probe_stream_fixed && h->ku_cols == nu && h->d_ku;
+        if (!resident) {
+            if (skipped_cols) {                    // bring the callback's stream to where the reference's would be
+                hostU.resize((size_t)N * skipped_cols);
+                if (probes(user, N, skipped_cols, hostU.data())) return sgb_fail(h, "getAIScore: probe callback failed");
+                skipped_cols = 0;
+            }
+            hostU.resize((size_t)N * nu);
+            if (probes(user, N, nu, hostU.data())) return sgb_fail(h, "getAIScore: probe callback failed");
+        }
         if (first) {
             // ---- one (1+nu)-column product K.[PY | U] ----                        FG.cpp:3285, 3140
-            SGB_TRY(up(h, dB + N, hostU.data(), (size_t)N * nu));
+            if (resident) {
+                CUDA_OK(h, cudaMemcpyAsync(dB + N, h->d_ku, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
+                skipped_cols = nu;
+                h->cnt.n_probe_batches_resident++;
+            } else SGB_TRY(up(h, dB + N, hostU.data(), (size_t)N * nu));
             // K.U does not change between outer iterations (same probe stream): reuse it when U is bitwise the same
-            bool reuse = false;
-            if (h->ku_cols == nu && h->d_ku) {
+            bool reuse = resident;
+            if (!resident && h->ku_cols == nu && h->d_ku) {
                 int *d_cnt = h->d_idx + 8000, ndiff = 1;
                 SGB_TRY(k_count_diff(h, dB + N, h->d_ku, N * nu, d_cnt));
                 CUDA_OK(h, cudaMemcpyAsync(&ndiff, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
                 CUDA_OK(h, cudaStreamSynchronize(h->stream));
                 reuse = ndiff == 0;
             }
+            {
+            SGB_PROF(h, "K.[PY | U]");
             if (reuse) {
                 SGB_TRY(sgb_crossprod_device(h, dB, 1, dK, 0));
                 CUDA_OK(h, cudaMemcpyAsync(dK + N, h->d_ku + (size_t)N * nu, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
@@ -651,6 +699,7 @@ static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *
                 CUDA_OK(h, cudaMemcpyAsync(h->d_ku, dB + N, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
                 CUDA_OK(h, cudaMemcpyAsync(h->d_ku + (size_t)N * nu, dK + N, sizeof(double) * N * nu, cudaMemcpyDeviceToDevice, h->stream));
                 h->ku_cols = nu;
+            }
             }
             pairs.assign({0, 0});
             if (quant) { pairs.push_back(0); pairs.push_back(0); }
@@ -762,14 +811,9 @@ extern "C" int sgb_get_ai_score_q(sgb_ctx *h, const double *Y, const double *X, 
     return ai_score_impl(h, true, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, out8, PY);
 }
 
-// fitglmmaiRPCG (FG.cpp:3302-3341)
-extern "C" int sgb_fit_glmmai_rpcg(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, double *tau,
-                                   const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun, int maxiterPCG,
-                                   double tolPCG, double tol, double traceCVcutoff, sgb_probe_fn probes, void *user)
+// the tau update of fitglmmaiRPCG (FG.cpp:3321-3340) from o = {YPAPY, YPA0PY, Trace0, Trace1, AI00, AI01, AI11, nrun}
+static void tau_step_binary(const double *o, double *tau, double tol)
 {
-    std::vector<double> PY(h->N > 0 ? h->N : 1);
-    double o[8];
-    SGB_TRY(ai_score_impl(h, false, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, o, PY.data()));
     double score1 = o[0] - o[3], AI1 = o[6];
     double Dtau = score1 / AI1;
     double tau0[2] = {tau[0], tau[1]};
@@ -778,6 +822,38 @@ extern "C" int sgb_fit_glmmai_rpcg(sgb_ctx *h, const double *Y, const double *X,
     double step = 1.0;
     while (tau[1] < 0.0) { step *= 0.5; tau[1] = tau0[1] + step * Dtau; }
     for (int i = 0; i < 2; i++) if (tau[i] < tol) tau[i] = 0;
+}
+
+// the tau update of fitglmmaiRPCG_q (FG.cpp:3634-3661); zero[i] = tau[i] < tol before the AI step; false: singular AI matrix
+static bool tau_step_q(const double *o, const bool *zero, double *tau, double tol)
+{
+    double s0 = o[1] - o[2], s1 = o[0] - o[3];
+    double a00 = o[4], a01 = o[5], a11 = o[6];
+    double det = a00 * a11 - a01 * a01;
+    if (det == 0.0 || !std::isfinite(det)) return false;
+    double D0 = (a11 * s0 - a01 * s1) / det, D1 = (-a01 * s0 + a00 * s1) / det;     // solve(AI, score)
+    double tau0[2] = {tau[0], tau[1]};
+    tau[0] = tau0[0] + D0; tau[1] = tau0[1] + D1;
+    for (int i = 0; i < 2; i++) if (zero[i] && tau[i] < tol) tau[i] = 0;
+    double step = 1.0;
+    while (tau[0] < 0.0 || tau[1] < 0.0) {
+        step *= 0.5;
+        tau[0] = tau0[0] + step * D0; tau[1] = tau0[1] + step * D1;
+        for (int i = 0; i < 2; i++) if (zero[i] && tau[i] < tol) tau[i] = 0;
+    }
+    for (int i = 0; i < 2; i++) if (tau[i] < tol) tau[i] = 0;
+    return true;
+}
+
+// fitglmmaiRPCG (FG.cpp:3302-3341)
+extern "C" int sgb_fit_glmmai_rpcg(sgb_ctx *h, const double *Y, const double *X, int p, const double *w, double *tau,
+                                   const double *Sigma_iY, const double *Sigma_iX, const double *cov, int nrun, int maxiterPCG,
+                                   double tolPCG, double tol, double traceCVcutoff, sgb_probe_fn probes, void *user)
+{
+    std::vector<double> PY(h->N > 0 ? h->N : 1);
+    double o[8];
+    SGB_TRY(ai_score_impl(h, false, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, o, PY.data()));
+    tau_step_binary(o, tau, tol);
     return 0;
 }
 
@@ -790,21 +866,389 @@ extern "C" int sgb_fit_glmmai_rpcg_q(sgb_ctx *h, const double *Y, const double *
     double o[8];
     bool zero[2] = {tau[0] < tol, tau[1] < tol};
     SGB_TRY(ai_score_impl(h, true, Y, X, p, w, tau, Sigma_iY, Sigma_iX, cov, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, o, PY.data()));
-    double s0 = o[1] - o[2], s1 = o[0] - o[3];
-    double a00 = o[4], a01 = o[5], a11 = o[6];
-    double det = a00 * a11 - a01 * a01;
-    if (det == 0.0 || !std::isfinite(det)) return sgb_fail(h, "fitglmmaiRPCG_q: singular AI matrix");
-    double D0 = (a11 * s0 - a01 * s1) / det, D1 = (-a01 * s0 + a00 * s1) / det;     // solve(AI, score)
-    double tau0[2] = {tau[0], tau[1]};
-    tau[0] = tau0[0] + D0; tau[1] = tau0[1] + D1;
-    for (int i = 0; i < 2; i++) if (zero[i] && tau[i] < tol) tau[i] = 0;
-    double step = 1.0;
-    while (tau[0] < 0.0 || tau[1] < 0.0) {
-        step *= 0.5;
-        tau[0] = tau0[0] + step * D0; tau[1] = tau0[1] + step * D1;
-        for (int i = 0; i < 2; i++) if (zero[i] && tau[i] < tol) tau[i] = 0;
+    if (!tau_step_q(o, zero, tau, tol)) return sgb_fail(h, "fitglmmaiRPCG_q: singular AI matrix");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI: driver loops of SAIGE_fitGLMM_fast.R with the N-vectors resident on the device
+// ---------------------------------------------------------------------------------------------------
+// device state of one Get_Coef loop: w = W, YX = [Y | X], S = Sigma^-1 [Y | X], eta (offset included), mu, y, offset
+struct coef_dev { double *w, *YX, *S, *eta, *mu, *y, *off, *al; };
+
+static int coef_dev_take(sgb_ctx *h, int p, size_t extra, arena *a, coef_dev *s)
+{
+    const int64_t N = h->N;
+    SGB_TRY(arena_begin(h, (size_t)N * (2 * (1 + p) + 5) + 64 + extra, a));
+    s->w = a->take(N); s->YX = a->take((size_t)N * (1 + p)); s->S = a->take((size_t)N * (1 + p));
+    s->eta = a->take(N); s->mu = a->take(N); s->y = a->take(N); s->off = a->take(N); s->al = a->take(64);
+    return 0;
+}
+
+// Get_Coef (FG.R:2-35) on device state: s.eta holds eta0 on entry and the final eta on return; alpha0 is updated to the
+// last alpha that entered a convergence test, as the R loop leaves it
+static int get_coef_device(sgb_ctx *h, int family, const coef_dev &s, int p, const double *tau, std::vector<double> &alpha0,
+                           int maxiter, int maxiterPCG, double tolPCG, int loco, std::vector<double> &covm,
+                           std::vector<double> &al, int32_t *n_iter)
+{
+    const int64_t N = h->N;
+    const double tol_coef = 0.1;
+    SGB_RANGE("get_coef");
+    SGB_PROF(h, loco ? "Get_Coef_LOCO" : "Get_Coef");
+    SGB_TRY(k_irls_update(h, family, s.eta, 0, s.y, s.off, s.eta, s.mu, s.YX, s.w));
+    std::vector<int> pairs;
+    for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) { pairs.push_back(1 + i); pairs.push_back(1 + j); }   // X_i . SiX_j
+    for (int i = 0; i < p; i++) { pairs.push_back(0); pairs.push_back(1 + i); }                                   // Y . SiX_i
+    std::vector<double> d(pairs.size() / 2);
+    int it = 0;
+    while (it < maxiter) {
+        it++;
+        // getCoefficients (FG.cpp:3160-3200): Sigma^-1 [Y | X] as one (1+p)-column solve
+        SGB_TRY(sgb_pcg_device(h, s.w, tau, s.YX, 1 + p, maxiterPCG, tolPCG, loco, s.S, nullptr));
+        SGB_TRY(dots_to_host(h, s.YX, s.S, pairs, d.data()));
+        covm.assign(d.begin(), d.begin() + p * p);
+        inv_sympd_or_pinv(covm, p);
+        al = matmul_pp(covm, p, d.data() + p * p, 1);
+        SGB_TRY(up(h, s.al, al.data(), p));
+        SGB_TRY(k_eta(h, s.YX, s.S, s.S + N, p, s.al, s.w, tau[0], s.eta));                 // re.coef$eta
+        SGB_TRY(k_irls_update(h, family, s.eta, 1, s.y, s.off, s.eta, s.mu, s.YX, s.w));    // eta + offset, mu, Y, W
+        double worst = 0.0;
+        for (int i = 0; i < p; i++) worst = std::max(worst, fabs(al[i] - alpha0[i]) / (fabs(al[i]) + fabs(alpha0[i]) + tol_coef));
+        if (worst < tol_coef) break;
+        alpha0 = al;
     }
-    for (int i = 0; i < 2; i++) if (tau[i] < tol) tau[i] = 0;
+    if (n_iter) *n_iter = it;
+    return 0;
+}
+
+static int coef_args_ok(sgb_ctx *h, int family, int p, int maxiter)
+{
+    if (family != 0 && family != 1) return sgb_fail(h, "Get_Coef: family %d (0 = binomial, 1 = gaussian)", family);
+    if (p < 1 || p > 30) return sgb_fail(h, "Get_Coef: p=%d out of range [1,30]", p);
+    if (maxiter < 1) return sgb_fail(h, "Get_Coef: maxiter must be >= 1");
+    return 0;
+}
+
+extern "C" int sgb_get_coef(sgb_ctx *h, int family, const double *y, const double *X, int p, const double *offset, const double *tau,
+                            const double *alpha0, const double *eta0, int maxiter, int maxiterPCG, double tolPCG, int loco,
+                            double *Y, double *alpha, double *eta, double *W, double *cov, double *Sigma_iY, double *Sigma_iX,
+                            double *mu, int32_t *n_iter)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    SGB_TRY(coef_args_ok(h, family, p, maxiter));
+    const int64_t N = h->N;
+    arena a; coef_dev s;
+    SGB_TRY(coef_dev_take(h, p, 0, &a, &s));
+    SGB_TRY(up(h, s.y, y, N));
+    SGB_TRY(up(h, s.off, offset, N));
+    SGB_TRY(up(h, s.eta, eta0, N));
+    SGB_TRY(up(h, s.YX + N, X, (size_t)N * p));
+    std::vector<double> a0(alpha0, alpha0 + p), covm, al;
+    SGB_TRY(get_coef_device(h, family, s, p, tau, a0, maxiter, maxiterPCG, tolPCG, loco, covm, al, n_iter));
+    if (Y) SGB_TRY(down(h, Y, s.YX, N));
+    if (eta) SGB_TRY(down(h, eta, s.eta, N));
+    if (W) SGB_TRY(down(h, W, s.w, N));
+    if (mu) SGB_TRY(down(h, mu, s.mu, N));
+    if (Sigma_iY) SGB_TRY(down(h, Sigma_iY, s.S, N));
+    if (Sigma_iX) SGB_TRY(down(h, Sigma_iX, s.S + N, (size_t)N * p));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    memcpy(cov, covm.data(), sizeof(double) * p * p);
+    memcpy(alpha, al.data(), sizeof(double) * p);
+    return 0;
+}
+
+extern "C" int sgb_get_coef_loco_all(sgb_ctx *h, int family, const double *y, const double *X, int p, const double *offset,
+                                     const double *tau, const double *alpha0, const double *eta0, int maxiter, int maxiterPCG,
+                                     double tolPCG, double *Y, double *alpha, double *eta, double *cov, double *mu, int32_t *n_iter,
+                                     sgb_chrom_done_fn on_chrom, void *chrom_user)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    SGB_TRY(coef_args_ok(h, family, p, maxiter));
+    if (!h->diag_loco_ready) return sgb_fail(h, "LOCO refits requested before set_Diagof_StdGeno_LOCO");
+    const int64_t N = h->N;
+    const int nchr = (int)h->startVec.size();
+    arena a; coef_dev s;
+    SGB_TRY(coef_dev_take(h, p, 0, &a, &s));
+    SGB_TRY(up(h, s.y, y, N));
+    SGB_TRY(up(h, s.off, offset, N));
+    SGB_TRY(up(h, s.eta, eta0, N));
+    SGB_TRY(up(h, s.YX + N, X, (size_t)N * p));
+    std::vector<double> a0(alpha0, alpha0 + p), covm, al;
+    for (int c = 0; c < nchr; c++) {
+        if (h->startVec[c] == -1 || h->endVec[c] == -1) continue;
+        SGB_TRY(sgb_set_start_end_index(h, h->startVec[c], h->endVec[c], c));
+        int32_t it = 0;
+        // chromosome c starts from chromosome c-1's (alpha, eta): FG.R:265, 272-273
+        SGB_TRY(get_coef_device(h, family, s, p, tau, a0, maxiter, maxiterPCG, tolPCG, 1, covm, al, &it));
+        a0 = al;
+        SGB_TRY(down(h, Y + (size_t)c * N, s.YX, N));
+        SGB_TRY(down(h, eta + (size_t)c * N, s.eta, N));
+        SGB_TRY(down(h, mu + (size_t)c * N, s.mu, N));
+        memcpy(cov + (size_t)c * p * p, covm.data(), sizeof(double) * p * p);
+        memcpy(alpha + (size_t)c * p, al.data(), sizeof(double) * p);
+        if (n_iter) n_iter[c] = it;
+        if (on_chrom) {
+            CUDA_OK(h, cudaStreamSynchronize(h->stream));
+            on_chrom(chrom_user, c);
+        }
+    }
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549) as one call: every Get_Coef, the AI steps and
+// (LOCO) the leave-one-chromosome-out refits on one device-resident state; the host sees tau, alpha, cov and the trace scalars.
+extern "C" int sgb_glmmkin_ai_pcg(sgb_ctx *h, int quantitative, const double *y, const double *X, int p, const double *offset,
+                                  const double *alpha_fit0, const double *eta_fit0, const double *tauInit, int maxiter, double tol,
+                                  int nrun, double tolPCG, int maxiterPCG, double traceCVcutoff, int loco, sgb_probe_fn probes,
+                                  void *user, double *tau_out, double *alpha, double *eta, double *mu, double *Yout, double *cov,
+                                  int32_t *converged, int32_t *n_outer, double *Y_loco, double *alpha_loco, double *eta_loco,
+                                  double *cov_loco, double *mu_loco, int32_t *n_iter_loco, sgb_chrom_done_fn on_chrom, void *chrom_user)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    const bool quant = quantitative != 0;
+    const int family = quant ? 1 : 0;
+    SGB_TRY(coef_args_ok(h, family, p, maxiter));
+    if (nrun < 2 || nrun > 500) return sgb_fail(h, "glmmkin.ai_PCG: nrun=%d out of range [2,500]", nrun);
+    if (!probes) return sgb_fail(h, "glmmkin.ai_PCG: probe callback is NULL (probes are drawn by the caller's RNG)");
+    if (loco && !(Y_loco && alpha_loco && eta_loco && cov_loco && mu_loco)) return sgb_fail(h, "glmmkin.ai_PCG: LOCO outputs are NULL");
+    const int64_t N = h->N;
+    SGB_RANGE("glmmkin_ai_pcg");
+    arena a; coef_dev s;
+    SGB_TRY(coef_dev_take(h, p, (size_t)N + ai_scratch_elems(N, nrun), &a, &s));
+    double *d_eta_loop = a.take(N);                 // the R loop's `eta`: fit0's until the first iteration ends (FG.R:139, 179, 196)
+    ai_scratch sc;
+    ai_scratch_take(&a, N, nrun, &sc);
+    SGB_TRY(up(h, s.y, y, N));
+    SGB_TRY(up(h, s.off, offset, N));
+    SGB_TRY(up(h, d_eta_loop, eta_fit0, N));
+    SGB_TRY(up(h, s.YX + N, X, (size_t)N * p));
+    double tau[2] = {0.0, 0.0};
+    if (!quant) { tau[0] = 1.0; tau[1] = tauInit[1] == 0.0 ? 0.1 : tauInit[1]; }                  // FG.R:145-156
+    else if (tauInit[0] + tauInit[1] == 0.0) { tau[0] = 1.0; tau[1] = 0.0; }                        // FG.R:375-381
+    else { tau[0] = tauInit[0]; tau[1] = tauInit[1]; }
+    double tau0[2] = {tau[0], tau[1]};
+    std::vector<double> a0(alpha_fit0, alpha_fit0 + p), covm, al, al_loop(alpha_fit0, alpha_fit0 + p);
+    double o[8];
+    auto coef = [&](const std::vector<double> &start) -> int {      // Get_Coef from (start, the loop's eta)
+        a0 = start;
+        CUDA_OK(h, cudaMemcpyAsync(s.eta, d_eta_loop, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
+        return get_coef_device(h, family, s, p, tau, a0, maxiter, maxiterPCG, tolPCG, 0, covm, al, nullptr);
+    };
+    auto ai = [&]() -> int {                                         // the AI step on the state Get_Coef left
+        CUDA_OK(h, cudaMemcpyAsync(sc.dB, s.S, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
+        return ai_score_core(h, quant, s.w, s.YX, s.YX + N, s.S + N, p, tau, covm.data(), nrun, maxiterPCG, tolPCG, traceCVcutoff,
+                             probes, user, sc, o, nullptr);
+    };
+    SGB_TRY(coef(al_loop));
+    SGB_TRY(ai());
+    tau[1] = std::max(0.0, tau0[1] + tau0[1] * tau0[1] * (o[0] - o[3]) / (double)N);                // FG.R:163, 388-389
+    if (quant) tau[0] = std::max(0.0, tau0[0] + tau0[0] * tau0[0] * (o[1] - o[2]) / (double)N);
+    if (!quant) al_loop = al;                       // binary: alpha0 = re.coef$alpha; quantitative keeps fit0's until the loop sets it
+    int i = 0;
+    for (i = 1; i <= maxiter; i++) {
+        tau0[0] = tau[0]; tau0[1] = tau[1];
+        SGB_TRY(coef(al_loop));
+        bool zero[2] = {tau[0] < tol, tau[1] < tol};
+        SGB_TRY(ai());
+        if (!quant) tau_step_binary(o, tau, tol);
+        else if (!tau_step_q(o, zero, tau, tol)) return sgb_fail(h, "fitglmmaiRPCG_q: singular AI matrix");
+        al_loop = al;                                                                                // alpha = re.coef$alpha
+        CUDA_OK(h, cudaMemcpyAsync(d_eta_loop, s.eta, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));   // eta = re.coef$eta
+        if (quant && tau[0] <= 0.0) return sgb_fail(h, "ERROR! The first variance component parameter estimate is 0");
+        if ((!quant && tau[1] == 0.0) || (quant && tau[1] <= 0.0)) break;
+        double worst = 0.0;
+        for (int q = 0; q < 2; q++) worst = std::max(worst, fabs(tau[q] - tau0[q]) / (fabs(tau[q]) + fabs(tau0[q]) + tol));
+        if (worst < tol) break;
+        if (std::max(tau[0], tau[1]) > 1.0 / (tol * tol)) { i = maxiter; break; }
+    }
+    if (i > maxiter) i = maxiter;                   // seq_len(maxiter) ran out: R leaves i == maxiter
+    SGB_TRY(coef(al_loop));                         // FG.R:206
+    SGB_TRY(down(h, Yout, s.YX, N));
+    SGB_TRY(down(h, eta, s.eta, N));
+    SGB_TRY(down(h, mu, s.mu, N));
+    memcpy(cov, covm.data(), sizeof(double) * p * p);
+    memcpy(alpha, al.data(), sizeof(double) * p);
+    tau_out[0] = tau[0]; tau_out[1] = tau[1];
+    if (converged) *converged = i < maxiter;
+    if (n_outer) *n_outer = i;
+    if (on_chrom) {
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        on_chrom(chrom_user, -1);
+    }
+    if (loco) {
+        // FG.R:255-292: set_Diagof_StdGeno_LOCO, then every chromosome from the previous one's (alpha, eta), starting at the fit's
+        SGB_TRY(sgb_diag_loco_device(h));
+        a0 = al;
+        const int nchr = (int)h->startVec.size();
+        for (int c = 0; c < nchr; c++) {
+            if (h->startVec[c] == -1 || h->endVec[c] == -1) continue;
+            SGB_TRY(sgb_set_start_end_index(h, h->startVec[c], h->endVec[c], c));
+            int32_t it = 0;
+            SGB_TRY(get_coef_device(h, family, s, p, tau, a0, maxiter, maxiterPCG, tolPCG, 1, covm, al, &it));
+            a0 = al;
+            SGB_TRY(down(h, Y_loco + (size_t)c * N, s.YX, N));
+            SGB_TRY(down(h, eta_loco + (size_t)c * N, s.eta, N));
+            SGB_TRY(down(h, mu_loco + (size_t)c * N, s.mu, N));
+            memcpy(cov_loco + (size_t)c * p * p, covm.data(), sizeof(double) * p * p);
+            memcpy(alpha_loco + (size_t)c * p, al.data(), sizeof(double) * p);
+            if (n_iter_loco) n_iter_loco[c] = it;
+            if (on_chrom) {
+                CUDA_OK(h, cudaStreamSynchronize(h->stream));
+                on_chrom(chrom_user, c);
+            }
+        }
+    }
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int sgb_set_probe_stream_fixed(sgb_ctx *h, int on)
+{
+    h->probe_stream_fixed = on ? 1 : 0;
+    return 0;
+}
+
+// A x = b for `nrhs` right-hand sides by Gaussian elimination with partial pivoting (R's solve(); p <= 30).  A, B column-major.
+static bool solve_pp(std::vector<double> A, int p, std::vector<double> &B, int nrhs)
+{
+    for (int c = 0; c < p; c++) {
+        int piv = c;
+        for (int r = c + 1; r < p; r++) if (fabs(A[r + c * p]) > fabs(A[piv + c * p])) piv = r;
+        if (A[piv + c * p] == 0.0) return false;
+        if (piv != c) {
+            for (int q = 0; q < p; q++) std::swap(A[c + q * p], A[piv + q * p]);
+            for (int j = 0; j < nrhs; j++) std::swap(B[c + (size_t)j * p], B[piv + (size_t)j * p]);
+        }
+        for (int r = c + 1; r < p; r++) {
+            const double f = A[r + c * p] / A[c + c * p];
+            if (f == 0.0) continue;
+            for (int q = c; q < p; q++) A[r + q * p] -= f * A[c + q * p];
+            for (int j = 0; j < nrhs; j++) B[r + (size_t)j * p] -= f * B[c + (size_t)j * p];
+        }
+    }
+    for (int j = 0; j < nrhs; j++)
+        for (int r = p - 1; r >= 0; r--) {
+            double v = B[r + (size_t)j * p];
+            for (int q = r + 1; q < p; q++) v -= A[r + q * p] * B[q + (size_t)j * p];
+            B[r + (size_t)j * p] = v / A[r + r * p];
+        }
+    return true;
+}
+
+static int dots_chunked(sgb_ctx *h, const double *A, const double *B, const std::vector<int> &pairs, double *out)
+{
+    const size_t np = pairs.size() / 2;
+    for (size_t o = 0; o < np; o += 2048) {
+        const size_t n = std::min<size_t>(2048, np - o);
+        std::vector<int> part(pairs.begin() + 2 * o, pairs.begin() + 2 * (o + n));
+        SGB_TRY(dots_to_host(h, A, B, part, out + o));
+    }
+    return 0;
+}
+
+extern "C" int sgb_variance_ratio_markers(sgb_ctx *h, const int64_t *marker_idx, int nmark, int from_vr_store, const double *w,
+                                          const double *tau, const double *X, int p, const double *XV, const double *XXVX_inv,
+                                          const double *Sigma_iX, const double *mu2, int maxiterPCG, double tolPCG, double *var1,
+                                          double *var2null, double *AC)
+{
+    NEED_LOADED(h);
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (p < 1 || p > 30) return sgb_fail(h, "variance ratio: p=%d out of range [1,30]", p);
+    if (nmark < 1 || nmark > 128) return sgb_fail(h, "variance ratio: %d markers per call (1..128)", nmark);
+    const int64_t N = h->N, Bv = (N + 3) / 4;
+    const int64_t Mstore = from_vr_store ? h->Mvr : h->M;
+    for (int j = 0; j < nmark; j++)
+        if (marker_idx[j] < 0 || marker_idx[j] >= Mstore)
+            return sgb_fail(h, "variance ratio: marker index %lld out of range [0,%lld)", (long long)marker_idx[j], (long long)Mstore);
+    SGB_RANGE("variance_ratio_markers");
+    arena a;
+    SGB_TRY(arena_begin(h, (size_t)N * (2 + 4 * p + 3 * (size_t)nmark) + 4096, &a));
+    double *dw = a.take(N), *dmu2 = a.take(N), *dX = a.take((size_t)N * p), *dXVt = a.take((size_t)N * p);
+    double *dXX = a.take((size_t)N * p), *dSiX = a.take((size_t)N * p);
+    double *dG = a.take((size_t)N * nmark), *dSiG = a.take((size_t)N * nmark), *dT = a.take((size_t)N * nmark), *dC = a.take(4096);
+    SGB_TRY(up(h, dw, w, N));
+    if (mu2) SGB_TRY(up(h, dmu2, mu2, N));
+    SGB_TRY(up(h, dX, X, (size_t)N * p));
+    SGB_TRY(up(h, dXX, XXVX_inv, (size_t)N * p));
+    SGB_TRY(up(h, dSiX, Sigma_iX, (size_t)N * p));
+    {   // XV is p x N (R's layout): its transpose is the N x p operand of the dot products
+        std::vector<double> t((size_t)N * p);
+        for (int64_t i = 0; i < N; i++) for (int q = 0; q < p; q++) t[(size_t)q * N + i] = XV[(size_t)i * p + q];
+        SGB_TRY(up(h, dXVt, t.data(), (size_t)N * p));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
+    // ---- G0: the markers' genotype columns (Get_OneSNP_Geno[_forVarRatio], FG.R:2305-2309) ----
+    int64_t *d_rows = reinterpret_cast<int64_t *>(h->d_idx);
+    std::vector<int64_t> rows(nmark);
+    // workspace: the packed hold-out rows first, then the partial sums of the column sums / dot products
+    SGB_TRY(sgb_ensure(h, &h->ws, &h->ws_bytes, std::max((size_t)nmark * Bv, (size_t)2048 * SGB_PART_BLOCKS * sizeof(double))));
+    if (from_vr_store) {
+        for (int j = 0; j < nmark; j++) {
+            CUDA_OK(h, cudaMemcpyAsync((uint8_t *)h->ws + (size_t)j * Bv, h->vr_packed.data() + (size_t)marker_idx[j] * Bv, (size_t)Bv,
+                                       cudaMemcpyHostToDevice, h->stream));
+            rows[j] = j;
+        }
+        CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int64_t) * nmark, cudaMemcpyHostToDevice, h->stream));
+        SGB_TRY(k_decode_marker_cols(h, (const uint8_t *)h->ws, 0, Bv, d_rows, nmark, dG));
+    } else {
+        for (int j = 0; j < nmark; j++) {
+            rows[j] = -1;
+            if (sgb_owner_of(h, marker_idx[j]) == h->rank)
+                rows[j] = std::lower_bound(h->loc2glob.begin(), h->loc2glob.end(), marker_idx[j]) - h->loc2glob.begin();
+        }
+        CUDA_OK(h, cudaMemcpyAsync(d_rows, rows.data(), sizeof(int64_t) * nmark, cudaMemcpyHostToDevice, h->stream));
+        SGB_TRY(k_decode_marker_cols(h, h->dG, 1, h->sG, d_rows, nmark, dG));
+        if (h->world > 1) SGB_TRY(sgb_allreduce_sum(h, dG, N * nmark));      // the owner's column + zeros
+    }
+    // ---- flip to the minor allele, AC (FG.R:2318-2322) ----
+    std::vector<double> sums(nmark);
+    SGB_TRY(k_colsum(h, dG, N, N, nmark, h->d_scal + SC_COLSUM));
+    CUDA_OK(h, cudaMemcpyAsync(h->h_scal, h->d_scal + SC_COLSUM, sizeof(double) * nmark, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    std::vector<int> flip(nmark);
+    for (int j = 0; j < nmark; j++) {
+        sums[j] = h->h_scal[j];
+        flip[j] = sums[j] / (double)(2 * N) > 0.5;
+        AC[j] = flip[j] ? (double)(2 * N) - sums[j] : sums[j];
+    }
+    CUDA_OK(h, cudaMemcpyAsync(h->d_idx, flip.data(), sizeof(int) * nmark, cudaMemcpyHostToDevice, h->stream));
+    SGB_TRY(k_flip_cols(h, dG, h->d_idx, nmark));
+    // ---- G = G0 - XXVX_inv (XV G0)  (FG.R:2333) ----
+    std::vector<int> pairs;
+    for (int j = 0; j < nmark; j++) for (int q = 0; q < p; q++) { pairs.push_back(q); pairs.push_back(j); }
+    std::vector<double> c((size_t)p * nmark);
+    SGB_TRY(dots_chunked(h, dXVt, dG, pairs, c.data()));
+    SGB_TRY(up(h, dC, c.data(), (size_t)p * nmark));
+    SGB_TRY(k_project(h, dG, dXX, p, dC, nmark, dG));
+    // ---- Sigma^-1 G: one nmark-column solve (getSigma_G per marker in the reference, FG.R:2341) ----
+    SGB_TRY(sgb_pcg_device(h, dw, tau, dG, nmark, maxiterPCG, tolPCG, 0, dSiG, nullptr));
+    // ---- var1, var2null (FG.R:2344-2345, 2367-2371) ----
+    std::vector<double> gsg(nmark), gsx((size_t)p * nmark), xsg((size_t)p * nmark), xsx((size_t)p * p), v2(nmark);
+    pairs.clear();
+    for (int j = 0; j < nmark; j++) { pairs.push_back(j); pairs.push_back(j); }
+    SGB_TRY(dots_chunked(h, dG, dSiG, pairs, gsg.data()));                   // G_j . Sigma_iG_j
+    if (mu2) {
+        SGB_TRY(k_rowscale_cols(h, dmu2, dG, nmark, dT));
+        SGB_TRY(dots_chunked(h, dT, dG, pairs, v2.data()));                  // sum mu2 G_j^2
+    } else SGB_TRY(dots_chunked(h, dG, dG, pairs, v2.data()));
+    pairs.clear();
+    for (int j = 0; j < nmark; j++) for (int q = 0; q < p; q++) { pairs.push_back(q); pairs.push_back(j); }
+    SGB_TRY(dots_chunked(h, dSiX, dG, pairs, gsx.data()));                   // Sigma_iX_q . G_j
+    SGB_TRY(dots_chunked(h, dX, dSiG, pairs, xsg.data()));                   // X_q . Sigma_iG_j
+    pairs.clear();
+    for (int r = 0; r < p; r++) for (int q = 0; q < p; q++) { pairs.push_back(q); pairs.push_back(r); }
+    SGB_TRY(dots_chunked(h, dX, dSiX, pairs, xsx.data()));                   // (X' Sigma_iX)[q, r]
+    if (!solve_pp(xsx, p, xsg, nmark)) return sgb_fail(h, "variance ratio: t(X) Sigma_iX is singular");
+    for (int j = 0; j < nmark; j++) {
+        double corr = 0.0;
+        for (int q = 0; q < p; q++) corr += gsx[q + (size_t)j * p] * xsg[q + (size_t)j * p];
+        var1[j] = (gsg[j] - corr) / AC[j];
+        var2null[j] = v2[j] / AC[j];
+    }
     return 0;
 }
 

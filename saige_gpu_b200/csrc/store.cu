@@ -9,7 +9,9 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <algorithm>
 #include <fstream>
@@ -32,6 +34,33 @@ int sgb_fail(sgb_ctx *h, const char *fmt, ...)
 }
 
 extern "C" const char *sgb_last_error(sgb_ctx *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static bool sgb_prof_enabled()
+{
+    static const bool on = getenv("SGB_PROFILE") && atoi(getenv("SGB_PROFILE")) > 0;
+    return on;
+}
+static int g_prof_depth = 0;
+static double prof_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+sgb_prof_scope::sgb_prof_scope(sgb_ctx *h_, const char *name_) : h(h_), name(name_), t0(0.0), on(sgb_prof_enabled())
+{
+    if (!on) return;
+    cudaStreamSynchronize(h->stream);
+    g_prof_depth++;
+    t0 = prof_now();
+}
+sgb_prof_scope::~sgb_prof_scope()
+{
+    if (!on) return;
+    cudaStreamSynchronize(h->stream);
+    g_prof_depth--;
+    fprintf(stderr, "[sgb] %*s%s: %.3f ms\n", 2 * g_prof_depth, "", name, prof_now() - t0);
+}
 
 int sgb_ensure(sgb_ctx *h, void **p, size_t *cur, size_t need)
 {

@@ -162,7 +162,10 @@ class ProbeStream:
         return draw
 
 
-def Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, loco=False):
+def Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, loco=False, native=False):
+    """FG.R:2-35 (loco: 42-73).  native=True: the same loop inside the library (sgb_get_coef), N-vectors device resident."""
+    if native:
+        return geno.Get_Coef(y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, loco=loco)
     tol_coef = 0.1
     mu = family.linkinv(eta0)
     me = family.mu_eta(eta0)
@@ -186,8 +189,17 @@ def Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, 
 
 
 def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxiter=20, tol=0.02, nrun=30,
-                   tolPCG=1e-5, maxiterPCG=500, traceCVcutoff=0.0025, LOCO=False, verbose=False, timings=None):
-    """glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549)."""
+                   tolPCG=1e-5, maxiterPCG=500, traceCVcutoff=0.0025, LOCO=False, verbose=False, timings=None, native_loops=False):
+    """glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549).
+    native_loops=True: Get_Coef, the LOCO refit loop and the first probe batch run inside the library (sgb_get_coef,
+    sgb_get_coef_loco_all, sgb_set_probe_stream_fixed) instead of in this mirror of the R code; same results (the IRLS
+    update uses the device's exp instead of numpy's: differences at the 1e-15 level).  native_loops=True runs the whole function
+    as ONE library call (sgb_glmmkin_ai_pcg), native_loops="calls" keeps this loop and calls the library once per R loop."""
+    nat = dict(native=True) if native_loops else {}
+    geno.setProbeStreamFixed(bool(native_loops))
+    if native_loops is True:
+        return _glmmkin_ai_PCG_one_call(geno, fit0, probes, trait, tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG, traceCVcutoff, LOCO,
+                                        verbose, timings)
     y, X, offset, family = fit0["y"], fit0["X"], fit0["offset"], fit0["family"]
     X = np.asfortranarray(X, dtype=np.float64)      # column-major once: every ABI call takes it without another copy
     n = len(y)
@@ -205,7 +217,7 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
         tau[:] = tauInit
     tau0 = tau.copy()
     t0 = time.time()
-    rc = Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter)
+    rc = Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, **nat)
     if not quant:
         re = geno.getAIScore(rc["Y"], X, rc["W"], tau, rc["Sigma_iY"], rc["Sigma_iX"], rc["cov"], nrun, maxiterPCG, tolPCG,
                              traceCVcutoff, probes.fresh())
@@ -224,7 +236,7 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
         alpha0 = alpha if quant else rc["alpha"]
         tau0 = tau.copy()
         eta0 = eta
-        rc = Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter)
+        rc = Get_Coef(geno, y, X, tau, family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, **nat)
         fit = (geno.fitglmmaiRPCG_q if quant else geno.fitglmmaiRPCG)(
             rc["Y"], X, rc["W"], tau, rc["Sigma_iY"], rc["Sigma_iX"], rc["cov"], nrun, maxiterPCG, tolPCG, tol,
             traceCVcutoff, probes.fresh())
@@ -242,7 +254,7 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
         if np.max(tau) > tol ** (-2):
             i = maxiter
             break
-    rc = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter)
+    rc = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, **nat)
     alpha, eta, mu = rc["alpha"], rc["eta"], rc["mu"]
     mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau[0])
     out = dict(theta=tau, coefficients=alpha, linear_predictors=eta, fitted_values=mu, Y=rc["Y"], residuals=y - mu,
@@ -261,22 +273,73 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
         # several workers: at 8 GPUs a chromosome's solves take ~25 ms, about what one score-test matrix set costs on a host
         # core, so a single worker would become the critical path of the refit phase
         with ThreadPoolExecutor(max_workers=4) as pool:
+            early = {}
+
+            def on_chrom(c, rl_c):          # chromosome c is done: its score-test matrices start while the GPU refits c + 1
+                mu_c = rl_c["mu"]
+                early[c] = pool.submit(ScoreTest_NULL_Model, mu_c, mu_c * (1 - mu_c) if not quant else np.full(n, 1.0 / tau[0]), y, X)
+            allchr = (geno.Get_Coef_LOCO_all(y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, on_chrom=on_chrom)
+                      if native_loops else None)
             for j, (s, e) in enumerate(zip(geno_start_vec(geno), geno_end_vec(geno))):
                 if s == -1 or e == -1:
                     out["LOCOResult"].append(dict(isLOCO=False))
                     continue
-                geno.setStartEndIndex(s, e, j)
-                rl = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, loco=True)
+                if native_loops:
+                    rl = allchr[j]
+                else:
+                    geno.setStartEndIndex(s, e, j)
+                    rl = Get_Coef(geno, y, X, tau, family, alpha, eta, offset, maxiterPCG, tolPCG, maxiter, loco=True)
                 alpha, eta, mu = rl["alpha"], rl["eta"], rl["mu"]
                 mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau[0])
                 entry = dict(isLOCO=True, coefficients=alpha, linear_predictors=eta, fitted_values=mu,
                              Y=rl["Y"], residuals=y - mu, cov=rl["cov"])
-                pending.append((entry, pool.submit(ScoreTest_NULL_Model, mu, mu2, y, X)))
+                pending.append((entry, early[j] if native_loops else pool.submit(ScoreTest_NULL_Model, mu, mu2, y, X)))
                 out["LOCOResult"].append(entry)
             for entry, fut in pending:
                 entry["obj_noK"] = fut.result()
         if timings is not None:
             timings["loco_s"] = time.time() - t1
+    return out
+
+
+def _glmmkin_ai_PCG_one_call(geno, fit0, probes, trait, tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG, traceCVcutoff, LOCO, verbose,
+                             timings):
+    """glmmkin_ai_PCG through sgb_glmmkin_ai_pcg; what stays here is what the R function does after its loops: the result list and
+    the score-test matrices (ScoreTest_NULL_Model, FG.R:231-238, 283-288).  Those are started on host threads from the library's
+    per-chromosome callback, i.e. while the GPU already refits the next chromosome."""
+    y, X, offset = fit0["y"], np.asfortranarray(fit0["X"], dtype=np.float64), fit0["offset"]
+    quant = trait == "quantitative"
+    n = len(y)
+    t0 = time.time()
+    futures = {}
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        def on_chrom(c, r):
+            mu = r["fitted_values"] if c < 0 else r["mu"]
+            tau0 = r["theta"][0] if c < 0 else tau_box[0]
+            if c < 0:
+                tau_box[0] = float(r["theta"][0])
+            mu2 = mu * (1 - mu) if not quant else np.full(n, 1.0 / tau0)
+            futures[c] = pool.submit(ScoreTest_NULL_Model, mu, mu2, y, X)
+        tau_box = [1.0]
+        r = geno.glmmkin_ai_PCG(trait, y, X, offset, fit0["coef"], fit0["eta"], tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG,
+                                traceCVcutoff, LOCO, probes.fresh(), on_chrom=on_chrom)
+        tau, mu = r["theta"], r["fitted_values"]
+        if verbose:
+            print("Final", tau)
+        out = dict(theta=tau, coefficients=r["coefficients"], linear_predictors=r["linear_predictors"], fitted_values=mu, Y=r["Y"],
+                   residuals=y - mu, cov=r["cov"], converged=r["converged"], y=y, X=X, traitType=trait, LOCO=LOCO, offset=offset,
+                   n_outer=r["n_outer"], obj_noK=futures[-1].result())
+        if LOCO:
+            out["LOCOResult"] = []
+            for c, rl in enumerate(r["loco"]):
+                if rl is None:
+                    out["LOCOResult"].append(dict(isLOCO=False))
+                    continue
+                out["LOCOResult"].append(dict(isLOCO=True, coefficients=rl["alpha"], linear_predictors=rl["eta"], fitted_values=rl["mu"],
+                                              Y=rl["Y"], residuals=y - rl["mu"], cov=rl["cov"], obj_noK=futures[c].result()))
+    if timings is not None:
+        timings["fit_s"] = time.time() - t0
+        timings["loco_s"] = 0.0
     return out
 
 
@@ -296,7 +359,7 @@ def set_loco_ranges(geno, chr_of_qc_marker):
 
 
 def extractVarianceRatio(geno, model, family, marker_order, numMarkers=30, maxiterPCG=500, tolPCG=1e-5,
-                         ratioCVcutoff=0.001, batch=True):
+                         ratioCVcutoff=0.001, batch=True, native_loops=False):
     """FG.R:2152-2423 (one ratio).  `marker_order` = the caller's `sample(MACindex)` permutation (FG.R:2242).
     With batch=True the getSigma_G solves of a round (numMarkers, then +10 per CV retry) run as one multi-column
     PCG; results are identical to the sequential loop because each column follows its own recurrence."""
@@ -312,7 +375,15 @@ def extractVarianceRatio(geno, model, family, marker_order, numMarkers=30, maxit
     while True:
         take = marker_order[pos:pos + (target - len(ratios))]
         pos += len(take)
-        if len(take):
+        if len(take) and native_loops:
+            # the marker loop inside the library (sgb_variance_ratio_markers): genotype columns, covariate adjustment, the
+            # multi-column solve and the quadratic forms stay on the device
+            mu2 = mu * (1 - mu) if model["traitType"] == "binary" else None
+            for c0 in range(0, len(take), 128):
+                v1, v2, _ = geno.varianceRatioMarkers(take[c0:c0 + 128], use_vr, W, tau, X, noK["XV"], noK["XXVX_inv"], Sigma_iX,
+                                                      mu2, maxiterPCG, tolPCG)
+                ratios.extend((v1 / v2).tolist())
+        elif len(take):
             Gs, ACs = [], []
             for i in take:
                 G0 = (geno.Get_OneSNP_Geno_forVarRatio(i) if use_vr else geno.Get_OneSNP_Geno(i)).astype(np.float64)

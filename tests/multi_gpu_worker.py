@@ -54,6 +54,21 @@ probes = step1.ProbeStream(N0, 130, 200)
 mo = O.glmmkin_ai_PCG(o, O.glm_fit(y, Xc, O.Binomial), (0, 0), probes.U, trait="binary")
 mg = step1.glmmkin_ai_PCG(g, step1.glm_fit(y, Xc, step1.Binomial), probes, trait="binary")
 res["tau"] = rel(mg["theta"], mo["theta"]); res["alpha"] = rel(mg["coefficients"], mo["coefficients"])
+# the same fit with the R driver loops run inside the library (sgb_get_coef, sgb_get_coef_loco_all, resident probes) and the
+# 22 leave-one-chromosome-out refits; then the variance-ratio marker loop (genotype columns of markers other ranks own arrive by
+# an allreduce) -- against the mirror of the R loops on the same ranks and against the oracle
+mm = step1.glmmkin_ai_PCG(g, step1.glm_fit(y, Xc, step1.Binomial), probes, trait="binary", LOCO=True)
+mn = step1.glmmkin_ai_PCG(g, step1.glm_fit(y, Xc, step1.Binomial), probes, trait="binary", LOCO=True, native_loops=True)
+g.setProbeStreamFixed(False)
+native_same = max([rel(mn[k], mm[k]) for k in ("theta", "coefficients", "fitted_values")] +
+                  [rel(a[k], b[k]) for a, b in zip(mn["LOCOResult"], mm["LOCOResult"]) if a["isLOCO"] for k in ("coefficients", "fitted_values", "Y", "cov")])
+res["native_tau"] = rel(mn["theta"], mo["theta"]); res["native_alpha"] = rel(mn["coefficients"], mo["coefficients"])
+order = np.random.default_rng(1).permutation(o.M)[:200]
+vo, lo_ = O.extractVarianceRatio(o, mo, O.Binomial, order)
+vm, lm_ = step1.extractVarianceRatio(g, mg, step1.Binomial, order)
+vn, ln_ = step1.extractVarianceRatio(g, mg, step1.Binomial, order, native_loops=True)
+res["vr"] = rel(vm, vo); res["native_vr"] = rel(vn, vo)
+native_same = max(native_same, rel(ln_, lm_)) if len(ln_) == len(lm_) else 1.0
 # dense GRM: block-rows dealt over the ranks, every rank contracts over all marker shards (ncclBroadcast), products
 # from the stored matrix end in the same allreduce
 Z = np.stack([o.Get_OneSNP_StdGeno(m) for m in range(o.M)], axis=1)
@@ -136,12 +151,13 @@ if rank == 0:
         for k in a) for a, b in zip(cat, full))
     assert len(full) > 20
 
-pcg_keys = ("pcg", "tau", "alpha", "dense_pcg", "synth_pcg")
+pcg_keys = ("pcg", "tau", "alpha", "dense_pcg", "synth_pcg", "native_tau", "native_alpha", "vr", "native_vr")
 worst_mv = max(v for k, v in res.items() if k not in pcg_keys)
 ok = (worst_mv < 1e-10 and res["dense_pcg"] < 1e-6 and res["pcg"] < 1e-6 and res["tau"] < 1e-6 and res["alpha"] < 1e-6
-      and res["synth_pcg"] < 1e-6 and step2_ok and ingest_ok)
-print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e/%.2e tau %.2e alpha %.2e step2 %s ingest %s allreduces %d -> %s"
-      % (rank, world, g.Mloc, worst_mv, res["pcg"], res["synth_pcg"], res["tau"], res["alpha"], step2_ok, ingest_ok,
+      and res["synth_pcg"] < 1e-6 and step2_ok and ingest_ok and native_same < 1e-9
+      and max(res["native_tau"], res["native_alpha"], res["vr"], res["native_vr"]) < 1e-6)
+print("rank %d/%d Mloc=%d worst product err %.2e pcg %.2e/%.2e tau %.2e alpha %.2e native loops vs mirror %.2e vr %.2e step2 %s ingest %s allreduces %d -> %s"
+      % (rank, world, g.Mloc, worst_mv, res["pcg"], res["synth_pcg"], res["tau"], res["alpha"], native_same, res["native_vr"], step2_ok, ingest_ok,
          g.counters()["n_allreduce"], "OK" if ok else "FAIL"), flush=True)
 if not ok:
     print({k: v for k, v in res.items() if v > 1e-10}, flush=True)
