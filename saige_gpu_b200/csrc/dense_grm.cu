@@ -316,12 +316,18 @@ static void symv_launch(sgb_ctx *h, const sgb_dense *d, const double *B, int64_t
 //   part B   y[i][c]        += sum_n panel[i][n] b[128R + n][c]      A = panel rows (8 x 4 per MMA), B = b
 //   part A   y[128R + n][c] += sum_i b[i][c] panel[i][n]             A = b^T (8 columns x 4 rows), B = panel rows (4 x 8)
 // so the cross-lane reductions that bound the DFMA kernel at >= 4 columns (shuffle butterfly, 220-255 registers, one CTA of
-// 8 latency-bound warps per SM: 3.1 / 1.8 TB/s at 4 / 8 columns) are done by the MMA.  Each warp streams its own groups of
-// 8 panel rows (8 KB) through a private 3-stage shared-memory ring filled by cp.async.bulk (one 1 KB copy per row into a
-// row stride of 130 doubles: fragment loads are bank-conflict free for part B and 1.5-way for part A), 64 DMMAs per group.
+// 8 latency-bound warps per SM: 3.1 / 1.8 TB/s at 4 / 8 columns) are done by the MMA.
+// PERSISTENT WARPS: one CTA of 8 warps per SM; every warp owns whole items (<= 512 panel rows of one block-row), item
+// wid, wid + W, ... of the list, and streams their groups of 8 rows (8 KB) through a private 3-stage shared-memory ring filled by
+// cp.async.bulk (one 1 KB copy per row into a row stride of 130 doubles: fragment loads are bank-conflict free for part B and
+// 1.5-way for part A).  The ring runs ACROSS items -- the copies of the next item are in flight while the current one is consumed
+// -- and a warp never meets another one: part-B's operand b[128R + .] sits in 32 registers per lane for the whole item, part-A's
+// sums leave through 32 atomics per lane and item.  (The first version gave a 512-row item to one CTA, 8 groups per warp, and
+// met in shared memory at the end: 12 us of copy pipeline per CTA that the 10 us of DMMA work did not overlap -- 3.4 TB/s where the
+// copies alone ran at 6.4 and the MMAs alone at 7.4.)  64 DMMAs and 64 LDS.64 per lane and group.
 // ---------------------------------------------------------------------------------------------------
 #define DM_STAGES 3
-#define DM_RS 130               // doubles per staged panel row / per staged b column
+#define DM_RS 130               // doubles per staged panel row
 
 __device__ __forceinline__ uint32_t dm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
@@ -329,134 +335,129 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <bool PARTB>
 __global__ void __launch_bounds__(256, 1)
-dense_symm_mma_kernel(const double *__restrict__ pool, const dg_item *__restrict__ items, int64_t item0, const double *__restrict__ B, int kc,
-                      int64_t N, double *__restrict__ Y, int dbg_arg)
+dense_symm_mma_kernel(const double *__restrict__ pool, const dg_item *__restrict__ items, int64_t n_items, const double *__restrict__ B, int kc,
+                      int64_t N, double *__restrict__ Y)
 {
-#ifdef SGB_ABLATION          // timing experiments only (make ABLATION=1): 1 = no part-A MMAs, 2 = no part-B MMAs, 4 = no fragment loads at all
-    const int dbg = dbg_arg;
-#else
-    constexpr int dbg = 0;
-    (void)dbg_arg;
-#endif
     extern __shared__ __align__(128) double dm_smem[];
     __shared__ uint64_t full[8][DM_STAGES];
-    double *sbn = dm_smem;                                    // [8][DM_RS]: b over the block-row's own samples, columns >= kc zero
-    const dg_item it = items[item0 + blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
-    double *ring = dm_smem + 8 * DM_RS + (size_t)warp * (DM_STAGES * 8 * DM_RS);
-    for (int e = threadIdx.x; e < 8 * DG_BLOCK; e += 256) {
-        const int c = e >> 7, n = e & 127;
-        const int64_t j = (int64_t)it.R * DG_BLOCK + n;
-        sbn[c * DM_RS + n] = (c < kc && j < N) ? B[(int64_t)c * N + j] : 0.0;
-    }
+    double *ring = dm_smem + (size_t)warp * (DM_STAGES * 8 * DM_RS);
+    // neighbouring items (adjacent chunks of one panel) go to different SMs at the same time
+    const int64_t W = (int64_t)gridDim.x * 8, wid = (int64_t)warp * gridDim.x + blockIdx.x;
     if (lane == 0) {
         for (int s = 0; s < DM_STAGES; s++)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dm_smem_u32(&full[warp][s])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    __syncthreads();
-    const double *panel = pool + it.off + (int64_t)it.i0 * DG_BLOCK;        // first row of this chunk
-    const int ngroups = it.rows >> 3;                                       // groups of 8 rows; this warp takes g = warp, warp + 8, ...
-    const int mine = ngroups > warp ? (ngroups - warp + 7) >> 3 : 0;
-    auto issue = [&](int k) {                                                // lane 0: group k of this warp -> stage k % DM_STAGES
-        const int st = k % DM_STAGES;
+    __syncwarp();
+    // ---- producer cursor (lane 0): the next group of 8 rows to copy, running over this warp's items ----
+    int64_t ti = wid;
+    int gi = 0, ngi = 0;
+    const double *srci = nullptr;
+    auto open_item = [&]() {
+        if (ti < n_items) {
+            const dg_item t = items[ti];
+            ngi = t.rows >> 3; gi = 0;
+            srci = pool + t.off + (int64_t)t.i0 * DG_BLOCK;
+        }
+    };
+    auto issue = [&](int st) {
+        while (ti < n_items && gi >= ngi) { ti += W; open_item(); }
+        if (ti >= n_items) return;
         const uint32_t bar = dm_smem_u32(&full[warp][st]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8 * DG_BLOCK * 8) : "memory");
-        const double *src = panel + (int64_t)(warp + 8 * k) * 8 * DG_BLOCK;
+        const double *src = srci + (int64_t)gi * 8 * DG_BLOCK;
         double *dst = ring + (size_t)st * (8 * DM_RS);
 #pragma unroll
         for (int row = 0; row < 8; row++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dm_smem_u32(dst + row * DM_RS)),
                          "l"(src + row * DG_BLOCK), "r"(DG_BLOCK * 8), "r"(bar)
                          : "memory");
+        gi++;
     };
-    if (lane == 0)
-        for (int k = 0; k < DM_STAGES && k < mine; k++) issue(k);
-    double accA[16][2];
-#pragma unroll
-    for (int t = 0; t < 16; t++) { accA[t][0] = 0.0; accA[t][1] = 0.0; }
+    if (lane == 0) {
+        open_item();
+        for (int s = 0; s < DM_STAGES; s++) issue(s);
+    }
     const bool colok = r < kc;
-    for (int k = 0; k < mine; k++) {
-        const int st = k % DM_STAGES;
-        const uint32_t parity = (uint32_t)((k / DM_STAGES) & 1);
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "WAIT_LOOP:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra DONE;\n\t"
-            "bra WAIT_LOOP;\n\t"
-            "DONE:\n\t}" ::"r"(dm_smem_u32(&full[warp][st])),
-            "r"(parity)
-            : "memory");
-        const double *tile = ring + (size_t)st * (8 * DM_RS);
-        const int64_t irow0 = (int64_t)it.i0 + (int64_t)(warp + 8 * k) * 8;    // panel row of tile row 0
-        // ---- part A: D[c][n] += sum over the 8 rows (two k = 4 halves) of b[i][c] * panel[i][n], 16 n-tiles ----
+    uint32_t tile_no = 0;                                                    // groups consumed so far: stage and phase of the ring
+    for (int64_t tc = wid; tc < n_items; tc += W) {
+        const dg_item it = items[tc];
+        const int ng = it.rows >> 3;
+        // part B's second operand for this block-row: b[128 R + 4 j + q][c = r], zero for padding columns / samples
+        double tb[32];
+        if (it.partB) {
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            if (dbg & 5) break;
-            const int64_t i = irow0 + 4 * hh + q;
-            const double bA = (colok && i < N) ? B[(int64_t)r * N + i] : 0.0;       // A fragment: row = column c = r, k = q
-            const double *trow = tile + (4 * hh + q) * DM_RS + r;                    // B fragment: k = q (row 4hh + q), col = r
-#pragma unroll
-            for (int t = 0; t < 16; t++) dmma_m8n8k4(accA[t][0], accA[t][1], bA, trow[8 * t]);
-        }
-        // ---- part B: D[i][c] = sum_n panel[i][n] b[128R + n][c], 32 MMAs over n = 4 j + q ----
-        if (PARTB && !(dbg & 6)) {
-            // four independent accumulator pairs: a single chain of 32 dependent MMAs would be latency-bound
-            double dd[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-            const double *ta = tile + r * DM_RS + q, *tb = sbn + r * DM_RS + q;
-#pragma unroll
-            for (int j = 0; j < 32; j++) dmma_m8n8k4(dd[j & 3][0], dd[j & 3][1], ta[4 * j], tb[4 * j]);
-            const double d0 = (dd[0][0] + dd[1][0]) + (dd[2][0] + dd[3][0]), d1 = (dd[0][1] + dd[1][1]) + (dd[2][1] + dd[3][1]);
-            const int64_t i = irow0 + r;                                             // D fragment: row = r, columns 2q, 2q + 1
-            if (i < N) {
-                if (2 * q < kc && d0 != 0.0) atomicAdd(Y + (int64_t)(2 * q) * N + i, d0);
-                if (2 * q + 1 < kc && d1 != 0.0) atomicAdd(Y + (int64_t)(2 * q + 1) * N + i, d1);
+            for (int j = 0; j < 32; j++) {
+                const int64_t jj = (int64_t)it.R * DG_BLOCK + 4 * j + q;
+                tb[j] = (colok && jj < N) ? B[(int64_t)r * N + jj] : 0.0;
             }
         }
-        __syncwarp();
-        if (lane == 0 && k + DM_STAGES < mine) issue(k + DM_STAGES);
-    }
-    // part-A sums of the 8 warps meet in shared memory (the b stage is free now), then one atomic per (column, sample)
-    __syncthreads();
-    double *red = dm_smem;                                    // [8][128]
-    for (int e = threadIdx.x; e < 8 * DG_BLOCK; e += 256) red[e] = 0.0;
-    __syncthreads();
-    if (mine > 0 && colok) {
+        double accA[16][2];
 #pragma unroll
-        for (int t = 0; t < 16; t++) {                        // D fragment: row = c = r, columns n = 8 t + 2 q, + 1
-            atomicAdd(&red[r * DG_BLOCK + 8 * t + 2 * q], accA[t][0]);
-            atomicAdd(&red[r * DG_BLOCK + 8 * t + 2 * q + 1], accA[t][1]);
+        for (int t = 0; t < 16; t++) { accA[t][0] = 0.0; accA[t][1] = 0.0; }
+        for (int g = 0; g < ng; g++, tile_no++) {
+            const int st = (int)(tile_no % DM_STAGES);
+            const uint32_t parity = (tile_no / DM_STAGES) & 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "WAIT_LOOP:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra DONE;\n\t"
+                "bra WAIT_LOOP;\n\t"
+                "DONE:\n\t}" ::"r"(dm_smem_u32(&full[warp][st])),
+                "r"(parity)
+                : "memory");
+            const double *tile = ring + (size_t)st * (8 * DM_RS);
+            const int64_t irow0 = (int64_t)it.i0 + (int64_t)g * 8;                   // panel row of tile row 0
+            // ---- part A: D[c][n] += sum over the 8 rows (two k = 4 halves) of b[i][c] * panel[i][n], 16 n-tiles ----
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int64_t i = irow0 + 4 * hh + q;
+                const double bA = (colok && i < N) ? B[(int64_t)r * N + i] : 0.0;       // A fragment: row = column c = r, k = q
+                const double *trow = tile + (4 * hh + q) * DM_RS + r;                    // B fragment: k = q (row 4hh + q), col = r
+#pragma unroll
+                for (int t = 0; t < 16; t++) dmma_m8n8k4(accA[t][0], accA[t][1], bA, trow[8 * t]);
+            }
+            // ---- part B: D[i][c] = sum_n panel[i][n] b[128R + n][c], 32 MMAs over n = 4 j + q ----
+            if (it.partB) {
+                // four independent accumulator pairs: a single chain of 32 dependent MMAs would be latency-bound
+                double dd[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                const double *ta = tile + r * DM_RS + q;
+#pragma unroll
+                for (int j = 0; j < 32; j++) dmma_m8n8k4(dd[j & 3][0], dd[j & 3][1], ta[4 * j], tb[j]);
+                const double d0 = (dd[0][0] + dd[1][0]) + (dd[2][0] + dd[3][0]), d1 = (dd[0][1] + dd[1][1]) + (dd[2][1] + dd[3][1]);
+                const int64_t i = irow0 + r;                                             // D fragment: row = r, columns 2q, 2q + 1
+                if (i < N) {
+                    if (2 * q < kc && d0 != 0.0) atomicAdd(Y + (int64_t)(2 * q) * N + i, d0);
+                    if (2 * q + 1 < kc && d1 != 0.0) atomicAdd(Y + (int64_t)(2 * q + 1) * N + i, d1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) issue(st);
         }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < kc * DG_BLOCK; e += 256) {
-        const int c = e >> 7, n = e & 127;
-        const int64_t j = (int64_t)it.R * DG_BLOCK + n;
-        const double v = red[e];
-        if (j < N && v != 0.0) atomicAdd(Y + (int64_t)c * N + j, v);
+        // part-A sums of this item: D fragment row = c = r, columns n = 8 t + 2 q, + 1
+        if (colok) {
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const int64_t j = (int64_t)it.R * DG_BLOCK + 8 * t + 2 * q;
+                if (j < N && accA[t][0] != 0.0) atomicAdd(Y + (int64_t)r * N + j, accA[t][0]);
+                if (j + 1 < N && accA[t][1] != 0.0) atomicAdd(Y + (int64_t)r * N + j + 1, accA[t][1]);
+            }
+        }
     }
 }
 
 static void symm_mma_launch(sgb_ctx *h, const sgb_dense *d, const double *B, int kc, int64_t N, double *Y)
 {
-    const size_t smem = sizeof(double) * (size_t)(8 * DM_RS + 8 * DM_STAGES * 8 * DM_RS);
-    if (sgb_first_on_device(h->device, SGB_SITE_SYMV_BASE + 0)) {
-        cudaFuncSetAttribute(dense_symm_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(dense_symm_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-#ifdef SGB_ABLATION
-    static const int dbg = getenv("SGB_DM_DBG") ? atoi(getenv("SGB_DM_DBG")) : 0;
-#else
-    const int dbg = 0;
-#endif
-    if (d->n_items_b)
-        dense_symm_mma_kernel<true><<<(unsigned)d->n_items_b, 256, smem, h->stream>>>(d->pool, d->d_items, 0, B, kc, N, Y, dbg);
-    if (d->n_items > d->n_items_b)
-        dense_symm_mma_kernel<false><<<(unsigned)(d->n_items - d->n_items_b), 256, smem, h->stream>>>(d->pool, d->d_items, d->n_items_b, B, kc, N, Y, dbg);
-    h->cnt.n_kernel_launches += 2;
+    const size_t smem = sizeof(double) * (size_t)(8 * DM_STAGES * 8 * DM_RS);
+    if (sgb_first_on_device(h->device, SGB_SITE_SYMV_BASE + 0))
+        cudaFuncSetAttribute(dense_symm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!d->n_items) return;
+    const int64_t grid = std::min<int64_t>(h->sm_count, (d->n_items + 7) / 8);
+    dense_symm_mma_kernel<<<(unsigned)grid, 256, smem, h->stream>>>(d->pool, d->d_items, d->n_items, B, kc, N, Y);
+    h->cnt.n_kernel_launches += 1;
 }
 
 // out[a + b*ni] = K[i0+a][j0+b] if this rank stores it, else 0
