@@ -198,7 +198,9 @@ int sgb_get_coef_loco_all(sgb_ctx *h, int family, const double *y, const double 
  * tau[0] fixed at 1; 1: gaussian.  alpha_fit0 / eta_fit0: coefficients and linear predictors of the glm fit0 (eta includes the
  * offset); tauInit[2] as the R argument.  Outputs: tau_out[2], alpha (p), eta, mu, Y (N), cov (p x p), converged (i < maxiter),
  * n_outer (iterations of the outer loop); the *_loco outputs are laid out as in sgb_get_coef_loco_all and may be NULL when
- * loco = 0.  Probes come from `probes` exactly as in sgb_get_ai_score (sgb_set_probe_stream_fixed applies). */
+ * loco = 0.  Probes come from `probes` as in sgb_get_ai_score (sgb_set_probe_stream_fixed applies); because this call holds
+ * several trace estimates, `probes(user, N, 0, NULL)` is called before each one: the callback restarts its stream there, as
+ * GetTrace's set_seed(200) does (FG.cpp:3114). */
 int sgb_glmmkin_ai_pcg(sgb_ctx *h, int quantitative, const double *y, const double *X, int p, const double *offset,
                        const double *alpha_fit0, const double *eta_fit0, const double *tauInit, int maxiter, double tol,
                        int nrun, double tolPCG, int maxiterPCG, double traceCVcutoff, int loco, sgb_probe_fn probes,

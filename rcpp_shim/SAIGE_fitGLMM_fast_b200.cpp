@@ -64,6 +64,14 @@ static int draw_probes(void *, int64_t n, int count, double *out)
     }
     return 0;
 }
+static void set_seed(unsigned int seed);
+// sgb_glmmkin_ai_pcg runs several trace estimates inside one call and announces each with count = 0: re-seed there, as GetTrace
+// does (FG.cpp:3114)
+static int draw_probes_reseeding(void *u, int64_t n, int count, double *out)
+{
+    if (count == 0) { set_seed(200); return 0; }
+    return draw_probes(u, n, count, out);
+}
 static void set_seed(unsigned int seed)
 {
 #if defined(USE_pbdMPI)
@@ -247,4 +255,73 @@ arma::fvec getPCG1ofSigmaAndVector(arma::fvec &wVec, arma::fvec &tauVec, arma::f
 }
 // [[Rcpp::export]]
 arma::fvec get_DiagofKin() { arma::vec x(sgb_get_nnomissing(ctx())); ck(sgb_get_diag_of_kin(ctx(), x.memptr())); return arma::conv_to<arma::fvec>::from(x); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// OPTIONAL exports (new names: they need `Rcpp::compileAttributes()` and the R-side patch of INTEGRATION.md "Driver loops
+// inside the library").  The 28 exports above are the drop-in; these run whole R functions of R/SAIGE_fitGLMM_fast.R as one
+// library call each, with every N-vector resident on the device between the solves.
+// ---------------------------------------------------------------------------------------------------------------------
+static int family_code(const std::string &f)
+{
+    if (f == "binomial") return 0;
+    if (f == "gaussian") return 1;
+    Rcpp::stop("saige_b200: family '" + f + "' is not built into the library (binomial, gaussian); use the R loop");
+}
+
+// Get_Coef / Get_Coef_LOCO (R/SAIGE_fitGLMM_fast.R:2-35, 42-73): body of the R function becomes
+//   Get_Coef_b200(y, X, tau, family$family, alpha0, eta0, offset, maxiterPCG, tolPCG, maxiter, FALSE)
+// [[Rcpp::export]]
+Rcpp::List Get_Coef_b200(arma::vec &y, arma::mat &X, arma::vec &tau, std::string family, arma::vec &alpha0, arma::vec &eta0,
+                         arma::vec &offset, int maxiterPCG, double tolPCG, int maxiter, bool isLOCO)
+{
+    const int p = X.n_cols; const arma::uword N = X.n_rows;
+    arma::vec Y(N), alpha(p), eta(N), W(N), SiY(N), mu(N); arma::mat cov(p, p), SiX(N, p); int32_t nit = 0;
+    ck(sgb_get_coef(ctx(), family_code(family), y.memptr(), X.memptr(), p, offset.memptr(), tau.memptr(), alpha0.memptr(),
+                    eta0.memptr(), maxiter, maxiterPCG, tolPCG, isLOCO ? 1 : 0, Y.memptr(), alpha.memptr(), eta.memptr(), W.memptr(),
+                    cov.memptr(), SiY.memptr(), SiX.memptr(), mu.memptr(), &nit));
+    return Rcpp::List::create(Named("Y") = Y, Named("alpha") = alpha, Named("eta") = eta, Named("W") = W, Named("cov") = cov,
+                              Named("sqrtW") = arma::sqrt(W), Named("Sigma_iY") = SiY, Named("Sigma_iX") = SiX, Named("mu") = mu);
+}
+
+// glmmkin.ai_PCG_Rcpp_Binary / _Quantitative between setgeno and the result list (R/SAIGE_fitGLMM_fast.R:127-292, 340-549):
+// returns theta, coefficients, linear.predictors, fitted.values, Y, cov, converged and, with LOCO, N x 22 matrices
+// (Y, linear.predictors, fitted.values), p x 22 coefficients and p*p x 22 covariances of the leave-one-chromosome-out refits;
+// the R function keeps its own tail (ScoreTest_NULL_Model, Covariate_Transform_Back, the LOCOResult list).
+// [[Rcpp::export]]
+Rcpp::List glmmkin_ai_PCG_b200(bool isQuantitative, arma::vec &y, arma::mat &X, arma::vec &offset, arma::vec &alpha_fit0,
+                               arma::vec &eta_fit0, arma::vec &tauInit, int maxiter, double tol, int nrun, double tolPCG,
+                               int maxiterPCG, double traceCVcutoff, bool LOCO, int nChrom)
+{
+    const int p = X.n_cols; const arma::uword N = X.n_rows; const int nc = LOCO ? nChrom : 1;
+    arma::vec tau(2), alpha(p), eta(N), mu(N), Y(N); arma::mat cov(p, p);
+    arma::mat Yl(N, nc, arma::fill::zeros), el(N, nc, arma::fill::zeros), ml(N, nc, arma::fill::zeros), al(p, nc, arma::fill::zeros),
+              cl(p * p, nc, arma::fill::zeros);
+    arma::ivec nit(nc, arma::fill::zeros); int32_t conv = 0, nouter = 0;
+    sgb_set_probe_stream_fixed(ctx(), 1);                       // the first nrun probes of every estimate are the same vectors
+    ck(sgb_glmmkin_ai_pcg(ctx(), isQuantitative ? 1 : 0, y.memptr(), X.memptr(), p, offset.memptr(), alpha_fit0.memptr(),
+                          eta_fit0.memptr(), tauInit.memptr(), maxiter, tol, nrun, tolPCG, maxiterPCG, traceCVcutoff, LOCO ? 1 : 0,
+                          draw_probes_reseeding, nullptr, tau.memptr(), alpha.memptr(), eta.memptr(), mu.memptr(), Y.memptr(),
+                          cov.memptr(), &conv, &nouter, Yl.memptr(), al.memptr(), el.memptr(), cl.memptr(), ml.memptr(),
+                          reinterpret_cast<int32_t *>(nit.memptr()), nullptr, nullptr));
+    return Rcpp::List::create(Named("theta") = tau, Named("coefficients") = alpha, Named("linear.predictors") = eta,
+                              Named("fitted.values") = mu, Named("Y") = Y, Named("cov") = cov, Named("converged") = conv != 0,
+                              Named("LOCO.Y") = Yl, Named("LOCO.coefficients") = al, Named("LOCO.linear.predictors") = el,
+                              Named("LOCO.cov") = cl, Named("LOCO.fitted.values") = ml);
+}
+
+// The marker loop of extractVarianceRatio (R/SAIGE_fitGLMM_fast.R:2298-2378) for the markers of one round (numMarkers, then +10):
+// markerIdx 0-based into the GRM store (isVarRatioGeno = FALSE) or the hold-out store; returns var1, var2null, AC per marker.
+// [[Rcpp::export]]
+Rcpp::List varianceRatioMarkers_b200(Rcpp::IntegerVector markerIdx, bool isVarRatioGeno, arma::vec &W, arma::vec &tau, arma::mat &X,
+                                     arma::mat &XV, arma::mat &XXVX_inv, arma::mat &Sigma_iX, arma::vec &mu2, bool isBinary,
+                                     int maxiterPCG, double tolPCG)
+{
+    const int n = markerIdx.size();
+    std::vector<int64_t> idx(markerIdx.begin(), markerIdx.end());
+    arma::vec v1(n), v2(n), ac(n);
+    ck(sgb_variance_ratio_markers(ctx(), idx.data(), n, isVarRatioGeno ? 1 : 0, W.memptr(), tau.memptr(), X.memptr(), X.n_cols,
+                                  XV.memptr(), XXVX_inv.memptr(), Sigma_iX.memptr(), isBinary ? mu2.memptr() : nullptr, maxiterPCG,
+                                  tolPCG, v1.memptr(), v2.memptr(), ac.memptr()));
+    return Rcpp::List::create(Named("var1") = v1, Named("var2null") = v2, Named("AC") = ac);
+}
 #endif  // USE_SAIGE_B200

@@ -282,12 +282,18 @@ class SaigeB200:
         return self.getPCG1ofSigmaAndVector(wVec, tauVec, bVec, maxiterPCG, tolPCG, True)
 
     # ---- AI-REML ----
-    def _probe_cb(self, draw):
+    def _probe_cb(self, draw, factory=None):
+        """draw(n) -> the next n probe columns.  factory: makes a fresh draw(); used when the library announces a new trace
+        estimate with count = 0 (sgb_glmmkin_ai_pcg), where the reference re-seeds its generator."""
         N = self.N
+        state = [draw]
 
         def cb(user, n, count, out):
             try:
-                U = np.asarray(draw(int(count)), dtype=np.float64).reshape(N, -1)
+                if count == 0:
+                    state[0] = factory()
+                    return 0
+                U = np.asarray(state[0](int(count)), dtype=np.float64).reshape(N, -1)
                 if U.shape[1] != count:
                     return 1
                 dst = np.ctypeslib.as_array(out, shape=(int(n) * int(count),))
@@ -360,8 +366,9 @@ class SaigeB200:
         return [None if (s == -1 or e == -1) else view(c) for c, (s, e) in enumerate(zip(self._loco_start, self._loco_end))]
 
     def glmmkin_ai_PCG(self, trait, y, X, offset, alpha_fit0, eta_fit0, tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG,
-                       traceCVcutoff, LOCO, draw, on_chrom=None):
+                       traceCVcutoff, LOCO, draw_factory, on_chrom=None):
         """glmmkin.ai_PCG_Rcpp_Binary / _Quantitative after setgeno (FG.R:127-304, 340-549) as one call (sgb_glmmkin_ai_pcg).
+        draw_factory() -> draw(n): a fresh probe stream per trace estimate (GetTrace re-seeds, FG.cpp:3114).
         on_chrom(c, dict): called when the genome-wide fit (c = -1) / chromosome c's refit is complete, while the GPU goes on."""
         X = _f64(np.asarray(X).reshape(self.N, -1))
         p = X.shape[1]
@@ -373,7 +380,7 @@ class SaigeB200:
         nchr = len(self._loco_start) if LOCO else 0
         Yl, el, ml = (np.zeros((N, max(nchr, 1)), order="F") for _ in range(3))
         al, cl, nl = np.zeros((p, max(nchr, 1)), order="F"), np.zeros((p * p, max(nchr, 1)), order="F"), np.zeros(max(nchr, 1), dtype=np.int32)
-        cb = self._probe_cb(draw)
+        cb = self._probe_cb(None, draw_factory)
 
         def view(c):
             if c < 0:

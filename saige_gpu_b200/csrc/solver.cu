@@ -594,7 +594,7 @@ static void ai_scratch_take(arena *a, int64_t N, int nrun, ai_scratch *sc)
 }
 static int ai_score_core(sgb_ctx *h, bool quant, const double *dw, const double *dY, const double *dX, const double *dSiX, int p,
                          const double *tau, const double *cov_in, int nrun, int maxiterPCG, double tolPCG, double traceCVcutoff,
-                         sgb_probe_fn probes, void *user, const ai_scratch &sc, double *out8, double *PY_out);
+                         sgb_probe_fn probes, void *user, const ai_scratch &sc, double *out8, double *PY_out, bool announce);
 
 // Shared body of getAIScore / getAIScore_q.  out: YPAPY, YPA0PY, Trace0, Trace1, AI00, AI01, AI11, nrun used.
 static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *X, int p, const double *w, const double *tau,
@@ -617,16 +617,19 @@ static int ai_score_impl(sgb_ctx *h, bool quant, const double *Y, const double *
     SGB_TRY(up(h, dX, X, (size_t)N * p));
     SGB_TRY(up(h, dSiX, Sigma_iX, (size_t)N * p));
     SGB_TRY(up(h, sc.dB, Sigma_iY, N));            // dB[:,0] = Sigma_iY for now
-    return ai_score_core(h, quant, dw, dY, dX, dSiX, p, tau, cov_in, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, sc, out8, PY_out);
+    return ai_score_core(h, quant, dw, dY, dX, dSiX, p, tau, cov_in, nrun, maxiterPCG, tolPCG, traceCVcutoff, probes, user, sc, out8, PY_out, false);
 }
 
 // The AI step on device-resident inputs (the host wrapper above uploads them; sgb_glmmkin_ai_pcg takes them from its Get_Coef)
 static int ai_score_core(sgb_ctx *h, bool quant, const double *dw, const double *dY, const double *dX, const double *dSiX, int p,
                          const double *tau, const double *cov_in, int nrun, int maxiterPCG, double tolPCG, double traceCVcutoff,
-                         sgb_probe_fn probes, void *user, const ai_scratch &sc, double *out8, double *PY_out)
+                         sgb_probe_fn probes, void *user, const ai_scratch &sc, double *out8, double *PY_out, bool announce)
 {
     const int64_t N = h->N;
     const int kb = sc.kb;
+    // several trace estimates share one callback inside sgb_glmmkin_ai_pcg: count = 0 tells it that a new estimate starts
+    // (the reference re-seeds there, GetTrace, FG.cpp:3114)
+    if (announce && probes(user, N, 0, nullptr)) return sgb_fail(h, "getAIScore: probe callback failed");
     double *dB = sc.dB, *dK = sc.dK, *dS = sc.dS, *dPr = sc.dPr, *dC = sc.dC;
     SGB_RANGE("ai_score");
     SGB_PROF(h, "AI step (getAIScore / fitglmmaiRPCG)");
@@ -1041,7 +1044,7 @@ extern "C" int sgb_glmmkin_ai_pcg(sgb_ctx *h, int quantitative, const double *y,
     auto ai = [&]() -> int {                                         // the AI step on the state Get_Coef left
         CUDA_OK(h, cudaMemcpyAsync(sc.dB, s.S, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->stream));
         return ai_score_core(h, quant, s.w, s.YX, s.YX + N, s.S + N, p, tau, covm.data(), nrun, maxiterPCG, tolPCG, traceCVcutoff,
-                             probes, user, sc, o, nullptr);
+                             probes, user, sc, o, nullptr, true);
     };
     SGB_TRY(coef(al_loop));
     SGB_TRY(ai());

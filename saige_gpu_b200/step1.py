@@ -322,7 +322,7 @@ def _glmmkin_ai_PCG_one_call(geno, fit0, probes, trait, tauInit, maxiter, tol, n
             futures[c] = pool.submit(ScoreTest_NULL_Model, mu, mu2, y, X)
         tau_box = [1.0]
         r = geno.glmmkin_ai_PCG(trait, y, X, offset, fit0["coef"], fit0["eta"], tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG,
-                                traceCVcutoff, LOCO, probes.fresh(), on_chrom=on_chrom)
+                                traceCVcutoff, LOCO, probes.fresh, on_chrom=on_chrom)
         tau, mu = r["theta"], r["fitted_values"]
         if verbose:
             print("Final", tau)

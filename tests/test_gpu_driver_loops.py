@@ -176,6 +176,34 @@ def test_probe_stream_fixed_with_cv_retries(loco_pair, golden_dir):
         assert got["Trace"] == want["Trace"] and got["YPAPY"] == want["YPAPY"] and got["AI"] == want["AI"]
 
 
+def test_one_call_fit_with_cv_retries_equals_mirror(loco_pair, golden_dir):
+    """A trace CV cut-off that needs +10 retry batches in every AI step: inside the one-call fit the probe stream restarts at
+    every trace estimate (count = 0 announcement) and the resident first batch is replayed before a retry, so the fit equals the
+    mirror's, which re-seeds per call."""
+    from saige_gpu_b200 import step1
+    g, o = loco_pair
+    yb, _, X = _pheno(golden_dir)
+    fit0 = step1.glm_fit(yb, X, step1.Binomial)
+    probes = step1.ProbeStream(o.N, nmax=1000, seed=200)
+    g.reset_counters()
+    m0 = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", traceCVcutoff=1.0)         # no estimate needs more than nrun probes
+    base = g.counters()["n_pcg_solves"] / len(m0["tau_path"])
+    for cutoff in (1e-3, 7e-4, 5e-4, 3e-4):
+        g.reset_counters()
+        mm = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", traceCVcutoff=cutoff)
+        cm = g.counters()
+        if cm["n_pcg_solves"] / len(mm["tau_path"]) >= base + 10:                         # columns solved per outer step grew by a retry batch
+            break
+    else:
+        pytest.fail("no CV cut-off produced retry batches")
+    g.reset_counters()
+    mn = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", traceCVcutoff=cutoff, native_loops=True)
+    cn = g.counters()
+    g.setProbeStreamFixed(False)
+    assert cn["n_pcg_solves"] == cm["n_pcg_solves"] and cn["n_pcg_iterations"] == cm["n_pcg_iterations"]
+    assert rel(mn["theta"], mm["theta"]) < TOL_SAME and rel(mn["coefficients"], mm["coefficients"]) < TOL_SAME
+
+
 @pytest.mark.parametrize("trait", ["binary", "quantitative"])
 def test_variance_ratio_markers_native(loco_pair, golden_dir, trait):
     from oracle import oracle as O

@@ -1,2 +1,2 @@
 set -x
-(SGB_PROFILE=1 timeout 600 python tools/profile_step1_host.py 200000 62500 > gpurun_out/r02_step1_phases_M62500.txt 2>&1); grep -v "K.\[PY" gpurun_out/r02_step1_phases_M62500.txt | tail -150
+(timeout 900 python -m pytest tests/test_gpu_driver_loops.py -m gpu -x -q > gpurun_out/r02_gputests_loops.log 2>&1; echo rc=$? >> gpurun_out/r02_gputests_loops.log); tail -25 gpurun_out/r02_gputests_loops.log
