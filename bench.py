@@ -250,6 +250,8 @@ def main():
 
     import torch
     import torch.distributed as dist
+    if os.environ.get("SGB_PROFILE_RANK0") and int(os.environ.get("RANK", "0")) == 0:
+        os.environ["SGB_PROFILE"] = "1"            # library phase timer (stderr) on rank 0 only: a diagnostic run, not a bench value
     from saige_gpu_b200 import SaigeB200, synth, step1
 
     if world > 1:

@@ -335,115 +335,152 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1)
+// WARP PAIRS: 16 warps per SM.  Pair w = (warp 2w, warp 2w + 1) shares one ring; the even warp does part A of every tile and
+// owns the copies, the odd warp does part B.  (One warp doing both halves needed 222 registers, so 8 warps per SM: tensor pipe 53 %,
+// DRAM 60 %, warps active 12 % under ncu -- latency-bound.  Split, each role fits 128 registers.)  full[pair][stage]: copy landed
+// (expect_tx); empty[pair][stage]: both consumers are done with the tile (count 2) -- the producer lane waits for it before refilling.
+__device__ __forceinline__ void dm_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1)
 dense_symm_mma_kernel(const double *__restrict__ pool, const dg_item *__restrict__ items, int64_t n_items, const double *__restrict__ B, int kc,
                       int64_t N, double *__restrict__ Y)
 {
     extern __shared__ __align__(128) double dm_smem[];
-    __shared__ uint64_t full[8][DM_STAGES];
+    __shared__ uint64_t full[8][DM_STAGES], empty[8][DM_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
-    double *ring = dm_smem + (size_t)warp * (DM_STAGES * 8 * DM_RS);
+    const int pair = warp >> 1, role = warp & 1;
+    double *ring = dm_smem + (size_t)pair * (DM_STAGES * 8 * DM_RS);
     // neighbouring items (adjacent chunks of one panel) go to different SMs at the same time
-    const int64_t W = (int64_t)gridDim.x * 8, wid = (int64_t)warp * gridDim.x + blockIdx.x;
-    if (lane == 0) {
-        for (int s = 0; s < DM_STAGES; s++)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dm_smem_u32(&full[warp][s])), "r"(1));
+    const int64_t W = (int64_t)gridDim.x * 8, wid = (int64_t)pair * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 8; w++)
+            for (int s = 0; s < DM_STAGES; s++) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dm_smem_u32(&full[w][s])), "r"(1));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dm_smem_u32(&empty[w][s])), "r"(2));
+            }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    __syncwarp();
-    // ---- producer cursor (lane 0): the next group of 8 rows to copy, running over this warp's items ----
-    int64_t ti = wid;
-    int gi = 0, ngi = 0;
-    const double *srci = nullptr;
-    auto open_item = [&]() {
-        if (ti < n_items) {
-            const dg_item t = items[ti];
-            ngi = t.rows >> 3; gi = 0;
-            srci = pool + t.off + (int64_t)t.i0 * DG_BLOCK;
-        }
-    };
-    auto issue = [&](int st) {
-        while (ti < n_items && gi >= ngi) { ti += W; open_item(); }
-        if (ti >= n_items) return;
-        const uint32_t bar = dm_smem_u32(&full[warp][st]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8 * DG_BLOCK * 8) : "memory");
-        const double *src = srci + (int64_t)gi * 8 * DG_BLOCK;
-        double *dst = ring + (size_t)st * (8 * DM_RS);
-#pragma unroll
-        for (int row = 0; row < 8; row++)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dm_smem_u32(dst + row * DM_RS)),
-                         "l"(src + row * DG_BLOCK), "r"(DG_BLOCK * 8), "r"(bar)
-                         : "memory");
-        gi++;
-    };
-    if (lane == 0) {
-        open_item();
-        for (int s = 0; s < DM_STAGES; s++) issue(s);
-    }
+    __syncthreads();
     const bool colok = r < kc;
     uint32_t tile_no = 0;                                                    // groups consumed so far: stage and phase of the ring
-    for (int64_t tc = wid; tc < n_items; tc += W) {
-        const dg_item it = items[tc];
-        const int ng = it.rows >> 3;
-        // part B's second operand for this block-row: b[128 R + 4 j + q][c = r], zero for padding columns / samples
-        double tb[32];
-        if (it.partB) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int64_t jj = (int64_t)it.R * DG_BLOCK + 4 * j + q;
-                tb[j] = (colok && jj < N) ? B[(int64_t)r * N + jj] : 0.0;
+    if (role == 0) {
+        // ---- producer cursor (lane 0): the next group of 8 rows to copy, running over this pair's items ----
+        int64_t ti = wid;
+        int gi = 0, ngi = 0;
+        uint32_t issued = 0;
+        const double *srci = nullptr;
+        auto open_item = [&]() {
+            if (ti < n_items) {
+                const dg_item t = items[ti];
+                ngi = t.rows >> 3; gi = 0;
+                srci = pool + t.off + (int64_t)t.i0 * DG_BLOCK;
             }
+        };
+        auto issue = [&]() {
+            while (ti < n_items && gi >= ngi) { ti += W; open_item(); }
+            if (ti >= n_items) return;
+            const int st = (int)(issued % DM_STAGES);
+            if (issued >= DM_STAGES) dm_wait(dm_smem_u32(&empty[pair][st]), ((issued / DM_STAGES) - 1) & 1u);   // both consumers left the stage
+            const uint32_t bar = dm_smem_u32(&full[pair][st]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8 * DG_BLOCK * 8) : "memory");
+            const double *src = srci + (int64_t)gi * 8 * DG_BLOCK;
+            double *dst = ring + (size_t)st * (8 * DM_RS);
+#pragma unroll
+            for (int row = 0; row < 8; row++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dm_smem_u32(dst + row * DM_RS)),
+                             "l"(src + row * DG_BLOCK), "r"(DG_BLOCK * 8), "r"(bar)
+                             : "memory");
+            gi++; issued++;
+        };
+        if (lane == 0) {
+            open_item();
+            for (int s = 0; s < DM_STAGES; s++) issue();
         }
-        double accA[16][2];
+        // ---- part A: D[c][n] += sum over the 8 rows (two k = 4 halves) of b[i][c] * panel[i][n], 16 n-tiles ----
+        for (int64_t tc = wid; tc < n_items; tc += W) {
+            const dg_item it = items[tc];
+            const int ng = it.rows >> 3;
+            double accA[16][2];
 #pragma unroll
-        for (int t = 0; t < 16; t++) { accA[t][0] = 0.0; accA[t][1] = 0.0; }
-        for (int g = 0; g < ng; g++, tile_no++) {
-            const int st = (int)(tile_no % DM_STAGES);
-            const uint32_t parity = (tile_no / DM_STAGES) & 1u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "WAIT_LOOP:\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                "@p bra DONE;\n\t"
-                "bra WAIT_LOOP;\n\t"
-                "DONE:\n\t}" ::"r"(dm_smem_u32(&full[warp][st])),
-                "r"(parity)
-                : "memory");
-            const double *tile = ring + (size_t)st * (8 * DM_RS);
-            const int64_t irow0 = (int64_t)it.i0 + (int64_t)g * 8;                   // panel row of tile row 0
-            // ---- part A: D[c][n] += sum over the 8 rows (two k = 4 halves) of b[i][c] * panel[i][n], 16 n-tiles ----
+            for (int t = 0; t < 16; t++) { accA[t][0] = 0.0; accA[t][1] = 0.0; }
+            for (int g = 0; g < ng; g++, tile_no++) {
+                const int st = (int)(tile_no % DM_STAGES);
+                const int64_t irow0 = (int64_t)it.i0 + (int64_t)g * 8;               // panel row of tile row 0
+                double bA[2];
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                const int64_t i = irow0 + 4 * hh + q;
-                const double bA = (colok && i < N) ? B[(int64_t)r * N + i] : 0.0;       // A fragment: row = column c = r, k = q
-                const double *trow = tile + (4 * hh + q) * DM_RS + r;                    // B fragment: k = q (row 4hh + q), col = r
+                for (int hh = 0; hh < 2; hh++) {                                     // A fragment: row = column c = r, k = q
+                    const int64_t i = irow0 + 4 * hh + q;
+                    bA[hh] = (colok && i < N) ? B[(int64_t)r * N + i] : 0.0;
+                }
+                dm_wait(dm_smem_u32(&full[pair][st]), (tile_no / DM_STAGES) & 1u);
+                const double *tile = ring + (size_t)st * (8 * DM_RS);
 #pragma unroll
-                for (int t = 0; t < 16; t++) dmma_m8n8k4(accA[t][0], accA[t][1], bA, trow[8 * t]);
-            }
-            // ---- part B: D[i][c] = sum_n panel[i][n] b[128R + n][c], 32 MMAs over n = 4 j + q ----
-            if (it.partB) {
-                // four independent accumulator pairs: a single chain of 32 dependent MMAs would be latency-bound
-                double dd[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-                const double *ta = tile + r * DM_RS + q;
+                for (int hh = 0; hh < 2; hh++) {
+                    const double *trow = tile + (4 * hh + q) * DM_RS + r;            // B fragment: k = q (row 4hh + q), col = r
 #pragma unroll
-                for (int j = 0; j < 32; j++) dmma_m8n8k4(dd[j & 3][0], dd[j & 3][1], ta[4 * j], tb[j]);
-                const double d0 = (dd[0][0] + dd[1][0]) + (dd[2][0] + dd[3][0]), d1 = (dd[0][1] + dd[1][1]) + (dd[2][1] + dd[3][1]);
-                const int64_t i = irow0 + r;                                             // D fragment: row = r, columns 2q, 2q + 1
-                if (i < N) {
-                    if (2 * q < kc && d0 != 0.0) atomicAdd(Y + (int64_t)(2 * q) * N + i, d0);
-                    if (2 * q + 1 < kc && d1 != 0.0) atomicAdd(Y + (int64_t)(2 * q + 1) * N + i, d1);
+                    for (int t = 0; t < 16; t++) dmma_m8n8k4(accA[t][0], accA[t][1], bA[hh], trow[8 * t]);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dm_smem_u32(&empty[pair][st])) : "memory");
+                    issue();
                 }
             }
-            __syncwarp();
-            if (lane == 0) issue(st);
-        }
-        // part-A sums of this item: D fragment row = c = r, columns n = 8 t + 2 q, + 1
-        if (colok) {
+            // part-A sums of this item: D fragment row = c = r, columns n = 8 t + 2 q, + 1
+            if (colok) {
 #pragma unroll
-            for (int t = 0; t < 16; t++) {
-                const int64_t j = (int64_t)it.R * DG_BLOCK + 8 * t + 2 * q;
-                if (j < N && accA[t][0] != 0.0) atomicAdd(Y + (int64_t)r * N + j, accA[t][0]);
-                if (j + 1 < N && accA[t][1] != 0.0) atomicAdd(Y + (int64_t)r * N + j + 1, accA[t][1]);
+                for (int t = 0; t < 16; t++) {
+                    const int64_t j = (int64_t)it.R * DG_BLOCK + 8 * t + 2 * q;
+                    if (j < N && accA[t][0] != 0.0) atomicAdd(Y + (int64_t)r * N + j, accA[t][0]);
+                    if (j + 1 < N && accA[t][1] != 0.0) atomicAdd(Y + (int64_t)r * N + j + 1, accA[t][1]);
+                }
+            }
+        }
+    } else {
+        // ---- part B: D[i][c] = sum_n panel[i][n] b[128R + n][c], 32 MMAs over n = 4 j + q ----
+        for (int64_t tc = wid; tc < n_items; tc += W) {
+            const dg_item it = items[tc];
+            const int ng = it.rows >> 3;
+            // the second operand for this block-row: b[128 R + 4 j + q][c = r], zero for padding columns / samples
+            double tb[32];
+            if (it.partB) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int64_t jj = (int64_t)it.R * DG_BLOCK + 4 * j + q;
+                    tb[j] = (colok && jj < N) ? B[(int64_t)r * N + jj] : 0.0;
+                }
+            }
+            for (int g = 0; g < ng; g++, tile_no++) {
+                const int st = (int)(tile_no % DM_STAGES);
+                // also for a diagonal item (no part B): waiting for the copy keeps this warp within one ring of its partner, so
+                // that the two arrivals that free a stage always belong to the same tile
+                dm_wait(dm_smem_u32(&full[pair][st]), (tile_no / DM_STAGES) & 1u);
+                if (it.partB) {
+                    const double *ta = ring + (size_t)st * (8 * DM_RS) + r * DM_RS + q;
+                    // four independent accumulator pairs: a single chain of 32 dependent MMAs would be latency-bound
+                    double dd[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                    for (int j = 0; j < 32; j++) dmma_m8n8k4(dd[j & 3][0], dd[j & 3][1], ta[4 * j], tb[j]);
+                    const double d0 = (dd[0][0] + dd[1][0]) + (dd[2][0] + dd[3][0]), d1 = (dd[0][1] + dd[1][1]) + (dd[2][1] + dd[3][1]);
+                    const int64_t i = (int64_t)it.i0 + (int64_t)g * 8 + r;           // D fragment: row = r, columns 2q, 2q + 1
+                    if (i < N) {
+                        if (2 * q < kc && d0 != 0.0) atomicAdd(Y + (int64_t)(2 * q) * N + i, d0);
+                        if (2 * q + 1 < kc && d1 != 0.0) atomicAdd(Y + (int64_t)(2 * q + 1) * N + i, d1);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dm_smem_u32(&empty[pair][st])) : "memory");
             }
         }
     }
@@ -456,7 +493,7 @@ static void symm_mma_launch(sgb_ctx *h, const sgb_dense *d, const double *B, int
         cudaFuncSetAttribute(dense_symm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (!d->n_items) return;
     const int64_t grid = std::min<int64_t>(h->sm_count, (d->n_items + 7) / 8);
-    dense_symm_mma_kernel<<<(unsigned)grid, 256, smem, h->stream>>>(d->pool, d->d_items, d->n_items, B, kc, N, Y);
+    dense_symm_mma_kernel<<<(unsigned)grid, 512, smem, h->stream>>>(d->pool, d->d_items, d->n_items, B, kc, N, Y);
     h->cnt.n_kernel_launches += 1;
 }
 
