@@ -196,7 +196,9 @@ def glmmkin_ai_PCG(geno, fit0, probes, trait="binary", tauInit=(0.0, 0.0), maxit
     update uses the device's exp instead of numpy's: differences at the 1e-15 level).  native_loops=True runs the whole function
     as ONE library call (sgb_glmmkin_ai_pcg), native_loops="calls" keeps this loop and calls the library once per R loop."""
     nat = dict(native=True) if native_loops else {}
-    geno.setProbeStreamFixed(bool(native_loops))
+    set_fixed = getattr(geno, "setProbeStreamFixed", None)      # a device context has it; the oracle-backed test double does not
+    if set_fixed is not None:
+        set_fixed(bool(native_loops))
     if native_loops is True:
         return _glmmkin_ai_PCG_one_call(geno, fit0, probes, trait, tauInit, maxiter, tol, nrun, tolPCG, maxiterPCG, traceCVcutoff, LOCO,
                                         verbose, timings)
