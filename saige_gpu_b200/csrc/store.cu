@@ -139,6 +139,7 @@ static void free_store(sgb_ctx *h)
     void **ptrs[] = {(void **)&h->dG, (void **)&h->dGt, (void **)&h->d_f2, (void **)&h->d_s, (void **)&h->d_s2,
                      (void **)&h->d_diag, (void **)&h->d_diag_loco};
     for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    h->diag_loco_elems = 0;
     h->loaded = false; h->diag_ready = false; h->diag_loco_ready = false; h->ku_cols = 0;
     h->Mloc = h->M = h->Mvr = 0;
 }
@@ -728,6 +729,14 @@ extern "C" int sgb_set_start_end_index_vec(sgb_ctx *h, const int32_t *start, con
     h->startVec.assign(start, start + n);
     h->endVec.assign(end, end + n);
     h->diag_loco_ready = false;
+    if (h->loaded && n > 0) {
+        // the N x nchr buffer of set_Diagof_StdGeno_LOCO: allocated here, next to setgeno's allocations, so that the first fit
+        // does not pay a cudaMalloc between its solves
+        cudaSetDevice(h->device);
+        size_t bytes = h->diag_loco_elems * sizeof(double);
+        SGB_TRY(sgb_ensure(h, (void **)&h->d_diag_loco, &bytes, sizeof(double) * (size_t)h->N * n));
+        h->diag_loco_elems = bytes / sizeof(double);
+    }
     return 0;
 }
 

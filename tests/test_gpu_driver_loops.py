@@ -260,3 +260,51 @@ def test_variance_ratio_markers_from_holdout_store(golden_dir):
             g.varianceRatioMarkers(np.zeros(129, dtype=np.int64), True, W, m["theta"], m["X"], noK["XV"], noK["XXVX_inv"], SiX, None, 500, 1e-5)
     finally:
         g.close()
+
+
+def test_one_call_fit_stopping_rules_and_errors(loco_pair, golden_dir):
+    """maxiter exhausted -> converged False with the same tau path as the mirror; argument errors are reported, not crashed on."""
+    import ctypes as C
+    from saige_gpu_b200 import step1, SaigeB200Error, _lib
+    g, o = loco_pair
+    yb, _, X = _pheno(golden_dir)
+    fit0 = step1.glm_fit(yb, X, step1.Binomial)
+    probes = step1.ProbeStream(o.N, nmax=130, seed=200)
+    mm = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", maxiter=1, tol=1e-9)
+    mn = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", maxiter=1, tol=1e-9, native_loops=True)
+    g.setProbeStreamFixed(False)
+    assert mm["converged"] is False and mn["converged"] is False and mn["n_outer"] == 1
+    assert rel(mn["theta"], mm["theta"]) < TOL_SAME and rel(mn["coefficients"], mm["coefficients"]) < TOL_SAME
+    # tauInit given (FG.R:152-156): the start value is taken over
+    m2 = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", tauInit=(0.0, 0.4))
+    n2 = step1.glmmkin_ai_PCG(g, fit0, probes, trait="binary", tauInit=(0.0, 0.4), native_loops=True)
+    g.setProbeStreamFixed(False)
+    assert rel(n2["theta"], m2["theta"]) < TOL_SAME and n2["n_outer"] == len(m2["tau_path"]) - 1
+    # NULL probe callback, nrun out of range, family code out of range
+    N, p = o.N, X.shape[1]
+    z = np.zeros(N); Xf = np.asfortranarray(X); out = np.zeros((N, 30), order="F")
+    pp = lambda a: a.ctypes.data_as(C.c_void_p)
+    L = _lib.lib()
+    args = lambda nrun, cb: (g._h, 0, pp(yb), pp(Xf), p, pp(z), pp(np.zeros(p)), pp(z), pp(np.zeros(2)), 5, 0.02, nrun, 1e-5, 500, 0.0025, 0,
+                             cb, None, pp(np.zeros(2)), pp(np.zeros(p)), pp(out), pp(out), pp(out), pp(np.zeros((p, p))), None, None,
+                             None, None, None, None, None, None, _lib.CHROM_FN(), None)
+    assert L.sgb_glmmkin_ai_pcg(*args(30, _lib.PROBE_FN())) != 0 and b"probe callback" in L.sgb_last_error(g._h)
+    assert L.sgb_glmmkin_ai_pcg(*args(1, g._probe_cb(None, probes.fresh))) != 0 and b"nrun" in L.sgb_last_error(g._h)
+    with pytest.raises(SaigeB200Error):
+        g.Get_Coef_LOCO_all(yb, X, np.array([1.0, 0.3]), "binomial", np.zeros(p), fit0["eta"], z, 500, 1e-5, 0)
+
+
+def test_loco_all_requires_loco_diagonal(chr22, golden_dir):
+    from saige_gpu_b200 import SaigeB200, SaigeB200Error, step1
+    from oracle import oracle as O
+    N0, M0 = chr22["N0"], chr22["M0"]
+    g = SaigeB200(device=0)
+    try:
+        g.setminMAFforGRM(0.01); g.setmaxMissingRateforGRM(0.15)
+        g.setgeno_mem(chr22["bed"], N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+        step1.set_loco_ranges(g, chr22["chrs"][g.getQCdMarkerIndex()])
+        yb, _, X = _pheno(golden_dir)
+        with pytest.raises(SaigeB200Error, match="set_Diagof_StdGeno_LOCO"):
+            g.Get_Coef_LOCO_all(yb, X, np.array([1.0, 0.3]), "binomial", np.zeros(3), np.zeros(N0), np.zeros(N0), 500, 1e-5, 5)
+    finally:
+        g.close()
