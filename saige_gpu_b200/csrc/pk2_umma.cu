@@ -490,9 +490,24 @@ int k_pk2_umma_rows(sgb_ctx *h, const uint8_t *P, int64_t stride, int64_t rows_p
     // int32 accumulation: |sum| <= 2 * 128 * (genotypes per row)
     if (kbytes * 4 > ((int64_t)1 << 23)) return sgb_fail(h, "k_pk2_umma: %lld genotypes per row exceed the int32 accumulation bound", (long long)(kbytes * 4));
     const int64_t row_tiles = rows_pad / UMMA_ROWS;
-    // split K only when there are too few row tiles to fill the machine
-    int64_t kchunks = cdiv64((int64_t)h->sm_count * 4, row_tiles);
-    if (kchunks < 1) kchunks = 1;
+    // K split.  All CTAs of a launch do the same work, so the launch takes ceil(CTAs / resident slots) rounds of one CTA time:
+    // 1564 sample tiles on 296 slots are 5.3 rounds of work done in 6, 492 marker tiles x 2 chunks 3.3 done in 4.  Pick the
+    // number of k-chunks that minimises rounds x (k-steps per chunk + a fixed per-CTA cost of ~16 k-steps: tensor-memory
+    // allocation, pipeline fill, accumulator read-out); chunks of one row tile meet in `out` with atomics.
+    const int first_pass_cols = nrows > 256 ? ((((nrows + (nrows + 255) / 256 - 1) / ((nrows + 255) / 256)) + 15) & ~15) : nrows;
+    const int64_t slots = (int64_t)h->sm_count * (first_pass_cols <= 128 ? 2 : 1);
+    int64_t kchunks = 1, best_cost = -1;
+    for (int64_t kc = 1; kc <= 24; kc++) {
+        int64_t per_c = cdiv64(ksteps, kc);
+        if (per_c < 8) per_c = 8;
+        if (per_c > ksteps) per_c = ksteps;
+        const int64_t kcr = cdiv64(ksteps, per_c);
+        const int64_t cost = cdiv64(row_tiles * kcr, slots) * (per_c + 16);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; kchunks = kcr; }
+    }
+#ifdef SGB_ABLATION
+    if (getenv("SGB_UMMA_KCHUNKS")) kchunks = atoi(getenv("SGB_UMMA_KCHUNKS"));
+#endif
     int64_t per = cdiv64(ksteps, kchunks);
     if (per < 8) per = 8;
     if (per > ksteps) per = ksteps;
