@@ -296,13 +296,13 @@ Rcpp::List glmmkin_ai_PCG_b200(bool isQuantitative, arma::vec &y, arma::mat &X, 
     arma::vec tau(2), alpha(p), eta(N), mu(N), Y(N); arma::mat cov(p, p);
     arma::mat Yl(N, nc, arma::fill::zeros), el(N, nc, arma::fill::zeros), ml(N, nc, arma::fill::zeros), al(p, nc, arma::fill::zeros),
               cl(p * p, nc, arma::fill::zeros);
-    arma::ivec nit(nc, arma::fill::zeros); int32_t conv = 0, nouter = 0;
+    std::vector<int32_t> nit(nc, 0); int32_t conv = 0, nouter = 0;
     sgb_set_probe_stream_fixed(ctx(), 1);                       // the first nrun probes of every estimate are the same vectors
     ck(sgb_glmmkin_ai_pcg(ctx(), isQuantitative ? 1 : 0, y.memptr(), X.memptr(), p, offset.memptr(), alpha_fit0.memptr(),
                           eta_fit0.memptr(), tauInit.memptr(), maxiter, tol, nrun, tolPCG, maxiterPCG, traceCVcutoff, LOCO ? 1 : 0,
                           draw_probes_reseeding, nullptr, tau.memptr(), alpha.memptr(), eta.memptr(), mu.memptr(), Y.memptr(),
                           cov.memptr(), &conv, &nouter, Yl.memptr(), al.memptr(), el.memptr(), cl.memptr(), ml.memptr(),
-                          reinterpret_cast<int32_t *>(nit.memptr()), nullptr, nullptr));
+                          nit.data(), nullptr, nullptr));
     return Rcpp::List::create(Named("theta") = tau, Named("coefficients") = alpha, Named("linear.predictors") = eta,
                               Named("fitted.values") = mu, Named("Y") = Y, Named("cov") = cov, Named("converged") = conv != 0,
                               Named("LOCO.Y") = Yl, Named("LOCO.coefficients") = al, Named("LOCO.linear.predictors") = el,

@@ -117,3 +117,22 @@ def test_header_is_plain_c():
     hdr = os.path.join(ROOT, "include", "saige_b200.h")
     subprocess.check_call(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr])
     subprocess.check_call(["g++", "-fsyntax-only", "-x", "c++", "-Wall", "-Werror", hdr])
+
+
+def test_rcpp_shim_type_checks_against_the_header():
+    """R / Rcpp / Armadillo are not installed here, so the step-1 shim cannot be built for real; it is at least run through the
+    compiler's front end with declaration-only stand-ins for their classes (tests/stubs/RcppArmadillo.h), which checks every
+    sgb_* call of the shim -- name, arity, pointer and scalar types, callback signatures -- against include/saige_b200.h,
+    in the single-process and in the pbdMPI configuration."""
+    import subprocess
+    shim = os.path.join(ROOT, "rcpp_shim", "SAIGE_fitGLMM_fast_b200.cpp")
+    base = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-Werror", "-DUSE_SAIGE_B200",
+            "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + os.path.join(ROOT, "include"), shim]
+    subprocess.check_call(base)
+    subprocess.check_call(base + ["-DUSE_pbdMPI"])
+    # every export of the header that the step-1 R path needs is referenced by the shim
+    src = open(shim).read()
+    for sym in ("sgb_setgeno", "sgb_get_coefficients", "sgb_get_ai_score", "sgb_get_ai_score_q", "sgb_fit_glmmai_rpcg", "sgb_fit_glmmai_rpcg_q",
+                "sgb_get_sigma_x", "sgb_get_sigma_g", "sgb_set_diag_of_stdgeno_loco", "sgb_get_coef", "sgb_glmmkin_ai_pcg",
+                "sgb_variance_ratio_markers", "sgb_set_probe_stream_fixed"):
+        assert sym in src, sym
