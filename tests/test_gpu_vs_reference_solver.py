@@ -1,0 +1,106 @@
+"""The CUDA library against the REFERENCE'S OWN solver code (oracle/_ref/libfg_ref64.so: getPCG1ofSigmaAndVector,
+getCoefficients, GetTrace, getAIScore, fitglmmaiRPCG and the _q / _LOCO variants compiled unmodified from
+SAIGE_fitGLMM_fast.cpp:2322-3662 with `float` read as `double`; see tests/test_reference_solver.py and oracle/Makefile).
+The reference code gets its GRM product and diagonal from the CPU oracle; everything above the product is the reference's text.
+
+north_star tolerances: PCG solutions / coefficients / tau <= 1e-6 relative, PCG iteration counts identical."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_solver as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(64), reason="oracle/_ref/libfg_ref64.so not built")]
+TOL = 1e-6
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def trio(grm10k, golden_dir):
+    from oracle import oracle as O
+    from saige_gpu_b200 import SaigeB200, step1
+    N0, M0 = grm10k["N0"], grm10k["M0"]
+    o = O.OracleGeno(); o.minMAF, o.maxMissing = 0.01, 0.15
+    o.setgeno(grm10k["bed"], N0, M0, np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+    g = SaigeB200(device=0)
+    g.setminMAFforGRM(0.01); g.setmaxMissingRateforGRM(0.15)
+    p = grm10k["prefix"]
+    g.setgeno(p + ".bed", p + ".bim", p + ".fam", np.arange(1, N0 + 1), np.ones(N0, np.uint8))
+    probes = step1.ProbeStream(o.N, nmax=200, seed=200)
+    rows = [l.split() for l in open(os.path.join(golden_dir, "pheno_1000samples.txt")).readlines()]
+    col = {h: i for i, h in enumerate(rows[0])}
+    yb = np.array([float(r[col["y_binary"]]) for r in rows[1:]])
+    yq = np.array([float(r[col["y_quantitative"]]) for r in rows[1:]])
+    X = np.column_stack([np.ones(N0), [float(r[col["x1"]]) for r in rows[1:]], [float(r[col["x2"]]) for r in rows[1:]]])
+    chrq = np.array([int(c) for c in grm10k["chrs"]])[o.qc_mask]
+    _, s, e = O.updateChrStartEndIndexVec(chrq)
+    o.setStartEndIndexVec(s, e); o.set_Diagof_StdGeno_LOCO()
+    step1.set_loco_ranges(g, chrq); g.set_Diagof_StdGeno_LOCO()
+    yield g, o, R.RefSolver(o, 64, probes.U), probes, yb, yq, X
+    g.close()
+
+
+def test_pcg_and_coefficients_vs_reference_code(trio):
+    g, o, r, probes, yb, yq, X = trio
+    rng = np.random.default_rng(11)
+    w = rng.uniform(0.02, 0.25, size=o.N); tau = np.array([1.0, 0.45]); B = rng.normal(size=(o.N, 4))
+    Xg, itg = g.getPCG1ofSigmaAndVector(w, tau, B, 500, 1e-5, return_iter=True)
+    for c in range(B.shape[1]):
+        xr, itr = r.getPCG1ofSigmaAndVector(w, tau, B[:, c], 500, 1e-5, return_iter=True)
+        assert int(itg[c]) == itr and rel(Xg[:, c], xr) < TOL
+    Y = rng.normal(size=o.N) + 1.0
+    a, b = g.getCoefficients(Y, X, w, tau, 500, 1e-5), r.getCoefficients(Y, X, w, tau, 500, 1e-5)
+    for key in ("Sigma_iY", "Sigma_iX", "cov", "alpha", "eta"):
+        assert rel(a[key], b[key]) < TOL, key
+    for c in (2, 17):                                  # leave-one-chromosome-out: getCoefficients_LOCO
+        r.set_loco_chromosome(c); g.setStartEndIndex(g._loco_start[c], g._loco_end[c], c)
+        a, b = g.getCoefficients(Y, X, w, tau, 500, 1e-5, loco=True), r.getCoefficients(Y, X, w, tau, 500, 1e-5, loco=True)
+        for key in ("Sigma_iY", "Sigma_iX", "cov", "alpha", "eta"):
+            assert rel(a[key], b[key]) < TOL, (c, key)
+
+
+@pytest.mark.parametrize("cvcut", [0.0025, 3e-4])
+def test_ai_score_and_tau_update_vs_reference_code(trio, cvcut):
+    g, o, r, probes, yb, yq, X = trio
+    W = np.random.default_rng(12).uniform(0.05, 0.25, size=o.N); tau = np.array([1.0, 0.3])
+    c = r.getCoefficients(yb, X, W, tau, 500, 1e-5)
+    a = g.getAIScore(yb, X, W, tau, c["Sigma_iY"], c["Sigma_iX"], c["cov"], 30, 500, 1e-5, cvcut, probes.fresh())
+    b = r.getAIScore(yb, X, W, tau, c["Sigma_iY"], c["Sigma_iX"], c["cov"], 30, 500, 1e-5, cvcut)
+    assert a["nrun_used"] == b["nrun_used"]
+    for key in ("YPAPY", "Trace", "AI", "PY"):
+        assert rel(a[key], b[key]) < TOL, key
+    tg = g.fitglmmaiRPCG(yb, X, W, tau, c["Sigma_iY"], c["Sigma_iX"], c["cov"], 30, 500, 1e-5, 0.02, cvcut, probes.fresh())["tau"]
+    assert rel(tg, r.fitglmmaiRPCG(yb, X, W, tau, c["Sigma_iY"], c["Sigma_iX"], c["cov"], 30, 500, 1e-5, 0.02, cvcut)) < TOL
+    # quantitative trait
+    Wq = np.ones(o.N); tq = np.array([0.6, 0.3])
+    cq = r.getCoefficients(yq, X, Wq, tq, 500, 1e-5)
+    a = g.getAIScore_q(yq, X, Wq, tq, cq["Sigma_iY"], cq["Sigma_iX"], cq["cov"], 30, 500, 1e-5, cvcut, probes.fresh())
+    b = r.getAIScore_q(yq, X, Wq, tq, cq["Sigma_iY"], cq["Sigma_iX"], cq["cov"], 30, 500, 1e-5, cvcut)
+    assert a["nrun_used"] == b["nrun_used"]
+    for key in ("YPAPY", "YPA0PY", "Trace", "AI", "PY"):
+        assert rel(a[key], b[key]) < TOL, key
+    tg = g.fitglmmaiRPCG_q(yq, X, Wq, tq, cq["Sigma_iY"], cq["Sigma_iX"], cq["cov"], 30, 500, 1e-5, 0.02, cvcut, probes.fresh())["tau"]
+    assert rel(tg, r.fitglmmaiRPCG(yq, X, Wq, tq, cq["Sigma_iY"], cq["Sigma_iX"], cq["cov"], 30, 500, 1e-5, 0.02, cvcut, quant=True)) < TOL
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+@pytest.mark.parametrize("native", [False, True])
+def test_whole_fit_vs_reference_code(trio, trait, native):
+    """tau and alpha of the whole null-GLMM fit: the GPU library (per-export driver and one-call driver) against the R-level loop
+    run over the reference's compiled C++ exports."""
+    from oracle import oracle as O
+    from saige_gpu_b200 import step1
+    g, o, r, probes, yb, yq, X = trio
+    fam_o, fam_g, y = (O.Binomial, step1.Binomial, yb) if trait == "binary" else (O.Gaussian, step1.Gaussian, yq)
+    want = R.fit_through_reference(o, r, O.glm_fit(y, X, fam_o), probes.U, trait)
+    got = step1.glmmkin_ai_PCG(g, step1.glm_fit(y, X, fam_g), probes, trait=trait, native_loops=native)
+    g.setProbeStreamFixed(False)
+    assert got["converged"] == want["converged"]
+    assert rel(got["theta"], want["theta"]) < TOL
+    assert rel(got["coefficients"], want["coefficients"]) < TOL
+    assert rel(got["fitted_values"], want["fitted_values"]) < TOL
