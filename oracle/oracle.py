@@ -7,9 +7,12 @@ Heavy loops (ingest/QC/repack, decode, GRM.vector, diag) live in saige_oracle.c;
 matvec is restated here in numpy fp64, one function per reference function, citing
 /root/reference/src/SAIGE/src/SAIGE_fitGLMM_fast.cpp ("FG.cpp") and src/SAIGE/R/SAIGE_fitGLMM_fast.R ("FG.R").
 
-Parity status: decode/allele counts/QC are pinned by the reference's .frq fixture (tests/test_oracle_golden.py).
-PCG / AI-REML call boundaries have no golden vectors in the reference and the reference cannot be built in
-this environment => PARITY UNPINNED above the matvec (restated from the source text).
+Parity status: decode/allele counts/QC are pinned by the reference's .frq / .acount fixtures (tests/test_oracle_golden.py).
+The solver / AI-REML functions below (getDiagOfSigma ... fitglmmaiRPCG_q) are pinned to the reference's OWN code: 18 functions of
+FG.cpp:2322-3662 are cut out of the reference tree at build time and compiled unmodified into oracle/_ref/libfg_ref{64,32}.so
+(oracle/Makefile, oracle/ref_fg/, binding oracle/ref_solver.py); tests/test_reference_solver.py holds identical PCG iteration
+counts and <= 1e-9 on every output and on the whole fit.  What stays restated from the source text only: the R-level driver
+(Get_Coef, the outer AI-REML loop, the LOCO loop, extractVarianceRatio; R is not available here).
 """
 import ctypes as C
 import os

@@ -12,8 +12,8 @@
  * Parity pins (tests/test_oracle_golden.py):
  *   - decode + allele counts + MAF filter  <-> extdata/input/plinkforGRM_1000samples_10kMarkers.frq (exact)
  *   - fp32 reference-order matvec vs fp64 matvec (informational, ~1e-6)
- *   - everything above the matvec (PCG / AI-REML) is restated in numpy (oracle/oracle.py); those
- *     call boundaries have no golden vectors in the reference => "parity unpinned" there.
+ *   - everything above the matvec (PCG / AI-REML) is restated in numpy (oracle/oracle.py) and pinned there to the
+ *     reference's own functions, compiled unmodified into oracle/_ref/libfg_ref{64,32}.so (tests/test_reference_solver.py).
  *
  * Two arithmetic modes for the matvec:
  *   mode 0 ("fp64")   : f = AC/(2N) and s = 1/sqrt(2f(1-f)) evaluated in double from the integer allele

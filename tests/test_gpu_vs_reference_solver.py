@@ -57,7 +57,8 @@ def test_pcg_and_coefficients_vs_reference_code(trio):
     a, b = g.getCoefficients(Y, X, w, tau, 500, 1e-5), r.getCoefficients(Y, X, w, tau, 500, 1e-5)
     for key in ("Sigma_iY", "Sigma_iX", "cov", "alpha", "eta"):
         assert rel(a[key], b[key]) < TOL, key
-    for c in (2, 17):                                  # leave-one-chromosome-out: getCoefficients_LOCO
+    have = [c for c in range(len(g._loco_start)) if g._loco_start[c] != -1]
+    for c in (have[1], have[-1]):                      # leave-one-chromosome-out: getCoefficients_LOCO
         r.set_loco_chromosome(c); g.setStartEndIndex(g._loco_start[c], g._loco_end[c], c)
         a, b = g.getCoefficients(Y, X, w, tau, 500, 1e-5, loco=True), r.getCoefficients(Y, X, w, tau, 500, 1e-5, loco=True)
         for key in ("Sigma_iY", "Sigma_iX", "cov", "alpha", "eta"):
