@@ -102,11 +102,74 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_baseline_reference(N, M, target_s=12.0, msample=8192, steps=None, warmup=1):
+    """The reference's OWN CPU matvec: genoClass + parallelCrossProd (the OpenMP marker loop, SAIGE_fitGLMM_fast.cpp:37-1183,
+    1576-1708) compiled unmodified into oracle/_ref/libfg_refcpu.so (oracle/Makefile), fed a PLINK fileset of `msample` synthetic
+    markers x all N samples through its own reader, on all host cores.  The full-workload figure is the sample time scaled linearly
+    in M (the loop is a sum over markers) and says so."""
+    import tempfile
+    from oracle import oracle as O
+    from oracle import ref_solver as R
+    bed = O.synth_bed(N, msample, SEED)
+    d = tempfile.mkdtemp(prefix="saige_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    prefix = os.path.join(d, "sample")
+    try:
+        with open(prefix + ".bed", "wb") as f:
+            f.write(bytes([0x6C, 0x1B, 0x01]))
+            f.write(np.ascontiguousarray(bed, dtype=np.uint8).tobytes())
+        with open(prefix + ".bim", "w") as f:
+            f.writelines("1\tsnp%d\t0\t%d\tA\tC\n" % (m, m + 1) for m in range(msample))
+        with open(prefix + ".fam", "w") as f:
+            f.writelines("f%d i%d 0 0 1 -9\n" % (i, i) for i in range(N))
+        del bed
+        r = R.RefCPU()
+        r.L.fgref_set_num_threads(host_cores())
+        cores = r.L.fgref_num_threads()
+        t_in = time.time()
+        r.setgeno(prefix + ".bed", prefix + ".bim", prefix + ".fam", np.arange(1, N + 1), np.ones(N, np.uint8), minMAF=0.01, maxMissing=0.15)
+        t_in = time.time() - t_in
+    finally:
+        for ext in (".bed", ".bim", ".fam"):
+            if os.path.exists(prefix + ext):
+                os.unlink(prefix + ext)
+        os.rmdir(d)
+    b = np.random.default_rng(1).integers(0, 2, N) * 2.0 - 1.0
+    for _ in range(max(1, warmup)):
+        r.getCrossprodMatAndKin(b)
+    times = []
+    t0 = time.time()
+    while True:
+        t1 = time.perf_counter()
+        r.getCrossprodMatAndKin(b)
+        times.append(time.perf_counter() - t1)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.time() - t0 > target_s or len(times) >= 50:
+            break
+    per_sample = float(np.sum(times)) / len(times)
+    scale = M / r.M
+    return {"value": 1.0 / (per_sample * scale), "unit": "matvecs/s", "cores": int(cores), "kind": "reference",
+            "sample": "%d of %d markers x %d samples through the reference's own genoClass + parallelCrossProd (fp32, OpenMP marker loop, "
+                      "%d threads; compiled unmodified from SAIGE_fitGLMM_fast.cpp into oracle/_ref/libfg_refcpu.so), %d timed sample steps, "
+                      "scaled linearly in M (x%.1f)" % (r.M, M, N, cores, len(times), scale),
+            "extrapolated": True, "scale_in_markers": scale, "sample_steps": len(times), "reference_setgeno_s": t_in,
+            "s_per_sample_matvec": per_sample, "s_per_sample_matvec_median": float(np.median(times)),
+            "s_timed_total": float(np.sum(times))}
+
+
 def cpu_baseline(N, M, target_s=12.0, msample=8192, steps=None, warmup=1):
-    """Reference CPU matvec (fp32, reference operation order: the marker loop of parallelCrossProdOpenMP, FG.cpp:1576-1598) on a
-    bounded marker sample of the same workload, on ALL host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, so the
-    thread count is set explicitly through the oracle.  One "sample step" = one matvec over `msample` markers x all N samples;
-    the full-workload figure is that time scaled linearly in M (the loop is a sum over markers) and says so."""
+    """CPU baseline on a bounded marker sample of the same workload, on ALL host cores (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, so the thread count is set explicitly).  kind "reference": the reference's own compiled CPU path when
+    oracle/_ref/libfg_refcpu.so is there (it travels with the snapshot); else kind "port": the oracle's fp32 reference-order matvec
+    (the marker loop of parallelCrossProdOpenMP, FG.cpp:1576-1598, restated in oracle/saige_oracle.c).  One "sample step" = one
+    matvec over `msample` markers x all N samples; the full-workload figure is that time scaled linearly in M and says so."""
+    from oracle import ref_solver as R
+    if R.available("cpu"):
+        # the reference's own PLINK reader is single-threaded (~45 M genotypes/s: genoClass::setGenoObj decodes, counts and re-packs
+        # marker by marker), so its marker sample is kept to ~1.6e9 genotypes: ~35 s of ingest before the timed matvecs
+        ref_sample = max(1024, min(msample, int(1.6e9 // max(N, 1)) // 1024 * 1024))
+        return cpu_baseline_reference(N, M, target_s=target_s, msample=ref_sample, steps=steps, warmup=warmup)
     from oracle import oracle as O
     O.lib().orc_set_num_threads(host_cores())
     cores = O.lib().orc_num_threads()

@@ -6,7 +6,7 @@ compiles it against oracle/ref_fg/mini_arma.h.  The whole file cannot be built h
 cuBLAS), these functions can: they only need vector algebra, the genotype object's diagonal and the GRM product, which the shim
 supplies.
 
-usage: extract_ref.py <SAIGE_fitGLMM_fast.cpp> <out.inc>"""
+usage: extract_ref.py <SAIGE_fitGLMM_fast.cpp> <out.inc> [solver|cpu]"""
 import re
 import sys
 
@@ -30,6 +30,26 @@ WANT = [
     r"arma::fvec GetTrace_q\(arma::fmat Sigma_iX, arma::fmat& Xmat, arma::fvec& wVec, arma::fvec& tauVec, arma::fmat& cov1,  int nrun, int maxiterPCG, float tolPCG, float traceCVcutoff\)\{",
     r"Rcpp::List getAIScore_q\(arma::fvec& Yvec, arma::fmat& Xmat, arma::fvec& wVec,  arma::fvec& tauVec,",
     r"Rcpp::List fitglmmaiRPCG_q\(arma::fvec& Yvec, arma::fmat& Xmat, arma::fvec &wVec,  arma::fvec &tauVec,",
+]
+
+
+# the genotype store and the CPU product (built only into libfg_refcpu.so): the whole genoClass, the OpenMP marker loop and the
+# small exports that configure / query it
+WANT_CPU = [
+    r"class genoClass\{",
+    r"arma::fvec parallelCrossProdOpenMP\(int startIndex, int endIndex, arma::fcolvec &bVec, int &count\)",
+    r"arma::fvec parallelCrossProd\(arma::fcolvec & bVec\) \{",
+    r"arma::fvec parallelCrossProd_full\(arma::fcolvec & bVec, int & markerNum\) \{",
+    r"arma::fvec parallelCrossProd_LOCO\(arma::fcolvec & bVec\) \{",
+    r"void setgeno\(std::string bedfile, std::string bimfile, std::string famfile, std::vector<int> & subSampleInGeno, std::vector<bool> & indicatorGenoSamplesWithPheno, float memoryChunk, bool isDiagofKinSetAsOne\)",
+    r"arma::ivec Get_OneSNP_Geno\(int SNPIdx\)",
+    r"arma::ivec Get_OneSNP_Geno_forVarRatio\(int SNPIdx\)",
+    r"void setStartEndIndex\(int startIndex, int endIndex, int chromIndex\)\{",
+    r"void setStartEndIndexVec\( arma::ivec & startIndex_vec,  arma::ivec & endIndex_vec\)\{",
+    r"void setminMAFforGRM\(float minMAFforGRM\)\{",
+    r"void setmaxMissingRateforGRM\(float maxMissingforGRM\)\{",
+    r"void set_Diagof_StdGeno_LOCO\(\)\{",
+    r"void setminMAC_VarianceRatio\(float t_minMACVarRatio, float t_maxMACVarRatio, bool t_isVarianceRatioinGeno\)\{",
 ]
 
 
@@ -58,17 +78,22 @@ def function_end(text, start):
     raise SystemExit("unbalanced braces after offset %d" % start)
 
 
-def main(src, out):
+def main(src, out, which="solver"):
     text = open(src, encoding="utf-8", errors="replace").read()
     parts = []
-    for pat in WANT:
+    for pat in (WANT_CPU if which == "cpu" else WANT):
         hits = [m for m in re.finditer("^" + pat, text, flags=re.M)]
         if len(hits) != 1:
             raise SystemExit("expected exactly one definition matching %r, found %d" % (pat, len(hits)))
         s = hits[0].start()
         e = function_end(text, s)
+        if pat.startswith("class "):
+            e = text.index(";", e) + 1                          # the class definition ends with "};"
+            tail = "\n// the reference's global instance (FG.cpp:1188)\ngenoClass geno;\n"
+        else:
+            tail = ""
         line0 = text.count("\n", 0, s) + 1
-        parts.append("// ---- %s:%d-%d ----\n%s\n" % (src, line0, line0 + text.count("\n", s, e), text[s:e]))
+        parts.append("// ---- %s:%d-%d ----\n%s\n%s" % (src, line0, line0 + text.count("\n", s, e), text[s:e], tail))
     with open(out, "w") as f:
         f.write("// GENERATED at build time by oracle/ref_fg/extract_ref.py from the reference tree; not part of the repository.\n")
         f.write("\n".join(parts))
@@ -76,4 +101,4 @@ def main(src, out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "solver")

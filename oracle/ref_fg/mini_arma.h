@@ -21,7 +21,13 @@ typedef unsigned long long uword;
 
 template <typename T> struct Col;
 template <typename T> struct Mat;
+namespace fill { struct zeros_t {}; static const zeros_t zeros = zeros_t(); }
+struct distr_param { long long a, b; distr_param(long long a_, long long b_) : a(a_), b(b_) {} };
 
+// s * v, not yet evaluated: Armadillo's expression templates fuse `acc += s * v` into one pass without a temporary, and the
+// reference's marker loop (FG.cpp:1591) lives on exactly that statement -- a stand-in that allocated N floats per marker there
+// would make the reference look slower than it is.  Everywhere else the product is simply materialised.
+template <typename T> struct Scaled { T s; const Col<T> *v; };
 template <typename T> struct RowView { const Col<T> *v; };            // v.t()
 template <typename T> struct ElemView {                                // v.elem(idx)
     Col<T> *v; std::vector<uword> idx;
@@ -33,9 +39,22 @@ template <typename T> struct Col {
     uword n_elem = 0;
     Col() {}
     template <typename I, ARMA_INTEG(I)> explicit Col(I n) : d((size_t)n, T(0)), n_elem((uword)n) {}
+    template <typename I, ARMA_INTEG(I)> Col(I n, fill::zeros_t) : d((size_t)n, T(0)), n_elem((uword)n) {}
     void zeros() { std::fill(d.begin(), d.end(), T(0)); }
+    template <typename I, ARMA_INTEG(I)> void zeros(I n) { d.assign((size_t)n, T(0)); n_elem = (uword)n; }
     void clear() { d.clear(); n_elem = 0; }
     template <typename I> void resize(I n) { d.resize((size_t)n, T(0)); n_elem = (uword)n; }
+    template <typename I> void set_size(I n) { d.resize((size_t)n); n_elem = (uword)n; }
+    Col(const Scaled<T> &e) : d(e.v->n_elem), n_elem(e.v->n_elem) { for (uword i = 0; i < n_elem; i++) d[i] = e.s * e.v->d[i]; }
+    Col &operator+=(const Scaled<T> &e)
+    {
+        if (e.v->n_elem != n_elem) throw std::logic_error("mini_arma: += on vectors of different length");
+        const T s = e.s; const T *x = e.v->d.data(); T *y = d.data();
+        for (uword i = 0; i < n_elem; i++) y[i] += s * x[i];
+        return *this;
+    }
+    Col &operator+=(const Col &o) { if (o.n_elem != n_elem) throw std::logic_error("mini_arma: += on vectors of different length"); for (uword i = 0; i < n_elem; i++) d[i] += o.d[i]; return *this; }
+    Col &operator-=(const Col &o) { if (o.n_elem != n_elem) throw std::logic_error("mini_arma: -= on vectors of different length"); for (uword i = 0; i < n_elem; i++) d[i] -= o.d[i]; return *this; }
     template <typename I> T &operator()(I i) { return d[(size_t)i]; }
     template <typename I> const T &operator()(I i) const { return d[(size_t)i]; }
     template <typename I> T &operator[](I i) { return d[(size_t)i]; }
@@ -65,7 +84,14 @@ template <typename T> Col<T> operator-(const Col<T> &a, const Col<T> &b) { retur
 template <typename T> Col<T> operator%(const Col<T> &a, const Col<T> &b) { return zip(a, b, [](T x, T y) { return x * y; }); }
 template <typename T> Col<T> operator/(const Col<T> &a, const Col<T> &b) { return zip(a, b, [](T x, T y) { return x / y; }); }
 template <typename T, typename S, ARMA_ARITH(S)> Col<T> operator*(const Col<T> &a, S s) { return map(a, [s](T x) { return x * (T)s; }); }
-template <typename T, typename S, ARMA_ARITH(S)> Col<T> operator*(S s, const Col<T> &a) { return map(a, [s](T x) { return (T)s * x; }); }
+template <typename T, typename S, ARMA_ARITH(S)> Scaled<T> operator*(S s, const Col<T> &a) { return Scaled<T>{(T)s, &a}; }
+template <typename T> Col<T> operator+(const Col<T> &a, const Scaled<T> &b) { Col<T> r = a; r += b; return r; }
+template <typename T> Col<T> operator-(const Col<T> &a, const Scaled<T> &b) { Col<T> r = a; r += Scaled<T>{-b.s, b.v}; return r; }
+template <typename T> Col<T> operator+(const Scaled<T> &a, const Scaled<T> &b) { Col<T> r(a); r += b; return r; }
+template <typename T> Col<T> operator+(const Scaled<T> &a, const Col<T> &b) { Col<T> r(a); r += b; return r; }
+template <typename T> Col<T> operator/(const Scaled<T> &a, const Col<T> &b) { return Col<T>(a) / b; }
+template <typename T, typename S, ARMA_ARITH(S)> Col<T> operator/(const Scaled<T> &a, S s) { return Col<T>(a) / s; }
+template <typename T> Col<T> operator%(const Scaled<T> &a, const Col<T> &b) { return Col<T>(a) % b; }
 template <typename T, typename S, ARMA_ARITH(S)> Col<T> operator/(const Col<T> &a, S s) { return map(a, [s](T x) { return x / (T)s; }); }
 template <typename T, typename S, ARMA_ARITH(S)> Col<T> operator/(S s, const Col<T> &a) { return map(a, [s](T x) { return (T)s / x; }); }
 template <typename T, typename S, ARMA_ARITH(S)> Col<T> operator+(const Col<T> &a, S s) { return map(a, [s](T x) { return x + (T)s; }); }
@@ -75,6 +101,34 @@ template <typename T, typename S, ARMA_ARITH(S)> uvec operator<(const Col<T> &a,
 {
     uvec r(a.n_elem);
     for (uword i = 0; i < a.n_elem; i++) r.d[i] = a.d[i] < (T)s ? 1 : 0;
+    return r;
+}
+struct SizeMat { uword r, c; uword operator[](int i) const { return i == 0 ? r : c; } };
+template <typename T> SizeMat size(const Col<T> &v) { return SizeMat{v.n_elem, 1}; }
+template <typename T, typename S, ARMA_ARITH(S)> uvec operator==(const Col<T> &a, S s)
+{
+    uvec r(a.n_elem);
+    for (uword i = 0; i < a.n_elem; i++) r.d[i] = a.d[i] == (T)s ? 1 : 0;
+    return r;
+}
+inline bool any(const uvec &m) { for (uword x : m.d) if (x) return true; return false; }
+template <typename T> Col<T> sort(Col<T> v) { std::sort(v.d.begin(), v.d.end()); return v; }
+template <typename T> Col<T> unique(Col<T> v)
+{
+    std::sort(v.d.begin(), v.d.end());
+    v.d.erase(std::unique(v.d.begin(), v.d.end()), v.d.end());
+    v.n_elem = v.d.size();
+    return v;
+}
+// arma::randi(n, distr_param(a, b)): the reference draws its variance-ratio hold-out candidates with it (FG.cpp:866-868).  A
+// parity harness must see the SAME draw on every side, so the stand-in returns the vector its caller installed.
+inline std::vector<long long> &randi_supply() { static std::vector<long long> v; return v; }
+inline Col<long long> randi(long long n, const distr_param &)
+{
+    Col<long long> r;
+    r.d = randi_supply();
+    r.n_elem = r.d.size();
+    (void)n;
     return r;
 }
 inline uvec find(const uvec &m)
@@ -116,6 +170,7 @@ template <typename T> struct Mat {
     template <typename I, typename J> T &operator()(I i, J j) { return d[(size_t)i + (size_t)j * n_rows]; }
     template <typename I, typename J> const T &operator()(I i, J j) const { return d[(size_t)i + (size_t)j * n_rows]; }
     template <typename I> ColView<T> col(I j) { return ColView<T>{this, (uword)j}; }
+    template <typename I, typename J> void zeros(I r, J c) { d.assign((size_t)r * (size_t)c, T(0)); n_rows = (uword)r; n_cols = (uword)c; n_elem = n_rows * n_cols; }
     Mat t() const
     {
         Mat r(n_cols, n_rows);
@@ -137,6 +192,8 @@ template <typename T> ColView<T> &ColView<T>::operator=(const Col<T> &v)
     for (uword i = 0; i < m->n_rows; i++) (*m)(i, j) = v.d[i];
     return *this;
 }
+template <typename T> Col<T> operator+(const ColView<T> &a, const Col<T> &b) { return Col<T>(a) + b; }
+template <typename T> Col<T> operator-(const Col<T> &a, const ColView<T> &b) { return a - Col<T>(b); }
 template <typename T> Col<T> operator*(const Mat<T> &A, const Col<T> &x)
 {
     if (A.n_cols != x.n_elem) throw std::logic_error("mini_arma: matrix * vector dimension mismatch");

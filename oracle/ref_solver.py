@@ -19,7 +19,8 @@ DP = C.c_void_p
 
 
 def available(bits=64):
-    return os.path.exists(os.path.join(_HERE, "_ref", "libfg_ref%d.so" % bits))
+    """bits: 64 / 32 = the solver layer over the oracle's product; "cpu" = the reference's whole CPU path (libfg_refcpu.so)"""
+    return os.path.exists(os.path.join(_HERE, "_ref", "libfg_ref%s.so" % bits))
 
 
 def _p(a):
@@ -37,22 +38,9 @@ class RefSolver:
     def __init__(self, geno, bits=64, U=None):
         self.L = C.CDLL(os.path.join(_HERE, "_ref", "libfg_ref%d.so" % bits))
         L = self.L
-        L.fgref_last_error.restype = C.c_char_p
-        L.fgref_log.restype = C.c_char_p
-        L.fgref_cal_cv.restype = C.c_double
-        L.fgref_draws_used.restype = C.c_long
-        L.fgref_cal_cv.argtypes = [DP, C.c_int]
+        self._signatures()
         L.fgref_set_problem.argtypes = [C.c_int, C.c_int, DP, C.c_int, CB]
         L.fgref_set_loco.argtypes = [DP, C.c_int, C.c_int, CB]
-        L.fgref_set_draws.argtypes = [DP, C.c_long]
-        L.fgref_diag_of_sigma.argtypes = [DP, DP, C.c_int, DP]
-        L.fgref_pcg.argtypes = [DP, DP, DP, C.c_int, C.c_double, C.c_int, DP]
-        L.fgref_get_coefficients.argtypes = [DP, DP, C.c_int, DP, DP, C.c_int, C.c_double, C.c_int, DP, DP, DP, DP, DP]
-        L.fgref_get_ai_score.argtypes = [C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_double, DP, DP]
-        L.fgref_fit_glmmai_rpcg.argtypes = [C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_double,
-                                            C.c_double]
-        L.fgref_get_sigma_x.argtypes = [DP, DP, DP, C.c_int, C.c_int, C.c_double, DP]
-        L.fgref_get_sigma_g.argtypes = [DP, DP, DP, C.c_int, C.c_double, DP]
         assert L.fgref_real_bytes() == bits // 8
         self.g, self.N = geno, geno.N
         self.products = 0
@@ -72,6 +60,23 @@ class RefSolver:
         self._draws = None
         if U is not None:
             self.set_probes(U)
+
+    def _signatures(self):
+        L = self.L
+        L.fgref_last_error.restype = C.c_char_p
+        L.fgref_log.restype = C.c_char_p
+        L.fgref_cal_cv.restype = C.c_double
+        L.fgref_draws_used.restype = C.c_long
+        L.fgref_cal_cv.argtypes = [DP, C.c_int]
+        L.fgref_set_draws.argtypes = [DP, C.c_long]
+        L.fgref_diag_of_sigma.argtypes = [DP, DP, C.c_int, DP]
+        L.fgref_pcg.argtypes = [DP, DP, DP, C.c_int, C.c_double, C.c_int, DP]
+        L.fgref_get_coefficients.argtypes = [DP, DP, C.c_int, DP, DP, C.c_int, C.c_double, C.c_int, DP, DP, DP, DP, DP]
+        L.fgref_get_ai_score.argtypes = [C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_double, DP, DP]
+        L.fgref_fit_glmmai_rpcg.argtypes = [C.c_int, DP, DP, C.c_int, DP, DP, DP, DP, DP, C.c_int, C.c_int, C.c_double, C.c_double,
+                                            C.c_double]
+        L.fgref_get_sigma_x.argtypes = [DP, DP, DP, C.c_int, C.c_int, C.c_double, DP]
+        L.fgref_get_sigma_g.argtypes = [DP, DP, DP, C.c_int, C.c_double, DP]
 
     def set_probes(self, U):
         self._draws = _f(((np.asarray(U) + 1.0) / 2.0).T.reshape(-1))        # column after column
@@ -154,6 +159,110 @@ class RefSolver:
         w, tau, G, out = _f(w), _f(tau), _f(G), np.zeros(self.N)
         self._ck(self.L.fgref_get_sigma_g(_p(w), _p(tau), _p(G), int(maxiterPCG), float(tolPCG), _p(out)))
         return out
+
+
+class RefCPU(RefSolver):
+    """oracle/_ref/libfg_refcpu.so: the reference's own CPU path END TO END, as shipped (fp32) -- genoClass (FG.cpp:37-1183: PLINK
+    reader, QC, imputation, re-pack, standardised genotypes, diagonals), the OpenMP marker loop parallelCrossProd (FG.cpp:1576-1851)
+    and the solver layer on top of it.  Nothing here comes from the oracle: files in, tau out, all reference text."""
+
+    def __init__(self, U=None):
+        # the reference keeps its genotype store in a file-global object that setgeno fills once per process (FG.cpp:1188); every
+        # RefCPU therefore loads its own private copy of the library
+        import shutil
+        import tempfile
+        self._tmp = tempfile.NamedTemporaryFile(prefix="libfg_refcpu_", suffix=".so", delete=False)
+        self._tmp.close()
+        shutil.copyfile(os.path.join(_HERE, "_ref", "libfg_refcpu.so"), self._tmp.name)
+        self.L = C.CDLL(self._tmp.name)
+        os.unlink(self._tmp.name)                      # the mapping stays valid; nothing is left behind
+        L = self.L
+        RefSolver._signatures(self)
+        L.fgref_setgeno.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, DP, C.c_int, DP, C.c_int, C.c_double, C.c_double, C.c_int,
+                                    C.c_double, C.c_double, C.c_int, DP, C.c_int]
+        for f in ("fgref_N", "fgref_M_qc", "fgref_M_raw", "fgref_M_vr"):
+            getattr(L, f).restype = C.c_long
+        L.fgref_one_snp_geno.argtypes = [C.c_int, C.c_int, DP]
+        L.fgref_one_snp_stdgeno.argtypes = [C.c_int, DP]
+        L.fgref_crossprod.argtypes = [DP, C.c_int, DP]
+        L.fgref_set_start_end_index_vec.argtypes = [DP, DP, C.c_int]
+        L.fgref_set_start_end_index.argtypes = [C.c_int, C.c_int, C.c_int]
+        assert L.fgref_real_bytes() == 4
+        self._draws = None
+        self.N = 0
+        self._U = U
+
+    def setgeno(self, bedfile, bimfile, famfile, subSampleInGeno, indicator, minMAF=0.0, maxMissing=1.0, isVarRatio=False,
+                minMACvr=20.0, maxMACvr=-1.0, isDiagofKinSetAsOne=False, vr_rand_idx=None):
+        sub = np.ascontiguousarray(subSampleInGeno, dtype=np.int32)
+        ind = np.ascontiguousarray(indicator, dtype=np.uint8)
+        vr = np.ascontiguousarray([] if vr_rand_idx is None else vr_rand_idx, dtype=np.int64)
+        self._ck(self.L.fgref_setgeno(bedfile.encode(), bimfile.encode(), famfile.encode(), _p(sub), len(sub), _p(ind), len(ind),
+                                      float(minMAF), float(maxMissing), int(isVarRatio), float(minMACvr), float(maxMACvr),
+                                      int(isDiagofKinSetAsOne), _p(vr), len(vr)))
+        self.N, self.M, self.M0, self.Mvr = self.L.fgref_N(), self.L.fgref_M_qc(), self.L.fgref_M_raw(), self.L.fgref_M_vr()
+        self.L.fgref_clear_log()
+        if self._U is not None:
+            self.set_probes(self._U)
+
+    def _vec(self, fn, n, dtype=np.float64):
+        out = np.zeros(max(n, 1), dtype=dtype)
+        fn(_p(out))
+        return out[:n]
+
+    def getAlleleFreqVec(self):
+        return self._vec(self.L.fgref_allele_freq, self.M)
+
+    def getInvStdVec(self):
+        return self._vec(self.L.fgref_inv_std, self.M)
+
+    def getMACVec(self):
+        return self._vec(self.L.fgref_mac, self.M, np.int64)
+
+    def getQCdMarkerIndex(self):
+        return self._vec(self.L.fgref_qc_mask, self.M0, np.uint8).astype(bool)
+
+    def getIndexVec_forVarRatio(self):
+        return self._vec(self.L.fgref_vr_index, self.Mvr, np.int64)
+
+    def getMACVec_forVarRatio(self):
+        return self._vec(self.L.fgref_vr_mac, self.Mvr, np.int64)
+
+    def Get_OneSNP_Geno(self, idx, vr=False):
+        out = np.zeros(self.N, dtype=np.int64)
+        self._ck(self.L.fgref_one_snp_geno(int(idx), int(vr), _p(out)))
+        return out
+
+    def Get_OneSNP_StdGeno(self, idx):
+        out = np.zeros(self.N)
+        self._ck(self.L.fgref_one_snp_stdgeno(int(idx), _p(out)))
+        return out
+
+    def Get_Diagof_StdGeno(self):
+        out = np.zeros(self.N)
+        self._ck(self.L.fgref_diag_stdgeno(_p(out)))
+        return out
+
+    def getCrossprodMatAndKin(self, b, loco=False):
+        b, out = _f(b), np.zeros(self.N)
+        self._ck(self.L.fgref_crossprod(_p(b), int(loco), _p(out)))
+        return out
+
+    def getCrossprodMatAndKin_LOCO(self, b):
+        return self.getCrossprodMatAndKin(b, loco=True)
+
+    def setStartEndIndexVec(self, start, end):
+        s, e = np.ascontiguousarray(start, dtype=np.int64), np.ascontiguousarray(end, dtype=np.int64)
+        self._ck(self.L.fgref_set_start_end_index_vec(_p(s), _p(e), len(s)))
+
+    def setStartEndIndex(self, start, end, chromIndex):
+        self._ck(self.L.fgref_set_start_end_index(int(start), int(end), int(chromIndex)))
+
+    def set_Diagof_StdGeno_LOCO(self):
+        self._ck(self.L.fgref_set_diag_loco())
+
+    def set_loco_chromosome(self, c):
+        raise NotImplementedError("use setStartEndIndex: this build holds the reference's own genotype object")
 
 
 def fit_through_reference(o, r, fit0, U, trait, **kw):

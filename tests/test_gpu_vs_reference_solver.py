@@ -105,3 +105,46 @@ def test_whole_fit_vs_reference_code(trio, trait, native):
     assert rel(got["theta"], want["theta"]) < TOL
     assert rel(got["coefficients"], want["coefficients"]) < TOL
     assert rel(got["fitted_values"], want["fitted_values"]) < TOL
+
+
+@pytest.mark.skipif(not R.available("cpu"), reason="oracle/_ref/libfg_refcpu.so not built")
+def test_ingest_and_product_vs_reference_cpu_path(tmp_path, grm10k):
+    """The CUDA library against the reference's own CPU path (oracle/_ref/libfg_refcpu.so: genoClass + parallelCrossProd compiled
+    unmodified), both reading the same PLINK files: QC mask / MAC / genotypes / variance-ratio hold-out bit-exact, allele
+    frequencies equal as the floats the reference stores, products to the reference's fp32 accuracy."""
+    from oracle import oracle as O
+    from saige_gpu_b200 import SaigeB200
+    from tests_support import write_plink
+    N0, M0 = 1237, 3000
+    bed = O.synth_bed(N0, M0, seed=77, miss_rate=0.02)
+    rng = np.random.default_rng(4)
+    keep = np.sort(rng.choice(N0, size=1001, replace=False))
+    sub = rng.permutation(keep) + 1
+    ind = np.zeros(N0, np.uint8); ind[keep] = 1
+    vr = np.unique(rng.integers(0, M0, size=200))
+    prefix = str(tmp_path / "cohort")
+    write_plink(prefix, bed, N0, M0)
+    cases = [(prefix, sub, ind, 0.06, 0.03, True, vr), (grm10k["prefix"], np.arange(1, 1001), np.ones(1000, np.uint8), 0.01, 0.15, False, None)]
+    for pre, s_, i_, maf, miss, isvr, vridx in cases:
+        r = R.RefCPU()
+        r.setgeno(pre + ".bed", pre + ".bim", pre + ".fam", s_, i_, minMAF=maf, maxMissing=miss, isVarRatio=isvr, vr_rand_idx=vridx)
+        g = SaigeB200(device=0)
+        try:
+            g.setminMAFforGRM(maf); g.setmaxMissingRateforGRM(miss); g.setminMAC_VarianceRatio(20, -1, isvr)
+            g.setgeno(pre + ".bed", pre + ".bim", pre + ".fam", s_, i_, vr_rand_idx=vridx)
+            assert (g.N, g.M, g.Mvr) == (r.N, r.M, r.Mvr)
+            assert np.array_equal(g.getQCdMarkerIndex(), r.getQCdMarkerIndex())
+            assert np.array_equal(g.getMACVec(), r.getMACVec())
+            assert np.array_equal(g.getAlleleFreqVec().astype(np.float32), r.getAlleleFreqVec().astype(np.float32))
+            for i in range(0, g.M, 211):
+                assert np.array_equal(g.Get_OneSNP_Geno(i), r.Get_OneSNP_Geno(i)), i
+            if isvr:
+                assert np.array_equal(g.getIndexVec_forVarRatio(), r.getIndexVec_forVarRatio())
+                assert np.array_equal(g.getMACVec_forVarRatio(), r.getMACVec_forVarRatio())
+                for i in range(0, g.Mvr, 9):
+                    assert np.array_equal(g.Get_OneSNP_Geno_forVarRatio(i), r.Get_OneSNP_Geno(i, vr=True)), i
+            b = rng.normal(size=g.N)
+            assert rel(g.getCrossprodMatAndKin(b), r.getCrossprodMatAndKin(b)) < 2e-6
+            assert rel(g.get_DiagofKin() * g.M, r.Get_Diagof_StdGeno()) < 1e-5
+        finally:
+            g.close()
