@@ -896,6 +896,8 @@ struct sgb_step2 {
     uint8_t *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
     double *pout[2] = {nullptr, nullptr}; size_t pout_bytes = 0;      // capacities tracked apart: the chunk length depends on n_fam
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;               // H2D of chunk c+1 runs here while h->stream works on chunk c
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};        // "rows of buffer i have arrived" (recorded on copy_stream)
     // batched score sums (tensor engine): limb images of the model columns, built once per model
     int kv = 0;                           // value-plane columns: A (p) | mu2 X (p) | res | mu2
     int64_t stride = 0;                   // packed bytes per variant row of the tiled chunk store (multiple of 64)
@@ -1104,8 +1106,8 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
     if (n_markers <= 0) return 0;
     const int64_t B0 = (n_fam + 3) / 4;
     if (B0 > 200 * 1024) return sgb_fail(h, "step2: more than 819,200 samples in the .fam are not supported yet");
-    // chunks of <= 1 GB of raw rows, double-buffered: the H2D of chunk c+1 and the D2H of chunk c-1's results overlap the kernels
-    // of chunk c.  The chunk is this large for the flagged variants: a saddle-point variant keeps one CTA busy for milliseconds
+    // chunks of <= 1 GB of raw rows, double-buffered: the H2D of chunk c+1 (on its own copy stream, one event per buffer) overlaps
+    // the kernels of chunk c on h->stream.  The chunk is this large for the flagged variants: a saddle-point variant keeps one CTA busy for milliseconds
     // (~20 passes over all samples), so the per-variant kernel only fills the machine (444 resident CTAs) when a chunk holds
     // >= ~10^4 variants of which ~5 % are flagged (measured: 43 us per flagged variant with 256 MB chunks at N = 200k)
     // at most 65,024 variants per chunk: the re-pack / gather kernels index the variant with blockIdx.y (<= 65,535)
@@ -1124,6 +1126,8 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
         s->pout_bytes = obytes;
     }
     for (int i = 0; i < 2; i++) if (!s->ev[i]) CUDA_OK(h, cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) if (!s->ev_up[i]) CUDA_OK(h, cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+    if (!s->copy_stream) CUDA_OK(h, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     SGB_TRY(sgb_ensure(h, (void **)&s->d_bed, &s->bed_bytes, 2 * cbytes));
     size_t ob = s->out_elems * sizeof(double);
     SGB_TRY(sgb_ensure(h, (void **)&s->d_out, &ob, 2 * obytes));
@@ -1165,7 +1169,11 @@ extern "C" int sgb_step2_test_markers(sgb_ctx *h, const uint8_t *bed_rows, int64
         if (!rows_pinned) s2_par_copy(s->pin[cur], bed_rows + (size_t)m0 * B0, (size_t)nm * B0);
         uint8_t *db = s->d_bed + cur * cbytes;
         double *dout = s->d_out + cur * (size_t)chunk * S2_NOUT;
-        CUDA_OK(h, cudaMemcpyAsync(db, rows_pinned ? bed_rows + (size_t)m0 * B0 : s->pin[cur], (size_t)nm * B0, cudaMemcpyHostToDevice, h->stream));
+        // db was last read by the kernels of chunk c-2 (finished: ev[cur] above), so the copy engine may refill it while
+        // chunk c-1's kernels still run on h->stream
+        CUDA_OK(h, cudaMemcpyAsync(db, rows_pinned ? bed_rows + (size_t)m0 * B0 : s->pin[cur], (size_t)nm * B0, cudaMemcpyHostToDevice, s->copy_stream));
+        CUDA_OK(h, cudaEventRecord(s->ev_up[cur], s->copy_stream));
+        CUDA_OK(h, cudaStreamWaitEvent(h->stream, s->ev_up[cur], 0));
         h->cnt.bytes_h2d += nm * B0;
         if (batched) {
             SGB_RANGE("step2_chunk_batched");
@@ -1262,7 +1270,8 @@ void sgb_step2_free(sgb_ctx *h)
     void *more[] = {s->d_V, s->d_csum, s->d_Lv, s->d_Li, s->d_multv, s->d_multi, s->d_lsv, s->d_lsi, s->d_gath, s->d_tiled, s->d_accv, s->d_acci,
                     s->d_raw, s->d_cnt, s->d_list, s->d_spa};
     for (auto q : more) if (q) cudaFree(q);
-    for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); }
+    for (int i = 0; i < 2; i++) { if (s->pin[i]) cudaFreeHost(s->pin[i]); if (s->pout[i]) cudaFreeHost(s->pout[i]); if (s->ev[i]) cudaEventDestroy(s->ev[i]); if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]); }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
     h->step2 = nullptr;
 }

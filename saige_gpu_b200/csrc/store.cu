@@ -65,12 +65,18 @@ sgb_prof_scope::~sgb_prof_scope()
 int sgb_ensure(sgb_ctx *h, void **p, size_t *cur, size_t need)
 {
     if (*cur >= need && *p) return 0;
+    const bool prof = sgb_prof_enabled();
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    const double t0 = prof ? prof_now() : 0.0;
+    const size_t had = *cur;
     if (*p) CUDA_OK(h, cudaFree(*p));
     *p = nullptr; *cur = 0;
+    const double t1 = prof ? prof_now() : 0.0;
     size_t want = need + need / 8 + 256;
     CUDA_OK(h, cudaMalloc(p, want));
     *cur = want;
+    if (prof) fprintf(stderr, "[sgb] %*s(re)allocation %.1f -> %.1f MB: cudaFree %.3f ms, cudaMalloc %.3f ms\n", 2 * g_prof_depth, "", had / 1048576.0,
+                      want / 1048576.0, t1 - t0, prof_now() - t1);
     return 0;
 }
 
