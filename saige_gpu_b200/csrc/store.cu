@@ -276,7 +276,7 @@ struct chunk_reader {     // yields raw marker rows [m0, m1) either from memory 
 };
 
 // Host -> device streaming of raw .bed rows through two pinned staging buffers: the host fill of piece i+1 (fread, or
-// a 4-thread memcpy from the caller's buffer) overlaps the asynchronous H2D copy of piece i.
+// a multi-thread memcpy from the caller's buffer) overlaps the asynchronous H2D copy of piece i.
 struct stager {
     sgb_ctx *h = nullptr;
     uint8_t *pin[2] = {nullptr, nullptr};
@@ -296,9 +296,16 @@ struct stager {
     {
         for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); pin[i] = nullptr; ev[i] = nullptr; }
     }
-    static void par_copy(uint8_t *dst, const uint8_t *src, size_t n)
+    // staging threads per rank: one thread copies ~6 GB/s and the copy engine takes ~50 GB/s, so up to 8 -- fewer when the ranks
+    // of one box would oversubscribe its cores
+    int host_threads() const
     {
-        const int nt = n > ((size_t)8 << 20) ? 4 : 1;
+        const int hw = (int)std::thread::hardware_concurrency(), per_rank = hw / std::max(1, h->world);
+        return std::max(2, std::min(8, per_rank));
+    }
+    void par_copy(uint8_t *dst, const uint8_t *src, size_t n) const
+    {
+        const int nt = n > ((size_t)8 << 20) ? host_threads() : 1;
         if (nt == 1) { memcpy(dst, src, n); return; }
         std::vector<std::thread> th;
         size_t per = (n + nt - 1) / nt;
@@ -318,9 +325,9 @@ struct stager {
             CUDA_OK(h, cudaEventSynchronize(ev[cur]));            // the previous H2D out of this buffer has finished
             if (rd.mem) par_copy(pin[cur], rd.mem + (size_t)m0 * B0 + off, n);
             else {
-                // marker i starts at byte 3 + B0*i of the file (FG.cpp:902); 4 threads pread disjoint slices
+                // marker i starts at byte 3 + B0*i of the file (FG.cpp:902); the staging threads pread disjoint slices
                 const off_t fo = 3 + (off_t)m0 * B0 + (off_t)off;
-                const int fd = fileno(rd.fp), nt = n > ((size_t)8 << 20) ? 4 : 1;
+                const int fd = fileno(rd.fp), nt = n > ((size_t)8 << 20) ? host_threads() : 1;
                 std::vector<std::thread> th;
                 std::vector<int> okv(nt, 1);
                 const size_t per = (n + nt - 1) / nt;
