@@ -590,9 +590,12 @@ def main():
             return dict(model=model, wall=wall, tim=tim, abi_s=abi_s, abi_calls=abi_calls, c=c, vr=vr, vr_n=len(vr_list), vr_s=vr_s,
                         loco=loco)
 
+        # the fit is timed on its second run: the first one also pays the library's scratch allocations for these batch widths, the
+        # first NCCL collectives of their sizes and whatever state the legs above left on the host (reported as first_call_wall_s)
+        rn_first = run_fit(True)
         rn = run_fit(True)
         model, c, tim = rn["model"], rn["c"], rn["tim"]
-        step1_info = {"wall_s": rn["wall"], "load_synth_s": t_load, "tau": [float(v) for v in model["theta"]],
+        step1_info = {"wall_s": rn["wall"], "first_call_wall_s": rn_first["wall"], "load_synth_s": t_load, "tau": [float(v) for v in model["theta"]],
                       "converged": bool(model["converged"]), "outer_iterations": int(model["n_outer"]),
                       "pcg_solves": c["n_pcg_solves"], "pcg_iterations": c["n_pcg_iterations"],
                       "product_columns": c["n_crossprod_columns"], "products": c["n_crossprod_calls"], "LOCO": bool(rn["loco"]),
