@@ -714,19 +714,29 @@ __device__ __forceinline__ bool stats_ticket(double s, unsigned long long m, int
     __syncthreads();
     return *last_flag != 0;
 }
-__device__ __forceinline__ double sum_partials_v(const double *part, int nblk)
+// Last block of a column: the partials of all blocks come in with ONE load per thread (a single thread walking the list paid a
+// full L2 round trip per element: ~0.13 ms for 256 partials, more than the rest of a narrow product's epilogue), then thread 0 adds
+// them in block order (the fixed order every engine and batch width shares) and thread 32 takes the maximum.
+// Returns the sum in thread 0 and the maximum in thread 32.  fin / finm: SGB_PART_BLOCKS elements of shared memory each.
+__device__ __forceinline__ void finish_column_partials(const double *psum_c, const unsigned long long *pmax_c, int nblk, double *fin,
+                                                       unsigned long long *finm, double *tot, unsigned long long *mxv)
 {
-    const volatile double *p = part;
-    double t = 0.0;
-    for (int i = 0; i < nblk; i++) t += p[i];
-    return t;
-}
-__device__ __forceinline__ unsigned long long max_partials_v(const unsigned long long *part, int nblk)
-{
-    const volatile unsigned long long *p = part;
-    unsigned long long t = 0;
-    for (int i = 0; i < nblk; i++) t = p[i] > t ? p[i] : t;
-    return t;
+    __syncthreads();                                                    // fin / finm may still be read by the previous column
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+        fin[i] = reinterpret_cast<const volatile double *>(psum_c)[i];
+        finm[i] = reinterpret_cast<const volatile unsigned long long *>(pmax_c)[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < nblk; i++) t += fin[i];
+        *tot = t;
+    }
+    if (threadIdx.x == 32) {
+        unsigned long long t = 0;
+        for (int i = 0; i < nblk; i++) t = finm[i] > t ? finm[i] : t;
+        *mxv = t;
+    }
 }
 
 // colsum[c] = sum V[:,c]; mx[c] = bits(max |V[:,c]|); the limb sums of the coming split are zeroed
@@ -751,8 +761,13 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const double *__restrict
     s = block_sum_256(s, sm);
     m = block_max_256(m, smx);
     if (!stats_ticket(s, m, c, psum, pmax, ticket, &last)) return;
-    if (threadIdx.x == 0) { colsum[c] = sum_partials_v(psum + (int64_t)c * SGB_PART_BLOCKS, gridDim.x); ticket[c] = 0; }
-    if (threadIdx.x == 32) mx[c] = max_partials_v(pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x);
+    __shared__ double fin[SGB_PART_BLOCKS];
+    __shared__ unsigned long long finm[SGB_PART_BLOCKS];
+    double tot = 0.0;
+    unsigned long long mxv = 0;
+    finish_column_partials(psum + (int64_t)c * SGB_PART_BLOCKS, pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x, fin, finm, &tot, &mxv);
+    if (threadIdx.x == 0) { colsum[c] = tot; ticket[c] = 0; }
+    if (threadIdx.x == 32) mx[c] = mxv;
     if (threadIdx.x >= 64 && threadIdx.x < 64 + nlimb) limbsum[c * nlimb + threadIdx.x - 64] = 0;
 }
 
@@ -800,14 +815,116 @@ __global__ void __launch_bounds__(256) recomb_post1_kernel(int32_t *__restrict__
     t = block_sum_256(t, sm);
     m = block_max_256(m, smx);
     if (!stats_ticket(t, m, c, psum, pmax, ticket, &last)) return;
+    __shared__ double fin[SGB_PART_BLOCKS];
+    __shared__ unsigned long long finm[SGB_PART_BLOCKS];
+    double tt = 0.0;
+    unsigned long long mxv = 0;
+    finish_column_partials(psum + (int64_t)c * SGB_PART_BLOCKS, pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x, fin, finm, &tt, &mxv);
     if (threadIdx.x == 0) {
-        double tt = sum_partials_v(psum + (int64_t)c * SGB_PART_BLOCKS, gridDim.x);
         t_out[c] = tt;
         if (t_out2) t_out2[c] = tt;
         ticket[c] = 0;
     }
-    if (threadIdx.x == 32) mx[c] = max_partials_v(pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x);
+    if (threadIdx.x == 32) mx[c] = mxv;
     if (threadIdx.x >= 64 && threadIdx.x < 64 + nlimb2) limbsum2[c * nlimb2 + threadIdx.x - 64] = 0;
+}
+
+// The same epilogue for the tcgen05 engine (NL = 5..7), TILED through shared memory: a block owns SGB_RCG consecutive columns and
+// moves a 256-row x (NL SGB_RCG)-word tile of the accumulators with 128-bit loads along the rows (<= 224 contiguous bytes per row),
+// zeroing it behind the loads, instead of NL scalar loads + NL scalar stores per (row, column) at a stride of one accumulator
+// row -- the column-per-block version spent 1.7 ms on a 31-column batch (0.45 GB of accumulators), ten times its HBM time.
+// Thread tid then finishes row tid of the tile column by column from shared memory (row stride NL SGB_RCG + 1 words: no bank
+// conflicts).  Rows -> threads -> blocks and the order of every sum are those of recomb_post1_kernel, so t_c and the column
+// maxima come out bit-identical.
+template <int NL>
+__global__ void __launch_bounds__(256) recomb_post1_wide_kernel(int32_t *__restrict__ acc, int64_t rows_pad, int64_t Mloc, int k, int pad,
+                                                                const double *__restrict__ mult, const int32_t *__restrict__ limbsum, int c0,
+                                                                const double *__restrict__ f2, const double *__restrict__ s2,
+                                                                const double *__restrict__ colsum, int64_t mask_lo, int64_t mask_hi,
+                                                                double *__restrict__ D, int64_t ld, double *__restrict__ psum,
+                                                                unsigned long long *__restrict__ pmax, unsigned int *__restrict__ ticket,
+                                                                double *__restrict__ t_out, double *__restrict__ t_out2,
+                                                                unsigned long long *__restrict__ mx, int32_t *__restrict__ limbsum2, int nlimb2)
+{
+    constexpr int WP = NL * SGB_RCG + 1;
+    extern __shared__ int32_t tile[];                                   // 256 rows x WP words
+    __shared__ double sm[8];
+    __shared__ unsigned long long smx[8];
+    __shared__ int last;
+    __shared__ int32_t ls[NL * SGB_RCG];
+    __shared__ double sbs[SGB_RCG], mus[SGB_RCG];
+    __shared__ double fin[SGB_PART_BLOCKS];
+    __shared__ unsigned long long finm[SGB_PART_BLOCKS];
+    const int cg0 = blockIdx.y * SGB_RCG, nc = k - cg0 < SGB_RCG ? k - cg0 : SGB_RCG;
+    const int w0 = NL * cg0, w1 = cg0 + SGB_RCG >= k ? pad : NL * (cg0 + SGB_RCG);
+    const int W4 = (w1 - w0) >> 2 < 2 * NL ? (w1 - w0) >> 2 : 2 * NL;   // 16-byte pieces per tile row (padding columns past NL SGB_RCG are never written)
+    if (threadIdx.x < NL * SGB_RCG) ls[threadIdx.x] = threadIdx.x < NL * nc ? limbsum[w0 + threadIdx.x] : 0;
+    if (threadIdx.x < SGB_RCG) {
+        sbs[threadIdx.x] = threadIdx.x < nc ? colsum[cg0 + threadIdx.x] : 0.0;
+        mus[threadIdx.x] = threadIdx.x < nc ? mult[cg0 + threadIdx.x] : 0.0;
+    }
+    double t[SGB_RCG];
+    unsigned long long m[SGB_RCG];
+#pragma unroll
+    for (int cc = 0; cc < SGB_RCG; cc++) { t[cc] = 0.0; m[cc] = 0; }
+    for (int64_t rb = (int64_t)blockIdx.x * 256; rb < rows_pad; rb += (int64_t)gridDim.x * 256) {
+        __syncthreads();                                                // the previous tile has been consumed (and ls / sbs / mus are visible)
+        // all loads of a thread first (independent, one DRAM round trip), then the shared-memory stores and the zeroing: with a
+        // load -> zero -> stash sequence per piece the in-order issue made every piece wait for the one before (ncu: 3 % issue
+        // slots used, long-scoreboard stalls, 3.2 ms for a 31-column batch)
+        int4 v[2 * NL];
+#pragma unroll
+        for (int i = 0; i < 2 * NL; i++)
+            if (i < W4) {
+                const int idx = threadIdx.x + 256 * i, row = idx / W4, q = idx - row * W4;
+                v[i] = *(reinterpret_cast<const int4 *>(acc + (rb + row) * pad + w0) + q);
+            }
+#pragma unroll
+        for (int i = 0; i < 2 * NL; i++)
+            if (i < W4) {
+                const int idx = threadIdx.x + 256 * i, row = idx / W4, q = idx - row * W4;
+                *(reinterpret_cast<int4 *>(acc + (rb + row) * pad + w0) + q) = make_int4(0, 0, 0, 0);
+                int32_t *d = tile + row * WP + 4 * q;
+                d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+            }
+        __syncthreads();
+        const int64_t r = rb + threadIdx.x;
+        if (r < Mloc) {
+            const int32_t *p = tile + threadIdx.x * WP;
+            const double f = f2[r], sc = s2[r];
+            const bool masked = r >= mask_lo && r < mask_hi;
+#pragma unroll
+            for (int cc = 0; cc < SGB_RCG; cc++)
+                if (cc < nc) {
+                    const double v = sgb_umma_value<NL>(p + NL * cc, ls + NL * cc, c0) * mus[cc];
+                    double d = sc * (v - f * sbs[cc]);
+                    if (masked) d = 0.0;
+                    D[r + (int64_t)(cg0 + cc) * ld] = d;
+                    t[cc] += f * d;
+                    const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(d));
+                    m[cc] = b > m[cc] ? b : m[cc];
+                }
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < SGB_RCG; cc++) {
+        if (cc >= nc) break;                                            // uniform over the block
+        const int c = cg0 + cc;
+        const double tt = block_sum_256(t[cc], sm);
+        const unsigned long long mm = block_max_256(m[cc], smx);
+        if (stats_ticket(tt, mm, c, psum, pmax, ticket, &last)) {
+            double tot = 0.0;
+            unsigned long long mxv = 0;
+            finish_column_partials(psum + (int64_t)c * SGB_PART_BLOCKS, pmax + (int64_t)c * SGB_PART_BLOCKS, gridDim.x, fin, finm, &tot, &mxv);
+            if (threadIdx.x == 0) {
+                t_out[c] = tot;
+                if (t_out2) t_out2[c] = tot;
+                ticket[c] = 0;
+            }
+            if (threadIdx.x == 32) mx[c] = mxv;
+            if (threadIdx.x >= 64 && threadIdx.x < 64 + nlimb2) limbsum2[c * nlimb2 + threadIdx.x - 64] = 0;
+        }
+    }
 }
 
 int k_recomb_post1(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, int pad, const double *d_mult, const int32_t *d_limbsum,
@@ -819,12 +936,20 @@ int k_recomb_post1(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, in
     unsigned long long *pmax = reinterpret_cast<unsigned long long *>(h->d_red) + 1024 * SGB_PART_BLOCKS;
     // the partial-sum pattern over the first Mloc rows must not depend on the padding: blocks as for Mloc elements
     int nb = k_grid_blocks(h, h->Mloc);
-    dim3 grid(nb, k);
+    dim3 grid(nb, k), gridw(nb, (k + SGB_RCG - 1) / SGB_RCG);
 #define RP1(NLV) recomb_post1_kernel<NLV><<<grid, 256, 0, h->stream>>>(acc, rows_pad, h->Mloc, pad, d_mult, d_limbsum, 2, h->d_f2, h->d_s2, d_colsum, \
                                                                        mask_lo, mask_hi, D, ld, psum, pmax, h->d_ticket, d_t, d_t2, mx, d_limbsum2, nlimb2)
-    switch (nl) { case 8: RP1(8); break; case 7: RP1(7); break; case 6: RP1(6); break; case 5: RP1(5); break;
+#define RP1W(NLV) do { \
+        constexpr size_t sb_ = (size_t)256 * (NLV * SGB_RCG + 1) * sizeof(int32_t); \
+        if (sgb_first_on_device(h->device, SGB_SITE_POST1_5 + NLV - 5)) \
+            CUDA_OK(h, cudaFuncSetAttribute(recomb_post1_wide_kernel<NLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_)); \
+        recomb_post1_wide_kernel<NLV><<<gridw, 256, sb_, h->stream>>>(acc, rows_pad, h->Mloc, k, pad, d_mult, d_limbsum, 2, h->d_f2, h->d_s2, d_colsum, \
+                                                                      mask_lo, mask_hi, D, ld, psum, pmax, h->d_ticket, d_t, d_t2, mx, d_limbsum2, nlimb2); \
+    } while (0)
+    switch (nl) { case 8: RP1(8); break; case 7: RP1W(7); break; case 6: RP1W(6); break; case 5: RP1W(5); break;
                   default: return sgb_fail(h, "recomb_post1: unsupported limb count %d", nl); }
 #undef RP1
+#undef RP1W
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -844,14 +969,42 @@ __global__ void __launch_bounds__(256) recomb_post2_kernel(int32_t *__restrict__
     else raw[i + (int64_t)c * ldr] = v;
 }
 
+// row-wide version for the tcgen05 engine (see recomb_post1_wide_kernel)
+template <int NL>
+__global__ void __launch_bounds__(256) recomb_post2_wide_kernel(int32_t *__restrict__ acc, int64_t rows_pad, int64_t N, int k, int pad,
+                                                                const double *__restrict__ mult, const int32_t *__restrict__ limbsum, int c0,
+                                                                const double *__restrict__ t, double inv_m, double *__restrict__ Y, int64_t ldy,
+                                                                double *__restrict__ raw, int64_t ldr)
+{
+    __shared__ int32_t ls[NL * SGB_RCG];
+    const int cg0 = blockIdx.y * SGB_RCG, nc = k - cg0 < SGB_RCG ? k - cg0 : SGB_RCG;
+    const int w0 = NL * cg0, w1 = cg0 + SGB_RCG >= k ? pad : NL * (cg0 + SGB_RCG), W4 = (w1 - w0) >> 2;
+    if (threadIdx.x < NL * SGB_RCG) ls[threadIdx.x] = threadIdx.x < NL * nc ? limbsum[w0 + threadIdx.x] : 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_pad) return;
+    int32_t a[NL * SGB_RCG];
+    sgb_take_row_digits<NL>(acc + i * pad + w0, W4, a);
+#pragma unroll
+    for (int cc = 0; cc < SGB_RCG; cc++)
+        if (cc < nc) {
+            const int c = cg0 + cc;
+            const double v = sgb_umma_value<NL>(a + NL * cc, ls + NL * cc, c0) * mult[c];
+            if (Y) { if (i < N) Y[i + (int64_t)c * ldy] = (v - t[c]) * inv_m; }
+            else raw[i + (int64_t)c * ldr] = v;
+        }
+}
+
 int k_recomb_post2(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, int pad, const double *d_mult, const int32_t *d_limbsum,
                    const double *d_t, double inv_m, double *Y, int64_t ldy, double *raw, int64_t ldr)
 {
-    dim3 grid((unsigned)cdiv(rows_pad, 256), k);
+    dim3 grid((unsigned)cdiv(rows_pad, 256), k), gridw((unsigned)cdiv(rows_pad, 256), (k + SGB_RCG - 1) / SGB_RCG);
 #define RP2(NLV) recomb_post2_kernel<NLV><<<grid, 256, 0, h->stream>>>(acc, rows_pad, h->N, pad, d_mult, d_limbsum, 2, d_t, inv_m, Y, ldy, raw, ldr)
-    switch (nl) { case 8: RP2(8); break; case 7: RP2(7); break; case 6: RP2(6); break; case 5: RP2(5); break;
+#define RP2W(NLV) recomb_post2_wide_kernel<NLV><<<gridw, 256, 0, h->stream>>>(acc, rows_pad, h->N, k, pad, d_mult, d_limbsum, 2, d_t, inv_m, Y, ldy, raw, ldr)
+    switch (nl) { case 8: RP2(8); break; case 7: RP2W(7); break; case 6: RP2W(6); break; case 5: RP2W(5); break;
                   default: return sgb_fail(h, "recomb_post2: unsupported limb count %d", nl); }
 #undef RP2
+#undef RP2W
     LAUNCH_CHECK(h);
     return 0;
 }

@@ -25,15 +25,15 @@ __device__ __forceinline__ double sgb_recombine_imma(int32_t *__restrict__ acc, 
 // mma.sync engine; fewer digits = a coarser fixed point, see sgb_set_rhs_limbs); acc layout [row][npad], column of
 // (c, l) = NL*c + l.  Zeroes the accumulators.
 // Exact integer sum (up to ~2^81), then ONE correctly rounded conversion: keep 62 leading bits plus a sticky bit.
+// sgb_umma_value: the value of ONE (row, column) from its NL digits `p` (any address space) and the column's limb sums `ls`.
 template <int NL>
-__device__ __forceinline__ double sgb_recombine_umma(int32_t *__restrict__ acc, int64_t r, int c, int npad, const int32_t *__restrict__ limbsum, int c0)
+__device__ __forceinline__ double sgb_umma_value(const int32_t *p, const int32_t *__restrict__ ls, int c0)
 {
-    int32_t *p = acc + r * npad + NL * c;
     long long x[7];
 #pragma unroll
     for (int l = 0; l < 7; l++) x[l] = 0;
 #pragma unroll
-    for (int l = 0; l < NL; l++) { x[l] = (long long)c0 * limbsum[c * NL + l] - (long long)p[l]; p[l] = 0; }
+    for (int l = 0; l < NL; l++) x[l] = (long long)c0 * ls[l] - (long long)p[l];
     const long long l4 = x[0] + (x[1] << 8) + (x[2] << 16) + (x[3] << 24);
     const long long h3 = x[4] + (x[5] << 8) + (x[6] << 16);
     const __int128 T = ((__int128)h3 << 32) + (__int128)l4;
@@ -44,8 +44,34 @@ __device__ __forceinline__ double sgb_recombine_umma(int32_t *__restrict__ acc, 
     const int shift = bits > 62 ? bits - 62 : 0;
     unsigned long long m = (unsigned long long)(a >> shift);
     if (shift && (a & ((((unsigned __int128)1) << shift) - 1))) m |= 1ull;
-    double v = scalbn((double)m, shift);
+    // (double)m is the one rounding; 2^shift (shift <= 66) scales it exactly
+    const double v = (double)m * __longlong_as_double((long long)(1023 + shift) << 52);
     return neg ? -v : v;
+}
+
+template <int NL>
+__device__ __forceinline__ double sgb_recombine_umma(int32_t *__restrict__ acc, int64_t r, int c, int npad, const int32_t *__restrict__ limbsum, int c0)
+{
+    int32_t *p = acc + r * npad + NL * c;
+    const double v = sgb_umma_value<NL>(p, limbsum + c * NL, c0);
+#pragma unroll
+    for (int l = 0; l < NL; l++) p[l] = 0;
+    return v;
+}
+
+// One row's digits of SGB_RCG consecutive columns (the accumulator words [w0, w0 + W), W a multiple of 8) with 128-bit loads,
+// the words zeroed behind them: the access pattern of the row-wide epilogues of wide batches.
+#define SGB_RCG 8
+template <int NL>
+__device__ __forceinline__ void sgb_take_row_digits(int32_t *__restrict__ acc_row, int W4, int32_t (&a)[NL * SGB_RCG])
+{
+    int4 *g = reinterpret_cast<int4 *>(acc_row);
+#pragma unroll
+    for (int q = 0; q < NL * SGB_RCG / 4; q++) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (q < W4) { v = g[q]; g[q] = make_int4(0, 0, 0, 0); }
+        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
 }
 
 // NL = 8: the mma.sync engine; NL = 5..7: the tcgen05 engine with NL digits
