@@ -969,29 +969,46 @@ __global__ void __launch_bounds__(256) recomb_post2_kernel(int32_t *__restrict__
     else raw[i + (int64_t)c * ldr] = v;
 }
 
-// row-wide version for the tcgen05 engine (see recomb_post1_wide_kernel)
+// tiled version for the tcgen05 engine (see recomb_post1_wide_kernel): one 256-row tile per block
 template <int NL>
 __global__ void __launch_bounds__(256) recomb_post2_wide_kernel(int32_t *__restrict__ acc, int64_t rows_pad, int64_t N, int k, int pad,
                                                                 const double *__restrict__ mult, const int32_t *__restrict__ limbsum, int c0,
                                                                 const double *__restrict__ t, double inv_m, double *__restrict__ Y, int64_t ldy,
                                                                 double *__restrict__ raw, int64_t ldr)
 {
+    constexpr int WP = NL * SGB_RCG + 1;
+    extern __shared__ int32_t tile[];                                   // 256 rows x WP words
     __shared__ int32_t ls[NL * SGB_RCG];
     const int cg0 = blockIdx.y * SGB_RCG, nc = k - cg0 < SGB_RCG ? k - cg0 : SGB_RCG;
-    const int w0 = NL * cg0, w1 = cg0 + SGB_RCG >= k ? pad : NL * (cg0 + SGB_RCG), W4 = (w1 - w0) >> 2;
+    const int w0 = NL * cg0, w1 = cg0 + SGB_RCG >= k ? pad : NL * (cg0 + SGB_RCG);
+    const int W4 = (w1 - w0) >> 2 < 2 * NL ? (w1 - w0) >> 2 : 2 * NL;
     if (threadIdx.x < NL * SGB_RCG) ls[threadIdx.x] = threadIdx.x < NL * nc ? limbsum[w0 + threadIdx.x] : 0;
+    const int64_t rb = (int64_t)blockIdx.x * 256;                       // rows_pad is a multiple of 256
+    int4 v[2 * NL];
+#pragma unroll
+    for (int i = 0; i < 2 * NL; i++)
+        if (i < W4) {
+            const int idx = threadIdx.x + 256 * i, row = idx / W4, q = idx - row * W4;
+            v[i] = *(reinterpret_cast<const int4 *>(acc + (rb + row) * pad + w0) + q);
+        }
+#pragma unroll
+    for (int i = 0; i < 2 * NL; i++)
+        if (i < W4) {
+            const int idx = threadIdx.x + 256 * i, row = idx / W4, q = idx - row * W4;
+            *(reinterpret_cast<int4 *>(acc + (rb + row) * pad + w0) + q) = make_int4(0, 0, 0, 0);
+            int32_t *d = tile + row * WP + 4 * q;
+            d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+        }
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows_pad) return;
-    int32_t a[NL * SGB_RCG];
-    sgb_take_row_digits<NL>(acc + i * pad + w0, W4, a);
+    const int64_t i = rb + threadIdx.x;
+    const int32_t *p = tile + threadIdx.x * WP;
 #pragma unroll
     for (int cc = 0; cc < SGB_RCG; cc++)
         if (cc < nc) {
             const int c = cg0 + cc;
-            const double v = sgb_umma_value<NL>(a + NL * cc, ls + NL * cc, c0) * mult[c];
-            if (Y) { if (i < N) Y[i + (int64_t)c * ldy] = (v - t[c]) * inv_m; }
-            else raw[i + (int64_t)c * ldr] = v;
+            const double val = sgb_umma_value<NL>(p + NL * cc, ls + NL * cc, c0) * mult[c];
+            if (Y) { if (i < N) Y[i + (int64_t)c * ldy] = (val - t[c]) * inv_m; }
+            else raw[i + (int64_t)c * ldr] = val;
         }
 }
 
@@ -999,8 +1016,14 @@ int k_recomb_post2(sgb_ctx *h, int nl, int32_t *acc, int64_t rows_pad, int k, in
                    const double *d_t, double inv_m, double *Y, int64_t ldy, double *raw, int64_t ldr)
 {
     dim3 grid((unsigned)cdiv(rows_pad, 256), k), gridw((unsigned)cdiv(rows_pad, 256), (k + SGB_RCG - 1) / SGB_RCG);
+    if (nl != 8 && rows_pad % 256) return sgb_fail(h, "recomb_post2: %lld accumulator rows are not a multiple of 256", (long long)rows_pad);
 #define RP2(NLV) recomb_post2_kernel<NLV><<<grid, 256, 0, h->stream>>>(acc, rows_pad, h->N, pad, d_mult, d_limbsum, 2, d_t, inv_m, Y, ldy, raw, ldr)
-#define RP2W(NLV) recomb_post2_wide_kernel<NLV><<<gridw, 256, 0, h->stream>>>(acc, rows_pad, h->N, k, pad, d_mult, d_limbsum, 2, d_t, inv_m, Y, ldy, raw, ldr)
+#define RP2W(NLV) do { \
+        constexpr size_t sb_ = (size_t)256 * (NLV * SGB_RCG + 1) * sizeof(int32_t); \
+        if (sgb_first_on_device(h->device, SGB_SITE_POST2_5 + NLV - 5)) \
+            CUDA_OK(h, cudaFuncSetAttribute(recomb_post2_wide_kernel<NLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_)); \
+        recomb_post2_wide_kernel<NLV><<<gridw, 256, sb_, h->stream>>>(acc, rows_pad, h->N, k, pad, d_mult, d_limbsum, 2, d_t, inv_m, Y, ldy, raw, ldr); \
+    } while (0)
     switch (nl) { case 8: RP2(8); break; case 7: RP2W(7); break; case 6: RP2W(6); break; case 5: RP2W(5); break;
                   default: return sgb_fail(h, "recomb_post2: unsupported limb count %d", nl); }
 #undef RP2

@@ -1,6 +1,5 @@
 set -x
 (timeout 1500 python -m pytest tests/ -m gpu -q -x > gpurun_out/r02_gputests_9.log 2>&1; echo rc=$? >> gpurun_out/r02_gputests_9.log); tail -5 gpurun_out/r02_gputests_9.log
-(timeout 600 python tools/sweep_bench.py 200000 500000 1,3,4,8,16,31 > gpurun_out/r02_sweep_wide_epi7.txt 2>&1); cat gpurun_out/r02_sweep_wide_epi7.txt
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches_wide_epi.csv python tools/sweep_bench.py 200000 500000 4,31 > gpurun_out/r02_sweep_under_ncu.log 2>&1)
 python - <<'PY'
 import csv,collections
