@@ -296,13 +296,9 @@ struct stager {
     {
         for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); pin[i] = nullptr; ev[i] = nullptr; }
     }
-    // staging threads per rank: one thread copies ~6 GB/s and the copy engine takes ~50 GB/s, so up to 8 -- fewer when the ranks
-    // of one box would oversubscribe its cores
-    int host_threads() const
-    {
-        const int hw = (int)std::thread::hardware_concurrency(), per_rank = hw / std::max(1, h->world);
-        return std::max(2, std::min(8, per_rank));
-    }
+    // four staging threads per rank: eight were measured no faster on one GPU (21.2 against 20.9 GB/s) and slower on two
+    // (14.5 against 24.7 GB/s: the ranks' threads then compete for the host's memory bandwidth)
+    int host_threads() const { return 4; }
     void par_copy(uint8_t *dst, const uint8_t *src, size_t n) const
     {
         const int nt = n > ((size_t)8 << 20) ? host_threads() : 1;
