@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "sgb_internal.h"
 #include "recombine.cuh"
 
@@ -397,49 +398,59 @@ __global__ void __launch_bounds__(256) split_limbs_umma_wide_kernel(const double
                                                                     int64_t nblk, const unsigned long long *__restrict__ mx,
                                                                     int8_t *__restrict__ L, double *__restrict__ mult, int32_t *__restrict__ limbsum)
 {
-    extern __shared__ __align__(16) uint8_t img[];                      // ngroups x 1024 bytes
-    const int64_t blk = blockIdx.x;
+    extern __shared__ __align__(16) uint8_t img[];                      // ngroups x 1024 bytes, then NL k limb sums of this block
+    int32_t *lsum = reinterpret_cast<int32_t *>(img + (size_t)ngroups * 1024);
     const int nq = ngroups * 64;                                        // 16-byte pieces of the image
-    for (int i = threadIdx.x; i < nq; i += 256) reinterpret_cast<int4 *>(img)[i] = make_int4(0, 0, 0, 0);
-    __syncthreads();
     const int col = threadIdx.x & 31, w = col >> 2, q = col & 3;
     constexpr int SH = 8 * NL - 3;
-    const int64_t i0 = blk * UMMA_KBLK + 16 * w + ((q & 1) ? 8 : 0) + ((q & 2) ? 1 : 0);
-    for (int cb = 0; cb < k; cb += 8) {
-        const int c = cb + (threadIdx.x >> 5);
-        if (c >= k) continue;                                           // warp-uniform
-        const unsigned long long mb = mx[c];
-        int E = (int)((mb >> 52) & 0x7FF) - 1023;
-        if (E < -1000) E = -1000;
-        if (E > 1000) E = 1000;
-        if (blk == 0 && col == 0) mult[c] = mb ? scalbn(1.0, E - SH) : 0.0;
-        long long qv[4];
-#pragma unroll
-        for (int sl = 0; sl < 4; sl++) {
-            const int64_t i = i0 + 2 * sl;
-            qv[sl] = (i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], SH - E)) : 0;
-        }
-#pragma unroll
-        for (int l = 0; l < NL; l++) {
-            uint32_t word = 0;
-            int ssum = 0;
+    for (int i = threadIdx.x; i < NL * k; i += 256) lsum[i] = 0;
+    // A block walks over several k-blocks and keeps the limb sums in shared memory: one global atomic per (column, digit) and
+    // BLOCK.  One per k-block (3908 x 217 atomics on 217 neighbouring words = a handful of L2 slices) took 0.3 of the 0.37 ms
+    // this kernel needed for 31 columns x 500k markers.
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        __syncthreads();                                                // the previous image has been written out; lsum is zeroed
+        for (int i = threadIdx.x; i < nq; i += 256) reinterpret_cast<int4 *>(img)[i] = make_int4(0, 0, 0, 0);
+        __syncthreads();
+        const int64_t i0 = blk * UMMA_KBLK + 16 * w + ((q & 1) ? 8 : 0) + ((q & 2) ? 1 : 0);
+        for (int cb = 0; cb < k; cb += 8) {
+            const int c = cb + (threadIdx.x >> 5);
+            if (c >= k) continue;                                       // warp-uniform
+            const unsigned long long mb = mx[c];
+            int E = (int)((mb >> 52) & 0x7FF) - 1023;
+            if (E < -1000) E = -1000;
+            if (E > 1000) E = 1000;
+            if (blk == 0 && col == 0) mult[c] = mb ? scalbn(1.0, E - SH) : 0.0;
+            long long qv[4];
 #pragma unroll
             for (int sl = 0; sl < 4; sl++) {
-                const int d = (int)((qv[sl] + 128) & 255) - 128;
-                qv[sl] = (qv[sl] - d) >> 8;
-                word |= (uint32_t)(d & 255) << (8 * sl);
-                ssum += d;
+                const int64_t i = i0 + 2 * sl;
+                qv[sl] = (i < len && mb) ? __double2ll_rn(scalbn(V[(int64_t)c * ld + i], SH - E)) : 0;
             }
-            const int n = NL * c + l;
-            *reinterpret_cast<uint32_t *>(img + (n >> 3) * 1024 + w * 128 + (n & 7) * 16 + 4 * q) = word;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-            if (col == 0 && ssum) atomicAdd(&limbsum[c * NL + l], ssum);
+            for (int l = 0; l < NL; l++) {
+                uint32_t word = 0;
+                int ssum = 0;
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) {
+                    const int d = (int)((qv[sl] + 128) & 255) - 128;
+                    qv[sl] = (qv[sl] - d) >> 8;
+                    word |= (uint32_t)(d & 255) << (8 * sl);
+                    ssum += d;
+                }
+                const int n = NL * c + l;
+                *reinterpret_cast<uint32_t *>(img + (n >> 3) * 1024 + w * 128 + (n & 7) * 16 + 4 * q) = word;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                if (col == 0 && ssum) lsum[c * NL + l] += ssum;         // (column, digit) belongs to this warp alone
+            }
         }
+        __syncthreads();
+        int4 *dst = reinterpret_cast<int4 *>(L + blk * (int64_t)ngroups * 1024);
+        for (int i = threadIdx.x; i < nq; i += 256) dst[i] = reinterpret_cast<const int4 *>(img)[i];
     }
     __syncthreads();
-    int4 *dst = reinterpret_cast<int4 *>(L + blk * (int64_t)ngroups * 1024);
-    for (int i = threadIdx.x; i < nq; i += 256) dst[i] = reinterpret_cast<const int4 *>(img)[i];
+    for (int i = threadIdx.x; i < NL * k; i += 256)
+        if (lsum[i]) atomicAdd(&limbsum[i], lsum[i]);
 }
 
 // raw[r + c*ld] = (c0 * limbsum - sum_l acc[r][NL c+l] 256^l) * mult[c];  the accumulators are reset for the next product
@@ -515,10 +526,16 @@ int k_split_limbs_umma(sgb_ctx *h, const double *V, int64_t len, int64_t ld, int
     }
     if (wide) {
         if (nblk == 0) return 0;
-        const size_t sb = (size_t)(npad / 8) * 1024;
-        if (nl == 7) split_limbs_umma_wide_kernel<7><<<(unsigned)nblk, 256, sb, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
-        else if (nl == 6) split_limbs_umma_wide_kernel<6><<<(unsigned)nblk, 256, sb, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
-        else split_limbs_umma_wide_kernel<5><<<(unsigned)nblk, 256, sb, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
+        const size_t sb = (size_t)(npad / 8) * 1024 + sizeof(int32_t) * nl * k;        // <= 48 KB + 1.5 KB
+        const unsigned gb = (unsigned)std::min<int64_t>(nblk, (int64_t)h->sm_count * 4);
+        if (sb > 48 * 1024 && sgb_first_on_device(h->device, SGB_SITE_SPLIT_UMMA)) {
+            CUDA_OK(h, cudaFuncSetAttribute(split_limbs_umma_wide_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
+            CUDA_OK(h, cudaFuncSetAttribute(split_limbs_umma_wide_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
+            CUDA_OK(h, cudaFuncSetAttribute(split_limbs_umma_wide_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
+        }
+        if (nl == 7) split_limbs_umma_wide_kernel<7><<<gb, 256, sb, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
+        else if (nl == 6) split_limbs_umma_wide_kernel<6><<<gb, 256, sb, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
+        else split_limbs_umma_wide_kernel<5><<<gb, 256, sb, h->stream>>>(V, len, ld, k, npad / 8, nblk, mx, L, d_mult, d_limbsum);
         UMMA_LAUNCH_CHECK(h);
         return 0;
     }

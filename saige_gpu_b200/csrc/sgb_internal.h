@@ -233,7 +233,7 @@ int k_grid_blocks(sgb_ctx *h, int64_t n);
 
 // cudaFuncSetAttribute acts on the current device: every launch site that raises a kernel's dynamic shared-memory limit
 // does so once per device ordinal (a process may hold handles on several devices), not once per process
-enum sgb_attr_site { SGB_SITE_REPACK = 0, SGB_SITE_UMMA, SGB_SITE_STEP2, SGB_SITE_STREAM1, SGB_SITE_STREAM2, SGB_SITE_POST1_5, SGB_SITE_POST1_6, SGB_SITE_POST1_7, SGB_SITE_POST2_5, SGB_SITE_POST2_6, SGB_SITE_POST2_7, SGB_SITE_SYMV_BASE /* + KC, KC <= 8 */, SGB_SITE_COUNT = SGB_SITE_SYMV_BASE + 9 };
+enum sgb_attr_site { SGB_SITE_REPACK = 0, SGB_SITE_UMMA, SGB_SITE_STEP2, SGB_SITE_STREAM1, SGB_SITE_STREAM2, SGB_SITE_POST1_5, SGB_SITE_POST1_6, SGB_SITE_POST1_7, SGB_SITE_POST2_5, SGB_SITE_POST2_6, SGB_SITE_POST2_7, SGB_SITE_SPLIT_UMMA, SGB_SITE_SYMV_BASE /* + KC, KC <= 8 */, SGB_SITE_COUNT = SGB_SITE_SYMV_BASE + 9 };
 inline bool sgb_first_on_device(int device, int site)
 {
     static unsigned char done[SGB_SITE_COUNT][64];
