@@ -176,3 +176,93 @@ def test_tcgen05_engine_uses_seven_byte_limbs():
         assert to_double(T) == float(T)                       # Python's int -> float is correctly rounded
     for T in [2 ** 80 + 1, 2 ** 80 + 2 ** 27, 2 ** 80 + 2 ** 27 + 1, -(2 ** 81) - 3, 2 ** 53 + 1, 2 ** 62 + 2 ** 8 + 1]:
         assert to_double(T) == float(T)
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05-engine epilogues (recomb_post{1,2}_wide_kernel, kernels.cu) and limb split (pk2_umma.cu): index algebra of the
+# column groups / tile pieces and the one-rounding recombination (recombine.cuh), emulated on the CPU
+# ---------------------------------------------------------------------------------------------------
+RCG = 8          # SGB_RCG: right-hand-side columns per block
+
+
+def _npad(k, nl):
+    return (nl * k + 15) & ~15
+
+
+def _group_pieces(k, nl, gy):
+    """(w0, W4, nc) of column group gy exactly as the wide kernels compute them"""
+    pad = _npad(k, nl)
+    cg0 = gy * RCG
+    nc = min(RCG, k - cg0)
+    w0 = nl * cg0
+    w1 = pad if cg0 + RCG >= k else nl * (cg0 + RCG)
+    W4 = min((w1 - w0) >> 2, 2 * nl)
+    return w0, W4, nc, pad
+
+
+def test_wide_epilogue_groups_cover_every_digit_once_and_stay_aligned():
+    for nl in (5, 6, 7):
+        for k in range(1, 61):
+            pad = _npad(k, nl)
+            ngroups = (k + RCG - 1) // RCG
+            seen = np.zeros(pad, dtype=np.int32)
+            for gy in range(ngroups):
+                w0, W4, nc, _ = _group_pieces(k, nl, gy)
+                assert 1 <= nc <= RCG
+                assert (w0 * 4) % 16 == 0, "tile row starts on a 16-byte boundary"       # 128-bit loads
+                assert (pad * 4) % 64 == 0                                                 # accumulator row stride
+                assert 0 < W4 <= 2 * nl and w0 + 4 * W4 <= pad, "pieces stay inside the accumulator row"
+                assert 4 * W4 >= nl * nc, "every digit of the group's columns is inside the tile"
+                seen[w0:w0 + 4 * W4] += 1
+                # the tile piece -> (row, q) map of a 256-row tile: every (row, q) exactly once
+                idx = np.arange(256 * W4)
+                row, q = idx // W4, idx % W4
+                assert len(set(zip(row.tolist(), q.tolist()))) == 256 * W4 and row.max() == 255
+            assert np.all(seen[:nl * k] == 1), (nl, k)         # real digits: loaded and zeroed exactly once
+            assert np.all(seen <= 1)                           # padding words: at most once (they are always zero)
+
+
+def _umma_value(digits_acc, limbsum, c0):
+    """sgb_umma_value: exact integer sum, 62 leading bits + sticky bit, ONE rounding, exact power-of-two scaling"""
+    x = [c0 * int(ls) - int(a) for ls, a in zip(limbsum, digits_acc)]
+    T = sum(v << (8 * l) for l, v in enumerate(x))
+    neg, a = T < 0, abs(T)
+    bits = a.bit_length()
+    shift = max(0, bits - 62)
+    m = a >> shift
+    if shift and (a & ((1 << shift) - 1)):
+        m |= 1
+    v = float(m) * float(2 ** shift)             # float(m): round-to-nearest-even of a < 2^63 integer
+    return -v if neg else v
+
+
+def test_umma_recombination_is_the_correctly_rounded_exact_sum():
+    from fractions import Fraction
+    rng = np.random.default_rng(11)
+    for nl in (5, 6, 7):
+        for _ in range(300):
+            acc = rng.integers(-2**31, 2**31, size=nl)
+            ls = rng.integers(-2**27, 2**27, size=nl)
+            got = _umma_value(acc, ls, 2)
+            exact = sum((2 * int(s) - int(a)) << (8 * l) for l, (s, a) in enumerate(zip(ls, acc)))
+            # correctly rounded: the double nearest to the exact integer (ties cannot be hit through the sticky bit)
+            want = float(Fraction(exact))
+            assert got == want, (nl, exact, got, want)
+
+
+def _image_offset(n, w, q):
+    """byte offset of the 4-byte word (accumulator column n, TMEM column group w, slot quad q) inside the image of a k-block"""
+    return (n >> 3) * 1024 + w * 128 + (n & 7) * 16 + 4 * q
+
+
+def test_limb_image_words_of_a_k_block_do_not_overlap():
+    for nl, k in ((7, 31), (5, 31), (7, 4), (6, 9)):
+        ngroups = _npad(k, nl) // 8
+        used = np.zeros(ngroups * 1024, dtype=np.int32)
+        for c in range(k):
+            for l in range(nl):
+                for col in range(32):
+                    o = _image_offset(nl * c + l, col >> 2, col & 3)
+                    used[o:o + 4] += 1
+        assert used.max() == 1
+        assert used.sum() == nl * k * 128                      # 128 genotypes x one byte per digit and column
