@@ -59,20 +59,8 @@ __device__ __forceinline__ double sgb_recombine_umma(int32_t *__restrict__ acc, 
     return v;
 }
 
-// One row's digits of SGB_RCG consecutive columns (the accumulator words [w0, w0 + W), W a multiple of 8) with 128-bit loads,
-// the words zeroed behind them: the access pattern of the row-wide epilogues of wide batches.
+// right-hand-side columns per block of the tiled epilogues (recomb_post{1,2}_wide_kernel)
 #define SGB_RCG 8
-template <int NL>
-__device__ __forceinline__ void sgb_take_row_digits(int32_t *__restrict__ acc_row, int W4, int32_t (&a)[NL * SGB_RCG])
-{
-    int4 *g = reinterpret_cast<int4 *>(acc_row);
-#pragma unroll
-    for (int q = 0; q < NL * SGB_RCG / 4; q++) {
-        int4 v = make_int4(0, 0, 0, 0);
-        if (q < W4) { v = g[q]; g[q] = make_int4(0, 0, 0, 0); }
-        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-    }
-}
 
 // NL = 8: the mma.sync engine; NL = 5..7: the tcgen05 engine with NL digits
 template <int NL>
