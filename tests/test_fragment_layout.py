@@ -266,3 +266,45 @@ def test_limb_image_words_of_a_k_block_do_not_overlap():
                     used[o:o + 4] += 1
         assert used.max() == 1
         assert used.sum() == nl * k * 128                      # 128 genotypes x one byte per digit and column
+
+
+def _split_umma(v, nl):
+    """split_limbs_umma_kernel: q = rint(v 2^(8 nl - 3 - E)) as nl balanced base-256 digits; E = exponent of max |v|"""
+    mb = np.max(np.abs(v))
+    E = int(np.floor(np.log2(mb))) if mb > 0 else 0
+    sh = 8 * nl - 3
+    q = np.rint(np.ldexp(v, sh - E)).astype(np.int64)
+    q0 = q.copy()
+    digits = np.zeros((len(v), nl), dtype=np.int64)
+    for l in range(nl):
+        d = ((q + 128) & 255) - 128
+        q = (q - d) >> 8
+        digits[:, l] = d
+    assert np.all(q == 0), "nl balanced base-256 digits hold |q| <= 2^(8 nl - 2)"
+    return digits, q0, float(np.ldexp(1.0, E - sh))
+
+
+def test_umma_digits_product_and_tolerance_model():
+    """The tcgen05 engine end to end on the CPU: digits -> int32 accumulators of sum (2 - g) digit -> recombination.  7 digits
+    reproduce the exact fixed-point dot product (the integers of the mma.sync engine); 5 digits stay within 2^-38 of the column
+    maximum per input element (sgb_set_product_tolerance)."""
+    rng = np.random.default_rng(5)
+    n = 4096
+    g = rng.integers(0, 3, size=n)
+    for nl in (5, 6, 7):
+        v = rng.normal(size=n) * np.exp(rng.normal(scale=3.0, size=n))      # heavy-tailed column
+        digits, q, mult = _split_umma(v, nl)
+        assert np.all(np.abs(digits) <= 128)
+        assert np.array_equal(sum(digits[:, l] << (8 * l) for l in range(nl)), q)        # digits are q, exactly
+        acc = ((2 - g)[:, None] * digits).sum(axis=0)                                     # what the MMAs accumulate
+        assert np.all(np.abs(acc) < 2**31)
+        limbsum = digits.sum(axis=0)
+        got = _umma_value(acc, limbsum, 2) * mult
+        exact_fixed = int((g * q).sum())                                                  # sum g q, exact integer
+        assert got == float(exact_fixed) * mult or abs(got - exact_fixed * mult) <= abs(exact_fixed * mult) * 2.0**-52
+        # quantisation of the inputs: |v - q mult| <= mult / 2 per element, mult = 2^(E - 8 nl + 3)
+        assert np.max(np.abs(v - q * mult)) <= 0.5 * mult
+        mb = np.max(np.abs(v))
+        assert mult <= mb * 2.0 ** -(8 * nl - 3)            # nl = 5: <= 2^-37 of the column maximum, i.e. error <= 2^-38 per element
+        err = abs(got - float((g * v).sum()))
+        assert err <= n * 2 * 0.5 * mult + abs(got) * 2.0**-52
