@@ -308,3 +308,65 @@ def test_umma_digits_product_and_tolerance_model():
         assert mult <= mb * 2.0 ** -(8 * nl - 3)            # nl = 5: <= 2^-37 of the column maximum, i.e. error <= 2^-38 per element
         err = abs(got - float((g * v).sum()))
         assert err <= n * 2 * 0.5 * mult + abs(got) * 2.0**-52
+
+
+def test_shipped_recombination_header_on_the_host(tmp_path):
+    """recombine.cuh itself (the product's arithmetic, not a restatement) compiled for the host with the CUDA intrinsics
+    shimmed: both engines' recombination against exact integer arithmetic."""
+    import ctypes, os, subprocess
+    from fractions import Fraction
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "recomb_host.cpp"
+    src.write_text(r'''
+#include <stdint.h>
+#include <string.h>
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+#include "recombine.cuh"
+extern "C" double umma5(const int32_t *p, const int32_t *ls, int c0) { return sgb_umma_value<5>(p, ls, c0); }
+extern "C" double umma6(const int32_t *p, const int32_t *ls, int c0) { return sgb_umma_value<6>(p, ls, c0); }
+extern "C" double umma7(const int32_t *p, const int32_t *ls, int c0) { return sgb_umma_value<7>(p, ls, c0); }
+extern "C" double umma7_acc(int32_t *acc, long long r, int c, int npad, const int32_t *ls, int c0) { return sgb_recombine_umma<7>(acc, r, c, npad, ls, c0); }
+extern "C" double imma(int32_t *acc, long long r, int c, int kpad, const int32_t *ls, int c0) { return sgb_recombine_imma(acc, r, c, kpad, ls, c0); }
+''')
+    so = tmp_path / "librecomb_host.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(root, "saige_gpu_b200", "csrc"),
+                           "-o", str(so), str(src)])
+    L = ctypes.CDLL(str(so))
+    for f in (L.umma5, L.umma6, L.umma7, L.umma7_acc, L.imma):
+        f.restype = ctypes.c_double
+    rng = np.random.default_rng(17)
+    I32 = ctypes.POINTER(ctypes.c_int32)
+    for nl, fn in ((5, L.umma5), (6, L.umma6), (7, L.umma7)):
+        for trial in range(400):
+            hi = 2**31 if trial % 2 else 2**12                              # large and small magnitudes (shift = 0 path)
+            acc = rng.integers(-hi, hi, size=nl).astype(np.int32)
+            ls = rng.integers(-2**27, 2**27, size=nl).astype(np.int32)
+            got = fn(acc.ctypes.data_as(I32), ls.ctypes.data_as(I32), 2)
+            exact = sum((2 * int(s) - int(a)) << (8 * l) for l, (s, a) in enumerate(zip(ls, acc)))
+            assert got == float(Fraction(exact)), (nl, exact, got)
+            assert got == _umma_value(acc, ls, 2)
+    # the accumulator-walking wrappers: value of (row, column) and the digits zeroed behind it
+    npad, k = 32, 4
+    acc = rng.integers(-2**30, 2**30, size=(3, npad)).astype(np.int32)
+    ls = rng.integers(-2**20, 2**20, size=7 * k).astype(np.int32)
+    ref = acc.copy()
+    L.umma7_acc.argtypes = [I32, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, I32, ctypes.c_int]
+    got = L.umma7_acc(acc.ctypes.data_as(I32), 1, 2, npad, ls.ctypes.data_as(I32), 2)
+    assert got == _umma_value(ref[1, 14:21], ls[14:21], 2)
+    assert np.all(acc[1, 14:21] == 0) and np.array_equal(np.delete(acc, np.s_[14:21], axis=1), np.delete(ref, np.s_[14:21], axis=1))
+    # mma.sync engine: 8 base-128 digits, layout [row][kpad*8 + c*8 + l]
+    kpad = 2
+    acc8 = rng.integers(-2**30, 2**30, size=(2, kpad * 8)).astype(np.int32)
+    ls8 = rng.integers(-2**20, 2**20, size=kpad * 8).astype(np.int32)
+    ref8 = acc8.copy()
+    L.imma.argtypes = [I32, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, I32, ctypes.c_int]
+    got = L.imma(acc8.ctypes.data_as(I32), 1, 1, kpad, ls8.ctypes.data_as(I32), 2)
+    exact = sum((2 * int(ls8[8 + l]) - int(ref8[1, 8 + l])) << (7 * l) for l in range(8))
+    assert got == float(Fraction(exact))
+    assert np.all(acc8[1, 8:16] == 0) and np.array_equal(acc8[0], ref8[0]) and np.array_equal(acc8[1, :8], ref8[1, :8])
